@@ -1,0 +1,153 @@
+/* libuncrtaints_b200.so -- C ABI of the B200 (sm_100a) UnCRtainTS forward/backward hot path.
+ *
+ * The reference (PatrickTUM/UnCRtainTS @ 5e1f1b5) is pure Python and has no FFI; the boundary this
+ * library sits under is the Python operator surface listed below.  Each entry point names the
+ * reference interface (file:line under /root/reference) whose computation it replaces; the Python shim
+ * in uncrtaints_b200/ binds these with ctypes and re-exposes the reference's classes unchanged
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *  - the caller owns every buffer (inputs, outputs, gradients, workspace); the library allocates nothing,
+ *    retains nothing between calls and never synchronises the device;
+ *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *  - return value: 0 on success, negative UB200_ERR_* otherwise;
+ *  - API tensors are float32, contiguous, in the reference's layouts (NCHW); internal activations in the
+ *    workspace are pixel-major.
+ */
+#ifndef UNCRTAINTS_B200_H
+#define UNCRTAINTS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB200_OK 0
+#define UB200_ERR_ARG -1        /* unsupported shape / configuration */
+#define UB200_ERR_CUDA -2       /* a CUDA launch or runtime call failed */
+#define UB200_ERR_WORKSPACE -3  /* workspace too small */
+
+/* Parameter table.  `params` / `grads` arguments are arrays of device pointers in this order; entries that
+ * do not exist for the configuration (BatchNorm running statistics of a GroupNorm layer, and the
+ * corresponding gradient slots) are NULL.  Names are the reference's state-dict keys. */
+enum {
+    UB200_P_IN_W = 0,      /* in_conv.conv.conv.0.weight [128][C_in]                 (utae.py:478)  */
+    UB200_P_IN_B,          /* in_conv.conv.conv.0.bias   [128]                                      */
+    UB200_P_IN_NORM_W,     /* in_conv.conv.conv.1.weight [128]                       (utae.py:470)  */
+    UB200_P_IN_NORM_B,     /* in_conv.conv.conv.1.bias   [128]                                      */
+    UB200_P_IN_NORM_RM,    /* running_mean (BatchNorm encoder only)                                 */
+    UB200_P_IN_NORM_RV,    /* running_var                                                           */
+    UB200_P_LTAE_AP,       /* folded L-TAE score matrix Ap [16][128]   (see uncrtaints_b200/ltae_fold.py) */
+    UB200_P_LTAE_E,        /* folded additive score term e [B][T][16]                               */
+    UB200_P_OUT_W,         /* out_conv.conv.conv.0.weight [out_dim][128]             (uncrtaints.py:381) */
+    UB200_P_OUT_B,         /* out_conv.conv.conv.0.bias   [out_dim]                                 */
+    UB200_P_BLOCK0         /* first MBConv block (in_block.0); block i starts at UB200_P_BLOCK0 + i*UB200_BLOCK_STRIDE;
+                              blocks 1..n_dec_blocks are out_block.0 .. out_block.(n-1)              */
+};
+/* Per-MBConv-block parameter offsets (uncrtaints.py:100-146; X = in_block.0 / out_block.i). */
+enum {
+    UB200_B_N0_W = 0,      /* X.conv.norm.weight [128]    PreNorm (uncrtaints.py:72-79)              */
+    UB200_B_N0_B,          /* X.conv.norm.bias                                                       */
+    UB200_B_N0_RM,         /* X.conv.norm.running_mean (BatchNorm only, updated in training)         */
+    UB200_B_N0_RV,
+    UB200_B_W1,            /* X.conv.fn.0.weight [256][128]   1x1 expand (uncrtaints.py:126)         */
+    UB200_B_N1_W,          /* X.conv.fn.1.* [256]                                                    */
+    UB200_B_N1_B,
+    UB200_B_N1_RM,
+    UB200_B_N1_RV,
+    UB200_B_WDW,           /* X.conv.fn.3.weight [256][1][3][3] depthwise (uncrtaints.py:130-131)    */
+    UB200_B_N2_W,          /* X.conv.fn.4.* [256]                                                    */
+    UB200_B_N2_B,
+    UB200_B_N2_RM,
+    UB200_B_N2_RV,
+    UB200_B_F1,            /* X.conv.fn.6.fc.0.weight [32][256]  SE (uncrtaints.py:82-97)            */
+    UB200_B_F2,            /* X.conv.fn.6.fc.2.weight [256][32]                                      */
+    UB200_B_W2,            /* X.conv.fn.7.weight [128][256]   1x1 project (uncrtaints.py:136)        */
+    UB200_B_N3_W,          /* X.conv.fn.8.* [128]                                                    */
+    UB200_B_N3_B,
+    UB200_B_N3_RM,
+    UB200_B_N3_RV,
+    UB200_BLOCK_STRIDE
+};
+
+typedef struct ub200_desc {
+    int B, T, C_in, H, W;       /* input [B][T][C_in][H][W]; H, W multiples of 32; T <= 8; C_in <= 16 */
+    int n_dec_blocks;           /* len(decoder_widths), default 5 (uncrtaints.py:236); one encoder block */
+    int out_dim;                /* 13 + covar_dim: 26 (diag/uni), 14 (iso), 13 (none) (uncrtaints.py:357-368) */
+    int enc_groups;             /* encoder_norm: 4 = GroupNorm(4) (default), 0 = BatchNorm2d */
+    int dec_groups;             /* decoder_norm: 0 = BatchNorm2d (default), 4 = GroupNorm(4) */
+    int training;               /* nn.Module.training: BatchNorm batch statistics + running update, dropout on */
+    int need_grad;              /* keep what ub200_backward needs */
+    int mean_sigmoid;           /* out_nonlin_mean (uncrtaints.py:384) */
+    int gemm_backend;           /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 tensor-core GEMMs (bf16x3 split) */
+    float scale_by;             /* uncrtaints.py:250,384 */
+    float var_eps;              /* 1e-9 if scale_by == 1 else 1e-3 (uncrtaints.py:374) */
+    float pad_value;            /* uncrtaints.py:245,392 */
+    float norm_eps;             /* 1e-5 */
+    float bn_momentum;          /* 0.1 */
+    float dropout_p;            /* 0.1 in training (uncrtaints.py:154), forced to 0 when !training */
+    unsigned long long seed;    /* Philox seed / offset for the attention dropout (ignored when keep_mask != NULL) */
+    unsigned long long offset;
+} ub200_desc;
+
+int ub200_version(void);
+
+/* Number of pointer slots in a params / grads table for this configuration. */
+int ub200_num_param_slots(const ub200_desc* d);
+
+/* Bytes of workspace ub200_forward / ub200_backward need.  The same workspace must be passed, untouched,
+ * from a forward call to its backward call (it holds the saved activations). */
+size_t ub200_workspace_bytes(const ub200_desc* d);
+
+/* Locate a named intermediate inside the workspace (tests / debugging): "x0", "pooled", "pool_idx", "attn",
+ * "agg", "notpad", "blk<i>.h1|h2|y|out".  Returns 0 and fills offset/bytes, or UB200_ERR_ARG. */
+int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, size_t* bytes);
+
+/* UNCRTAINTS.forward (model/src/backbones/uncrtaints.py:391-446).
+ *   input  [B][T][C_in][H][W], output [B][1][out_dim][H][W];
+ *   keep_mask: optional explicit Bernoulli keep mask of the attention dropout, uint8 [16][B][T][H][W]
+ *   (uncrtaints.py:202); NULL -> in-kernel Philox(seed, offset).
+ * BatchNorm running_mean / running_var in `params` are updated in place when d->training. */
+int ub200_forward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                  float* output, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of UNCRTAINTS.forward (autograd of the reference, triggered at base_model.py:77).
+ *   grad_output [B][1][out_dim][H][W]; output = the tensor ub200_forward produced;
+ *   grads: table like params; every non-NULL slot is ACCUMULATED into (zero it first for plain gradients).
+ * The input has no gradient (in_conv is the first layer, the reference never asks for it). */
+int ub200_backward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                   const float* output, const float* grad_output, void* const* grads, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* MultiGaussianNLLLoss.forward -> multi_gaussian_nll_loss (model/src/losses.py:353,149-218), reduction='mean'.
+ *   pred/target/var: base pointers of [B][1][13 | var_ch][H][W] tensors whose batch stride (in elements) is
+ *   *_sb and whose [c][h][w] block is contiguous (slices of the network output qualify); var_ch = 13 (diag)
+ *   or 1 (iso).  loss: device scalar.  dpred [B][13][P] / dvar [B][var_ch][P]: d loss / d input (NULL to skip).
+ *   neg_flag: device int, set to 1 if any var < 0 (the reference raises ValueError, losses.py:199-200).
+ *   scratch: 16 bytes of device memory. */
+int ub200_mgnll_forward(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
+                        long long var_sb, int var_ch, int B, int P, float eps, float* loss, float* dpred, float* dvar,
+                        int* neg_flag, void* scratch, void* stream);
+
+/* out[i] = in[i] * grad_loss[0]  (chain rule with the upstream gradient of the scalar loss). */
+int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, size_t n, void* stream);
+
+/* Second return value of the loss: diag_embed(max(var, eps)) -> [B][1][13][13][H][W] (losses.py:145,211). */
+int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int P, float eps, float* cov, void* stream);
+
+/* One MBConv block on pixel-major tensors (tests): x, out, dout, dx are [N][H*W][128].
+ * block_params / block_grads: UB200_BLOCK_STRIDE pointers.  groups: 4 = GroupNorm(4), 0 = BatchNorm2d. */
+size_t ub200_mbconv_workspace_bytes(int N, int H, int W);
+int ub200_mbconv_forward(const float* x, const void* const* block_params, int N, int H, int W, int groups, int training,
+                         float eps, float momentum, int gemm_backend, float* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int ub200_mbconv_backward(const float* x, const void* const* block_params, const float* dout, void* const* block_grads,
+                          int N, int H, int W, int groups, int training, int gemm_backend, float* dx, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNCRTAINTS_B200_H */

@@ -1,0 +1,124 @@
+"""CPU tests of the oracle: against the committed golden vectors (generated from the unmodified reference by
+tests/golden/make_golden.py) and, where /root/reference exists, against the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz, rel_l2, is_zero_grad_param
+from oracle import uncrtaints_oracle as O, ref_import
+
+
+def _sd64(w):
+    return {k: (v.double() if v.is_floating_point() else v) for k, v in w.items()}
+
+
+def test_oracle_matches_golden_train_pad(golden_weights):
+    c = load_npz("case_diag_train_pad.npz")
+    x, y, d = (torch.from_numpy(c[k]).double() for k in ("x", "y", "dates"))
+    B, T, _, H, W = x.shape
+    keep = torch.from_numpy(np.unpackbits(c["keep"])[:16 * B * T * H * W].reshape(16, B, T, H, W)).bool()
+    cfg = O.OracleConfig()
+    out, loss, grads, newbuf = O.step(_sd64(golden_weights), x, y, d, cfg, True, keep)
+    assert rel_l2(out, torch.from_numpy(c["out"])) < 1e-6
+    assert abs(loss.item() - float(c["loss"])) / abs(float(c["loss"])) < 1e-9
+    for k, g in grads.items():
+        ref = torch.from_numpy(c["grad." + k])
+        if is_zero_grad_param(k):
+            assert g.norm() < 1e-6 * max(1.0, float(ref.norm()) * 1e6)
+        else:
+            assert rel_l2(g, ref) < 1e-5, k
+    for k, v in newbuf.items():
+        assert torch.allclose(v.double(), torch.from_numpy(c["buf." + k]).double(), rtol=1e-5, atol=1e-6), k
+    # bit-exact items
+    taps = {}
+    O.forward(_sd64(golden_weights), x, d, cfg, True, keep, None, taps)
+    assert torch.equal(taps["pad_mask"], torch.from_numpy(c["pad_mask"]))
+    assert torch.equal(taps["pool_idx"].to(torch.int16), torch.from_numpy(c["pool_idx"]))
+
+
+def test_oracle_matches_golden_iso_eval(golden_weights):
+    c = load_npz("case_iso_eval.npz")
+    x, y, d = (torch.from_numpy(c[k]).double() for k in ("x", "y", "dates"))
+    cfg = O.OracleConfig(covmode="iso")
+    sd = _sd64(golden_weights)
+    sd["out_conv.conv.conv.0.weight"] = sd["out_conv.conv.conv.0.weight"][:14]
+    sd["out_conv.conv.conv.0.bias"] = sd["out_conv.conv.conv.0.bias"][:14]
+    out = O.forward(sd, x, d, cfg, training=False)
+    loss = O.mgnll(out[:, :, :13], y, out[:, :, 13:14], "iso")
+    assert rel_l2(out, torch.from_numpy(c["out"])) < 1e-6
+    assert abs(loss.item() - float(c["loss"])) / abs(float(c["loss"])) < 1e-9
+
+
+@pytest.mark.parametrize("mode", ["diag", "iso"])
+def test_oracle_mgnll_matches_golden(mode):
+    c = load_npz("case_mgnll.npz")
+    pred = torch.from_numpy(c[f"{mode}.pred"]).double().requires_grad_(True)
+    var = torch.from_numpy(c[f"{mode}.var"]).double().requires_grad_(True)
+    targ = torch.from_numpy(c[f"{mode}.target"]).double()
+    loss = O.mgnll(pred, targ, var, mode)
+    loss.backward()
+    assert abs(loss.item() - float(c[f"{mode}.loss"])) / abs(float(c[f"{mode}.loss"])) < 1e-6
+    assert rel_l2(pred.grad, torch.from_numpy(c[f"{mode}.dpred"])) < 1e-5
+    assert rel_l2(var.grad, torch.from_numpy(c[f"{mode}.dvar"])) < 1e-5
+    cov = O.covariance(var.detach(), mode)
+    assert cov.shape == (pred.shape[0], 1, 13, 13, pred.shape[3], pred.shape[4])
+    assert abs(cov.sum().item() - float(c[f"{mode}.cov_diag_sum"])) / float(c[f"{mode}.cov_diag_sum"]) < 1e-5
+
+
+def test_mgnll_error_semantics():
+    p = torch.rand(2, 1, 13, 4, 4)
+    with pytest.raises(ValueError, match="var has negative entry/entries"):
+        O.mgnll(p, p, -torch.ones_like(p))
+    with pytest.raises(ValueError, match="is not valid"):
+        O.mgnll(p, p, torch.ones_like(p), reduction="bogus")
+
+
+def test_maxpool_first_max_tie_rule():
+    x = torch.zeros(1, 1, 64, 64)
+    val, idx = O.adaptive_max_pool(x)
+    ref_v, ref_i = torch.nn.functional.adaptive_max_pool2d(x, (32, 32), return_indices=True)
+    assert torch.equal(idx, ref_i) and torch.equal(val, ref_v)
+    x = torch.rand(2, 3, 96, 64)
+    val, idx = O.adaptive_max_pool(x)
+    ref_v, ref_i = torch.nn.functional.adaptive_max_pool2d(x, (32, 32), return_indices=True)
+    assert torch.equal(idx, ref_i) and torch.equal(val, ref_v)
+
+
+def test_bilinear_matches_torch():
+    a = torch.rand(3, 2, 32, 32, dtype=torch.float64)
+    up = O.bilinear_upsample(a, 256, 64)
+    ref = torch.nn.functional.interpolate(a, size=(256, 64), mode="bilinear", align_corners=False)
+    assert torch.allclose(up, ref, atol=1e-12)
+
+
+def test_depthwise_reflect_matches_torch():
+    x = torch.rand(2, 8, 9, 7, dtype=torch.float64)
+    w = torch.rand(8, 1, 3, 3, dtype=torch.float64)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1), mode="reflect"), w, groups=8)
+    assert torch.allclose(O.depthwise3x3_reflect(x, w), ref, atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_matches_live_reference_fp64():
+    U, Lm, winit = ref_import.load()
+    torch.manual_seed(3)
+    m = U.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", covmode="diag",
+                     scale_by=10.0)
+    m.apply(winit)
+    m = m.double().train()
+    B, T, H, W = 1, 2, 64, 64
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=11, dtype=torch.float64)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=12)
+    m.temporal_aggregator.attn_dropout = ref_import.InjectedDropout(keep)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    out = m(x, batch_positions=d)
+    loss, var = Lm.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None)(
+        out[:, :, :13], y, out[:, :, 13:26])
+    loss.backward()
+    o_out, o_loss, o_g, _ = O.step(sd, x, y, d, O.OracleConfig(), True, keep)
+    assert rel_l2(o_out, out) < 1e-12
+    assert abs(o_loss.item() - loss.item()) / abs(loss.item()) < 1e-9
+    for k, p in m.named_parameters():
+        if not is_zero_grad_param(k):
+            assert rel_l2(o_g[k], p.grad) < 1e-9, k
+    assert torch.equal(O.covariance(out[:, :, 13:26].detach(), "diag"), var)

@@ -1,0 +1,16 @@
+"""uncrtaints_b200 -- B200 (sm_100a) implementation of the UnCRtainTS forward/backward hot path.
+
+Public surface (mirrors the reference's):
+  UNCRTAINTS(...)                      <- model/src/backbones/uncrtaints.py:230
+  MultiGaussianNLLLoss, get_loss, calc_loss   <- model/src/losses.py:14,35,288
+  install()                            patch the above into the reference's ``src`` package
+  FlatGradAllReduce                    one-collective data-parallel gradient reduction (new; reference is single-GPU)
+The compute lives in libuncrtaints_b200.so (C ABI: include/uncrtaints_b200.h); there is no CPU fallback.
+"""
+from .backbone import UNCRTAINTS, set_default_gemm_backend  # noqa: F401
+from .losses import MultiGaussianNLLLoss, get_loss, calc_loss, multi_gaussian_nll_loss, covariance_diag  # noqa: F401
+from .install import install  # noqa: F401
+from .parallel import FlatGradAllReduce, shard_batch  # noqa: F401
+
+__all__ = ["UNCRTAINTS", "MultiGaussianNLLLoss", "get_loss", "calc_loss", "multi_gaussian_nll_loss", "covariance_diag",
+           "install", "FlatGradAllReduce", "shard_batch", "set_default_gemm_backend"]

@@ -1,0 +1,121 @@
+// Common device helpers for the UnCRtainTS sm_100a hot path.
+//
+// Data layout in HBM: every internal activation is pixel-major ("NHWC"):
+//   act[n][p][c], n = frame (b*T+t for the encoder, b for the decoder), p = y*W+x, c = channel,
+// so the 1x1 convolutions are row-major GEMMs with the reduction dimension contiguous and every
+// normalisation statistic is a column sum.  API tensors stay NCHW (converted inside in_conv /
+// out_conv, which touch only 15 / 26 channels).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define UB_WIDTH 128      // encoder/decoder width   (uncrtaints.py:235-236 defaults)
+#define UB_HID 256        // MBConv hidden = width * expansion(2)  (uncrtaints.py:105,317)
+#define UB_SE 32          // SE bottleneck int(128*0.25) (uncrtaints.py:83-87,134)
+#define UB_HEADS 16       // n_head (uncrtaints.py:242)
+#define UB_LOW 32         // att_down (uncrtaints.py:403)
+#define UB_TMAX 8         // max sequence length handled by the L-TAE kernels
+#define UB_S2 13          // S2_BANDS (uncrtaints.py:13)
+
+#define UB_OK 0
+#define UB_ERR_ARG -1
+#define UB_ERR_CUDA -2
+#define UB_ERR_WORKSPACE -3
+
+#define UB_CHECK_LAUNCH()                                  \
+    do {                                                   \
+        cudaError_t e__ = cudaGetLastError();              \
+        if (e__ != cudaSuccess) return UB_ERR_CUDA;        \
+    } while (0)
+
+namespace ub {
+
+// ---- per-(frame, channel) coefficient records --------------------------------------------
+// forward:  v_norm = v * scale + shift          (GroupNorm and BatchNorm alike)
+// saved:    mean, rstd                          (for x_hat = (v-mean)*rstd in backward)
+// backward: dv = a*dy + b*v + c                 (normalisation backward, see norm.cu)
+struct __align__(8) Coef { float scale, shift; };
+struct __align__(8) MeanRstd { float mean, rstd; };
+struct __align__(16) BCoef { float a, b, c, pad; };
+
+__device__ __forceinline__ Coef ldg(const Coef* p) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return Coef{v.x, v.y};
+}
+__device__ __forceinline__ MeanRstd ldg(const MeanRstd* p) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return MeanRstd{v.x, v.y};
+}
+
+__device__ __forceinline__ float gelu_f(float x) {
+    // exact-erf GELU (nn.GELU default; uncrtaints.py:88,128,133)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming (read-once / write-once) variants: keep L1 for the reused weights and coefficients
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- Philox4x32-10 counter RNG (dropout on the upsampled attention, uncrtaints.py:154,202) ----
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+// Bernoulli keep decision for element `idx` of the [16*B, T, H, W] upsampled attention tensor.
+// One Philox call covers 4 consecutive elements; returns 1.0f (keep) or 0.0f (drop).
+__device__ __forceinline__ float dropout_keep(uint64_t seed, uint64_t offset, uint64_t idx, float p) {
+    const uint64_t blk = (idx >> 2) + offset;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t lane = (uint32_t)(idx & 3);
+    const uint32_t bits = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+    const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+    return u >= p ? 1.0f : 0.0f;
+}
+
+// Bilinear taps of nn.Upsample(mode='bilinear', align_corners=False) (uncrtaints.py:198-200):
+// src = max((o+0.5)/s - 0.5, 0); i0 = floor(src); i1 = min(i0+1, in-1); lam = src - i0.
+__device__ __forceinline__ void bilinear_tap(int o, float inv_scale, int in_size, int& i0, int& i1, float& lam) {
+    float src = ((float)o + 0.5f) * inv_scale - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    i1 = i0 + 1 < in_size ? i0 + 1 : in_size - 1;
+    lam = src - (float)i0;
+}
+
+}  // namespace ub

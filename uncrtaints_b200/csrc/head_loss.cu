@@ -1,0 +1,272 @@
+// Output head and loss of UnCRtainTS.
+//
+//   out_conv + head : Conv2d(128 -> 13+covdim, k=1, bias) (model/src/backbones/uncrtaints.py:381,432), then
+//                     mean = scale_by * sigmoid(.) (uncrtaints.py:384-385,441), var = softplus(beta=1, thr=20)(.) + eps
+//                     (uncrtaints.py:223-228,444), concatenated as [B,1,13+covdim,H,W] NCHW (uncrtaints.py:436-446).
+//   MGNLL           : multi_gaussian_nll_loss / multi_diag_gaussian_nll (model/src/losses.py:131-145,149-218), closed form:
+//                     loss = 6.5*log(2*pi_f32) + 1/2 mean_hw[ sum_{b,c} log v ] + 1/2 mean_{b,hw}[ max(nan_to_num(sum_c e^2/v), 1e-9) ]
+//                     (the log-determinant is summed over the batch, losses.py:138), v = max(var, eps) with identity gradient.
+//   covariance      : diag_embed(v) -> [B,1,13,13,H,W] (losses.py:145,211).
+//
+// Both are HBM-bound byte shufflers over 26-channel planes: thread-per-pixel with plane-coalesced accesses.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ub {
+
+constexpr int HD_MAXO = 26;
+constexpr int HD_PX = 128;
+
+// ------------------------------------------------------------------------------------------
+// out_conv + head forward.  CTA = 64 pixels x 4 output groups (group g owns outputs g, g+4, g+8, ...).
+// ------------------------------------------------------------------------------------------
+constexpr int HF_PX = 64, HF_G = 4, HF_PER = (HD_MAXO + HF_G - 1) / HF_G;
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ dec /* [B][P][128] */, const float* __restrict__ w /* [O][128] */,
+                                                        const float* __restrict__ bias, float* __restrict__ out /* [B][O][P] */,
+                                                        int O, int P, float scale_by, int mean_sigmoid, float var_eps) {
+    constexpr int C = UB_WIDTH, PITCH = C + 1;
+    __shared__ float as[HF_PX * PITCH];
+    __shared__ float ws[HD_MAXO * C];
+    __shared__ float bs[HD_MAXO];
+    const int b = blockIdx.y, p0 = blockIdx.x * HF_PX, tid = threadIdx.x;
+    for (int i = tid; i < O * C; i += 256) ws[i] = w[i];
+    if (tid < O) bs[tid] = bias[tid];
+    for (int i = tid; i < HF_PX * (C / 4); i += 256) {
+        const int px = i / (C / 4), k4 = i % (C / 4);
+        const float4 v = ld4_stream(dec + ((size_t)b * P + p0 + px) * C + k4 * 4);
+        float* d = as + px * PITCH + k4 * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    const int px = tid % HF_PX, grp = tid / HF_PX;
+    float acc[HF_PER];
+#pragma unroll
+    for (int j = 0; j < HF_PER; ++j) acc[j] = (grp + HF_G * j < O) ? bs[grp + HF_G * j] : 0.f;
+    for (int k = 0; k < C; ++k) {
+        const float a = as[px * PITCH + k];
+#pragma unroll
+        for (int j = 0; j < HF_PER; ++j)
+            if (grp + HF_G * j < O) acc[j] = fmaf(a, ws[(grp + HF_G * j) * C + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < HF_PER; ++j) {
+        const int o = grp + HF_G * j;
+        if (o < O) {
+            float v = acc[j];
+            if (o < UB_S2) { if (mean_sigmoid) v = scale_by * sigmoid_f(v); }
+            else v = (v > 20.f ? v : log1pf(expf(v))) + var_eps;
+            out[((size_t)b * O + o) * P + p0 + px] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// head backward.  do = dOut * f'(out) from the saved output; dDec = do * W; dW += do^T dec; db += sum do.
+// Persistent CTAs: register accumulators for dW/db, flushed once.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dout /* [B][O][P] */, const float* __restrict__ out,
+                                                        const float* __restrict__ dec, const float* __restrict__ w,
+                                                        float* __restrict__ ddec, float* dw, float* db, int O, int P,
+                                                        long long total_tiles, float scale_by, int mean_sigmoid, float var_eps) {
+    constexpr int C = UB_WIDTH;
+    __shared__ __align__(16) float ws[HD_MAXO * C];
+    __shared__ float dos[HD_MAXO * HD_PX];      // [o][px]
+    __shared__ __align__(16) float red[8 * C];
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    for (int i = tid; i < O * C; i += 256) ws[i] = w[i];
+    float4 gw[HD_MAXO];
+    float gb = 0.f;   // thread tid < O accumulates db[tid]
+#pragma unroll
+    for (int o = 0; o < HD_MAXO; ++o) gw[o] = make_float4(0, 0, 0, 0);
+    const int tiles_per_img = P / HD_PX;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = (int)(t / tiles_per_img), p0 = (int)(t % tiles_per_img) * HD_PX;
+        __syncthreads();
+        for (int i = tid; i < O * HD_PX; i += 256) {
+            const int o = i / HD_PX, px = i % HD_PX;
+            const size_t g = ((size_t)b * O + o) * P + p0 + px;
+            const float d = dout[g], v = out[g];
+            float der;
+            if (o < UB_S2) {
+                if (mean_sigmoid) { const float sg = v / scale_by; der = scale_by * sg * (1.f - sg); }
+                else der = 1.f;
+            } else {
+                der = 1.f - expf(-(v - var_eps));   // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x)); == 1 beyond the threshold in fp32
+            }
+            dos[i] = d * der;
+        }
+        __syncthreads();
+        if (tid < O) {
+            float s = 0.f;
+            for (int px = 0; px < HD_PX; ++px) s += dos[tid * HD_PX + px];
+            gb += s;
+        }
+        for (int px = warp; px < HD_PX; px += 8) {
+            const size_t row = (size_t)b * P + p0 + px;
+            const float4 a = ld4_stream(dec + row * C + lane * 4);
+            float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int o = 0; o < HD_MAXO; ++o) {
+                if (o < O) {
+                    const float d = dos[o * HD_PX + px];
+                    const float4 wv = ld4(ws + o * C + lane * 4);
+                    acc.x = fmaf(d, wv.x, acc.x); acc.y = fmaf(d, wv.y, acc.y);
+                    acc.z = fmaf(d, wv.z, acc.z); acc.w = fmaf(d, wv.w, acc.w);
+                    gw[o].x = fmaf(d, a.x, gw[o].x); gw[o].y = fmaf(d, a.y, gw[o].y);
+                    gw[o].z = fmaf(d, a.z, gw[o].z); gw[o].w = fmaf(d, a.w, gw[o].w);
+                }
+            }
+            st4(ddec + row * C + lane * 4, acc);
+        }
+    }
+    if (tid < O) atomicAdd(&db[tid], gb);
+#pragma unroll 1
+    for (int o = 0; o < O; ++o) {
+        float4 v = gw[0];
+#pragma unroll
+        for (int j = 1; j < HD_MAXO; ++j) if (j == o) v = gw[j];
+        __syncthreads();
+        st4(red + warp * C + lane * 4, v);
+        __syncthreads();
+        if (tid < C) {
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += red[r * C + tid];
+            atomicAdd(&dw[o * C + tid], t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// MGNLL forward (+ gradients).  Thread per pixel, loops over batch and channel; planes are coalesced.
+// pred/var/target are addressed as base + b*stride_b + c*P + p (slices of the [B,1,26,H,W] network output).
+// acc[0] += sum_p sum_{b,c} log v ; acc[1] += sum_p sum_b maha_b ; flag |= any(var < 0)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mgnll_fwd_kernel(const float* __restrict__ pred, long long pred_sb,
+                                                         const float* __restrict__ target, long long targ_sb,
+                                                         const float* __restrict__ var, long long var_sb, int var_ch,
+                                                         float* __restrict__ dpred /* [B][13][P] or null */,
+                                                         float* __restrict__ dvar /* [B][var_ch][P] or null */, double* acc,
+                                                         int* neg_flag, int B, int P, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    float logdet = 0.f, maha_sum = 0.f;
+    bool neg = false;
+    if (p < P) {
+        const float inv_p = 1.0f / (float)P, inv_bp = 1.0f / ((float)B * (float)P);
+        for (int b = 0; b < B; ++b) {
+            float e[UB_S2], iv[UB_S2];
+            float maha = 0.f;
+#pragma unroll
+            for (int c = 0; c < UB_S2; ++c) {
+                const float vr = var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p];
+                neg |= (vr < 0.f);
+                const float v = fmaxf(vr, eps);
+                e[c] = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
+                iv[c] = 1.0f / v;
+                logdet += logf(v);
+                maha = fmaf(e[c] * e[c], iv[c], maha);
+            }
+            const bool isn = maha != maha;
+            float m = isn ? 0.f : maha;                       // nan_to_num
+            m = fminf(m, 3.4028234663852886e38f);             // +inf -> float max
+            const bool live = !isn && m >= 1e-9f && maha <= 3.4028234663852886e38f;   // clamp(min=1e-9) / inf: no gradient
+            maha_sum += fmaxf(m, 1e-9f);
+            if (dpred) {
+                float dv_iso = 0.f;
+#pragma unroll
+                for (int c = 0; c < UB_S2; ++c) {
+                    const float gm = live ? e[c] * iv[c] * inv_bp : 0.f;
+                    dpred[((size_t)b * UB_S2 + c) * P + p] = gm;
+                    const float gv = 0.5f * iv[c] * inv_p - (live ? 0.5f * e[c] * e[c] * iv[c] * iv[c] * inv_bp : 0.f);
+                    if (var_ch == 1) dv_iso += gv;
+                    else dvar[((size_t)b * UB_S2 + c) * P + p] = gv;
+                }
+                if (var_ch == 1) dvar[(size_t)b * P + p] = dv_iso;
+            }
+        }
+    }
+    double l = warp_sum_d((double)logdet), m = warp_sum_d((double)maha_sum);
+    __shared__ double sl[8], sm[8];
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    if (lane == 0) { sl[warp] = l; sm[warp] = m; }
+    if (neg) *neg_flag = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int i = 0; i < 8; ++i) { a += sl[i]; c += sm[i]; }
+        atomicAdd(&acc[0], a);
+        atomicAdd(&acc[1], c);
+    }
+}
+
+__global__ void mgnll_finalize_kernel(const double* acc, float* loss, int B, int P) {
+    // 13/2 * log(2*float32(pi)) evaluated in float32 (losses.py:143)
+    const float cst = 6.5f * logf(2.0f * 3.14159274101257324f);
+    const double v = (double)cst + 0.5 * acc[0] / (double)P + 0.5 * acc[1] / ((double)B * (double)P);
+    *loss = (float)v;
+}
+
+// out[i] = in[i] * g[0]   (chain rule with the upstream scalar gradient)
+__global__ void scale_by_scalar_kernel(const float* __restrict__ in, const float* __restrict__ g, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] * g[0];
+}
+
+// covariance[b][0][i][j][p] = (i == j) ? max(var[b][i or 0][p], eps) : 0
+__global__ void __launch_bounds__(256) covariance_kernel(const float* __restrict__ var, long long var_sb, int var_ch,
+                                                          float* __restrict__ cov, int P, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (p >= P) return;
+    float v[UB_S2];
+#pragma unroll
+    for (int c = 0; c < UB_S2; ++c) v[c] = fmaxf(var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p], eps);
+    float* dst = cov + (size_t)b * UB_S2 * UB_S2 * P + p;
+#pragma unroll
+    for (int i = 0; i < UB_S2; ++i)
+#pragma unroll
+        for (int j = 0; j < UB_S2; ++j) dst[(size_t)(i * UB_S2 + j) * P] = (i == j) ? v[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_head_fwd(const float* dec, const float* w, const float* bias, float* out, int B, int O, int P, float scale_by,
+                    int mean_sigmoid, float var_eps, cudaStream_t st) {
+    if (O > HD_MAXO || O < UB_S2 || P % HF_PX) return UB_ERR_ARG;
+    head_fwd_kernel<<<dim3(P / HF_PX, B), 256, 0, st>>>(dec, w, bias, out, O, P, scale_by, mean_sigmoid, var_eps);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_head_bwd(const float* dout, const float* out, const float* dec, const float* w, float* ddec, float* dw, float* db,
+                    int B, int O, int P, float scale_by, int mean_sigmoid, float var_eps, int num_sms, cudaStream_t st) {
+    if (O > HD_MAXO || O < UB_S2 || P % HD_PX) return UB_ERR_ARG;
+    const long long tiles = (long long)B * (P / HD_PX);
+    const int blocks = (int)(tiles < 2LL * num_sms ? tiles : 2LL * num_sms);
+    head_bwd_kernel<<<blocks, 256, 0, st>>>(dout, out, dec, w, ddec, dw, db, O, P, tiles, scale_by, mean_sigmoid, var_eps);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_mgnll(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
+                 long long var_sb, int var_ch, float* dpred, float* dvar, double* acc, int* neg_flag, float* loss, int B,
+                 int P, float eps, cudaStream_t st) {
+    if (cudaMemsetAsync(acc, 0, 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
+    if (cudaMemsetAsync(neg_flag, 0, sizeof(int), st) != cudaSuccess) return UB_ERR_CUDA;
+    mgnll_fwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, dpred, dvar, acc,
+                                                      neg_flag, B, P, eps);
+    UB_CHECK_LAUNCH();
+    mgnll_finalize_kernel<<<1, 1, 0, st>>>(acc, loss, B, P);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_scale_by_scalar(const float* in, const float* g, float* out, size_t n, cudaStream_t st) {
+    scale_by_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, g, out, n);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_covariance(const float* var, long long var_sb, int var_ch, float* cov, int B, int P, float eps, cudaStream_t st) {
+    covariance_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(var, var_sb, var_ch, cov, P, eps);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+}  // namespace ub

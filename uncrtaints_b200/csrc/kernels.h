@@ -1,0 +1,90 @@
+// Internal launcher declarations shared by the translation units of libuncrtaints_b200.so.
+// Every launcher enqueues on the given stream only, allocates nothing, never synchronises, and
+// returns UB_OK or a negative UB_ERR_* code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ub {
+
+struct Coef;
+struct MeanRstd;
+struct BCoef;
+
+// norm.cu
+int launch_norm_finalize(const double* stats, const float* gamma, const float* beta, float* rm, float* rv, Coef* coef,
+                         MeanRstd* mr, int N, int C, int groups, double count, float eps, float momentum, int training,
+                         cudaStream_t st);
+int launch_norm_finalize_bwd(const double* bstats, const float* gamma, const MeanRstd* mr, BCoef* bcoef, float* dgamma,
+                             float* dbeta, int N, int C, int groups, double count, int training, cudaStream_t st);
+int launch_residual_fwd(const float* x, const float* y, const Coef* coef3, float* out, double* out_stats, int N, int P,
+                        cudaStream_t st);
+int launch_se_pool(const float* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
+                   int P, cudaStream_t st);
+int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
+int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
+                        cudaStream_t st);
+
+// gemm_simt.cu
+int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);
+int simt_gemm1_fwd(const float* x, const Coef* coef0, const float* w1t, float* h1, double* stats1, int N, int P, cudaStream_t st);
+int simt_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const float* w2t, float* y, double* stats3, int N,
+                   int P, cudaStream_t st);
+int simt_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const float* w2, float* du, const float* h2,
+                   const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, cudaStream_t st);
+int simt_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const float* w1, float* dn0, const float* x,
+                   const MeanRstd* mr0, double* bstats0, int N, int P, cudaStream_t st);
+int simt_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
+                float* partial, int max_parts, float* dw2, int N, int P, cudaStream_t st);
+int simt_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
+                int max_parts, float* dw1, int N, int P, cudaStream_t st);
+
+// dwconv.cu
+int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
+                      cudaStream_t st);
+int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
+                      const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
+                      float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
+
+// se.cu
+int launch_se_fwd(const double* pool_stats, const float* f1, const float* f2, float* save, float* gate, int N, int P,
+                  cudaStream_t st);
+int launch_se_bwd(const double* sums3, const double* gp_stats, const float* f1, const float* f2, const float* save,
+                  float* df1, float* df2, float* dmp, double* bstats2, int N, int P, cudaStream_t st);
+
+// inconv.cu
+int launch_inconv_stats(const float* x, const float* w, const float* b, double* stats, int* notpad, float pad_value, int N,
+                        int Cin, int P, cudaStream_t st);
+int launch_inconv_apply(const float* x, const float* w, const float* b, const Coef* coef, float* x0, double* stats_x0, int N,
+                        int Cin, int P, cudaStream_t st);
+int launch_inconv_bwd_stats(const float* x, const float* w, const float* b, const Coef* coef, const MeanRstd* mr,
+                            const float* dx0, double* bstats, int N, int Cin, int P, cudaStream_t st);
+int launch_inconv_bwd_wgrad(const float* x, const float* w, const float* b, const Coef* coef, const MeanRstd* mr,
+                            const BCoef* bc, const float* dx0, float* dw, float* db, int N, int Cin, int P, cudaStream_t st);
+
+// temporal.cu
+int launch_maxpool_fwd(const float* x, float* pooled, int* idx, int N, int H, int W, cudaStream_t st);
+int launch_maxpool_bwd(const float* dpooled, const int* idx, float* denc, int N, int HW, cudaStream_t st);
+int launch_ltae_fwd(const float* pooled, const float* Ap, const float* e, const int* notpad, float* attn, int B, int T,
+                    float eps, cudaStream_t st);
+int launch_ltae_bwd(const float* pooled, const float* Ap, const float* attn, const float* dattn, float* dpooled, float* dAp,
+                    float* de, int B, int T, float eps, cudaStream_t st);
+int launch_aggregate_fwd(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
+                         unsigned long long offset, float drop_p, const float* x, float* out, double* out_stats, int B,
+                         int T, int H, int W, cudaStream_t st);
+int launch_aggregate_bwd(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
+                         unsigned long long offset, float drop_p, const float* x, const float* dagg, float* denc,
+                         float* dwup, float* dattn, int B, int T, int H, int W, cudaStream_t st);
+
+// head_loss.cu
+int launch_head_fwd(const float* dec, const float* w, const float* bias, float* out, int B, int O, int P, float scale_by,
+                    int mean_sigmoid, float var_eps, cudaStream_t st);
+int launch_head_bwd(const float* dout, const float* out, const float* dec, const float* w, float* ddec, float* dw, float* db,
+                    int B, int O, int P, float scale_by, int mean_sigmoid, float var_eps, int num_sms, cudaStream_t st);
+int launch_mgnll(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
+                 long long var_sb, int var_ch, float* dpred, float* dvar, double* acc, int* neg_flag, float* loss, int B,
+                 int P, float eps, cudaStream_t st);
+int launch_scale_by_scalar(const float* in, const float* g, float* out, size_t n, cudaStream_t st);
+int launch_covariance(const float* var, long long var_sb, int var_ch, float* cov, int B, int P, float eps, cudaStream_t st);
+
+}  // namespace ub

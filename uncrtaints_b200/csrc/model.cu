@@ -1,0 +1,486 @@
+// Host-side orchestration of the UnCRtainTS hot path and the C ABI (include/uncrtaints_b200.h).
+//
+// Forward  = UNCRTAINTS.forward   (model/src/backbones/uncrtaints.py:391-446)
+// Backward = what autograd derives from it in the reference (triggered at base_model.py:77)
+//
+// Kernel sequence per MBConv block (uncrtaints.py:100-146), "one HBM materialisation per normalisation barrier":
+//   fwd  K1 gemm1 (PreNorm apply -> 1x1 expand -> h1 + stats)      K2 dwconv (Norm1+GELU -> 3x3 reflect -> h2 + stats)
+//        K3 se_pool (Norm2+GELU -> pooled sums)  se_fwd            K4 gemm2 (Norm2+GELU+gate -> 1x1 project -> y + stats)
+//        K5 residual (x + Norm3(y) -> out + stats for the next PreNorm)
+//   bwd  B5a norm_bwd_stats  B5b gemm2_bwd (+ wgrad2)  se_bwd  B3 dwconv_bwd  B2b gemm1_bwd (+ wgrad1)  B1 residual_bwd
+// with tiny finalize kernels turning column sums into per-(frame, channel) coefficients in between.
+#include <string.h>
+#include <stdio.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/uncrtaints_b200.h"
+
+namespace ub {
+
+#define UB_TRY(expr)                    \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != UB_OK) return rc__; \
+    } while (0)
+
+struct Bump {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+// Workspace slices of one MBConv block (offsets in bytes).
+struct BlockWs {
+    // saved activations
+    size_t h1, h2, y, out;
+    // forward statistics (fp64, inside the forward zero arena)
+    size_t stats0, stats1, stats2, stats3, pool, gp;
+    // coefficients
+    size_t coef0, coef1, coef2, coef3, mr0, mr1, mr2, mr3, se_save, gate, w1t, w2t;
+    // backward statistics (inside the backward zero arena) and coefficients
+    size_t bstats0, bstats1, bstats2, bstats3, sums3, bc0, bc1, bc2, bc3, dmp;
+};
+
+struct Layout {
+    int Ne, B, P, nblk, Nmax;
+    size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
+    size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
+    size_t bstats_in, bc_in;
+    size_t gA, gB, dn0, du, dz1, partial, dwup, dattn, dpooled;
+    BlockWs blk[1 + 16];
+    size_t total;
+};
+
+constexpr int MAX_PARTS = 148;
+
+static void block_fwd_stats(Bump& b, BlockWs& w, int N) {
+    w.stats0 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
+    w.stats1 = b.take((size_t)N * UB_HID * 2 * sizeof(double));
+    w.stats2 = b.take((size_t)N * UB_HID * 2 * sizeof(double));
+    w.stats3 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
+    w.pool = b.take((size_t)N * UB_HID * 2 * sizeof(double));
+    w.gp = b.take((size_t)N * UB_HID * 2 * sizeof(double));
+}
+static void block_bwd_stats(Bump& b, BlockWs& w, int N) {
+    w.bstats0 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
+    w.bstats1 = b.take((size_t)N * UB_HID * 2 * sizeof(double));
+    w.bstats2 = b.take((size_t)N * UB_HID * 2 * sizeof(double));
+    w.bstats3 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
+    w.sums3 = b.take((size_t)N * UB_HID * 3 * sizeof(double));
+}
+static void block_rest(Bump& b, BlockWs& w, int N, size_t P) {
+    w.h1 = b.take((size_t)N * P * UB_HID * sizeof(float));
+    w.h2 = b.take((size_t)N * P * UB_HID * sizeof(float));
+    w.y = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
+    w.out = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
+    w.coef0 = b.take((size_t)N * UB_WIDTH * sizeof(Coef));
+    w.coef1 = b.take((size_t)N * UB_HID * sizeof(Coef));
+    w.coef2 = b.take((size_t)N * UB_HID * sizeof(Coef));
+    w.coef3 = b.take((size_t)N * UB_WIDTH * sizeof(Coef));
+    w.mr0 = b.take((size_t)N * UB_WIDTH * sizeof(MeanRstd));
+    w.mr1 = b.take((size_t)N * UB_HID * sizeof(MeanRstd));
+    w.mr2 = b.take((size_t)N * UB_HID * sizeof(MeanRstd));
+    w.mr3 = b.take((size_t)N * UB_WIDTH * sizeof(MeanRstd));
+    w.se_save = b.take((size_t)N * (UB_HID + UB_SE + UB_HID) * sizeof(float));
+    w.gate = b.take((size_t)N * UB_HID * sizeof(float));
+    w.w1t = b.take((size_t)UB_WIDTH * UB_HID * sizeof(float));
+    w.w2t = b.take((size_t)UB_WIDTH * UB_HID * sizeof(float));
+    w.bc0 = b.take((size_t)N * UB_WIDTH * sizeof(BCoef));
+    w.bc1 = b.take((size_t)N * UB_HID * sizeof(BCoef));
+    w.bc2 = b.take((size_t)N * UB_HID * sizeof(BCoef));
+    w.bc3 = b.take((size_t)N * UB_WIDTH * sizeof(BCoef));
+    w.dmp = b.take((size_t)N * UB_HID * sizeof(float));
+}
+
+static int make_layout(const ub200_desc* d, Layout& L) {
+    if (!d || d->B < 1 || d->T < 1 || d->T > UB_TMAX || d->C_in < 1 || d->C_in > 16) return UB_ERR_ARG;
+    if (d->H < UB_LOW || d->W < UB_LOW || d->H % UB_LOW || d->W % UB_LOW) return UB_ERR_ARG;
+    if (d->n_dec_blocks < 1 || d->n_dec_blocks > 16) return UB_ERR_ARG;
+    if (d->out_dim < UB_S2 || d->out_dim > 26) return UB_ERR_ARG;
+    L.B = d->B; L.Ne = d->B * d->T; L.P = d->H * d->W; L.nblk = 1 + d->n_dec_blocks;
+    L.Nmax = L.Ne;
+    const size_t P = (size_t)L.P;
+    Bump b;
+    L.fwd_zero_begin = b.off;
+    L.notpad = b.take((size_t)L.Ne * sizeof(int));
+    L.stats_c0 = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
+    for (int i = 0; i < L.nblk; ++i) block_fwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
+    L.fwd_zero_end = b.off;
+    L.bwd_zero_begin = b.off;
+    L.bstats_in = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
+    for (int i = 0; i < L.nblk; ++i) block_bwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
+    L.bwd_zero_end = b.off;
+    L.coef_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(Coef));
+    L.mr_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(MeanRstd));
+    L.bc_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(BCoef));
+    L.x0 = b.take((size_t)L.Ne * P * UB_WIDTH * sizeof(float));
+    L.pooled = b.take((size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * sizeof(float));
+    L.pool_idx = b.take((size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * sizeof(int));
+    L.attn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
+    L.agg = b.take((size_t)L.B * P * UB_WIDTH * sizeof(float));
+    for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P);
+    if (d->need_grad) {
+        L.gA = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
+        L.gB = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
+        L.dn0 = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
+        L.du = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
+        L.dz1 = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
+        L.partial = b.take((size_t)MAX_PARTS * UB_WIDTH * UB_HID * sizeof(float));
+        L.dwup = b.take((size_t)UB_HEADS * L.Ne * P * sizeof(float));
+        L.dattn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
+        L.dpooled = b.take((size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * sizeof(float));
+    } else {
+        L.gA = L.gB = L.dn0 = L.du = L.dz1 = L.partial = L.dwup = L.dattn = L.dpooled = 0;
+    }
+    L.total = b.off;
+    return UB_OK;
+}
+
+template <class T>
+static inline T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+static inline const float* pf(const void* const* tab, int i) { return static_cast<const float*>(tab[i]); }
+static inline float* pfm(const void* const* tab, int i) { return const_cast<float*>(static_cast<const float*>(tab[i])); }
+static inline float* gf(void* const* tab, int i) { return static_cast<float*>(tab[i]); }
+
+struct BlockCtx {
+    const void* const* p;   // UB200_BLOCK_STRIDE parameter pointers
+    void* const* g;         // gradient pointers (backward) or null
+    const BlockWs* w;
+    void* ws;
+    int N, H, W, groups, training, backend;
+    float eps, momentum;
+    cudaStream_t st;
+};
+
+static int finalize(const BlockCtx& c, size_t stats, int wi, size_t coef, size_t mr, int C) {
+    return launch_norm_finalize(at<double>(c.ws, stats), pf(c.p, wi), pf(c.p, wi + 1), pfm(c.p, wi + 2), pfm(c.p, wi + 3),
+                                at<Coef>(c.ws, coef), at<MeanRstd>(c.ws, mr), c.N, C, c.groups, (double)c.H * c.W, c.eps,
+                                c.momentum, c.training, c.st);
+}
+static int finalize_bwd(const BlockCtx& c, size_t bstats, int wi, size_t mr, size_t bc, int C) {
+    return launch_norm_finalize_bwd(at<double>(c.ws, bstats), pf(c.p, wi), at<MeanRstd>(c.ws, mr), at<BCoef>(c.ws, bc),
+                                    gf(c.g, wi), gf(c.g, wi + 1), c.N, C, c.groups, (double)c.H * c.W, c.training, c.st);
+}
+
+// x: block input (stats0 already accumulated); next_stats: where K5 adds the column sums of `out` (or null)
+static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats, bool need_gp) {
+    const BlockWs& w = *c.w;
+    const int P = c.H * c.W;
+    void* ws = c.ws;
+    UB_TRY(launch_transpose(pf(c.p, UB200_B_W1), at<float>(ws, w.w1t), UB_HID, UB_WIDTH, c.st));
+    UB_TRY(launch_transpose(pf(c.p, UB200_B_W2), at<float>(ws, w.w2t), UB_WIDTH, UB_HID, c.st));
+    UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
+    UB_TRY(simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
+    UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
+    UB_TRY(launch_dwconv_fwd(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
+                             at<double>(ws, w.stats2), c.N, c.H, c.W, c.st));
+    UB_TRY(finalize(c, w.stats2, UB200_B_N2_W, w.coef2, w.mr2, UB_HID));
+    UB_TRY(launch_se_pool(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.pool),
+                          need_gp ? at<double>(ws, w.gp) : nullptr, c.N, P, c.st));
+    UB_TRY(launch_se_fwd(at<double>(ws, w.pool), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2), at<float>(ws, w.se_save),
+                         at<float>(ws, w.gate), c.N, P, c.st));
+    UB_TRY(simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
+                          at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
+    UB_TRY(finalize(c, w.stats3, UB200_B_N3_W, w.coef3, w.mr3, UB_WIDTH));
+    UB_TRY(launch_residual_fwd(x, at<float>(ws, w.y), at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats, c.N, P, c.st));
+    return UB_OK;
+}
+
+// dout: gradient w.r.t. the block output; dx: gradient w.r.t. the block input (may not alias dout)
+static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout, float* dx, float* dn0, float* du, float* dz1,
+                           float* partial) {
+    const BlockWs& w = *c.w;
+    const int P = c.H * c.W;
+    void* ws = c.ws;
+    UB_TRY(launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
+    UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
+    UB_TRY(simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
+                          at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
+    UB_TRY(simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
+                       at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
+    UB_TRY(launch_se_bwd(at<double>(ws, w.sums3), at<double>(ws, w.gp), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2),
+                         at<float>(ws, w.se_save), gf(c.g, UB200_B_F1), gf(c.g, UB200_B_F2), at<float>(ws, w.dmp),
+                         at<double>(ws, w.bstats2), c.N, P, c.st));
+    UB_TRY(finalize_bwd(c, w.bstats2, UB200_B_N2_W, w.mr2, w.bc2, UB_HID));
+    UB_TRY(launch_dwconv_bwd(du, at<float>(ws, w.h2), at<float>(ws, w.h1), at<float>(ws, w.gate), at<float>(ws, w.dmp),
+                             at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
+                             pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
+    UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
+    UB_TRY(simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
+                          at<double>(ws, w.bstats0), c.N, P, c.st));
+    UB_TRY(simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
+                       gf(c.g, UB200_B_W1), c.N, P, c.st));
+    UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
+    UB_TRY(launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.st));
+    return UB_OK;
+}
+
+// column sums of a [N][P][128] tensor (standalone MBConv entry point only)
+__global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ x, double* stats, int P, int chunk) {
+    constexpr int C = UB_WIDTH;
+    __shared__ float red[2 * 8 * C];
+    const int n = blockIdx.y, lane = threadIdx.x % 32, row = threadIdx.x / 32;
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    for (int p = p0 + row; p < p1; p += 8) {
+        const float4 v = ld4(x + ((size_t)n * P + p) * C + lane * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+    }
+    float4* r4 = reinterpret_cast<float4*>(red);
+    r4[row * 32 + lane] = s;
+    r4[256 + row * 32 + lane] = q;
+    __syncthreads();
+    const int which = threadIdx.x / C, ch = threadIdx.x % C;
+    double t = 0.0;
+    for (int r = 0; r < 8; ++r) t += (double)red[which * 8 * C + r * C + ch];
+    atomicAdd(&stats[((size_t)n * C + ch) * 2 + which], t);
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+}  // namespace ub
+
+using namespace ub;
+
+extern "C" {
+
+int ub200_version(void) { return 100; }
+
+int ub200_num_param_slots(const ub200_desc* d) {
+    if (!d) return UB_ERR_ARG;
+    return UB200_P_BLOCK0 + (1 + d->n_dec_blocks) * UB200_BLOCK_STRIDE;
+}
+
+size_t ub200_workspace_bytes(const ub200_desc* d) {
+    Layout L;
+    if (make_layout(d, L) != UB_OK) return 0;
+    return L.total;
+}
+
+int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, size_t* bytes) {
+    Layout L;
+    if (!name || !offset || !bytes || make_layout(d, L) != UB_OK) return UB_ERR_ARG;
+    const size_t P = (size_t)L.P;
+    struct { const char* n; size_t off, sz; } fixed[] = {
+        {"x0", L.x0, (size_t)L.Ne * P * UB_WIDTH * 4},
+        {"pooled", L.pooled, (size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * 4},
+        {"pool_idx", L.pool_idx, (size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * 4},
+        {"attn", L.attn, (size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * 4},
+        {"agg", L.agg, (size_t)L.B * P * UB_WIDTH * 4},
+        {"notpad", L.notpad, (size_t)L.Ne * 4},
+    };
+    for (auto& f : fixed)
+        if (!strcmp(f.n, name)) { *offset = f.off; *bytes = f.sz; return UB_OK; }
+    int bi = -1;
+    char what[16];
+    if (sscanf(name, "blk%d.%15s", &bi, what) == 2 && bi >= 0 && bi < L.nblk) {
+        const size_t N = bi == 0 ? L.Ne : L.B;
+        const BlockWs& w = L.blk[bi];
+        if (!strcmp(what, "h1")) { *offset = w.h1; *bytes = N * P * UB_HID * 4; return UB_OK; }
+        if (!strcmp(what, "h2")) { *offset = w.h2; *bytes = N * P * UB_HID * 4; return UB_OK; }
+        if (!strcmp(what, "y")) { *offset = w.y; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
+        if (!strcmp(what, "out")) { *offset = w.out; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
+    }
+    return UB_ERR_ARG;
+}
+
+static BlockCtx make_ctx(const ub200_desc* d, const Layout& L, int i, const void* const* params, void* const* grads, void* ws,
+                         cudaStream_t st) {
+    BlockCtx c;
+    c.p = params + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE;
+    c.g = grads ? grads + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE : nullptr;
+    c.w = &L.blk[i];
+    c.ws = ws;
+    c.N = i == 0 ? L.Ne : L.B;
+    c.H = d->H; c.W = d->W;
+    c.groups = i == 0 ? d->enc_groups : d->dec_groups;
+    c.training = d->training;
+    c.backend = d->gemm_backend;
+    c.eps = d->norm_eps; c.momentum = d->bn_momentum;
+    c.st = st;
+    return c;
+}
+
+int ub200_forward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                  float* output, void* ws, size_t ws_bytes, void* stream) {
+    Layout L;
+    UB_TRY(make_layout(d, L));
+    if (!input || !params || !output || !ws) return UB_ERR_ARG;
+    if (ws_bytes < L.total) return UB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int P = L.P;
+    if (cudaMemsetAsync(at<char>(ws, L.fwd_zero_begin), 0, L.fwd_zero_end - L.fwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
+
+    // in_conv: conv1x1 + norm + ReLU (+ pad-mask test), NCHW -> pixel-major
+    UB_TRY(launch_inconv_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.stats_c0),
+                               at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
+    UB_TRY(launch_norm_finalize(at<double>(ws, L.stats_c0), pf(params, UB200_P_IN_NORM_W), pf(params, UB200_P_IN_NORM_B),
+                                pfm(params, UB200_P_IN_NORM_RM), pfm(params, UB200_P_IN_NORM_RV), at<Coef>(ws, L.coef_in),
+                                at<MeanRstd>(ws, L.mr_in), L.Ne, UB_WIDTH, d->enc_groups, (double)P, d->norm_eps, d->bn_momentum,
+                                d->training, st));
+    UB_TRY(launch_inconv_apply(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+                               at<float>(ws, L.x0), at<double>(ws, L.blk[0].stats0), L.Ne, d->C_in, P, st));
+    // encoder block
+    BlockCtx enc = make_ctx(d, L, 0, params, nullptr, ws, st);
+    UB_TRY(mbconv_forward(enc, at<float>(ws, L.x0), nullptr, d->need_grad != 0));
+    const float* enc_out = at<float>(ws, L.blk[0].out);
+    // temporal path
+    UB_TRY(launch_maxpool_fwd(enc_out, at<float>(ws, L.pooled), at<int>(ws, L.pool_idx), L.Ne, d->H, d->W, st));
+    UB_TRY(launch_ltae_fwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), pf(params, UB200_P_LTAE_E),
+                           at<int>(ws, L.notpad), at<float>(ws, L.attn), d->B, d->T, d->norm_eps, st));
+    const float drop_p = d->training ? d->dropout_p : 0.f;
+    UB_TRY(launch_aggregate_fwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out,
+                                at<float>(ws, L.agg), at<double>(ws, L.blk[1].stats0), d->B, d->T, d->H, d->W, st));
+    // decoder blocks
+    const float* x = at<float>(ws, L.agg);
+    for (int i = 1; i < L.nblk; ++i) {
+        BlockCtx c = make_ctx(d, L, i, params, nullptr, ws, st);
+        UB_TRY(mbconv_forward(c, x, i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr, d->need_grad != 0));
+        x = at<float>(ws, L.blk[i].out);
+    }
+    UB_TRY(launch_head_fwd(x, pf(params, UB200_P_OUT_W), pf(params, UB200_P_OUT_B), output, d->B, d->out_dim, P, d->scale_by,
+                           d->mean_sigmoid, d->var_eps, st));
+    return UB_OK;
+}
+
+int ub200_backward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                   const float* output, const float* grad_output, void* const* grads, void* ws, size_t ws_bytes, void* stream) {
+    Layout L;
+    UB_TRY(make_layout(d, L));
+    if (!input || !params || !output || !grad_output || !grads || !ws || !d->need_grad) return UB_ERR_ARG;
+    if (ws_bytes < L.total) return UB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int P = L.P;
+    if (cudaMemsetAsync(at<char>(ws, L.bwd_zero_begin), 0, L.bwd_zero_end - L.bwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
+    float* gA = at<float>(ws, L.gA);
+    float* gB = at<float>(ws, L.gB);
+    float* dn0 = at<float>(ws, L.dn0);
+    float* du = at<float>(ws, L.du);
+    float* dz1 = at<float>(ws, L.dz1);
+    float* partial = at<float>(ws, L.partial);
+
+    const float* dec_out = at<float>(ws, L.blk[L.nblk - 1].out);
+    UB_TRY(launch_head_bwd(grad_output, output, dec_out, pf(params, UB200_P_OUT_W), gA, gf(grads, UB200_P_OUT_W),
+                           gf(grads, UB200_P_OUT_B), d->B, d->out_dim, P, d->scale_by, d->mean_sigmoid, d->var_eps, num_sms(), st));
+    for (int i = L.nblk - 1; i >= 1; --i) {
+        BlockCtx c = make_ctx(d, L, i, params, grads, ws, st);
+        const float* x = i == 1 ? at<float>(ws, L.agg) : at<float>(ws, L.blk[i - 1].out);
+        UB_TRY(mbconv_backward(c, x, gA, gB, dn0, du, dz1, partial));
+        float* t = gA; gA = gB; gB = t;
+    }
+    // gA = dAgg.  Temporal path backward; dEnc accumulates in gB.
+    const float* enc_out = at<float>(ws, L.blk[0].out);
+    const float drop_p = d->training ? d->dropout_p : 0.f;
+    UB_TRY(launch_aggregate_bwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out, gA,
+                                gB, at<float>(ws, L.dwup), at<float>(ws, L.dattn), d->B, d->T, d->H, d->W, st));
+    UB_TRY(launch_ltae_bwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), at<float>(ws, L.attn), at<float>(ws, L.dattn),
+                           at<float>(ws, L.dpooled), gf(grads, UB200_P_LTAE_AP), gf(grads, UB200_P_LTAE_E), d->B, d->T,
+                           d->norm_eps, st));
+    UB_TRY(launch_maxpool_bwd(at<float>(ws, L.dpooled), at<int>(ws, L.pool_idx), gB, L.Ne, P, st));
+    BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
+    UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
+    // in_conv backward (no input gradient)
+    UB_TRY(launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+                                   at<MeanRstd>(ws, L.mr_in), gA, at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
+    UB_TRY(launch_norm_finalize_bwd(at<double>(ws, L.bstats_in), pf(params, UB200_P_IN_NORM_W), at<MeanRstd>(ws, L.mr_in),
+                                    at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_NORM_W), gf(grads, UB200_P_IN_NORM_B), L.Ne,
+                                    UB_WIDTH, d->enc_groups, (double)P, d->training, st));
+    UB_TRY(launch_inconv_bwd_wgrad(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+                                   at<MeanRstd>(ws, L.mr_in), at<BCoef>(ws, L.bc_in), gA, gf(grads, UB200_P_IN_W),
+                                   gf(grads, UB200_P_IN_B), L.Ne, d->C_in, P, st));
+    return UB_OK;
+}
+
+int ub200_mgnll_forward(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
+                        long long var_sb, int var_ch, int B, int P, float eps, float* loss, float* dpred, float* dvar,
+                        int* neg_flag, void* scratch, void* stream) {
+    if (!pred || !target || !var || !loss || !neg_flag || !scratch || (var_ch != 1 && var_ch != UB_S2) || B < 1 || P < 1)
+        return UB_ERR_ARG;
+    if ((dpred == nullptr) != (dvar == nullptr)) return UB_ERR_ARG;
+    return launch_mgnll(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, dpred, dvar, static_cast<double*>(scratch),
+                        neg_flag, loss, B, P, eps, static_cast<cudaStream_t>(stream));
+}
+
+int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, size_t n, void* stream) {
+    if (!in || !grad_loss || !out) return UB_ERR_ARG;
+    return launch_scale_by_scalar(in, grad_loss, out, n, static_cast<cudaStream_t>(stream));
+}
+
+int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int P, float eps, float* cov, void* stream) {
+    if (!var || !cov || (var_ch != 1 && var_ch != UB_S2)) return UB_ERR_ARG;
+    return launch_covariance(var, var_sb, var_ch, cov, B, P, eps, static_cast<cudaStream_t>(stream));
+}
+
+// ---- standalone MBConv block (tests) -------------------------------------------------------------------
+struct MbLayout { BlockWs w; size_t zero_begin, zero_end, bzero_begin, bzero_end, dn0, du, dz1, partial, total; };
+static void mb_layout(int N, int H, int W, MbLayout& M) {
+    Bump b;
+    M.zero_begin = b.off;
+    block_fwd_stats(b, M.w, N);
+    M.zero_end = b.off;
+    M.bzero_begin = b.off;
+    block_bwd_stats(b, M.w, N);
+    M.bzero_end = b.off;
+    block_rest(b, M.w, N, (size_t)H * W);
+    M.dn0 = b.take((size_t)N * H * W * UB_WIDTH * 4);
+    M.du = b.take((size_t)N * H * W * UB_HID * 4);
+    M.dz1 = b.take((size_t)N * H * W * UB_HID * 4);
+    M.partial = b.take((size_t)MAX_PARTS * UB_WIDTH * UB_HID * 4);
+    M.total = b.off;
+}
+size_t ub200_mbconv_workspace_bytes(int N, int H, int W) {
+    MbLayout M;
+    mb_layout(N, H, W, M);
+    return M.total;
+}
+static BlockCtx mb_ctx(const MbLayout& M, const void* const* p, void* const* g, void* ws, int N, int H, int W, int groups,
+                       int training, float eps, float momentum, int backend, cudaStream_t st) {
+    BlockCtx c;
+    c.p = p; c.g = g; c.w = &M.w; c.ws = ws; c.N = N; c.H = H; c.W = W; c.groups = groups; c.training = training;
+    c.backend = backend; c.eps = eps; c.momentum = momentum; c.st = st;
+    return c;
+}
+int ub200_mbconv_forward(const float* x, const void* const* block_params, int N, int H, int W, int groups, int training,
+                         float eps, float momentum, int gemm_backend, float* out, void* ws, size_t ws_bytes, void* stream) {
+    if (!x || !block_params || !out || !ws || N < 1 || H % 8 || W % 32) return UB_ERR_ARG;
+    MbLayout M;
+    mb_layout(N, H, W, M);
+    if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int P = H * W;
+    if (cudaMemsetAsync(at<char>(ws, M.zero_begin), 0, M.zero_end - M.zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
+    const int chunk = 256;
+    colstats_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(x, at<double>(ws, M.w.stats0), P, chunk);
+    UB_CHECK_LAUNCH();
+    BlockCtx c = mb_ctx(M, block_params, nullptr, ws, N, H, W, groups, training, eps, momentum, gemm_backend, st);
+    UB_TRY(mbconv_forward(c, x, nullptr, true));
+    if (cudaMemcpyAsync(out, at<float>(ws, M.w.out), (size_t)N * P * UB_WIDTH * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return UB_ERR_CUDA;
+    return UB_OK;
+}
+int ub200_mbconv_backward(const float* x, const void* const* block_params, const float* dout, void* const* block_grads, int N,
+                          int H, int W, int groups, int training, int gemm_backend, float* dx, void* ws, size_t ws_bytes,
+                          void* stream) {
+    if (!x || !block_params || !dout || !block_grads || !dx || !ws) return UB_ERR_ARG;
+    MbLayout M;
+    mb_layout(N, H, W, M);
+    if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(at<char>(ws, M.bzero_begin), 0, M.bzero_end - M.bzero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
+    BlockCtx c = mb_ctx(M, block_params, block_grads, ws, N, H, W, groups, training, 1e-5f, 0.1f, gemm_backend, st);
+    return mbconv_backward(c, x, dout, dx, at<float>(ws, M.dn0), at<float>(ws, M.du), at<float>(ws, M.dz1),
+                           at<float>(ws, M.partial));
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Normalisation finalisers (GroupNorm / BatchNorm2d) and the HBM-bound pixel-major
+// elementwise passes of an MBConv block.
+//
+// Reference semantics: get_norm_layer / PreNorm (model/src/backbones/uncrtaints.py:16-22,72-79),
+// nn.GroupNorm(4 groups) in the encoder, nn.BatchNorm2d in the decoder; MBConv residual add
+// (uncrtaints.py:142-146).  Statistics are produced by the kernel that writes a tensor (column sums
+// in its epilogue, fp64 accumulation) and consumed as per-(frame, channel) scale/shift here.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ub {
+
+// Reduce two float4 column accumulators over the pixel-rows of a 256-thread block and add them to
+// stats_n[c][0..1] (fp64).  Thread layout: c4 = tid % (C/4), row = tid / (C/4).
+template <int C>
+__device__ __forceinline__ void block_reduce_cols2(float4 a, float4 b, double* stats_n, float* smem) {
+    constexpr int Q = C / 4, ROWS = 256 / Q;
+    const int c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    float4* sa = reinterpret_cast<float4*>(smem);
+    float4* sb = sa + ROWS * Q;
+    sa[r * Q + c4] = a;
+    sb[r * Q + c4] = b;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        const int which = i / C, ch = i % C;
+        const float* src = reinterpret_cast<const float*>(which ? sb : sa);
+        double t = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) t += (double)src[rr * C + ch];
+        atomicAdd(&stats_n[ch * 2 + which], t);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// forward finaliser: raw (sum, sumsq) -> scale/shift (+ saved mean/rstd, BN running stats)
+// grid = N blocks, C threads.  groups == 0 -> BatchNorm over all frames.
+// ------------------------------------------------------------------------------------------
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* running_mean, float* running_var,
+                                     Coef* __restrict__ coef, MeanRstd* __restrict__ mr, int N, int C, int groups,
+                                     double count, float eps, float momentum, int training) {
+    extern __shared__ double sm[];
+    const int n = blockIdx.x, c = threadIdx.x;
+    double mean, var;
+    if (groups > 0) {
+        sm[c] = stats[((size_t)n * C + c) * 2 + 0];
+        sm[C + c] = stats[((size_t)n * C + c) * 2 + 1];
+        __syncthreads();
+        const int gs = C / groups, g0 = (c / gs) * gs;
+        double s = 0.0, q = 0.0;
+        for (int j = 0; j < gs; ++j) { s += sm[g0 + j]; q += sm[C + g0 + j]; }
+        const double cnt = count * gs;
+        mean = s / cnt;
+        var = q / cnt - mean * mean;
+    } else if (training) {
+        double s = 0.0, q = 0.0;
+        for (int j = 0; j < N; ++j) {
+            s += stats[((size_t)j * C + c) * 2 + 0];
+            q += stats[((size_t)j * C + c) * 2 + 1];
+        }
+        const double cnt = count * N;
+        mean = s / cnt;
+        var = q / cnt - mean * mean;
+        if (n == 0 && running_mean != nullptr) {
+            const double unbiased = var * (cnt / (cnt > 1.0 ? cnt - 1.0 : 1.0));
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const float sc = (float)(gamma[c] * rstd);
+    coef[(size_t)n * C + c] = Coef{sc, (float)(beta[c] - mean * gamma[c] * rstd)};
+    mr[(size_t)n * C + c] = MeanRstd{(float)mean, (float)rstd};
+}
+
+// ------------------------------------------------------------------------------------------
+// backward finaliser.  bstats[n][c] = (sum_p dy, sum_p dy*x_hat), dy = grad w.r.t. the norm output.
+//   dx = r*(g*dy - m1 - x_hat*m2),  m1 = mean_S(g*dy), m2 = mean_S(g*dy*x_hat)
+//      = (r g) dy + (-r^2 m2) x + (r^2 m2 mu - r m1)
+// S = (group channels x pixels) of one frame for GroupNorm, (all frames x pixels) of one channel for
+// BatchNorm in training; eval-mode BatchNorm has no statistics term.
+// Also accumulates dgamma[c] += sum_n sum_p dy*x_hat, dbeta[c] += sum_n sum_p dy.
+// ------------------------------------------------------------------------------------------
+__global__ void norm_finalize_bwd_kernel(const double* __restrict__ bstats, const float* __restrict__ gamma,
+                                         const MeanRstd* __restrict__ mr, BCoef* __restrict__ bcoef,
+                                         float* dgamma, float* dbeta, int N, int C, int groups, double count,
+                                         int training) {
+    extern __shared__ double sm[];
+    const int n = blockIdx.x, c = threadIdx.x;
+    const double g = gamma[c];
+    const MeanRstd s = mr[(size_t)n * C + c];
+    const double r = s.rstd, mu = s.mean;
+    double m1 = 0.0, m2 = 0.0;
+    if (groups > 0) {
+        sm[c] = g * bstats[((size_t)n * C + c) * 2 + 0];
+        sm[C + c] = g * bstats[((size_t)n * C + c) * 2 + 1];
+        __syncthreads();
+        const int gs = C / groups, g0 = (c / gs) * gs;
+        for (int j = 0; j < gs; ++j) { m1 += sm[g0 + j]; m2 += sm[C + g0 + j]; }
+        m1 /= count * gs;
+        m2 /= count * gs;
+    }
+    double sdy = 0.0, sdyx = 0.0;
+    if (groups == 0 || n == 0) {
+        for (int j = 0; j < N; ++j) {
+            sdy += bstats[((size_t)j * C + c) * 2 + 0];
+            sdyx += bstats[((size_t)j * C + c) * 2 + 1];
+        }
+    }
+    if (groups == 0 && training) {
+        m1 = g * sdy / (count * N);
+        m2 = g * sdyx / (count * N);
+    }
+    bcoef[(size_t)n * C + c] = BCoef{(float)(r * g), (float)(-r * r * m2), (float)(r * r * m2 * mu - r * m1), 0.f};
+    if (n == 0) {
+        if (dgamma) dgamma[c] += (float)sdyx;
+        if (dbeta) dbeta[c] += (float)sdy;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: out = x + (y*scale3 + shift3); epilogue: column sums of `out` for the next block's PreNorm.
+// grid (chunks, N); 256 threads; C = 128.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) residual_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const Coef* __restrict__ coef3, float* __restrict__ out,
+                                                            double* out_stats, int P, int chunk) {
+    constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[2 * ROWS * C];
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    const Coef k0 = coef3[(size_t)n * C + c4 * 4 + 0], k1 = coef3[(size_t)n * C + c4 * 4 + 1],
+               k2 = coef3[(size_t)n * C + c4 * 4 + 2], k3 = coef3[(size_t)n * C + c4 * 4 + 3];
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    const size_t base = (size_t)n * P * C + c4 * 4;
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 xv = ld4_stream(x + base + (size_t)p * C);
+        const float4 yv = ld4_stream(y + base + (size_t)p * C);
+        float4 o;
+        o.x = xv.x + fmaf(yv.x, k0.scale, k0.shift);
+        o.y = xv.y + fmaf(yv.y, k1.scale, k1.shift);
+        o.z = xv.z + fmaf(yv.z, k2.scale, k2.shift);
+        o.w = xv.w + fmaf(yv.w, k3.scale, k3.shift);
+        st4(out + base + (size_t)p * C, o);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
+    }
+    if (out_stats) block_reduce_cols2<C>(s, q, out_stats + (size_t)n * C * 2, smem);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: SE squeeze.  pool[n][c][0] += sum_p gelu(z2), z2 = h2*scale2 + shift2.  C = 256.
+// In training it also gathers gp_stats[n][c] += (sum_p gelu'(z2), sum_p gelu'(z2)*h2_hat): the two terms of
+// the Norm2 backward statistics that do not depend on the incoming gradient (see se_bwd_kernel).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) se_pool_kernel(const float* __restrict__ h2, const Coef* __restrict__ coef2,
+                                                       const MeanRstd* __restrict__ mr2, double* pool_stats,
+                                                       double* gp_stats, int P, int chunk) {
+    constexpr int C = UB_HID, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[2 * ROWS * C];
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    Coef k[4];
+    MeanRstd m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k[i] = coef2[(size_t)n * C + c4 * 4 + i]; m[i] = mr2[(size_t)n * C + c4 * 4 + i]; }
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float s[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, gh[4] = {0, 0, 0, 0};
+    const size_t base = (size_t)n * P * C + c4 * 4;
+    const bool train = gp_stats != nullptr;
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 v = ld4(h2 + base + (size_t)p * C);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(vv[i], k[i].scale, k[i].shift);
+            s[i] += gelu_f(z);
+            if (train) {
+                const float gp = gelu_grad_f(z);
+                g[i] += gp;
+                gh[i] += gp * (vv[i] - m[i].mean) * m[i].rstd;
+            }
+        }
+    }
+    block_reduce_cols2<C>(make_float4(s[0], s[1], s[2], s[3]), make_float4(0, 0, 0, 0), pool_stats + (size_t)n * C * 2, smem);
+    if (train)
+        block_reduce_cols2<C>(make_float4(g[0], g[1], g[2], g[3]), make_float4(gh[0], gh[1], gh[2], gh[3]),
+                              gp_stats + (size_t)n * C * 2, smem);
+}
+
+// ------------------------------------------------------------------------------------------
+// B5a: statistics of the normalisation backward: bstats[n][c] += (sum dy, sum dy * v_hat),
+// v_hat = (v - mean) * rstd.  C = 128 (used for the last norm of a block: dy = dOut, v = y).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ v,
+                                                              const MeanRstd* __restrict__ mr, double* bstats, int P,
+                                                              int chunk) {
+    constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[2 * ROWS * C];
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    const MeanRstd m0 = mr[(size_t)n * C + c4 * 4 + 0], m1 = mr[(size_t)n * C + c4 * 4 + 1],
+                   m2 = mr[(size_t)n * C + c4 * 4 + 2], m3 = mr[(size_t)n * C + c4 * 4 + 3];
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    const size_t base = (size_t)n * P * C + c4 * 4;
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 d = ld4(dy + base + (size_t)p * C);
+        const float4 w = ld4(v + base + (size_t)p * C);
+        s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+        q.x += d.x * (w.x - m0.mean) * m0.rstd;
+        q.y += d.y * (w.y - m1.mean) * m1.rstd;
+        q.z += d.z * (w.z - m2.mean) * m2.rstd;
+        q.w += d.w * (w.w - m3.mean) * m3.rstd;
+    }
+    block_reduce_cols2<C>(s, q, bstats + (size_t)n * C * 2, smem);
+}
+
+// ------------------------------------------------------------------------------------------
+// B1: dX = dOut + (a0*dn0 + b0*x + c0)   (residual + PreNorm backward).  C = 128.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dn0,
+                                                            const float* __restrict__ x, const BCoef* __restrict__ bc0,
+                                                            float* __restrict__ dx, int P, int chunk) {
+    constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    const BCoef k0 = bc0[(size_t)n * C + c4 * 4 + 0], k1 = bc0[(size_t)n * C + c4 * 4 + 1],
+                k2 = bc0[(size_t)n * C + c4 * 4 + 2], k3 = bc0[(size_t)n * C + c4 * 4 + 3];
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    const size_t base = (size_t)n * P * C + c4 * 4;
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 g = ld4_stream(dout + base + (size_t)p * C);
+        const float4 d = ld4_stream(dn0 + base + (size_t)p * C);
+        const float4 xv = ld4_stream(x + base + (size_t)p * C);
+        float4 o;
+        o.x = g.x + fmaf(k0.a, d.x, fmaf(k0.b, xv.x, k0.c));
+        o.y = g.y + fmaf(k1.a, d.y, fmaf(k1.b, xv.y, k1.c));
+        o.z = g.z + fmaf(k2.a, d.z, fmaf(k2.b, xv.z, k2.c));
+        o.w = g.w + fmaf(k3.a, d.w, fmaf(k3.b, xv.w, k3.c));
+        st4(dx + base + (size_t)p * C, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static inline int chunk_for(int P) { return P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64); }
+
+int launch_norm_finalize(const double* stats, const float* gamma, const float* beta, float* rm, float* rv, Coef* coef,
+                         MeanRstd* mr, int N, int C, int groups, double count, float eps, float momentum, int training,
+                         cudaStream_t st) {
+    norm_finalize_kernel<<<N, C, 2 * C * sizeof(double), st>>>(stats, gamma, beta, rm, rv, coef, mr, N, C, groups, count,
+                                                                 eps, momentum, training);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_norm_finalize_bwd(const double* bstats, const float* gamma, const MeanRstd* mr, BCoef* bcoef, float* dgamma,
+                             float* dbeta, int N, int C, int groups, double count, int training, cudaStream_t st) {
+    norm_finalize_bwd_kernel<<<N, C, 2 * C * sizeof(double), st>>>(bstats, gamma, mr, bcoef, dgamma, dbeta, N, C, groups,
+                                                                     count, training);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_residual_fwd(const float* x, const float* y, const Coef* coef3, float* out, double* out_stats, int N, int P,
+                        cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    residual_fwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(x, y, coef3, out, out_stats, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_se_pool(const float* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
+                   int P, cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    se_pool_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(h2, coef2, mr2, pool_stats, gp_stats, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, double* bstats, int N, int P,
+                          cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    norm_bwd_stats_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, v, mr, bstats, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
+                        cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    residual_bwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+}  // namespace ub

@@ -1,0 +1,464 @@
+// Temporal path of UnCRtainTS: adaptive max-pool to 32x32, L-TAE-tiny attention, attention-weighted
+// temporal aggregation -- forward and backward.
+//
+//   maxpool    : nn.AdaptiveMaxPool2d((32,32)) (model/src/backbones/uncrtaints.py:403-404), first-max argmax
+//   ltae       : LTAE2dtiny.forward + MultiHeadAttentionSmall + ScaledDotProductAttentionSmall
+//                (model/src/backbones/ltae.py:197-239, 341-385, 431-458)
+//   aggregate  : Compact_Temporal_Aggregator, mode att_group (uncrtaints.py:156-210): bilinear x(H/32) upsample
+//                (align_corners=False) -> Dropout(0.1) -> (~pad_mask) -> sum_t a[c//8] * x[t, c]
+//
+// L-TAE algebra.  The query is input independent (ltae.py:324,347), so with x_hat the GroupNorm(16)-normalised
+// pooled features (groups = 8 channels x T time steps per low-res pixel, ltae.py:211):
+//   score[h,t] = 1/2 * ( sum_c Ap[h,c] * x_hat[c,t] + e[b,t,h] )
+//   Ap[h,c] = gamma_c * sum_k Ak[h,k] * W_in[k,c],  Ak[h,k] = sum_d Q[h,d] * W_k[4h+d,k]
+//   e[b,t,h] = pe[b,t,:].Ak[h,:] + (terms constant in t, which cancel in the softmax)
+// Ap and e are produced by the Python shim from the reference's parameters with differentiable torch ops
+// (they are functions of ~100K weights, not of activations); the kernels here return dAp and de.
+// The upsampled attention ([16*B, T, H, W], 201 MB at B=16 in the reference) is never materialised:
+// the four bilinear taps are evaluated inside the aggregation kernel.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ub {
+
+// ------------------------------------------------------------------------------------------
+// adaptive max pool (H, W multiples of 32): window s x s, s = H/32.  grid (1024, N), 128 threads (= channel)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ pooled,
+                                                           int* __restrict__ idx, int H, int W) {
+    constexpr int C = UB_WIDTH;
+    const int n = blockIdx.y, win = blockIdx.x, wy = win / UB_LOW, wx = win % UB_LOW, c = threadIdx.x;
+    const int sy = H / UB_LOW, sx = W / UB_LOW;
+    const float* src = x + (size_t)n * H * W * C + c;
+    float best = -INFINITY;
+    int bi = (wy * sy) * W + wx * sx;
+    for (int i = 0; i < sy; ++i)
+        for (int j = 0; j < sx; ++j) {
+            const int p = (wy * sy + i) * W + wx * sx + j;
+            const float v = src[(size_t)p * C];
+            if (v > best || v != v) { best = v; bi = p; }   // ATen rule: (val > max) || isnan(val)
+        }
+    pooled[((size_t)n * UB_LOW * UB_LOW + win) * C + c] = best;
+    idx[((size_t)n * UB_LOW * UB_LOW + win) * C + c] = bi;
+}
+
+// dEnc[n][idx][c] += dpooled[n][win][c]   (windows are disjoint: plain read-modify-write)
+__global__ void __launch_bounds__(128) maxpool_bwd_kernel(const float* __restrict__ dpooled, const int* __restrict__ idx,
+                                                           float* __restrict__ denc, int HW) {
+    constexpr int C = UB_WIDTH;
+    const int n = blockIdx.y, win = blockIdx.x, c = threadIdx.x;
+    const size_t o = ((size_t)n * UB_LOW * UB_LOW + win) * C + c;
+    denc[((size_t)n * HW + idx[o]) * C + c] += dpooled[o];
+}
+
+// ------------------------------------------------------------------------------------------
+// L-TAE tiny.  One warp per low-res pixel; lane l owns channels 4l..4l+3 (GroupNorm group = lanes 2g, 2g+1).
+// ------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ void ltae_normalize(const float* __restrict__ pooled, int b, int q, int lane, float eps,
+                                               float (&xh)[T][4], float& rstd) {
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const float4 v = ld4(pooled + (((size_t)(b * T + t)) * UB_LOW * UB_LOW + q) * UB_WIDTH + lane * 4);
+        xh[t][0] = v.x; xh[t][1] = v.y; xh[t][2] = v.z; xh[t][3] = v.w;
+        sum += v.x + v.y + v.z + v.w;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    const float mean = sum / (8.f * T);
+    float var = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xh[t][j] -= mean; var = fmaf(xh[t][j], xh[t][j], var); }
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    rstd = 1.0f / sqrtf(var / (8.f * T) + eps);
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xh[t][j] *= rstd;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) ltae_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ Ap /* [16][128] */,
+                                                        const float* __restrict__ e /* [B][T][16] */, const int* __restrict__ notpad /* [B*T] */,
+                                                        float* __restrict__ attn /* [16][B][T][1024] */, int B, float eps) {
+    __shared__ __align__(16) float sAp[UB_HEADS * UB_WIDTH];
+    for (int i = threadIdx.x; i < UB_HEADS * UB_WIDTH; i += 256) sAp[i] = Ap[i];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int pix = blockIdx.x * 8 + warp;          // b * 1024 + q
+    if (pix >= B * UB_LOW * UB_LOW) return;
+    const int b = pix / (UB_LOW * UB_LOW), q = pix % (UB_LOW * UB_LOW);
+    float xh[T][4], rstd;
+    ltae_normalize<T>(pooled, b, q, lane, eps, xh, rstd);
+    float sc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) sc[t] = 0.f;
+#pragma unroll 4
+    for (int h = 0; h < UB_HEADS; ++h) {
+        const float4 a = ld4(sAp + h * UB_WIDTH + lane * 4);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            float part = a.x * xh[t][0] + a.y * xh[t][1] + a.z * xh[t][2] + a.w * xh[t][3];
+            part = warp_sum(part);
+            if (lane == h) sc[t] = part;
+        }
+    }
+    if (lane < UB_HEADS) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            sc[t] = 0.5f * (sc[t] + e[((size_t)b * T + t) * UB_HEADS + lane]);    // / temperature sqrt(d_k)=2, ltae.py:339,433
+            if (!notpad[b * T + t]) sc[t] = -1000.0f;                             // masked_fill(pad, -1e3), ltae.py:435
+            mx = fmaxf(mx, sc[t]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { sc[t] = expf(sc[t] - mx); den += sc[t]; }
+        const float inv = 1.0f / den;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+            attn[(((size_t)lane * B + b) * T + t) * (UB_LOW * UB_LOW) + q] = sc[t] * inv;
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) ltae_bwd_kernel(const float* __restrict__ pooled, const float* __restrict__ Ap,
+                                                        const float* __restrict__ attn, const float* __restrict__ dattn,
+                                                        float* __restrict__ dpooled, float* dAp, float* de, int B, float eps,
+                                                        int pix_per_warp) {
+    __shared__ __align__(16) float sAp[UB_HEADS * UB_WIDTH];
+    for (int i = threadIdx.x; i < UB_HEADS * UB_WIDTH; i += 256) sAp[i] = Ap[i];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int npix = B * UB_LOW * UB_LOW;
+    float4 gA[UB_HEADS];
+#pragma unroll
+    for (int h = 0; h < UB_HEADS; ++h) gA[h] = make_float4(0, 0, 0, 0);
+    const int first = (blockIdx.x * 8 + warp) * pix_per_warp;
+    for (int pix = first; pix < first + pix_per_warp && pix < npix; ++pix) {
+        const int b = pix / (UB_LOW * UB_LOW), q = pix % (UB_LOW * UB_LOW);
+        float xh[T][4], rstd;
+        ltae_normalize<T>(pooled, b, q, lane, eps, xh, rstd);
+        // softmax backward on lanes < 16 (lane = head); masked entries have attn == 0 => zero gradient
+        float ds[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) ds[t] = 0.f;
+        if (lane < UB_HEADS) {
+            float a[T], dot = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const size_t o = (((size_t)lane * B + b) * T + t) * (UB_LOW * UB_LOW) + q;
+                a[t] = attn[o];
+                ds[t] = dattn[o];
+                dot = fmaf(a[t], ds[t], dot);
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                ds[t] = 0.5f * a[t] * (ds[t] - dot);
+                atomicAdd(&de[((size_t)b * T + t) * UB_HEADS + lane], ds[t]);
+            }
+        }
+        float dxh[T][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dxh[t][j] = 0.f;
+#pragma unroll
+        for (int h = 0; h < UB_HEADS; ++h) {
+            const float4 a = ld4(sAp + h * UB_WIDTH + lane * 4);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float d = __shfl_sync(0xffffffffu, ds[t], h);
+                gA[h].x = fmaf(d, xh[t][0], gA[h].x); gA[h].y = fmaf(d, xh[t][1], gA[h].y);
+                gA[h].z = fmaf(d, xh[t][2], gA[h].z); gA[h].w = fmaf(d, xh[t][3], gA[h].w);
+                dxh[t][0] = fmaf(a.x, d, dxh[t][0]); dxh[t][1] = fmaf(a.y, d, dxh[t][1]);
+                dxh[t][2] = fmaf(a.z, d, dxh[t][2]); dxh[t][3] = fmaf(a.w, d, dxh[t][3]);
+            }
+        }
+        // GroupNorm backward without affine (gamma/beta are folded into Ap / e)
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { m1 += dxh[t][j]; m2 = fmaf(dxh[t][j], xh[t][j], m2); }
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+        m1 /= 8.f * T; m2 /= 8.f * T;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            float4 o;
+            o.x = rstd * (dxh[t][0] - m1 - xh[t][0] * m2);
+            o.y = rstd * (dxh[t][1] - m1 - xh[t][1] * m2);
+            o.z = rstd * (dxh[t][2] - m1 - xh[t][2] * m2);
+            o.w = rstd * (dxh[t][3] - m1 - xh[t][3] * m2);
+            st4(dpooled + (((size_t)(b * T + t)) * UB_LOW * UB_LOW + q) * UB_WIDTH + lane * 4, o);
+        }
+    }
+    // dAp: reduce over the 8 warps, then one atomic per element per CTA
+    __shared__ __align__(16) float red[8 * UB_WIDTH];
+#pragma unroll 1
+    for (int h = 0; h < UB_HEADS; ++h) {
+        float4 v = gA[0];
+#pragma unroll
+        for (int j = 1; j < UB_HEADS; ++j) if (j == h) v = gA[j];
+        __syncthreads();
+        st4(red + warp * UB_WIDTH + lane * 4, v);
+        __syncthreads();
+        if (threadIdx.x < UB_WIDTH) {
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += red[r * UB_WIDTH + threadIdx.x];
+            atomicAdd(&dAp[h * UB_WIDTH + threadIdx.x], t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// aggregation.  One warp per group of 4 consecutive pixels (one Philox call per (head, t) covers the 4).
+// lane l owns channels 4l..4l+3, head h = l/2.
+// ------------------------------------------------------------------------------------------
+struct AggArgs {
+    const float* attn;        // [16][B][T][32][32]
+    const int* notpad;        // [B*T]
+    const unsigned char* keep_mask;   // optional explicit dropout keep mask [16][B][T][H][W] (tests), else Philox
+    unsigned long long seed, offset;
+    float drop_p;             // 0 => no dropout (eval)
+    int B, T, H, W;
+};
+
+// attention weight of (head h, frame b,t) at pixels (y, x0..x0+3)
+__device__ __forceinline__ void agg_weights(const AggArgs& a, int h, int b, int t, int y, int x0, float (&w)[4]) {
+    const float* src = a.attn + (((size_t)h * a.B + b) * a.T + t) * (UB_LOW * UB_LOW);
+    const float inv_sy = (float)UB_LOW / (float)a.H, inv_sx = (float)UB_LOW / (float)a.W;
+    int y0, y1; float ly;
+    bilinear_tap(y, inv_sy, UB_LOW, y0, y1, ly);
+    const float scale = a.notpad[b * a.T + t] ? 1.0f : 0.0f;
+    const size_t lin = ((((size_t)h * a.B + b) * a.T + t) * a.H + y) * a.W + x0;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    const bool philox = a.drop_p > 0.f && a.keep_mask == nullptr;
+    if (philox) {
+        const unsigned long long blk = (lin >> 2) + a.offset;
+        rnd = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u),
+                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+    }
+    const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int xa, xb; float lx;
+        bilinear_tap(x0 + i, inv_sx, UB_LOW, xa, xb, lx);
+        const float top = src[y0 * UB_LOW + xa] * (1.f - lx) + src[y0 * UB_LOW + xb] * lx;
+        const float bot = src[y1 * UB_LOW + xa] * (1.f - lx) + src[y1 * UB_LOW + xb] * lx;
+        float v = top * (1.f - ly) + bot * ly;
+        if (a.drop_p > 0.f) {
+            float keep;
+            if (philox) keep = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f)) >= a.drop_p ? 1.f : 0.f;
+            else keep = a.keep_mask[lin + i] ? 1.f : 0.f;
+            v = v * keep / (1.f - a.drop_p);
+        }
+        w[i] = v * scale;
+    }
+}
+
+__global__ void __launch_bounds__(256) aggregate_fwd_kernel(AggArgs a, const float* __restrict__ x /* [B*T][P][128] */,
+                                                             float* __restrict__ out /* [B][P][128] */, double* out_stats,
+                                                             int groups_per_block) {
+    constexpr int C = UB_WIDTH;
+    __shared__ __align__(16) float smem[2 * 8 * C];
+    const int b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
+    const int P = a.H * a.W;
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    const int g0 = blockIdx.x * groups_per_block;
+    for (int g = g0 + warp; g < g0 + groups_per_block && g * 4 < P; g += 8) {
+        const int p = g * 4, y = p / a.W, x0 = p % a.W;
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0, 0, 0, 0);
+        for (int t = 0; t < a.T; ++t) {
+            float w[4];
+            agg_weights(a, h, b, t, y, x0, w);
+            const float* xr = x + (((size_t)(b * a.T + t)) * P + p) * C + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = ld4_stream(xr + (size_t)i * C);
+                acc[i].x = fmaf(w[i], v.x, acc[i].x); acc[i].y = fmaf(w[i], v.y, acc[i].y);
+                acc[i].z = fmaf(w[i], v.z, acc[i].z); acc[i].w = fmaf(w[i], v.w, acc[i].w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            st4(out + ((size_t)b * P + p + i) * C + lane * 4, acc[i]);
+            s.x += acc[i].x; s.y += acc[i].y; s.z += acc[i].z; s.w += acc[i].w;
+            q.x += acc[i].x * acc[i].x; q.y += acc[i].y * acc[i].y; q.z += acc[i].z * acc[i].z; q.w += acc[i].w * acc[i].w;
+        }
+    }
+    // block reduce (c4 = lane, row = warp) -> per-(b, c) sums for the first decoder PreNorm
+    float4* sa = reinterpret_cast<float4*>(smem);
+    sa[warp * 32 + lane] = s;
+    sa[256 + warp * 32 + lane] = q;
+    __syncthreads();
+    {
+        const int which = threadIdx.x / C, ch = threadIdx.x % C;
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += (double)smem[which * 8 * C + r * C + ch];
+        atomicAdd(&out_stats[((size_t)b * C + ch) * 2 + which], t);
+    }
+}
+
+// backward A: dEnc[b,t,p,c] = w[h,b,t,p] * dAgg[b,p,c];  dwup[h,b,t,p] = d(upsampled attention)
+__global__ void __launch_bounds__(256) aggregate_bwd_kernel(AggArgs a, const float* __restrict__ x, const float* __restrict__ dagg,
+                                                             float* __restrict__ denc, float* __restrict__ dwup /* [16][B][T][P] */,
+                                                             int groups_per_block) {
+    constexpr int C = UB_WIDTH;
+    const int b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
+    const int P = a.H * a.W;
+    const int g0 = blockIdx.x * groups_per_block;
+    for (int g = g0 + warp; g < g0 + groups_per_block && g * 4 < P; g += 8) {
+        const int p = g * 4, y = p / a.W, x0 = p % a.W;
+        float4 d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = ld4_stream(dagg + ((size_t)b * P + p + i) * C + lane * 4);
+        for (int t = 0; t < a.T; ++t) {
+            float w[4], one[4];
+            agg_weights(a, h, b, t, y, x0, w);
+            // d(weight)/d(upsampled attention) = keep/(1-p) * notpad: evaluate the same chain on attn == 1
+            const size_t fr = ((size_t)(b * a.T + t)) * P + p;
+            float dots[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = ld4_stream(x + (fr + i) * C + lane * 4);
+                st4(denc + (fr + i) * C + lane * 4, make_float4(w[i] * d[i].x, w[i] * d[i].y, w[i] * d[i].z, w[i] * d[i].w));
+                float dot = d[i].x * v.x + d[i].y * v.y + d[i].z * v.z + d[i].w * v.w;
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                dots[i] = dot;
+            }
+            if ((lane & 1) == 0) {
+                const float scale = a.notpad[b * a.T + t] ? 1.0f : 0.0f;
+                const size_t lin = ((((size_t)h * a.B + b) * a.T + t) * a.H + y) * a.W + x0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float k = scale;
+                    if (a.drop_p > 0.f) {
+                        float keep;
+                        if (a.keep_mask) keep = a.keep_mask[lin + i] ? 1.f : 0.f;
+                        else keep = dropout_keep(a.seed, a.offset, lin + i, a.drop_p);
+                        k = k * keep / (1.f - a.drop_p);
+                    }
+                    one[i] = k;
+                }
+                st4(dwup + lin, make_float4(dots[0] * one[0], dots[1] * one[1], dots[2] * one[2], dots[3] * one[3]));
+            }
+        }
+    }
+}
+
+// backward B: adjoint of the bilinear upsampling, gather form (deterministic, no atomics):
+// dattn[h,b,t,Y,X] = sum over the footprint of cell (Y,X) of tapweight * dwup[h,b,t,y,x]
+__global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __restrict__ dwup, float* __restrict__ dattn,
+                                                                int H, int W, int total_cells) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= total_cells) return;
+    const int X = cell % UB_LOW, Y = (cell / UB_LOW) % UB_LOW;
+    const size_t img = (size_t)(cell / (UB_LOW * UB_LOW));
+    const int sy = H / UB_LOW, sx = W / UB_LOW;
+    const float inv_sy = (float)UB_LOW / (float)H, inv_sx = (float)UB_LOW / (float)W;
+    const int ya = max(0, (Y - 1) * sy + sy / 2 - 1), yb = min(H - 1, (Y + 1) * sy + sy / 2);
+    const int xa = max(0, (X - 1) * sx + sx / 2 - 1), xb = min(W - 1, (X + 1) * sx + sx / 2);
+    const float* src = dwup + img * H * W;
+    float acc = 0.f;
+    for (int y = ya; y <= yb; ++y) {
+        int y0, y1; float ly;
+        bilinear_tap(y, inv_sy, UB_LOW, y0, y1, ly);
+        const float wy = (y0 == Y ? 1.f - ly : 0.f) + (y1 == Y ? ly : 0.f);
+        if (wy == 0.f) continue;
+        float rowacc = 0.f;
+        for (int x = xa; x <= xb; ++x) {
+            int x0, x1; float lx;
+            bilinear_tap(x, inv_sx, UB_LOW, x0, x1, lx);
+            const float wx = (x0 == X ? 1.f - lx : 0.f) + (x1 == X ? lx : 0.f);
+            rowacc = fmaf(wx, src[(size_t)y * W + x], rowacc);
+        }
+        acc = fmaf(wy, rowacc, acc);
+    }
+    dattn[cell] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_maxpool_fwd(const float* x, float* pooled, int* idx, int N, int H, int W, cudaStream_t st) {
+    if (H % UB_LOW || W % UB_LOW) return UB_ERR_ARG;
+    maxpool_fwd_kernel<<<dim3(UB_LOW * UB_LOW, N), 128, 0, st>>>(x, pooled, idx, H, W);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_maxpool_bwd(const float* dpooled, const int* idx, float* denc, int N, int HW, cudaStream_t st) {
+    maxpool_bwd_kernel<<<dim3(UB_LOW * UB_LOW, N), 128, 0, st>>>(dpooled, idx, denc, HW);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+#define UB_DISPATCH_T(T_, ...)                     \
+    switch (T_) {                                  \
+        case 1: { constexpr int TT = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int TT = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int TT = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int TT = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int TT = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int TT = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int TT = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int TT = 8; __VA_ARGS__; } break; \
+        default: return UB_ERR_ARG;                \
+    }
+
+int launch_ltae_fwd(const float* pooled, const float* Ap, const float* e, const int* notpad, float* attn, int B, int T,
+                    float eps, cudaStream_t st) {
+    const int npix = B * UB_LOW * UB_LOW;
+    UB_DISPATCH_T(T, (ltae_fwd_kernel<TT><<<(npix + 7) / 8, 256, 0, st>>>(pooled, Ap, e, notpad, attn, B, eps)));
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_ltae_bwd(const float* pooled, const float* Ap, const float* attn, const float* dattn, float* dpooled, float* dAp,
+                    float* de, int B, int T, float eps, cudaStream_t st) {
+    const int npix = B * UB_LOW * UB_LOW;
+    const int ppw = 8;
+    const int blocks = (npix + 8 * ppw - 1) / (8 * ppw);
+    UB_DISPATCH_T(T, (ltae_bwd_kernel<TT><<<blocks, 256, 0, st>>>(pooled, Ap, attn, dattn, dpooled, dAp, de, B, eps, ppw)));
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+static AggArgs make_agg(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
+                        unsigned long long offset, float drop_p, int B, int T, int H, int W) {
+    AggArgs a;
+    a.attn = attn; a.notpad = notpad; a.keep_mask = keep_mask; a.seed = seed; a.offset = offset; a.drop_p = drop_p;
+    a.B = B; a.T = T; a.H = H; a.W = W;
+    return a;
+}
+int launch_aggregate_fwd(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
+                         unsigned long long offset, float drop_p, const float* x, float* out, double* out_stats, int B,
+                         int T, int H, int W, cudaStream_t st) {
+    if (W % 4) return UB_ERR_ARG;
+    const int groups = H * W / 4, gpb = 128;
+    aggregate_fwd_kernel<<<dim3((groups + gpb - 1) / gpb, B), 256, 0, st>>>(
+        make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W), x, out, out_stats, gpb);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_aggregate_bwd(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
+                         unsigned long long offset, float drop_p, const float* x, const float* dagg, float* denc,
+                         float* dwup, float* dattn, int B, int T, int H, int W, cudaStream_t st) {
+    if (W % 4) return UB_ERR_ARG;
+    const int groups = H * W / 4, gpb = 128;
+    aggregate_bwd_kernel<<<dim3((groups + gpb - 1) / gpb, B), 256, 0, st>>>(
+        make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W), x, dagg, denc, dwup, gpb);
+    UB_CHECK_LAUNCH();
+    const int cells = UB_HEADS * B * T * UB_LOW * UB_LOW;
+    upsample_adjoint_kernel<<<(cells + 255) / 256, 256, 0, st>>>(dwup, dattn, H, W, cells);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+}  // namespace ub

@@ -1,0 +1,136 @@
+"""MGNLL loss on the B200 path, with the reference's call surface.
+
+Mirrors model/src/losses.py: ``get_loss(config)`` (:14-32), ``calc_loss(criterion, config, out, y, var)`` (:35-43),
+``MultiGaussianNLLLoss(*, full, eps, reduction, mode, chunk)(input, target, var) -> (loss, variance)`` (:288-354).
+
+* ``loss`` is a 0-d CUDA tensor with autograd (one fused kernel computes the loss and both gradients).
+* ``variance`` is diag_embed(max(var, eps)) of shape [B,1,13,13,H,W] (losses.py:145,211).  The reference
+  builds it on the CPU (a 44 MB/sample D2H copy inside the loss); here it is a tensor on the loss's device,
+  built by one kernel, and ``covariance='none'`` skips it.  Callers only use ``.cpu()``, scalar multiply,
+  ``.diagonal``, ``.mean`` and indexing on it (base_model.py:112-113,131; train_reconstruct.py:185-191,324-352),
+  all of which work unchanged.
+* ``var`` with a negative entry raises ``ValueError`` like the reference (:199-200); the check costs a host sync,
+  ``check_negative=False`` defers it away.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+S2_BANDS = 13
+
+
+def _plane_view(t: torch.Tensor):
+    """(tensor, batch stride in elements) with a contiguous [C,H,W] block per sample, without copying slices
+    of the network output (base_model.py:83 passes fake_B[:, :, :13] and fake_B[:, :, 13:26])."""
+    B, one, Cc, H, W = t.shape
+    if t.stride(4) == 1 and t.stride(3) == W and t.stride(2) == H * W:
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, t.stride(0)
+
+
+class _MGNLLFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, var, eps, check_negative):
+        L = _lib.lib()
+        B, _, C, H, W = pred.shape
+        P = H * W
+        var_ch = var.shape[2]
+        pred_v, pred_sb = _plane_view(pred)
+        targ_v, targ_sb = _plane_view(target)
+        var_v, var_sb = _plane_view(var)
+        dev = pred.device
+        need_grad = pred.requires_grad or var.requires_grad
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        scratch = torch.empty(4, dtype=torch.float64, device=dev)   # 16 B accumulators + the int flag
+        flag = scratch[2:].view(torch.int32)[:1]
+        dpred = torch.empty((B, 1, S2_BANDS, H, W), dtype=torch.float32, device=dev) if need_grad else None
+        dvar = torch.empty((B, 1, var_ch, H, W), dtype=torch.float32, device=dev) if need_grad else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.ub200_mgnll_forward(pred_v.data_ptr(), pred_sb, targ_v.data_ptr(), targ_sb, var_v.data_ptr(), var_sb,
+                                         var_ch, B, P, float(eps), loss.data_ptr(),
+                                         dpred.data_ptr() if need_grad else None, dvar.data_ptr() if need_grad else None,
+                                         flag.data_ptr(), scratch.data_ptr(), stream), "ub200_mgnll_forward")
+        if check_negative and int(flag.item()) != 0:
+            raise ValueError("var has negative entry/entries")
+        if need_grad:
+            ctx.save_for_backward(dpred, dvar)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        dpred, dvar = ctx.saved_tensors
+        g = g.contiguous().float()
+        stream = torch.cuda.current_stream(dpred.device).cuda_stream
+        gp, gv = torch.empty_like(dpred), torch.empty_like(dvar)
+        _lib.check(L.ub200_scale_by_scalar(dpred.data_ptr(), g.data_ptr(), gp.data_ptr(), dpred.numel(), stream), "scale")
+        _lib.check(L.ub200_scale_by_scalar(dvar.data_ptr(), g.data_ptr(), gv.data_ptr(), dvar.numel(), stream), "scale")
+        return gp, None, gv, None, None
+
+
+def covariance_diag(var: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """diag_embed(max(var, eps)) -> [B,1,13,13,H,W] on var's device (losses.py:145,211)."""
+    L = _lib.lib()
+    B, _, var_ch, H, W = var.shape
+    var_v, var_sb = _plane_view(var.detach())
+    cov = torch.empty((B, 1, S2_BANDS, S2_BANDS, H, W), dtype=torch.float32, device=var.device)
+    stream = torch.cuda.current_stream(var.device).cuda_stream
+    _lib.check(L.ub200_covariance(var_v.data_ptr(), var_sb, var_ch, B, H * W, float(eps), cov.data_ptr(), stream),
+               "ub200_covariance")
+    return cov
+
+
+def multi_gaussian_nll_loss(input, target, var, full=False, eps=1e-8, reduction="mean", mode="diag", chunk=None,
+                            covariance="dense", check_negative=True):
+    """multi_gaussian_nll_loss (losses.py:149-218).  ``full`` and ``chunk`` are accepted and ignored, as in the
+    reference (the constant is always included, :143)."""
+    if reduction != "none" and reduction != "mean" and reduction != "sum":
+        raise ValueError(reduction + " is not valid")
+    if reduction != "mean":
+        raise NotImplementedError("B200 path: only reduction='mean' (what get_loss builds, losses.py:19) is implemented")
+    if mode not in ("iso", "diag"):
+        raise NotImplementedError("B200 path: covmode must be 'iso' or 'diag' for MGNLL")
+    if not input.is_cuda:
+        raise RuntimeError("uncrtaints_b200 MGNLL runs on CUDA tensors only (no CPU fallback)")
+    if input.dim() != 5 or input.shape[2] != S2_BANDS or var.shape[2] not in (1, S2_BANDS):
+        raise NotImplementedError("B200 path: expects [B,1,13,H,W] predictions and [B,1,13|1,H,W] variances")
+    loss = _MGNLLFunction.apply(input.float(), target.float(), var.float(), eps, check_negative)
+    variance = covariance_diag(var, eps) if covariance == "dense" else None
+    return loss, variance
+
+
+class MultiGaussianNLLLoss(nn.Module):
+    """Same constructor / call as the reference class (losses.py:288-354)."""
+
+    def __init__(self, *, full: bool = False, eps: float = 1e-8, reduction: str = "mean", mode: str = "diag", chunk=None,
+                 covariance: str = "dense", check_negative: bool = True) -> None:
+        super().__init__()
+        self.full, self.eps, self.reduction, self.mode, self.chunk = full, eps, reduction, mode, chunk
+        self.covariance, self.check_negative = covariance, check_negative
+
+    def forward(self, input, target, var):
+        return multi_gaussian_nll_loss(input, target, var, full=self.full, eps=self.eps, reduction=self.reduction,
+                                       mode=self.mode, chunk=self.chunk, covariance=self.covariance,
+                                       check_negative=self.check_negative)
+
+
+def get_loss(config):
+    """losses.get_loss (losses.py:14-32) for the MGNLL branch; other losses are outside the hot path."""
+    if config.loss != "MGNLL":
+        raise NotImplementedError("B200 path builds the MGNLL loss only; use the reference's losses for " + str(config.loss))
+    criterion1 = MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=config.covmode,
+                                      chunk=getattr(config, "chunk_size", None))
+    return lambda pred, targ, var: criterion1(pred, targ, var)
+
+
+def calc_loss(criterion, config, out, y, var=None):
+    """losses.calc_loss (losses.py:35-43)."""
+    if config.loss in ["GNLL", "MGNLL"]:
+        loss, variance = criterion(out, y, var)
+    else:
+        loss, variance = criterion(out, y), None
+    return loss, variance
