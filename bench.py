@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the UnCRtainTS hot path (forward + MGNLL + backward) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (oracle port), host cores
+
+Metric (BASELINE.json): samples/s for netG.forward + MGNLL + backward (+ one gradient all-reduce when N > 1) on
+synthetic (B, T=3, 15, 256, 256) input, train mode, fp32 -- BASELINE config #2 (1xB200, batch 16) at N=1 and the
+same per-GPU batch on every rank at N>1 (weak scaling, batch sharded by sample).
+One step = one pass of the hot path over one batch.  The optimizer step is outside the metric.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same through
+the public API with pinned-host inputs copied H2D and the loss read back D2H every step; `roofline` = the dominant
+kernel class, timed with CUDA events on the launch stream inside the timed region, against MEASURED_PEAKS.json;
+`cpu_baseline` = the oracle (port of the reference, fused torch CPU ops) on a bounded sample on the host cores.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+P_FULL = 256 * 256
+METRIC = "samples/sec fwd+bwd (T=3, 15x256x256)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE config #2: 16)")
+    ap.add_argument("--t", type=int, default=3)
+    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--covmode", default="diag")
+    ap.add_argument("--backend", type=int, default=None, help="0 = fp32 CUDA-core GEMMs, 1 = tcgen05 bf16x3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def synthetic(b, t, hw, seed=1234, scale_by=10.0):
+    """SURVEY.md §8d synthetic inputs: x = scale_by*U[0,1), y likewise, dates = sorted integer days in [1400,1900]."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    x = scale_by * torch.rand(b, t, 15, hw, hw, generator=g)
+    y = scale_by * torch.rand(b, 1, 13, hw, hw, generator=g)
+    d = torch.sort(torch.randint(1400, 1901, (b, t), generator=g), dim=1).values.float()
+    return x, y, d
+
+
+def init_like_reference(net, seed=1):
+    """Random init with the distributions of the reference's weight_init (learning/weight_init.py:13-47)."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, nn.Conv1d):
+            nn.init.normal_(m.weight, 0, 1.0); nn.init.normal_(m.bias, 0, 1.0)
+        elif isinstance(m, nn.Conv2d):
+            nn.init.xavier_normal_(m.weight, gain=1.0)
+            if m.bias is not None:
+                nn.init.normal_(m.bias, 0, 1.0)
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.normal_(m.weight, 0, 1.0); nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.Linear):
+            nn.init.xavier_normal_(m.weight, gain=1.0)
+            if m.bias is not None:
+                nn.init.normal_(m.bias, 0, 1.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def algorithmic_bytes(kernel, frames, P):
+    """algorithmic HBM bytes of one launch over `frames` frames (fp32; A = 128 ch, Hh = 256 ch per pixel)."""
+    A, Hh = 128 * P * 4, 256 * P * 4
+    per_frame = {
+        "gemm1_fwd": A + Hh, "dwconv_fwd": 2 * Hh, "se_pool": Hh, "gemm2_fwd": Hh + A, "residual_fwd": 3 * A,
+        "norm_bwd_stats": 2 * A, "gemm2_bwd": 2 * A + 2 * Hh, "wgrad2": 2 * A + Hh, "dwconv_bwd": 4 * Hh,
+        "gemm1_bwd": 2 * Hh + 2 * A, "wgrad1": A + 2 * Hh, "residual_bwd": 4 * A,
+    }
+    return per_frame.get(kernel, 0) * frames
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_arm(args, steps, warmup, batch):
+    """The reference's CPU path: oracle port (FUSED torch CPU ops = the ATen/oneDNN kernels the reference's modules
+    dispatch to), all host threads, each step a bounded sample of `batch` samples of the same workload."""
+    from oracle import uncrtaints_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O.set_fused(True)
+    cfg = O.OracleConfig(covmode=args.covmode)
+    p = O.init_params(cfg, seed=1)
+    x, y, d = O.synthetic_batch(batch, args.t, args.hw, args.hw, seed=1234)
+    keep = O.dropout_keep_mask(16, batch, args.t, args.hw, args.hw)
+    for _ in range(warmup):
+        O.step(p, x, y, d, cfg, True, keep)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.step(p, x, y, d, cfg, True, keep)
+    dt = time.perf_counter() - t0
+    O.set_fused(False)
+    return {"value": batch * steps / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of B={batch}, T={args.t}, 15x{args.hw}x{args.hw}, fp32, train mode, "
+                      f"fwd+MGNLL+bwd, {cores} host threads (torch CPU / oneDNN)", "ms_per_step": 1e3 * dt / steps}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"BASELINE config #2: uncrtaints --input_t {args.t} --n_head 16 --block_type mbconv --covmode "
+                          f"{args.covmode}, per-GPU batch {args.batch}, synthetic 15x{args.hw}x{args.hw}, fwd+MGNLL+bwd, train mode",
+              "per_gpu_batch": args.batch, "global_batch": args.batch * world, "T": args.t,
+              "parallelism": f"dp{world} (batch sharded by sample, one NCCL all-reduce of the flat 2.28 MB gradient)",
+              "l2_note": "per-step working set (>= 10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_arm(args, max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample_batch)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": 0,
+                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    import uncrtaints_b200 as ub
+    from uncrtaints_b200 import _lib
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device for the product arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    L = _lib.lib()
+
+    cov = {"diag": 13, "iso": 1}[args.covmode]
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[13 + cov], out_nonlin_mean=True, out_nonlin_var="softplus",
+                        covmode=args.covmode, scale_by=10.0, gemm_backend=args.backend)
+    init_like_reference(net, seed=1)
+    net = net.to(dev).train()
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=args.covmode, chunk=None)
+    bucket = ub.FlatGradAllReduce(net.parameters())
+
+    # rank r owns samples [r*B, (r+1)*B) of the global batch (weak scaling: fixed per-GPU batch)
+    xh, yh, dh = synthetic(args.batch, args.t, args.hw, seed=1234 + rank)
+    xh, yh, dh = xh.pin_memory(), yh.pin_memory(), dh.pin_memory()
+    x, y, d = xh.to(dev), yh.to(dev), dh.to(dev)
+
+    def step(xi, yi, di):
+        bucket.zero_()
+        out = net(xi, batch_positions=di)
+        loss, _ = crit(out[:, :, :net.mean_idx], yi, out[:, :, net.mean_idx:net.vars_idx])
+        loss.backward()
+        bucket.all_reduce_mean()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up; the last warm-up step records every kernel class to find the dominant one -----------------
+    nk = L.ub200_prof_num_kernels()
+    names = [L.ub200_prof_kernel_name(k).decode() for k in range(nk)]
+    for w in range(max(args.warmup, 3)):
+        if w == max(args.warmup, 3) - 1:
+            L.ub200_prof_enable((1 << nk) - 1)
+        step(x, y, d)
+    torch.cuda.synchronize(dev)
+    import ctypes
+    breakdown = {}
+    for k in range(nk):
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        _lib.check(L.ub200_prof_read(k, ctypes.byref(ms), ctypes.byref(n)), "prof_read")
+        if n.value:
+            breakdown[names[k]] = {"ms": round(ms.value, 4), "launches": n.value}
+    gemm_like = [k for k in breakdown if algorithmic_bytes(k, 1, 1) > 0]
+    top = max(gemm_like, key=lambda k: breakdown[k]["ms"])
+    L.ub200_prof_enable(1 << names.index(top))
+
+    # ---- timed region: device-resident inputs ------------------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = L.ub200_launch_count()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x, y, d)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.ub200_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    tms, tn = ctypes.c_double(), ctypes.c_int()
+    _lib.check(L.ub200_prof_read(names.index(top), ctypes.byref(tms), ctypes.byref(tn)), "prof_read")
+    L.ub200_prof_enable(0)
+
+    # ---- end-to-end: pinned host inputs copied H2D and the loss read back D2H inside the timed region ------
+    xd, yd, dd = torch.empty_like(x), torch.empty_like(y), torch.empty_like(d)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True); yd.copy_(yh, non_blocking=True); dd.copy_(dh, non_blocking=True)
+        return float(step(xd, yd, dd).item())
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        last_loss = e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    samples = args.batch * world * args.steps
+    value = samples / (ms_total / 1e3)
+    peak, peak_src = measured_peaks()
+    # frames per launch of the dominant class: 1 encoder launch over B*T frames + n_dec launches over B frames per step
+    n_dec = len(net.out_block)
+    total_frames = (args.batch * args.t + n_dec * args.batch) * args.steps
+    P = args.hw * args.hw
+    bytes_total = algorithmic_bytes(top, total_frames, P)
+    achieved = bytes_total / (tms.value / 1e3) / 1e9 if tms.value > 0 else 0.0
+    roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches": tn.value, "avg_launch_ms": round(tms.value / max(tn.value, 1), 4),
+                "algorithmic_bytes_per_launch": bytes_total // max(tn.value, 1),
+                "share_of_step": round(tms.value / ms_total, 4),
+                "note": "achieved = algorithmic bytes (DESIGN.md §4) / CUDA-event time of the kernel class inside the timed region"}
+    line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "gemm_backend": int(args.backend if args.backend is not None else ub.backbone._default_backend()),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": round(samples / (e2e_ms / 1e3), 3), "unit": "samples/s", "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "h2d_bytes_per_step": int((xh.numel() + yh.numel() + dh.numel()) * 4), "d2h_bytes_per_step": 4,
+                    "last_loss": last_loss},
+            "roofline": roofline, "kernels_ms_per_step": breakdown}
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_arm(args, 1, 0, args.cpu_sample_batch)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,7 @@ enum {
     UB200_P_IN_NORM_B,     /* in_conv.conv.conv.1.bias   [128]                                      */
     UB200_P_IN_NORM_RM,    /* running_mean (BatchNorm encoder only)                                 */
     UB200_P_IN_NORM_RV,    /* running_var                                                           */
-    UB200_P_LTAE_AP,       /* folded L-TAE score matrix Ap [16][128]   (see uncrtaints_b200/ltae_fold.py) */
+    UB200_P_LTAE_AP,       /* folded L-TAE score matrix Ap [16][128]   (uncrtaints_b200/backbone.py: fold_ltae) */
     UB200_P_LTAE_E,        /* folded additive score term e [B][T][16]                               */
     UB200_P_OUT_W,         /* out_conv.conv.conv.0.weight [out_dim][128]             (uncrtaints.py:381) */
     UB200_P_OUT_B,         /* out_conv.conv.conv.0.bias   [out_dim]                                 */
@@ -93,6 +93,18 @@ typedef struct ub200_desc {
 } ub200_desc;
 
 int ub200_version(void);
+
+/* Number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches). */
+unsigned long long ub200_launch_count(void);
+
+/* Optional per-kernel timing used by bench.py for the roofline line: while bit k of `mask` is set, every launch of
+ * kernel class k inside ub200_forward / ub200_backward is bracketed by CUDA events on the launch stream.
+ * ub200_prof_enable resets the records; ub200_prof_read synchronises the recorded events (host-blocking) and returns
+ * the summed device time and the number of launches of class `kid`. */
+int ub200_prof_enable(unsigned long long mask);
+int ub200_prof_num_kernels(void);
+const char* ub200_prof_kernel_name(int kid);
+int ub200_prof_read(int kid, double* total_ms, int* launches);
 
 /* Number of pointer slots in a params / grads table for this configuration. */
 int ub200_num_param_slots(const ub200_desc* d);

@@ -68,14 +68,29 @@ class OracleConfig:
 # --------------------------------------------------------------------------------------
 # elementary ops
 # --------------------------------------------------------------------------------------
+# FUSED = True routes the elementary ops below through the same torch.nn.functional kernels the reference's
+# nn.Modules dispatch to (oneDNN conv, ATen group/batch norm, ...).  Used for the CPU-baseline timing in bench.py,
+# where the point is to time what the reference executes on the host; tests/test_oracle.py checks FUSED == elementary.
+FUSED = False
+
+
+def set_fused(flag: bool) -> None:
+    global FUSED
+    FUSED = bool(flag)
+
+
 def gelu_erf(x: torch.Tensor) -> torch.Tensor:
     """Exact-erf GELU, nn.GELU() default (uncrtaints.py:88,128,133)."""
+    if FUSED:
+        return F.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
 def group_norm(x: torch.Tensor, groups: int, weight, bias, eps: float = 1e-5) -> torch.Tensor:
     """nn.GroupNorm over [N, C, *]: biased variance per (sample, group)
     (uncrtaints.py:22, utae.py:470-473, ltae.py:191-194)."""
+    if FUSED:
+        return F.group_norm(x, groups, weight, bias, eps)
     n, c = x.shape[:2]
     xg = x.reshape(n, groups, -1)
     mu = xg.mean(dim=2, keepdim=True)
@@ -92,6 +107,8 @@ def batch_norm(x, weight, bias, running_mean, running_var, training: bool,
     stats updated with the *unbiased* var.  Eval: running stats.  Buffer updates are
     returned through ``new_buffers`` (the oracle is functional)."""
     shape = [1, -1, 1, 1]
+    if FUSED and new_buffers is None:
+        return F.batch_norm(x, running_mean.clone(), running_var.clone(), weight, bias, training, momentum, eps)
     if training:
         mu = x.mean(dim=(0, 2, 3))
         var = ((x - mu.reshape(shape)) ** 2).mean(dim=(0, 2, 3))
@@ -116,6 +133,8 @@ def reflect_pad1(x: torch.Tensor) -> torch.Tensor:
 def depthwise3x3_reflect(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """groups=C 3x3 cross-correlation, stride 1, reflect padding, no bias
     (uncrtaints.py:130-131).  w: [C,1,3,3]."""
+    if FUSED:
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, groups=x.shape[1])
     xp = reflect_pad1(x)
     h, wd = x.shape[-2:]
     out = torch.zeros_like(x)
@@ -127,6 +146,8 @@ def depthwise3x3_reflect(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 
 def conv1x1(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Conv2d(k=1): per-pixel matmul.  w: [Cout, Cin, 1, 1]."""
+    if FUSED:
+        return F.conv2d(x, w, b)
     out = torch.einsum("nchw,oc->nohw", x, w[:, :, 0, 0])
     if b is not None:
         out = out + b.reshape(1, -1, 1, 1)
@@ -137,6 +158,8 @@ def adaptive_max_pool(x: torch.Tensor, out_hw: int = ATT_DOWN) -> Tuple[torch.Te
     """nn.AdaptiveMaxPool2d((32,32)) for H,W multiples of 32 (uncrtaints.py:403-404).
     Returns values and flat (h*W + w) int64 argmax with the *first* maximum in row-major
     window order."""
+    if FUSED:
+        return F.adaptive_max_pool2d(x, (out_hw, out_hw), return_indices=True)
     n, c, h, w = x.shape
     assert h % out_hw == 0 and w % out_hw == 0
     kh, kw = h // out_hw, w // out_hw
@@ -166,6 +189,10 @@ def bilinear_weights(out_size: int, in_size: int, dtype) -> Tuple[torch.Tensor, 
 
 def bilinear_upsample(a: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     """[..., h, w] -> [..., out_h, out_w], separable 4-tap lerp."""
+    if FUSED:
+        lead = a.shape[:-2]
+        up = F.interpolate(a.reshape(-1, 1, *a.shape[-2:]), size=(out_h, out_w), mode="bilinear", align_corners=False)
+        return up.reshape(*lead, out_h, out_w)
     y0, y1, ly = bilinear_weights(out_h, a.shape[-2], a.dtype)
     x0, x1, lx = bilinear_weights(out_w, a.shape[-1], a.dtype)
     rows = a[..., y0, :] * (1 - ly).reshape(-1, 1) + a[..., y1, :] * ly.reshape(-1, 1)

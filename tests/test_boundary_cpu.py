@@ -1,0 +1,114 @@
+"""CPU-side tests of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+the Python shim reproduces the reference's constructor / state-dict surface, and nothing falls back to the CPU."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN
+
+
+def test_library_exports_every_declared_symbol():
+    from uncrtaints_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "uncrtaints_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ub200_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    assert sorted(_lib.SYMBOLS) == declared
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert _lib.lib().ub200_version() >= 100
+
+
+def test_desc_struct_and_workspace_query_without_gpu():
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Desc()
+    d.B, d.T, d.C_in, d.H, d.W, d.n_dec_blocks, d.out_dim, d.need_grad = 16, 3, 15, 256, 256, 5, 26, 1
+    n = L.ub200_workspace_bytes(d)
+    assert 30e9 < n < 60e9                      # ~40 GB of saved activations + scratch at BASELINE config #2
+    assert L.ub200_num_param_slots(d) == _lib.UB200_P_BLOCK0 + 6 * _lib.UB200_BLOCK_STRIDE
+    d.H = 250                                   # not a multiple of 32 -> unsupported
+    assert L.ub200_workspace_bytes(d) == 0
+    d.H, d.T = 256, 9                           # T > 8 -> unsupported
+    assert L.ub200_workspace_bytes(d) == 0
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    d.T = 3
+    assert L.ub200_workspace_tap(d, b"blk3.h2", ctypes.byref(off), ctypes.byref(nb)) == 0
+    assert nb.value == 16 * 65536 * 256 * 4
+    assert L.ub200_workspace_tap(d, b"nonsense", ctypes.byref(off), ctypes.byref(nb)) == -1
+
+
+def test_state_dict_surface_matches_reference():
+    import uncrtaints_b200 as ub
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", covmode="diag", scale_by=10.0)
+    got = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert list(got.keys()) == list(want.keys())
+    assert got == want
+    assert sum(p.numel() for p in net.parameters()) == 570010
+    assert (net.mean_idx, net.vars_idx, net.variance) == (13, 26, None)
+    iso = ub.UNCRTAINTS(input_dim=15, out_conv=[14], out_nonlin_mean=True, out_nonlin_var="softplus", covmode="iso", scale_by=10.0)
+    assert (iso.mean_idx, iso.vars_idx) == (13, 14)
+    # weight_init dispatches on isinstance (learning/weight_init.py:13-47): the holders must be the real nn types
+    kinds = {type(m).__name__ for m in net.modules()}
+    assert {"Conv2d", "Conv1d", "Linear", "GroupNorm", "BatchNorm2d"} <= kinds
+
+
+def test_unsupported_configurations_raise():
+    import uncrtaints_b200 as ub
+    kw = dict(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
+    for bad in (dict(block_type="residual"), dict(use_v=True), dict(is_mono=True), dict(n_head=4), dict(encoder_widths=[64]),
+                dict(agg_mode="mean"), dict(out_nonlin_var="relu"), dict(out_conv=[13])):
+        with pytest.raises(NotImplementedError):
+            ub.UNCRTAINTS(**{**kw, **bad})
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    import uncrtaints_b200 as ub
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 2, 15, 32, 32), batch_positions=torch.zeros(1, 2))
+    p = torch.rand(1, 1, 13, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ub.MultiGaussianNLLLoss(mode="diag", chunk=None)(p, p, p + 1)
+    with pytest.raises(ValueError, match="is not valid"):
+        ub.MultiGaussianNLLLoss(mode="diag", chunk=None, reduction="bogus")(p, p, p + 1)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "uncrtaints_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no oracle", ""), fn
+
+
+def test_ltae_fold_is_exact_in_fp64(golden_weights):
+    """Ap / e folding (uncrtaints_b200/backbone.py:fold_ltae) reproduces the reference score chain."""
+    import uncrtaints_b200 as ub
+    from oracle import uncrtaints_oracle as O
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
+    net.load_state_dict(golden_weights)
+    net = net.double()
+    with torch.no_grad():
+        net.temporal_encoder.in_norm.weight.mul_(1.3).add_(0.1)
+        net.temporal_encoder.in_norm.bias.add_(0.2)
+    B, T = 2, 3
+    g = torch.Generator().manual_seed(0)
+    down = torch.randn(B, T, 128, 32, 32, generator=g, dtype=torch.float64)
+    dates = torch.tensor([[1400., 1500., 1890.], [1411., 1412., 1700.]], dtype=torch.float64)
+    pad = torch.tensor([[False, False, True], [False, False, False]])
+    p = {k: v for k, v in net.state_dict().items()}
+    ref = O.ltae_tiny(down, dates, pad, p, O.OracleConfig())                     # [16,B,T,32,32]
+    ap, e = ub.backbone.fold_ltae(net.temporal_encoder, dates, B, T, "cpu")
+    seq = down.permute(0, 3, 4, 2, 1).reshape(B * 1024, 128, T)
+    xg = seq.reshape(B * 1024, 16, -1)
+    xh = ((xg - xg.mean(2, keepdim=True)) / torch.sqrt(xg.var(2, unbiased=False, keepdim=True) + 1e-5)).reshape(seq.shape)
+    score = 0.5 * (torch.einsum("hc,nct->nht", ap, xh) + e.double().permute(0, 2, 1).repeat_interleave(1024, 0))
+    score = score.masked_fill(pad.reshape(B, 1, T).repeat_interleave(1024, 0), -1e3)
+    mine = torch.softmax(score, -1).reshape(B, 32, 32, 16, T).permute(3, 0, 4, 1, 2)
+    assert float((mine - ref).abs().max()) < 1e-9

@@ -1,0 +1,313 @@
+"""GPU parity tests (run on the B200 with ``pytest -m gpu``): the CUDA path, called through the C ABI by the
+Python shim, against (a) the committed golden vectors generated from the unmodified reference and (b) the CPU
+oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): floating point within 1e-3 relative (rel-L2 per tensor) in fp32;
+pad mask and max-pool argmax bit-exact.  Gradients that are analytically zero in the reference are compared
+with an absolute tolerance.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz, rel_l2, is_zero_grad_param, report
+from oracle import uncrtaints_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def make_net(weights, covmode="diag", backend=None):
+    import uncrtaints_b200 as ub
+    cov = {"diag": 13, "iso": 1}[covmode]
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[13 + cov], out_nonlin_mean=True, out_nonlin_var="softplus",
+                        covmode=covmode, scale_by=10.0, gemm_backend=backend)
+    sd = {k: v.clone() for k, v in weights.items()}
+    sd["out_conv.conv.conv.0.weight"] = sd["out_conv.conv.conv.0.weight"][:13 + cov]
+    sd["out_conv.conv.conv.0.bias"] = sd["out_conv.conv.conv.0.bias"][:13 + cov]
+    net.load_state_dict(sd, strict=True)
+    return net.cuda()
+
+
+def tap(net, name, shape_nhwc, dtype=torch.float32):
+    """Read a named intermediate out of the workspace of the last forward call."""
+    from uncrtaints_b200 import _lib
+    desc, ws = net._last_workspace
+    off, nbytes = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(_lib.lib().ub200_workspace_tap(desc, name.encode(), ctypes.byref(off), ctypes.byref(nbytes)), "tap")
+    raw = ws[off.value:off.value + nbytes.value]
+    return raw.view(dtype).reshape(shape_nhwc)
+
+
+def check_grads(named_params, ref_grads, tag, tol=TOL):
+    lines, bad = [], []
+    scale = max(float(torch.as_tensor(g).double().norm()) for g in ref_grads.values())
+    for k, p in named_params:
+        ref = torch.as_tensor(ref_grads[k])
+        g = p.grad
+        assert g is not None, k
+        if is_zero_grad_param(k):
+            err = float(g.double().norm().cpu())
+            ok = err <= 1e-3 * max(float(ref.double().norm()), 1e-6 * scale) or err <= 1e-6 * scale
+            lines.append(f"{tag} zero-grad {k}: |g|={err:.3e} (ref {float(ref.double().norm()):.3e}) {'ok' if ok else 'FAIL'}")
+        else:
+            err = rel_l2(g, ref)
+            ok = err <= tol
+            lines.append(f"{tag} grad {k}: rel_l2={err:.3e} {'ok' if ok else 'FAIL'}")
+        if not ok:
+            bad.append(k)
+    report("parity_report.txt", lines)
+    assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
+
+
+@pytest.mark.parametrize("backend", [0])
+def test_golden_diag_train_pad(golden_weights, backend):
+    import uncrtaints_b200 as ub
+    c = load_npz("case_diag_train_pad.npz")
+    x, y, d = (torch.from_numpy(c[k]).cuda() for k in ("x", "y", "dates"))
+    B, T, _, H, W = x.shape
+    keep = torch.from_numpy(np.unpackbits(c["keep"])[:16 * B * T * H * W].reshape(16, B, T, H, W))
+    net = make_net(golden_weights, "diag", backend).train()
+    net._injected_keep_mask = keep
+    out = net(x, batch_positions=d)
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None)
+    loss, cov = crit(out[:, :, :13], y, out[:, :, 13:26])
+    loss.backward()
+    torch.cuda.synchronize()
+    lines = [f"golden_diag backend={backend} out rel_l2={rel_l2(out, torch.from_numpy(c['out'])):.3e}",
+             f"golden_diag loss={loss.item():.6f} ref={float(c['loss']):.6f}"]
+    report("parity_report.txt", lines)
+    # bit-exact items
+    notpad = tap(net, "notpad", (B, T), torch.int32).cpu()
+    assert torch.equal(notpad == 0, torch.from_numpy(c["pad_mask"]))
+    idx = tap(net, "pool_idx", (B * T, 32, 32, 128), torch.int32).permute(0, 3, 1, 2).cpu()
+    # bit-exact index semantics: on the SAME fp32 encoder output, the kernel's argmax (first maximum in row-major
+    # window order) must equal the oracle's / ATen's exactly ...
+    enc = tap(net, "blk0.out", (B * T, H, W, 128)).permute(0, 3, 1, 2).cpu()
+    val, own_idx = O.adaptive_max_pool(enc)
+    assert torch.equal(idx.long(), own_idx), "max-pool argmax must be bit-exact"
+    assert torch.equal(tap(net, "pooled", (B * T, 32, 32, 128)).permute(0, 3, 1, 2).cpu(), val)
+    # ... and against the fp64 golden run only fp32-rounding near-ties may differ
+    gold_idx = torch.from_numpy(c["pool_idx"]).long()
+    assert float((idx.long() != gold_idx).float().mean()) < 1e-4
+    # floating point
+    assert out.shape == (B, 1, 26, H, W)
+    assert rel_l2(out, torch.from_numpy(c["out"])) <= TOL
+    assert abs(loss.item() - float(c["loss"])) / abs(float(c["loss"])) <= TOL
+    assert cov.shape == (B, 1, 13, 13, H, W)
+    ref_cov = O.covariance(torch.from_numpy(c["out"])[:, :, 13:26], "diag")
+    assert rel_l2(cov, ref_cov) <= TOL
+    check_grads(net.named_parameters(), {k[5:]: v for k, v in c.items() if k.startswith("grad.")}, f"golden_diag[b{backend}]")
+    sd = net.state_dict()
+    for k, v in c.items():
+        if k.startswith("buf."):
+            got = sd[k[4:]].double().cpu()
+            assert torch.allclose(got, torch.from_numpy(v).double(), rtol=1e-3, atol=1e-4), k
+
+
+def test_golden_iso_eval(golden_weights):
+    import uncrtaints_b200 as ub
+    c = load_npz("case_iso_eval.npz")
+    x, y, d = (torch.from_numpy(c[k]).cuda() for k in ("x", "y", "dates"))
+    net = make_net(golden_weights, "iso").eval()
+    with torch.no_grad():
+        out = net(x, batch_positions=d)
+        loss, cov = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="iso", chunk=None)(
+            out[:, :, :13], y, out[:, :, 13:14])
+    report("parity_report.txt", [f"golden_iso_eval out rel_l2={rel_l2(out, torch.from_numpy(c['out'])):.3e} "
+                                 f"loss={loss.item():.6f} ref={float(c['loss']):.6f}"])
+    assert out.shape == tuple(c["out"].shape)
+    assert rel_l2(out, torch.from_numpy(c["out"])) <= TOL
+    assert abs(loss.item() - float(c["loss"])) / abs(float(c["loss"])) <= TOL
+    assert cov.shape == (x.shape[0], 1, 13, 13, x.shape[3], x.shape[4])
+
+
+@pytest.mark.parametrize("mode", ["diag", "iso"])
+def test_golden_mgnll(mode):
+    import uncrtaints_b200 as ub
+    c = load_npz("case_mgnll.npz")
+    pred = torch.from_numpy(c[f"{mode}.pred"]).cuda().requires_grad_(True)
+    var = torch.from_numpy(c[f"{mode}.var"]).cuda().requires_grad_(True)
+    targ = torch.from_numpy(c[f"{mode}.target"]).cuda()
+    loss, cov = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=mode, chunk=None)(pred, targ, var)
+    (2.0 * loss).backward()          # upstream gradient != 1 exercises the chain rule
+    assert abs(loss.item() - float(c[f"{mode}.loss"])) / abs(float(c[f"{mode}.loss"])) <= 1e-4
+    assert rel_l2(pred.grad / 2, torch.from_numpy(c[f"{mode}.dpred"])) <= TOL
+    assert rel_l2(var.grad / 2, torch.from_numpy(c[f"{mode}.dvar"])) <= TOL
+    assert abs(cov.double().sum().item() - float(c[f"{mode}.cov_diag_sum"])) / float(c[f"{mode}.cov_diag_sum"]) <= 1e-4
+    off = cov.clone()
+    for i in range(13):
+        off[:, :, i, i] = 0
+    assert float(off.abs().max()) == 0.0
+    with pytest.raises(ValueError, match="var has negative entry/entries"):
+        ub.MultiGaussianNLLLoss(mode=mode, chunk=None)(pred.detach(), targ, -var.detach())
+    with pytest.raises(ValueError, match="is not valid"):
+        ub.MultiGaussianNLLLoss(mode=mode, chunk=None, reduction="bogus")(pred.detach(), targ, var.detach())
+
+
+def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
+    n, c, h, w = t.shape
+    return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
+
+
+@pytest.mark.parametrize("groups,training", [(4, 1), (0, 1), (0, 0)])
+def test_mbconv_block_vs_oracle(golden_weights, groups, training):
+    """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64)."""
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    kind = "group" if groups else "batch"
+    pre = "in_block.0." if groups else "out_block.2."
+    N, H, W = 3, 16, 32
+    g = torch.Generator("cpu").manual_seed(21)
+    x = torch.randn(N, 128, H, W, generator=g) * 1.5 + 0.3
+    dout = torch.randn(N, 128, H, W, generator=g)
+    p64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.double() if v.is_floating_point() else v)
+           for k, v in golden_weights.items() if k.startswith(pre)}
+    if not groups:       # BatchNorm weights of weight_init are N(0,1); keep them as they are (can be negative)
+        pass
+    x64 = x.double().requires_grad_(True)
+    newbuf = {}
+    ref = O.mbconv(x64, p64, pre, kind, bool(training), O.OracleConfig(), newbuf)
+    leaves = [v for v in p64.values() if v.requires_grad]
+    names = [k for k, v in p64.items() if v.requires_grad]
+    grads = torch.autograd.grad(ref, [x64] + leaves, dout.double())
+    ref_dx, ref_g = grads[0], dict(zip(names, grads[1:]))
+
+    rel = {_lib.UB200_B_N0_W: "conv.norm.weight", _lib.UB200_B_N0_B: "conv.norm.bias", _lib.UB200_B_N0_RM: "conv.norm.running_mean",
+           _lib.UB200_B_N0_RV: "conv.norm.running_var", _lib.UB200_B_W1: "conv.fn.0.weight", _lib.UB200_B_N1_W: "conv.fn.1.weight",
+           _lib.UB200_B_N1_B: "conv.fn.1.bias", _lib.UB200_B_N1_RM: "conv.fn.1.running_mean", _lib.UB200_B_N1_RV: "conv.fn.1.running_var",
+           _lib.UB200_B_WDW: "conv.fn.3.weight", _lib.UB200_B_N2_W: "conv.fn.4.weight", _lib.UB200_B_N2_B: "conv.fn.4.bias",
+           _lib.UB200_B_N2_RM: "conv.fn.4.running_mean", _lib.UB200_B_N2_RV: "conv.fn.4.running_var", _lib.UB200_B_F1: "conv.fn.6.fc.0.weight",
+           _lib.UB200_B_F2: "conv.fn.6.fc.2.weight", _lib.UB200_B_W2: "conv.fn.7.weight", _lib.UB200_B_N3_W: "conv.fn.8.weight",
+           _lib.UB200_B_N3_B: "conv.fn.8.bias", _lib.UB200_B_N3_RM: "conv.fn.8.running_mean", _lib.UB200_B_N3_RV: "conv.fn.8.running_var"}
+    dev = {k: golden_weights[pre + v].clone().cuda().contiguous() for k, v in rel.items() if pre + v in golden_weights}
+    gdev = {k: torch.zeros_like(v) for k, v in dev.items() if "running" not in rel[k]}
+    ptab = _lib.ptr_table([dev[k].data_ptr() if k in dev else 0 for k in range(_lib.UB200_BLOCK_STRIDE)])
+    gtab = _lib.ptr_table([gdev[k].data_ptr() if k in gdev else 0 for k in range(_lib.UB200_BLOCK_STRIDE)])
+    xd, dd = _nhwc(x).cuda(), _nhwc(dout).cuda()
+    out, dx = torch.empty_like(xd), torch.empty_like(xd)
+    nbytes = L.ub200_mbconv_workspace_bytes(N, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.ub200_mbconv_forward(xd.data_ptr(), ptab, N, H, W, groups, training, 1e-5, 0.1, 0, out.data_ptr(),
+                                      ws.data_ptr(), nbytes, st), "mbconv_forward")
+    _lib.check(L.ub200_mbconv_backward(xd.data_ptr(), ptab, dd.data_ptr(), gtab, N, H, W, groups, training, 0, dx.data_ptr(),
+                                       ws.data_ptr(), nbytes, st), "mbconv_backward")
+    torch.cuda.synchronize()
+    tag = f"mbconv[{kind},train={training}]"
+    lines = [f"{tag} out rel_l2={rel_l2(out, _nhwc(ref.detach())):.3e}", f"{tag} dx rel_l2={rel_l2(dx, _nhwc(ref_dx)):.3e}"]
+    errs = {}
+    for k, gbuf in gdev.items():
+        name = pre + rel[k]
+        errs[name] = rel_l2(gbuf.reshape(-1), ref_g[name].reshape(-1))
+        lines.append(f"{tag} grad {name}: rel_l2={errs[name]:.3e}")
+    report("parity_report.txt", lines)
+    assert rel_l2(out, _nhwc(ref.detach())) <= TOL
+    assert rel_l2(dx, _nhwc(ref_dx)) <= TOL
+    for name, e in errs.items():
+        if kind == "batch" and name.endswith("conv.norm.bias"):
+            continue      # cancels through the following BatchNorm only when it is in training mode; checked below
+        assert e <= TOL, (name, e)
+    if not groups and training:
+        for k, v in newbuf.items():
+            slot = [s for s, nm in rel.items() if pre + nm == k]
+            if slot:
+                assert torch.allclose(dev[slot[0]].double().cpu(), v.double(), rtol=1e-4, atol=1e-5), k
+
+
+@pytest.mark.parametrize("B,T,H,W,covmode,train,pad", [
+    (1, 2, 256, 256, "diag", True, False),     # full-resolution frame (x8 upsampling), dropout mask injected
+    (2, 5, 64, 96, "diag", True, True),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
+    (1, 3, 128, 64, "iso", False, False),      # eval mode, isotropic covariance
+])
+def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad):
+    import uncrtaints_b200 as ub
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=100 + T, pad_last=pad)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=7) if train else None
+    cfg = O.OracleConfig(covmode=covmode)
+    cov = cfg.covar_dim
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in golden_weights.items()}
+    sd64["out_conv.conv.conv.0.weight"] = sd64["out_conv.conv.conv.0.weight"][:13 + cov]
+    sd64["out_conv.conv.conv.0.bias"] = sd64["out_conv.conv.conv.0.bias"][:13 + cov]
+    taps = {}
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd64.items()}
+    o_out = O.forward(leaf, x.double(), d.double(), cfg, train, keep, None, taps)
+    o_loss = O.mgnll(o_out[:, :, :13], y.double(), o_out[:, :, 13:13 + cov], covmode)
+    names = [k for k, v in leaf.items() if v.requires_grad]
+    o_grads = dict(zip(names, torch.autograd.grad(o_loss, [leaf[k] for k in names], allow_unused=True)))
+    o_grads = {k: (g if g is not None else torch.zeros_like(leaf[k])) for k, g in o_grads.items()}
+
+    net = make_net(golden_weights, covmode)
+    net.train(train)
+    net._injected_keep_mask = keep.to(torch.uint8) if keep is not None else None
+    out = net(x.cuda(), batch_positions=d.cuda())
+    loss, _ = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=covmode, chunk=None)(
+        out[:, :, :13], y.cuda(), out[:, :, 13:13 + cov])
+    loss.backward()
+    torch.cuda.synchronize()
+    tag = f"oracle[B{B}T{T} {H}x{W} {covmode} train={train} pad={pad}]"
+    N = B * T
+
+    def nchw(t, n):
+        return t.reshape(n, H, W, -1).permute(0, 3, 1, 2)
+    stage = [
+        ("x0", rel_l2(nchw(tap(net, "x0", (N, H * W, 128)), N), taps["in_conv"])),
+        ("enc.out", rel_l2(nchw(tap(net, "blk0.out", (N, H * W, 128)), N), taps["in_block.0.out"])),
+        ("pooled", rel_l2(tap(net, "pooled", (N, 32, 32, 128)).permute(0, 3, 1, 2), taps["down"])),
+        ("attn", rel_l2(tap(net, "attn", (16, B, T, 32, 32)), taps["attn"])),
+        ("agg", rel_l2(nchw(tap(net, "agg", (B, H * W, 128)), B), taps["agg"])),
+    ] + [(f"dec{i}.out", rel_l2(nchw(tap(net, f"blk{i + 1}.out", (B, H * W, 128)), B), taps[f"out_block.{i}.out"])) for i in range(5)]
+    lines = [f"{tag} stage {n}: rel_l2={e:.3e}" for n, e in stage]
+    lines += [f"{tag} out rel_l2={rel_l2(out, o_out):.3e} loss={loss.item():.6f} oracle={o_loss.item():.6f}"]
+    report("parity_report.txt", lines)
+    idx = tap(net, "pool_idx", (N, 32, 32, 128), torch.int32).permute(0, 3, 1, 2).cpu().long()
+    mism = (idx != taps["pool_idx"])
+    if mism.any():   # an fp32-vs-fp64 rounding can flip an argmax between near-equal maxima: values must then be near-ties
+        enc = taps["in_block.0.out"].reshape(N, 128, -1)
+        a = torch.gather(enc, 2, idx.reshape(N, 128, -1))
+        b = torch.gather(enc, 2, taps["pool_idx"].reshape(N, 128, -1))
+        assert float(((a - b).abs() / b.abs().clamp_min(1e-6)).max()) < 1e-5 and mism.float().mean() < 1e-4
+    assert torch.equal(tap(net, "notpad", (B, T), torch.int32).cpu() == 0, taps["pad_mask"])
+    for n, e in stage:
+        assert e <= TOL, (n, e)
+    assert rel_l2(out, o_out) <= TOL
+    assert abs(loss.item() - o_loss.item()) / abs(o_loss.item()) <= TOL
+    check_grads(net.named_parameters(), o_grads, tag)
+
+
+def test_no_cpu_fallback(golden_weights):
+    import uncrtaints_b200 as ub
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 2, 15, 32, 32), batch_positions=torch.zeros(1, 2))
+    with pytest.raises(NotImplementedError):
+        net.cuda()(torch.zeros(1, 2, 15, 48, 48, device="cuda"), batch_positions=torch.zeros(1, 2, device="cuda"))
+
+
+def test_philox_dropout_statistics(golden_weights):
+    """Production dropout is in-kernel Philox (statistically, not bit-, identical to torch's stream): with dropout the
+    aggregated features must differ from the no-dropout run, be reproducible under the same seed, and their mean over
+    many pixels must stay unbiased (E[keep/(1-p)] = 1)."""
+    B, T, H, W = 1, 2, 128, 128
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=5)
+    net = make_net(golden_weights, "diag").train()
+    with torch.no_grad():
+        net.temporal_aggregator.attn_dropout.p = 0.0
+        net(x.cuda(), batch_positions=d.cuda())
+        base = tap(net, "agg", (B, H * W, 128)).clone()
+        net.temporal_aggregator.attn_dropout.p = 0.1
+        torch.manual_seed(3)
+        net(x.cuda(), batch_positions=d.cuda())
+        a1 = tap(net, "agg", (B, H * W, 128)).clone()
+        torch.manual_seed(3)
+        net(x.cuda(), batch_positions=d.cuda())
+        a2 = tap(net, "agg", (B, H * W, 128)).clone()
+        torch.manual_seed(4)
+        net(x.cuda(), batch_positions=d.cuda())
+        a3 = tap(net, "agg", (B, H * W, 128)).clone()
+    assert torch.equal(a1, a2)
+    assert not torch.equal(a1, a3) and not torch.equal(a1, base)
+    assert abs(float(a1.double().mean() / base.double().mean()) - 1.0) < 5e-3

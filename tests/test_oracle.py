@@ -122,3 +122,21 @@ def test_oracle_matches_live_reference_fp64():
         if not is_zero_grad_param(k):
             assert rel_l2(o_g[k], p.grad) < 1e-9, k
     assert torch.equal(O.covariance(out[:, :, 13:26].detach(), "diag"), var)
+
+
+def test_fused_mode_equals_elementary(golden_weights):
+    """bench.py times the oracle with FUSED=True (the ATen/oneDNN kernels the reference's modules dispatch to)."""
+    cfg = O.OracleConfig()
+    sd = _sd64(golden_weights)
+    x, y, d = O.synthetic_batch(1, 2, 64, 64, seed=8, dtype=torch.float64)
+    keep = O.dropout_keep_mask(16, 1, 2, 64, 64)
+    a_out, a_loss, a_g, _ = O.step(sd, x, y, d, cfg, True, keep)
+    O.set_fused(True)
+    try:
+        b_out, b_loss, b_g, _ = O.step(sd, x, y, d, cfg, True, keep)
+    finally:
+        O.set_fused(False)
+    assert rel_l2(b_out, a_out) < 1e-12 and abs(a_loss.item() - b_loss.item()) < 1e-9 * abs(a_loss.item())
+    for k in a_g:
+        if not is_zero_grad_param(k):
+            assert rel_l2(b_g[k], a_g[k]) < 1e-9, k

@@ -154,7 +154,7 @@ def fold_ltae(te: LTAE2dtiny, batch_positions: Optional[torch.Tensor], B: int, T
         d = te.d_model // nh
         # PositionalEncoder (positional_encoding.py:11-13,20-29): float32 denominators, even->sin, odd->cos, tiled x n_head
         denom = torch.pow(torch.tensor(float(te.T)), 2 * (torch.arange(0, d).float() // 2) / d).to(device)
-        tab = batch_positions.to(torch.float32)[:, :, None] / denom[None, None, :]
+        tab = batch_positions.to(ak.dtype)[:, :, None] / denom.to(ak.dtype)[None, None, :]
         tab = torch.stack([torch.sin(tab[:, :, 0::2]), torch.cos(tab[:, :, 1::2])], dim=-1).reshape(B, T, d)
         pe = tab.repeat(1, 1, nh)                               # [B,T,256]
         e = pe @ ak.t() + const[None, None, :]

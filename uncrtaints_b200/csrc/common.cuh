@@ -23,10 +23,13 @@
 #define UB_ERR_CUDA -2
 #define UB_ERR_WORKSPACE -3
 
+namespace ub { extern unsigned long long g_launch_count; }   // kernels launched by this library (model.cu)
+
 #define UB_CHECK_LAUNCH()                                  \
     do {                                                   \
         cudaError_t e__ = cudaGetLastError();              \
         if (e__ != cudaSuccess) return UB_ERR_CUDA;        \
+        ++::ub::g_launch_count;                            \
     } while (0)
 
 namespace ub {

@@ -17,6 +17,38 @@
 
 namespace ub {
 
+unsigned long long g_launch_count = 0;
+
+// ---- optional per-kernel timing (bench.py): CUDA events recorded on the launch stream around selected kernels ----
+enum KernelId {
+    KID_GEMM1_FWD = 0, KID_DWCONV_FWD, KID_SE_POOL, KID_GEMM2_FWD, KID_RESIDUAL_FWD, KID_NORM_BWD_STATS, KID_GEMM2_BWD,
+    KID_WGRAD2, KID_DWCONV_BWD, KID_GEMM1_BWD, KID_WGRAD1, KID_RESIDUAL_BWD, KID_INCONV, KID_MAXPOOL, KID_LTAE, KID_AGGREGATE,
+    KID_HEAD, KID_INCONV_BWD, KID_TEMPORAL_BWD, KID_HEAD_BWD, KID_COUNT
+};
+struct ProfRec { int kid; cudaEvent_t a, b; };
+static unsigned long long g_prof_mask = 0;
+static ProfRec g_prof[8192];
+static int g_prof_n = 0, g_prof_created = 0;
+static inline void prof_begin(int kid, cudaStream_t st) {
+    if (!((g_prof_mask >> kid) & 1ull) || g_prof_n >= 8192) return;
+    ProfRec& r = g_prof[g_prof_n];
+    if (g_prof_n >= g_prof_created) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); g_prof_created = g_prof_n + 1; }
+    r.kid = kid;
+    cudaEventRecord(r.a, st);
+}
+static inline void prof_end(int kid, cudaStream_t st) {
+    if (!((g_prof_mask >> kid) & 1ull) || g_prof_n >= 8192) return;
+    cudaEventRecord(g_prof[g_prof_n].b, st);
+    ++g_prof_n;
+}
+#define UB_PROF(kid, st, expr)          \
+    do {                                \
+        prof_begin(kid, st);            \
+        int rc__ = (expr);              \
+        prof_end(kid, st);              \
+        if (rc__ != UB_OK) return rc__; \
+    } while (0)
+
 #define UB_TRY(expr)                    \
     do {                                \
         int rc__ = (expr);              \
@@ -173,19 +205,19 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     UB_TRY(launch_transpose(pf(c.p, UB200_B_W1), at<float>(ws, w.w1t), UB_HID, UB_WIDTH, c.st));
     UB_TRY(launch_transpose(pf(c.p, UB200_B_W2), at<float>(ws, w.w2t), UB_WIDTH, UB_HID, c.st));
     UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
-    UB_TRY(simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
+    UB_PROF(KID_GEMM1_FWD, c.st, simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
-    UB_TRY(launch_dwconv_fwd(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
+    UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
                              at<double>(ws, w.stats2), c.N, c.H, c.W, c.st));
     UB_TRY(finalize(c, w.stats2, UB200_B_N2_W, w.coef2, w.mr2, UB_HID));
-    UB_TRY(launch_se_pool(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.pool),
+    UB_PROF(KID_SE_POOL, c.st, launch_se_pool(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.pool),
                           need_gp ? at<double>(ws, w.gp) : nullptr, c.N, P, c.st));
     UB_TRY(launch_se_fwd(at<double>(ws, w.pool), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2), at<float>(ws, w.se_save),
                          at<float>(ws, w.gate), c.N, P, c.st));
-    UB_TRY(simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
+    UB_PROF(KID_GEMM2_FWD, c.st, simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
                           at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats3, UB200_B_N3_W, w.coef3, w.mr3, UB_WIDTH));
-    UB_TRY(launch_residual_fwd(x, at<float>(ws, w.y), at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats, c.N, P, c.st));
+    UB_PROF(KID_RESIDUAL_FWD, c.st, launch_residual_fwd(x, at<float>(ws, w.y), at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats, c.N, P, c.st));
     return UB_OK;
 }
 
@@ -195,26 +227,26 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     const BlockWs& w = *c.w;
     const int P = c.H * c.W;
     void* ws = c.ws;
-    UB_TRY(launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
+    UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
-    UB_TRY(simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
+    UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
                           at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    UB_TRY(simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
+    UB_PROF(KID_WGRAD2, c.st, simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                        at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
     UB_TRY(launch_se_bwd(at<double>(ws, w.sums3), at<double>(ws, w.gp), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2),
                          at<float>(ws, w.se_save), gf(c.g, UB200_B_F1), gf(c.g, UB200_B_F2), at<float>(ws, w.dmp),
                          at<double>(ws, w.bstats2), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats2, UB200_B_N2_W, w.mr2, w.bc2, UB_HID));
-    UB_TRY(launch_dwconv_bwd(du, at<float>(ws, w.h2), at<float>(ws, w.h1), at<float>(ws, w.gate), at<float>(ws, w.dmp),
+    UB_PROF(KID_DWCONV_BWD, c.st, launch_dwconv_bwd(du, at<float>(ws, w.h2), at<float>(ws, w.h1), at<float>(ws, w.gate), at<float>(ws, w.dmp),
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    UB_TRY(simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
+    UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                           at<double>(ws, w.bstats0), c.N, P, c.st));
-    UB_TRY(simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
+    UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                        gf(c.g, UB200_B_W1), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
-    UB_TRY(launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.st));
+    UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.st));
     return UB_OK;
 }
 
@@ -256,6 +288,37 @@ using namespace ub;
 extern "C" {
 
 int ub200_version(void) { return 100; }
+
+unsigned long long ub200_launch_count(void) { return g_launch_count; }
+
+int ub200_prof_enable(unsigned long long mask) {
+    g_prof_mask = mask;
+    g_prof_n = 0;
+    return UB_OK;
+}
+int ub200_prof_num_kernels(void) { return KID_COUNT; }
+const char* ub200_prof_kernel_name(int kid) {
+    static const char* names[KID_COUNT] = {"gemm1_fwd", "dwconv_fwd", "se_pool", "gemm2_fwd", "residual_fwd", "norm_bwd_stats",
+        "gemm2_bwd", "wgrad2", "dwconv_bwd", "gemm1_bwd", "wgrad1", "residual_bwd", "inconv", "maxpool", "ltae", "aggregate",
+        "head", "inconv_bwd", "temporal_bwd", "head_bwd"};
+    return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "";
+}
+int ub200_prof_read(int kid, double* total_ms, int* launches) {
+    if (!total_ms || !launches) return UB_ERR_ARG;
+    double t = 0.0;
+    int n = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        if (g_prof[i].kid != kid) continue;
+        if (cudaEventSynchronize(g_prof[i].b) != cudaSuccess) return UB_ERR_CUDA;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b) != cudaSuccess) return UB_ERR_CUDA;
+        t += ms;
+        ++n;
+    }
+    *total_ms = t;
+    *launches = n;
+    return UB_OK;
+}
 
 int ub200_num_param_slots(const ub200_desc* d) {
     if (!d) return UB_ERR_ARG;
@@ -323,24 +386,24 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
     if (cudaMemsetAsync(at<char>(ws, L.fwd_zero_begin), 0, L.fwd_zero_end - L.fwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
 
     // in_conv: conv1x1 + norm + ReLU (+ pad-mask test), NCHW -> pixel-major
-    UB_TRY(launch_inconv_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.stats_c0),
+    UB_PROF(KID_INCONV, st, launch_inconv_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.stats_c0),
                                at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize(at<double>(ws, L.stats_c0), pf(params, UB200_P_IN_NORM_W), pf(params, UB200_P_IN_NORM_B),
                                 pfm(params, UB200_P_IN_NORM_RM), pfm(params, UB200_P_IN_NORM_RV), at<Coef>(ws, L.coef_in),
                                 at<MeanRstd>(ws, L.mr_in), L.Ne, UB_WIDTH, d->enc_groups, (double)P, d->norm_eps, d->bn_momentum,
                                 d->training, st));
-    UB_TRY(launch_inconv_apply(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+    UB_PROF(KID_INCONV, st, launch_inconv_apply(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
                                at<float>(ws, L.x0), at<double>(ws, L.blk[0].stats0), L.Ne, d->C_in, P, st));
     // encoder block
     BlockCtx enc = make_ctx(d, L, 0, params, nullptr, ws, st);
     UB_TRY(mbconv_forward(enc, at<float>(ws, L.x0), nullptr, d->need_grad != 0));
     const float* enc_out = at<float>(ws, L.blk[0].out);
     // temporal path
-    UB_TRY(launch_maxpool_fwd(enc_out, at<float>(ws, L.pooled), at<int>(ws, L.pool_idx), L.Ne, d->H, d->W, st));
-    UB_TRY(launch_ltae_fwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), pf(params, UB200_P_LTAE_E),
+    UB_PROF(KID_MAXPOOL, st, launch_maxpool_fwd(enc_out, at<float>(ws, L.pooled), at<int>(ws, L.pool_idx), L.Ne, d->H, d->W, st));
+    UB_PROF(KID_LTAE, st, launch_ltae_fwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), pf(params, UB200_P_LTAE_E),
                            at<int>(ws, L.notpad), at<float>(ws, L.attn), d->B, d->T, d->norm_eps, st));
     const float drop_p = d->training ? d->dropout_p : 0.f;
-    UB_TRY(launch_aggregate_fwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out,
+    UB_PROF(KID_AGGREGATE, st, launch_aggregate_fwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out,
                                 at<float>(ws, L.agg), at<double>(ws, L.blk[1].stats0), d->B, d->T, d->H, d->W, st));
     // decoder blocks
     const float* x = at<float>(ws, L.agg);
@@ -349,7 +412,7 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
         UB_TRY(mbconv_forward(c, x, i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr, d->need_grad != 0));
         x = at<float>(ws, L.blk[i].out);
     }
-    UB_TRY(launch_head_fwd(x, pf(params, UB200_P_OUT_W), pf(params, UB200_P_OUT_B), output, d->B, d->out_dim, P, d->scale_by,
+    UB_PROF(KID_HEAD, st, launch_head_fwd(x, pf(params, UB200_P_OUT_W), pf(params, UB200_P_OUT_B), output, d->B, d->out_dim, P, d->scale_by,
                            d->mean_sigmoid, d->var_eps, st));
     return UB_OK;
 }
@@ -371,7 +434,7 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
     float* partial = at<float>(ws, L.partial);
 
     const float* dec_out = at<float>(ws, L.blk[L.nblk - 1].out);
-    UB_TRY(launch_head_bwd(grad_output, output, dec_out, pf(params, UB200_P_OUT_W), gA, gf(grads, UB200_P_OUT_W),
+    UB_PROF(KID_HEAD_BWD, st, launch_head_bwd(grad_output, output, dec_out, pf(params, UB200_P_OUT_W), gA, gf(grads, UB200_P_OUT_W),
                            gf(grads, UB200_P_OUT_B), d->B, d->out_dim, P, d->scale_by, d->mean_sigmoid, d->var_eps, num_sms(), st));
     for (int i = L.nblk - 1; i >= 1; --i) {
         BlockCtx c = make_ctx(d, L, i, params, grads, ws, st);
@@ -382,21 +445,21 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
     // gA = dAgg.  Temporal path backward; dEnc accumulates in gB.
     const float* enc_out = at<float>(ws, L.blk[0].out);
     const float drop_p = d->training ? d->dropout_p : 0.f;
-    UB_TRY(launch_aggregate_bwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out, gA,
+    UB_PROF(KID_TEMPORAL_BWD, st, launch_aggregate_bwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out, gA,
                                 gB, at<float>(ws, L.dwup), at<float>(ws, L.dattn), d->B, d->T, d->H, d->W, st));
-    UB_TRY(launch_ltae_bwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), at<float>(ws, L.attn), at<float>(ws, L.dattn),
+    UB_PROF(KID_TEMPORAL_BWD, st, launch_ltae_bwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), at<float>(ws, L.attn), at<float>(ws, L.dattn),
                            at<float>(ws, L.dpooled), gf(grads, UB200_P_LTAE_AP), gf(grads, UB200_P_LTAE_E), d->B, d->T,
                            d->norm_eps, st));
-    UB_TRY(launch_maxpool_bwd(at<float>(ws, L.dpooled), at<int>(ws, L.pool_idx), gB, L.Ne, P, st));
+    UB_PROF(KID_TEMPORAL_BWD, st, launch_maxpool_bwd(at<float>(ws, L.dpooled), at<int>(ws, L.pool_idx), gB, L.Ne, P, st));
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
     // in_conv backward (no input gradient)
-    UB_TRY(launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
                                    at<MeanRstd>(ws, L.mr_in), gA, at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize_bwd(at<double>(ws, L.bstats_in), pf(params, UB200_P_IN_NORM_W), at<MeanRstd>(ws, L.mr_in),
                                     at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_NORM_W), gf(grads, UB200_P_IN_NORM_B), L.Ne,
                                     UB_WIDTH, d->enc_groups, (double)P, d->training, st));
-    UB_TRY(launch_inconv_bwd_wgrad(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_wgrad(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
                                    at<MeanRstd>(ws, L.mr_in), at<BCoef>(ws, L.bc_in), gA, gf(grads, UB200_P_IN_W),
                                    gf(grads, UB200_P_IN_B), L.Ne, d->C_in, P, st));
     return UB_OK;
