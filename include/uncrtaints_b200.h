@@ -106,6 +106,16 @@ int ub200_prof_num_kernels(void);
 const char* ub200_prof_kernel_name(int kid);
 int ub200_prof_read(int kid, double* total_ms, int* launches);
 
+/* Debug hook for the tcgen05 path: override the shared-memory matrix-descriptor upper word, its LBO field and the
+ * instruction descriptor (defaults follow CUTLASS cute/arch/mma_sm100_desc.hpp). */
+int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+
+/* The 1x1 expand GEMM of an MBConv block alone (uncrtaints.py:126 with the PreNorm apply fused in front and the
+ * Norm1 statistics behind): h1[N*P][256] = (x[N*P][128]*scale + shift) . W1^T; stats[N][256][2] = column (sum, sumsq).
+ * coef: [N][128] (scale, shift); scratch: 256 KB device memory; backend as in ub200_desc.gemm_backend. */
+int ub200_gemm1_forward(int backend, const float* x, const float* coef, const float* w1, float* h1, double* stats, int N, int P,
+                        void* scratch, void* stream);
+
 /* Number of pointer slots in a params / grads table for this configuration. */
 int ub200_num_param_slots(const ub200_desc* d);
 

@@ -17,10 +17,11 @@ ZERO_GRAD_SUFFIXES = ("temporal_encoder.in_norm.bias", "temporal_encoder.inconv.
                       "temporal_encoder.attention_heads.fc1_k.bias")
 
 
-def is_zero_grad_param(name: str, decoder_norm: str = "batch") -> bool:
+def is_zero_grad_param(name: str, decoder_norm: str = "batch", training: bool = True) -> bool:
     if name in ZERO_GRAD_SUFFIXES:
         return True
-    return decoder_norm == "batch" and name.startswith("out_block.") and name.endswith("conv.norm.bias")
+    # only a BatchNorm that normalises with *batch* statistics (training mode) removes the per-channel constant
+    return training and decoder_norm == "batch" and name.startswith("out_block.") and name.endswith("conv.norm.bias")
 
 
 def pytest_configure(config):

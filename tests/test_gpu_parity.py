@@ -42,14 +42,14 @@ def tap(net, name, shape_nhwc, dtype=torch.float32):
     return raw.view(dtype).reshape(shape_nhwc)
 
 
-def check_grads(named_params, ref_grads, tag, tol=TOL):
+def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     lines, bad = [], []
     scale = max(float(torch.as_tensor(g).double().norm()) for g in ref_grads.values())
     for k, p in named_params:
         ref = torch.as_tensor(ref_grads[k])
         g = p.grad
         assert g is not None, k
-        if is_zero_grad_param(k):
+        if is_zero_grad_param(k, training=training):
             err = float(g.double().norm().cpu())
             ok = err <= 1e-3 * max(float(ref.double().norm()), 1e-6 * scale) or err <= 1e-6 * scale
             lines.append(f"{tag} zero-grad {k}: |g|={err:.3e} (ref {float(ref.double().norm()):.3e}) {'ok' if ok else 'FAIL'}")
@@ -63,7 +63,7 @@ def check_grads(named_params, ref_grads, tag, tol=TOL):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0])
+@pytest.mark.parametrize("backend", [0, 1])
 def test_golden_diag_train_pad(golden_weights, backend):
     import uncrtaints_b200 as ub
     c = load_npz("case_diag_train_pad.npz")
@@ -153,8 +153,9 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
+@pytest.mark.parametrize("backend", [0, 1])
 @pytest.mark.parametrize("groups,training", [(4, 1), (0, 1), (0, 0)])
-def test_mbconv_block_vs_oracle(golden_weights, groups, training):
+def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
     """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64)."""
     from uncrtaints_b200 import _lib
     L = _lib.lib()
@@ -192,12 +193,12 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training):
     nbytes = L.ub200_mbconv_workspace_bytes(N, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(L.ub200_mbconv_forward(xd.data_ptr(), ptab, N, H, W, groups, training, 1e-5, 0.1, 0, out.data_ptr(),
+    _lib.check(L.ub200_mbconv_forward(xd.data_ptr(), ptab, N, H, W, groups, training, 1e-5, 0.1, backend, out.data_ptr(),
                                       ws.data_ptr(), nbytes, st), "mbconv_forward")
-    _lib.check(L.ub200_mbconv_backward(xd.data_ptr(), ptab, dd.data_ptr(), gtab, N, H, W, groups, training, 0, dx.data_ptr(),
+    _lib.check(L.ub200_mbconv_backward(xd.data_ptr(), ptab, dd.data_ptr(), gtab, N, H, W, groups, training, backend, dx.data_ptr(),
                                        ws.data_ptr(), nbytes, st), "mbconv_backward")
     torch.cuda.synchronize()
-    tag = f"mbconv[{kind},train={training}]"
+    tag = f"mbconv[{kind},train={training},backend={backend}]"
     lines = [f"{tag} out rel_l2={rel_l2(out, _nhwc(ref.detach())):.3e}", f"{tag} dx rel_l2={rel_l2(dx, _nhwc(ref_dx)):.3e}"]
     errs = {}
     for k, gbuf in gdev.items():
@@ -218,12 +219,13 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training):
                 assert torch.allclose(dev[slot[0]].double().cpu(), v.double(), rtol=1e-4, atol=1e-5), k
 
 
-@pytest.mark.parametrize("B,T,H,W,covmode,train,pad", [
-    (1, 2, 256, 256, "diag", True, False),     # full-resolution frame (x8 upsampling), dropout mask injected
-    (2, 5, 64, 96, "diag", True, True),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
-    (1, 3, 128, 64, "iso", False, False),      # eval mode, isotropic covariance
+@pytest.mark.parametrize("B,T,H,W,covmode,train,pad,backend", [
+    (1, 2, 256, 256, "diag", True, False, 0),     # full-resolution frame (x8 upsampling), dropout mask injected
+    (1, 2, 256, 256, "diag", True, False, 1),     # same through the tcgen05 GEMMs
+    (2, 5, 64, 96, "diag", True, True, 1),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
+    (1, 3, 128, 64, "iso", False, False, 0),      # eval mode, isotropic covariance
 ])
-def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad):
+def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub
     x, y, d = O.synthetic_batch(B, T, H, W, seed=100 + T, pad_last=pad)
     keep = O.dropout_keep_mask(16, B, T, H, W, seed=7) if train else None
@@ -240,7 +242,7 @@ def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad):
     o_grads = dict(zip(names, torch.autograd.grad(o_loss, [leaf[k] for k in names], allow_unused=True)))
     o_grads = {k: (g if g is not None else torch.zeros_like(leaf[k])) for k, g in o_grads.items()}
 
-    net = make_net(golden_weights, covmode)
+    net = make_net(golden_weights, covmode, backend)
     net.train(train)
     net._injected_keep_mask = keep.to(torch.uint8) if keep is not None else None
     out = net(x.cuda(), batch_positions=d.cuda())
@@ -248,7 +250,7 @@ def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad):
         out[:, :, :13], y.cuda(), out[:, :, 13:13 + cov])
     loss.backward()
     torch.cuda.synchronize()
-    tag = f"oracle[B{B}T{T} {H}x{W} {covmode} train={train} pad={pad}]"
+    tag = f"oracle[B{B}T{T} {H}x{W} {covmode} train={train} pad={pad} backend={backend}]"
     N = B * T
 
     def nchw(t, n):
@@ -275,7 +277,7 @@ def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad):
         assert e <= TOL, (n, e)
     assert rel_l2(out, o_out) <= TOL
     assert abs(loss.item() - o_loss.item()) / abs(o_loss.item()) <= TOL
-    check_grads(net.named_parameters(), o_grads, tag)
+    check_grads(net.named_parameters(), o_grads, tag, training=train)
 
 
 def test_no_cpu_fallback(golden_weights):
@@ -311,3 +313,29 @@ def test_philox_dropout_statistics(golden_weights):
     assert torch.equal(a1, a2)
     assert not torch.equal(a1, a3) and not torch.equal(a1, base)
     assert abs(float(a1.double().mean() / base.double().mean()) - 1.0) < 5e-3
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+def test_gemm1_op_vs_fp64(backend):
+    """The 1x1 expand GEMM alone (ub200_gemm1_forward): fp32 CUDA-core path and tcgen05 bf16x3 path vs an fp64 matmul."""
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    N, P = 2, 1024
+    g = torch.Generator("cpu").manual_seed(31)
+    x = torch.randn(N, P, 128, generator=g) * 2 + 0.5
+    coef = torch.stack([torch.rand(N, 128, generator=g) + 0.5, torch.randn(N, 128, generator=g)], dim=-1).contiguous()
+    w1 = torch.randn(256, 128, generator=g) * 0.1
+    a = x.double() * coef[:, None, :, 0].double() + coef[:, None, :, 1].double()
+    ref = a @ w1.double().t()
+    xd, cd, wd = x.cuda(), coef.cuda(), w1.cuda()
+    h1 = torch.zeros(N, P, 256, device="cuda")
+    stats = torch.zeros(N, 256, 2, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(256 * 1024, dtype=torch.uint8, device="cuda")
+    _lib.check(L.ub200_gemm1_forward(backend, xd.data_ptr(), cd.data_ptr(), wd.data_ptr(), h1.data_ptr(), stats.data_ptr(), N, P,
+                                     scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "gemm1_forward")
+    torch.cuda.synchronize()
+    e = rel_l2(h1, ref)
+    es = rel_l2(stats[..., 0], ref.sum(1))
+    eq = rel_l2(stats[..., 1], (ref ** 2).sum(1))
+    report("parity_report.txt", [f"gemm1 op backend={backend}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
+    assert e < 5e-5 and es < 1e-4 and eq < 1e-4

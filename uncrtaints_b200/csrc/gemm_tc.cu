@@ -1,0 +1,388 @@
+// tcgen05 (5th-gen tensor core) streaming GEMMs for the MBConv 1x1 convolutions and their input-gradient passes
+// (model/src/backbones/uncrtaints.py:126,136 and their autograd backward).
+//
+//   D[ch_out (128 TMEM lanes per M-block), px (128 TMEM columns)] = sum_k W[ch_out][k] * f(act)[px][k]
+//
+// * fp32 parity on bf16 tensor cores: every operand is split x = hi + lo (two bf16), and three MMAs accumulate
+//   W_hi*A_hi + W_hi*A_lo + W_lo*A_hi in the fp32 TMEM accumulator (relative error ~1e-5; single-pass TF32
+//   measured 1e-3..8e-3 on this network's gradients and fails the 1e-3 parity target).
+// * the activation operand cannot come straight from HBM by TMA: the normalisation / GELU / SE gate / norm-backward
+//   must be applied first (the statistics barrier forces the apply into the consumer).  All 512 threads load
+//   fp32 rows with coalesced 32-byte pieces, transform in registers, split, and write the bf16 hi/lo tiles into
+//   shared memory in the canonical K-major SWIZZLE_128B layout (8 rows x 128 B atoms, 16-byte chunk index XOR
+//   row%8), then fence.proxy.async and hand them to the single MMA-issuing thread.
+// * weights are the M operand (prepared once per step as a swizzled bf16 hi/lo image, 128 KB, resident in shared
+//   memory); pixels are the N operand.  With channels on TMEM lanes the epilogue is trivial: tcgen05.ld 32x32b
+//   gives each thread ONE channel x 32 pixels, so global stores are 128-byte coalesced across the warp, the
+//   per-channel statistics are plain per-thread sums, and per-channel coefficients are thread constants.
+// * pipeline: 2-slot shared-memory ring of 64-channel K-blocks (tcgen05.commit -> mbarrier frees a slot) and a
+//   double-buffered TMEM accumulator (2 x 256 columns): the MMAs of tile t run while the threads do the epilogue
+//   of tile t-1 and load tile t+1.
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ub {
+namespace tc {
+
+constexpr int THREADS = 512;
+constexpr int TILE_PX = 128;          // UMMA N
+constexpr int KBLK = 64;              // channels per K-block (one 128-byte swizzle row of bf16)
+constexpr int NSTAGE = 2;
+constexpr int STAGE_BYTES = 2 * TILE_PX * KBLK * 2;   // hi + lo tiles, 32 KB
+
+// runtime-tunable descriptor constants (ub200_tc_debug_set; defaults follow cute/arch/mma_sm100_desc.hpp)
+__device__ __constant__ uint32_t c_desc_hi = (64u) | (1u << 14) | (2u << 29);   // SBO=1024B>>4, version=1, SWIZZLE_128B
+__device__ __constant__ uint32_t c_desc_lbo = 1u;                                // LBO field (ignored for SW128 K-major)
+__device__ __constant__ uint32_t c_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (16u << 17) | (8u << 24);  // F32 acc, BF16 x BF16, N=128, M=128
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(c_desc_lbo & 0x3FFFu) << 16) | ((uint64_t)c_desc_hi << 32);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                   "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 8 fp32 values into bf16 hi / lo (x ~= hi + lo) and store both 16-byte chunks
+__device__ __forceinline__ void split_store8(const float (&v)[8], char* hi_chunk, char* lo_chunk) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        uint32_t hp;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(b), "f"(a));     // upper half <- b, lower half <- a
+        const float ah = __uint_as_float(hp << 16), bh = __uint_as_float(hp & 0xFFFF0000u);
+        uint32_t lp;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(b - bh), "f"(a - ah));
+        h[i] = hp; l[i] = lp;
+    }
+    *reinterpret_cast<uint4*>(hi_chunk) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_chunk) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// operand loaders: per-frame coefficients live in shared memory as float4 per input channel
+// ------------------------------------------------------------------------------------------
+struct TLoadNormed {           // a = x*scale + shift
+    const float* x; const Coef* coef;
+    __device__ void fill(int n, int K, float4* cf) const {
+        for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; cf[k] = make_float4(c.scale, c.shift, 0.f, 0.f); }
+    }
+    __device__ void load8(size_t row, int K, int ch0, const float4* cf, float (&v)[8]) const {
+        const float4 a = ld4_stream(x + row * K + ch0), b = ld4_stream(x + row * K + ch0 + 4);
+        const float in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 c = cf[ch0 + i]; v[i] = fmaf(in[i], c.x, c.y); }
+    }
+};
+struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
+    const float* h2; const Coef* coef; const float* gate;
+    __device__ void fill(int n, int K, float4* cf) const {
+        for (int k = threadIdx.x; k < K; k += THREADS) {
+            const Coef c = coef[(size_t)n * K + k];
+            cf[k] = make_float4(c.scale, c.shift, gate[(size_t)n * K + k], 0.f);
+        }
+    }
+    __device__ void load8(size_t row, int K, int ch0, const float4* cf, float (&v)[8]) const {
+        const float4 a = ld4_stream(h2 + row * K + ch0), b = ld4_stream(h2 + row * K + ch0 + 4);
+        const float in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 c = cf[ch0 + i]; v[i] = gelu_f(fmaf(in[i], c.x, c.y)) * c.z; }
+    }
+};
+struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
+    const float* dy; const float* vv; const BCoef* bc;
+    __device__ void fill(int n, int K, float4* cf) const {
+        for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; cf[k] = make_float4(c.a, c.b, c.c, 0.f); }
+    }
+    __device__ void load8(size_t row, int K, int ch0, const float4* cf, float (&v)[8]) const {
+        const float4 a = ld4_stream(dy + row * K + ch0), b = ld4_stream(dy + row * K + ch0 + 4);
+        const float4 p = ld4(vv + row * K + ch0), q = ld4(vv + row * K + ch0 + 4);
+        const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float w[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 c = cf[ch0 + i]; v[i] = fmaf(c.x, d[i], fmaf(c.y, w[i], c.z)); }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// epilogues: thread = one output channel; v[32] = 32 consecutive pixels of that channel
+// ------------------------------------------------------------------------------------------
+struct TEpiStoreStats {        // raw output + (sum, sumsq)
+    static constexpr int NS = 2;
+    float* out; double* stats;
+    struct State {};
+    __device__ void init(int n, int NOUT, int ch, State&) const {}
+    __device__ void apply(const State&, size_t row0, int NOUT, int ch, const float (&v)[32], float* s) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            out[(row0 + i) * NOUT + ch] = v[i];
+            s[0] += v[i];
+            s[1] = fmaf(v[i], v[i], s[1]);
+        }
+    }
+    __device__ double* dst(int n, int NOUT) const { return stats + (size_t)n * NOUT * NS; }
+};
+struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
+    static constexpr int NS = 3;
+    float* du; const float* h2; const Coef* coef2; const MeanRstd* mr2; double* sums;
+    struct State { Coef k; MeanRstd m; };
+    __device__ void init(int n, int NOUT, int ch, State& st) const { st.k = coef2[(size_t)n * NOUT + ch]; st.m = mr2[(size_t)n * NOUT + ch]; }
+    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float (&v)[32], float* s) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const size_t o = (row0 + i) * NOUT + ch;
+            du[o] = v[i];
+            const float h = h2[o];
+            const float z = fmaf(h, st.k.scale, st.k.shift);
+            const float gp = gelu_grad_f(z);
+            s[0] = fmaf(v[i], gelu_f(z), s[0]);
+            s[1] = fmaf(v[i], gp, s[1]);
+            s[2] = fmaf(v[i] * gp, (h - st.m.mean) * st.m.rstd, s[2]);
+        }
+    }
+    __device__ double* dst(int n, int NOUT) const { return sums + (size_t)n * NOUT * NS; }
+};
+struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
+    static constexpr int NS = 2;
+    float* dn0; const float* x; const MeanRstd* mr0; double* bstats;
+    struct State { MeanRstd m; };
+    __device__ void init(int n, int NOUT, int ch, State& st) const { st.m = mr0[(size_t)n * NOUT + ch]; }
+    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float (&v)[32], float* s) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const size_t o = (row0 + i) * NOUT + ch;
+            dn0[o] = v[i];
+            s[0] += v[i];
+            s[1] = fmaf(v[i], (x[o] - st.m.mean) * st.m.rstd, s[1]);
+        }
+    }
+    __device__ double* dst(int n, int NOUT) const { return bstats + (size_t)n * NOUT * NS; }
+};
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int K, int NOUT, class ALoad, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P,
+               int tiles_per_block) {
+    constexpr int KB = K / KBLK, MH = NOUT / 128;
+    constexpr int W_BYTES = K * NOUT * 4;                 // hi image + lo image
+    constexpr int W_HALF = K * NOUT * 2;
+    constexpr int ACC_COLS = MH * TILE_PX;                // TMEM columns per accumulator stage
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
+    char* sW = smem;                                      // [hi|lo][KB][NOUT rows][128 B]
+    char* sA = smem + W_BYTES;                            // NSTAGE x {hi tile 16 KB, lo tile 16 KB}
+    float4* sCf = reinterpret_cast<float4*>(sA + NSTAGE * STAGE_BYTES);   // K coefficients
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + K);                // free[NSTAGE], accfull[2]
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + NSTAGE + 2);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, n = blockIdx.y;
+
+    // ---- one-time setup: weights, coefficients, barriers, TMEM ----
+    for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
+    al.fill(n, K, sCf);
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE + 2; ++i) mbar_init(smem_u32(&sBar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+
+    // epilogue role of this thread: TMEM lane quarter = warp % 4, pixel block = warp / 4, M-blocks j = 0..MH-1
+    const int lq = warp % 4, pc = warp / 4;
+    typename Epi::State est[MH];
+    float stat[MH][Epi::NS];
+#pragma unroll
+    for (int j = 0; j < MH; ++j) {
+        ep.init(n, NOUT, j * 128 + lq * 32 + lane, est[j]);
+#pragma unroll
+        for (int s = 0; s < Epi::NS; ++s) stat[j][s] = 0.f;
+    }
+    // producer role: 16-byte chunk c of rows r0 and r0 + 64
+    const int pc8 = tid % 8, pr = tid / 8;
+
+    const int tiles_per_frame = P / TILE_PX;
+    const int t0 = blockIdx.x * tiles_per_block, t1 = min(t0 + tiles_per_block, tiles_per_frame);
+    uint32_t use = 0;                                     // K-blocks produced so far (ring position)
+    for (int t = t0; t <= t1; ++t) {
+        const int it = t - t0;                            // local tile index
+        if (t < t1) {
+            const size_t row0 = (size_t)n * P + (size_t)t * TILE_PX;
+            const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
+            for (int kb = 0; kb < KB; ++kb, ++use) {
+                const uint32_t slot = use % NSTAGE, u = use / NSTAGE;
+                mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);          // MMAs that read this slot are done
+                char* hi = sA + slot * STAGE_BYTES;
+                char* lo = hi + STAGE_BYTES / 2;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = pr + 64 * j;
+                    float v[8];
+                    al.load8(row0 + r, K, kb * KBLK + pc8 * 8, sCf, v);
+                    const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
+                    split_store8(v, hi + off, lo + off);
+                }
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
+                    const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
+                    const uint32_t idesc = c_idesc;
+#pragma unroll
+                    for (int j = 0; j < MH; ++j) {
+                        const uint32_t d = tmem_base + acc + j * TILE_PX;
+#pragma unroll
+                        for (int k16 = 0; k16 < KBLK / 16; ++k16) {
+                            const uint64_t wa = make_desc(a_hi + j * (128 * 128) + k16 * 32);
+                            const uint64_t wl = make_desc(a_lo + j * (128 * 128) + k16 * 32);
+                            const uint64_t xa = make_desc(b_hi + k16 * 32);
+                            const uint64_t xl = make_desc(b_lo + k16 * 32);
+                            tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
+                            tc_mma(d, wa, xl, idesc, 1);
+                            tc_mma(d, wl, xa, idesc, 1);
+                        }
+                    }
+                    tc_commit(smem_u32(&sBar[slot]));                              // frees the ring slot
+                    if (kb == KB - 1) tc_commit(smem_u32(&sBar[NSTAGE + (it & 1)]));   // accumulator of this tile complete
+                }
+            }
+        }
+        if (it > 0) {
+            // epilogue of the previous tile; its MMAs were committed one iteration ago
+            const int pit = it - 1;
+            const size_t prow0 = (size_t)n * P + (size_t)(t - 1) * TILE_PX + pc * 32;
+            mbar_wait(smem_u32(&sBar[NSTAGE + (pit & 1)]), (uint32_t)(pit >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < MH; ++j) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(pit & 1) * ACC_COLS + j * TILE_PX + pc * 32, v);
+                ep.apply(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+            }
+            tc_fence_before();     // order the TMEM reads before the barrier that precedes the next overwrite of this stage
+        }
+    }
+    // per-channel statistics: 4 warps (pixel blocks) share a channel -> 4 atomics per channel per CTA
+    double* dst = ep.dst(n, NOUT);
+#pragma unroll
+    for (int j = 0; j < MH; ++j)
+#pragma unroll
+        for (int s = 0; s < Epi::NS; ++s)
+            atomicAdd(&dst[(size_t)(j * 128 + lq * 32 + lane) * Epi::NS + s], (double)stat[j][s]);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+template <int K, int NOUT, class ALoad, class Epi>
+static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t st) {
+    if (P % TILE_PX != 0) return UB_ERR_ARG;
+    constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + K * sizeof(float4) + (NSTAGE + 2) * 8 + 16 + 1024;
+    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+        attr_set = true;
+    }
+    const int tiles = P / TILE_PX;
+    const int tpb = tiles >= 8 ? 8 : tiles;
+    kern<<<dim3((tiles + tpb - 1) / tpb, N), THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P, tpb);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+// Weight image: src is fp32 [rows][K] (transpose == 0) or [K][rows] (transpose == 1, i.e. the M operand is src^T).
+// Output: bf16 hi image then lo image, each [K/64][rows][64] in the K-major SWIZZLE_128B layout.
+__global__ void prep_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ img, int rows, int K, int transpose) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * K) return;
+    const int r = i / K, k = i % K;
+    const float w = transpose ? src[(size_t)k * rows + r] : src[i];
+    const __nv_bfloat16 hb = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lb = __float2bfloat16_rn(w - __bfloat162float(hb));
+    const int kb = k / KBLK, kk = k % KBLK;
+    const size_t off = ((size_t)kb * rows + r) * 128 + (((kk / 8) ^ (r & 7)) << 4) + (kk % 8) * 2;   // bytes
+    img[off / 2] = __bfloat16_as_ushort(hb);
+    img[(off + (size_t)rows * K * 2) / 2] = __bfloat16_as_ushort(lb);
+}
+
+}  // namespace tc
+
+int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, cudaStream_t st) {
+    tc::prep_weights_kernel<<<(rows * K + 255) / 256, 256, 0, st>>>(src, static_cast<uint16_t*>(img), rows, K, transpose);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, cudaStream_t st) {
+    tc::TLoadNormed al{x, coef0};
+    tc::TEpiStoreStats ep{h1, stats1};
+    return tc::launch<UB_WIDTH, UB_HID>(al, w1img, ep, N, P, st);
+}
+int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N, int P, cudaStream_t st) {
+    tc::TLoadGeluGate al{h2, coef2, gate};
+    tc::TEpiStoreStats ep{y, stats3};
+    return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, st);
+}
+int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
+                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, cudaStream_t st) {
+    tc::TLoadNormBwd al{dout, y, bc3};
+    tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
+    return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, ep, N, P, st);
+}
+int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                 const MeanRstd* mr0, double* bstats0, int N, int P, cudaStream_t st) {
+    tc::TLoadNormBwd al{dz1, h1, bc1};
+    tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
+    return tc::launch<UB_HID, UB_WIDTH>(al, w1timg, ep, N, P, st);
+}
+int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
+    if (cudaMemcpyToSymbol(tc::c_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
+    if (cudaMemcpyToSymbol(tc::c_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;
+    if (cudaMemcpyToSymbol(tc::c_idesc, &idesc, 4) != cudaSuccess) return UB_ERR_CUDA;
+    return UB_OK;
+}
+
+}  // namespace ub

@@ -39,6 +39,17 @@ int simt_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float
 int simt_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
                 int max_parts, float* dw1, int N, int P, cudaStream_t st);
 
+// gemm_tc.cu (tcgen05 bf16x3 tensor-core versions of the four streaming GEMMs)
+int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, cudaStream_t st);
+int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, cudaStream_t st);
+int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N,
+                 int P, cudaStream_t st);
+int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
+                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, cudaStream_t st);
+int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                 const MeanRstd* mr0, double* bstats0, int N, int P, cudaStream_t st);
+int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+
 // dwconv.cu
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st);

@@ -72,6 +72,7 @@ struct BlockWs {
     size_t stats0, stats1, stats2, stats3, pool, gp;
     // coefficients
     size_t coef0, coef1, coef2, coef3, mr0, mr1, mr2, mr3, se_save, gate, w1t, w2t;
+    size_t w1img, w2img, w2timg, w1timg;   // tcgen05 weight images (bf16 hi/lo, swizzled), 128 KB each
     // backward statistics (inside the backward zero arena) and coefficients
     size_t bstats0, bstats1, bstats2, bstats3, sums3, bc0, bc1, bc2, bc3, dmp;
 };
@@ -120,6 +121,10 @@ static void block_rest(Bump& b, BlockWs& w, int N, size_t P) {
     w.gate = b.take((size_t)N * UB_HID * sizeof(float));
     w.w1t = b.take((size_t)UB_WIDTH * UB_HID * sizeof(float));
     w.w2t = b.take((size_t)UB_WIDTH * UB_HID * sizeof(float));
+    w.w1img = b.take((size_t)UB_WIDTH * UB_HID * 4);
+    w.w2img = b.take((size_t)UB_WIDTH * UB_HID * 4);
+    w.w2timg = b.take((size_t)UB_WIDTH * UB_HID * 4);
+    w.w1timg = b.take((size_t)UB_WIDTH * UB_HID * 4);
     w.bc0 = b.take((size_t)N * UB_WIDTH * sizeof(BCoef));
     w.bc1 = b.take((size_t)N * UB_HID * sizeof(BCoef));
     w.bc2 = b.take((size_t)N * UB_HID * sizeof(BCoef));
@@ -202,10 +207,22 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     const BlockWs& w = *c.w;
     const int P = c.H * c.W;
     void* ws = c.ws;
-    UB_TRY(launch_transpose(pf(c.p, UB200_B_W1), at<float>(ws, w.w1t), UB_HID, UB_WIDTH, c.st));
-    UB_TRY(launch_transpose(pf(c.p, UB200_B_W2), at<float>(ws, w.w2t), UB_WIDTH, UB_HID, c.st));
+    const bool tcb = c.backend == 1;
+    if (tcb) {
+        // M-operand images: W1 [256][128] and W2 [128][256] as stored; W2^T / W1^T for the input-gradient GEMMs
+        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, c.st));
+        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2img), UB_WIDTH, UB_HID, 0, c.st));
+        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2timg), UB_HID, UB_WIDTH, 1, c.st));
+        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1timg), UB_WIDTH, UB_HID, 1, c.st));
+    } else {
+        UB_TRY(launch_transpose(pf(c.p, UB200_B_W1), at<float>(ws, w.w1t), UB_HID, UB_WIDTH, c.st));
+        UB_TRY(launch_transpose(pf(c.p, UB200_B_W2), at<float>(ws, w.w2t), UB_WIDTH, UB_HID, c.st));
+    }
     UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
-    UB_PROF(KID_GEMM1_FWD, c.st, simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
+    if (tcb)
+        UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
+    else
+        UB_PROF(KID_GEMM1_FWD, c.st, simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
     UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
                              at<double>(ws, w.stats2), c.N, c.H, c.W, c.st));
@@ -214,8 +231,12 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
                           need_gp ? at<double>(ws, w.gp) : nullptr, c.N, P, c.st));
     UB_TRY(launch_se_fwd(at<double>(ws, w.pool), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2), at<float>(ws, w.se_save),
                          at<float>(ws, w.gate), c.N, P, c.st));
-    UB_PROF(KID_GEMM2_FWD, c.st, simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
-                          at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
+    if (tcb)
+        UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img),
+                              at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
+    else
+        UB_PROF(KID_GEMM2_FWD, c.st, simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
+                              at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats3, UB200_B_N3_W, w.coef3, w.mr3, UB_WIDTH));
     UB_PROF(KID_RESIDUAL_FWD, c.st, launch_residual_fwd(x, at<float>(ws, w.y), at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats, c.N, P, c.st));
     return UB_OK;
@@ -229,8 +250,13 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     void* ws = c.ws;
     UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
-    UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
-                          at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
+    const bool tcb = c.backend == 1;
+    if (tcb)
+        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
+                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
+    else
+        UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
+                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
     UB_PROF(KID_WGRAD2, c.st, simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                        at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
     UB_TRY(launch_se_bwd(at<double>(ws, w.sums3), at<double>(ws, w.gp), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2),
@@ -241,8 +267,12 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
-                          at<double>(ws, w.bstats0), c.N, P, c.st));
+    if (tcb)
+        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
+                              at<double>(ws, w.bstats0), c.N, P, c.st));
+    else
+        UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
+                              at<double>(ws, w.bstats0), c.N, P, c.st));
     UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                        gf(c.g, UB200_B_W1), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
@@ -290,6 +320,23 @@ extern "C" {
 int ub200_version(void) { return 100; }
 
 unsigned long long ub200_launch_count(void) { return g_launch_count; }
+
+int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
+
+// h1[N*P][256] = (x[N*P][128] * scale + shift) . W1^T, stats[N][256][2] += column (sum, sumsq): the 1x1 expand GEMM alone
+// (unit tests and the roofline micro-benchmark).  coef: [N][128] (scale, shift) pairs; scratch: 256 KB.
+int ub200_gemm1_forward(int backend, const float* x, const float* coef, const float* w1, float* h1, double* stats, int N, int P,
+                        void* scratch, void* stream) {
+    if (!x || !coef || !w1 || !h1 || !stats || !scratch || P % 128) return UB_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(stats, 0, (size_t)N * UB_HID * 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
+    if (backend == 1) {
+        UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, st));
+        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, st);
+    }
+    UB_TRY(launch_transpose(w1, static_cast<float*>(scratch), UB_HID, UB_WIDTH, st));
+    return simt_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), static_cast<const float*>(scratch), h1, stats, N, P, st);
+}
 
 int ub200_prof_enable(unsigned long long mask) {
     g_prof_mask = mask;
