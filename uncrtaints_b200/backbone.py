@@ -378,7 +378,7 @@ class UNCRTAINTS(nn.Module):
         return out
 
 
-_BACKEND = 0
+_BACKEND = 1     # tcgen05 bf16x3 GEMMs by default; 0 selects the fp32 CUDA-core GEMMs
 
 
 def set_default_gemm_backend(backend: int) -> None:
