@@ -81,7 +81,7 @@ typedef struct ub200_desc {
     int training;               /* nn.Module.training: BatchNorm batch statistics + running update, dropout on */
     int need_grad;              /* keep what ub200_backward needs */
     int mean_sigmoid;           /* out_nonlin_mean (uncrtaints.py:384) */
-    int gemm_backend;           /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 tensor-core GEMMs (bf16x3 split) */
+    int gemm_backend;           /* bit 0: tcgen05 (bf16x3) forward / input-gradient GEMMs; bit 1: tcgen05 weight-gradient GEMMs; 0 = fp32 CUDA cores */
     float scale_by;             /* uncrtaints.py:250,384 */
     float var_eps;              /* 1e-9 if scale_by == 1 else 1e-3 (uncrtaints.py:374) */
     float pad_value;            /* uncrtaints.py:245,392 */
@@ -109,6 +109,13 @@ int ub200_prof_read(int kid, double* total_ms, int* launches);
 /* Debug hook for the tcgen05 path: override the shared-memory matrix-descriptor upper word, its LBO field and the
  * instruction descriptor (defaults follow CUTLASS cute/arch/mma_sm100_desc.hpp). */
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+
+/* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
+ * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,
+ * bc1: [N][256] (a,b,c,pad) quads).  scratch: 148 * 128 KB. */
+int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const float* dz1, const float* h1, const float* bc1,
+                         float* dw1, int N, int P, void* scratch, void* stream);
 
 /* The 1x1 expand GEMM of an MBConv block alone (uncrtaints.py:126 with the PreNorm apply fused in front and the
  * Norm1 statistics behind): h1[N*P][256] = (x[N*P][128]*scale + shift) . W1^T; stats[N][256][2] = column (sum, sumsq).

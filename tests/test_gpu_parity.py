@@ -63,7 +63,7 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 3])
 def test_golden_diag_train_pad(golden_weights, backend):
     import uncrtaints_b200 as ub
     c = load_npz("case_diag_train_pad.npz")
@@ -153,7 +153,7 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 3])
 @pytest.mark.parametrize("groups,training", [(4, 1), (0, 1), (0, 0)])
 def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
     """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64)."""
@@ -222,7 +222,7 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
 @pytest.mark.parametrize("B,T,H,W,covmode,train,pad,backend", [
     (1, 2, 256, 256, "diag", True, False, 0),     # full-resolution frame (x8 upsampling), dropout mask injected
     (1, 2, 256, 256, "diag", True, False, 1),     # same through the tcgen05 GEMMs
-    (2, 5, 64, 96, "diag", True, True, 1),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
+    (2, 5, 64, 96, "diag", True, True, 3),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
     (1, 3, 128, 64, "iso", False, False, 0),      # eval mode, isotropic covariance
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
@@ -340,3 +340,29 @@ def test_gemm1_op_vs_fp64(backend):
     eq = rel_l2(stats[..., 1], (ref ** 2).sum(1))
     report("parity_report.txt", [f"gemm1 op backend={backend}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
     assert e < 5e-5 and es < 1e-4 and eq < 1e-4
+
+
+@pytest.mark.parametrize("backend", [0, 2])
+def test_wgrad1_op_vs_fp64(backend):
+    """Weight-gradient GEMM alone (ub200_wgrad1_forward): CUDA-core path and tcgen05 MN-major bf16x3 path vs fp64."""
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    N, P = 3, 1024
+    g = torch.Generator("cpu").manual_seed(33)
+    x = torch.randn(N, P, 128, generator=g)
+    dz1 = torch.randn(N, P, 256, generator=g)
+    h1 = torch.randn(N, P, 256, generator=g)
+    coef0 = torch.stack([torch.rand(N, 128, generator=g) + 0.5, torch.randn(N, 128, generator=g)], dim=-1).contiguous()
+    bc1 = torch.cat([torch.randn(N, 256, 3, generator=g), torch.zeros(N, 256, 1)], dim=-1).contiguous()
+    n0 = x.double() * coef0[:, None, :, 0].double() + coef0[:, None, :, 1].double()
+    dh1 = bc1[:, None, :, 0].double() * dz1.double() + bc1[:, None, :, 1].double() * h1.double() + bc1[:, None, :, 2].double()
+    ref = torch.einsum("npo,npk->ok", dh1, n0)
+    dw1 = torch.zeros(256, 128, device="cuda")
+    scratch = torch.empty(148 * 128 * 256 * 4, dtype=torch.uint8, device="cuda")
+    args = [t.cuda() for t in (x, coef0, dz1, h1, bc1)]
+    _lib.check(L.ub200_wgrad1_forward(backend, *[a.data_ptr() for a in args], dw1.data_ptr(), N, P, scratch.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), "wgrad1_forward")
+    torch.cuda.synchronize()
+    e = rel_l2(dw1, ref)
+    report("parity_report.txt", [f"wgrad1 op backend={backend}: rel_l2={e:.3e}"])
+    assert e < 5e-5

@@ -315,6 +315,12 @@ static int launch_wgrad(LA la, LB lb, float* partial, int max_parts, float* grad
     return UB_OK;
 }
 
+int launch_reduce_partials(const float* partial, float* grad, int count, int nparts, cudaStream_t st) {
+    reduce_partials_kernel<<<(count + 255) / 256, 256, 0, st>>>(partial, grad, count, nparts);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
 // [rows][cols] -> [cols][rows]; used once per step for the forward weight layouts
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

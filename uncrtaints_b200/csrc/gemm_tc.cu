@@ -334,6 +334,149 @@ static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t
     return UB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// weight gradient on tensor cores:  dW[m][n] = sum_px fa(px)[m] * fb(px)[n],  m < 128, n < 256
+//
+// The contraction runs over pixels, i.e. over the ROWS of the pixel-major tiles, so both operands are
+// "MN-major" for the MMA.  The canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) [uint128
+// units, cute/atom/mma_traits_sm100.hpp] is byte-for-byte the layout the producers already write for K-major
+// tiles: 128-byte rows (one pixel, 64 channels), 8-row 1024-byte atoms with the 16-byte chunk index XOR row%8.
+// Column blocks of 64 channels are LBO apart, 8-pixel groups SBO = 1024 B apart; one MMA consumes 16 pixels.
+// One persistent CTA per SM walks a contiguous range of 64-pixel tiles (2-stage ring), accumulating the whole
+// 128 x 256 gradient in TMEM (256 columns); partials are summed by reduce_partials_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int WG_PX = 64;
+constexpr int WG_A_BYTES = 2 * WG_PX * 128 * 2;      // hi+lo, 128 channels: 32 KB
+constexpr int WG_B_BYTES = 2 * WG_PX * 256 * 2;      // hi+lo, 256 channels: 64 KB
+constexpr int WG_STAGE = WG_A_BYTES + WG_B_BYTES;    // 96 KB
+constexpr int WG_BLK = WG_PX * 128;                  // one [64 px][64 ch] bf16 block: 8 KB
+
+__device__ __constant__ uint32_t c_wg_desc_hi = (64u) | (1u << 14) | (2u << 29);                  // SBO = 1024 B
+__device__ __constant__ uint32_t c_wg_desc_lbo = (uint32_t)(WG_BLK >> 4);                           // LBO = 8 KB between 64-channel blocks
+__device__ __constant__ uint32_t c_wg_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (32u << 17) | (8u << 24);
+
+__device__ __forceinline__ uint64_t make_wg_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(c_wg_desc_lbo & 0x3FFFu) << 16) | ((uint64_t)c_wg_desc_hi << 32);
+}
+
+template <class LA, class LB>
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long total_tiles, int sa, int sb) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    char* sStage = smem;                                                       // 2 x {A hi, A lo, B hi, B lo}
+    float4* sCfA = reinterpret_cast<float4*>(smem + 2 * WG_STAGE);            // 128 coefficients
+    float4* sCfB = sCfA + 128;                                                 // 256 coefficients
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCfB + 256);                 // free[2], done
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 3);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sBar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+
+    const int tiles_per_frame = P / WG_PX;
+    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
+    int cur_n = -1;
+    uint32_t use = 0;
+    for (long long t = t0; t < t1; ++t, ++use) {
+        const int n = (int)(t / tiles_per_frame);
+        if (n != cur_n) {                       // block-uniform: refill the per-frame coefficients
+            __syncthreads();
+            la.fill(n, 128, sCfA);
+            lb.fill(n, 256, sCfB);
+            cur_n = n;
+            __syncthreads();
+        }
+        const size_t row0 = (size_t)t * WG_PX;
+        const uint32_t slot = use & 1, u = use >> 1;
+        mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);
+        char* a_hi = sStage + slot * WG_STAGE;
+        char* a_lo = a_hi + WG_A_BYTES / 2;
+        char* b_hi = a_hi + WG_A_BYTES;
+        char* b_lo = b_hi + WG_B_BYTES / 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {           // A operand: 64 rows x 16 chunks
+            const int i = tid + THREADS * j, r = i / 16, c = i % 16;
+            float v[8];
+            la.load8(row0 + r, 128, c * 8, sCfA, v);
+            const int off = (c / 8) * WG_BLK + r * 128 + (((c % 8) ^ (r & 7)) << 4);
+            split_store8(v, a_hi + off, a_lo + off);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {           // B operand: 64 rows x 32 chunks
+            const int i = tid + THREADS * j, r = i / 32, c = i % 32;
+            float v[8];
+            lb.load8(row0 + r, 256, c * 8, sCfB, v);
+            const int off = (c / 8) * WG_BLK + r * 128 + (((c % 8) ^ (r & 7)) << 4);
+            split_store8(v, b_hi + off, b_lo + off);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t idesc = c_wg_idesc;
+#pragma unroll
+            for (int p16 = 0; p16 < WG_PX / 16; ++p16) {
+                const uint64_t ah = make_wg_desc(smem_u32(a_hi) + p16 * 2048), al = make_wg_desc(smem_u32(a_lo) + p16 * 2048);
+                const uint64_t bh = make_wg_desc(smem_u32(b_hi) + p16 * 2048), bl = make_wg_desc(smem_u32(b_lo) + p16 * 2048);
+                tc_mma(tmem_base, ah, bh, idesc, (use | (uint32_t)p16) != 0);
+                tc_mma(tmem_base, ah, bl, idesc, 1);
+                tc_mma(tmem_base, al, bh, idesc, 1);
+            }
+            tc_commit(smem_u32(&sBar[slot]));
+            if (t == t1 - 1) tc_commit(smem_u32(&sBar[2]));
+        }
+    }
+    float* dst = partial + (size_t)blockIdx.x * 128 * 256;
+    if (t1 > t0) {
+        mbar_wait(smem_u32(&sBar[2]), 0);
+        tc_fence_after();
+        const int lq = warp % 4, cb = warp / 4;          // lanes lq*32.., columns cb*64..
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + cb * 64 + h * 32, v);
+            const int m = lq * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)m * sa + (size_t)(cb * 64 + h * 32 + i) * sb] = v[i];
+        }
+    } else {
+        for (int i = tid; i < 128 * 256; i += THREADS) dst[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+template <class LA, class LB>
+static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb, int* nparts, cudaStream_t st) {
+    if (P % WG_PX != 0) return UB_ERR_ARG;
+    constexpr size_t smem = (size_t)2 * WG_STAGE + 384 * sizeof(float4) + 3 * 8 + 16 + 1024;
+    auto kern = wgrad_tc_kernel<LA, LB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+        attr_set = true;
+    }
+    const long long total = (long long)N * (P / WG_PX);
+    const int blocks = (int)(total < max_parts ? total : max_parts);
+    kern<<<blocks, THREADS, smem, st>>>(la, lb, partial, P, total, sa, sb);
+    UB_CHECK_LAUNCH();
+    *nparts = blocks;
+    return UB_OK;
+}
+
 // Weight image: src is fp32 [rows][K] (transpose == 0) or [K][rows] (transpose == 1, i.e. the M operand is src^T).
 // Output: bf16 hi image then lo image, each [K/64][rows][64] in the K-major SWIZZLE_128B layout.
 __global__ void prep_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ img, int rows, int K, int transpose) {
@@ -377,6 +520,32 @@ int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void
     tc::TLoadNormBwd al{dz1, h1, bc1};
     tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
     return tc::launch<UB_HID, UB_WIDTH>(al, w1timg, ep, N, P, st);
+}
+// dW2[o][k] += sum_p dy[p][o] * u[p][k]
+int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
+              float* partial, int max_parts, float* dw2, int N, int P, cudaStream_t st) {
+    tc::TLoadNormBwd la{dout, y, bc3};
+    tc::TLoadGeluGate lb{h2, coef2, gate};
+    int nparts = 0;
+    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, UB_HID, 1, &nparts, st);
+    if (rc != UB_OK) return rc;
+    return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
+}
+// dW1[o][k] += sum_p dh1[p][o] * n0[p][k]   (M side = n0 (128 channels, index k), N side = dh1 (256 channels, index o))
+int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
+              int max_parts, float* dw1, int N, int P, cudaStream_t st) {
+    tc::TLoadNormed la{x, coef0};
+    tc::TLoadNormBwd lb{dz1, h1, bc1};
+    int nparts = 0;
+    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, 1, UB_WIDTH, &nparts, st);
+    if (rc != UB_OK) return rc;
+    return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
+}
+int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
+    if (cudaMemcpyToSymbol(tc::c_wg_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
+    if (cudaMemcpyToSymbol(tc::c_wg_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;
+    if (cudaMemcpyToSymbol(tc::c_wg_idesc, &idesc, 4) != cudaSuccess) return UB_ERR_CUDA;
+    return UB_OK;
 }
 int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
     if (cudaMemcpyToSymbol(tc::c_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;

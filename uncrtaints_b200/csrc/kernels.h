@@ -27,6 +27,7 @@ int launch_residual_bwd(const float* dout, const float* dn0, const float* x, con
 
 // gemm_simt.cu
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);
+int launch_reduce_partials(const float* partial, float* grad, int count, int nparts, cudaStream_t st);
 int simt_gemm1_fwd(const float* x, const Coef* coef0, const float* w1t, float* h1, double* stats1, int N, int P, cudaStream_t st);
 int simt_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const float* w2t, float* y, double* stats3, int N,
                    int P, cudaStream_t st);
@@ -48,7 +49,12 @@ int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void
                  const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, cudaStream_t st);
 int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
                  const MeanRstd* mr0, double* bstats0, int N, int P, cudaStream_t st);
+int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
+              float* partial, int max_parts, float* dw2, int N, int P, cudaStream_t st);
+int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
+              int max_parts, float* dw1, int N, int P, cudaStream_t st);
 int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 
 // dwconv.cu
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,

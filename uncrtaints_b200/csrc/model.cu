@@ -207,7 +207,7 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     const BlockWs& w = *c.w;
     const int P = c.H * c.W;
     void* ws = c.ws;
-    const bool tcb = c.backend == 1;
+    const bool tcb = (c.backend & 1) != 0;
     if (tcb) {
         // M-operand images: W1 [256][128] and W2 [128][256] as stored; W2^T / W1^T for the input-gradient GEMMs
         UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, c.st));
@@ -250,15 +250,19 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     void* ws = c.ws;
     UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
-    const bool tcb = c.backend == 1;
+    const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
     if (tcb)
         UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
     else
         UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    UB_PROF(KID_WGRAD2, c.st, simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
-                       at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
+    if (tcw)
+        UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
+                           at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
+    else
+        UB_PROF(KID_WGRAD2, c.st, simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
+                           at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
     UB_TRY(launch_se_bwd(at<double>(ws, w.sums3), at<double>(ws, w.gp), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2),
                          at<float>(ws, w.se_save), gf(c.g, UB200_B_F1), gf(c.g, UB200_B_F2), at<float>(ws, w.dmp),
                          at<double>(ws, w.bstats2), c.N, P, c.st));
@@ -273,8 +277,12 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     else
         UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
-    UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
-                       gf(c.g, UB200_B_W1), c.N, P, c.st));
+    if (tcw)
+        UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
+                           gf(c.g, UB200_B_W1), c.N, P, c.st));
+    else
+        UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
+                           gf(c.g, UB200_B_W1), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
     UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.st));
     return UB_OK;
@@ -322,6 +330,20 @@ int ub200_version(void) { return 100; }
 unsigned long long ub200_launch_count(void) { return g_launch_count; }
 
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
+int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set_wgrad(desc_hi, desc_lbo, idesc); }
+
+// dW1[256][128] = sum_p dh1[p][o] * n0[p][k] with n0 = x*coef0 (x: [N*P][128]) and dh1 = a*dz1 + b*h1 + c ([N*P][256]):
+// the weight-gradient GEMM of the 1x1 expand convolution alone (unit tests).  dw1 is accumulated into.
+int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const float* dz1, const float* h1, const float* bc1,
+                         float* dw1, int N, int P, void* scratch, void* stream) {
+    if (!x || !coef0 || !dz1 || !h1 || !bc1 || !dw1 || !scratch || P % 64) return UB_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (backend & 2)
+        return tc_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
+                         static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
+    return simt_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
+                       static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
+}
 
 // h1[N*P][256] = (x[N*P][128] * scale + shift) . W1^T, stats[N][256][2] += column (sum, sumsq): the 1x1 expand GEMM alone
 // (unit tests and the roofline micro-benchmark).  coef: [N][128] (scale, shift) pairs; scratch: 256 KB.
@@ -330,7 +352,7 @@ int ub200_gemm1_forward(int backend, const float* x, const float* coef, const fl
     if (!x || !coef || !w1 || !h1 || !stats || !scratch || P % 128) return UB_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(stats, 0, (size_t)N * UB_HID * 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
-    if (backend == 1) {
+    if (backend & 1) {
         UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, st));
         return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, st);
     }
