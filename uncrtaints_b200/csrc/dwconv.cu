@@ -6,48 +6,52 @@
 //      dg1 = DW3x3^T(dh2) with the adjoint of reflect padding;  dz1 = dg1 * gelu'(z1)
 //      dWdw[c][i][j] += sum_p dh2[p] * g1[reflect(p + (i-1, j-1))];  bstats1 += (sum dz1, sum dz1*h1_hat)
 //
-// A CTA owns a 32-column strip of one frame for a 64-channel chunk and walks down the image in tiles of
-// 8 rows; the (8+2) x (32+2) x 64 halo tile of the transformed operand lives in shared memory, so the
-// normalisation + GELU is evaluated once per element (1.33x with halo) instead of 9x.  Reflection is index
-// arithmetic on the load (no padded copy as in the reference's F.pad path).
+// A CTA owns a 32-column strip of one frame for a 32-channel chunk (one 128-byte line per pixel) and walks down the
+// image in tiles of 8 rows; the (8+2) x (32+2) x 32 halo tile of the transformed operand lives in shared memory
+// (43.5 KB), so the normalisation + GELU is evaluated once per element (1.33x with halo) instead of 9x, and 4-5
+// (forward) / 2 (backward) CTAs are resident per SM to overlap one CTA's load phase with another's stencil phase.
+// Reflection is index arithmetic on the load (no padded copy as in the reference's F.pad path).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ub {
 
-constexpr int DW_TH = 8, DW_TW = 32, DW_CC = 64;            // tile rows, cols, channel chunk
+constexpr int DW_TH = 8, DW_TW = 32, DW_CC = 32;            // tile rows, cols, channel chunk
+constexpr int DW_Q = DW_CC / 4;                              // channel quads per chunk (8)
+constexpr int DW_PT = 256 / DW_Q;                            // pixel threads (32): one column each
 constexpr int DW_HR = DW_TH + 2, DW_HC = DW_TW + 2;         // halo tile
-constexpr int DW_TILE_FLOATS = DW_HR * DW_HC * DW_CC;       // 21760 floats = 87 KB
+constexpr int DW_TILE_FLOATS = DW_HR * DW_HC * DW_CC;       // 10880 floats = 43.5 KB
 
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-// reduce per-thread float4 partials over the 16 pixel-threads (tid/16) for each of the 16 channel quads
+// reduce per-thread float4 partials over the 32 pixel-threads (tid / 8) for each of the 8 channel quads and add the
+// result to dst[ch][0..1] (fp64)
 __device__ __forceinline__ void reduce_pt_atomic2(float4 a, float4 b, double* dst /* &stats[n][cbase][0] */, float* smem) {
-    const int cq = threadIdx.x % 16, pt = threadIdx.x / 16;
+    const int cq = threadIdx.x % DW_Q, pt = threadIdx.x / DW_Q;
     float4* sa = reinterpret_cast<float4*>(smem);
     float4* sb = sa + 256;
     __syncthreads();
-    sa[pt * 16 + cq] = a;
-    sb[pt * 16 + cq] = b;
+    sa[pt * DW_Q + cq] = a;
+    sb[pt * DW_Q + cq] = b;
     __syncthreads();
-    if (threadIdx.x < 128) {
-        const int which = threadIdx.x / 64, ch = threadIdx.x % 64;
+    if (threadIdx.x < 2 * DW_CC) {
+        const int which = threadIdx.x / DW_CC, ch = threadIdx.x % DW_CC;
         const float* src = reinterpret_cast<const float*>(which ? sb : sa);
         double t = 0.0;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) t += (double)src[r * 64 + ch];
+#pragma unroll 8
+        for (int r = 0; r < DW_PT; ++r) t += (double)src[r * DW_CC + ch];
         atomicAdd(&dst[ch * 2 + which], t);
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 3)
 dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, const float* __restrict__ wdw /* [256][9] */,
                   float* __restrict__ h2, double* stats2, int H, int W) {
     extern __shared__ __align__(16) float tile[];
     constexpr int C = UB_HID;
     const int n = blockIdx.z, cbase = blockIdx.y * DW_CC, x0 = blockIdx.x * DW_TW;
-    const int cq = threadIdx.x % 16, pt = threadIdx.x / 16;
+    const int cq = threadIdx.x % DW_Q, col = threadIdx.x / DW_Q;
     const int c0 = cbase + cq * 4;
     Coef k[4];
     float w[9][4];
@@ -63,8 +67,8 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        for (int e = threadIdx.x; e < DW_HR * DW_HC * 16; e += 256) {   // e % 16 == cq
-            const int pix = e / 16, ry = pix / DW_HC, rx = pix % DW_HC;
+        for (int e = threadIdx.x; e < DW_HR * DW_HC * DW_Q; e += 256) {   // e % 8 == cq
+            const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
             const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
             const float4 v = ld4(src + ((size_t)sy * W + sx) * C + c0);
             float4 g;
@@ -75,31 +79,36 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
             st4(tile + pix * DW_CC + cq * 4, g);
         }
         __syncthreads();
-#pragma unroll 1
-        for (int col = pt * 2; col < pt * 2 + 2; ++col) {
+        // one column per thread, 8 output rows
 #pragma unroll 2
-            for (int r = 0; r < DW_TH; ++r) {
-                float4 o = make_float4(0, 0, 0, 0);
+        for (int r = 0; r < DW_TH; ++r) {
+            float4 o = make_float4(0, 0, 0, 0);
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const float4 t = ld4(tile + ((r + i) * DW_HC + col + j) * DW_CC + cq * 4);
-                        o.x = fmaf(w[i * 3 + j][0], t.x, o.x);
-                        o.y = fmaf(w[i * 3 + j][1], t.y, o.y);
-                        o.z = fmaf(w[i * 3 + j][2], t.z, o.z);
-                        o.w = fmaf(w[i * 3 + j][3], t.w, o.w);
-                    }
-                st4(dst + ((size_t)(y0 + r) * W + x0 + col) * C + c0, o);
-                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-                q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
-            }
+                for (int j = 0; j < 3; ++j) {
+                    const float4 t = ld4(tile + ((r + i) * DW_HC + col + j) * DW_CC + cq * 4);
+                    o.x = fmaf(w[i * 3 + j][0], t.x, o.x);
+                    o.y = fmaf(w[i * 3 + j][1], t.y, o.y);
+                    o.z = fmaf(w[i * 3 + j][2], t.z, o.z);
+                    o.w = fmaf(w[i * 3 + j][3], t.w, o.w);
+                }
+            st4(dst + ((size_t)(y0 + r) * W + x0 + col) * C + c0, o);
+            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+            q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
         }
     }
     reduce_pt_atomic2(s, q, stats2 + ((size_t)n * C + cbase) * 2, tile);
 }
 
-__global__ void __launch_bounds__(256, 1)
+// per-chunk coefficient block staged in shared memory for the backward kernel (one float4 per channel and kind)
+struct DwBwdCoef {
+    float4 k2sg[DW_CC];   // scale2, shift2, gate, dpool/P
+    float4 b2[DW_CC];     // a2, b2, c2, -
+    float4 k1m1[DW_CC];   // scale1, shift1, mean1, rstd1
+};
+
+__global__ void __launch_bounds__(256, 2)
 dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
                   const float* __restrict__ gate /* s[n][c] */, const float* __restrict__ dmp /* dpool/P [n][c] */,
                   const Coef* __restrict__ coef2, const BCoef* __restrict__ bc2, const Coef* __restrict__ coef1,
@@ -108,32 +117,37 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
     extern __shared__ __align__(16) float smem[];
     float* tdh = smem;                       // dh2, zero outside the image
     float* tg = smem + DW_TILE_FLOATS;       // g1 = gelu(z1) at reflected positions
+    DwBwdCoef* cf = reinterpret_cast<DwBwdCoef*>(smem + 2 * DW_TILE_FLOATS);
     constexpr int C = UB_HID;
     const int n = blockIdx.z, cbase = blockIdx.y * DW_CC, x0 = blockIdx.x * DW_TW;
-    const int cq = threadIdx.x % 16, pt = threadIdx.x / 16;
+    const int cq = threadIdx.x % DW_Q, col = threadIdx.x / DW_Q;
     const int c0 = cbase + cq * 4;
-    Coef k2[4], k1[4];
-    BCoef b2[4];
-    MeanRstd m1[4];
-    float sg[4], dm[4], w[9][4];
+    if (threadIdx.x < DW_CC) {
+        const size_t ci = (size_t)n * C + cbase + threadIdx.x;
+        const Coef a = coef2[ci], b = coef1[ci];
+        const BCoef bb = bc2[ci];
+        const MeanRstd m = mr1[ci];
+        cf->k2sg[threadIdx.x] = make_float4(a.scale, a.shift, gate[ci], dmp[ci]);
+        cf->b2[threadIdx.x] = make_float4(bb.a, bb.b, bb.c, 0.f);
+        cf->k1m1[threadIdx.x] = make_float4(b.scale, b.shift, m.mean, m.rstd);
+    }
+    float w[9][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const size_t ci = (size_t)n * C + c0 + i;
-        k2[i] = coef2[ci]; k1[i] = coef1[ci]; b2[i] = bc2[ci]; m1[i] = mr1[ci];
-        sg[i] = gate[ci]; dm[i] = dmp[ci];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 9; ++j) w[j][i] = wdw[(size_t)(c0 + i) * 9 + j];
-    }
     const size_t fbase = (size_t)n * H * W * C;
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     float4 gw[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) gw[j] = make_float4(0, 0, 0, 0);
+    const int qx = x0 + col;
+    const bool x_lo = (qx == 1), x_hi = (qx == W - 2);
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        for (int e = threadIdx.x; e < DW_HR * DW_HC * 16; e += 256) {
-            const int pix = e / 16, ry = pix / DW_HC, rx = pix % DW_HC;
+        for (int e = threadIdx.x; e < DW_HR * DW_HC * DW_Q; e += 256) {
+            const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
             const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
             float4 dh = make_float4(0, 0, 0, 0);
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
@@ -144,89 +158,85 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
                 float o[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float z = fmaf(hvv[i], k2[i].scale, k2[i].shift);
-                    const float dz = fmaf(dvv[i], sg[i], dm[i]) * gelu_grad_f(z);
-                    o[i] = fmaf(b2[i].a, dz, fmaf(b2[i].b, hvv[i], b2[i].c));
+                    const float4 k2 = cf->k2sg[cq * 4 + i], b2 = cf->b2[cq * 4 + i];
+                    const float z = fmaf(hvv[i], k2.x, k2.y);
+                    const float dz = fmaf(dvv[i], k2.z, k2.w) * gelu_grad_f(z);
+                    o[i] = fmaf(b2.x, dz, fmaf(b2.y, hvv[i], b2.z));
                 }
                 dh = make_float4(o[0], o[1], o[2], o[3]);
             }
             st4(tdh + pix * DW_CC + cq * 4, dh);
             const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
             const float4 v = ld4(h1 + fbase + ((size_t)sy * W + sx) * C + c0);
-            float4 g;
-            g.x = gelu_f(fmaf(v.x, k1[0].scale, k1[0].shift));
-            g.y = gelu_f(fmaf(v.y, k1[1].scale, k1[1].shift));
-            g.z = gelu_f(fmaf(v.z, k1[2].scale, k1[2].shift));
-            g.w = gelu_f(fmaf(v.w, k1[3].scale, k1[3].shift));
-            st4(tg + pix * DW_CC + cq * 4, g);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            float g[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
+            st4(tg + pix * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
         }
         __syncthreads();
 #pragma unroll 1
-        for (int col = pt * 2; col < pt * 2 + 2; ++col) {
-            const int qx = x0 + col;
-            const bool x_lo = (qx == 1), x_hi = (qx == W - 2);
-#pragma unroll 1
-            for (int r = 0; r < DW_TH; ++r) {
-                const int qy = y0 + r;
-                const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
-                const float4 dhc = ld4(tdh + ((r + 1) * DW_HC + col + 1) * DW_CC + cq * 4);
-                float4 o = make_float4(0, 0, 0, 0);
+        for (int r = 0; r < DW_TH; ++r) {
+            const int qy = y0 + r;
+            const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
+            const float4 dhc = ld4(tdh + ((r + 1) * DW_HC + col + 1) * DW_CC + cq * 4);
+            float4 o = make_float4(0, 0, 0, 0);
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
+            for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        // adjoint of reflect padding: source p = q + (dy, dx) reaches q through tap (1-dy, 1-dx) and,
-                        // on rows/cols 1 and H-2 / W-2, additionally through the reflected tap.
-                        const float4 t = ld4(tdh + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
-                        const int i0 = 1 - dy, j0 = 1 - dx;               // compile-time after unrolling
-                        const int i1 = (dy == -1) ? 0 : 2, j1 = (dx == -1) ? 0 : 2;
-                        const bool ya = (dy == -1) ? y_lo : ((dy == 1) ? y_hi : false);
-                        const bool xa = (dx == -1) ? x_lo : ((dx == 1) ? x_hi : false);
-                        float we[4];
+                for (int dx = -1; dx <= 1; ++dx) {
+                    // adjoint of reflect padding: source p = q + (dy, dx) reaches q through tap (1-dy, 1-dx) and,
+                    // on rows/cols 1 and H-2 / W-2, additionally through the reflected tap.
+                    const float4 t = ld4(tdh + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
+                    const int i0 = 1 - dy, j0 = 1 - dx;               // compile-time after unrolling
+                    const int i1 = (dy == -1) ? 0 : 2, j1 = (dx == -1) ? 0 : 2;
+                    const bool ya = (dy == -1) ? y_lo : ((dy == 1) ? y_hi : false);
+                    const bool xa = (dx == -1) ? x_lo : ((dx == 1) ? x_hi : false);
+                    float we[4];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float v = w[i0 * 3 + j0][c];
-                            if (xa) v += w[i0 * 3 + j1][c];
-                            if (ya) v += w[i1 * 3 + j0][c];
-                            if (ya && xa) v += w[i1 * 3 + j1][c];
-                            we[c] = v;
-                        }
-                        o.x = fmaf(we[0], t.x, o.x); o.y = fmaf(we[1], t.y, o.y);
-                        o.z = fmaf(we[2], t.z, o.z); o.w = fmaf(we[3], t.w, o.w);
-                        // depthwise weight gradient: tap (dy+1, dx+1) pairs dh2[q] with g1[reflect(q + (dy, dx))]
-                        const float4 g = ld4(tg + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
-                        float4& a = gw[(dy + 1) * 3 + dx + 1];
-                        a.x = fmaf(dhc.x, g.x, a.x); a.y = fmaf(dhc.y, g.y, a.y);
-                        a.z = fmaf(dhc.z, g.z, a.z); a.w = fmaf(dhc.w, g.w, a.w);
+                    for (int c = 0; c < 4; ++c) {
+                        float v = w[i0 * 3 + j0][c];
+                        if (xa) v += w[i0 * 3 + j1][c];
+                        if (ya) v += w[i1 * 3 + j0][c];
+                        if (ya && xa) v += w[i1 * 3 + j1][c];
+                        we[c] = v;
                     }
-                const size_t off = fbase + ((size_t)qy * W + qx) * C + c0;
-                const float4 hv = ld4(h1 + off);
-                const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
-                const float ov[4] = {o.x, o.y, o.z, o.w};
-                float dz[4], dzh[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float z = fmaf(hvv[c], k1[c].scale, k1[c].shift);
-                    dz[c] = ov[c] * gelu_grad_f(z);
-                    dzh[c] = dz[c] * (hvv[c] - m1[c].mean) * m1[c].rstd;
+                    o.x = fmaf(we[0], t.x, o.x); o.y = fmaf(we[1], t.y, o.y);
+                    o.z = fmaf(we[2], t.z, o.z); o.w = fmaf(we[3], t.w, o.w);
+                    // depthwise weight gradient: tap (dy+1, dx+1) pairs dh2[q] with g1[reflect(q + (dy, dx))]
+                    const float4 g = ld4(tg + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
+                    float4& a = gw[(dy + 1) * 3 + dx + 1];
+                    a.x = fmaf(dhc.x, g.x, a.x); a.y = fmaf(dhc.y, g.y, a.y);
+                    a.z = fmaf(dhc.z, g.z, a.z); a.w = fmaf(dhc.w, g.w, a.w);
                 }
-                st4(dz1 + off, make_float4(dz[0], dz[1], dz[2], dz[3]));
-                s.x += dz[0]; s.y += dz[1]; s.z += dz[2]; s.w += dz[3];
-                q.x += dzh[0]; q.y += dzh[1]; q.z += dzh[2]; q.w += dzh[3];
+            const size_t off = fbase + ((size_t)qy * W + qx) * C + c0;
+            const float4 hv = ld4(h1 + off);
+            const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+            float dz[4], dzh[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 k1 = cf->k1m1[cq * 4 + c];
+                const float z = fmaf(hvv[c], k1.x, k1.y);
+                dz[c] = ov[c] * gelu_grad_f(z);
+                dzh[c] = dz[c] * (hvv[c] - k1.z) * k1.w;
             }
+            st4(dz1 + off, make_float4(dz[0], dz[1], dz[2], dz[3]));
+            s.x += dz[0]; s.y += dz[1]; s.z += dz[2]; s.w += dz[3];
+            q.x += dzh[0]; q.y += dzh[1]; q.z += dzh[2]; q.w += dzh[3];
         }
     }
     reduce_pt_atomic2(s, q, bstats1 + ((size_t)n * C + cbase) * 2, smem);
-    // depthwise weight gradient: reduce over the 16 pixel-threads, one atomic per (channel, tap) per CTA
-    float* red = smem;  // [9][16 pt][64 ch]
+    // depthwise weight gradient: reduce over the 32 pixel-threads, one atomic per (channel, tap) per CTA
+    float* red = smem;  // [9][32 pt][32 ch]
 #pragma unroll
-    for (int j = 0; j < 9; ++j) st4(red + (j * 16 + pt) * 64 + cq * 4, gw[j]);
+    for (int j = 0; j < 9; ++j) st4(red + (j * DW_PT + col) * DW_CC + cq * 4, gw[j]);
     __syncthreads();
-    for (int e = threadIdx.x; e < 9 * 64; e += 256) {
-        const int j = e / 64, ch = e % 64;
+    for (int e = threadIdx.x; e < 9 * DW_CC; e += 256) {
+        const int j = e / DW_CC, ch = e % DW_CC;
         float t = 0.f;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) t += red[(j * 16 + r) * 64 + ch];
+#pragma unroll 8
+        for (int r = 0; r < DW_PT; ++r) t += red[(j * DW_PT + r) * DW_CC + ch];
         atomicAdd(&dwdw[(size_t)(cbase + ch) * 9 + j], t);
     }
 }
@@ -249,7 +259,7 @@ int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const f
                       const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
                       float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st) {
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
-    constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float);
+    constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float) + sizeof(DwBwdCoef);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;

@@ -88,8 +88,9 @@ struct EpiGemm2Bwd {           // B5b: du = acc; sums (du*g2, du*gp2, du*gp2*h2h
             const Coef k = ldg(&coef2[(size_t)n * UB_HID + col + i]);
             const MeanRstd m = ldg(&mr2[(size_t)n * UB_HID + col + i]);
             const float z = fmaf(hv[i], k.scale, k.shift);
-            const float gp = gelu_grad_f(z);
-            r0[i] = dv[i] * gelu_f(z);
+            float gz, gp;
+            gelu_both(z, gz, gp);
+            r0[i] = dv[i] * gz;
             r1[i] = dv[i] * gp;
             r2[i] = dv[i] * gp * (hv[i] - m.mean) * m.rstd;
         }

@@ -94,47 +94,67 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], char* hi_chunk
 }
 
 // ------------------------------------------------------------------------------------------
-// operand loaders: per-frame coefficients live in shared memory as float4 per input channel
+// operand loaders.  issue(): raw global loads only (kept in flight across the previous K-block's convert / MMA
+// issue / epilogue).  finish(): apply the transform with the per-frame coefficients, which live in shared memory as
+// three structure-of-arrays vectors cf[0..K), cf[K..2K), cf[2K..3K) (conflict-free 32-byte reads per lane).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4_nc(const float* p) {      // read-only path WITH L1 allocation: the two 16-byte halves of
+    float4 r;                                                     // a lane's 32-byte piece share sectors
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = ld4_nc(p), b = ld4_nc(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 struct TLoadNormed {           // a = x*scale + shift
     const float* x; const Coef* coef;
-    __device__ void fill(int n, int K, float4* cf) const {
-        for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; cf[k] = make_float4(c.scale, c.shift, 0.f, 0.f); }
+    struct Raw { float a[8]; };
+    __device__ void fill(int n, int K, float* cf) const {
+        for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; cf[k] = c.scale; cf[K + k] = c.shift; }
     }
-    __device__ void load8(size_t row, int K, int ch0, const float4* cf, float (&v)[8]) const {
-        const float4 a = ld4_stream(x + row * K + ch0), b = ld4_stream(x + row * K + ch0 + 4);
-        const float in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(x + row * K + ch0, r.a); }
+    __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
+        float sc[8], sh[8];
+        lds8(cf + ch0, sc); lds8(cf + K + ch0, sh);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 c = cf[ch0 + i]; v[i] = fmaf(in[i], c.x, c.y); }
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(r.a[i], sc[i], sh[i]);
     }
 };
 struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
     const float* h2; const Coef* coef; const float* gate;
-    __device__ void fill(int n, int K, float4* cf) const {
+    struct Raw { float a[8]; };
+    __device__ void fill(int n, int K, float* cf) const {
         for (int k = threadIdx.x; k < K; k += THREADS) {
             const Coef c = coef[(size_t)n * K + k];
-            cf[k] = make_float4(c.scale, c.shift, gate[(size_t)n * K + k], 0.f);
+            cf[k] = c.scale; cf[K + k] = c.shift; cf[2 * K + k] = gate[(size_t)n * K + k];
         }
     }
-    __device__ void load8(size_t row, int K, int ch0, const float4* cf, float (&v)[8]) const {
-        const float4 a = ld4_stream(h2 + row * K + ch0), b = ld4_stream(h2 + row * K + ch0 + 4);
-        const float in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(h2 + row * K + ch0, r.a); }
+    __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
+        float sc[8], sh[8], g[8];
+        lds8(cf + ch0, sc); lds8(cf + K + ch0, sh); lds8(cf + 2 * K + ch0, g);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 c = cf[ch0 + i]; v[i] = gelu_f(fmaf(in[i], c.x, c.y)) * c.z; }
+        for (int i = 0; i < 8; ++i) v[i] = gelu_f(fmaf(r.a[i], sc[i], sh[i])) * g[i];
     }
 };
 struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
     const float* dy; const float* vv; const BCoef* bc;
-    __device__ void fill(int n, int K, float4* cf) const {
-        for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; cf[k] = make_float4(c.a, c.b, c.c, 0.f); }
+    struct Raw { float a[8], b[8]; };
+    __device__ void fill(int n, int K, float* cf) const {
+        for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; cf[k] = c.a; cf[K + k] = c.b; cf[2 * K + k] = c.c; }
     }
-    __device__ void load8(size_t row, int K, int ch0, const float4* cf, float (&v)[8]) const {
-        const float4 a = ld4_stream(dy + row * K + ch0), b = ld4_stream(dy + row * K + ch0 + 4);
-        const float4 p = ld4(vv + row * K + ch0), q = ld4(vv + row * K + ch0 + 4);
-        const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        const float w[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(dy + row * K + ch0, r.a); ld8(vv + row * K + ch0, r.b); }
+    __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
+        float ca[8], cb[8], cc[8];
+        lds8(cf + ch0, ca); lds8(cf + K + ch0, cb); lds8(cf + 2 * K + ch0, cc);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 c = cf[ch0 + i]; v[i] = fmaf(c.x, d[i], fmaf(c.y, w[i], c.z)); }
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(ca[i], r.a[i], fmaf(cb[i], r.b[i], cc[i]));
     }
 };
 
@@ -168,8 +188,9 @@ struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
             du[o] = v[i];
             const float h = h2[o];
             const float z = fmaf(h, st.k.scale, st.k.shift);
-            const float gp = gelu_grad_f(z);
-            s[0] = fmaf(v[i], gelu_f(z), s[0]);
+            float gz, gp;
+            gelu_both(z, gz, gp);
+            s[0] = fmaf(v[i], gz, s[0]);
             s[1] = fmaf(v[i], gp, s[1]);
             s[2] = fmaf(v[i] * gp, (h - st.m.mean) * st.m.rstd, s[2]);
         }
@@ -194,12 +215,13 @@ struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
 };
 
 // ------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  grid = (G, N frames); CTA b of a frame owns tiles [b*T/G, (b+1)*T/G) of that frame.
+// The (tile, K-block) sequence is software pipelined: the raw loads of step q+1 are issued before step q is
+// converted, so HBM requests stay in flight across the convert / fence / barrier / MMA issue / epilogue of step q.
 // ------------------------------------------------------------------------------------------
 template <int K, int NOUT, class ALoad, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P,
-               int tiles_per_block) {
+gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P) {
     constexpr int KB = K / KBLK, MH = NOUT / 128;
     constexpr int W_BYTES = K * NOUT * 4;                 // hi image + lo image
     constexpr int W_HALF = K * NOUT * 2;
@@ -208,10 +230,23 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
     char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
     char* sW = smem;                                      // [hi|lo][KB][NOUT rows][128 B]
     char* sA = smem + W_BYTES;                            // NSTAGE x {hi tile 16 KB, lo tile 16 KB}
-    float4* sCf = reinterpret_cast<float4*>(sA + NSTAGE * STAGE_BYTES);   // K coefficients
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + K);                // free[NSTAGE], accfull[2]
+    float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);     // 3 x K coefficients (SoA)
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * K);            // free[NSTAGE], accfull[2]
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + NSTAGE + 2);
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, n = blockIdx.y;
+
+    const int tiles_per_frame = P / TILE_PX;
+    const int t0 = (int)(((long long)blockIdx.x * tiles_per_frame) / gridDim.x);
+    const int t1 = (int)(((long long)(blockIdx.x + 1) * tiles_per_frame) / gridDim.x);
+    const int Q = (t1 - t0) * KB;                         // pipeline steps of this CTA
+    // producer role: 16-byte chunk pc8 of rows pr and pr + 64
+    const int pc8 = tid % 8, pr = tid / 8;
+    typename ALoad::Raw raw[2];
+    if (Q > 0) {
+        const size_t row0 = (size_t)n * P + (size_t)t0 * TILE_PX;
+        al.issue(row0 + pr, K, pc8 * 8, raw[0]);
+        al.issue(row0 + pr + 64, K, pc8 * 8, raw[1]);
+    }
 
     // ---- one-time setup: weights, coefficients, barriers, TMEM ----
     for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
@@ -240,71 +275,69 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
 #pragma unroll
         for (int s = 0; s < Epi::NS; ++s) stat[j][s] = 0.f;
     }
-    // producer role: 16-byte chunk c of rows r0 and r0 + 64
-    const int pc8 = tid % 8, pr = tid / 8;
 
-    const int tiles_per_frame = P / TILE_PX;
-    const int t0 = blockIdx.x * tiles_per_block, t1 = min(t0 + tiles_per_block, tiles_per_frame);
-    uint32_t use = 0;                                     // K-blocks produced so far (ring position)
-    for (int t = t0; t <= t1; ++t) {
-        const int it = t - t0;                            // local tile index
-        if (t < t1) {
-            const size_t row0 = (size_t)n * P + (size_t)t * TILE_PX;
-            const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
-            for (int kb = 0; kb < KB; ++kb, ++use) {
-                const uint32_t slot = use % NSTAGE, u = use / NSTAGE;
-                mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);          // MMAs that read this slot are done
-                char* hi = sA + slot * STAGE_BYTES;
-                char* lo = hi + STAGE_BYTES / 2;
+    auto epilogue = [&](int pit) {        // local tile index pit: TMEM -> registers -> global (+ statistics)
+        const size_t prow0 = (size_t)n * P + (size_t)(t0 + pit) * TILE_PX + pc * 32;
+        mbar_wait(smem_u32(&sBar[NSTAGE + (pit & 1)]), (uint32_t)(pit >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = pr + 64 * j;
-                    float v[8];
-                    al.load8(row0 + r, K, kb * KBLK + pc8 * 8, sCf, v);
-                    const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
-                    split_store8(v, hi + off, lo + off);
-                }
-                fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
-                    const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
-                    const uint32_t idesc = c_idesc;
-#pragma unroll
-                    for (int j = 0; j < MH; ++j) {
-                        const uint32_t d = tmem_base + acc + j * TILE_PX;
-#pragma unroll
-                        for (int k16 = 0; k16 < KBLK / 16; ++k16) {
-                            const uint64_t wa = make_desc(a_hi + j * (128 * 128) + k16 * 32);
-                            const uint64_t wl = make_desc(a_lo + j * (128 * 128) + k16 * 32);
-                            const uint64_t xa = make_desc(b_hi + k16 * 32);
-                            const uint64_t xl = make_desc(b_lo + k16 * 32);
-                            tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
-                            tc_mma(d, wa, xl, idesc, 1);
-                            tc_mma(d, wl, xa, idesc, 1);
-                        }
-                    }
-                    tc_commit(smem_u32(&sBar[slot]));                              // frees the ring slot
-                    if (kb == KB - 1) tc_commit(smem_u32(&sBar[NSTAGE + (it & 1)]));   // accumulator of this tile complete
-                }
-            }
+        for (int j = 0; j < MH; ++j) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(pit & 1) * ACC_COLS + j * TILE_PX + pc * 32, v);
+            ep.apply(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
         }
-        if (it > 0) {
-            // epilogue of the previous tile; its MMAs were committed one iteration ago
-            const int pit = it - 1;
-            const size_t prow0 = (size_t)n * P + (size_t)(t - 1) * TILE_PX + pc * 32;
-            mbar_wait(smem_u32(&sBar[NSTAGE + (pit & 1)]), (uint32_t)(pit >> 1) & 1);
+        tc_fence_before();     // order the TMEM reads before the barrier that precedes the next overwrite of this stage
+    };
+
+    for (int q = 0; q < Q; ++q) {
+        const int it = q / KB, kb = q % KB;               // local tile, K-block
+        typename ALoad::Raw cur[2] = {raw[0], raw[1]};
+        if (q + 1 < Q) {                                  // prefetch the next step's operands
+            const int nit = (q + 1) / KB, nkb = (q + 1) % KB;
+            const size_t nrow0 = (size_t)n * P + (size_t)(t0 + nit) * TILE_PX;
+            al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
+            al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
+        }
+        const uint32_t slot = (uint32_t)q % NSTAGE, u = (uint32_t)q / NSTAGE;
+        mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);    // MMAs that read this ring slot are done
+        char* hi = sA + slot * STAGE_BYTES;
+        char* lo = hi + STAGE_BYTES / 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = pr + 64 * j;
+            float v[8];
+            al.finish(cur[j], K, kb * KBLK + pc8 * 8, sCf, v);
+            const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
+            split_store8(v, hi + off, lo + off);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
             tc_fence_after();
+            const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
+            const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
+            const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
+            const uint32_t idesc = c_idesc;
 #pragma unroll
             for (int j = 0; j < MH; ++j) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(pit & 1) * ACC_COLS + j * TILE_PX + pc * 32, v);
-                ep.apply(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+                const uint32_t d = tmem_base + acc + j * TILE_PX;
+#pragma unroll
+                for (int k16 = 0; k16 < KBLK / 16; ++k16) {
+                    const uint64_t wa = make_desc(a_hi + j * (128 * 128) + k16 * 32);
+                    const uint64_t wl = make_desc(a_lo + j * (128 * 128) + k16 * 32);
+                    const uint64_t xa = make_desc(b_hi + k16 * 32);
+                    const uint64_t xl = make_desc(b_lo + k16 * 32);
+                    tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
+                    tc_mma(d, wa, xl, idesc, 1);
+                    tc_mma(d, wl, xa, idesc, 1);
+                }
             }
-            tc_fence_before();     // order the TMEM reads before the barrier that precedes the next overwrite of this stage
+            tc_commit(smem_u32(&sBar[slot]));                                  // frees the ring slot
+            if (kb == KB - 1) tc_commit(smem_u32(&sBar[NSTAGE + (it & 1)]));   // accumulator of this tile complete
         }
+        if (kb == KB - 1 && it > 0) epilogue(it - 1);     // previous tile, while this tile's MMAs run
     }
+    if (Q > 0) epilogue(t1 - t0 - 1);
     // per-channel statistics: 4 warps (pixel blocks) share a channel -> 4 atomics per channel per CTA
     double* dst = ep.dst(n, NOUT);
 #pragma unroll
@@ -317,10 +350,29 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+// CTAs per frame: G*N a multiple of the SM count (equal waves), about 8-16 tiles per CTA
+static int blocks_per_frame(int N, int tiles) {
+    const int sms = sm_count();
+    const int unit = sms / gcd_int(sms, N);
+    int g = unit;
+    while (g * 2 <= tiles / 8) g *= 2;
+    if (g > tiles) g = tiles;
+    return g < 1 ? 1 : g;
+}
+
 template <int K, int NOUT, class ALoad, class Epi>
 static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t st) {
     if (P % TILE_PX != 0) return UB_ERR_ARG;
-    constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + K * sizeof(float4) + (NSTAGE + 2) * 8 + 16 + 1024;
+    constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + (NSTAGE + 2) * 8 + 16 + 1024;
     auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -328,8 +380,7 @@ static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t
         attr_set = true;
     }
     const int tiles = P / TILE_PX;
-    const int tpb = tiles >= 8 ? 8 : tiles;
-    kern<<<dim3((tiles + tpb - 1) / tpb, N), THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P, tpb);
+    kern<<<dim3(blocks_per_frame(N, tiles), N), THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
@@ -365,11 +416,26 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
     extern __shared__ __align__(1024) char smem_raw[];
     char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     char* sStage = smem;                                                       // 2 x {A hi, A lo, B hi, B lo}
-    float4* sCfA = reinterpret_cast<float4*>(smem + 2 * WG_STAGE);            // 128 coefficients
-    float4* sCfB = sCfA + 128;                                                 // 256 coefficients
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCfB + 256);                 // free[2], done
+    float* sCfA = reinterpret_cast<float*>(smem + 2 * WG_STAGE);              // 3 x 128 coefficients (SoA)
+    float* sCfB = sCfA + 3 * 128;                                              // 3 x 256 coefficients
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCfB + 3 * 256);             // free[2], done
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 3);
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+
+    const int tiles_per_frame = P / WG_PX;
+    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
+    const long long H = (t1 > t0 ? (t1 - t0) : 0) * 2;     // pipeline steps: half tiles of 32 pixel rows
+    // producer role per half tile: one A item (row ra, chunk ca) and two B items (rows rb, rb+16; chunk cb)
+    const int ra = tid / 16, ca = tid % 16, rb = tid / 32, cb = tid % 32;
+    typename LA::Raw rawa;
+    typename LB::Raw rawb[2];
+    if (H > 0) {
+        const size_t row0 = (size_t)t0 * WG_PX;
+        la.issue(row0 + ra, 128, ca * 8, rawa);
+        lb.issue(row0 + rb, 256, cb * 8, rawb[0]);
+        lb.issue(row0 + rb + 16, 256, cb * 8, rawb[1]);
+    }
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sBar[i]), 1);
@@ -384,12 +450,11 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
 
-    const int tiles_per_frame = P / WG_PX;
-    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
     int cur_n = -1;
-    uint32_t use = 0;
-    for (long long t = t0; t < t1; ++t, ++use) {
+    for (long long h = 0; h < H; ++h) {
+        const long long t = t0 + (h >> 1);
+        const int half = (int)(h & 1);
+        const uint32_t use = (uint32_t)(h >> 1);
         const int n = (int)(t / tiles_per_frame);
         if (n != cur_n) {                       // block-uniform: refill the per-frame coefficients
             __syncthreads();
@@ -398,58 +463,66 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
             cur_n = n;
             __syncthreads();
         }
-        const size_t row0 = (size_t)t * WG_PX;
+        const typename LA::Raw ca_raw = rawa;
+        const typename LB::Raw cb_raw[2] = {rawb[0], rawb[1]};
+        if (h + 1 < H) {                        // prefetch the next half tile
+            const size_t nrow0 = (size_t)(t0 + ((h + 1) >> 1)) * WG_PX + (size_t)((h + 1) & 1) * 32;
+            la.issue(nrow0 + ra, 128, ca * 8, rawa);
+            lb.issue(nrow0 + rb, 256, cb * 8, rawb[0]);
+            lb.issue(nrow0 + rb + 16, 256, cb * 8, rawb[1]);
+        }
         const uint32_t slot = use & 1, u = use >> 1;
-        mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);
+        if (half == 0) mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);
         char* a_hi = sStage + slot * WG_STAGE;
         char* a_lo = a_hi + WG_A_BYTES / 2;
         char* b_hi = a_hi + WG_A_BYTES;
         char* b_lo = b_hi + WG_B_BYTES / 2;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {           // A operand: 64 rows x 16 chunks
-            const int i = tid + THREADS * j, r = i / 16, c = i % 16;
+        {
+            const int r = half * 32 + ra;
             float v[8];
-            la.load8(row0 + r, 128, c * 8, sCfA, v);
-            const int off = (c / 8) * WG_BLK + r * 128 + (((c % 8) ^ (r & 7)) << 4);
+            la.finish(ca_raw, 128, ca * 8, sCfA, v);
+            const int off = (ca / 8) * WG_BLK + r * 128 + (((ca % 8) ^ (r & 7)) << 4);
             split_store8(v, a_hi + off, a_lo + off);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {           // B operand: 64 rows x 32 chunks
-            const int i = tid + THREADS * j, r = i / 32, c = i % 32;
+        for (int j = 0; j < 2; ++j) {
+            const int r = half * 32 + rb + 16 * j;
             float v[8];
-            lb.load8(row0 + r, 256, c * 8, sCfB, v);
-            const int off = (c / 8) * WG_BLK + r * 128 + (((c % 8) ^ (r & 7)) << 4);
+            lb.finish(cb_raw[j], 256, cb * 8, sCfB, v);
+            const int off = (cb / 8) * WG_BLK + r * 128 + (((cb % 8) ^ (r & 7)) << 4);
             split_store8(v, b_hi + off, b_lo + off);
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t idesc = c_wg_idesc;
+        if (half == 1) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = c_wg_idesc;
 #pragma unroll
-            for (int p16 = 0; p16 < WG_PX / 16; ++p16) {
-                const uint64_t ah = make_wg_desc(smem_u32(a_hi) + p16 * 2048), al = make_wg_desc(smem_u32(a_lo) + p16 * 2048);
-                const uint64_t bh = make_wg_desc(smem_u32(b_hi) + p16 * 2048), bl = make_wg_desc(smem_u32(b_lo) + p16 * 2048);
-                tc_mma(tmem_base, ah, bh, idesc, (use | (uint32_t)p16) != 0);
-                tc_mma(tmem_base, ah, bl, idesc, 1);
-                tc_mma(tmem_base, al, bh, idesc, 1);
+                for (int p16 = 0; p16 < WG_PX / 16; ++p16) {
+                    const uint64_t ah = make_wg_desc(smem_u32(a_hi) + p16 * 2048), al = make_wg_desc(smem_u32(a_lo) + p16 * 2048);
+                    const uint64_t bh = make_wg_desc(smem_u32(b_hi) + p16 * 2048), bl = make_wg_desc(smem_u32(b_lo) + p16 * 2048);
+                    tc_mma(tmem_base, ah, bh, idesc, (use | (uint32_t)p16) != 0);
+                    tc_mma(tmem_base, ah, bl, idesc, 1);
+                    tc_mma(tmem_base, al, bh, idesc, 1);
+                }
+                tc_commit(smem_u32(&sBar[slot]));
+                if (h == H - 1) tc_commit(smem_u32(&sBar[2]));
             }
-            tc_commit(smem_u32(&sBar[slot]));
-            if (t == t1 - 1) tc_commit(smem_u32(&sBar[2]));
         }
     }
     float* dst = partial + (size_t)blockIdx.x * 128 * 256;
-    if (t1 > t0) {
+    if (H > 0) {
         mbar_wait(smem_u32(&sBar[2]), 0);
         tc_fence_after();
-        const int lq = warp % 4, cb = warp / 4;          // lanes lq*32.., columns cb*64..
+        const int lq = warp % 4, cbk = warp / 4;          // lanes lq*32.., columns cbk*64..
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int hh = 0; hh < 2; ++hh) {
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + cb * 64 + h * 32, v);
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + cbk * 64 + hh * 32, v);
             const int m = lq * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dst[(size_t)m * sa + (size_t)(cb * 64 + h * 32 + i) * sb] = v[i];
+            for (int i = 0; i < 32; ++i) dst[(size_t)m * sa + (size_t)(cbk * 64 + hh * 32 + i) * sb] = v[i];
         }
     } else {
         for (int i = tid; i < 128 * 256; i += THREADS) dst[i] = 0.f;
@@ -462,7 +535,7 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
 template <class LA, class LB>
 static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb, int* nparts, cudaStream_t st) {
     if (P % WG_PX != 0) return UB_ERR_ARG;
-    constexpr size_t smem = (size_t)2 * WG_STAGE + 384 * sizeof(float4) + 3 * 8 + 16 + 1024;
+    constexpr size_t smem = (size_t)2 * WG_STAGE + 3 * 384 * sizeof(float) + 3 * 8 + 16 + 1024;
     auto kern = wgrad_tc_kernel<LA, LB>;
     static bool attr_set = false;
     if (!attr_set) {

@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const float* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float z = fmaf(vv[i], k[i].scale, k[i].shift);
-            s[i] += gelu_f(z);
+            float gz, gp;
+            gelu_both(z, gz, gp);
+            s[i] += gz;
             if (train) {
-                const float gp = gelu_grad_f(z);
                 g[i] += gp;
                 gh[i] += gp * (vv[i] - m[i].mean) * m[i].rstd;
             }
