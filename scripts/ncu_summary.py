@@ -1,0 +1,82 @@
+"""Summarise ncu captures brought back in gpurun_out/ into tracked files under profiles/.
+
+    python scripts/ncu_summary.py r01            # reads gpurun_out/prof_*.ncu-rep and gpurun_out/launches.csv
+"""
+import csv
+import glob
+import io
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+KEYS = [
+    ("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pct"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_pct"),
+    ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+]
+lines = [f"# ncu --set full summaries ({tag})", "",
+         "Captured with `scripts/gpu_ncu.sh` (`ncu --set full --clock-control none --import-source on`, bench.py --batch 4 --steps 1);",
+         "times are cold-cache single launches: compare shares and percentages, not absolutes. Units as printed by ncu "
+         "(time: us or ms per the raw page; bytes: MB).", ""]
+for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+    lines += [f"## {os.path.basename(rep)}", "", "| kernel | " + " | ".join(k for _, k in KEYS) + " | top stalls |", "|---|" + "---|" * (len(KEYS) + 1)]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        u = dict(zip(hdr, units))
+        name = d.get("Kernel Name", "?").split("(")[0][:70]
+        vals = []
+        for k, _ in KEYS:
+            v = d.get(k, "")
+            try:
+                v = f"{float(v):.4g}"
+            except ValueError:
+                pass
+            vals.append(f"{v} {u.get(k, '')}".strip() if k.startswith(("gpu__time", "dram__bytes")) else v)
+        st = [(float(v), h.replace("smsp__pcsamp_warps_issue_stalled_", "")) for h, v in d.items()
+              if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h and v not in ("", "n/a")]
+        tot = sum(x for x, _ in st) or 1.0
+        top = ", ".join(f"{h} {100 * x / tot:.0f}%" for x, h in sorted(st, reverse=True)[:4])
+        lines.append(f"| {name} | " + " | ".join(vals) + f" | {top} |")
+    lines.append("")
+open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w").write("\n".join(lines))
+
+src = os.path.join(ROOT, "gpurun_out", "launches.csv")
+if os.path.exists(src):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = {}
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        v = v / 1e3 if r[ui] in ("ns", "nsecond") else (v * 1e3 if r[ui] in ("ms", "msecond") else v)   # -> us
+        name = r[ki].split("(")[0][:80]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    total = sum(a[1] for a in agg.values())
+    with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
+        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over one bench.py step\n\n")
+        f.write("Per-launch times are cold-cache and serialised; the SHARE column is what is comparable with bench.py's CUDA-event breakdown.\n\n")
+        f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
+        for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| {name} | {cnt} | {us:.1f} | {100 * us / total:.1f}% |\n")
+    import shutil
+    shutil.copy(src, os.path.join(out_dir, f"{tag}_launches.csv"))
+print("written", os.listdir(out_dir))

@@ -67,16 +67,30 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        for (int e = threadIdx.x; e < DW_HR * DW_HC * DW_Q; e += 256) {   // e % 8 == cq
-            const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
-            const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
-            const float4 v = ld4(src + ((size_t)sy * W + sx) * C + c0);
-            float4 g;
-            g.x = gelu_f(fmaf(v.x, k[0].scale, k[0].shift));
-            g.y = gelu_f(fmaf(v.y, k[1].scale, k[1].shift));
-            g.z = gelu_f(fmaf(v.z, k[2].scale, k[2].shift));
-            g.w = gelu_f(fmaf(v.w, k[3].scale, k[3].shift));
-            st4(tile + pix * DW_CC + cq * 4, g);
+        // halo tile load: 4 independent 16-byte loads in flight per thread before any of them is consumed
+        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {   // e % 8 == cq
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                if (e < DW_HR * DW_HC * DW_Q) {
+                    const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
+                    const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
+                    v[u] = ld4(src + ((size_t)sy * W + sx) * C + c0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                if (e < DW_HR * DW_HC * DW_Q) {
+                    float4 g;
+                    g.x = gelu_f(fmaf(v[u].x, k[0].scale, k[0].shift));
+                    g.y = gelu_f(fmaf(v[u].y, k[1].scale, k[1].shift));
+                    g.z = gelu_f(fmaf(v[u].z, k[2].scale, k[2].shift));
+                    g.w = gelu_f(fmaf(v[u].w, k[3].scale, k[3].shift));
+                    st4(tile + (e / DW_Q) * DW_CC + cq * 4, g);
+                }
+            }
         }
         __syncthreads();
         // one column per thread, 8 output rows
@@ -106,6 +120,8 @@ struct DwBwdCoef {
     float4 k2sg[DW_CC];   // scale2, shift2, gate, dpool/P
     float4 b2[DW_CC];     // a2, b2, c2, -
     float4 k1m1[DW_CC];   // scale1, shift1, mean1, rstd1
+    float4 w[9][DW_Q];    // depthwise taps, [tap][channel quad] (kept out of registers: the stencil phase needs them for
+                          // the h1 prefetch and the weight-gradient accumulators)
 };
 
 __global__ void __launch_bounds__(256, 2)
@@ -131,11 +147,10 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
         cf->b2[threadIdx.x] = make_float4(bb.a, bb.b, bb.c, 0.f);
         cf->k1m1[threadIdx.x] = make_float4(b.scale, b.shift, m.mean, m.rstd);
     }
-    float w[9][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 9; ++j) w[j][i] = wdw[(size_t)(c0 + i) * 9 + j];
+    for (int e = threadIdx.x; e < 9 * DW_CC; e += 256) {
+        const int j = e / DW_CC, ch = e % DW_CC;
+        reinterpret_cast<float*>(&cf->w[j][0])[ch] = wdw[(size_t)(cbase + ch) * 9 + j];
+    }
     const size_t fbase = (size_t)n * H * W * C;
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     float4 gw[9];
@@ -146,38 +161,62 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        for (int e = threadIdx.x; e < DW_HR * DW_HC * DW_Q; e += 256) {
-            const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
-            const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
-            float4 dh = make_float4(0, 0, 0, 0);
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                const size_t off = fbase + ((size_t)yy * W + xx) * C + c0;
-                const float4 d = ld4_stream(du + off);
-                const float4 hv = ld4(h2 + off);
-                const float dvv[4] = {d.x, d.y, d.z, d.w}, hvv[4] = {hv.x, hv.y, hv.z, hv.w};
-                float o[4];
+        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {
+            float4 vd[4], vh2[4], vh1[4];
+            bool inside[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 k2 = cf->k2sg[cq * 4 + i], b2 = cf->b2[cq * 4 + i];
-                    const float z = fmaf(hvv[i], k2.x, k2.y);
-                    const float dz = fmaf(dvv[i], k2.z, k2.w) * gelu_grad_f(z);
-                    o[i] = fmaf(b2.x, dz, fmaf(b2.y, hvv[i], b2.z));
+            for (int u = 0; u < 4; ++u) {        // issue every load of the batch first
+                const int e = e0 + u * 256;
+                inside[u] = false;
+                if (e < DW_HR * DW_HC * DW_Q) {
+                    const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
+                    const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
+                    inside[u] = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+                    if (inside[u]) {
+                        const size_t off = fbase + ((size_t)yy * W + xx) * C + c0;
+                        vd[u] = ld4_stream(du + off);
+                        vh2[u] = ld4(h2 + off);
+                    }
+                    const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
+                    vh1[u] = ld4(h1 + fbase + ((size_t)sy * W + sx) * C + c0);
                 }
-                dh = make_float4(o[0], o[1], o[2], o[3]);
             }
-            st4(tdh + pix * DW_CC + cq * 4, dh);
-            const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
-            const float4 v = ld4(h1 + fbase + ((size_t)sy * W + sx) * C + c0);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            float g[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
-            st4(tg + pix * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                if (e < DW_HR * DW_HC * DW_Q) {
+                    const int pix = e / DW_Q;
+                    float4 dh = make_float4(0, 0, 0, 0);
+                    if (inside[u]) {
+                        const float dvv[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w}, hvv[4] = {vh2[u].x, vh2[u].y, vh2[u].z, vh2[u].w};
+                        float o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 k2 = cf->k2sg[cq * 4 + i], b2 = cf->b2[cq * 4 + i];
+                            const float z = fmaf(hvv[i], k2.x, k2.y);
+                            const float dz = fmaf(dvv[i], k2.z, k2.w) * gelu_grad_f(z);
+                            o[i] = fmaf(b2.x, dz, fmaf(b2.y, hvv[i], b2.z));
+                        }
+                        dh = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                    st4(tdh + pix * DW_CC + cq * 4, dh);
+                    const float vv[4] = {vh1[u].x, vh1[u].y, vh1[u].z, vh1[u].w};
+                    float g[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
+                    st4(tg + pix * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
+                }
+            }
         }
+        // interior h1 of this thread's column (needed for gelu'(z1) and h1_hat), software-prefetched one row ahead:
+        // the first row's load is in flight across the barrier, row r+1's across the 9-tap stencil of row r
+        float4 h1next = ld4(h1 + fbase + ((size_t)y0 * W + qx) * C + c0);
         __syncthreads();
 #pragma unroll 1
         for (int r = 0; r < DW_TH; ++r) {
             const int qy = y0 + r;
+            const float4 hv = h1next;
+            if (r + 1 < DW_TH) h1next = ld4(h1 + fbase + ((size_t)(qy + 1) * W + qx) * C + c0);
             const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
             const float4 dhc = ld4(tdh + ((r + 1) * DW_HC + col + 1) * DW_CC + cq * 4);
             float4 o = make_float4(0, 0, 0, 0);
@@ -192,17 +231,12 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
                     const int i1 = (dy == -1) ? 0 : 2, j1 = (dx == -1) ? 0 : 2;
                     const bool ya = (dy == -1) ? y_lo : ((dy == 1) ? y_hi : false);
                     const bool xa = (dx == -1) ? x_lo : ((dx == 1) ? x_hi : false);
-                    float we[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float v = w[i0 * 3 + j0][c];
-                        if (xa) v += w[i0 * 3 + j1][c];
-                        if (ya) v += w[i1 * 3 + j0][c];
-                        if (ya && xa) v += w[i1 * 3 + j1][c];
-                        we[c] = v;
-                    }
-                    o.x = fmaf(we[0], t.x, o.x); o.y = fmaf(we[1], t.y, o.y);
-                    o.z = fmaf(we[2], t.z, o.z); o.w = fmaf(we[3], t.w, o.w);
+                    float4 we = cf->w[i0 * 3 + j0][cq];
+                    if (xa) { const float4 a = cf->w[i0 * 3 + j1][cq]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
+                    if (ya) { const float4 a = cf->w[i1 * 3 + j0][cq]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
+                    if (ya && xa) { const float4 a = cf->w[i1 * 3 + j1][cq]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
+                    o.x = fmaf(we.x, t.x, o.x); o.y = fmaf(we.y, t.y, o.y);
+                    o.z = fmaf(we.z, t.z, o.z); o.w = fmaf(we.w, t.w, o.w);
                     // depthwise weight gradient: tap (dy+1, dx+1) pairs dh2[q] with g1[reflect(q + (dy, dx))]
                     const float4 g = ld4(tg + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
                     float4& a = gw[(dy + 1) * 3 + dx + 1];
@@ -210,7 +244,6 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
                     a.z = fmaf(dhc.z, g.z, a.z); a.w = fmaf(dhc.w, g.w, a.w);
                 }
             const size_t off = fbase + ((size_t)qy * W + qx) * C + c0;
-            const float4 hv = ld4(h1 + off);
             const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
             const float ov[4] = {o.x, o.y, o.z, o.w};
             float dz[4], dzh[4];
