@@ -158,31 +158,32 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
     for (int j = 0; j < 9; ++j) gw[j] = make_float4(0, 0, 0, 0);
     const int qx = x0 + col;
     const bool x_lo = (qx == 1), x_hi = (qx == W - 2);
+    const float* tcol = tdh + (col + 1) * DW_CC + cq * 4;      // centre tap of this thread's column, halo row 0
+    const float* gcol = tg + (col + 1) * DW_CC + cq * 4;
+    constexpr int ROW = DW_HC * DW_CC;                          // floats per halo row
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {
-            float4 vd[4], vh2[4], vh1[4];
-            bool inside[4];
+        // ---- load phase: dh2 (zero outside the image) and g1 (reflected) halo tiles, 2 items = 6 loads in flight ----
+        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 2 * 256) {
+            float4 vd[2], vh2[2], vh1[2];
+            bool inside[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {        // issue every load of the batch first
+            for (int u = 0; u < 2; ++u) {
                 const int e = e0 + u * 256;
                 inside[u] = false;
                 if (e < DW_HR * DW_HC * DW_Q) {
-                    const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
+                    const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
                     const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
                     inside[u] = (yy >= 0 && yy < H && xx >= 0 && xx < W);
-                    if (inside[u]) {
-                        const size_t off = fbase + ((size_t)yy * W + xx) * C + c0;
-                        vd[u] = ld4_stream(du + off);
-                        vh2[u] = ld4(h2 + off);
-                    }
                     const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
-                    vh1[u] = ld4(h1 + fbase + ((size_t)sy * W + sx) * C + c0);
+                    const size_t off = fbase + ((size_t)sy * W + sx) * C + c0;      // == the pixel itself when inside
+                    vh1[u] = ld4(h1 + off);
+                    if (inside[u]) { vd[u] = ld4_stream(du + off); vh2[u] = ld4(h2 + off); }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int e = e0 + u * 256;
                 if (e < DW_HR * DW_HC * DW_Q) {
                     const int pix = e / DW_Q;
@@ -208,55 +209,83 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
                 }
             }
         }
-        // interior h1 of this thread's column (needed for gelu'(z1) and h1_hat), software-prefetched one row ahead:
-        // the first row's load is in flight across the barrier, row r+1's across the 9-tap stencil of row r
+        // interior h1 of this thread's column (for gelu'(z1) and h1_hat), software-prefetched one row ahead
         float4 h1next = ld4(h1 + fbase + ((size_t)y0 * W + qx) * C + c0);
         __syncthreads();
+
+        // ---- pass A: dg1 = DW^T(dh2), dz1 = dg1 * gelu'(z1), Norm1-backward statistics ----
+        {
+            float4 w[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) w[j] = cf->w[j][cq];
 #pragma unroll 1
+            for (int r = 0; r < DW_TH; ++r) {
+                const int qy = y0 + r;
+                const float4 hv = h1next;
+                if (r + 1 < DW_TH) h1next = ld4(h1 + fbase + ((size_t)(qy + 1) * W + qx) * C + c0);
+                const float* tc = tcol + (r + 1) * ROW;
+                float4 o = make_float4(0, 0, 0, 0);
+                // source p = q + (dy, dx) reaches q through tap (1-dy, 1-dx)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const float4 t = ld4(tc + dy * ROW + dx * DW_CC);
+                        const float4 ww = w[(1 - dy) * 3 + (1 - dx)];
+                        o.x = fmaf(ww.x, t.x, o.x); o.y = fmaf(ww.y, t.y, o.y);
+                        o.z = fmaf(ww.z, t.z, o.z); o.w = fmaf(ww.w, t.w, o.w);
+                    }
+                // adjoint of reflect padding (rare): on rows 1 / H-2 and columns 1 / W-2 the border source reaches q a
+                // second time through the reflected tap: (dy=-1 -> tap row 0), (dy=+1 -> tap row 2), same for columns
+                const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
+                if (y_lo | y_hi | x_lo | x_hi) {
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const bool ya = (dy == -1) ? y_lo : ((dy == 1) ? y_hi : false);
+                            const bool xa = (dx == -1) ? x_lo : ((dx == 1) ? x_hi : false);
+                            if (ya | xa) {
+                                const int i0 = 1 - dy, j0 = 1 - dx, i1 = (dy == -1) ? 0 : 2, j1 = (dx == -1) ? 0 : 2;
+                                float4 we = make_float4(0, 0, 0, 0);
+                                if (xa) { const float4 a = w[i0 * 3 + j1]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
+                                if (ya) { const float4 a = w[i1 * 3 + j0]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
+                                if (ya && xa) { const float4 a = w[i1 * 3 + j1]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
+                                const float4 t = ld4(tc + dy * ROW + dx * DW_CC);
+                                o.x = fmaf(we.x, t.x, o.x); o.y = fmaf(we.y, t.y, o.y);
+                                o.z = fmaf(we.z, t.z, o.z); o.w = fmaf(we.w, t.w, o.w);
+                            }
+                        }
+                }
+                const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+                float dz[4], dzh[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 k1 = cf->k1m1[cq * 4 + c];
+                    const float z = fmaf(hvv[c], k1.x, k1.y);
+                    dz[c] = ov[c] * gelu_grad_f(z);
+                    dzh[c] = dz[c] * (hvv[c] - k1.z) * k1.w;
+                }
+                st4(dz1 + fbase + ((size_t)qy * W + qx) * C + c0, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                s.x += dz[0]; s.y += dz[1]; s.z += dz[2]; s.w += dz[3];
+                q.x += dzh[0]; q.y += dzh[1]; q.z += dzh[2]; q.w += dzh[3];
+            }
+        }
+        // ---- pass B: depthwise weight gradient, tap (dy+1, dx+1) pairs dh2[q] with g1[reflect(q + (dy, dx))] ----
+#pragma unroll 2
         for (int r = 0; r < DW_TH; ++r) {
-            const int qy = y0 + r;
-            const float4 hv = h1next;
-            if (r + 1 < DW_TH) h1next = ld4(h1 + fbase + ((size_t)(qy + 1) * W + qx) * C + c0);
-            const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
-            const float4 dhc = ld4(tdh + ((r + 1) * DW_HC + col + 1) * DW_CC + cq * 4);
-            float4 o = make_float4(0, 0, 0, 0);
+            const float4 dhc = ld4(tcol + (r + 1) * ROW);
+            const float* gc = gcol + (r + 1) * ROW;
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
-                    // adjoint of reflect padding: source p = q + (dy, dx) reaches q through tap (1-dy, 1-dx) and,
-                    // on rows/cols 1 and H-2 / W-2, additionally through the reflected tap.
-                    const float4 t = ld4(tdh + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
-                    const int i0 = 1 - dy, j0 = 1 - dx;               // compile-time after unrolling
-                    const int i1 = (dy == -1) ? 0 : 2, j1 = (dx == -1) ? 0 : 2;
-                    const bool ya = (dy == -1) ? y_lo : ((dy == 1) ? y_hi : false);
-                    const bool xa = (dx == -1) ? x_lo : ((dx == 1) ? x_hi : false);
-                    float4 we = cf->w[i0 * 3 + j0][cq];
-                    if (xa) { const float4 a = cf->w[i0 * 3 + j1][cq]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
-                    if (ya) { const float4 a = cf->w[i1 * 3 + j0][cq]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
-                    if (ya && xa) { const float4 a = cf->w[i1 * 3 + j1][cq]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
-                    o.x = fmaf(we.x, t.x, o.x); o.y = fmaf(we.y, t.y, o.y);
-                    o.z = fmaf(we.z, t.z, o.z); o.w = fmaf(we.w, t.w, o.w);
-                    // depthwise weight gradient: tap (dy+1, dx+1) pairs dh2[q] with g1[reflect(q + (dy, dx))]
-                    const float4 g = ld4(tg + ((r + 1 + dy) * DW_HC + col + 1 + dx) * DW_CC + cq * 4);
+                    const float4 g = ld4(gc + dy * ROW + dx * DW_CC);
                     float4& a = gw[(dy + 1) * 3 + dx + 1];
                     a.x = fmaf(dhc.x, g.x, a.x); a.y = fmaf(dhc.y, g.y, a.y);
                     a.z = fmaf(dhc.z, g.z, a.z); a.w = fmaf(dhc.w, g.w, a.w);
                 }
-            const size_t off = fbase + ((size_t)qy * W + qx) * C + c0;
-            const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
-            const float ov[4] = {o.x, o.y, o.z, o.w};
-            float dz[4], dzh[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4 k1 = cf->k1m1[cq * 4 + c];
-                const float z = fmaf(hvv[c], k1.x, k1.y);
-                dz[c] = ov[c] * gelu_grad_f(z);
-                dzh[c] = dz[c] * (hvv[c] - k1.z) * k1.w;
-            }
-            st4(dz1 + off, make_float4(dz[0], dz[1], dz[2], dz[3]));
-            s.x += dz[0]; s.y += dz[1]; s.z += dz[2]; s.w += dz[3];
-            q.x += dzh[0]; q.y += dzh[1]; q.z += dzh[2]; q.w += dzh[3];
         }
     }
     reduce_pt_atomic2(s, q, bstats1 + ((size_t)n * C + cbase) * 2, smem);
