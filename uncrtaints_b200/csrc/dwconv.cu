@@ -115,19 +115,53 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
     reduce_pt_atomic2(s, q, stats2 + ((size_t)n * C + cbase) * 2, tile);
 }
 
+// B3a (pointwise, in place): du <- dh2 = a2*dz2 + b2*h2 + c2 with dz2 = (du*s + dpool/P) * gelu'(h2*scale2 + shift2):
+// the SE-gate backward and the Norm2 backward of one element.  Splitting this off the stencil kernel keeps the stencil
+// kernel's halo tile free of arithmetic (it is filled by cp.async) and both kernels out of register spills.
+__global__ void __launch_bounds__(256) dh2_kernel(float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ gate,
+                                                   const float* __restrict__ dmp, const Coef* __restrict__ coef2,
+                                                   const BCoef* __restrict__ bc2, int P, int chunk) {
+    constexpr int C = UB_HID, Q = C / 4, ROWS = 256 / Q;
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    Coef k[4]; BCoef b[4]; float sg[4], dm[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const size_t ci = (size_t)n * C + c4 * 4 + i;
+        k[i] = coef2[ci]; b[i] = bc2[ci]; sg[i] = gate[ci]; dm[i] = dmp[ci];
+    }
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    const size_t base = (size_t)n * P * C + c4 * 4;
+#pragma unroll 2
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 d = ld4(du + base + (size_t)p * C);
+        const float4 hv = ld4_stream(h2 + base + (size_t)p * C);
+        const float dv[4] = {d.x, d.y, d.z, d.w}, hh[4] = {hv.x, hv.y, hv.z, hv.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(hh[i], k[i].scale, k[i].shift);
+            const float dz = fmaf(dv[i], sg[i], dm[i]) * gelu_grad_f(z);
+            o[i] = fmaf(b[i].a, dz, fmaf(b[i].b, hh[i], b[i].c));
+        }
+        st4(du + base + (size_t)p * C, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 // per-chunk coefficient block staged in shared memory for the backward kernel (one float4 per channel and kind)
 struct DwBwdCoef {
-    float4 k2sg[DW_CC];   // scale2, shift2, gate, dpool/P
-    float4 b2[DW_CC];     // a2, b2, c2, -
     float4 k1m1[DW_CC];   // scale1, shift1, mean1, rstd1
     float4 w[9][DW_Q];    // depthwise taps, [tap][channel quad] (kept out of registers: the stencil phase needs them for
                           // the h1 prefetch and the weight-gradient accumulators)
 };
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;                    // src-size 0 => the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
 __global__ void __launch_bounds__(256, 2)
-dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
-                  const float* __restrict__ gate /* s[n][c] */, const float* __restrict__ dmp /* dpool/P [n][c] */,
-                  const Coef* __restrict__ coef2, const BCoef* __restrict__ bc2, const Coef* __restrict__ coef1,
+dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, const Coef* __restrict__ coef1,
                   const MeanRstd* __restrict__ mr1, const float* __restrict__ wdw, float* __restrict__ dz1,
                   double* bstats1, float* dwdw /* [256][9] accumulated */, int H, int W) {
     extern __shared__ __align__(16) float smem[];
@@ -140,11 +174,8 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
     const int c0 = cbase + cq * 4;
     if (threadIdx.x < DW_CC) {
         const size_t ci = (size_t)n * C + cbase + threadIdx.x;
-        const Coef a = coef2[ci], b = coef1[ci];
-        const BCoef bb = bc2[ci];
+        const Coef b = coef1[ci];
         const MeanRstd m = mr1[ci];
-        cf->k2sg[threadIdx.x] = make_float4(a.scale, a.shift, gate[ci], dmp[ci]);
-        cf->b2[threadIdx.x] = make_float4(bb.a, bb.b, bb.c, 0.f);
         cf->k1m1[threadIdx.x] = make_float4(b.scale, b.shift, m.mean, m.rstd);
     }
     for (int e = threadIdx.x; e < 9 * DW_CC; e += 256) {
@@ -164,51 +195,36 @@ dwconv_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        // ---- load phase: dh2 (zero outside the image) and g1 (reflected) halo tiles, 2 items = 6 loads in flight ----
-        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 2 * 256) {
-            float4 vd[2], vh2[2], vh1[2];
-            bool inside[2];
+        // ---- load phase: dh2 halo tile by cp.async (zero-filled outside the image, no registers, no arithmetic);
+        //      g1 = gelu(norm1(h1)) halo tile at reflected positions through registers, 4 loads in flight ----
+        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {
+            float4 vh1[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 const int e = e0 + u * 256;
-                inside[u] = false;
                 if (e < DW_HR * DW_HC * DW_Q) {
                     const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
                     const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
-                    inside[u] = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+                    const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
                     const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
                     const size_t off = fbase + ((size_t)sy * W + sx) * C + c0;      // == the pixel itself when inside
+                    cp_async16(tdh + pix * DW_CC + cq * 4, dh2 + off, inside);
                     vh1[u] = ld4(h1 + off);
-                    if (inside[u]) { vd[u] = ld4_stream(du + off); vh2[u] = ld4(h2 + off); }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 const int e = e0 + u * 256;
                 if (e < DW_HR * DW_HC * DW_Q) {
-                    const int pix = e / DW_Q;
-                    float4 dh = make_float4(0, 0, 0, 0);
-                    if (inside[u]) {
-                        const float dvv[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w}, hvv[4] = {vh2[u].x, vh2[u].y, vh2[u].z, vh2[u].w};
-                        float o[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 k2 = cf->k2sg[cq * 4 + i], b2 = cf->b2[cq * 4 + i];
-                            const float z = fmaf(hvv[i], k2.x, k2.y);
-                            const float dz = fmaf(dvv[i], k2.z, k2.w) * gelu_grad_f(z);
-                            o[i] = fmaf(b2.x, dz, fmaf(b2.y, hvv[i], b2.z));
-                        }
-                        dh = make_float4(o[0], o[1], o[2], o[3]);
-                    }
-                    st4(tdh + pix * DW_CC + cq * 4, dh);
                     const float vv[4] = {vh1[u].x, vh1[u].y, vh1[u].z, vh1[u].w};
                     float g[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
-                    st4(tg + pix * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
+                    st4(tg + (e / DW_Q) * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
                 }
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         // interior h1 of this thread's column (for gelu'(z1) and h1_hat), software-prefetched one row ahead
         float4 h1next = ld4(h1 + fbase + ((size_t)y0 * W + qx) * C + c0);
         __syncthreads();
@@ -317,18 +333,21 @@ int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, floa
     return UB_OK;
 }
 
-int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
-                      const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
-                      float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st) {
+int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
+                      const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
+                      float* dwdw, int N, int H, int W, cudaStream_t st) {
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
+    const int P = H * W;
+    const int chunk = P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64);
+    dh2_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(du, h2, gate, dmp, coef2, bc2, P, chunk);   // du <- dh2 in place
+    UB_CHECK_LAUNCH();
     constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float) + sizeof(DwBwdCoef);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
         attr_set = true;
     }
-    dwconv_bwd_kernel<<<dim3(W / DW_TW, UB_HID / DW_CC, N), 256, smem, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1,
-                                                                            wdw, dz1, bstats1, dwdw, H, W);
+    dwconv_bwd_kernel<<<dim3(W / DW_TW, UB_HID / DW_CC, N), 256, smem, st>>>(du, h1, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }

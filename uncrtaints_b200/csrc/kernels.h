@@ -59,7 +59,7 @@ int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 // dwconv.cu
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st);
-int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
+int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
                       const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
                       float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
 
