@@ -67,29 +67,26 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        // halo tile load: 4 independent 16-byte loads in flight per thread before any of them is consumed
+        // halo tile load: 4 independent 16-byte loads in flight per thread before any of them is consumed.  Loads are
+        // unconditional (tail items clamp to the last valid item) so that the values stay in registers.
         for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {   // e % 8 == cq
             float4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 256;
-                if (e < DW_HR * DW_HC * DW_Q) {
-                    const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix % DW_HC;
-                    const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
-                    v[u] = ld4(src + ((size_t)sy * W + sx) * C + c0);
-                }
+                const int e = min(e0 + u * 256, DW_HR * DW_HC * DW_Q - DW_Q + cq);
+                const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
+                const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
+                v[u] = ld4(src + ((size_t)sy * W + sx) * C + c0);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int e = e0 + u * 256;
-                if (e < DW_HR * DW_HC * DW_Q) {
-                    float4 g;
-                    g.x = gelu_f(fmaf(v[u].x, k[0].scale, k[0].shift));
-                    g.y = gelu_f(fmaf(v[u].y, k[1].scale, k[1].shift));
-                    g.z = gelu_f(fmaf(v[u].z, k[2].scale, k[2].shift));
-                    g.w = gelu_f(fmaf(v[u].w, k[3].scale, k[3].shift));
-                    st4(tile + (e / DW_Q) * DW_CC + cq * 4, g);
-                }
+                float4 g;
+                g.x = gelu_f(fmaf(v[u].x, k[0].scale, k[0].shift));
+                g.y = gelu_f(fmaf(v[u].y, k[1].scale, k[1].shift));
+                g.z = gelu_f(fmaf(v[u].z, k[2].scale, k[2].shift));
+                g.w = gelu_f(fmaf(v[u].w, k[3].scale, k[3].shift));
+                if (e < DW_HR * DW_HC * DW_Q) st4(tile + (e / DW_Q) * DW_CC + cq * 4, g);
             }
         }
         __syncthreads();
@@ -200,28 +197,24 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
         for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {
             float4 vh1[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 256;
-                if (e < DW_HR * DW_HC * DW_Q) {
-                    const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
-                    const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
-                    const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
-                    const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
-                    const size_t off = fbase + ((size_t)sy * W + sx) * C + c0;      // == the pixel itself when inside
-                    cp_async16(tdh + pix * DW_CC + cq * 4, dh2 + off, inside);
-                    vh1[u] = ld4(h1 + off);
-                }
+            for (int u = 0; u < 4; ++u) {        // unconditional loads (tail items clamp to the last valid item)
+                const int e = min(e0 + u * 256, DW_HR * DW_HC * DW_Q - DW_Q + cq);
+                const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
+                const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
+                const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+                const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
+                const size_t off = fbase + ((size_t)sy * W + sx) * C + c0;      // == the pixel itself when inside
+                cp_async16(tdh + pix * DW_CC + cq * 4, dh2 + off, inside);
+                vh1[u] = ld4(h1 + off);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int e = e0 + u * 256;
-                if (e < DW_HR * DW_HC * DW_Q) {
-                    const float vv[4] = {vh1[u].x, vh1[u].y, vh1[u].z, vh1[u].w};
-                    float g[4];
+                const float vv[4] = {vh1[u].x, vh1[u].y, vh1[u].z, vh1[u].w};
+                float g[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
-                    st4(tg + (e / DW_Q) * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
-                }
+                for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
+                if (e < DW_HR * DW_HC * DW_Q) st4(tg + (e / DW_Q) * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
