@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--t", type=int, default=3)
     ap.add_argument("--hw", type=int, default=256)
     ap.add_argument("--covmode", default="diag")
-    ap.add_argument("--backend", type=int, default=None, help="0 = fp32 CUDA-core GEMMs, 1 = tcgen05 bf16x3")
+    ap.add_argument("--backend", type=int, default=None, help="bit 0: tcgen05 fwd/dX GEMMs, bit 1: tcgen05 wgrad GEMMs (default 3); 0 = fp32 CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     return ap.parse_args()

@@ -378,11 +378,11 @@ class UNCRTAINTS(nn.Module):
         return out
 
 
-_BACKEND = 1     # tcgen05 bf16x3 GEMMs by default; 0 selects the fp32 CUDA-core GEMMs
+_BACKEND = 3     # bit 0: tcgen05 bf16x3 forward/input-gradient GEMMs, bit 1: tcgen05 weight-gradient GEMMs; 0 = fp32 CUDA cores
 
 
 def set_default_gemm_backend(backend: int) -> None:
-    """0 = fp32 CUDA-core GEMMs, 1 = tcgen05 bf16x3 tensor-core GEMMs."""
+    """bit 0: tcgen05 forward/input-gradient GEMMs, bit 1: tcgen05 weight-gradient GEMMs (default 3); 0 = fp32 CUDA cores."""
     global _BACKEND
     _BACKEND = int(backend)
 

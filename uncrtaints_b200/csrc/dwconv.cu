@@ -147,8 +147,7 @@ __global__ void __launch_bounds__(256) dh2_kernel(float* __restrict__ du, const 
 // per-chunk coefficient block staged in shared memory for the backward kernel (one float4 per channel and kind)
 struct DwBwdCoef {
     float4 k1m1[DW_CC];   // scale1, shift1, mean1, rstd1
-    float4 w[9][DW_Q];    // depthwise taps, [tap][channel quad] (kept out of registers: the stencil phase needs them for
-                          // the h1 prefetch and the weight-gradient accumulators)
+    float4 w[9][DW_Q];    // depthwise taps [tap][channel quad]: read per use (LDS.128), keeps the stencil loop at <= 85 registers
 };
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
@@ -157,15 +156,21 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, b
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 
+// B3b (stencil).  Both the input gradient and the weight gradient are written per INPUT pixel p of the convolution:
+//   D[tap] = sum of dh2[q] over all outputs q that read p through `tap`   (normally the single q = p - off(tap);
+//            on rows/cols 1 and H-2/W-2 also the border output that reaches p through reflect padding)
+//   dg1[p] = sum_tap w[tap] * D[tap]         dW[tap] += g1[p] * D[tap]         dz1[p] = dg1[p] * gelu'(z1[p])
+// so gelu(z1) and gelu'(z1) are evaluated once per pixel (no halo arithmetic at all) and the only shared-memory tile
+// is the raw dh2 halo tile, filled by cp.async with zero-fill outside the image.
 __global__ void __launch_bounds__(256, 2)
 dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, const Coef* __restrict__ coef1,
                   const MeanRstd* __restrict__ mr1, const float* __restrict__ wdw, float* __restrict__ dz1,
                   double* bstats1, float* dwdw /* [256][9] accumulated */, int H, int W) {
     extern __shared__ __align__(16) float smem[];
-    float* tdh = smem;                       // dh2, zero outside the image
-    float* tg = smem + DW_TILE_FLOATS;       // g1 = gelu(z1) at reflected positions
-    DwBwdCoef* cf = reinterpret_cast<DwBwdCoef*>(smem + 2 * DW_TILE_FLOATS);
+    float* tdh = smem;                       // dh2 halo tile, zero outside the image
+    DwBwdCoef* cf = reinterpret_cast<DwBwdCoef*>(smem + DW_TILE_FLOATS);
     constexpr int C = UB_HID;
+    constexpr int ROW = DW_HC * DW_CC;       // floats per halo row
     const int n = blockIdx.z, cbase = blockIdx.y * DW_CC, x0 = blockIdx.x * DW_TW;
     const int cq = threadIdx.x % DW_Q, col = threadIdx.x / DW_Q;
     const int c0 = cbase + cq * 4;
@@ -186,115 +191,63 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
     for (int j = 0; j < 9; ++j) gw[j] = make_float4(0, 0, 0, 0);
     const int qx = x0 + col;
     const bool x_lo = (qx == 1), x_hi = (qx == W - 2);
-    const float* tcol = tdh + (col + 1) * DW_CC + cq * 4;      // centre tap of this thread's column, halo row 0
-    const float* gcol = tg + (col + 1) * DW_CC + cq * 4;
-    constexpr int ROW = DW_HC * DW_CC;                          // floats per halo row
+    const float* tcol = tdh + (col + 1) * DW_CC + cq * 4;      // this thread's column, halo row 0
 
     for (int y0 = 0; y0 < H; y0 += DW_TH) {
         __syncthreads();
-        // ---- load phase: dh2 halo tile by cp.async (zero-filled outside the image, no registers, no arithmetic);
-        //      g1 = gelu(norm1(h1)) halo tile at reflected positions through registers, 4 loads in flight ----
-        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {
-            float4 vh1[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {        // unconditional loads (tail items clamp to the last valid item)
-                const int e = min(e0 + u * 256, DW_HR * DW_HC * DW_Q - DW_Q + cq);
-                const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
-                const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
-                const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
-                const int sy = reflect_idx(yy, H), sx = reflect_idx(xx, W);
-                const size_t off = fbase + ((size_t)sy * W + sx) * C + c0;      // == the pixel itself when inside
-                cp_async16(tdh + pix * DW_CC + cq * 4, dh2 + off, inside);
-                vh1[u] = ld4(h1 + off);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 256;
-                const float vv[4] = {vh1[u].x, vh1[u].y, vh1[u].z, vh1[u].w};
-                float g[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const float4 k1 = cf->k1m1[cq * 4 + i]; g[i] = gelu_f(fmaf(vv[i], k1.x, k1.y)); }
-                if (e < DW_HR * DW_HC * DW_Q) st4(tg + (e / DW_Q) * DW_CC + cq * 4, make_float4(g[0], g[1], g[2], g[3]));
-            }
+        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 256) {
+            const int pix = e0 / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
+            const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
+            const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+            const size_t off = fbase + ((size_t)(inside ? yy : 0) * W + (inside ? xx : 0)) * C + c0;
+            cp_async16(tdh + pix * DW_CC + cq * 4, dh2 + off, inside);
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        // interior h1 of this thread's column (for gelu'(z1) and h1_hat), software-prefetched one row ahead
+        // h1 of this thread's column, software-prefetched one row ahead (first row in flight across the barrier)
         float4 h1next = ld4(h1 + fbase + ((size_t)y0 * W + qx) * C + c0);
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-
-        // ---- pass A: dg1 = DW^T(dh2), dz1 = dg1 * gelu'(z1), Norm1-backward statistics ----
-        {
-            float4 w[9];
-#pragma unroll
-            for (int j = 0; j < 9; ++j) w[j] = cf->w[j][cq];
+        const float4 km0 = cf->k1m1[cq * 4 + 0], km1 = cf->k1m1[cq * 4 + 1], km2 = cf->k1m1[cq * 4 + 2], km3 = cf->k1m1[cq * 4 + 3];
 #pragma unroll 1
-            for (int r = 0; r < DW_TH; ++r) {
-                const int qy = y0 + r;
-                const float4 hv = h1next;
-                if (r + 1 < DW_TH) h1next = ld4(h1 + fbase + ((size_t)(qy + 1) * W + qx) * C + c0);
-                const float* tc = tcol + (r + 1) * ROW;
-                float4 o = make_float4(0, 0, 0, 0);
-                // source p = q + (dy, dx) reaches q through tap (1-dy, 1-dx)
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const float4 t = ld4(tc + dy * ROW + dx * DW_CC);
-                        const float4 ww = w[(1 - dy) * 3 + (1 - dx)];
-                        o.x = fmaf(ww.x, t.x, o.x); o.y = fmaf(ww.y, t.y, o.y);
-                        o.z = fmaf(ww.z, t.z, o.z); o.w = fmaf(ww.w, t.w, o.w);
-                    }
-                // adjoint of reflect padding (rare): on rows 1 / H-2 and columns 1 / W-2 the border source reaches q a
-                // second time through the reflected tap: (dy=-1 -> tap row 0), (dy=+1 -> tap row 2), same for columns
-                const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
-                if (y_lo | y_hi | x_lo | x_hi) {
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const bool ya = (dy == -1) ? y_lo : ((dy == 1) ? y_hi : false);
-                            const bool xa = (dx == -1) ? x_lo : ((dx == 1) ? x_hi : false);
-                            if (ya | xa) {
-                                const int i0 = 1 - dy, j0 = 1 - dx, i1 = (dy == -1) ? 0 : 2, j1 = (dx == -1) ? 0 : 2;
-                                float4 we = make_float4(0, 0, 0, 0);
-                                if (xa) { const float4 a = w[i0 * 3 + j1]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
-                                if (ya) { const float4 a = w[i1 * 3 + j0]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
-                                if (ya && xa) { const float4 a = w[i1 * 3 + j1]; we.x += a.x; we.y += a.y; we.z += a.z; we.w += a.w; }
-                                const float4 t = ld4(tc + dy * ROW + dx * DW_CC);
-                                o.x = fmaf(we.x, t.x, o.x); o.y = fmaf(we.y, t.y, o.y);
-                                o.z = fmaf(we.z, t.z, o.z); o.w = fmaf(we.w, t.w, o.w);
-                            }
-                        }
-                }
-                const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
-                const float ov[4] = {o.x, o.y, o.z, o.w};
-                float dz[4], dzh[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float4 k1 = cf->k1m1[cq * 4 + c];
-                    const float z = fmaf(hvv[c], k1.x, k1.y);
-                    dz[c] = ov[c] * gelu_grad_f(z);
-                    dzh[c] = dz[c] * (hvv[c] - k1.z) * k1.w;
-                }
-                st4(dz1 + fbase + ((size_t)qy * W + qx) * C + c0, make_float4(dz[0], dz[1], dz[2], dz[3]));
-                s.x += dz[0]; s.y += dz[1]; s.z += dz[2]; s.w += dz[3];
-                q.x += dzh[0]; q.y += dzh[1]; q.z += dzh[2]; q.w += dzh[3];
-            }
-        }
-        // ---- pass B: depthwise weight gradient, tap (dy+1, dx+1) pairs dh2[q] with g1[reflect(q + (dy, dx))] ----
-#pragma unroll 2
         for (int r = 0; r < DW_TH; ++r) {
-            const float4 dhc = ld4(tcol + (r + 1) * ROW);
-            const float* gc = gcol + (r + 1) * ROW;
+            const int qy = y0 + r;
+            const float4 hv = h1next;
+            if (r + 1 < DW_TH) h1next = ld4(h1 + fbase + ((size_t)(qy + 1) * W + qx) * C + c0);
+            float4 g, gp;
+            gelu_both(fmaf(hv.x, km0.x, km0.y), g.x, gp.x);
+            gelu_both(fmaf(hv.y, km1.x, km1.y), g.y, gp.y);
+            gelu_both(fmaf(hv.z, km2.x, km2.y), g.z, gp.z);
+            gelu_both(fmaf(hv.w, km3.x, km3.y), g.w, gp.w);
+            const float* tc = tcol + (r + 1) * ROW;            // centre of the 3x3 neighbourhood of p
+            const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
+            const bool border = y_lo | y_hi | x_lo | x_hi;
+            float4 o = make_float4(0, 0, 0, 0);
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const float4 g = ld4(gc + dy * ROW + dx * DW_CC);
-                    float4& a = gw[(dy + 1) * 3 + dx + 1];
-                    a.x = fmaf(dhc.x, g.x, a.x); a.y = fmaf(dhc.y, g.y, a.y);
-                    a.z = fmaf(dhc.z, g.z, a.z); a.w = fmaf(dhc.w, g.w, a.w);
+                for (int j = 0; j < 3; ++j) {
+                    // tap (i, j) has offset (i-1, j-1); the regular reader of p through it is q = p - off
+                    float4 d = ld4(tc + (1 - i) * ROW + (1 - j) * DW_CC);
+                    if (border) {   // rare: adjoint of reflect padding, the mirrored reader q = p + off
+                        const bool ya = (i == 0 && y_lo) || (i == 2 && y_hi);
+                        const bool xa = (j == 0 && x_lo) || (j == 2 && x_hi);
+                        if (ya) { const float4 e = ld4(tc + (i - 1) * ROW + (1 - j) * DW_CC); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+                        if (xa) { const float4 e = ld4(tc + (1 - i) * ROW + (j - 1) * DW_CC); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+                        if (ya && xa) { const float4 e = ld4(tc + (i - 1) * ROW + (j - 1) * DW_CC); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+                    }
+                    const float4 ww = cf->w[i * 3 + j][cq];
+                    o.x = fmaf(ww.x, d.x, o.x); o.y = fmaf(ww.y, d.y, o.y);
+                    o.z = fmaf(ww.z, d.z, o.z); o.w = fmaf(ww.w, d.w, o.w);
+                    float4& a = gw[i * 3 + j];
+                    a.x = fmaf(g.x, d.x, a.x); a.y = fmaf(g.y, d.y, a.y);
+                    a.z = fmaf(g.z, d.z, a.z); a.w = fmaf(g.w, d.w, a.w);
                 }
+            const float4 dz = make_float4(o.x * gp.x, o.y * gp.y, o.z * gp.z, o.w * gp.w);
+            st4(dz1 + fbase + ((size_t)qy * W + qx) * C + c0, dz);
+            s.x += dz.x; s.y += dz.y; s.z += dz.z; s.w += dz.w;
+            q.x = fmaf(dz.x, (hv.x - km0.z) * km0.w, q.x);
+            q.y = fmaf(dz.y, (hv.y - km1.z) * km1.w, q.y);
+            q.z = fmaf(dz.z, (hv.z - km2.z) * km2.w, q.z);
+            q.w = fmaf(dz.w, (hv.w - km3.z) * km3.w, q.w);
         }
     }
     reduce_pt_atomic2(s, q, bstats1 + ((size_t)n * C + cbase) * 2, smem);
@@ -334,7 +287,7 @@ int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* 
     const int chunk = P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64);
     dh2_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(du, h2, gate, dmp, coef2, bc2, P, chunk);   // du <- dh2 in place
     UB_CHECK_LAUNCH();
-    constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float) + sizeof(DwBwdCoef);
+    constexpr size_t smem = (size_t)DW_TILE_FLOATS * sizeof(float) + sizeof(DwBwdCoef);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
