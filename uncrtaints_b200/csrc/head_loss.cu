@@ -75,32 +75,33 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     for (int i = tid; i < O * C; i += 256) ws[i] = w[i];
     float4 gw[HD_MAXO];
-    float gb = 0.f;   // thread tid < O accumulates db[tid]
+    float gbk[HD_MAXO / 2];   // bias-gradient partials: in the fill loop thread `tid` always sees outputs o = 2k + tid/128
 #pragma unroll
     for (int o = 0; o < HD_MAXO; ++o) gw[o] = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < HD_MAXO / 2; ++k) gbk[k] = 0.f;
     const int tiles_per_img = P / HD_PX;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = (int)(t / tiles_per_img), p0 = (int)(t % tiles_per_img) * HD_PX;
         __syncthreads();
-        for (int i = tid; i < O * HD_PX; i += 256) {
-            const int o = i / HD_PX, px = i % HD_PX;
-            const size_t g = ((size_t)b * O + o) * P + p0 + px;
-            const float d = dout[g], v = out[g];
-            float der;
-            if (o < UB_S2) {
-                if (mean_sigmoid) { const float sg = v / scale_by; der = scale_by * sg * (1.f - sg); }
-                else der = 1.f;
-            } else {
-                der = 1.f - expf(-(v - var_eps));   // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x)); == 1 beyond the threshold in fp32
+#pragma unroll
+        for (int k = 0; k < HD_MAXO / 2; ++k) {
+            const int i = tid + 256 * k, o = i / HD_PX, px = i % HD_PX;     // HD_PX == 128: o = 2k + tid/128
+            if (o < O) {
+                const size_t g = ((size_t)b * O + o) * P + p0 + px;
+                const float d = dout[g], v = out[g];
+                float der;
+                if (o < UB_S2) {
+                    if (mean_sigmoid) { const float sg = v / scale_by; der = scale_by * sg * (1.f - sg); }
+                    else der = 1.f;
+                } else {
+                    der = 1.f - expf(-(v - var_eps));   // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x)); == 1 beyond the threshold in fp32
+                }
+                dos[i] = d * der;
+                gbk[k] += d * der;
             }
-            dos[i] = d * der;
         }
         __syncthreads();
-        if (tid < O) {
-            float s = 0.f;
-            for (int px = 0; px < HD_PX; ++px) s += dos[tid * HD_PX + px];
-            gb += s;
-        }
         for (int px = warp; px < HD_PX; px += 8) {
             const size_t row = (size_t)b * P + p0 + px;
             const float4 a = ld4_stream(dec + row * C + lane * 4);
@@ -119,7 +120,13 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
             st4(ddec + row * C + lane * 4, acc);
         }
     }
-    if (tid < O) atomicAdd(&db[tid], gb);
+    // bias gradient: warp-reduce the per-thread partials (a warp lies inside one half of the 256 threads => one output)
+#pragma unroll
+    for (int k = 0; k < HD_MAXO / 2; ++k) {
+        const float t = warp_sum(gbk[k]);
+        const int o = 2 * k + tid / HD_PX;
+        if (lane == 0 && o < O) atomicAdd(&db[o], t);
+    }
 #pragma unroll 1
     for (int o = 0; o < O; ++o) {
         float4 v = gw[0];
