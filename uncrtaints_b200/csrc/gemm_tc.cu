@@ -107,8 +107,11 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
     const float4 a = ld4_nc(p), b = ld4_nc(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+// Coefficient vectors are stored "quad-split": the first float4 of every 8-channel chunk in the lower half of the vector,
+// the second in the upper half, so that the two LDS.128 of a lane are 16-byte contiguous across lanes (no bank conflicts).
+__device__ __forceinline__ int cf_pos(int k, int K) { return ((k >> 2) & 1) * (K / 2) + (k >> 3) * 4 + (k & 3); }
+__device__ __forceinline__ void lds8(const float* vec, int K, int ch0, float (&v)[8]) {      // ch0 % 8 == 0
+    const float4 a = *reinterpret_cast<const float4*>(vec + (ch0 >> 1)), b = *reinterpret_cast<const float4*>(vec + K / 2 + (ch0 >> 1));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
@@ -116,12 +119,12 @@ struct TLoadNormed {           // a = x*scale + shift
     const float* x; const Coef* coef;
     struct Raw { float a[8]; };
     __device__ void fill(int n, int K, float* cf) const {
-        for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; cf[k] = c.scale; cf[K + k] = c.shift; }
+        for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.scale; cf[K + q] = c.shift; }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(x + row * K + ch0, r.a); }
     __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
         float sc[8], sh[8];
-        lds8(cf + ch0, sc); lds8(cf + K + ch0, sh);
+        lds8(cf, K, ch0, sc); lds8(cf + K, K, ch0, sh);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(r.a[i], sc[i], sh[i]);
     }
@@ -132,13 +135,14 @@ struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
     __device__ void fill(int n, int K, float* cf) const {
         for (int k = threadIdx.x; k < K; k += THREADS) {
             const Coef c = coef[(size_t)n * K + k];
-            cf[k] = c.scale; cf[K + k] = c.shift; cf[2 * K + k] = gate[(size_t)n * K + k];
+            const int q = cf_pos(k, K);
+            cf[q] = c.scale; cf[K + q] = c.shift; cf[2 * K + q] = gate[(size_t)n * K + k];
         }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(h2 + row * K + ch0, r.a); }
     __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
         float sc[8], sh[8], g[8];
-        lds8(cf + ch0, sc); lds8(cf + K + ch0, sh); lds8(cf + 2 * K + ch0, g);
+        lds8(cf, K, ch0, sc); lds8(cf + K, K, ch0, sh); lds8(cf + 2 * K, K, ch0, g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = gelu_f(fmaf(r.a[i], sc[i], sh[i])) * g[i];
     }
@@ -147,12 +151,12 @@ struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
     const float* dy; const float* vv; const BCoef* bc;
     struct Raw { float a[8], b[8]; };
     __device__ void fill(int n, int K, float* cf) const {
-        for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; cf[k] = c.a; cf[K + k] = c.b; cf[2 * K + k] = c.c; }
+        for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.a; cf[K + q] = c.b; cf[2 * K + q] = c.c; }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(dy + row * K + ch0, r.a); ld8(vv + row * K + ch0, r.b); }
     __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
         float ca[8], cb[8], cc[8];
-        lds8(cf + ch0, ca); lds8(cf + K + ch0, cb); lds8(cf + 2 * K + ch0, cc);
+        lds8(cf, K, ch0, ca); lds8(cf + K, K, ch0, cb); lds8(cf + 2 * K, K, ch0, cc);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(ca[i], r.a[i], fmaf(cb[i], r.b[i], cc[i]));
     }

@@ -45,3 +45,52 @@ class FlatGradAllReduce:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / dist.get_world_size(self.group))
+
+
+class HostToDevicePrefetcher:
+    """Double-buffered H2D input pipeline: the pinned-host batch of step k+1 is copied on a side stream while step k
+    computes (the reference moves every batch synchronously in `prepare_data_multi`, train_reconstruct.py:161-179, and
+    `BaseModel.set_input`, base_model.py:87-91).  Buffers are recycled only after the step that consumed them finished."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self.slots = [None] * depth          # device tensors per slot
+        self.ready = [None] * depth          # event: copy into slot finished
+        self.free = [None] * depth           # event: compute that consumed the slot finished
+        self.head = 0                        # next slot to fill
+        self.tail = 0                        # next slot to consume
+        self.pending = 0
+
+    def submit(self, *host_tensors):
+        """Start the asynchronous copy of one batch (pinned host tensors)."""
+        i = self.head
+        if self.slots[i] is None:
+            self.slots[i] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors]
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[i] is not None:
+                self.copy_stream.wait_event(self.free[i])
+            for d, h in zip(self.slots[i], host_tensors):
+                d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.ready[i] = ev
+        self.head = (i + 1) % self.depth
+        self.pending += 1
+
+    def get(self):
+        """Device tensors of the oldest submitted batch; the current stream waits for its copy."""
+        assert self.pending > 0, "get() without submit()"
+        i = self.tail
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        self.tail = (i + 1) % self.depth
+        self.pending -= 1
+        self._last = i
+        return self.slots[i]
+
+    def release(self):
+        """Call after the step that used the tensors of the last get() has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[self._last] = ev
