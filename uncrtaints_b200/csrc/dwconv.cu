@@ -45,11 +45,20 @@ __device__ __forceinline__ void reduce_pt_atomic2(float4 a, float4 b, double* ds
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 3)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;                    // src-size 0 => the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+// K2.  The raw h1 halo tile of the NEXT 8-row tile is fetched by cp.async into the second shared-memory buffer while
+// the current tile is normalised + GELU'd in place and convolved, so no thread ever waits on HBM with work undone.
+__global__ void __launch_bounds__(256, 2)
 dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, const float* __restrict__ wdw /* [256][9] */,
                   float* __restrict__ h2, double* stats2, int H, int W) {
-    extern __shared__ __align__(16) float tile[];
+    extern __shared__ __align__(16) float smem[];
     constexpr int C = UB_HID;
+    constexpr int NITEM = DW_HR * DW_HC * DW_Q;
     const int n = blockIdx.z, cbase = blockIdx.y * DW_CC, x0 = blockIdx.x * DW_TW;
     const int cq = threadIdx.x % DW_Q, col = threadIdx.x / DW_Q;
     const int c0 = cbase + cq * 4;
@@ -65,29 +74,30 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
     float* dst = h2 + (size_t)n * H * W * C;
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
 
-    for (int y0 = 0; y0 < H; y0 += DW_TH) {
-        __syncthreads();
-        // halo tile load: 4 independent 16-byte loads in flight per thread before any of them is consumed.  Loads are
-        // unconditional (tail items clamp to the last valid item) so that the values stay in registers.
-        for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 4 * 256) {   // e % 8 == cq
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = min(e0 + u * 256, DW_HR * DW_HC * DW_Q - DW_Q + cq);
-                const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
-                const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
-                v[u] = ld4(src + ((size_t)sy * W + sx) * C + c0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 256;
-                float4 g;
-                g.x = gelu_f(fmaf(v[u].x, k[0].scale, k[0].shift));
-                g.y = gelu_f(fmaf(v[u].y, k[1].scale, k[1].shift));
-                g.z = gelu_f(fmaf(v[u].z, k[2].scale, k[2].shift));
-                g.w = gelu_f(fmaf(v[u].w, k[3].scale, k[3].shift));
-                if (e < DW_HR * DW_HC * DW_Q) st4(tile + (e / DW_Q) * DW_CC + cq * 4, g);
-            }
+    auto fetch = [&](int y0, float* buf) {          // raw halo tile (reflected source rows / columns) -> shared memory
+        for (int e = threadIdx.x; e < NITEM; e += 256) {
+            const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
+            const int sy = reflect_idx(y0 - 1 + ry, H), sx = reflect_idx(x0 - 1 + rx, W);
+            cp_async16(buf + pix * DW_CC + cq * 4, src + ((size_t)sy * W + sx) * C + c0, true);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    fetch(0, smem);
+    for (int y0 = 0, it = 0; y0 < H; y0 += DW_TH, ++it) {
+        float* tile = smem + (it & 1) * DW_TILE_FLOATS;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                               // tile landed; everybody is done with the other buffer
+        if (y0 + DW_TH < H) fetch(y0 + DW_TH, smem + ((it + 1) & 1) * DW_TILE_FLOATS);
+        for (int e = threadIdx.x; e < NITEM; e += 256) {   // in-place Norm1 + GELU (e % 8 == cq)
+            float* ptr = tile + (e / DW_Q) * DW_CC + cq * 4;
+            const float4 v = ld4(ptr);
+            float4 g;
+            g.x = gelu_f(fmaf(v.x, k[0].scale, k[0].shift));
+            g.y = gelu_f(fmaf(v.y, k[1].scale, k[1].shift));
+            g.z = gelu_f(fmaf(v.z, k[2].scale, k[2].shift));
+            g.w = gelu_f(fmaf(v.w, k[3].scale, k[3].shift));
+            st4(ptr, g);
         }
         __syncthreads();
         // one column per thread, 8 output rows
@@ -109,7 +119,7 @@ dwconv_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
             q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
         }
     }
-    reduce_pt_atomic2(s, q, stats2 + ((size_t)n * C + cbase) * 2, tile);
+    reduce_pt_atomic2(s, q, stats2 + ((size_t)n * C + cbase) * 2, smem);
 }
 
 // B3a (pointwise, in place): du <- dh2 = a2*dz2 + b2*h2 + c2 with dz2 = (du*s + dpool/P) * gelu'(h2*scale2 + shift2):
@@ -149,12 +159,6 @@ struct DwBwdCoef {
     float4 k1m1[DW_CC];   // scale1, shift1, mean1, rstd1
     float4 w[9][DW_Q];    // depthwise taps [tap][channel quad]: read per use (LDS.128), keeps the stencil loop at <= 85 registers
 };
-
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 16 : 0;                    // src-size 0 => the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
 
 // B3b (stencil).  Both the input gradient and the weight gradient are written per INPUT pixel p of the convolution:
 //   D[tap] = sum of dh2[q] over all outputs q that read p through `tap`   (normally the single q = p - off(tap);
@@ -268,7 +272,7 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st) {
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
-    constexpr size_t smem = (size_t)DW_TILE_FLOATS * sizeof(float);
+    constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(dwconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
