@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) dh2_kernel(float* __restrict__ du, const 
     }
     const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
     const size_t base = (size_t)n * P * C + c4 * 4;
-#pragma unroll 2
+#pragma unroll 4
     for (int p = p0 + r; p < p1; p += ROWS) {
         const float4 d = ld4(du + base + (size_t)p * C);
         const float4 hv = ld4_stream(h2 + base + (size_t)p * C);
@@ -172,7 +172,7 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
                   double* bstats1, float* dwdw /* [256][9] accumulated */, int H, int W) {
     extern __shared__ __align__(16) float smem[];
     float* tdh = smem;                       // dh2 halo tile, zero outside the image
-    DwBwdCoef* cf = reinterpret_cast<DwBwdCoef*>(smem + DW_TILE_FLOATS);
+    DwBwdCoef* cf = reinterpret_cast<DwBwdCoef*>(smem + 2 * DW_TILE_FLOATS);
     constexpr int C = UB_HID;
     constexpr int ROW = DW_HC * DW_CC;       // floats per halo row
     const int n = blockIdx.z, cbase = blockIdx.y * DW_CC, x0 = blockIdx.x * DW_TW;
@@ -195,21 +195,25 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
     for (int j = 0; j < 9; ++j) gw[j] = make_float4(0, 0, 0, 0);
     const int qx = x0 + col;
     const bool x_lo = (qx == 1), x_hi = (qx == W - 2);
-    const float* tcol = tdh + (col + 1) * DW_CC + cq * 4;      // this thread's column, halo row 0
-
-    for (int y0 = 0; y0 < H; y0 += DW_TH) {
-        __syncthreads();
+    auto fetch = [&](int y0, float* buf) {          // raw dh2 halo tile, zero-filled outside the image
         for (int e0 = threadIdx.x; e0 < DW_HR * DW_HC * DW_Q; e0 += 256) {
             const int pix = e0 / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
             const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
             const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
             const size_t off = fbase + ((size_t)(inside ? yy : 0) * W + (inside ? xx : 0)) * C + c0;
-            cp_async16(tdh + pix * DW_CC + cq * 4, dh2 + off, inside);
+            cp_async16(buf + pix * DW_CC + cq * 4, dh2 + off, inside);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    fetch(0, tdh);
+    for (int y0 = 0, it = 0; y0 < H; y0 += DW_TH, ++it) {
+        const float* tcol = tdh + (it & 1) * DW_TILE_FLOATS + (col + 1) * DW_CC + cq * 4;   // this thread's column, halo row 0
         // h1 of this thread's column, software-prefetched one row ahead (first row in flight across the barrier)
         float4 h1next = ld4(h1 + fbase + ((size_t)y0 * W + qx) * C + c0);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                               // tile landed; everybody is done with the other buffer
+        if (y0 + DW_TH < H) fetch(y0 + DW_TH, tdh + ((it + 1) & 1) * DW_TILE_FLOATS);
         const float4 km0 = cf->k1m1[cq * 4 + 0], km1 = cf->k1m1[cq * 4 + 1], km2 = cf->k1m1[cq * 4 + 2], km3 = cf->k1m1[cq * 4 + 3];
 #pragma unroll 1
         for (int r = 0; r < DW_TH; ++r) {
@@ -291,7 +295,7 @@ int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* 
     const int chunk = P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64);
     dh2_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(du, h2, gate, dmp, coef2, bc2, P, chunk);   // du <- dh2 in place
     UB_CHECK_LAUNCH();
-    constexpr size_t smem = (size_t)DW_TILE_FLOATS * sizeof(float) + sizeof(DwBwdCoef);
+    constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float) + sizeof(DwBwdCoef);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const float* __restrict__ 
     float s[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, gh[4] = {0, 0, 0, 0};
     const size_t base = (size_t)n * P * C + c4 * 4;
     const bool train = gp_stats != nullptr;
+#pragma unroll 4
     for (int p = p0 + r; p < p1; p += ROWS) {
         const float4 v = ld4(h2 + base + (size_t)p * C);
         const float vv[4] = {v.x, v.y, v.z, v.w};
