@@ -122,11 +122,11 @@ struct TLoadNormed {           // a = x*scale + shift
         for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.scale; cf[K + q] = c.shift; }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(x + row * K + ch0, r.a); }
-    __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
-        float sc[8], sh[8];
-        lds8(cf, K, ch0, sc); lds8(cf + K, K, ch0, sh);
+    struct Cf { float sc[8], sh[8]; };
+    __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const { lds8(cf, K, ch0, c.sc); lds8(cf + K, K, ch0, c.sh); }
+    __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaf(r.a[i], sc[i], sh[i]);
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(r.a[i], c.sc[i], c.sh[i]);
     }
 };
 struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
@@ -140,11 +140,13 @@ struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
         }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(h2 + row * K + ch0, r.a); }
-    __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
-        float sc[8], sh[8], g[8];
-        lds8(cf, K, ch0, sc); lds8(cf + K, K, ch0, sh); lds8(cf + 2 * K, K, ch0, g);
+    struct Cf { float sc[8], sh[8], g[8]; };
+    __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const {
+        lds8(cf, K, ch0, c.sc); lds8(cf + K, K, ch0, c.sh); lds8(cf + 2 * K, K, ch0, c.g);
+    }
+    __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_f(fmaf(r.a[i], sc[i], sh[i])) * g[i];
+        for (int i = 0; i < 8; ++i) v[i] = gelu_f(fmaf(r.a[i], c.sc[i], c.sh[i])) * c.g[i];
     }
 };
 struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
@@ -154,11 +156,13 @@ struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
         for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.a; cf[K + q] = c.b; cf[2 * K + q] = c.c; }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(dy + row * K + ch0, r.a); ld8(vv + row * K + ch0, r.b); }
-    __device__ void finish(const Raw& r, int K, int ch0, const float* cf, float (&v)[8]) const {
-        float ca[8], cb[8], cc[8];
-        lds8(cf, K, ch0, ca); lds8(cf + K, K, ch0, cb); lds8(cf + 2 * K, K, ch0, cc);
+    struct Cf { float ca[8], cb[8], cc[8]; };
+    __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const {
+        lds8(cf, K, ch0, c.ca); lds8(cf + K, K, ch0, c.cb); lds8(cf + 2 * K, K, ch0, c.cc);
+    }
+    __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaf(ca[i], r.a[i], fmaf(cb[i], r.b[i], cc[i]));
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(c.ca[i], r.a[i], fmaf(c.cb[i], r.b[i], c.cc[i]));
     }
 };
 
@@ -306,13 +310,17 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
         mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);    // MMAs that read this ring slot are done
         char* hi = sA + slot * STAGE_BYTES;
         char* lo = hi + STAGE_BYTES / 2;
+        {
+            typename ALoad::Cf cfr;                        // this thread's 8 channels of the K-block: one coefficient read for both rows
+            al.coefs(K, kb * KBLK + pc8 * 8, sCf, cfr);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int r = pr + 64 * j;
-            float v[8];
-            al.finish(cur[j], K, kb * KBLK + pc8 * 8, sCf, v);
-            const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
-            split_store8(v, hi + off, lo + off);
+            for (int j = 0; j < 2; ++j) {
+                const int r = pr + 64 * j;
+                float v[8];
+                al.finish(cur[j], cfr, v);
+                const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
+                split_store8(v, hi + off, lo + off);
+            }
         }
         fence_proxy_async();
         __syncthreads();
@@ -484,15 +492,19 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
         {
             const int r = half * 32 + ra;
             float v[8];
-            la.finish(ca_raw, 128, ca * 8, sCfA, v);
+            typename LA::Cf cfa;
+            la.coefs(128, ca * 8, sCfA, cfa);
+            la.finish(ca_raw, cfa, v);
             const int off = (ca / 8) * WG_BLK + r * 128 + (((ca % 8) ^ (r & 7)) << 4);
             split_store8(v, a_hi + off, a_lo + off);
         }
+        typename LB::Cf cfb;                              // both B rows of this thread share the channel chunk
+        lb.coefs(256, cb * 8, sCfB, cfb);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int r = half * 32 + rb + 16 * j;
             float v[8];
-            lb.finish(cb_raw[j], 256, cb * 8, sCfB, v);
+            lb.finish(cb_raw[j], cfb, v);
             const int off = (cb / 8) * WG_BLK + r * 128 + (((cb % 8) ^ (r & 7)) << 4);
             split_store8(v, b_hi + off, b_lo + off);
         }

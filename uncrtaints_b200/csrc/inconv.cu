@@ -56,52 +56,78 @@ __global__ void __launch_bounds__(256) inconv_kernel(const float* __restrict__ x
             if (MODE == 0 && pb + px < p1 && !(v == pad_value)) any_nonpad = true;
         }
         __syncthreads();
-        for (int px = warp; px < IC_PX && pb + px < p1; px += 8) {
-            float4 acc = b4;
+        // each warp owns 8 consecutive pixels of the tile, processed as two groups of 4 (4-way ILP; the x values of a
+        // group are one broadcast LDS.128 per input channel, the weights one LDS.128 per lane)
+        for (int g4 = 0; g4 < 2; ++g4) {
+            const int px0 = warp * 8 + g4 * 4;
+            if (pb + px0 >= p1) break;
+            float4 acc[4] = {b4, b4, b4, b4};
             for (int ci = 0; ci < Cin; ++ci) {
-                const float xv = xs[ci * IC_PX + px];
+                const float4 xv = ld4(xs + ci * IC_PX + px0);
                 const float4 wv = ld4(ws + ci * C + lane * 4);
-                acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y);
-                acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+                const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[j].x = fmaf(xx[j], wv.x, acc[j].x); acc[j].y = fmaf(xx[j], wv.y, acc[j].y);
+                    acc[j].z = fmaf(xx[j], wv.z, acc[j].z); acc[j].w = fmaf(xx[j], wv.w, acc[j].w);
+                }
             }
-            const size_t row = (size_t)n * P + pb + px;
-            if (MODE == 0) {
-                s.x += acc.x; s.y += acc.y; s.z += acc.z; s.w += acc.w;
-                q.x += acc.x * acc.x; q.y += acc.y * acc.y; q.z += acc.z * acc.z; q.w += acc.w * acc.w;
-            } else if (MODE == 1) {
-                float4 o;
-                o.x = fmaxf(fmaf(acc.x, k[0].scale, k[0].shift), 0.f);
-                o.y = fmaxf(fmaf(acc.y, k[1].scale, k[1].shift), 0.f);
-                o.z = fmaxf(fmaf(acc.z, k[2].scale, k[2].shift), 0.f);
-                o.w = fmaxf(fmaf(acc.w, k[3].scale, k[3].shift), 0.f);
-                st4(x0 + row * C + lane * 4, o);
-                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-                q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
-            } else {
-                const float4 g = ld4_stream(dx0 + row * C + lane * 4);
-                const float cv[4] = {acc.x, acc.y, acc.z, acc.w};
-                const float gv[4] = {g.x, g.y, g.z, g.w};
-                float dgn[4];
+            float dcs[4][4];       // MODE 3: dc0 of the 4 pixels
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dgn[i] = fmaf(cv[i], k[i].scale, k[i].shift) > 0.f ? gv[i] : 0.f;
-                if (MODE == 2) {
-                    s.x += dgn[0]; s.y += dgn[1]; s.z += dgn[2]; s.w += dgn[3];
-                    q.x += dgn[0] * (cv[0] - m[0].mean) * m[0].rstd;
-                    q.y += dgn[1] * (cv[1] - m[1].mean) * m[1].rstd;
-                    q.z += dgn[2] * (cv[2] - m[2].mean) * m[2].rstd;
-                    q.w += dgn[3] * (cv[3] - m[3].mean) * m[3].rstd;
+            for (int j = 0; j < 4; ++j) {
+                const int px = px0 + j;
+                const bool live = pb + px < p1;
+                const size_t row = (size_t)n * P + pb + px;
+                const float cv[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+                if (MODE == 0) {
+                    if (live) {
+                        s.x += cv[0]; s.y += cv[1]; s.z += cv[2]; s.w += cv[3];
+                        q.x += cv[0] * cv[0]; q.y += cv[1] * cv[1]; q.z += cv[2] * cv[2]; q.w += cv[3] * cv[3];
+                    }
+                } else if (MODE == 1) {
+                    float4 o;
+                    o.x = fmaxf(fmaf(cv[0], k[0].scale, k[0].shift), 0.f);
+                    o.y = fmaxf(fmaf(cv[1], k[1].scale, k[1].shift), 0.f);
+                    o.z = fmaxf(fmaf(cv[2], k[2].scale, k[2].shift), 0.f);
+                    o.w = fmaxf(fmaf(cv[3], k[3].scale, k[3].shift), 0.f);
+                    if (live) {
+                        st4(x0 + row * C + lane * 4, o);
+                        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+                        q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
+                    }
                 } else {
-                    float dc[4];
+                    float4 g = make_float4(0, 0, 0, 0);
+                    if (live) g = ld4_stream(dx0 + row * C + lane * 4);
+                    const float gv[4] = {g.x, g.y, g.z, g.w};
+                    float dgn[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dc[i] = fmaf(bk[i].a, dgn[i], fmaf(bk[i].b, cv[i], bk[i].c));
-                    s.x += dc[0]; s.y += dc[1]; s.z += dc[2]; s.w += dc[3];
+                    for (int i = 0; i < 4; ++i) dgn[i] = fmaf(cv[i], k[i].scale, k[i].shift) > 0.f ? gv[i] : 0.f;
+                    if (MODE == 2) {
+                        if (live) {
+                            s.x += dgn[0]; s.y += dgn[1]; s.z += dgn[2]; s.w += dgn[3];
+                            q.x += dgn[0] * (cv[0] - m[0].mean) * m[0].rstd;
+                            q.y += dgn[1] * (cv[1] - m[1].mean) * m[1].rstd;
+                            q.z += dgn[2] * (cv[2] - m[2].mean) * m[2].rstd;
+                            q.w += dgn[3] * (cv[3] - m[3].mean) * m[3].rstd;
+                        }
+                    } else {
 #pragma unroll
-                    for (int ci = 0; ci < IC_MAXC; ++ci) {
-                        if (ci < Cin) {
-                            const float xv = xs[ci * IC_PX + px];
-                            float4& a = gw[MODE == 3 ? ci : 0];
-                            a.x = fmaf(dc[0], xv, a.x); a.y = fmaf(dc[1], xv, a.y);
-                            a.z = fmaf(dc[2], xv, a.z); a.w = fmaf(dc[3], xv, a.w);
+                        for (int i = 0; i < 4; ++i) dcs[j][i] = live ? fmaf(bk[i].a, dgn[i], fmaf(bk[i].b, cv[i], bk[i].c)) : 0.f;
+                        s.x += dcs[j][0]; s.y += dcs[j][1]; s.z += dcs[j][2]; s.w += dcs[j][3];
+                    }
+                }
+            }
+            if (MODE == 3) {
+#pragma unroll
+                for (int ci = 0; ci < IC_MAXC; ++ci) {
+                    if (ci < Cin) {
+                        const float4 xv = ld4(xs + ci * IC_PX + px0);
+                        const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+                        float4& a = gw[MODE == 3 ? ci : 0];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            a.x = fmaf(dcs[j][0], xx[j], a.x); a.y = fmaf(dcs[j][1], xx[j], a.y);
+                            a.z = fmaf(dcs[j][2], xx[j], a.z); a.w = fmaf(dcs[j][3], xx[j], a.w);
                         }
                     }
                 }
