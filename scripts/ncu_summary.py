@@ -23,6 +23,7 @@ KEYS = [
     ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
 ]
+traffic = {}
 lines = [f"# ncu --set full summaries ({tag})", "",
          "Captured with `scripts/gpu_ncu.sh` (`ncu --set full --clock-control none --import-source on`, bench.py --batch 4 --steps 1);",
          "times are cold-cache single launches: compare shares and percentages, not absolutes. Units as printed by ncu "
@@ -38,6 +39,14 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
         name = d.get("Kernel Name", "?").split("(")[0][:70]
+        try:   # DRAM traffic per launch in bytes (raw page prints Mbyte / Gbyte)
+            def tobytes(key):
+                v, un = float(d[key]), u.get(key, "").lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(un, 1)
+            traffic.setdefault(name.strip(), []).append({"dram_bytes": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
+                                                         "grid": d.get("launch__grid_size", "")})
+        except (KeyError, ValueError):
+            pass
         vals = []
         for k, _ in KEYS:
             v = d.get(k, "")
@@ -53,6 +62,10 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
         lines.append(f"| {name} | " + " | ".join(vals) + f" | {top} |")
     lines.append("")
 open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w").write("\n".join(lines))
+import json
+json.dump({"note": "per-launch dram__bytes_read.sum + dram__bytes_write.sum from ncu --set full; captured with bench.py --batch 4 "
+                   "(decoder launches = 4 frames, encoder launches = 12 frames)", "kernels": traffic},
+          open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1)
 
 src = os.path.join(ROOT, "gpurun_out", "launches.csv")
 if os.path.exists(src):

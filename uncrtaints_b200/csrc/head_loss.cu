@@ -62,28 +62,37 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------------------------------
 // head backward.  do = dOut * f'(out) from the saved output; dDec = do * W; dW += do^T dec; db += sum do.
-// Persistent CTAs: register accumulators for dW/db, flushed once.
+// Persistent CTAs (2 per SM).  Per 128-pixel tile: the decoder-output tile is staged in shared memory by cp.async
+// while the 26 x 128 `do` tile is built; dDec is produced one pixel per warp iteration; the weight gradient is split by
+// output over the warps (warp w owns outputs w, w+8, w+16, w+24: 4 float4 register accumulators, flushed once per CTA).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dout /* [B][O][P] */, const float* __restrict__ out,
-                                                        const float* __restrict__ dec, const float* __restrict__ w,
-                                                        float* __restrict__ ddec, float* dw, float* db, int O, int P,
-                                                        long long total_tiles, float scale_by, int mean_sigmoid, float var_eps) {
+__global__ void __launch_bounds__(256, 2) head_bwd_kernel(const float* __restrict__ dout /* [B][O][P] */, const float* __restrict__ out,
+                                                          const float* __restrict__ dec, const float* __restrict__ w,
+                                                          float* __restrict__ ddec, float* dw, float* db, int O, int P,
+                                                          long long total_tiles, float scale_by, int mean_sigmoid, float var_eps) {
     constexpr int C = UB_WIDTH;
-    __shared__ __align__(16) float ws[HD_MAXO * C];
-    __shared__ float dos[HD_MAXO * HD_PX];      // [o][px]
-    __shared__ __align__(16) float red[8 * C];
+    extern __shared__ __align__(16) float hsm[];
+    float* dect = hsm;                         // [128 px][128 ch]
+    float* ws = hsm + HD_PX * C;               // [O][128]
+    float* dos = ws + HD_MAXO * C;             // [O][128 px]
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     for (int i = tid; i < O * C; i += 256) ws[i] = w[i];
-    float4 gw[HD_MAXO];
+    float4 gw[4];
     float gbk[HD_MAXO / 2];   // bias-gradient partials: in the fill loop thread `tid` always sees outputs o = 2k + tid/128
 #pragma unroll
-    for (int o = 0; o < HD_MAXO; ++o) gw[o] = make_float4(0, 0, 0, 0);
+    for (int j = 0; j < 4; ++j) gw[j] = make_float4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < HD_MAXO / 2; ++k) gbk[k] = 0.f;
     const int tiles_per_img = P / HD_PX;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = (int)(t / tiles_per_img), p0 = (int)(t % tiles_per_img) * HD_PX;
+        const size_t row0 = (size_t)b * P + p0;
         __syncthreads();
+        for (int i = tid; i < HD_PX * (C / 4); i += 256) {       // contiguous 64 KB
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dect + i * 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(dec + row0 * C + (size_t)i * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
         for (int k = 0; k < HD_MAXO / 2; ++k) {
             const int i = tid + 256 * k, o = i / HD_PX, px = i % HD_PX;     // HD_PX == 128: o = 2k + tid/128
@@ -101,10 +110,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                 gbk[k] += d * der;
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        // input gradient: one pixel per warp iteration, lane = 4 channels
         for (int px = warp; px < HD_PX; px += 8) {
-            const size_t row = (size_t)b * P + p0 + px;
-            const float4 a = ld4_stream(dec + row * C + lane * 4);
             float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int o = 0; o < HD_MAXO; ++o) {
@@ -113,11 +122,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                     const float4 wv = ld4(ws + o * C + lane * 4);
                     acc.x = fmaf(d, wv.x, acc.x); acc.y = fmaf(d, wv.y, acc.y);
                     acc.z = fmaf(d, wv.z, acc.z); acc.w = fmaf(d, wv.w, acc.w);
-                    gw[o].x = fmaf(d, a.x, gw[o].x); gw[o].y = fmaf(d, a.y, gw[o].y);
-                    gw[o].z = fmaf(d, a.z, gw[o].z); gw[o].w = fmaf(d, a.w, gw[o].w);
                 }
             }
-            st4(ddec + row * C + lane * 4, acc);
+            st4(ddec + (row0 + px) * C + lane * 4, acc);
+        }
+        // weight gradient: warp owns outputs warp + 8j
+#pragma unroll 4
+        for (int px = 0; px < HD_PX; ++px) {
+            const float4 a = ld4(dect + px * C + lane * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = warp + 8 * j;
+                if (o < O) {
+                    const float d = dos[o * HD_PX + px];
+                    gw[j].x = fmaf(d, a.x, gw[j].x); gw[j].y = fmaf(d, a.y, gw[j].y);
+                    gw[j].z = fmaf(d, a.z, gw[j].z); gw[j].w = fmaf(d, a.w, gw[j].w);
+                }
+            }
         }
     }
     // bias gradient: warp-reduce the per-thread partials (a warp lies inside one half of the 256 threads => one output)
@@ -127,19 +148,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         const int o = 2 * k + tid / HD_PX;
         if (lane == 0 && o < O) atomicAdd(&db[o], t);
     }
-#pragma unroll 1
-    for (int o = 0; o < O; ++o) {
-        float4 v = gw[0];
 #pragma unroll
-        for (int j = 1; j < HD_MAXO; ++j) if (j == o) v = gw[j];
-        __syncthreads();
-        st4(red + warp * C + lane * 4, v);
-        __syncthreads();
-        if (tid < C) {
-            float t = 0.f;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) t += red[r * C + tid];
-            atomicAdd(&dw[o * C + tid], t);
+    for (int j = 0; j < 4; ++j) {
+        const int o = warp + 8 * j;
+        if (o < O) {
+            atomicAdd(&dw[o * C + lane * 4 + 0], gw[j].x); atomicAdd(&dw[o * C + lane * 4 + 1], gw[j].y);
+            atomicAdd(&dw[o * C + lane * 4 + 2], gw[j].z); atomicAdd(&dw[o * C + lane * 4 + 3], gw[j].w);
         }
     }
 }
@@ -247,9 +261,15 @@ int launch_head_fwd(const float* dec, const float* w, const float* bias, float* 
 int launch_head_bwd(const float* dout, const float* out, const float* dec, const float* w, float* ddec, float* dw, float* db,
                     int B, int O, int P, float scale_by, int mean_sigmoid, float var_eps, int num_sms, cudaStream_t st) {
     if (O > HD_MAXO || O < UB_S2 || P % HD_PX) return UB_ERR_ARG;
+    constexpr size_t smem = (size_t)(HD_PX * UB_WIDTH + HD_MAXO * UB_WIDTH + HD_MAXO * HD_PX) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+        attr_set = true;
+    }
     const long long tiles = (long long)B * (P / HD_PX);
     const int blocks = (int)(tiles < 2LL * num_sms ? tiles : 2LL * num_sms);
-    head_bwd_kernel<<<blocks, 256, 0, st>>>(dout, out, dec, w, ddec, dw, db, O, P, tiles, scale_by, mean_sigmoid, var_eps);
+    head_bwd_kernel<<<blocks, 256, smem, st>>>(dout, out, dec, w, ddec, dw, db, O, P, tiles, scale_by, mean_sigmoid, var_eps);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
