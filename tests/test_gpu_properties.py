@@ -29,13 +29,13 @@ def test_full_size_eval_determinism_and_permutation(golden_weights, full_batch):
         b = net(x, batch_positions=d).clone()
         assert a.shape == (16, 1, 26, 256, 256)
         assert rel_l2(a, b) < 1e-6                               # fp64 atomics may reorder; values must agree to rounding
-        perm = torch.randperm(16, generator=torch.Generator().manual_seed(0)).cuda()
-        c = net(x[perm].contiguous(), batch_positions=d[perm].contiguous())
-        assert rel_l2(c, a[perm]) < 1e-5                         # eval: GroupNorm per sample, BatchNorm running stats
         attn = tap(net, "attn", (16, 16, 3, 32, 32))
         assert float((attn.sum(dim=2) - 1).abs().max()) < 1e-5   # softmax over T
         notpad = tap(net, "notpad", (16, 3), torch.int32)
         assert int((notpad == 0).sum()) == 1 and int(notpad[3, 2]) == 0
+        perm = torch.randperm(16, generator=torch.Generator().manual_seed(0)).cuda()
+        c = net(x[perm].contiguous(), batch_positions=d[perm].contiguous())
+        assert rel_l2(c, a[perm]) < 1e-5                         # eval: GroupNorm per sample, BatchNorm running stats
     assert torch.isfinite(a).all()
     assert float(a[:, :, :13].min()) >= 0 and float(a[:, :, :13].max()) <= 10.0     # scale_by * sigmoid
     assert float(a[:, :, 13:].min()) >= 1e-3                                          # softplus + eps
