@@ -110,6 +110,8 @@ int ub200_prof_read(int kid, double* total_ms, int* launches);
  * instruction descriptor (defaults follow CUTLASS cute/arch/mma_sm100_desc.hpp). */
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+/* 1 (default): warp-specialised tcgen05 GEMM kernel (producer warps / epilogue warps); 0: the single-role kernel. */
+int ub200_tc_set_warp_specialized(int on);
 
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
  * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,

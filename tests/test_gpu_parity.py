@@ -63,8 +63,20 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3])
+@pytest.mark.parametrize("backend", [0, 1, 3, 103])
 def test_golden_diag_train_pad(golden_weights, backend):
+    import uncrtaints_b200 as ub
+    from uncrtaints_b200 import _lib
+    if backend >= 100:                      # 103: backend 3 with the single-role (not warp-specialised) tcgen05 GEMM kernel
+        backend -= 100
+        _lib.lib().ub200_tc_set_warp_specialized(0)
+    try:
+        _golden_diag_train_pad(golden_weights, backend)
+    finally:
+        _lib.lib().ub200_tc_set_warp_specialized(1)
+
+
+def _golden_diag_train_pad(golden_weights, backend):
     import uncrtaints_b200 as ub
     c = load_npz("case_diag_train_pad.npz")
     x, y, d = (torch.from_numpy(c[k]).cuda() for k in ("x", "y", "dates"))
@@ -316,8 +328,8 @@ def test_philox_dropout_statistics(golden_weights):
     assert abs(float(a1.double().mean() / base.double().mean()) - 1.0) < 5e-3
 
 
-@pytest.mark.parametrize("backend", [0, 1])
-def test_gemm1_op_vs_fp64(backend):
+@pytest.mark.parametrize("backend,ws", [(0, 1), (1, 0), (1, 1)])
+def test_gemm1_op_vs_fp64(backend, ws):
     """The 1x1 expand GEMM alone (ub200_gemm1_forward): fp32 CUDA-core path and tcgen05 bf16x3 path vs an fp64 matmul."""
     from uncrtaints_b200 import _lib
     L = _lib.lib()
@@ -332,13 +344,17 @@ def test_gemm1_op_vs_fp64(backend):
     h1 = torch.zeros(N, P, 256, device="cuda")
     stats = torch.zeros(N, 256, 2, dtype=torch.float64, device="cuda")
     scratch = torch.empty(256 * 1024, dtype=torch.uint8, device="cuda")
-    _lib.check(L.ub200_gemm1_forward(backend, xd.data_ptr(), cd.data_ptr(), wd.data_ptr(), h1.data_ptr(), stats.data_ptr(), N, P,
-                                     scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "gemm1_forward")
-    torch.cuda.synchronize()
+    L.ub200_tc_set_warp_specialized(ws)       # 1 = producer/epilogue warp-specialised kernel (default), 0 = single-role kernel
+    try:
+        _lib.check(L.ub200_gemm1_forward(backend, xd.data_ptr(), cd.data_ptr(), wd.data_ptr(), h1.data_ptr(), stats.data_ptr(), N, P,
+                                         scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "gemm1_forward")
+        torch.cuda.synchronize()
+    finally:
+        L.ub200_tc_set_warp_specialized(1)
     e = rel_l2(h1, ref)
     es = rel_l2(stats[..., 0], ref.sum(1))
     eq = rel_l2(stats[..., 1], (ref ** 2).sum(1))
-    report("parity_report.txt", [f"gemm1 op backend={backend}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
+    report("parity_report.txt", [f"gemm1 op backend={backend} ws={ws}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
     assert e < 5e-5 and es < 1e-4 and eq < 1e-4
 
 

@@ -362,6 +362,177 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-specialised variant (default): warps 0-7 produce operand tiles (and thread 0 issues the MMAs), warps 8-15 run
+// the epilogue, so the TMEM -> HBM stores of tile t-1 overlap the HBM loads / conversion of tile t instead of
+// alternating with them.  Synchronisation: named barrier 1 (256 producer threads) before each MMA batch; mbarriers
+// free[slot] (tcgen05.commit -> producers), accfull[stage] (tcgen05.commit -> epilogue), accempty[stage] (8 epilogue
+// warps -> MMA thread); the weight image arrives by cp.async.bulk (TMA bulk copy) on wbar while the first tile is built.
+// Producers work in half K-blocks (64 pixel rows) so that the register prefetch depth stays at 2 items per thread.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int K, int NOUT, class ALoad, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_ws_kernel(ALoad al, const uint4* __restrict__ wimg, Epi ep, int P) {
+    constexpr int KB = K / KBLK, MH = NOUT / 128;
+    constexpr int W_BYTES = K * NOUT * 4, W_HALF = K * NOUT * 2;
+    constexpr int ACC_COLS = MH * TILE_PX;
+    constexpr int NPROD = 256;
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    char* sW = smem;
+    char* sA = smem + W_BYTES;
+    float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * K);    // free[2], accfull[2], accempty[2], wbar
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 7);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, n = blockIdx.y;
+    const uint32_t bFree = smem_u32(&sBar[0]), bFull = smem_u32(&sBar[2]), bEmpty = smem_u32(&sBar[4]), bW = smem_u32(&sBar[6]);
+
+    const int tiles_per_frame = P / TILE_PX;
+    const int t0 = (int)(((long long)blockIdx.x * tiles_per_frame) / gridDim.x);
+    const int t1 = (int)(((long long)(blockIdx.x + 1) * tiles_per_frame) / gridDim.x);
+    const int ntiles = t1 - t0;
+
+    al.fill(n, K, sCf);
+    if (tid == 0) {
+        mbar_init(bFree, 1); mbar_init(bFree + 8, 1);
+        mbar_init(bFull, 1); mbar_init(bFull + 8, 1);
+        mbar_init(bEmpty, 8); mbar_init(bEmpty + 8, 8);
+        mbar_init(bW, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+
+    if (warp < 8) {
+        // ================= producers (+ MMA issue by thread 0) =================
+        if (tid == 0 && ntiles > 0) {        // weight image: 8 x 16 KB TMA bulk copies, completion on wbar
+            mbar_expect_tx(bW, W_BYTES);
+            for (int i = 0; i < W_BYTES / 16384; ++i)
+                bulk_g2s(smem_u32(sW) + i * 16384, reinterpret_cast<const char*>(wimg) + (size_t)i * 16384, 16384, bW);
+        }
+        const int pc8 = tid % 8, pr = tid / 8;             // chunk pc8 of rows pr, pr+32 within a 64-row half
+        const long long HS = (long long)ntiles * KB * 2;    // half-steps
+        typename ALoad::Raw raw[2];
+        if (HS > 0) {
+            const size_t row0 = (size_t)n * P + (size_t)t0 * TILE_PX;
+            al.issue(row0 + pr, K, pc8 * 8, raw[0]);
+            al.issue(row0 + pr + 32, K, pc8 * 8, raw[1]);
+        }
+        for (long long h = 0; h < HS; ++h) {
+            const int q = (int)(h >> 1), half = (int)(h & 1);
+            const int it = q / KB, kb = q % KB;
+            typename ALoad::Raw cur[2] = {raw[0], raw[1]};
+            if (h + 1 < HS) {
+                const int nq = (int)((h + 1) >> 1), nhalf = (int)((h + 1) & 1);
+                const size_t nrow0 = (size_t)n * P + (size_t)(t0 + nq / KB) * TILE_PX + nhalf * 64;
+                al.issue(nrow0 + pr, K, (nq % KB) * KBLK + pc8 * 8, raw[0]);
+                al.issue(nrow0 + pr + 32, K, (nq % KB) * KBLK + pc8 * 8, raw[1]);
+            }
+            const uint32_t slot = (uint32_t)q % NSTAGE, u = (uint32_t)q / NSTAGE;
+            if (half == 0) mbar_wait(bFree + slot * 8, (u & 1) ^ 1);
+            char* hi = sA + slot * STAGE_BYTES;
+            char* lo = hi + STAGE_BYTES / 2;
+            {
+                typename ALoad::Cf cfr;
+                al.coefs(K, kb * KBLK + pc8 * 8, sCf, cfr);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = half * 64 + pr + 32 * j;
+                    float v[8];
+                    al.finish(cur[j], cfr, v);
+                    const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
+                    split_store8(v, hi + off, lo + off);
+                }
+            }
+            if (half == 1) {
+                fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+                if (tid == 0) {
+                    if (q == 0) mbar_wait(bW, 0);                                  // weight image landed
+                    if (kb == 0) {                                                 // accumulator stage drained by the epilogue?
+                        const uint32_t v = (uint32_t)(it >> 1);
+                        mbar_wait(bEmpty + (it & 1) * 8, (v & 1) ^ 1);
+                    }
+                    tc_fence_after();
+                    const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
+                    const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
+                    const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
+                    const uint32_t idesc = c_idesc;
+#pragma unroll
+                    for (int j = 0; j < MH; ++j) {
+                        const uint32_t d = tmem_base + acc + j * TILE_PX;
+#pragma unroll
+                        for (int k16 = 0; k16 < KBLK / 16; ++k16) {
+                            const uint64_t wa = make_desc(a_hi + j * (128 * 128) + k16 * 32);
+                            const uint64_t wl = make_desc(a_lo + j * (128 * 128) + k16 * 32);
+                            const uint64_t xa = make_desc(b_hi + k16 * 32);
+                            const uint64_t xl = make_desc(b_lo + k16 * 32);
+                            tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
+                            tc_mma(d, wa, xl, idesc, 1);
+                            tc_mma(d, wl, xa, idesc, 1);
+                        }
+                    }
+                    tc_commit(bFree + slot * 8);
+                    if (kb == KB - 1) tc_commit(bFull + (it & 1) * 8);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int ew = warp - 8, lq = ew % 4, ph = ew / 4;     // TMEM lane quarter, pixel half (64 pixels)
+        typename Epi::State est[MH];
+        float stat[MH][Epi::NS];
+#pragma unroll
+        for (int j = 0; j < MH; ++j) {
+            ep.init(n, NOUT, j * 128 + lq * 32 + lane, est[j]);
+#pragma unroll
+            for (int s = 0; s < Epi::NS; ++s) stat[j][s] = 0.f;
+        }
+        for (int it = 0; it < ntiles; ++it) {
+            mbar_wait(bFull + (it & 1) * 8, (uint32_t)(it >> 1) & 1);
+            tc_fence_after();
+            const size_t prow0 = (size_t)n * P + (size_t)(t0 + it) * TILE_PX + ph * 64;
+#pragma unroll
+            for (int j = 0; j < MH; ++j)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(it & 1) * ACC_COLS + j * TILE_PX + ph * 64 + sl * 32, v);
+                    ep.apply(est[j], prow0 + sl * 32, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+                }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bEmpty + (it & 1) * 8);
+        }
+        double* dst = ep.dst(n, NOUT);
+#pragma unroll
+        for (int j = 0; j < MH; ++j)
+#pragma unroll
+            for (int s = 0; s < Epi::NS; ++s)
+                atomicAdd(&dst[(size_t)(j * 128 + lq * 32 + lane) * Epi::NS + s], (double)stat[j][s]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 static int sm_count() {
     static int n = 0;
@@ -381,18 +552,24 @@ static int blocks_per_frame(int N, int tiles) {
     return g < 1 ? 1 : g;
 }
 
+static int g_warp_specialized = 1;      // tc_set_warp_specialized(): 1 = gemm_tc_ws_kernel (default), 0 = gemm_tc_kernel
+
 template <int K, int NOUT, class ALoad, class Epi>
 static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t st) {
     if (P % TILE_PX != 0) return UB_ERR_ARG;
-    constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + (NSTAGE + 2) * 8 + 16 + 1024;
+    constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + 8 * 8 + 16 + 1024;
     auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi>;
+    auto kern_ws = gemm_tc_ws_kernel<K, NOUT, ALoad, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+        if (cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
         attr_set = true;
     }
     const int tiles = P / TILE_PX;
-    kern<<<dim3(blocks_per_frame(N, tiles), N), THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
+    const dim3 grid(blocks_per_frame(N, tiles), N);
+    if (g_warp_specialized) kern_ws<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
+    else kern<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
@@ -636,6 +813,7 @@ int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
     if (cudaMemcpyToSymbol(tc::c_wg_idesc, &idesc, 4) != cudaSuccess) return UB_ERR_CUDA;
     return UB_OK;
 }
+int tc_set_warp_specialized(int on) { tc::g_warp_specialized = on ? 1 : 0; return UB_OK; }
 int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
     if (cudaMemcpyToSymbol(tc::c_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
     if (cudaMemcpyToSymbol(tc::c_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;

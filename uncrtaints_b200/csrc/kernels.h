@@ -54,6 +54,7 @@ int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* 
 int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
               int max_parts, float* dw1, int N, int P, cudaStream_t st);
 int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+int tc_set_warp_specialized(int on);
 int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 
 // dwconv.cu
