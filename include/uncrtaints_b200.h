@@ -110,7 +110,8 @@ int ub200_prof_read(int kid, double* total_ms, int* launches);
  * instruction descriptor (defaults follow CUTLASS cute/arch/mma_sm100_desc.hpp). */
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
-/* 1 (default): warp-specialised tcgen05 GEMM kernel (producer warps / epilogue warps); 0: the single-role kernel. */
+/* 0 (default): single-role tcgen05 GEMM kernel; 1: warp-specialised variant (producer warps / epilogue warps, TMA bulk
+ * weight load) -- kept for experiments, measured slightly slower. */
 int ub200_tc_set_warp_specialized(int on);
 
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):

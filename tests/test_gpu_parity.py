@@ -67,13 +67,13 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
 def test_golden_diag_train_pad(golden_weights, backend):
     import uncrtaints_b200 as ub
     from uncrtaints_b200 import _lib
-    if backend >= 100:                      # 103: backend 3 with the single-role (not warp-specialised) tcgen05 GEMM kernel
+    if backend >= 100:                      # 103: backend 3 with the warp-specialised tcgen05 GEMM kernel
         backend -= 100
-        _lib.lib().ub200_tc_set_warp_specialized(0)
+        _lib.lib().ub200_tc_set_warp_specialized(1)
     try:
         _golden_diag_train_pad(golden_weights, backend)
     finally:
-        _lib.lib().ub200_tc_set_warp_specialized(1)
+        _lib.lib().ub200_tc_set_warp_specialized(0)
 
 
 def _golden_diag_train_pad(golden_weights, backend):
@@ -344,13 +344,13 @@ def test_gemm1_op_vs_fp64(backend, ws):
     h1 = torch.zeros(N, P, 256, device="cuda")
     stats = torch.zeros(N, 256, 2, dtype=torch.float64, device="cuda")
     scratch = torch.empty(256 * 1024, dtype=torch.uint8, device="cuda")
-    L.ub200_tc_set_warp_specialized(ws)       # 1 = producer/epilogue warp-specialised kernel (default), 0 = single-role kernel
+    L.ub200_tc_set_warp_specialized(ws)       # 1 = producer/epilogue warp-specialised kernel, 0 = single-role kernel (default)
     try:
         _lib.check(L.ub200_gemm1_forward(backend, xd.data_ptr(), cd.data_ptr(), wd.data_ptr(), h1.data_ptr(), stats.data_ptr(), N, P,
                                          scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "gemm1_forward")
         torch.cuda.synchronize()
     finally:
-        L.ub200_tc_set_warp_specialized(1)
+        L.ub200_tc_set_warp_specialized(0)
     e = rel_l2(h1, ref)
     es = rel_l2(stats[..., 0], ref.sum(1))
     eq = rel_l2(stats[..., 1], (ref ** 2).sum(1))

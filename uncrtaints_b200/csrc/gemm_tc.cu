@@ -363,7 +363,8 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-specialised variant (default): warps 0-7 produce operand tiles (and thread 0 issues the MMAs), warps 8-15 run
+// Warp-specialised variant (optional, ub200_tc_set_warp_specialized(1); measured 3-10% SLOWER than the single-role kernel on
+// B200 at B=16 -- halving the producer warps costs more load parallelism than the overlap buys): warps 0-7 produce operand tiles (and thread 0 issues the MMAs), warps 8-15 run
 // the epilogue, so the TMEM -> HBM stores of tile t-1 overlap the HBM loads / conversion of tile t instead of
 // alternating with them.  Synchronisation: named barrier 1 (256 producer threads) before each MMA batch; mbarriers
 // free[slot] (tcgen05.commit -> producers), accfull[stage] (tcgen05.commit -> epilogue), accempty[stage] (8 epilogue
@@ -552,7 +553,7 @@ static int blocks_per_frame(int N, int tiles) {
     return g < 1 ? 1 : g;
 }
 
-static int g_warp_specialized = 1;      // tc_set_warp_specialized(): 1 = gemm_tc_ws_kernel (default), 0 = gemm_tc_kernel
+static int g_warp_specialized = 0;      // tc_set_warp_specialized(): 0 = gemm_tc_kernel (default; measured faster), 1 = gemm_tc_ws_kernel
 
 template <int K, int NOUT, class ALoad, class Epi>
 static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t st) {
