@@ -112,3 +112,53 @@ def test_ltae_fold_is_exact_in_fp64(golden_weights):
     score = score.masked_fill(pad.reshape(B, 1, T).repeat_interleave(1024, 0), -1e3)
     mine = torch.softmax(score, -1).reshape(B, 32, 32, 16, T).permute(3, 0, 4, 1, 2)
     assert float((mine - ref).abs().max()) < 1e-9
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model/src"), reason="/root/reference not present (GPU box)")
+def test_install_patches_reference_factory_and_loss():
+    """uncrtaints_b200.install() makes the reference's own factory (model_utils.get_generator, model_utils.py:85-108) and
+    loss factory (losses.get_loss, losses.py:14-32) build the B200 classes, with the reference's config namespace."""
+    import sys
+    import types
+    from unittest import mock
+    import argparse
+    sys.path.insert(0, "/root/reference/model")
+    cwd = os.getcwd()
+    stubs = {"fvcore": types.ModuleType("fvcore"), "fvcore.nn": types.ModuleType("fvcore.nn")}
+    stubs["fvcore.nn"].FlopCountAnalysis = mock.MagicMock()
+    stubs["fvcore.nn"].flop_count_table = mock.MagicMock()
+    saved = None
+    try:
+        with mock.patch.dict(sys.modules, stubs):
+            import uncrtaints_b200 as ub
+            from src import losses as ref_losses
+            from src.backbones import uncrtaints as ref_uncrtaints
+            saved = (ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss)     # restored below: other tests use the reference
+            ub.install(verbose=False)
+            from src import model_utils                                # model_utils chdirs into ./model if it exists
+            assert ref_uncrtaints.UNCRTAINTS is ub.UNCRTAINTS
+            assert ref_losses.MultiGaussianNLLLoss is ub.MultiGaussianNLLLoss
+            cfg = argparse.Namespace(model="uncrtaints", use_sar=True, encoder_widths=[128], decoder_widths=[128] * 5,
+                                     out_conv=[26], mean_nonLinearity=True, var_nonLinearity="softplus", agg_mode="att_group",
+                                     encoder_norm="group", decoder_norm="batch", n_head=16, d_model=256, d_k=4, pad_value=0,
+                                     padding_mode="reflect", positional_encoding=True, covmode="diag", scale_by=10.0,
+                                     separate_out=False, use_v=False, block_type="mbconv", pretrain=False, loss="MGNLL",
+                                     chunk_size=None)
+            net = model_utils.get_generator(cfg)
+            assert isinstance(net, ub.UNCRTAINTS) and (net.mean_idx, net.vars_idx) == (13, 26)
+            crit = ref_losses.get_loss(cfg)
+            p = torch.rand(1, 1, 13, 4, 4)
+            with pytest.raises(RuntimeError, match="CUDA"):           # our loss, reached through the reference's wrapper
+                ref_losses.calc_loss(crit, cfg, p, p, p + 1)
+            # weight_init of the reference dispatches on module types (weight_init.py:13-47) and must touch every tensor it would
+            from src.learning.weight_init import weight_init
+            before = {k: v.clone() for k, v in net.state_dict().items()}
+            torch.manual_seed(0)
+            net.apply(weight_init)
+            changed = [k for k, v in net.state_dict().items() if not torch.equal(v, before[k])]
+            assert "in_conv.conv.conv.0.weight" in changed and "out_block.4.conv.fn.8.weight" in changed
+            assert "temporal_encoder.inconv.bias" in changed and "temporal_encoder.attention_heads.Q" not in changed
+    finally:
+        os.chdir(cwd)
+        if saved is not None:
+            ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss = saved
