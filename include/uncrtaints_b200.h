@@ -113,6 +113,8 @@ int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc
 /* 0 (default): single-role tcgen05 GEMM kernel; 1: warp-specialised variant (producer warps / epilogue warps, TMA bulk
  * weight load) -- kept for experiments, measured slightly slower. */
 int ub200_tc_set_warp_specialized(int on);
+/* 0 (default): fused depthwise-conv backward kernel; 1: pointwise dh2 kernel + stencil kernel (6 instead of 4 tensor passes). */
+int ub200_dwconv_set_bwd_split(int on);
 
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
  * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,

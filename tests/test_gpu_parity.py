@@ -165,10 +165,23 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3])
+@pytest.mark.parametrize("backend", [0, 1, 3, 203])
 @pytest.mark.parametrize("groups,training", [(4, 1), (0, 1), (0, 0)])
 def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
     """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64)."""
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    split = backend >= 200                  # 203: backend 3 with the two-kernel (pointwise + stencil) depthwise backward
+    if split:
+        backend -= 200
+    L.ub200_dwconv_set_bwd_split(int(split))
+    try:
+        _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split)
+    finally:
+        L.ub200_dwconv_set_bwd_split(0)
+
+
+def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split):
     from uncrtaints_b200 import _lib
     L = _lib.lib()
     kind = "group" if groups else "batch"
@@ -210,7 +223,7 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
     _lib.check(L.ub200_mbconv_backward(xd.data_ptr(), ptab, dd.data_ptr(), gtab, N, H, W, groups, training, backend, dx.data_ptr(),
                                        ws.data_ptr(), nbytes, st), "mbconv_backward")
     torch.cuda.synchronize()
-    tag = f"mbconv[{kind},train={training},backend={backend}]"
+    tag = f"mbconv[{kind},train={training},backend={backend},split={int(split)}]"
     lines = [f"{tag} out rel_l2={rel_l2(out, _nhwc(ref.detach())):.3e}", f"{tag} dx rel_l2={rel_l2(dx, _nhwc(ref_dx)):.3e}"]
     errs = {}
     for k, gbuf in gdev.items():

@@ -273,6 +273,172 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
     }
 }
 
+// B3 fused (default): one kernel, 4 Hh of HBM traffic instead of 6.  512 threads (16 warps), 1 CTA per SM.
+// The raw du and h2 halo tiles of the NEXT 8-row tile arrive by cp.async (zero-filled outside the image) into the second
+// pair of shared-memory buffers while the current pair is turned into dh2 in place (SE-gate backward, gelu'(z2), Norm2
+// backward; forced to 0 outside the image) and consumed by the input-stationary stencil described above.
+struct DwFusedCoef {
+    float4 k2sg[DW_CC];   // scale2, shift2, gate, dpool/P
+    float4 b2[DW_CC];     // a2, b2, c2, -
+    float4 k1m1[DW_CC];   // scale1, shift1, mean1, rstd1
+    float4 w[9][DW_Q];    // depthwise taps [tap][channel quad]
+};
+
+__global__ void __launch_bounds__(512, 1)
+dwconv_bwd_fused_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
+                        const float* __restrict__ gate, const float* __restrict__ dmp, const Coef* __restrict__ coef2,
+                        const BCoef* __restrict__ bc2, const Coef* __restrict__ coef1, const MeanRstd* __restrict__ mr1,
+                        const float* __restrict__ wdw, float* __restrict__ dz1, double* bstats1, float* dwdw, int H, int W) {
+    extern __shared__ __align__(16) float smem[];
+    // buffers: [2 stages][du tile | h2 tile]
+    DwFusedCoef* cf = reinterpret_cast<DwFusedCoef*>(smem + 4 * DW_TILE_FLOATS);
+    constexpr int C = UB_HID;
+    constexpr int ROW = DW_HC * DW_CC;
+    constexpr int NITEM = DW_HR * DW_HC * DW_Q;
+    const int n = blockIdx.z, cbase = blockIdx.y * DW_CC, x0 = blockIdx.x * DW_TW;
+    const int tid = threadIdx.x;
+    const int cq = tid % DW_Q, col = (tid / DW_Q) % DW_TW, rh = tid / 256;     // channel quad, column, row half (4 rows)
+    const int c0 = cbase + cq * 4;
+    if (tid < DW_CC) {
+        const size_t ci = (size_t)n * C + cbase + tid;
+        const Coef a = coef2[ci], b = coef1[ci];
+        const BCoef bb = bc2[ci];
+        const MeanRstd m = mr1[ci];
+        cf->k2sg[tid] = make_float4(a.scale, a.shift, gate[ci], dmp[ci]);
+        cf->b2[tid] = make_float4(bb.a, bb.b, bb.c, 0.f);
+        cf->k1m1[tid] = make_float4(b.scale, b.shift, m.mean, m.rstd);
+    }
+    for (int e = tid; e < 9 * DW_CC; e += 512) {
+        const int j = e / DW_CC, ch = e % DW_CC;
+        reinterpret_cast<float*>(&cf->w[j][0])[ch] = wdw[(size_t)(cbase + ch) * 9 + j];
+    }
+    const size_t fbase = (size_t)n * H * W * C;
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    float4 gw[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) gw[j] = make_float4(0, 0, 0, 0);
+    const int qx = x0 + col;
+    const bool x_lo = (qx == 1), x_hi = (qx == W - 2);
+
+    auto fetch = [&](int y0, float* bufd, float* bufh) {
+        for (int e = tid; e < NITEM; e += 512) {
+            const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
+            const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
+            const bool inside = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+            const size_t off = fbase + ((size_t)(inside ? yy : 0) * W + (inside ? xx : 0)) * C + c0;
+            cp_async16(bufd + pix * DW_CC + cq * 4, du + off, inside);
+            cp_async16(bufh + pix * DW_CC + cq * 4, h2 + off, inside);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    fetch(0, smem, smem + DW_TILE_FLOATS);
+    for (int y0 = 0, it = 0; y0 < H; y0 += DW_TH, ++it) {
+        float* td = smem + (it & 1) * 2 * DW_TILE_FLOATS;      // du tile -> dh2 tile (in place)
+        const float* th = td + DW_TILE_FLOATS;                  // h2 tile
+        // h1 of this thread's column / row half, software-prefetched one row ahead
+        float4 h1next = ld4(h1 + fbase + ((size_t)(y0 + rh * 4) * W + qx) * C + c0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                        // tiles landed; everybody is done with the other stage
+        if (y0 + DW_TH < H) fetch(y0 + DW_TH, smem + ((it + 1) & 1) * 2 * DW_TILE_FLOATS, smem + ((it + 1) & 1) * 2 * DW_TILE_FLOATS + DW_TILE_FLOATS);
+        // ---- dh2 in place (e % 8 == cq): dz2 = (du*s + dpool/P) * gelu'(z2); dh2 = a2*dz2 + b2*h2 + c2; 0 outside the image ----
+        {
+            const float4 k2a = cf->k2sg[cq * 4 + 0], k2b = cf->k2sg[cq * 4 + 1], k2c = cf->k2sg[cq * 4 + 2], k2d = cf->k2sg[cq * 4 + 3];
+            const float4 b2a = cf->b2[cq * 4 + 0], b2b = cf->b2[cq * 4 + 1], b2c = cf->b2[cq * 4 + 2], b2d = cf->b2[cq * 4 + 3];
+            for (int e = tid; e < NITEM; e += 512) {
+                const int pix = e / DW_Q, ry = pix / DW_HC, rx = pix - ry * DW_HC;
+                const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
+                float* ptr = td + pix * DW_CC + cq * 4;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    const float4 d = ld4(ptr);
+                    const float4 hv = ld4(th + pix * DW_CC + cq * 4);
+                    float4 o;
+                    o.x = fmaf(b2a.x, fmaf(d.x, k2a.z, k2a.w) * gelu_grad_f(fmaf(hv.x, k2a.x, k2a.y)), fmaf(b2a.y, hv.x, b2a.z));
+                    o.y = fmaf(b2b.x, fmaf(d.y, k2b.z, k2b.w) * gelu_grad_f(fmaf(hv.y, k2b.x, k2b.y)), fmaf(b2b.y, hv.y, b2b.z));
+                    o.z = fmaf(b2c.x, fmaf(d.z, k2c.z, k2c.w) * gelu_grad_f(fmaf(hv.z, k2c.x, k2c.y)), fmaf(b2c.y, hv.z, b2c.z));
+                    o.w = fmaf(b2d.x, fmaf(d.w, k2d.z, k2d.w) * gelu_grad_f(fmaf(hv.w, k2d.x, k2d.y)), fmaf(b2d.y, hv.w, b2d.z));
+                    st4(ptr, o);
+                }   // else: already zero-filled by cp.async
+            }
+        }
+        __syncthreads();
+        // ---- input-stationary stencil: 4 rows of this thread's column ----
+        const float4 km0 = cf->k1m1[cq * 4 + 0], km1 = cf->k1m1[cq * 4 + 1], km2 = cf->k1m1[cq * 4 + 2], km3 = cf->k1m1[cq * 4 + 3];
+        const float* tcol = td + (col + 1) * DW_CC + cq * 4;
+#pragma unroll 1
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = rh * 4 + rr, qy = y0 + r;
+            const float4 hv = h1next;
+            if (rr + 1 < 4) h1next = ld4(h1 + fbase + ((size_t)(qy + 1) * W + qx) * C + c0);
+            float4 g, gp;
+            gelu_both(fmaf(hv.x, km0.x, km0.y), g.x, gp.x);
+            gelu_both(fmaf(hv.y, km1.x, km1.y), g.y, gp.y);
+            gelu_both(fmaf(hv.z, km2.x, km2.y), g.z, gp.z);
+            gelu_both(fmaf(hv.w, km3.x, km3.y), g.w, gp.w);
+            const float* tc = tcol + (r + 1) * ROW;
+            const bool y_lo = (qy == 1), y_hi = (qy == H - 2);
+            const bool border = y_lo | y_hi | x_lo | x_hi;
+            float4 o = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float4 d = ld4(tc + (1 - i) * ROW + (1 - j) * DW_CC);
+                    if (border) {
+                        const bool ya = (i == 0 && y_lo) || (i == 2 && y_hi);
+                        const bool xa = (j == 0 && x_lo) || (j == 2 && x_hi);
+                        if (ya) { const float4 e = ld4(tc + (i - 1) * ROW + (1 - j) * DW_CC); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+                        if (xa) { const float4 e = ld4(tc + (1 - i) * ROW + (j - 1) * DW_CC); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+                        if (ya && xa) { const float4 e = ld4(tc + (i - 1) * ROW + (j - 1) * DW_CC); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+                    }
+                    const float4 ww = cf->w[i * 3 + j][cq];
+                    o.x = fmaf(ww.x, d.x, o.x); o.y = fmaf(ww.y, d.y, o.y);
+                    o.z = fmaf(ww.z, d.z, o.z); o.w = fmaf(ww.w, d.w, o.w);
+                    float4& a = gw[i * 3 + j];
+                    a.x = fmaf(g.x, d.x, a.x); a.y = fmaf(g.y, d.y, a.y);
+                    a.z = fmaf(g.z, d.z, a.z); a.w = fmaf(g.w, d.w, a.w);
+                }
+            const float4 dz = make_float4(o.x * gp.x, o.y * gp.y, o.z * gp.z, o.w * gp.w);
+            st4(dz1 + fbase + ((size_t)qy * W + qx) * C + c0, dz);
+            s.x += dz.x; s.y += dz.y; s.z += dz.z; s.w += dz.w;
+            q.x = fmaf(dz.x, (hv.x - km0.z) * km0.w, q.x);
+            q.y = fmaf(dz.y, (hv.y - km1.z) * km1.w, q.y);
+            q.z = fmaf(dz.z, (hv.z - km2.z) * km2.w, q.z);
+            q.w = fmaf(dz.w, (hv.w - km3.z) * km3.w, q.w);
+        }
+    }
+    // statistics and weight gradient: reduce over the 64 (column, row-half) threads of each channel quad
+    __syncthreads();
+    {
+        float4* sa = reinterpret_cast<float4*>(smem);
+        float4* sb = sa + 512;
+        const int pt = tid / DW_Q;                       // 0..63
+        sa[pt * DW_Q + cq] = s;
+        sb[pt * DW_Q + cq] = q;
+        __syncthreads();
+        if (tid < 2 * DW_CC) {
+            const int which = tid / DW_CC, ch = tid % DW_CC;
+            const float* src = reinterpret_cast<const float*>(which ? sb : sa);
+            double t = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < 64; ++r) t += (double)src[r * DW_CC + ch];
+            atomicAdd(&bstats1[((size_t)n * C + cbase + ch) * 2 + which], t);
+        }
+        __syncthreads();
+        float* red = smem;  // [9][64 pt][32 ch] = 73.7 KB
+#pragma unroll
+        for (int j = 0; j < 9; ++j) st4(red + (j * 64 + pt) * DW_CC + cq * 4, gw[j]);
+        __syncthreads();
+        for (int e = tid; e < 9 * DW_CC; e += 512) {
+            const int j = e / DW_CC, ch = e % DW_CC;
+            float t = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 64; ++r) t += red[(j * 64 + r) * DW_CC + ch];
+            atomicAdd(&dwdw[(size_t)(cbase + ch) * 9 + j], t);
+        }
+    }
+}
+
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st) {
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
@@ -287,10 +453,25 @@ int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, floa
     return UB_OK;
 }
 
+static int g_dw_bwd_split = 0;     // dwconv_set_bwd_split(): 0 = fused kernel (default), 1 = pointwise dh2 kernel + stencil kernel
+int dwconv_set_bwd_split(int on) { g_dw_bwd_split = on ? 1 : 0; return UB_OK; }
+
 int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
                       const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
                       float* dwdw, int N, int H, int W, cudaStream_t st) {
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
+    if (!g_dw_bwd_split) {
+        constexpr size_t smem = (size_t)4 * DW_TILE_FLOATS * sizeof(float) + sizeof(DwFusedCoef);
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(dwconv_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+            attr_set = true;
+        }
+        dwconv_bwd_fused_kernel<<<dim3(W / DW_TW, UB_HID / DW_CC, N), 512, smem, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw,
+                                                                                     dz1, bstats1, dwdw, H, W);
+        UB_CHECK_LAUNCH();
+        return UB_OK;
+    }
     const int P = H * W;
     const int chunk = P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64);
     dh2_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(du, h2, gate, dmp, coef2, bc2, P, chunk);   // du <- dh2 in place

@@ -64,6 +64,8 @@ int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* 
                       const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
                       float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
 
+int dwconv_set_bwd_split(int on);
+
 // se.cu
 int launch_se_fwd(const double* pool_stats, const float* f1, const float* f2, float* save, float* gate, int N, int P,
                   cudaStream_t st);

@@ -331,6 +331,7 @@ unsigned long long ub200_launch_count(void) { return g_launch_count; }
 
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
 int ub200_tc_set_warp_specialized(int on) { return tc_set_warp_specialized(on); }
+int ub200_dwconv_set_bwd_split(int on) { return dwconv_set_bwd_split(on); }
 int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set_wgrad(desc_hi, desc_lbo, idesc); }
 
 // dW1[256][128] = sum_p dh1[p][o] * n0[p][k] with n0 = x*coef0 (x: [N*P][128]) and dh1 = a*dz1 + b*h1 + c ([N*P][256]):
