@@ -113,7 +113,8 @@ int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc
 /* 0 (default): single-role tcgen05 GEMM kernel; 1: warp-specialised variant (producer warps / epilogue warps, TMA bulk
  * weight load) -- kept for experiments, measured slightly slower. */
 int ub200_tc_set_warp_specialized(int on);
-/* 0 (default): fused depthwise-conv backward kernel; 1: pointwise dh2 kernel + stencil kernel (6 instead of 4 tensor passes). */
+/* 1 (default): pointwise dh2 kernel + stencil kernel (6 tensor passes, measured faster); 0: fused depthwise-conv backward
+ * kernel (4 tensor passes, kept for tuning). */
 int ub200_dwconv_set_bwd_split(int on);
 
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):

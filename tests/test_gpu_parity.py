@@ -171,14 +171,15 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
     """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64)."""
     from uncrtaints_b200 import _lib
     L = _lib.lib()
-    split = backend >= 200                  # 203: backend 3 with the two-kernel (pointwise + stencil) depthwise backward
-    if split:
+    fused = backend >= 200                  # 203: backend 3 with the fused (single-kernel) depthwise backward
+    if fused:
         backend -= 200
+    split = not fused
     L.ub200_dwconv_set_bwd_split(int(split))
     try:
         _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split)
     finally:
-        L.ub200_dwconv_set_bwd_split(0)
+        L.ub200_dwconv_set_bwd_split(1)
 
 
 def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split):

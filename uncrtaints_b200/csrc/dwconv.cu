@@ -273,7 +273,7 @@ dwconv_bwd_kernel(const float* __restrict__ dh2, const float* __restrict__ h1, c
     }
 }
 
-// B3 fused (default): one kernel, 4 Hh of HBM traffic instead of 6.  512 threads (16 warps), 1 CTA per SM.
+// B3 fused (optional, ub200_dwconv_set_bwd_split(0); currently slower than the two-kernel path): one kernel, 4 Hh of HBM traffic instead of 6.  512 threads (16 warps), 1 CTA per SM.
 // The raw du and h2 halo tiles of the NEXT 8-row tile arrive by cp.async (zero-filled outside the image) into the second
 // pair of shared-memory buffers while the current pair is turned into dh2 in place (SE-gate backward, gelu'(z2), Norm2
 // backward; forced to 0 outside the image) and consumed by the input-stationary stencil described above.
@@ -453,7 +453,8 @@ int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, floa
     return UB_OK;
 }
 
-static int g_dw_bwd_split = 0;     // dwconv_set_bwd_split(): 0 = fused kernel (default), 1 = pointwise dh2 kernel + stencil kernel
+static int g_dw_bwd_split = 1;     // dwconv_set_bwd_split(): 1 = pointwise dh2 kernel + stencil kernel (default; measured 13.9 ms vs
+                                   // 19.6 ms per step at B=16), 0 = fused kernel
 int dwconv_set_bwd_split(int on) { g_dw_bwd_split = on ? 1 : 0; return UB_OK; }
 
 int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
