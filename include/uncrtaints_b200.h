@@ -116,6 +116,9 @@ int ub200_tc_set_warp_specialized(int on);
 /* 1 (default): pointwise dh2 kernel + stencil kernel (6 tensor passes, measured faster); 0: fused depthwise-conv backward
  * kernel (4 tensor passes, kept for tuning). */
 int ub200_dwconv_set_bwd_split(int on);
+/* Depthwise 3x3 kernel family: bit 0 = row-streaming forward, bit 1 = row-streaming FUSED backward (both fed by 1-D TMA
+ * bulk copies of whole 1 KB-per-pixel image rows), bit 2 = packed FFMA2 arithmetic in them; 0 = cp.async tile kernels.  Default 7. */
+int ub200_dwconv_set_mode(int mode);
 
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
  * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,

@@ -176,18 +176,34 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
         backend -= 200
     split = not fused
     L.ub200_dwconv_set_bwd_split(int(split))
+    L.ub200_dwconv_set_mode(0)              # the cp.async tile kernels (the row-streaming default has its own test below)
     try:
         _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split)
     finally:
         L.ub200_dwconv_set_bwd_split(1)
+        L.ub200_dwconv_set_mode(7)
 
 
-def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split):
+@pytest.mark.parametrize("mode", [3, 7])
+@pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16))])
+def test_mbconv_block_row_streaming_dwconv(golden_weights, groups, training, shape, mode):
+    """Same block check with the row-streaming (TMA bulk copy) depthwise kernels: edge strips only (W=32), interior strips
+    and several row chunks (64x64), a 3-strip non-square frame, and a single-strip frame (W=16: both reflect columns)."""
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    L.ub200_dwconv_set_mode(mode)
+    try:
+        _mbconv_block_vs_oracle(golden_weights, groups, training, 3, True, shape, f",dwmode={mode}")
+    finally:
+        L.ub200_dwconv_set_mode(7)
+
+
+def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, shape=(3, 16, 32), extra_tag=""):
     from uncrtaints_b200 import _lib
     L = _lib.lib()
     kind = "group" if groups else "batch"
     pre = "in_block.0." if groups else "out_block.2."
-    N, H, W = 3, 16, 32
+    N, H, W = shape
     g = torch.Generator("cpu").manual_seed(21)
     x = torch.randn(N, 128, H, W, generator=g) * 1.5 + 0.3
     dout = torch.randn(N, 128, H, W, generator=g)
@@ -224,7 +240,7 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split):
     _lib.check(L.ub200_mbconv_backward(xd.data_ptr(), ptab, dd.data_ptr(), gtab, N, H, W, groups, training, backend, dx.data_ptr(),
                                        ws.data_ptr(), nbytes, st), "mbconv_backward")
     torch.cuda.synchronize()
-    tag = f"mbconv[{kind},train={training},backend={backend},split={int(split)}]"
+    tag = f"mbconv[{kind},train={training},backend={backend},split={int(split)}{extra_tag},{N}x{H}x{W}]"
     lines = [f"{tag} out rel_l2={rel_l2(out, _nhwc(ref.detach())):.3e}", f"{tag} dx rel_l2={rel_l2(dx, _nhwc(ref_dx)):.3e}"]
     errs = {}
     for k, gbuf in gdev.items():

@@ -65,6 +65,14 @@ int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* 
                       float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
 
 int dwconv_set_bwd_split(int on);
+int dwconv_set_mode(int mode);
+
+// dwconv_rows.cu (row-streaming TMA bulk-copy versions; the backward one is fused: du, h2, h1 -> dz1 in one pass)
+int launch_dwrows_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
+                      int f2, cudaStream_t st);
+int launch_dwrows_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
+                      const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
+                      float* dwdw, int N, int H, int W, int f2, cudaStream_t st);
 
 // se.cu
 int launch_se_fwd(const double* pool_stats, const float* f1, const float* f2, float* save, float* gate, int N, int P,

@@ -332,6 +332,7 @@ unsigned long long ub200_launch_count(void) { return g_launch_count; }
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
 int ub200_tc_set_warp_specialized(int on) { return tc_set_warp_specialized(on); }
 int ub200_dwconv_set_bwd_split(int on) { return dwconv_set_bwd_split(on); }
+int ub200_dwconv_set_mode(int mode) { return dwconv_set_mode(mode); }
 int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set_wgrad(desc_hi, desc_lbo, idesc); }
 
 // dW1[256][128] = sum_p dh1[p][o] * n0[p][k] with n0 = x*coef0 (x: [N*P][128]) and dh1 = a*dz1 + b*h1 + c ([N*P][256]):
@@ -587,7 +588,7 @@ static BlockCtx mb_ctx(const MbLayout& M, const void* const* p, void* const* g, 
 }
 int ub200_mbconv_forward(const float* x, const void* const* block_params, int N, int H, int W, int groups, int training,
                          float eps, float momentum, int gemm_backend, float* out, void* ws, size_t ws_bytes, void* stream) {
-    if (!x || !block_params || !out || !ws || N < 1 || H % 8 || W % 32) return UB_ERR_ARG;
+    if (!x || !block_params || !out || !ws || N < 1 || H % 8 || W % 16) return UB_ERR_ARG;
     MbLayout M;
     mb_layout(N, H, W, M);
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
