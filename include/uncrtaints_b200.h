@@ -119,6 +119,9 @@ int ub200_dwconv_set_bwd_split(int on);
 /* Depthwise 3x3 kernel family: bit 0 = row-streaming forward, bit 1 = row-streaming FUSED backward (both fed by 1-D TMA
  * bulk copies of whole 1 KB-per-pixel image rows), bit 2 = packed FFMA2 arithmetic in them; 0 = cp.async tile kernels.  Default 7. */
 int ub200_dwconv_set_mode(int mode);
+/* 1 (default): in_conv GroupNorm statistics and weight gradients from per-frame input moments + one gram pass over dX0;
+ * 0: the recompute passes (statistics pass + weight-gradient pass, each re-evaluating the 15->128 convolution). */
+int ub200_inconv_set_moments(int on);
 
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
  * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,
@@ -174,6 +177,15 @@ int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, s
 
 /* Second return value of the loss: diag_embed(max(var, eps)) -> [B][1][13][13][H][W] (losses.py:145,211). */
 int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int P, float eps, float* cov, void* stream);
+
+/* out_conv + head alone (uncrtaints.py:381,432-446; tests and the calibration sweep of BASELINE config #5):
+ *   dec [B][P][128] pixel-major decoder output, w [out_dim][128], bias [out_dim] -> out [B][out_dim][P] with
+ *   mean = scale_by*sigmoid(.) (or identity) on the first 13 planes and softplus(.)+var_eps on the rest.
+ * Backward: ddec [B][P][128] is overwritten, dw / db are ACCUMULATED into.  P must be a multiple of 128. */
+int ub200_head_forward(const float* dec, const float* w, const float* bias, float* out, int B, int out_dim, int P, float scale_by,
+                       int mean_sigmoid, float var_eps, void* stream);
+int ub200_head_backward(const float* grad_out, const float* out, const float* dec, const float* w, float* ddec, float* dw, float* db,
+                        int B, int out_dim, int P, float scale_by, int mean_sigmoid, float var_eps, void* stream);
 
 /* One MBConv block on pixel-major tensors (tests): x, out, dout, dx are [N][H*W][128].
  * block_params / block_grads: UB200_BLOCK_STRIDE pointers.  groups: 4 = GroupNorm(4), 0 = BatchNorm2d. */

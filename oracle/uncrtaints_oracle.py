@@ -379,6 +379,46 @@ def covariance(var: torch.Tensor, mode: str = "diag", eps: float = 1e-8) -> torc
 
 
 # --------------------------------------------------------------------------------------
+# calibration statistics of the validation loop (BASELINE config #5)
+# --------------------------------------------------------------------------------------
+def errvar_samplewise(target: torch.Tensor, pred: torch.Tensor, var: torch.Tensor) -> Dict[str, float]:
+    """Image-wise error / uncertainty statistics of img_metrics (model/src/learning/metrics.py:41-53): one sample
+    = one image; `target`, `pred`, `var` are that sample's [1,13,H,W] tensors after BaseModel.rescale
+    (base_model.py:103-112: means / scale_by, variances / scale_by^2)."""
+    error = target - pred
+    return {"error": float(error.nanmean()), "mean ae": float(error.abs().nanmean()),
+            "mean se": float(error.square().nanmean()), "mean var": float(var.nanmean())}
+
+
+def variance_from_covariance(cov: torch.Tensor) -> torch.Tensor:
+    """[B,1,13,13,H,W] covariance -> [B,1,13,H,W] variances (train_reconstruct.py:321-324)."""
+    return cov.diagonal(dim1=2, dim2=3).moveaxis(-1, 2)
+
+
+def compute_uce_auce(var, errors, n_samples: int, percent: int = 5, l2: bool = True):
+    """Uncertainty calibration errors of the validation loop (model/train_reconstruct.py:489-512, plotting omitted):
+    the per-sample variances are grouped into 100/percent equal-width bins between their min and max
+    (np.digitize against linspace(min, max, n_bins)[1:], :487); per bin the root-mean variance and the RMSE
+    (l2) or mean std / mean |error| are compared; UCE weights the bin discrepancies by the bin population
+    / n_samples, AUCE is their unweighted nan-mean."""
+    import numpy as np
+    n_bins = 100 // percent
+    var, errors = torch.Tensor(var), torch.Tensor(errors)
+
+    def metric(arg):
+        return torch.sqrt(torch.mean(arg ** 2)) if l2 else torch.mean(torch.abs(arg))
+    edges = np.linspace(float(var.min()), float(var.max()), num=n_bins)[1:]
+    var_idx = torch.Tensor(np.digitize(var, bins=edges))
+    bk_var, bk_err = torch.empty(n_bins), torch.empty(n_bins)
+    for b in range(n_bins):
+        bk_var[b] = metric(var[var_idx == b].sqrt())
+        bk_err[b] = metric(errors[var_idx == b])
+    calib = torch.abs(bk_err - bk_var)
+    weight = torch.histogram(var_idx, n_bins)[0] / n_samples
+    return float(torch.nansum(weight * calib)), float(torch.nanmean(calib))
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs + init (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------
 def synthetic_batch(b: int, t: int, h: int, w: int, cin: int = 15, scale_by: float = 10.0,

@@ -160,6 +160,54 @@ def test_golden_mgnll(mode):
         ub.MultiGaussianNLLLoss(mode=mode, chunk=None, reduction="bogus")(pred.detach(), targ, var.detach())
 
 
+@pytest.mark.parametrize("mode", ["diag", "iso"])
+def test_calibration_sweep(mode):
+    """BASELINE config #5: variance logits sweeping [-30, 30] through the CUDA head (ub200_head_forward/backward), the CUDA
+    MGNLL loss and its covariance output; loss, logit gradients, per-sample statistics and UCE/AUCE against the fixture
+    generated from the unmodified reference (tests/golden/make_calibration.py)."""
+    import uncrtaints_b200 as ub
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    c = load_npz("case_calibration.npz")
+    vc = 13 if mode == "diag" else 1
+    O_dim, scale_by, var_eps = 13 + vc, 10.0, 1e-3
+    lm, lv, y = (torch.from_numpy(c[k]) for k in ("lm", f"{mode}.lv", "y"))
+    S, _, H, W = lm.shape
+    P = H * W
+    g = torch.Generator("cpu").manual_seed(3)
+    dec = torch.randn(S, P, 128, generator=g)                       # decoder features: logits in the first O_dim channels
+    dec[:, :, :O_dim] = torch.cat([lm, lv], dim=1).reshape(S, O_dim, P).permute(0, 2, 1)
+    w = torch.zeros(O_dim, 128)
+    w[:, :O_dim] = torch.eye(O_dim)                                  # out_conv = selection of those channels, zero bias
+    dec, w, bias = dec.cuda().contiguous(), w.cuda(), torch.zeros(O_dim, device="cuda")
+    out = torch.empty(S, 1, O_dim, H, W, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.ub200_head_forward(dec.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), S, O_dim, P, scale_by, 1, var_eps, st),
+               "head_forward")
+    out.requires_grad_(True)
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=mode, chunk=None)
+    loss, cov = crit(out[:, :, :13], y.cuda(), out[:, :, 13:O_dim])       # non-contiguous slices, as base_model.py:82-83
+    loss.backward()
+    ddec, dw, db = torch.empty_like(dec), torch.zeros_like(w), torch.zeros_like(bias)
+    _lib.check(L.ub200_head_backward(out.grad.contiguous().data_ptr(), out.detach().data_ptr(), dec.data_ptr(), w.data_ptr(),
+                                     ddec.data_ptr(), dw.data_ptr(), db.data_ptr(), S, O_dim, P, scale_by, 1, var_eps, st), "head_backward")
+    torch.cuda.synchronize()
+    dlog = ddec[:, :, :O_dim].permute(0, 2, 1).reshape(S, O_dim, H, W).cpu()
+    e_loss = abs(loss.item() - float(c[f"{mode}.loss"])) / abs(float(c[f"{mode}.loss"]))
+    e_dlm, e_dlv = rel_l2(dlog[:, :13], torch.from_numpy(c[f"{mode}.dlm"])), rel_l2(dlog[:, 13:], torch.from_numpy(c[f"{mode}.dlv"]))
+    # validation-loop statistics (base_model.py:103-112 rescale; train_reconstruct.py:316-329; metrics.py:41-53)
+    var5 = O.variance_from_covariance(cov.detach().cpu().double() / scale_by ** 2)
+    fake, real = out.detach().cpu().double()[:, :, :13] / scale_by, y.double() / scale_by
+    stats = [O.errvar_samplewise(real[s], fake[s], var5[s]) for s in range(S)]
+    mvar, err = np.array([s["mean var"] for s in stats]), np.array([s["error"] for s in stats])
+    uce, auce = O.compute_uce_auce(mvar, err, S)
+    report("parity_report.txt", [f"calibration[{mode}] loss rel={e_loss:.2e} dlm={e_dlm:.2e} dlv={e_dlv:.2e} uce={uce:.6f} "
+                                 f"(ref {float(c[f'{mode}.uce']):.6f}) auce={auce:.6f} (ref {float(c[f'{mode}.auce']):.6f})"])
+    assert e_loss <= 1e-4 and e_dlm <= TOL and e_dlv <= TOL
+    assert np.allclose(mvar, c[f"{mode}.mean_var"], rtol=1e-4) and np.allclose(err, c[f"{mode}.error"], rtol=1e-4, atol=1e-6)
+    assert abs(uce - float(c[f"{mode}.uce"])) <= 1e-4 and abs(auce - float(c[f"{mode}.auce"])) <= 1e-4
+
+
 def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     n, c, h, w = t.shape
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
@@ -412,3 +460,39 @@ def test_wgrad1_op_vs_fp64(backend):
     e = rel_l2(dw1, ref)
     report("parity_report.txt", [f"wgrad1 op backend={backend}: rel_l2={e:.3e}"])
     assert e < 5e-5
+
+
+def test_flat_bucket_in_place_gradients(golden_weights):
+    """FlatGradAllReduce flags the parameters so that the backward accumulates straight into the flat buffer (the C ABI adds
+    into its gradient slots): same gradients as the plain autograd route, two accumulating backwards add up, zero_() resets."""
+    import uncrtaints_b200 as ub
+    x, y, d = O.synthetic_batch(1, 2, 64, 64, seed=5)
+    keep = O.dropout_keep_mask(16, 1, 2, 64, 64, seed=6).to(torch.uint8)
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None)
+
+    def run(net):
+        net._injected_keep_mask = keep
+        out = net(x.cuda(), batch_positions=d.cuda())
+        loss, _ = crit(out[:, :, :13], y.cuda(), out[:, :, 13:26])
+        loss.backward()
+        return loss.item()
+    ref = make_net(golden_weights, "diag").train()
+    run(ref)
+    want = {k: p.grad.clone() for k, p in ref.named_parameters()}
+    net = make_net(golden_weights, "diag").train()
+    bucket = ub.FlatGradAllReduce(net.parameters())
+    ptrs = [p.grad.data_ptr() for p in net.parameters()]
+    run(net)
+    assert [p.grad.data_ptr() for p in net.parameters()] == ptrs, "gradients must stay views of the flat buffer"
+    scale = max(float(g.norm()) for g in want.values())
+    for k, p in net.named_parameters():
+        assert float((p.grad - want[k]).norm()) <= 1e-4 * float(want[k].norm()) + 1e-8 * scale, k   # (analytically-zero grads are noise)
+    once = bucket.flat.clone()
+    # BatchNorm running statistics moved after the first step; reload them so that the second backward is the same function
+    net.load_state_dict({k: v.clone() for k, v in ref.state_dict().items()}, strict=True)
+    ref2 = make_net(golden_weights, "diag").train()
+    net.load_state_dict(ref2.state_dict(), strict=True)
+    run(net)                                               # accumulates on top
+    assert float((bucket.flat - 2 * once).norm()) <= 1e-4 * float((2 * once).norm())
+    bucket.zero_()
+    assert float(bucket.flat.abs().max()) == 0.0

@@ -140,3 +140,31 @@ def test_fused_mode_equals_elementary(golden_weights):
     for k in a_g:
         if not is_zero_grad_param(k):
             assert rel_l2(b_g[k], a_g[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("mode", ["diag", "iso"])
+def test_oracle_calibration_sweep_matches_golden(mode):
+    """BASELINE config #5: head nonlinearities + MGNLL + rescale + per-sample statistics + UCE/AUCE of the oracle against the
+    fixture generated from the unmodified reference (tests/golden/make_calibration.py)."""
+    c = load_npz("case_calibration.npz")
+    S = c["lm"].shape[0]
+    vc = 13 if mode == "diag" else 1
+    cfg = O.OracleConfig(covmode=mode)
+    lm = torch.from_numpy(c["lm"]).double().requires_grad_(True)
+    lv = torch.from_numpy(c[f"{mode}.lv"]).double().requires_grad_(True)
+    y = torch.from_numpy(c["y"]).double()
+    out = O.head(torch.cat([lm, lv], dim=1), cfg)
+    loss = O.mgnll(out[:, :, :13], y, out[:, :, 13:13 + vc], mode)
+    loss.backward()
+    assert abs(loss.item() - float(c[f"{mode}.loss"])) / abs(float(c[f"{mode}.loss"])) < 1e-9
+    assert rel_l2(lm.grad, torch.from_numpy(c[f"{mode}.dlm"])) < 1e-6
+    assert rel_l2(lv.grad, torch.from_numpy(c[f"{mode}.dlv"])) < 1e-6
+    var5 = O.variance_from_covariance(O.covariance(out[:, :, 13:13 + vc].detach(), mode) / cfg.scale_by ** 2)
+    stats = [O.errvar_samplewise(y[s] / cfg.scale_by, out[s, :, :13].detach() / cfg.scale_by, var5[s]) for s in range(S)]
+    mvar, err = [s["mean var"] for s in stats], [s["error"] for s in stats]
+    assert np.allclose(mvar, c[f"{mode}.mean_var"], rtol=1e-9) and np.allclose(err, c[f"{mode}.error"], rtol=1e-9, atol=1e-12)
+    uce, auce = O.compute_uce_auce(mvar, err, S)
+    assert abs(uce - float(c[f"{mode}.uce"])) < 1e-6 and abs(auce - float(c[f"{mode}.auce"])) < 1e-6
+    # the restated metric also agrees with the reference's on its own golden inputs
+    uce2, auce2 = O.compute_uce_auce(c[f"{mode}.mean_var"], c[f"{mode}.error"], S)
+    assert abs(uce2 - float(c[f"{mode}.uce"])) < 1e-7 and abs(auce2 - float(c[f"{mode}.auce"])) < 1e-7

@@ -198,11 +198,25 @@ class _UncrtaintsFunction(torch.autograd.Function):
         L = _lib.lib()
         x, out, *tensors = ctx.saved_tensors
         grad_out = grad_out.contiguous()
-        sizes = [t.numel() for t in tensors]
+        # The C ABI ACCUMULATES into every gradient slot.  Parameters whose .grad is owned by a FlatGradAllReduce (flagged
+        # _ub200_grad_in_place) receive their gradient directly in that buffer and autograd gets None for them: no zeroed
+        # staging buffer and no per-parameter add_ kernel.  Everything else goes through a zero-initialised flat buffer.
+        def in_place(t):
+            if not (t.is_leaf and getattr(t, "_ub200_grad_in_place", False)):
+                return False
+            g = t.grad
+            return (g is not None and g.is_cuda and g.dtype == torch.float32
+                    and g.is_contiguous() and g.shape == t.shape)
+        direct = [in_place(t) for t in tensors]
+        sizes = [0 if d else t.numel() for t, d in zip(tensors, direct)]
         flat = torch.zeros(sum(sizes), dtype=torch.float32, device=x.device)
         gtable = [0] * len(ctx.table)
         views, off = [], 0
-        for slot, t, n in zip(ctx.slots, tensors, sizes):
+        for slot, t, n, d in zip(ctx.slots, tensors, sizes, direct):
+            if d:
+                gtable[slot] = t.grad.data_ptr()
+                views.append(None)
+                continue
             v = flat[off:off + n]
             gtable[slot] = v.data_ptr()
             views.append(v.view_as(t))
@@ -370,9 +384,10 @@ class UNCRTAINTS(nn.Module):
             km = km.to(device=x.device, dtype=torch.uint8).contiguous()
         out = _UncrtaintsFunction.apply(self, x, km, need_grad, *tensors)
         if self.training:
-            for m in self.modules():
-                if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
-                    m.num_batches_tracked += 1
+            counters = [m.num_batches_tracked for m in self.modules()
+                        if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None]
+            if counters:
+                torch._foreach_add_(counters, 1)          # one launch for all BatchNorm step counters
         if not self.covmode:
             return out[:, :, :self.mean_idx]
         return out

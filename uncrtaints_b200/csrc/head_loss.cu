@@ -169,41 +169,44 @@ __global__ void __launch_bounds__(256) mgnll_fwd_kernel(const float* __restrict_
                                                          float* __restrict__ dpred /* [B][13][P] or null */,
                                                          float* __restrict__ dvar /* [B][var_ch][P] or null */, double* acc,
                                                          int* neg_flag, int B, int P, float eps) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (sample, pixel): every reduction of the closed form is a plain global sum, so the batch needs no loop
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     float logdet = 0.f, maha_sum = 0.f;
     bool neg = false;
     if (p < P) {
         const float inv_p = 1.0f / (float)P, inv_bp = 1.0f / ((float)B * (float)P);
-        for (int b = 0; b < B; ++b) {
-            float e[UB_S2], iv[UB_S2];
-            float maha = 0.f;
+        float e[UB_S2], iv[UB_S2], vr[UB_S2];
+#pragma unroll
+        for (int c = 0; c < UB_S2; ++c) {         // all loads first: 27 (diag) / 15 (iso) independent requests in flight
+            if (var_ch != 1 || c == 0) vr[c] = var[b * var_sb + (size_t)c * P + p];
+            e[c] = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
+        }
+        float maha = 0.f;
+#pragma unroll
+        for (int c = 0; c < UB_S2; ++c) {
+            const float vraw = var_ch == 1 ? vr[0] : vr[c];
+            neg |= (vraw < 0.f);
+            const float v = fmaxf(vraw, eps);
+            iv[c] = 1.0f / v;
+            logdet += logf(v);
+            maha = fmaf(e[c] * e[c], iv[c], maha);
+        }
+        const bool isn = maha != maha;
+        float m = isn ? 0.f : maha;                       // nan_to_num
+        m = fminf(m, 3.4028234663852886e38f);             // +inf -> float max
+        const bool live = !isn && m >= 1e-9f && maha <= 3.4028234663852886e38f;   // clamp(min=1e-9) / inf: no gradient
+        maha_sum = fmaxf(m, 1e-9f);
+        if (dpred) {
+            float dv_iso = 0.f;
 #pragma unroll
             for (int c = 0; c < UB_S2; ++c) {
-                const float vr = var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p];
-                neg |= (vr < 0.f);
-                const float v = fmaxf(vr, eps);
-                e[c] = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
-                iv[c] = 1.0f / v;
-                logdet += logf(v);
-                maha = fmaf(e[c] * e[c], iv[c], maha);
+                const float gm = live ? e[c] * iv[c] * inv_bp : 0.f;
+                dpred[((size_t)b * UB_S2 + c) * P + p] = gm;
+                const float gv = 0.5f * iv[c] * inv_p - (live ? 0.5f * e[c] * e[c] * iv[c] * iv[c] * inv_bp : 0.f);
+                if (var_ch == 1) dv_iso += gv;
+                else dvar[((size_t)b * UB_S2 + c) * P + p] = gv;
             }
-            const bool isn = maha != maha;
-            float m = isn ? 0.f : maha;                       // nan_to_num
-            m = fminf(m, 3.4028234663852886e38f);             // +inf -> float max
-            const bool live = !isn && m >= 1e-9f && maha <= 3.4028234663852886e38f;   // clamp(min=1e-9) / inf: no gradient
-            maha_sum += fmaxf(m, 1e-9f);
-            if (dpred) {
-                float dv_iso = 0.f;
-#pragma unroll
-                for (int c = 0; c < UB_S2; ++c) {
-                    const float gm = live ? e[c] * iv[c] * inv_bp : 0.f;
-                    dpred[((size_t)b * UB_S2 + c) * P + p] = gm;
-                    const float gv = 0.5f * iv[c] * inv_p - (live ? 0.5f * e[c] * e[c] * iv[c] * iv[c] * inv_bp : 0.f);
-                    if (var_ch == 1) dv_iso += gv;
-                    else dvar[((size_t)b * UB_S2 + c) * P + p] = gv;
-                }
-                if (var_ch == 1) dvar[(size_t)b * P + p] = dv_iso;
-            }
+            if (var_ch == 1) dvar[(size_t)b * P + p] = dv_iso;
         }
     }
     double l = warp_sum_d((double)logdet), m = warp_sum_d((double)maha_sum);
@@ -278,7 +281,7 @@ int launch_mgnll(const float* pred, long long pred_sb, const float* target, long
                  int P, float eps, cudaStream_t st) {
     if (cudaMemsetAsync(acc, 0, 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
     if (cudaMemsetAsync(neg_flag, 0, sizeof(int), st) != cudaSuccess) return UB_ERR_CUDA;
-    mgnll_fwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, dpred, dvar, acc,
+    mgnll_fwd_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, dpred, dvar, acc,
                                                       neg_flag, B, P, eps);
     UB_CHECK_LAUNCH();
     mgnll_finalize_kernel<<<1, 1, 0, st>>>(acc, loss, B, P);

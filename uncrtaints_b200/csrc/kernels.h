@@ -90,6 +90,15 @@ int launch_inconv_bwd_stats(const float* x, const float* w, const float* b, cons
 int launch_inconv_bwd_wgrad(const float* x, const float* w, const float* b, const Coef* coef, const MeanRstd* mr,
                             const BCoef* bc, const float* dx0, float* dw, float* db, int N, int Cin, int P, cudaStream_t st);
 
+size_t inconv_moments_bytes(int N);
+size_t inconv_gram_bytes(int N);
+int launch_inconv_stats_moments(const float* x, const float* w, const float* b, double* mom, double* stats, int* notpad,
+                                float pad_value, int N, int Cin, int P, cudaStream_t st);
+int launch_inconv_bwd_gram(const float* x, const float* x0, const float* dx0, const float* w, const float* b, const MeanRstd* mr,
+                           double* gacc, double* bstats, int N, int Cin, int P, cudaStream_t st);
+int launch_inconv_bwd_finish(const double* gacc, const double* mom, const float* w, const float* b, const BCoef* bc, float* dw,
+                             float* db, int N, int Cin, int P, cudaStream_t st);
+
 // temporal.cu
 int launch_maxpool_fwd(const float* x, float* pooled, int* idx, int N, int H, int W, cudaStream_t st);
 int launch_maxpool_bwd(const float* dpooled, const int* idx, float* denc, int N, int HW, cudaStream_t st);

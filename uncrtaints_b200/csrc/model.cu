@@ -81,13 +81,15 @@ struct Layout {
     int Ne, B, P, nblk, Nmax;
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
-    size_t bstats_in, bc_in;
+    size_t bstats_in, bc_in, mom_in, gram_in;
     size_t gA, gB, dn0, du, dz1, partial, dwup, dattn, dpooled;
     BlockWs blk[1 + 16];
     size_t total;
 };
 
 constexpr int MAX_PARTS = 148;
+// 1 (default): in_conv statistics / weight gradients through input moments and one gram pass (inconv.cu); 0: recompute passes
+static int g_inconv_moments = 1;
 
 static void block_fwd_stats(Bump& b, BlockWs& w, int N) {
     w.stats0 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
@@ -144,10 +146,12 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     L.fwd_zero_begin = b.off;
     L.notpad = b.take((size_t)L.Ne * sizeof(int));
     L.stats_c0 = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
+    L.mom_in = b.take(inconv_moments_bytes(L.Ne));
     for (int i = 0; i < L.nblk; ++i) block_fwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
     L.fwd_zero_end = b.off;
     L.bwd_zero_begin = b.off;
     L.bstats_in = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
+    L.gram_in = b.take(inconv_gram_bytes(L.Ne));
     for (int i = 0; i < L.nblk; ++i) block_bwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
     L.bwd_zero_end = b.off;
     L.coef_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(Coef));
@@ -333,6 +337,7 @@ int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { re
 int ub200_tc_set_warp_specialized(int on) { return tc_set_warp_specialized(on); }
 int ub200_dwconv_set_bwd_split(int on) { return dwconv_set_bwd_split(on); }
 int ub200_dwconv_set_mode(int mode) { return dwconv_set_mode(mode); }
+int ub200_inconv_set_moments(int on) { g_inconv_moments = on ? 1 : 0; return UB_OK; }
 int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set_wgrad(desc_hi, desc_lbo, idesc); }
 
 // dW1[256][128] = sum_p dh1[p][o] * n0[p][k] with n0 = x*coef0 (x: [N*P][128]) and dh1 = a*dz1 + b*h1 + c ([N*P][256]):
@@ -458,8 +463,12 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
     if (cudaMemsetAsync(at<char>(ws, L.fwd_zero_begin), 0, L.fwd_zero_end - L.fwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
 
     // in_conv: conv1x1 + norm + ReLU (+ pad-mask test), NCHW -> pixel-major
-    UB_PROF(KID_INCONV, st, launch_inconv_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.stats_c0),
-                               at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
+    if (g_inconv_moments)
+        UB_PROF(KID_INCONV, st, launch_inconv_stats_moments(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.mom_in),
+                                   at<double>(ws, L.stats_c0), at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
+    else
+        UB_PROF(KID_INCONV, st, launch_inconv_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.stats_c0),
+                                   at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize(at<double>(ws, L.stats_c0), pf(params, UB200_P_IN_NORM_W), pf(params, UB200_P_IN_NORM_B),
                                 pfm(params, UB200_P_IN_NORM_RM), pfm(params, UB200_P_IN_NORM_RV), at<Coef>(ws, L.coef_in),
                                 at<MeanRstd>(ws, L.mr_in), L.Ne, UB_WIDTH, d->enc_groups, (double)P, d->norm_eps, d->bn_momentum,
@@ -526,12 +535,21 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
     // in_conv backward (no input gradient)
-    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+    if (g_inconv_moments)
+        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, at<float>(ws, L.x0), gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
+                                   at<MeanRstd>(ws, L.mr_in), at<double>(ws, L.gram_in), at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
+    else
+        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
                                    at<MeanRstd>(ws, L.mr_in), gA, at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize_bwd(at<double>(ws, L.bstats_in), pf(params, UB200_P_IN_NORM_W), at<MeanRstd>(ws, L.mr_in),
                                     at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_NORM_W), gf(grads, UB200_P_IN_NORM_B), L.Ne,
                                     UB_WIDTH, d->enc_groups, (double)P, d->training, st));
-    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_wgrad(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
+    if (g_inconv_moments)
+        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_finish(at<double>(ws, L.gram_in), at<double>(ws, L.mom_in), pf(params, UB200_P_IN_W),
+                                   pf(params, UB200_P_IN_B), at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_W), gf(grads, UB200_P_IN_B),
+                                   L.Ne, d->C_in, P, st));
+    else
+        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_wgrad(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
                                    at<MeanRstd>(ws, L.mr_in), at<BCoef>(ws, L.bc_in), gA, gf(grads, UB200_P_IN_W),
                                    gf(grads, UB200_P_IN_B), L.Ne, d->C_in, P, st));
     return UB_OK;
@@ -555,6 +573,19 @@ int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, s
 int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int P, float eps, float* cov, void* stream) {
     if (!var || !cov || (var_ch != 1 && var_ch != UB_S2)) return UB_ERR_ARG;
     return launch_covariance(var, var_sb, var_ch, cov, B, P, eps, static_cast<cudaStream_t>(stream));
+}
+
+// ---- standalone out_conv + head (tests, calibration sweep) ----
+int ub200_head_forward(const float* dec, const float* w, const float* bias, float* out, int B, int out_dim, int P, float scale_by,
+                       int mean_sigmoid, float var_eps, void* stream) {
+    if (!dec || !w || !bias || !out || B < 1) return UB_ERR_ARG;
+    return launch_head_fwd(dec, w, bias, out, B, out_dim, P, scale_by, mean_sigmoid, var_eps, static_cast<cudaStream_t>(stream));
+}
+int ub200_head_backward(const float* grad_out, const float* out, const float* dec, const float* w, float* ddec, float* dw, float* db,
+                        int B, int out_dim, int P, float scale_by, int mean_sigmoid, float var_eps, void* stream) {
+    if (!grad_out || !out || !dec || !w || !ddec || !dw || !db || B < 1) return UB_ERR_ARG;
+    return launch_head_bwd(grad_out, out, dec, w, ddec, dw, db, B, out_dim, P, scale_by, mean_sigmoid, var_eps, num_sms(),
+                           static_cast<cudaStream_t>(stream));
 }
 
 // ---- standalone MBConv block (tests) -------------------------------------------------------------------

@@ -23,7 +23,9 @@ def shard_batch(n: int, rank: int, world: int) -> slice:
 
 
 class FlatGradAllReduce:
-    """Owns a flat fp32 gradient buffer; ``p.grad`` of every parameter is a view into it."""
+    """Owns a flat fp32 gradient buffer; ``p.grad`` of every parameter is a view into it.  The parameters are flagged so
+    that ``uncrtaints_b200.UNCRTAINTS``'s backward accumulates straight into these views (the C ABI adds into its gradient
+    slots) instead of handing autograd one temporary per parameter; call ``zero_()`` before every backward."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -35,6 +37,7 @@ class FlatGradAllReduce:
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
+            p._ub200_grad_in_place = True
             off += n
 
     def zero_(self) -> None:
