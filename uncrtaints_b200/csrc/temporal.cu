@@ -228,64 +228,106 @@ struct AggArgs {
     int B, T, H, W;
 };
 
-// attention weight of (head h, frame b,t) at pixels (y, x0..x0+3)
-__device__ __forceinline__ void agg_weights(const AggArgs& a, int h, int b, int t, int y, int x0, float (&w)[4]) {
-    const float* src = a.attn + (((size_t)h * a.B + b) * a.T + t) * (UB_LOW * UB_LOW);
-    const float inv_sy = (float)UB_LOW / (float)a.H, inv_sx = (float)UB_LOW / (float)a.W;
+// Per-CTA shared state of the aggregation kernels.  A CTA owns ONE image row y of one sample, so the vertical half of the
+// bilinear upsampling is the same for all its pixels: the row-interpolated attention v[h][t][X] (x notpad[b,t]) of all 16
+// heads is staged once in shared memory (head stride padded by one float: the 16 heads of a warp hit 16 different banks)
+// and every pixel only needs the horizontal lerp of two shared-memory values -- the kernels no longer issue 16-way
+// scattered global loads per tap (ncu r01: 15 sectors per request, 56 % long-scoreboard stalls).
+template <int T>
+struct AggRow {
+    float v[UB_HEADS][T * UB_LOW + 1];
+};
+template <int T>
+__device__ __forceinline__ void agg_stage_row(const AggArgs& a, int b, int y, AggRow<T>& S) {
+    const float inv_sy = (float)UB_LOW / (float)a.H;
     int y0, y1; float ly;
     bilinear_tap(y, inv_sy, UB_LOW, y0, y1, ly);
-    const float scale = a.notpad[b * a.T + t] ? 1.0f : 0.0f;
-    const size_t lin = ((((size_t)h * a.B + b) * a.T + t) * a.H + y) * a.W + x0;
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    const bool philox = a.drop_p > 0.f && a.keep_mask == nullptr;
-    if (philox) {
-        const unsigned long long blk = (lin >> 2) + a.offset;
-        rnd = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u),
-                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+    for (int i = threadIdx.x; i < UB_HEADS * T * UB_LOW; i += blockDim.x) {
+        const int h = i / (T * UB_LOW), r = i % (T * UB_LOW), t = r / UB_LOW, X = r % UB_LOW;
+        const float* src = a.attn + (((size_t)h * a.B + b) * T + t) * (UB_LOW * UB_LOW);
+        const float vv = src[y0 * UB_LOW + X] * (1.f - ly) + src[y1 * UB_LOW + X] * ly;
+        S.v[h][r] = a.notpad[b * T + t] ? vv : 0.f;
     }
-    const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+}
+// dropout factors keep/(1-p) of head h (= lane/2) for frames t = 0..T-1 at the 4 pixels of group (y, x0): one Philox call
+// covers the 4 pixels of one (h, t); the two lanes of a head split the frames (even lane: even t) and swap 4-bit masks.
+template <int T>
+__device__ __forceinline__ void agg_dropout(const AggArgs& a, int h, int b, int y, int x0, int lane, float (&k)[T][4]) {
+    if (!(a.drop_p > 0.f)) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int xa, xb; float lx;
-        bilinear_tap(x0 + i, inv_sx, UB_LOW, xa, xb, lx);
-        const float top = src[y0 * UB_LOW + xa] * (1.f - lx) + src[y0 * UB_LOW + xb] * lx;
-        const float bot = src[y1 * UB_LOW + xa] * (1.f - lx) + src[y1 * UB_LOW + xb] * lx;
-        float v = top * (1.f - ly) + bot * ly;
-        if (a.drop_p > 0.f) {
-            float keep;
-            if (philox) keep = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f)) >= a.drop_p ? 1.f : 0.f;
-            else keep = a.keep_mask[lin + i] ? 1.f : 0.f;
-            v = v * keep / (1.f - a.drop_p);
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) k[t][i] = 1.f;
+        return;
+    }
+    const float inv_keep = 1.f / (1.f - a.drop_p);
+    uint32_t mine[(T + 1) / 2];
+#pragma unroll
+    for (int kk = 0; kk < (T + 1) / 2; ++kk) {
+        const int t = 2 * kk + (lane & 1);
+        uint32_t m = 0;
+        if (t < T) {
+            const size_t lin = ((((size_t)h * a.B + b) * T + t) * a.H + y) * a.W + x0;
+            if (a.keep_mask) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m |= (a.keep_mask[lin + i] ? 1u : 0u) << i;
+            } else {
+                const unsigned long long blk = (lin >> 2) + a.offset;
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u),
+                                                make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m |= (((float)(bits[i] >> 8) * (1.0f / 16777216.0f)) >= a.drop_p ? 1u : 0u) << i;
+            }
         }
-        w[i] = v * scale;
+        mine[kk] = m;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine[t >> 1], 1);
+        const uint32_t m = ((lane & 1) == (t & 1)) ? mine[t >> 1] : other;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) k[t][i] = ((m >> i) & 1u) ? inv_keep : 0.f;
     }
 }
 
+// forward: out[b,p,c] = sum_t w[h(c),b,t,p] * x[b,t,p,c].  grid (H, B), 256 threads; warp = groups of 4 pixels of the row,
+// lane = 4 channels (head = lane / 2).  All T x 4 activation loads of a group are issued before the first FMA.
+template <int T>
 __global__ void __launch_bounds__(256) aggregate_fwd_kernel(AggArgs a, const float* __restrict__ x /* [B*T][P][128] */,
-                                                             float* __restrict__ out /* [B][P][128] */, double* out_stats,
-                                                             int groups_per_block) {
+                                                             float* __restrict__ out /* [B][P][128] */, double* out_stats) {
     constexpr int C = UB_WIDTH;
+    __shared__ AggRow<T> S;
     __shared__ __align__(16) float smem[2 * 8 * C];
-    const int b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
+    const int y = blockIdx.x, b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
     const int P = a.H * a.W;
+    agg_stage_row<T>(a, b, y, S);
+    __syncthreads();
+    const float inv_sx = (float)UB_LOW / (float)a.W;
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-    const int g0 = blockIdx.x * groups_per_block;
-    for (int g = g0 + warp; g < g0 + groups_per_block && g * 4 < P; g += 8) {
-        const int p = g * 4, y = p / a.W, x0 = p % a.W;
+    for (int x0 = warp * 4; x0 < a.W; x0 += 32) {
+        const int p = y * a.W + x0;
+        float4 v[T][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[t][i] = ld4_stream(x + (((size_t)(b * T + t)) * P + p + i) * C + lane * 4);
+        float k[T][4];
+        agg_dropout<T>(a, h, b, y, x0, lane, k);
+        int xa[4], xb[4]; float lx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bilinear_tap(x0 + i, inv_sx, UB_LOW, xa[i], xb[i], lx[i]);
         float4 acc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i] = make_float4(0, 0, 0, 0);
-        for (int t = 0; t < a.T; ++t) {
-            float w[4];
-            agg_weights(a, h, b, t, y, x0, w);
-            const float* xr = x + (((size_t)(b * a.T + t)) * P + p) * C + lane * 4;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 v = ld4_stream(xr + (size_t)i * C);
-                acc[i].x = fmaf(w[i], v.x, acc[i].x); acc[i].y = fmaf(w[i], v.y, acc[i].y);
-                acc[i].z = fmaf(w[i], v.z, acc[i].z); acc[i].w = fmaf(w[i], v.w, acc[i].w);
+                const float w = (S.v[h][t * UB_LOW + xa[i]] * (1.f - lx[i]) + S.v[h][t * UB_LOW + xb[i]] * lx[i]) * k[t][i];
+                acc[i].x = fmaf(w, v[t][i].x, acc[i].x); acc[i].y = fmaf(w, v[t][i].y, acc[i].y);
+                acc[i].z = fmaf(w, v[t][i].z, acc[i].z); acc[i].w = fmaf(w, v[t][i].w, acc[i].w);
             }
-        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             st4(out + ((size_t)b * P + p + i) * C + lane * 4, acc[i]);
@@ -307,48 +349,47 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(AggArgs a, const flo
     }
 }
 
-// backward A: dEnc[b,t,p,c] = w[h,b,t,p] * dAgg[b,p,c];  dwup[h,b,t,p] = d(upsampled attention)
+// backward A: dEnc[b,t,p,c] = w[h,b,t,p] * dAgg[b,p,c];  dwup[h,b,t,p] = d(upsampled attention) = keep/(1-p) * notpad * <dAgg, x>_head
+template <int T>
 __global__ void __launch_bounds__(256) aggregate_bwd_kernel(AggArgs a, const float* __restrict__ x, const float* __restrict__ dagg,
-                                                             float* __restrict__ denc, float* __restrict__ dwup /* [16][B][T][P] */,
-                                                             int groups_per_block) {
+                                                             float* __restrict__ denc, float* __restrict__ dwup /* [16][B][T][P] */) {
     constexpr int C = UB_WIDTH;
-    const int b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
+    __shared__ AggRow<T> S;
+    const int y = blockIdx.x, b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
     const int P = a.H * a.W;
-    const int g0 = blockIdx.x * groups_per_block;
-    for (int g = g0 + warp; g < g0 + groups_per_block && g * 4 < P; g += 8) {
-        const int p = g * 4, y = p / a.W, x0 = p % a.W;
-        float4 d[4];
+    agg_stage_row<T>(a, b, y, S);
+    __syncthreads();
+    const float inv_sx = (float)UB_LOW / (float)a.W;
+    for (int x0 = warp * 4; x0 < a.W; x0 += 32) {
+        const int p = y * a.W + x0;
+        float4 d[4], v[T][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = ld4_stream(dagg + ((size_t)b * P + p + i) * C + lane * 4);
-        for (int t = 0; t < a.T; ++t) {
-            float w[4], one[4];
-            agg_weights(a, h, b, t, y, x0, w);
-            // d(weight)/d(upsampled attention) = keep/(1-p) * notpad: evaluate the same chain on attn == 1
-            const size_t fr = ((size_t)(b * a.T + t)) * P + p;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[t][i] = ld4_stream(x + (((size_t)(b * T + t)) * P + p + i) * C + lane * 4);
+        float k[T][4];
+        agg_dropout<T>(a, h, b, y, x0, lane, k);
+        int xa[4], xb[4]; float lx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bilinear_tap(x0 + i, inv_sx, UB_LOW, xa[i], xb[i], lx[i]);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const size_t fr = ((size_t)(b * T + t)) * P + p;
+            const float np = a.notpad[b * T + t] ? 1.f : 0.f;
             float dots[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 v = ld4_stream(x + (fr + i) * C + lane * 4);
-                st4(denc + (fr + i) * C + lane * 4, make_float4(w[i] * d[i].x, w[i] * d[i].y, w[i] * d[i].z, w[i] * d[i].w));
-                float dot = d[i].x * v.x + d[i].y * v.y + d[i].z * v.z + d[i].w * v.w;
+                const float w = (S.v[h][t * UB_LOW + xa[i]] * (1.f - lx[i]) + S.v[h][t * UB_LOW + xb[i]] * lx[i]) * k[t][i];
+                st4(denc + (fr + i) * C + lane * 4, make_float4(w * d[i].x, w * d[i].y, w * d[i].z, w * d[i].w));
+                float dot = d[i].x * v[t][i].x + d[i].y * v[t][i].y + d[i].z * v[t][i].z + d[i].w * v[t][i].w;
                 dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                dots[i] = dot;
+                dots[i] = dot * k[t][i] * np;
             }
             if ((lane & 1) == 0) {
-                const float scale = a.notpad[b * a.T + t] ? 1.0f : 0.0f;
-                const size_t lin = ((((size_t)h * a.B + b) * a.T + t) * a.H + y) * a.W + x0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float k = scale;
-                    if (a.drop_p > 0.f) {
-                        float keep;
-                        if (a.keep_mask) keep = a.keep_mask[lin + i] ? 1.f : 0.f;
-                        else keep = dropout_keep(a.seed, a.offset, lin + i, a.drop_p);
-                        k = k * keep / (1.f - a.drop_p);
-                    }
-                    one[i] = k;
-                }
-                st4(dwup + lin, make_float4(dots[0] * one[0], dots[1] * one[1], dots[2] * one[2], dots[3] * one[3]));
+                const size_t lin = ((((size_t)h * a.B + b) * T + t) * a.H + y) * a.W + x0;
+                st4(dwup + lin, make_float4(dots[0], dots[1], dots[2], dots[3]));
             }
         }
     }
@@ -440,20 +481,18 @@ static AggArgs make_agg(const float* attn, const int* notpad, const unsigned cha
 int launch_aggregate_fwd(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
                          unsigned long long offset, float drop_p, const float* x, float* out, double* out_stats, int B,
                          int T, int H, int W, cudaStream_t st) {
-    if (W % 4) return UB_ERR_ARG;
-    const int groups = H * W / 4, gpb = 128;
-    aggregate_fwd_kernel<<<dim3((groups + gpb - 1) / gpb, B), 256, 0, st>>>(
-        make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W), x, out, out_stats, gpb);
+    if (W % 32) return UB_ERR_ARG;
+    const AggArgs a = make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W);
+    UB_DISPATCH_T(T, (aggregate_fwd_kernel<TT><<<dim3(H, B), 256, 0, st>>>(a, x, out, out_stats)));
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
 int launch_aggregate_bwd(const float* attn, const int* notpad, const unsigned char* keep_mask, unsigned long long seed,
                          unsigned long long offset, float drop_p, const float* x, const float* dagg, float* denc,
                          float* dwup, float* dattn, int B, int T, int H, int W, cudaStream_t st) {
-    if (W % 4) return UB_ERR_ARG;
-    const int groups = H * W / 4, gpb = 128;
-    aggregate_bwd_kernel<<<dim3((groups + gpb - 1) / gpb, B), 256, 0, st>>>(
-        make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W), x, dagg, denc, dwup, gpb);
+    if (W % 32) return UB_ERR_ARG;
+    const AggArgs a = make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W);
+    UB_DISPATCH_T(T, (aggregate_bwd_kernel<TT><<<dim3(H, B), 256, 0, st>>>(a, x, dagg, denc, dwup)));
     UB_CHECK_LAUNCH();
     const int cells = UB_HEADS * B * T * UB_LOW * UB_LOW;
     upsample_adjoint_kernel<<<(cells + 255) / 256, 256, 0, st>>>(dwup, dattn, H, W, cells);
