@@ -117,7 +117,8 @@ int ub200_tc_set_warp_specialized(int on);
  * kernel (4 tensor passes, kept for tuning). */
 int ub200_dwconv_set_bwd_split(int on);
 /* Depthwise 3x3 kernel family: bit 0 = row-streaming forward, bit 1 = row-streaming FUSED backward (both fed by 1-D TMA
- * bulk copies of whole 1 KB-per-pixel image rows), bit 2 = packed FFMA2 arithmetic in them; 0 = cp.async tile kernels.  Default 7. */
+ * bulk copies of whole 1 KB-per-pixel image rows), bit 2 = packed FFMA2 stencil arithmetic, bit 3 = packed f32x2 GELU in them, bit 5 = 512-thread channel-pair form of the
+ * backward kernel; 0 = cp.async tile kernels.  Default 47. */
 int ub200_dwconv_set_mode(int mode);
 /* 1 (default): in_conv GroupNorm statistics and weight gradients from per-frame input moments + one gram pass over dX0;
  * 0: the recompute passes (statistics pass + weight-gradient pass, each re-evaluating the 15->128 convolution). */

@@ -97,7 +97,7 @@ def main():
         else:
             diff = " | diff vs first: " + " ".join(f"{k}={rel(v, base[k]):.1e}" for k, v in snap.items())
         print(f"[block N={N} {H}x{W} groups={a.groups}] mode={mode} ms: " + " ".join(line) + diff, flush=True)
-    L.ub200_dwconv_set_mode(7)
+    L.ub200_dwconv_set_mode(47)
 
 
 if __name__ == "__main__":

@@ -229,10 +229,10 @@ def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
         _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split)
     finally:
         L.ub200_dwconv_set_bwd_split(1)
-        L.ub200_dwconv_set_mode(7)
+        L.ub200_dwconv_set_mode(47)
 
 
-@pytest.mark.parametrize("mode", [3, 7])
+@pytest.mark.parametrize("mode", [3, 7, 15, 47])
 @pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16))])
 def test_mbconv_block_row_streaming_dwconv(golden_weights, groups, training, shape, mode):
     """Same block check with the row-streaming (TMA bulk copy) depthwise kernels: edge strips only (W=32), interior strips
@@ -243,7 +243,7 @@ def test_mbconv_block_row_streaming_dwconv(golden_weights, groups, training, sha
     try:
         _mbconv_block_vs_oracle(golden_weights, groups, training, 3, True, shape, f",dwmode={mode}")
     finally:
-        L.ub200_dwconv_set_mode(7)
+        L.ub200_dwconv_set_mode(47)
 
 
 def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, shape=(3, 16, 32), extra_tag=""):

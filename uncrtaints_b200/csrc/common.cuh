@@ -70,6 +70,50 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& gp) {
     g = x * cdf;
     gp = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
+// Packed (f32x2) form of the same formula for two values: the polynomial, the products and the final FMAs are FFMA2 /
+// FMUL2 (sm_100 `fma.rn.f32x2` / `mul.rn.f32x2`), the two MUFU ops per value stay scalar: 21 issue slots per PAIR instead
+// of 19 per value.  FFMA2 has the same FMA/clk as FFMA on B200 (measured, scripts/microbench/gelu_bench.cu), so this only
+// pays in issue-bound kernels.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+template <bool WANT_G, bool WANT_GP>
+__device__ __forceinline__ void gelu_pair(float x0, float x1, float& g0, float& g1, float& p0, float& p1) {
+    const float t0 = fast_rcp(fmaf(0.23164189f, fabsf(x0), 1.0f)), t1 = fast_rcp(fmaf(0.23164189f, fabsf(x1), 1.0f));
+    const f32x2_t t = pack2(t0, t1), x = pack2(x0, x1);
+    // 0.5 * (a1..a5) of Abramowitz-Stegun 7.1.26: q = 0.5 * erfc(|x| / sqrt(2))
+    f32x2_t poly = fma2(t, pack2(0.5307027145f, 0.5307027145f), pack2(-0.7265760135f, -0.7265760135f));
+    poly = fma2(t, poly, pack2(0.7107068705f, 0.7107068705f));
+    poly = fma2(t, poly, pack2(-0.142248368f, -0.142248368f));
+    poly = fma2(t, poly, pack2(0.127414796f, 0.127414796f));
+    float a0, a1;
+    unpack2(mul2(mul2(x, pack2(-0.72134752f, -0.72134752f)), x), a0, a1);
+    const f32x2_t e = pack2(fast_ex2(a0), fast_ex2(a1));                       // exp(-x^2 / 2)
+    float q0, q1;
+    unpack2(mul2(mul2(t, poly), e), q0, q1);
+    const f32x2_t cdf = pack2(x0 >= 0.f ? 1.0f - q0 : q0, x1 >= 0.f ? 1.0f - q1 : q1);
+    if (WANT_G) unpack2(mul2(x, cdf), g0, g1);
+    if (WANT_GP) unpack2(fma2(mul2(x, pack2(0.39894228040143267794f, 0.39894228040143267794f)), e, cdf), p0, p1);
+}
+// float4 front ends: v = x * scale + shift first (packed as well)
+__device__ __forceinline__ void gelu_both4_packed(const float4 z, float4& g, float4& gp) {
+    gelu_pair<true, true>(z.x, z.y, g.x, g.y, gp.x, gp.y);
+    gelu_pair<true, true>(z.z, z.w, g.z, g.w, gp.z, gp.w);
+}
+__device__ __forceinline__ float4 gelu4_packed(const float4 z) {
+    float4 g; float d0, d1;
+    gelu_pair<true, false>(z.x, z.y, g.x, g.y, d0, d1);
+    gelu_pair<true, false>(z.z, z.w, g.z, g.w, d0, d1);
+    return g;
+}
+__device__ __forceinline__ float4 gelu_grad4_packed(const float4 z) {
+    float4 gp; float d0, d1;
+    gelu_pair<false, true>(z.x, z.y, d0, d1, gp.x, gp.y);
+    gelu_pair<false, true>(z.z, z.w, d0, d1, gp.z, gp.w);
+    return gp;
+}
 __device__ __forceinline__ float gelu_f(float x) { float g, gp; gelu_both(x, g, gp); return g; }
 __device__ __forceinline__ float gelu_grad_f(float x) { float g, gp; gelu_both(x, g, gp); return gp; }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }

@@ -440,14 +440,15 @@ dwconv_bwd_fused_kernel(const float* __restrict__ du, const float* __restrict__ 
 }
 
 // dwconv_set_mode(): bit 0 = row-streaming forward (dwconv_rows.cu), bit 1 = row-streaming fused backward,
-// bit 2 = packed FFMA2 arithmetic in those kernels; 0 = the tile kernels of this file.  Default 7: measured at B=16,
+// bit 2 = packed FFMA2 arithmetic in those kernels, bit 3 = packed f32x2 GELU, bit 5 = 512-thread channel-pair backward;
+// 0 = the tile kernels of this file.  Default 47 (packed GELU: another 3-4 %, channel-pair backward: another 2 %): measured at B=16,
 // 256x256 forward 4.44 -> 3.38 ms, backward 14.0 -> 8.1 ms per step against the tile kernels.
-static int g_dw_mode = 7;
+static int g_dw_mode = 47;
 int dwconv_set_mode(int mode) { g_dw_mode = mode; return UB_OK; }
 
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st) {
-    if (g_dw_mode & 1) return launch_dwrows_fwd(h1, coef1, wdw, h2, stats2, N, H, W, (g_dw_mode >> 2) & 1, st);
+    if (g_dw_mode & 1) return launch_dwrows_fwd(h1, coef1, wdw, h2, stats2, N, H, W, (g_dw_mode >> 2) & 15, st);
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)2 * DW_TILE_FLOATS * sizeof(float);
     static bool attr_set = false;
@@ -468,7 +469,7 @@ int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* 
                       const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
                       float* dwdw, int N, int H, int W, cudaStream_t st) {
     if (g_dw_mode & 2)
-        return launch_dwrows_bwd(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, N, H, W, (g_dw_mode >> 2) & 1, st);
+        return launch_dwrows_bwd(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, N, H, W, (g_dw_mode >> 2) & 15, st);
     if (W % DW_TW != 0 || H % DW_TH != 0) return UB_ERR_ARG;
     if (!g_dw_bwd_split) {
         constexpr size_t smem = (size_t)4 * DW_TILE_FLOATS * sizeof(float) + sizeof(DwFusedCoef);

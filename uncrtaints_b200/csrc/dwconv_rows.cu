@@ -97,7 +97,7 @@ __device__ __forceinline__ void reduce_sq(float4 ssum, float4 qsum, double* stat
 // K2:  h2 = DW3x3_reflect(gelu(h1 * scale1 + shift1)),  stats2 += column (sum, sumsq) of h2
 // grid (W/16, H/R, N), 256 threads, 2 CTAs / SM (92 KB ring each)
 // ------------------------------------------------------------------------------------------------------------------
-template <bool F2>
+template <bool F2, bool PG>
 __global__ void __launch_bounds__(256, 2)
 dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, const float* __restrict__ wdw,
                   float* __restrict__ h2, double* stats2, int H, int W, int R) {
@@ -153,11 +153,10 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
             if (px < RWH) {
                 float* ptr = d + px * RC + q * 4;
                 const float4 v = ld4(ptr);
+                const float4 z = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
                 float4 g;
-                g.x = gelu_f(fmaf(v.x, sc.x, sh.x));
-                g.y = gelu_f(fmaf(v.y, sc.y, sh.y));
-                g.z = gelu_f(fmaf(v.z, sc.z, sh.z));
-                g.w = gelu_f(fmaf(v.w, sc.w, sh.w));
+                if constexpr (PG) g = gelu4_packed(z);
+                else g = make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w));
                 st4(ptr, g);
             }
         }
@@ -199,7 +198,7 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
 //            dz1 = dg1 * gelu'(z1);  dWdw[c][tap] += sum_p g1[p] * D[tap][p];  bstats1 += (sum dz1, sum dz1 * h1_hat)
 // grid (W/16, H/R, N), 256 threads, 1 CTA / SM (200 KB of rings)
 // ------------------------------------------------------------------------------------------------------------------
-template <bool F2>
+template <bool F2, bool PG>
 __global__ void __launch_bounds__(256, 1)
 dwrows_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
                   const float* __restrict__ gate, const float* __restrict__ dmp, const Coef* __restrict__ coef2,
@@ -299,10 +298,14 @@ dwrows_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
                     if (row_in && x >= 0 && x < W) {
                         const float4 dv = ld4(d + px * RC + q * 4);
                         const float4 hv = ld4(hh + px * RC + q * 4);
-                        o.x = fmaf(b0.x, fmaf(dv.x, k0.z, k0.w) * gelu_grad_f(fmaf(hv.x, k0.x, k0.y)), fmaf(b0.y, hv.x, b0.z));
-                        o.y = fmaf(b1.x, fmaf(dv.y, k1.z, k1.w) * gelu_grad_f(fmaf(hv.y, k1.x, k1.y)), fmaf(b1.y, hv.y, b1.z));
-                        o.z = fmaf(b2.x, fmaf(dv.z, k2.z, k2.w) * gelu_grad_f(fmaf(hv.z, k2.x, k2.y)), fmaf(b2.y, hv.z, b2.z));
-                        o.w = fmaf(b3.x, fmaf(dv.w, k3.z, k3.w) * gelu_grad_f(fmaf(hv.w, k3.x, k3.y)), fmaf(b3.y, hv.w, b3.z));
+                        const float4 z = make_float4(fmaf(hv.x, k0.x, k0.y), fmaf(hv.y, k1.x, k1.y), fmaf(hv.z, k2.x, k2.y), fmaf(hv.w, k3.x, k3.y));
+                        float4 gp;
+                        if constexpr (PG) gp = gelu_grad4_packed(z);
+                        else gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
+                        o.x = fmaf(b0.x, fmaf(dv.x, k0.z, k0.w) * gp.x, fmaf(b0.y, hv.x, b0.z));
+                        o.y = fmaf(b1.x, fmaf(dv.y, k1.z, k1.w) * gp.y, fmaf(b1.y, hv.y, b1.z));
+                        o.z = fmaf(b2.x, fmaf(dv.z, k2.z, k2.w) * gp.z, fmaf(b2.y, hv.z, b2.z));
+                        o.w = fmaf(b3.x, fmaf(dv.w, k3.z, k3.w) * gp.w, fmaf(b3.y, hv.w, b3.z));
                     }
                     st4(d + px * RC + q * 4, o);
                 }
@@ -327,10 +330,12 @@ dwrows_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4 hv = ld4(hp + j * RC);
-            gelu_both(fmaf(hv.x, sc1.x, sh1.x), g[j].x, gp[j].x);
-            gelu_both(fmaf(hv.y, sc1.y, sh1.y), g[j].y, gp[j].y);
-            gelu_both(fmaf(hv.z, sc1.z, sh1.z), g[j].z, gp[j].z);
-            gelu_both(fmaf(hv.w, sc1.w, sh1.w), g[j].w, gp[j].w);
+            const float4 z = make_float4(fmaf(hv.x, sc1.x, sh1.x), fmaf(hv.y, sc1.y, sh1.y), fmaf(hv.z, sc1.z, sh1.z), fmaf(hv.w, sc1.w, sh1.w));
+            if constexpr (PG) gelu_both4_packed(z, g[j], gp[j]);
+            else {
+                gelu_both(z.x, g[j].x, gp[j].x); gelu_both(z.y, g[j].y, gp[j].y);
+                gelu_both(z.z, g[j].z, gp[j].z); gelu_both(z.w, g[j].w, gp[j].w);
+            }
             o[j] = make_float4(0, 0, 0, 0);
         }
         // regular readers: tap (it, jj) of input pixel (yc, x) is read by output (yc - (it-1), x - (jj-1))
@@ -405,6 +410,230 @@ dwrows_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, co
     }
 }
 
+// (A warp-specialised form -- 8 stencil warps at 200 registers + 8 transform warps at 56 via setmaxnreg, mbarrier hand-off
+// per row instead of the CTA barrier -- was built and measured at 2.0 ms against 0.96 ms for this kernel at N=16: with the
+// 5-slot ring only one row can be in flight behind the three the stencil holds, and the lean transform warps lose their
+// ILP.  It was removed)
+
+// ------------------------------------------------------------------------------------------------------------------
+// B3 fused, 512-thread form: same tiles, rings, barriers and arithmetic as dwrows_bwd_kernel, but a thread owns a channel
+// PAIR (one f32x2 lane pair) instead of a quad.  Per-thread state halves (9 taps + 9 dW accumulators + coefficients:
+// 48 registers instead of 96), the kernel fits 128 registers, and 16 warps (4 per scheduler) are resident instead of 8:
+// the row loop is latency-bound (ncu r01: 45 % issue utilisation with 2 warps per scheduler), not throughput-bound.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RP = RC / 2;     // channel pairs
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void fma2v(float2& acc, const float2 a, const float2 b) {
+    unpack2(fma2(pack2(a.x, a.y), pack2(b.x, b.y), pack2(acc.x, acc.y)), acc.x, acc.y);
+}
+
+template <bool PG>
+__global__ void __launch_bounds__(512, 1)
+dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
+                   const float* __restrict__ gate, const float* __restrict__ dmp, const Coef* __restrict__ coef2,
+                   const BCoef* __restrict__ bc2, const Coef* __restrict__ coef1, const MeanRstd* __restrict__ mr1,
+                   const float* __restrict__ wdw, float* __restrict__ dz1, double* bstats1, float* dwdw, int H, int W, int R) {
+    extern __shared__ __align__(128) float smem[];
+    float* sD = smem;
+    float* sH2 = sD + ND * ROWF;
+    float* sH1 = sH2 + NH2 * ROWF;
+    float4* sK2 = reinterpret_cast<float4*>(sH1 + NH1 * ROWC);   // [2][128] scale2, shift2, gate, dpool/P   (channel 2p+c at [c][p])
+    float4* sB2 = sK2 + RC;                                        // [2][128] a2, b2, c2, -
+    const uint32_t barD = s32(sB2 + RC), barH2 = barD + ND * 8, barH1 = barH2 + NH2 * 8;
+    const int tid = threadIdx.x, p = tid & (RP - 1), s = tid >> 7;
+    const int n = blockIdx.z, x0 = blockIdx.x * RW, ybase = blockIdx.y * R;
+    const size_t fbase = (size_t)n * H * W * RC;
+    if (tid < RC) {
+        const size_t ci = (size_t)n * RC + tid;
+        const Coef a = coef2[ci];
+        const BCoef bb = bc2[ci];
+        const int slot = (tid & 1) * RP + (tid >> 1);
+        sK2[slot] = make_float4(a.scale, a.shift, gate[ci], dmp[ci]);
+        sB2[slot] = make_float4(bb.a, bb.b, bb.c, 0.f);
+    }
+    float2 wr[9], sc1, sh1, mu1, rs1;
+    {
+        const size_t c0 = (size_t)n * RC + p * 2;
+        const Coef ka = coef1[c0], kb = coef1[c0 + 1];
+        const MeanRstd ma = mr1[c0], mb = mr1[c0 + 1];
+        sc1 = make_float2(ka.scale, kb.scale); sh1 = make_float2(ka.shift, kb.shift);
+        mu1 = make_float2(ma.mean, mb.mean); rs1 = make_float2(ma.rstd, mb.rstd);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) wr[j] = make_float2(wdw[(size_t)(p * 2) * 9 + j], wdw[(size_t)(p * 2 + 1) * 9 + j]);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < ND + NH2 + NH1; ++i) mbar_init(barD + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int xs = max(x0 - 1, 0), xe = min(x0 + RW + 1, W);
+    const uint32_t rowbytes = (uint32_t)(xe - xs) * RC * 4;
+    const int dstoff = (xs - (x0 - 1)) * RC;
+    const int NIT = R + 2;
+    auto issue_dh = [&](int i) {
+        const int y = ybase - 1 + i;
+        const uint32_t bd = barD + (i % ND) * 8, bh = barH2 + (i % NH2) * 8;
+        if (y >= 0 && y < H) {
+            const size_t g = fbase + ((size_t)y * W + xs) * RC;
+            mbar_expect_tx(bd, rowbytes);
+            bulk_g2s(s32(sD + (i % ND) * ROWF + dstoff), du + g, rowbytes, bd);
+            mbar_expect_tx(bh, rowbytes);
+            bulk_g2s(s32(sH2 + (i % NH2) * ROWF + dstoff), h2 + g, rowbytes, bh);
+        } else {
+            mbar_arrive(bd);
+            mbar_arrive(bh);
+        }
+    };
+    auto issue_h1 = [&](int c) {
+        const uint32_t b = barH1 + (c % NH1) * 8;
+        mbar_expect_tx(b, ROWC * 4);
+        bulk_g2s(s32(sH1 + (c % NH1) * ROWC), h1 + fbase + ((size_t)(ybase + c) * W + x0) * RC, ROWC * 4, b);
+    };
+    if (tid == 0) { issue_dh(0); issue_dh(1); }
+    float2 gw[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) gw[j] = make_float2(0, 0);
+    float2 ssum = make_float2(0, 0), qsum = make_float2(0, 0);
+    const int xbase = x0 + 4 * s;
+    const bool colb = (xbase <= 1 && 1 < xbase + 4) || (xbase <= W - 2 && W - 2 < xbase + 4);
+    const int woff = (4 * s) * RC + p * 2;
+
+    for (int i = 0; i < NIT; ++i) {
+        {   // ---- du row -> dh2 row in place (pixel px = s + 4k, channel pair p); 0 outside the image ----
+            const int y = ybase - 1 + i;
+            const bool row_in = (y >= 0 && y < H);
+            float* d = sD + (i % ND) * ROWF;
+            const float* hh = sH2 + (i % NH2) * ROWF;
+            mbar_wait(barD + (i % ND) * 8, (uint32_t)(i / ND) & 1u);
+            mbar_wait(barH2 + (i % NH2) * 8, (uint32_t)(i / NH2) & 1u);
+            const float4 k0 = sK2[p], k1 = sK2[RP + p];
+            const float4 b0 = sB2[p], b1 = sB2[RP + p];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int px = s + 4 * k;
+                if (px < RWH) {
+                    const int x = x0 - 1 + px;
+                    float2 o = make_float2(0, 0);
+                    if (row_in && x >= 0 && x < W) {
+                        const float2 dv = ld2(d + px * RC + p * 2);
+                        const float2 hv = ld2(hh + px * RC + p * 2);
+                        const float z0 = fmaf(hv.x, k0.x, k0.y), z1 = fmaf(hv.y, k1.x, k1.y);
+                        float gp0, gp1;
+                        if constexpr (PG) { float u0, u1; gelu_pair<false, true>(z0, z1, u0, u1, gp0, gp1); }
+                        else { gp0 = gelu_grad_f(z0); gp1 = gelu_grad_f(z1); }
+                        o.x = fmaf(b0.x, fmaf(dv.x, k0.z, k0.w) * gp0, fmaf(b0.y, hv.x, b0.z));
+                        o.y = fmaf(b1.x, fmaf(dv.y, k1.z, k1.w) * gp1, fmaf(b1.y, hv.y, b1.z));
+                    }
+                    st2(d + px * RC + p * 2, o);
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            if (i + 2 < NIT) issue_dh(i + 2);
+            if (i < R) issue_h1(i);
+        }
+        if (i < 2) continue;
+        // ---- input-stationary stencil for image row yc: 4 pixels x 1 channel pair per thread ----
+        const int c = i - 2, yc = ybase + c;
+        const float* rp0 = sD + ((i - 2) % ND) * ROWF + woff;
+        const float* rp1 = sD + ((i - 1) % ND) * ROWF + woff;
+        const float* rp2 = sD + (i % ND) * ROWF + woff;
+        mbar_wait(barH1 + (c % NH1) * 8, (uint32_t)(c / NH1) & 1u);
+        const float* hp = sH1 + (c % NH1) * ROWC + woff;
+        float2 g[4], gp[4], o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 hv = ld2(hp + j * RC);
+            const float z0 = fmaf(hv.x, sc1.x, sh1.x), z1 = fmaf(hv.y, sc1.y, sh1.y);
+            if constexpr (PG) gelu_pair<true, true>(z0, z1, g[j].x, g[j].y, gp[j].x, gp[j].y);
+            else { gelu_both(z0, g[j].x, gp[j].x); gelu_both(z1, g[j].y, gp[j].y); }
+            o[j] = make_float2(0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float* rp = r == 0 ? rp0 : (r == 1 ? rp1 : rp2);
+            const int it = 2 - r;
+            float2 win[6];
+#pragma unroll
+            for (int wc = 0; wc < 6; ++wc) win[wc] = ld2(rp + wc * RC);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    fma2v(o[j], wr[it * 3 + jj], win[j + 2 - jj]);
+                    fma2v(gw[it * 3 + jj], g[j], win[j + 2 - jj]);
+                }
+        }
+        const bool y_lo = (yc == 1), y_hi = (yc == H - 2);
+        if (y_lo | y_hi | colb) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool x_lo = (xbase + j == 1), x_hi = (xbase + j == W - 2);
+                if (y_lo | y_hi | x_lo | x_hi) {
+#pragma unroll
+                    for (int it = 0; it < 3; ++it)
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj) {
+                            const bool ya = (it == 0 && y_lo) || (it == 2 && y_hi);
+                            const bool xa = (jj == 0 && x_lo) || (jj == 2 && x_hi);
+                            if (ya | xa) {
+                                const float* ra = it == 0 ? rp0 : (it == 1 ? rp1 : rp2);
+                                const float* rb = it == 0 ? rp2 : (it == 1 ? rp1 : rp0);
+                                float2 e = make_float2(0, 0);
+                                if (ya) { const float2 tt = ld2(ra + (j + 2 - jj) * RC); e.x += tt.x; e.y += tt.y; }
+                                if (xa) { const float2 tt = ld2(rb + (j + jj) * RC); e.x += tt.x; e.y += tt.y; }
+                                if (ya && xa) { const float2 tt = ld2(ra + (j + jj) * RC); e.x += tt.x; e.y += tt.y; }
+                                fma2v(o[j], wr[it * 3 + jj], e);
+                                fma2v(gw[it * 3 + jj], g[j], e);
+                            }
+                        }
+                }
+            }
+        }
+        float* op = dz1 + fbase + ((size_t)yc * W + xbase) * RC + p * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 dz = make_float2(o[j].x * gp[j].x, o[j].y * gp[j].y);
+            st2(op + j * RC, dz);
+            const float2 hv = ld2(hp + j * RC);
+            ssum.x += dz.x; ssum.y += dz.y;
+            qsum.x = fmaf(dz.x, (hv.x - mu1.x) * rs1.x, qsum.x);
+            qsum.y = fmaf(dz.y, (hv.y - mu1.y) * rs1.y, qsum.y);
+        }
+    }
+    __syncthreads();
+    {   // statistics: sum over the 4 column groups of every channel
+        float2* red = reinterpret_cast<float2*>(sD);
+        red[s * RP + p] = ssum;
+        red[4 * RP + s * RP + p] = qsum;
+        __syncthreads();
+        if (tid < RC) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) {
+                t0 += (double)sD[ss * RC + tid];
+                t1 += (double)sD[4 * RC + ss * RC + tid];
+            }
+            atomicAdd(&bstats1[((size_t)n * RC + tid) * 2 + 0], t0);
+            atomicAdd(&bstats1[((size_t)n * RC + tid) * 2 + 1], t1);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 9; ++j) red[(j * 4 + s) * RP + p] = gw[j];
+        __syncthreads();
+        for (int e = tid; e < 9 * RC; e += 512) {
+            const int j = e / RC, ch = e % RC;
+            float t = 0.f;
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) t += sD[(j * 4 + ss) * RC + ch];
+            atomicAdd(&dwdw[(size_t)ch * 9 + j], t);
+        }
+    }
+}
+
 constexpr size_t FWD_SMEM = (size_t)ND * ROWF * 4 + ND * 8;
 constexpr size_t BWD_SMEM = (size_t)(ND + NH2) * ROWF * 4 + (size_t)NH1 * ROWC * 4 + 2 * RC * 16 + (ND + NH2 + NH1) * 8;
 
@@ -423,14 +652,16 @@ int launch_dwrows_fwd(const float* h1, const Coef* coef1, const float* wdw, floa
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dwrows_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(dwrows_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(dwrows_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(dwrows_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(dwrows_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess)
             return UB_ERR_CUDA;
         attr_set = true;
     }
     const dim3 grid(W / RW, H / R, N);
-    if (f2) dwrows_fwd_kernel<true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
-    else dwrows_fwd_kernel<false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
+    if (f2 & 2) dwrows_fwd_kernel<true, true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
+    else if (f2) dwrows_fwd_kernel<true, false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
+    else dwrows_fwd_kernel<false, false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
@@ -442,14 +673,27 @@ int launch_dwrows_bwd(const float* du, const float* h2, const float* h1, const f
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dwrows_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(dwrows_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(dwrows_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(dwrows_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(dwrows_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess)
             return UB_ERR_CUDA;
         attr_set = true;
     }
     const dim3 grid(W / RW, H / R, N);
-    if (f2) dwrows_bwd_kernel<true><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
-    else dwrows_bwd_kernel<false><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
+    if (f2 & 8) {      // 512-thread channel-pair variant
+        static bool p_attr = false;
+        if (!p_attr) {
+            if (cudaFuncSetAttribute(dwrows_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess)
+                return UB_ERR_CUDA;
+            p_attr = true;
+        }
+        dwrows_bwd2_kernel<true><<<grid, 512, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
+        UB_CHECK_LAUNCH();
+        return UB_OK;
+    }
+    if (f2 & 2) dwrows_bwd_kernel<true, true><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
+    else if (f2) dwrows_bwd_kernel<true, false><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
+    else dwrows_bwd_kernel<false, false><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
