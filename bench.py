@@ -37,7 +37,7 @@ METRIC = "samples/sec fwd+bwd (T=3, 15x256x256)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE config #2: 16)")
@@ -133,6 +133,25 @@ def algorithmic_bytes(kernel, frames, P):
         "gemm1_bwd": 2 * Hh + 2 * A, "wgrad1": A + 2 * Hh, "residual_bwd": 4 * A,
     }
     return per_frame.get(kernel, 0) * frames
+
+
+# kernel class (ub200_prof_* name) -> substring of the ncu kernel name in profiles/r01_traffic.json
+NCU_NAME = {"dwconv_bwd": "dwrows_bwd2_kernel", "dwconv_fwd": "dwrows_fwd_kernel<1, 1>", "gemm1_fwd": "gemm_tc_kernel<128, 256, TLoadNormed",
+            "gemm2_fwd": "gemm_tc_kernel<256, 128, TLoadGeluGate", "wgrad2": "wgrad_tc_kernel<TLoadNormBwd, TLoadGeluGate>",
+            "wgrad1": "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>", "se_pool": "se_pool_kernel"}
+
+
+def ncu_traffic_per_frame(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per frame of `kernel` from the committed ncu --set full capture
+    (profiles/r01_traffic.json, written by scripts/ncu_summary.py), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    key = NCU_NAME.get(kernel)
+    if not key or not os.path.exists(p):
+        return None
+    for name, v in json.load(open(p)).get("per_frame_bytes", {}).items():
+        if key in name:
+            return float(v)
+    return None
 
 
 def measured_peaks():
@@ -305,8 +324,11 @@ def main():
     P = args.hw * args.hw
     bytes_total = algorithmic_bytes(top, total_frames, P)
     achieved = bytes_total / (tms.value / 1e3) / 1e9 if tms.value > 0 else 0.0
+    tpf = ncu_traffic_per_frame(top)
+    traffic = int(tpf * total_frames / max(tn.value, 1)) if tpf else None      # per launch, like algorithmic_bytes_per_launch
     roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": "profiles/r01_traffic.json (ncu --set full dram bytes per frame x frames per launch)" if tpf else None,
                 "launches": tn.value, "avg_launch_ms": round(tms.value / max(tn.value, 1), 4),
                 "algorithmic_bytes_per_launch": bytes_total // max(tn.value, 1),
                 "share_of_step": round(tms.value / ms_total, 4),

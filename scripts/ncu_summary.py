@@ -1,16 +1,28 @@
 """Summarise ncu captures brought back in gpurun_out/ into tracked files under profiles/.
 
-    python scripts/ncu_summary.py r01            # reads gpurun_out/prof_*.ncu-rep and gpurun_out/launches.csv
+    python scripts/ncu_summary.py r01 [--full-batch 4]
+
+Reads gpurun_out/launches.csv (`ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3`,
+every launch of the process) and gpurun_out/prof_*.ncu-rep (`ncu --set full --clock-control none --import-source on`, captured
+with `bench.py --batch <full-batch>`), writes
+  profiles/<tag>_launches.md / .csv   one training step (the launches between two consecutive in_conv moment kernels, i.e. from
+                                      the first kernel of a forward pass to the last kernel of its backward pass)
+  profiles/<tag>_ncu_full_summary.md  per-kernel table of the --set full captures
+  profiles/<tag>_traffic.json         dram__bytes_read.sum + dram__bytes_write.sum per launch and per frame (what bench.py's
+                                      roofline.traffic is derived from)
 """
 import csv
 import glob
 import io
+import json
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+full_batch = int(sys.argv[sys.argv.index("--full-batch") + 1]) if "--full-batch" in sys.argv else 4
+T = 3
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 KEYS = [
@@ -25,9 +37,10 @@ KEYS = [
 ]
 traffic = {}
 lines = [f"# ncu --set full summaries ({tag})", "",
-         "Captured with `scripts/gpu_ncu.sh` (`ncu --set full --clock-control none --import-source on`, bench.py --batch 4 --steps 1);",
-         "times are cold-cache single launches: compare shares and percentages, not absolutes. Units as printed by ncu "
-         "(time: us or ms per the raw page; bytes: MB).", ""]
+         f"Captured with `scripts/gpu_ncu2.sh` (`ncu --set full --clock-control none --import-source on`, `bench.py --batch {full_batch} "
+         f"--steps 1`: decoder launches cover {full_batch} frames, encoder launches {full_batch * T});",
+         "times are cold-cache single launches under the profiler: compare shares and percentages, not absolutes. Units as printed by "
+         "ncu.", ""]
 for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -38,13 +51,13 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
-        name = d.get("Kernel Name", "?").split("(")[0][:70]
-        try:   # DRAM traffic per launch in bytes (raw page prints Mbyte / Gbyte)
+        name = d.get("Kernel Name", "?").split("(")[0][:70].strip()
+        try:
             def tobytes(key):
                 v, un = float(d[key]), u.get(key, "").lower()
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(un, 1)
-            traffic.setdefault(name.strip(), []).append({"dram_bytes": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
-                                                         "grid": d.get("launch__grid_size", "")})
+            traffic.setdefault(name, []).append({"dram_bytes": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
+                                                 "grid": d.get("launch__grid_size", "")})
         except (KeyError, ValueError):
             pass
         vals = []
@@ -61,19 +74,31 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
         top = ", ".join(f"{h} {100 * x / tot:.0f}%" for x, h in sorted(st, reverse=True)[:4])
         lines.append(f"| {name} | " + " | ".join(vals) + f" | {top} |")
     lines.append("")
-open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w").write("\n".join(lines))
-import json
-json.dump({"note": "per-launch dram__bytes_read.sum + dram__bytes_write.sum from ncu --set full; captured with bench.py --batch 4 "
-                   "(decoder launches = 4 frames, encoder launches = 12 frames)", "kernels": traffic},
-          open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1)
+if len(lines) > 6:
+    open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w").write("\n".join(lines))
+    # per-frame traffic of the row-streaming depthwise kernels and the GEMMs: a decoder launch covers `full_batch` frames
+    per_frame = {}
+    for name, ls in traffic.items():
+        small = min(x["dram_bytes"] for x in ls)          # the decoder-sized launch
+        per_frame[name] = small / full_batch
+    json.dump({"note": f"per-launch dram__bytes_read.sum + dram__bytes_write.sum from ncu --set full (bench.py --batch {full_batch}: "
+                       f"decoder launches = {full_batch} frames, encoder launches = {full_batch * T} frames); per_frame = smallest launch / "
+                       f"{full_batch}", "per_frame_bytes": per_frame, "kernels": traffic},
+              open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1)
 
 src = os.path.join(ROOT, "gpurun_out", "launches.csv")
 if os.path.exists(src):
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
-    hdr = rows[0]
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    hdr = rows[hi]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    body = rows[hi + 1:]
+    marks = [i for i, r in enumerate(body) if "inconv_moments_kernel" in r[ki]]
+    # bench.py --steps 1 --warmup 3: steps 0-2 warm-up, step 3 the device-resident timed step
+    lo, hi2 = (marks[3], marks[4]) if len(marks) >= 5 else (marks[-2], marks[-1])
+    step = body[lo:hi2]
     agg = {}
-    for r in rows[1:]:
+    for r in step:
         try:
             v = float(r[vi].replace(",", ""))
         except ValueError:
@@ -85,11 +110,16 @@ if os.path.exists(src):
         a[1] += v
     total = sum(a[1] for a in agg.values())
     with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over one bench.py step\n\n")
-        f.write("Per-launch times are cold-cache and serialised; the SHARE column is what is comparable with bench.py's CUDA-event breakdown.\n\n")
+        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3`\n\n")
+        f.write(f"ONE training step at B=16, T=3 (launches {lo}..{hi2 - 1} of the process: from the first kernel of the 4th forward pass to the "
+                f"last kernel of its backward pass; {len(step)} launches, {total / 1e3:.2f} ms summed).  Per-launch times are cold-cache and "
+                "serialised by the profiler; the SHARE column is what is comparable with bench.py's CUDA-event breakdown "
+                "(`kernels_ms_per_step`).\n\n")
         f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
         for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {name} | {cnt} | {us:.1f} | {100 * us / total:.1f}% |\n")
-    import shutil
-    shutil.copy(src, os.path.join(out_dir, f"{tag}_launches.csv"))
-print("written", os.listdir(out_dir))
+    with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(hdr)
+        w.writerows(step)
+print("written", sorted(os.listdir(out_dir)))
