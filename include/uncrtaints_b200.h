@@ -113,6 +113,9 @@ int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc
 /* 0 (default): single-role tcgen05 GEMM kernel; 1: warp-specialised variant (producer warps / epilogue warps, TMA bulk
  * weight load) -- kept for experiments, measured slightly slower. */
 int ub200_tc_set_warp_specialized(int on);
+/* 1 (default): the epilogue (TMEM -> global, statistics) of tile t-1 is spread over the K-block steps of tile t in the forward
+ * GEMMs (two parts; measured -9 % / -5 %); 0: one burst after the last K-block everywhere. */
+int ub200_tc_set_split_epilogue(int on);
 /* 1 (default): pointwise dh2 kernel + stencil kernel (6 tensor passes, measured faster); 0: fused depthwise-conv backward
  * kernel (4 tensor passes, kept for tuning). */
 int ub200_dwconv_set_bwd_split(int on);

@@ -76,6 +76,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// N = 8 / 16 / 32 consecutive TMEM columns of this thread's lane (tcgen05.ld.32x32b.xN)
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+    static_assert(N == 8 || N == 16 || N == 32, "unsupported tcgen05.ld width");
+    if constexpr (N == 32) {
+        float t[32];
+        tmem_ld32(taddr, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = t[i];
+    } else if constexpr (N == 16) {
+        uint32_t r[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    } else {
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+    }
+}
+
 // split 8 fp32 values into bf16 hi / lo (x ~= hi + lo) and store both 16-byte chunks
 __device__ __forceinline__ void split_store8(const float (&v)[8], char* hi_chunk, char* lo_chunk) {
     uint32_t h[4], l[4];
@@ -171,12 +201,14 @@ struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
 // ------------------------------------------------------------------------------------------
 struct TEpiStoreStats {        // raw output + (sum, sumsq)
     static constexpr int NS = 2;
+    static constexpr int PARTS = 2;      // split epilogue (see gemm_tc_kernel): measured -9 % (128 -> 256) and -5 % (256 -> 128)
     float* out; double* stats;
     struct State {};
     __device__ void init(int n, int NOUT, int ch, State&) const {}
-    __device__ void apply(const State&, size_t row0, int NOUT, int ch, const float (&v)[32], float* s) const {
+    template <int NPX>
+    __device__ void apply(const State&, size_t row0, int NOUT, int ch, const float* v, float* s) const {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < NPX; ++i) {
             out[(row0 + i) * NOUT + ch] = v[i];
             s[0] += v[i];
             s[1] = fmaf(v[i], v[i], s[1]);
@@ -186,12 +218,14 @@ struct TEpiStoreStats {        // raw output + (sum, sumsq)
 };
 struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
     static constexpr int NS = 3;
+    static constexpr int PARTS = 1;      // these epilogues also READ a tensor per element: splitting measured neutral to +4 %
     float* du; const float* h2; const Coef* coef2; const MeanRstd* mr2; double* sums;
     struct State { Coef k; MeanRstd m; };
     __device__ void init(int n, int NOUT, int ch, State& st) const { st.k = coef2[(size_t)n * NOUT + ch]; st.m = mr2[(size_t)n * NOUT + ch]; }
-    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float (&v)[32], float* s) const {
+    template <int NPX>
+    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float* v, float* s) const {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < NPX; ++i) {
             const size_t o = (row0 + i) * NOUT + ch;
             du[o] = v[i];
             const float h = h2[o];
@@ -207,12 +241,14 @@ struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
 };
 struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
     static constexpr int NS = 2;
+    static constexpr int PARTS = 1;
     float* dn0; const float* x; const MeanRstd* mr0; double* bstats;
     struct State { MeanRstd m; };
     __device__ void init(int n, int NOUT, int ch, State& st) const { st.m = mr0[(size_t)n * NOUT + ch]; }
-    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float (&v)[32], float* s) const {
+    template <int NPX>
+    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float* v, float* s) const {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < NPX; ++i) {
             const size_t o = (row0 + i) * NOUT + ch;
             dn0[o] = v[i];
             s[0] += v[i];
@@ -227,7 +263,7 @@ struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
 // The (tile, K-block) sequence is software pipelined: the raw loads of step q+1 are issued before step q is
 // converted, so HBM requests stay in flight across the convert / fence / barrier / MMA issue / epilogue of step q.
 // ------------------------------------------------------------------------------------------
-template <int K, int NOUT, class ALoad, class Epi>
+template <int K, int NOUT, class ALoad, class Epi, int PARTS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P) {
     constexpr int KB = K / KBLK, MH = NOUT / 128;
@@ -292,9 +328,27 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
         for (int j = 0; j < MH; ++j) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(pit & 1) * ACC_COLS + j * TILE_PX + pc * 32, v);
-            ep.apply(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+            ep.template apply<32>(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
         }
         tc_fence_before();     // order the TMEM reads before the barrier that precedes the next overwrite of this stage
+    };
+    // PARTS > 1: the epilogue of tile t-1 is spread over the pipeline steps of tile t (32/PARTS pixels after every
+    // KB/PARTS-th K-block) instead of running as one burst of 64+ global stores / loads per thread after the last K-block:
+    // the operand prefetch of the next step is never more than a partial epilogue away, and the LSU queue does not fill
+    // up (ncu r01: lg_throttle 26 % in the write-heavy 128 -> 256 kernel, which gains 9 %; the 256 -> 128 kernels do not).
+    static_assert(PARTS == 1 || (KB % PARTS == 0 && 32 % PARTS == 0), "PARTS must divide the K-block count");
+    auto epilogue_part = [&](int pit, int part) {
+        constexpr int CH = 32 / PARTS;
+        const size_t prow0 = (size_t)n * P + (size_t)(t0 + pit) * TILE_PX + pc * 32 + part * CH;
+        if (part == 0) mbar_wait(smem_u32(&sBar[NSTAGE + (pit & 1)]), (uint32_t)(pit >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < MH; ++j) {
+            float v[CH];
+            tmem_ldn<CH>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(pit & 1) * ACC_COLS + j * TILE_PX + pc * 32 + part * CH, v);
+            ep.template apply<CH>(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+        }
+        tc_fence_before();
     };
 
     for (int q = 0; q < Q; ++q) {
@@ -347,9 +401,21 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
             tc_commit(smem_u32(&sBar[slot]));                                  // frees the ring slot
             if (kb == KB - 1) tc_commit(smem_u32(&sBar[NSTAGE + (it & 1)]));   // accumulator of this tile complete
         }
-        if (kb == KB - 1 && it > 0) epilogue(it - 1);     // previous tile, while this tile's MMAs run
+        if constexpr (PARTS > 1) {
+            constexpr int EVERY = KB / PARTS;
+            if (it > 0 && (kb + 1) % EVERY == 0) epilogue_part(it - 1, (kb + 1) / EVERY - 1);   // a slice of the previous tile, while this tile's MMAs run
+        } else {
+            if (kb == KB - 1 && it > 0) epilogue(it - 1);     // previous tile, while this tile's MMAs run
+        }
     }
-    if (Q > 0) epilogue(t1 - t0 - 1);
+    if (Q > 0) {
+        if constexpr (PARTS > 1) {
+#pragma unroll
+            for (int part = 0; part < PARTS; ++part) epilogue_part(t1 - t0 - 1, part);
+        } else {
+            epilogue(t1 - t0 - 1);
+        }
+    }
     // per-channel statistics: 4 warps (pixel blocks) share a channel -> 4 atomics per channel per CTA
     double* dst = ep.dst(n, NOUT);
 #pragma unroll
@@ -516,7 +582,7 @@ gemm_tc_ws_kernel(ALoad al, const uint4* __restrict__ wimg, Epi ep, int P) {
                 for (int sl = 0; sl < 2; ++sl) {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(it & 1) * ACC_COLS + j * TILE_PX + ph * 64 + sl * 32, v);
-                    ep.apply(est[j], prow0 + sl * 32, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+                    ep.template apply<32>(est[j], prow0 + sl * 32, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
                 }
             tc_fence_before();
             __syncwarp();
@@ -553,23 +619,28 @@ static int blocks_per_frame(int N, int tiles) {
     return g < 1 ? 1 : g;
 }
 
+// tc_set_split_epilogue(): 1 (default) = every kernel uses its epilogue's PARTS, 0 = one burst everywhere
+static int g_split_epilogue = 1;
 static int g_warp_specialized = 0;      // tc_set_warp_specialized(): 0 = gemm_tc_kernel (default; measured faster), 1 = gemm_tc_ws_kernel
 
 template <int K, int NOUT, class ALoad, class Epi>
 static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t st) {
     if (P % TILE_PX != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + 8 * 8 + 16 + 1024;
-    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi>;
+    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi, 1>;
+    auto kern_split = gemm_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS>;
     auto kern_ws = gemm_tc_ws_kernel<K, NOUT, ALoad, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+        if (cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
         if (cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
         attr_set = true;
     }
     const int tiles = P / TILE_PX;
     const dim3 grid(blocks_per_frame(N, tiles), N);
     if (g_warp_specialized) kern_ws<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
+    else if (g_split_epilogue) kern_split<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
     else kern<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P);
     UB_CHECK_LAUNCH();
     return UB_OK;
@@ -815,6 +886,7 @@ int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
     return UB_OK;
 }
 int tc_set_warp_specialized(int on) { tc::g_warp_specialized = on ? 1 : 0; return UB_OK; }
+int tc_set_split_epilogue(int on) { tc::g_split_epilogue = on ? 1 : 0; return UB_OK; }
 int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
     if (cudaMemcpyToSymbol(tc::c_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
     if (cudaMemcpyToSymbol(tc::c_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;

@@ -335,6 +335,7 @@ unsigned long long ub200_launch_count(void) { return g_launch_count; }
 
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
 int ub200_tc_set_warp_specialized(int on) { return tc_set_warp_specialized(on); }
+int ub200_tc_set_split_epilogue(int on) { return tc_set_split_epilogue(on); }
 int ub200_dwconv_set_bwd_split(int on) { return dwconv_set_bwd_split(on); }
 int ub200_dwconv_set_mode(int mode) { return dwconv_set_mode(mode); }
 int ub200_inconv_set_moments(int on) { g_inconv_moments = on ? 1 : 0; return UB_OK; }
