@@ -18,44 +18,74 @@ constexpr int HD_MAXO = 26;
 constexpr int HD_PX = 128;
 
 // ------------------------------------------------------------------------------------------
-// out_conv + head forward.  CTA = 64 pixels x 4 output groups (group g owns outputs g, g+4, g+8, ...).
+// out_conv + head forward.  Persistent CTAs over 128-pixel tiles.  The decoder tile is staged by cp.async into a
+// pitch-132 shared-memory tile (a lane's LDS.128 along k is conflict-free across the 8 pixels of a quarter warp); a thread
+// owns ONE pixel and 13 outputs (half = tid / 128 selects outputs 0-12 or 13-25), reads 4 k-values of its pixel with one
+// LDS.128 and the 13 weights of each k as 3 broadcast LDS.128 + 1 LDS.32 from a [k][32] table: 17 LDS per 52 FMA instead of
+// the 8 LDS per 7 FMA of a pixel x group-of-7 mapping (ncu r01: mio_throttle + short_scoreboard 35 %, 0.58 ms at B=16).
 // ------------------------------------------------------------------------------------------
-constexpr int HF_PX = 64, HF_G = 4, HF_PER = (HD_MAXO + HF_G - 1) / HF_G;
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ dec /* [B][P][128] */, const float* __restrict__ w /* [O][128] */,
-                                                        const float* __restrict__ bias, float* __restrict__ out /* [B][O][P] */,
-                                                        int O, int P, float scale_by, int mean_sigmoid, float var_eps) {
-    constexpr int C = UB_WIDTH, PITCH = C + 1;
-    __shared__ float as[HF_PX * PITCH];
-    __shared__ float ws[HD_MAXO * C];
-    __shared__ float bs[HD_MAXO];
-    const int b = blockIdx.y, p0 = blockIdx.x * HF_PX, tid = threadIdx.x;
-    for (int i = tid; i < O * C; i += 256) ws[i] = w[i];
-    if (tid < O) bs[tid] = bias[tid];
-    for (int i = tid; i < HF_PX * (C / 4); i += 256) {
-        const int px = i / (C / 4), k4 = i % (C / 4);
-        const float4 v = ld4_stream(dec + ((size_t)b * P + p0 + px) * C + k4 * 4);
-        float* d = as + px * PITCH + k4 * 4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+constexpr int HF_PX = 128, HF_PITCH = UB_WIDTH + 4, HF_HALF = 13, HF_WROW = 32;
+constexpr size_t HF_SMEM = (size_t)(HF_PX * HF_PITCH + UB_WIDTH * HF_WROW + 32) * sizeof(float);
+__global__ void __launch_bounds__(256, 2) head_fwd_kernel(const float* __restrict__ dec /* [B][P][128] */, const float* __restrict__ w /* [O][128] */,
+                                                           const float* __restrict__ bias, float* __restrict__ out /* [B][O][P] */,
+                                                           int O, int P, long long total_tiles, float scale_by, int mean_sigmoid,
+                                                           float var_eps) {
+    constexpr int C = UB_WIDTH;
+    extern __shared__ __align__(16) float fsm[];
+    float* as = fsm;                                  // [128 px][132]
+    float* ws = fsm + HF_PX * HF_PITCH;               // [128 k][32]: outputs 0-12 at columns 0-12, outputs 13-25 at columns 16-28
+    float* bs = ws + C * HF_WROW;                     // [32] bias in the same column order
+    const int tid = threadIdx.x, px = tid % HF_PX, half = tid / HF_PX;
+    for (int i = tid; i < C * HF_WROW; i += 256) {
+        const int k = i / HF_WROW, col = i % HF_WROW, o = (col / 16) * HF_HALF + (col % 16);
+        ws[i] = ((col % 16) < HF_HALF && o < O) ? w[o * C + k] : 0.f;
     }
-    __syncthreads();
-    const int px = tid % HF_PX, grp = tid / HF_PX;
-    float acc[HF_PER];
-#pragma unroll
-    for (int j = 0; j < HF_PER; ++j) acc[j] = (grp + HF_G * j < O) ? bs[grp + HF_G * j] : 0.f;
-    for (int k = 0; k < C; ++k) {
-        const float a = as[px * PITCH + k];
-#pragma unroll
-        for (int j = 0; j < HF_PER; ++j)
-            if (grp + HF_G * j < O) acc[j] = fmaf(a, ws[(grp + HF_G * j) * C + k], acc[j]);
+    if (tid < HF_WROW) {
+        const int o = (tid / 16) * HF_HALF + (tid % 16);
+        bs[tid] = ((tid % 16) < HF_HALF && o < O) ? bias[o] : 0.f;
     }
+    const int tiles_per_img = P / HF_PX;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = (int)(t / tiles_per_img), p0 = (int)(t % tiles_per_img) * HF_PX;
+        __syncthreads();                              // everybody is done with the previous tile (and the tables are written)
+        for (int i = tid; i < HF_PX * (C / 4); i += 256) {
+            const int r = i / (C / 4), k4 = i % (C / 4);
+            const unsigned d = (unsigned)__cvta_generic_to_shared(as + r * HF_PITCH + k4 * 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(dec + ((size_t)b * P + p0 + r) * C + k4 * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        float acc[HF_HALF];
 #pragma unroll
-    for (int j = 0; j < HF_PER; ++j) {
-        const int o = grp + HF_G * j;
-        if (o < O) {
-            float v = acc[j];
-            if (o < UB_S2) { if (mean_sigmoid) v = scale_by * sigmoid_f(v); }
-            else v = (v > 20.f ? v : log1pf(expf(v))) + var_eps;
-            out[((size_t)b * O + o) * P + p0 + px] = v;
+        for (int j = 0; j < HF_HALF; ++j) acc[j] = bs[half * 16 + j];
+        const float* ap = as + px * HF_PITCH;
+        const float* wp = ws + half * 16;
+#pragma unroll 2
+        for (int k4 = 0; k4 < C / 4; ++k4) {
+            const float4 a4 = ld4(ap + k4 * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float* wr = wp + (k4 * 4 + kk) * HF_WROW;
+                const float4 w0 = ld4(wr), w1 = ld4(wr + 4), w2 = ld4(wr + 8);
+                const float w3 = wr[12];
+                const float a = av[kk];
+                acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+                acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+                acc[8] = fmaf(a, w2.x, acc[8]); acc[9] = fmaf(a, w2.y, acc[9]); acc[10] = fmaf(a, w2.z, acc[10]); acc[11] = fmaf(a, w2.w, acc[11]);
+                acc[12] = fmaf(a, w3, acc[12]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HF_HALF; ++j) {
+            const int o = half * HF_HALF + j;
+            if (o < O) {
+                float v = acc[j];
+                if (o < UB_S2) { if (mean_sigmoid) v = scale_by * sigmoid_f(v); }
+                else v = (v > 20.f ? v : log1pf(expf(v))) + var_eps;
+                out[((size_t)b * O + o) * P + p0 + px] = v;
+            }
         }
     }
 }
@@ -112,31 +142,45 @@ __global__ void __launch_bounds__(256, 2) head_bwd_kernel(const float* __restric
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // input gradient: one pixel per warp iteration, lane = 4 channels
-        for (int px = warp; px < HD_PX; px += 8) {
-            float4 acc = make_float4(0, 0, 0, 0);
+        // input gradient: 4 consecutive pixels per warp iteration, lane = 4 channels: per output one broadcast LDS.128 of the 4
+        // `do` values and one LDS.128 of the weights feed 16 FMAs (was 2 LDS per 4 FMAs: mio_throttle + short_scoreboard 41 %)
+        for (int px0 = warp * 4; px0 < HD_PX; px0 += 32) {
+            float4 acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int o = 0; o < HD_MAXO; ++o) {
                 if (o < O) {
-                    const float d = dos[o * HD_PX + px];
+                    const float4 d4 = ld4(dos + o * HD_PX + px0);
                     const float4 wv = ld4(ws + o * C + lane * 4);
-                    acc.x = fmaf(d, wv.x, acc.x); acc.y = fmaf(d, wv.y, acc.y);
-                    acc.z = fmaf(d, wv.z, acc.z); acc.w = fmaf(d, wv.w, acc.w);
+                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i].x = fmaf(dd[i], wv.x, acc[i].x); acc[i].y = fmaf(dd[i], wv.y, acc[i].y);
+                        acc[i].z = fmaf(dd[i], wv.z, acc[i].z); acc[i].w = fmaf(dd[i], wv.w, acc[i].w);
+                    }
                 }
             }
-            st4(ddec + (row0 + px) * C + lane * 4, acc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st4(ddec + (row0 + px0 + i) * C + lane * 4, acc[i]);
         }
-        // weight gradient: warp owns outputs warp + 8j
-#pragma unroll 4
-        for (int px = 0; px < HD_PX; ++px) {
-            const float4 a = ld4(dect + px * C + lane * 4);
+        // weight gradient: warp owns outputs warp + 8j; 4 pixels per iteration
+#pragma unroll 2
+        for (int px0 = 0; px0 < HD_PX; px0 += 4) {
+            float4 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = ld4(dect + (px0 + i) * C + lane * 4);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int o = warp + 8 * j;
                 if (o < O) {
-                    const float d = dos[o * HD_PX + px];
-                    gw[j].x = fmaf(d, a.x, gw[j].x); gw[j].y = fmaf(d, a.y, gw[j].y);
-                    gw[j].z = fmaf(d, a.z, gw[j].z); gw[j].w = fmaf(d, a.w, gw[j].w);
+                    const float4 d4 = ld4(dos + o * HD_PX + px0);
+                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        gw[j].x = fmaf(dd[i], a[i].x, gw[j].x); gw[j].y = fmaf(dd[i], a[i].y, gw[j].y);
+                        gw[j].z = fmaf(dd[i], a[i].z, gw[j].z); gw[j].w = fmaf(dd[i], a[i].w, gw[j].w);
+                    }
                 }
             }
         }
@@ -257,7 +301,14 @@ __global__ void __launch_bounds__(256) covariance_kernel(const float* __restrict
 int launch_head_fwd(const float* dec, const float* w, const float* bias, float* out, int B, int O, int P, float scale_by,
                     int mean_sigmoid, float var_eps, cudaStream_t st) {
     if (O > HD_MAXO || O < UB_S2 || P % HF_PX) return UB_ERR_ARG;
-    head_fwd_kernel<<<dim3(P / HF_PX, B), 256, 0, st>>>(dec, w, bias, out, O, P, scale_by, mean_sigmoid, var_eps);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM) != cudaSuccess) return UB_ERR_CUDA;
+        attr_set = true;
+    }
+    const long long tiles = (long long)B * (P / HF_PX);
+    const int blocks = (int)(tiles < 2LL * 148 ? tiles : 2LL * 148);
+    head_fwd_kernel<<<blocks, 256, HF_SMEM, st>>>(dec, w, bias, out, O, P, tiles, scale_by, mean_sigmoid, var_eps);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
