@@ -191,7 +191,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"BASELINE config #2: uncrtaints --input_t {args.t} --n_head 16 --block_type mbconv --covmode "
+    tag = "BASELINE config #2" if (args.batch, args.t, args.covmode) == (16, 3, "diag") else \
+        ("BASELINE config #3 shape (fp32 storage)" if (args.batch, args.t) == (32, 5) else "variant of BASELINE config #2")
+    config = {"workload": f"{tag}: uncrtaints --input_t {args.t} --n_head 16 --block_type mbconv --covmode "
                           f"{args.covmode}, per-GPU batch {args.batch}, synthetic 15x{args.hw}x{args.hw}, fwd+MGNLL+bwd, train mode",
               "per_gpu_batch": args.batch, "global_batch": args.batch * world, "T": args.t,
               "parallelism": f"dp{world} (batch sharded by sample, one NCCL all-reduce of the flat 2.28 MB gradient)",

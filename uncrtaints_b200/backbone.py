@@ -180,6 +180,9 @@ class _UncrtaintsFunction(torch.autograd.Function):
             raise NotImplementedError(
                 f"unsupported configuration for the B200 path: B={desc.B} T={desc.T} C_in={desc.C_in} H={desc.H} W={desc.W} "
                 "(need H, W multiples of 32, T <= 8, C_in <= 16)")
+        # one workspace alive per model in the usual loop: drop the debugging reference to the previous call's workspace so that
+        # the caching allocator hands the same block back (at B=32, T=5 it is 102 GB: two would not fit in 180 GB)
+        net._last_workspace = None
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         out = torch.empty((desc.B, 1, desc.out_dim, desc.H, desc.W), dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
