@@ -176,7 +176,12 @@ struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
     }
     __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_f(fmaf(r.a[i], c.sc[i], c.sh[i])) * c.g[i];
+        for (int i = 0; i < 8; i += 2) {          // packed f32x2 GELU: 4 pairs
+            float g0, g1, d0, d1;
+            gelu_pair<true, false>(fmaf(r.a[i], c.sc[i], c.sh[i]), fmaf(r.a[i + 1], c.sc[i + 1], c.sh[i + 1]), g0, g1, d0, d1);
+            v[i] = g0 * c.g[i];
+            v[i + 1] = g1 * c.g[i + 1];
+        }
     }
 };
 struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
@@ -225,16 +230,19 @@ struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
     template <int NPX>
     __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float* v, float* s) const {
 #pragma unroll
-        for (int i = 0; i < NPX; ++i) {
-            const size_t o = (row0 + i) * NOUT + ch;
-            du[o] = v[i];
-            const float h = h2[o];
-            const float z = fmaf(h, st.k.scale, st.k.shift);
-            float gz, gp;
-            gelu_both(z, gz, gp);
-            s[0] = fmaf(v[i], gz, s[0]);
-            s[1] = fmaf(v[i], gp, s[1]);
-            s[2] = fmaf(v[i] * gp, (h - st.m.mean) * st.m.rstd, s[2]);
+        for (int i = 0; i < NPX; i += 2) {        // two pixels per step: packed f32x2 GELU + derivative
+            const size_t o0 = (row0 + i) * NOUT + ch, o1 = o0 + NOUT;
+            du[o0] = v[i];
+            du[o1] = v[i + 1];
+            const float h0 = h2[o0], h1v = h2[o1];
+            float g0, g1, p0, p1;
+            gelu_pair<true, true>(fmaf(h0, st.k.scale, st.k.shift), fmaf(h1v, st.k.scale, st.k.shift), g0, g1, p0, p1);
+            s[0] = fmaf(v[i], g0, s[0]);
+            s[1] = fmaf(v[i], p0, s[1]);
+            s[2] = fmaf(v[i] * p0, (h0 - st.m.mean) * st.m.rstd, s[2]);
+            s[0] = fmaf(v[i + 1], g1, s[0]);
+            s[1] = fmaf(v[i + 1], p1, s[1]);
+            s[2] = fmaf(v[i + 1] * p1, (h1v - st.m.mean) * st.m.rstd, s[2]);
         }
     }
     __device__ double* dst(int n, int NOUT) const { return sums + (size_t)n * NOUT * NS; }
