@@ -496,3 +496,20 @@ def test_flat_bucket_in_place_gradients(golden_weights):
     assert float((bucket.flat - 2 * once).norm()) <= 1e-4 * float((2 * once).norm())
     bucket.zero_()
     assert float(bucket.flat.abs().max()) == 0.0
+
+
+def test_mgnll_deferred_negative_check():
+    """check_negative="deferred": same loss, the ValueError of a negative variance surfaces at the next call / check()."""
+    import uncrtaints_b200 as ub
+    c = load_npz("case_mgnll.npz")
+    pred, var, targ = (torch.from_numpy(c[f"diag.{k}"]).cuda() for k in ("pred", "var", "target"))
+    crit = ub.MultiGaussianNLLLoss(mode="diag", chunk=None, check_negative="deferred")
+    loss, _ = crit(pred, targ, var)
+    assert abs(loss.item() - float(c["diag.loss"])) / abs(float(c["diag.loss"])) <= 1e-4
+    crit.check()                                   # nothing pending
+    crit(pred, targ, -var)                         # no error yet ...
+    with pytest.raises(ValueError, match="var has negative entry/entries"):
+        crit(pred, targ, var)                      # ... it surfaces one call later
+    crit(pred, targ, -var)
+    with pytest.raises(ValueError, match="var has negative entry/entries"):
+        crit.check()

@@ -10,7 +10,7 @@ The compute lives in libuncrtaints_b200.so (C ABI: include/uncrtaints_b200.h); t
 from .backbone import UNCRTAINTS, set_default_gemm_backend  # noqa: F401
 from .losses import MultiGaussianNLLLoss, get_loss, calc_loss, multi_gaussian_nll_loss, covariance_diag  # noqa: F401
 from .install import install  # noqa: F401
-from .parallel import FlatGradAllReduce, HostToDevicePrefetcher, shard_batch  # noqa: F401
+from .parallel import FlatGradAllReduce, HostToDevicePrefetcher, HostScalarReader, shard_batch  # noqa: F401
 
 __all__ = ["UNCRTAINTS", "MultiGaussianNLLLoss", "get_loss", "calc_loss", "multi_gaussian_nll_loss", "covariance_diag",
-           "install", "FlatGradAllReduce", "HostToDevicePrefetcher", "shard_batch", "set_default_gemm_backend"]
+           "install", "FlatGradAllReduce", "HostToDevicePrefetcher", "HostScalarReader", "shard_batch", "set_default_gemm_backend"]

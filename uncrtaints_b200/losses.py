@@ -9,8 +9,9 @@ Mirrors model/src/losses.py: ``get_loss(config)`` (:14-32), ``calc_loss(criterio
   built by one kernel, and ``covariance='none'`` skips it.  Callers only use ``.cpu()``, scalar multiply,
   ``.diagonal``, ``.mean`` and indexing on it (base_model.py:112-113,131; train_reconstruct.py:185-191,324-352),
   all of which work unchanged.
-* ``var`` with a negative entry raises ``ValueError`` like the reference (:199-200); the check costs a host sync,
-  ``check_negative=False`` defers it away.
+* ``var`` with a negative entry raises ``ValueError`` like the reference (:199-200).  Reading the device flag costs a host
+  sync per call (the CPU cannot enqueue the backward kernels until the forward has drained); ``check_negative="deferred"``
+  keeps the error but reads the flag of call k at call k+1 (or at ``MultiGaussianNLLLoss.check()``), ``False`` never reads it.
 """
 from __future__ import annotations
 
@@ -33,6 +34,8 @@ def _plane_view(t: torch.Tensor):
 
 
 class _MGNLLFunction(torch.autograd.Function):
+    last_flag = None
+
     @staticmethod
     def forward(ctx, pred, target, var, eps, check_negative):
         L = _lib.lib()
@@ -54,7 +57,10 @@ class _MGNLLFunction(torch.autograd.Function):
                                          var_ch, B, P, float(eps), loss.data_ptr(),
                                          dpred.data_ptr() if need_grad else None, dvar.data_ptr() if need_grad else None,
                                          flag.data_ptr(), scratch.data_ptr(), stream), "ub200_mgnll_forward")
-        if check_negative and int(flag.item()) != 0:
+        _MGNLLFunction.last_flag = flag              # device int: 1 if any var < 0 (read later in deferred mode)
+        if check_negative == "deferred":
+            pass
+        elif check_negative and int(flag.item()) != 0:
             raise ValueError("var has negative entry/entries")
         if need_grad:
             ctx.save_for_backward(dpred, dvar)
@@ -103,6 +109,7 @@ def multi_gaussian_nll_loss(input, target, var, full=False, eps=1e-8, reduction=
     return loss, variance
 
 
+
 class MultiGaussianNLLLoss(nn.Module):
     """Same constructor / call as the reference class (losses.py:288-354)."""
 
@@ -111,11 +118,23 @@ class MultiGaussianNLLLoss(nn.Module):
         super().__init__()
         self.full, self.eps, self.reduction, self.mode, self.chunk = full, eps, reduction, mode, chunk
         self.covariance, self.check_negative = covariance, check_negative
+        self._pending_flag = None
+
+    def check(self):
+        """Deferred mode: raise the reference's ValueError if the previous call saw a negative variance."""
+        flag, self._pending_flag = self._pending_flag, None
+        if flag is not None and int(flag.item()) != 0:
+            raise ValueError("var has negative entry/entries")
 
     def forward(self, input, target, var):
-        return multi_gaussian_nll_loss(input, target, var, full=self.full, eps=self.eps, reduction=self.reduction,
-                                       mode=self.mode, chunk=self.chunk, covariance=self.covariance,
-                                       check_negative=self.check_negative)
+        if self.check_negative == "deferred":
+            self.check()                 # flag of the previous call: that step has long finished, no pipeline bubble
+        loss, variance = multi_gaussian_nll_loss(input, target, var, full=self.full, eps=self.eps, reduction=self.reduction,
+                                                 mode=self.mode, chunk=self.chunk, covariance=self.covariance,
+                                                 check_negative=self.check_negative)
+        if self.check_negative == "deferred":
+            self._pending_flag = _MGNLLFunction.last_flag
+        return loss, variance
 
 
 def get_loss(config):

@@ -97,3 +97,48 @@ class HostToDevicePrefetcher:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.free[self._last] = ev
+
+
+class HostScalarReader:
+    """Device -> host read of a per-step scalar (the loss) without draining the GPU: the copy into pinned host memory runs on
+    a side stream behind an event recorded after the step, and the value is consumed one step later.  Every step's scalar
+    is still read; the host just never waits for the step it has only just enqueued (``loss.item()`` would)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.done = [None, None]
+        self.keep = [None, None]
+        self.i = 0
+        self.bytes_per_read = 4
+
+    def submit(self, scalar: torch.Tensor) -> None:
+        """Enqueue the read of `scalar` (0-d CUDA tensor produced on the current stream)."""
+        k = self.i & 1
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.host[k].copy_(scalar.detach(), non_blocking=True)
+            scalar.record_stream(self.stream)
+            d = torch.cuda.Event()
+            d.record(self.stream)
+        self.done[k], self.keep[k] = d, scalar
+        self.i += 1
+
+    def previous(self):
+        """Value submitted one call before the latest one (None if there is none yet)."""
+        if self.i < 2:
+            return None
+        k = self.i & 1                      # slot of submission i-2
+        self.done[k].synchronize()
+        return float(self.host[k])
+
+    def latest(self):
+        """Value of the latest submission (waits for that step to finish)."""
+        if self.i < 1:
+            return None
+        k = (self.i - 1) & 1
+        self.done[k].synchronize()
+        return float(self.host[k])
