@@ -41,8 +41,14 @@ lines = [f"# ncu --set full summaries ({tag})", "",
          f"--steps 1`: decoder launches cover {full_batch} frames, encoder launches {full_batch * T});",
          "times are cold-cache single launches under the profiler: compare shares and percentages, not absolutes. Units as printed by "
          "ncu.", ""]
-for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+reps = {os.path.splitext(p)[0] for p in glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))}
+reps |= {os.path.splitext(p)[0] for p in glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.csv"))}
+for stem in sorted(reps):
+    rep = stem + ".ncu-rep"
+    if os.path.exists(stem + ".csv") and os.path.getsize(stem + ".csv") > 0:      # raw page exported on the GPU box
+        raw = open(stem + ".csv").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         continue
@@ -77,10 +83,22 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
 if len(lines) > 6:
     open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w").write("\n".join(lines))
     # per-frame traffic of the row-streaming depthwise kernels and the GEMMs: a decoder launch covers `full_batch` frames
+    # A launch covers either the decoder batch (full_batch frames) or the encoder batch (full_batch * T frames); which one a
+    # captured launch was is decided by the algorithmic bytes per frame where the kernel has an entry.
+    A, Hh = 128 * 65536 * 4, 256 * 65536 * 4
+    ALG = {"dwrows_bwd2_kernel": 4 * Hh, "dwrows_fwd_kernel": 2 * Hh, "gemm_tc_kernel<128, 256, TLoadNormed": A + Hh,
+           "gemm_tc_kernel<256, 128, TLoadGeluGate": Hh + A, "gemm_tc_kernel<128, 256, TLoadNormBwd": 2 * A + 2 * Hh,
+           "gemm_tc_kernel<256, 128, TLoadNormBwd": 2 * Hh + 2 * A, "wgrad_tc_kernel<TLoadNormBwd, TLoadGeluGate>": 2 * A + Hh,
+           "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>": A + 2 * Hh, "se_pool_kernel": Hh, "residual_bwd_kernel": 4 * A,
+           "residual_fwd_kernel": 3 * A, "norm_bwd_stats_kernel": 2 * A}
     per_frame = {}
     for name, ls in traffic.items():
-        small = min(x["dram_bytes"] for x in ls)          # the decoder-sized launch
-        per_frame[name] = small / full_batch
+        small = min(x["dram_bytes"] for x in ls)
+        alg = next((v for k, v in ALG.items() if k in name), None)
+        frames = full_batch
+        if alg is not None and abs(small / (full_batch * T) - alg) < abs(small / full_batch - alg):
+            frames = full_batch * T
+        per_frame[name] = small / frames
     json.dump({"note": f"per-launch dram__bytes_read.sum + dram__bytes_write.sum from ncu --set full (bench.py --batch {full_batch}: "
                        f"decoder launches = {full_batch} frames, encoder launches = {full_batch * T} frames); per_frame = smallest launch / "
                        f"{full_batch}", "per_frame_bytes": per_frame, "kernels": traffic},
