@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--t", type=int, default=3)
     ap.add_argument("--hw", type=int, default=256)
     ap.add_argument("--covmode", default="diag")
-    ap.add_argument("--backend", type=int, default=None, help="bit 0: tcgen05 fwd/dX GEMMs, bit 1: tcgen05 wgrad GEMMs (default 3); 0 = fp32 CUDA cores")
+    ap.add_argument("--backend", type=int, default=None, help="bit 0: tcgen05 fwd/dX GEMMs, bit 1: tcgen05 wgrad GEMMs (default 3), bit 2: single-pass bf16 MMAs (7: reduced precision); 0 = fp32 CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     return ap.parse_args()
@@ -343,7 +343,8 @@ def main():
                 "note": "achieved = algorithmic bytes (DESIGN.md §4) / CUDA-event time of the kernel class inside the timed region"}
     line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MMA / f32 storage" if ((args.backend or 0) & 4) else "f32",
+            "data": "synthetic", "config": config,
             "gemm_backend": int(args.backend if args.backend is not None else ub.backbone._default_backend()),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(samples / (e2e_ms / 1e3), 3), "unit": "samples/s", "ms_per_step": round(e2e_ms / args.steps, 3),

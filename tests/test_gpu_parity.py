@@ -246,7 +246,14 @@ def test_mbconv_block_row_streaming_dwconv(golden_weights, groups, training, sha
         L.ub200_dwconv_set_mode(47)
 
 
-def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, shape=(3, 16, 32), extra_tag=""):
+@pytest.mark.parametrize("groups,training", [(4, 1), (0, 1)])
+def test_mbconv_block_single_pass_bf16(golden_weights, groups, training):
+    """gemm_backend bit 2 (BASELINE config #3's "bf16 tensor-core path"): one bf16 MMA per k-step instead of the bf16x3 split.
+    Reduced precision by design: bf16 operand rounding (2^-9) through four GEMMs; tolerance 5e-2, measured errors are reported."""
+    _mbconv_block_vs_oracle(golden_weights, groups, training, 7, True, (2, 64, 64), ",bf16x1", tol=5e-2)
+
+
+def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, shape=(3, 16, 32), extra_tag="", tol=None):
     from uncrtaints_b200 import _lib
     L = _lib.lib()
     kind = "group" if groups else "batch"
@@ -296,17 +303,18 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
         errs[name] = rel_l2(gbuf.reshape(-1), ref_g[name].reshape(-1))
         lines.append(f"{tag} grad {name}: rel_l2={errs[name]:.3e}")
     report("parity_report.txt", lines)
-    assert rel_l2(out, _nhwc(ref.detach())) <= TOL
-    assert rel_l2(dx, _nhwc(ref_dx)) <= TOL
+    tol = TOL if tol is None else tol
+    assert rel_l2(out, _nhwc(ref.detach())) <= tol
+    assert rel_l2(dx, _nhwc(ref_dx)) <= tol
     for name, e in errs.items():
         if kind == "batch" and name.endswith("conv.norm.bias"):
             continue      # cancels through the following BatchNorm only when it is in training mode; checked below
-        assert e <= TOL, (name, e)
+        assert e <= tol, (name, e)
     if not groups and training:
         for k, v in newbuf.items():
             slot = [s for s, nm in rel.items() if pre + nm == k]
             if slot:
-                assert torch.allclose(dev[slot[0]].double().cpu(), v.double(), rtol=1e-4, atol=1e-5), k
+                assert torch.allclose(dev[slot[0]].double().cpu(), v.double(), rtol=max(1e-4, tol), atol=max(1e-5, 0.1 * tol)), k
 
 
 @pytest.mark.parametrize("B,T,H,W,covmode,train,pad,backend", [
@@ -513,3 +521,28 @@ def test_mgnll_deferred_negative_check():
     crit(pred, targ, -var)
     with pytest.raises(ValueError, match="var has negative entry/entries"):
         crit.check()
+
+
+def test_model_single_pass_bf16_backend(golden_weights):
+    """Whole model at the BASELINE config #3 sequence length (T=5) through the single-pass bf16 tensor-core backend (7):
+    outputs / loss within 5e-2 of the fp64 oracle (reduced precision by design), errors reported."""
+    import uncrtaints_b200 as ub
+    B, T, H, W = 1, 5, 64, 64
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=17)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=18)
+    cfg = O.OracleConfig()
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in golden_weights.items()}
+    o_out, o_loss, o_grads, _ = O.step(p64, x.double(), y.double(), d.double(), cfg, True, keep)
+    net = make_net(golden_weights, "diag", backend=7).train()
+    net._injected_keep_mask = keep.to(torch.uint8)
+    out = net(x.cuda(), batch_positions=d.cuda())
+    loss, _ = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None)(out[:, :, :13], y.cuda(), out[:, :, 13:26])
+    loss.backward()
+    e_out = rel_l2(out, o_out)
+    e_loss = abs(loss.item() - o_loss.item()) / abs(o_loss.item())
+    gerr = {k: rel_l2(p.grad, o_grads[k]) for k, p in net.named_parameters() if not is_zero_grad_param(k)}
+    worst = max(gerr, key=gerr.get)
+    report("parity_report.txt", [f"bf16x1 backend: out rel_l2={e_out:.3e} loss rel={e_loss:.3e} worst grad {worst} rel_l2={gerr[worst]:.3e} "
+                                 f"median grad rel_l2={sorted(gerr.values())[len(gerr) // 2]:.3e}"])
+    assert e_out <= 5e-2 and e_loss <= 5e-2
+    assert sorted(gerr.values())[len(gerr) // 2] <= 5e-2

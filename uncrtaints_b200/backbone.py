@@ -396,7 +396,8 @@ class UNCRTAINTS(nn.Module):
         return out
 
 
-_BACKEND = 3     # bit 0: tcgen05 bf16x3 forward/input-gradient GEMMs, bit 1: tcgen05 weight-gradient GEMMs; 0 = fp32 CUDA cores
+_BACKEND = 3     # bit 0: tcgen05 bf16x3 forward/input-gradient GEMMs, bit 1: tcgen05 weight-gradient GEMMs, bit 2: single-pass bf16
+                 # MMAs in those (7 = the reduced-precision "bf16 tensor-core path" of BASELINE config #3); 0 = fp32 CUDA cores
 
 
 def set_default_gemm_backend(backend: int) -> None:

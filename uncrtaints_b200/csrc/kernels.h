@@ -56,6 +56,7 @@ int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* 
 int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 int tc_set_warp_specialized(int on);
 int tc_set_split_epilogue(int on);
+int tc_set_single_pass(int on);
 int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 
 // dwconv.cu

@@ -347,6 +347,7 @@ int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const 
                          float* dw1, int N, int P, void* scratch, void* stream) {
     if (!x || !coef0 || !dz1 || !h1 || !bc1 || !dw1 || !scratch || P % 64) return UB_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    UB_TRY(tc_set_single_pass((backend & 4) != 0));
     if (backend & 2)
         return tc_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
                          static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
@@ -361,6 +362,7 @@ int ub200_gemm1_forward(int backend, const float* x, const float* coef, const fl
     if (!x || !coef || !w1 || !h1 || !stats || !scratch || P % 128) return UB_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(stats, 0, (size_t)N * UB_HID * 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
+    UB_TRY(tc_set_single_pass((backend & 4) != 0));
     if (backend & 1) {
         UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, st));
         return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, st);
@@ -461,6 +463,7 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
     if (ws_bytes < L.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = L.P;
+    UB_TRY(tc_set_single_pass((d->gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, L.fwd_zero_begin), 0, L.fwd_zero_end - L.fwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
 
     // in_conv: conv1x1 + norm + ReLU (+ pad-mask test), NCHW -> pixel-major
@@ -507,6 +510,7 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
     if (ws_bytes < L.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = L.P;
+    UB_TRY(tc_set_single_pass((d->gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, L.bwd_zero_begin), 0, L.bwd_zero_end - L.bwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     float* gA = at<float>(ws, L.gA);
     float* gB = at<float>(ws, L.gB);
@@ -626,6 +630,7 @@ int ub200_mbconv_forward(const float* x, const void* const* block_params, int N,
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = H * W;
+    UB_TRY(tc_set_single_pass((gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, M.zero_begin), 0, M.zero_end - M.zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     const int chunk = 256;
     colstats_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(x, at<double>(ws, M.w.stats0), P, chunk);
@@ -644,6 +649,7 @@ int ub200_mbconv_backward(const float* x, const void* const* block_params, const
     mb_layout(N, H, W, M);
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    UB_TRY(tc_set_single_pass((gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, M.bzero_begin), 0, M.bzero_end - M.bzero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     BlockCtx c = mb_ctx(M, block_params, block_grads, ws, N, H, W, groups, training, 1e-5f, 0.1f, gemm_backend, st);
     return mbconv_backward(c, x, dout, dx, at<float>(ws, M.dn0), at<float>(ws, M.du), at<float>(ws, M.dz1),
