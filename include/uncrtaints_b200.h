@@ -116,6 +116,11 @@ int ub200_tc_set_warp_specialized(int on);
 /* 1 (default): the epilogue (TMEM -> global, statistics) of tile t-1 is spread over the K-block steps of tile t in the forward
  * GEMMs (two parts; measured -9 % / -5 %); 0: one burst after the last K-block everywhere. */
 int ub200_tc_set_split_epilogue(int on);
+/* The input-gradient GEMM and the weight-gradient GEMM of a 1x1 convolution as the two roles of ONE launch (paired CTAs
+ * sweep the same tiles at the same time, so the shared activation tensors come from HBM once and from the L2 once):
+ * bit 0 = expand convolution (gemm1_bwd + wgrad1, measured -5 %), bit 1 = project convolution (gemm2_bwd + wgrad2, measured
+ * +6 %).  Default 0 (two launches). */
+int ub200_tc_set_dual(int mask);
 /* 1 (default): pointwise dh2 kernel + stencil kernel (6 tensor passes, measured faster); 0: fused depthwise-conv backward
  * kernel (4 tensor passes, kept for tuning). */
 int ub200_dwconv_set_bwd_split(int on);

@@ -546,3 +546,17 @@ def test_model_single_pass_bf16_backend(golden_weights):
                                  f"median grad rel_l2={sorted(gerr.values())[len(gerr) // 2]:.3e}"])
     assert e_out <= 5e-2 and e_loss <= 5e-2
     assert sorted(gerr.values())[len(gerr) // 2] <= 5e-2
+
+
+@pytest.mark.parametrize("mask", [1, 3])
+def test_mbconv_block_dual_role_gemm(golden_weights, mask):
+    """ub200_tc_set_dual: input-gradient and weight-gradient GEMMs of a 1x1 convolution as the two roles of one launch (paired
+    CTAs share their activation reads through the L2); same block check as the two-launch default."""
+    from uncrtaints_b200 import _lib
+    L = _lib.lib()
+    L.ub200_tc_set_dual(mask)
+    try:
+        _mbconv_block_vs_oracle(golden_weights, 4, 1, 3, True, (2, 64, 64), f",dual={mask}")
+        _mbconv_block_vs_oracle(golden_weights, 0, 1, 3, True, (3, 32, 64), f",dual={mask}")
+    finally:
+        L.ub200_tc_set_dual(0)

@@ -278,8 +278,8 @@ struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
 // converted, so HBM requests stay in flight across the convert / fence / barrier / MMA issue / epilogue of step q.
 // ------------------------------------------------------------------------------------------
 template <int K, int NOUT, class ALoad, class Epi, int PARTS>
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P, int single) {
+__device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __restrict__ wimg, const Epi& ep, int P, int single,
+                                             const int bx /* CTA index within the frame */, const int gx /* CTAs per frame */, const int n) {
     constexpr int KB = K / KBLK, MH = NOUT / 128;
     constexpr int W_BYTES = K * NOUT * 4;                 // hi image + lo image
     constexpr int W_HALF = K * NOUT * 2;
@@ -291,11 +291,11 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
     float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);     // 3 x K coefficients (SoA)
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * K);            // free[NSTAGE], accfull[2]
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + NSTAGE + 2);
-    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, n = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
     const int tiles_per_frame = P / TILE_PX;
-    const int t0 = (int)(((long long)blockIdx.x * tiles_per_frame) / gridDim.x);
-    const int t1 = (int)(((long long)(blockIdx.x + 1) * tiles_per_frame) / gridDim.x);
+    const int t0 = (int)(((long long)bx * tiles_per_frame) / gx);
+    const int t1 = (int)(((long long)(bx + 1) * tiles_per_frame) / gx);
     const int Q = (t1 - t0) * KB;                         // pipeline steps of this CTA
     // producer role: 16-byte chunk pc8 of rows pr and pr + 64
     const int pc8 = tid % 8, pr = tid / 8;
@@ -442,6 +442,12 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+template <int K, int NOUT, class ALoad, class Epi, int PARTS>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P, int single) {
+    gemm_tc_body<K, NOUT, ALoad, Epi, PARTS>(al, wimg, ep, P, single, (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -691,8 +697,9 @@ __device__ __forceinline__ uint64_t make_wg_desc(uint32_t saddr) {
 }
 
 template <class LA, class LB>
-__global__ void __launch_bounds__(THREADS, 1)
-wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long total_tiles, int sa, int sb, int single) {
+__device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float* __restrict__ dst /* this CTA's [128][256] partial */, int P,
+                                              const long long t0, const long long t1 /* 64-pixel tiles [t0, t1) of the whole tensor */,
+                                              int sa, int sb, int single) {
     extern __shared__ __align__(1024) char smem_raw[];
     char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     char* sStage = smem;                                                       // 2 x {A hi, A lo, B hi, B lo}
@@ -703,8 +710,6 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
     const int tiles_per_frame = P / WG_PX;
-    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
     const long long H = (t1 > t0 ? (t1 - t0) : 0) * 2;     // pipeline steps: half tiles of 32 pixel rows
     // producer role per half tile: one A item (row ra, chunk ca) and two B items (rows rb, rb+16; chunk cb)
     const int ra = tid / 16, ca = tid % 16, rb = tid / 32, cb = tid % 32;
@@ -797,7 +802,6 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
             }
         }
     }
-    float* dst = partial + (size_t)blockIdx.x * 128 * 256;
     if (H > 0) {
         mbar_wait(smem_u32(&sBar[2]), 0);
         tc_fence_after();
@@ -819,6 +823,37 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
 }
 
 template <class LA, class LB>
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long total_tiles, int sa, int sb, int single) {
+    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
+    wgrad_tc_body<LA, LB>(la, lb, partial + (size_t)blockIdx.x * 128 * 256, P, t0, t1, sa, sb, single);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dual-role kernel: the input-gradient GEMM and the weight-gradient GEMM of one 1x1 convolution read the SAME activation
+// tensors (dOut, y, h2 for conv2; dz1, h1, x for conv1).  Launched back to back they stream those tensors from HBM twice
+// (the 126 MB L2 cannot hold 1-3 GB between the launches).  Here both run in ONE launch: grid (2G, N), CTA 2p of a frame
+// is the input-gradient role and CTA 2p+1 the weight-gradient role of the same tile range, so the hardware schedules the
+// two roles of a pair back to back on two SMs and they sweep the same ~14 tiles at the same time: whichever role touches
+// a line first pays the HBM access, the other one hits the L2 (and, being faster for it, catches up: the pair keeps itself
+// within a tile or two without any explicit synchronisation).  Partials: one [128][256] slot per weight-gradient CTA.
+// ------------------------------------------------------------------------------------------
+template <int K, int NOUT, class ALoad, class Epi, int PARTS, class LA, class LB>
+__global__ void __launch_bounds__(THREADS, 1)
+dual_tc_kernel(ALoad al, const uint4* __restrict__ wimg, Epi ep, LA la, LB lb, float* __restrict__ partial, int P, int sa, int sb, int single) {
+    const int pair = (int)blockIdx.x >> 1, G = (int)gridDim.x >> 1, n = (int)blockIdx.y;
+    if ((blockIdx.x & 1) == 0) {
+        gemm_tc_body<K, NOUT, ALoad, Epi, PARTS>(al, wimg, ep, P, single, pair, G, n);
+    } else {
+        const int tiles_per_frame = P / TILE_PX;
+        const long long g0 = ((long long)pair * tiles_per_frame) / G, g1 = ((long long)(pair + 1) * tiles_per_frame) / G;
+        const long long base = (long long)n * (P / WG_PX);
+        wgrad_tc_body<LA, LB>(la, lb, partial + ((size_t)n * G + pair) * 128 * 256, P, base + 2 * g0, base + 2 * g1, sa, sb, single);
+    }
+}
+
+template <class LA, class LB>
 static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb, int* nparts, cudaStream_t st) {
     if (P % WG_PX != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)2 * WG_STAGE + 3 * 384 * sizeof(float) + 3 * 8 + 16 + 1024;
@@ -833,6 +868,34 @@ static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, i
     kern<<<blocks, THREADS, smem, st>>>(la, lb, partial, P, total, sa, sb, g_single_pass);
     UB_CHECK_LAUNCH();
     *nparts = blocks;
+    return UB_OK;
+}
+
+// tc_set_dual(): bit 0 = the expand convolution's pair (gemm1_bwd + wgrad1) shares one launch, bit 1 = the project convolution's
+// pair (gemm2_bwd + wgrad2).  Measured at N=16 / N=48 frames: conv1 pair 1.234 -> 1.167 ms / 3.635 -> 3.452 ms (-5 %), conv2 pair
+// 1.256 -> 1.349 ms / 3.639 -> 3.854 ms (+6 %: both of its roles evaluate the GELU per element and are bound by their own SM, so
+// halving the SMs per role costs more than the shared reads save).  Default 0: the 1 % it buys per step is inside the box-to-box
+// noise, and bench.py's per-kernel roofline stays one kernel = one role.
+static int g_dual = 0;
+template <int K, int NOUT, class ALoad, class Epi, class LA, class LB>
+static int launch_dual(ALoad al, const void* wimg, Epi ep, LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb,
+                       int* nparts, cudaStream_t st) {
+    if (P % TILE_PX != 0) return UB_ERR_ARG;
+    constexpr size_t smem_g = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + 8 * 8 + 16 + 1024;
+    constexpr size_t smem_w = (size_t)2 * WG_STAGE + 3 * 384 * sizeof(float) + 3 * 8 + 16 + 1024;
+    constexpr size_t smem = smem_g > smem_w ? smem_g : smem_w;
+    auto kern = dual_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS, LA, LB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
+        attr_set = true;
+    }
+    const int tiles = P / TILE_PX;
+    const int G = blocks_per_frame(N, tiles);
+    if (G * N > max_parts) return UB_ERR_WORKSPACE;
+    kern<<<dim3(2 * G, N), THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, la, lb, partial, P, sa, sb, g_single_pass);
+    UB_CHECK_LAUNCH();
+    *nparts = G * N;
     return UB_OK;
 }
 
@@ -900,6 +963,34 @@ int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* 
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
 }
+// Dual-role launches (see dual_tc_kernel): input gradient + weight gradient of one 1x1 convolution in one kernel.
+int tc_gemm2_bwd_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
+                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
+                        float* dw2, int N, int P, cudaStream_t st) {
+    tc::TLoadNormBwd al{dout, y, bc3};
+    tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
+    tc::TLoadNormBwd la{dout, y, bc3};
+    tc::TLoadGeluGate lb{h2, coef2, gate};
+    int nparts = 0;
+    int rc = tc::launch_dual<UB_WIDTH, UB_HID>(al, w2timg, ep, la, lb, partial, max_parts, N, P, UB_HID, 1, &nparts, st);
+    if (rc != UB_OK) return rc;
+    return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
+}
+int tc_gemm1_bwd_wgrad1(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
+                        int P, cudaStream_t st) {
+    tc::TLoadNormBwd al{dz1, h1, bc1};
+    tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
+    tc::TLoadNormed la{x, coef0};
+    tc::TLoadNormBwd lb{dz1, h1, bc1};
+    int nparts = 0;
+    int rc = tc::launch_dual<UB_HID, UB_WIDTH>(al, w1timg, ep, la, lb, partial, max_parts, N, P, 1, UB_WIDTH, &nparts, st);
+    if (rc != UB_OK) return rc;
+    return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
+}
+int tc_dual_parts(int N, int P) { return tc::blocks_per_frame(N, P / tc::TILE_PX) * N; }
+int tc_set_dual(int mask) { tc::g_dual = mask & 3; return UB_OK; }
+int tc_dual_enabled() { return tc::g_dual; }
 int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
     if (cudaMemcpyToSymbol(tc::c_wg_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
     if (cudaMemcpyToSymbol(tc::c_wg_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;

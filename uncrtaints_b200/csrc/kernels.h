@@ -57,6 +57,15 @@ int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 int tc_set_warp_specialized(int on);
 int tc_set_split_epilogue(int on);
 int tc_set_single_pass(int on);
+int tc_gemm2_bwd_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
+                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
+                        float* dw2, int N, int P, cudaStream_t st);
+int tc_gemm1_bwd_wgrad1(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
+                        int P, cudaStream_t st);
+int tc_dual_parts(int N, int P);
+int tc_set_dual(int on);
+int tc_dual_enabled();
 int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
 
 // dwconv.cu

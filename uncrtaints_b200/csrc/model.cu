@@ -78,7 +78,7 @@ struct BlockWs {
 };
 
 struct Layout {
-    int Ne, B, P, nblk, Nmax;
+    int Ne, B, P, nblk, Nmax, max_parts;
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
     size_t bstats_in, bc_in, mom_in, gram_in;
@@ -169,12 +169,16 @@ static int make_layout(const ub200_desc* d, Layout& L) {
         L.dn0 = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
         L.du = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
         L.dz1 = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
-        L.partial = b.take((size_t)MAX_PARTS * UB_WIDTH * UB_HID * sizeof(float));
+        L.max_parts = MAX_PARTS;
+        if (tc_dual_parts(L.Ne, L.P) > L.max_parts) L.max_parts = tc_dual_parts(L.Ne, L.P);
+        if (tc_dual_parts(L.B, L.P) > L.max_parts) L.max_parts = tc_dual_parts(L.B, L.P);
+        L.partial = b.take((size_t)L.max_parts * UB_WIDTH * UB_HID * sizeof(float));
         L.dwup = b.take((size_t)UB_HEADS * L.Ne * P * sizeof(float));
         L.dattn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
         L.dpooled = b.take((size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * sizeof(float));
     } else {
         L.gA = L.gB = L.dn0 = L.du = L.dz1 = L.partial = L.dwup = L.dattn = L.dpooled = 0;
+        L.max_parts = 0;
     }
     L.total = b.off;
     return UB_OK;
@@ -192,6 +196,7 @@ struct BlockCtx {
     const BlockWs* w;
     void* ws;
     int N, H, W, groups, training, backend;
+    int max_parts = MAX_PARTS;      // [128][256] slots available in the weight-gradient partial buffer
     float eps, momentum;
     cudaStream_t st;
 };
@@ -255,13 +260,20 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
     const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
-    if (tcb)
+    const bool dual_ok = tcb && tcw && tc_dual_parts(c.N, P) <= c.max_parts;
+    const bool dual2 = dual_ok && (tc_dual_enabled() & 2), dual1 = dual_ok && (tc_dual_enabled() & 1);
+    if (dual2)
+        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
+                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), at<float>(ws, w.gate), partial,
+                              c.max_parts, gf(c.g, UB200_B_W2), c.N, P, c.st));
+    else if (tcb)
         UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
     else
         UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    if (tcw)
+    if (dual2) {
+    } else if (tcw)
         UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                            at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
     else
@@ -275,13 +287,17 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    if (tcb)
+    if (dual1)
+        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_wgrad1(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
+                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, c.max_parts, gf(c.g, UB200_B_W1), c.N, P, c.st));
+    else if (tcb)
         UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
     else
         UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
-    if (tcw)
+    if (dual1) {
+    } else if (tcw)
         UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, c.st));
     else
@@ -336,6 +352,7 @@ unsigned long long ub200_launch_count(void) { return g_launch_count; }
 int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
 int ub200_tc_set_warp_specialized(int on) { return tc_set_warp_specialized(on); }
 int ub200_tc_set_split_epilogue(int on) { return tc_set_split_epilogue(on); }
+int ub200_tc_set_dual(int mask) { return tc_set_dual(mask); }
 int ub200_dwconv_set_bwd_split(int on) { return dwconv_set_bwd_split(on); }
 int ub200_dwconv_set_mode(int mode) { return dwconv_set_mode(mode); }
 int ub200_inconv_set_moments(int on) { g_inconv_moments = on ? 1 : 0; return UB_OK; }
@@ -451,6 +468,7 @@ static BlockCtx make_ctx(const ub200_desc* d, const Layout& L, int i, const void
     c.training = d->training;
     c.backend = d->gemm_backend;
     c.eps = d->norm_eps; c.momentum = d->bn_momentum;
+    c.max_parts = L.max_parts > 0 ? L.max_parts : MAX_PARTS;
     c.st = st;
     return c;
 }
@@ -594,7 +612,7 @@ int ub200_head_backward(const float* grad_out, const float* out, const float* de
 }
 
 // ---- standalone MBConv block (tests) -------------------------------------------------------------------
-struct MbLayout { BlockWs w; size_t zero_begin, zero_end, bzero_begin, bzero_end, dn0, du, dz1, partial, total; };
+struct MbLayout { BlockWs w; size_t zero_begin, zero_end, bzero_begin, bzero_end, dn0, du, dz1, partial, total; int max_parts; };
 static void mb_layout(int N, int H, int W, MbLayout& M) {
     Bump b;
     M.zero_begin = b.off;
@@ -607,7 +625,8 @@ static void mb_layout(int N, int H, int W, MbLayout& M) {
     M.dn0 = b.take((size_t)N * H * W * UB_WIDTH * 4);
     M.du = b.take((size_t)N * H * W * UB_HID * 4);
     M.dz1 = b.take((size_t)N * H * W * UB_HID * 4);
-    M.partial = b.take((size_t)MAX_PARTS * UB_WIDTH * UB_HID * 4);
+    M.max_parts = tc_dual_parts(N, H * W) > MAX_PARTS ? tc_dual_parts(N, H * W) : MAX_PARTS;
+    M.partial = b.take((size_t)M.max_parts * UB_WIDTH * UB_HID * 4);
     M.total = b.off;
 }
 size_t ub200_mbconv_workspace_bytes(int N, int H, int W) {
@@ -620,6 +639,7 @@ static BlockCtx mb_ctx(const MbLayout& M, const void* const* p, void* const* g, 
     BlockCtx c;
     c.p = p; c.g = g; c.w = &M.w; c.ws = ws; c.N = N; c.H = H; c.W = W; c.groups = groups; c.training = training;
     c.backend = backend; c.eps = eps; c.momentum = momentum; c.st = st;
+    c.max_parts = M.max_parts;
     return c;
 }
 int ub200_mbconv_forward(const float* x, const void* const* block_params, int N, int H, int W, int groups, int training,
