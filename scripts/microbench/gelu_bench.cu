@@ -4,31 +4,11 @@
 #include <cuda_runtime.h>
 #include "../../uncrtaints_b200/csrc/common.cuh"
 using namespace ub;
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-
+typedef f32x2_t u64;
+__device__ __forceinline__ u64 pk(float a, float b) { return pack2(a, b); }
+__device__ __forceinline__ void upk(u64 v, float& a, float& b) { unpack2(v, a, b); }
 __device__ __forceinline__ void gelu_both2(float x0, float x1, float& g0, float& g1, float& p0, float& p1) {
-    const float t0 = fast_rcp(fmaf(0.23164189f, fabsf(x0), 1.0f)), t1 = fast_rcp(fmaf(0.23164189f, fabsf(x1), 1.0f));
-    const u64 t = pk(t0, t1), x = pk(x0, x1);
-    u64 poly = fma2(t, pk(0.5f * 1.061405429f, 0.5f * 1.061405429f), pk(0.5f * -1.453152027f, 0.5f * -1.453152027f));
-    poly = fma2(t, poly, pk(0.5f * 1.421413741f, 0.5f * 1.421413741f));
-    poly = fma2(t, poly, pk(0.5f * -0.284496736f, 0.5f * -0.284496736f));
-    poly = fma2(t, poly, pk(0.5f * 0.254829592f, 0.5f * 0.254829592f));
-    const u64 xs = mul2(x, pk(-0.72134752f, -0.72134752f));
-    float a0, a1;
-    upk(mul2(xs, x), a0, a1);
-    const float e0 = fast_ex2(a0), e1 = fast_ex2(a1);
-    const u64 e = pk(e0, e1);
-    float q0, q1;
-    upk(mul2(mul2(t, poly), e), q0, q1);
-    const float c0 = x0 >= 0.f ? 1.0f - q0 : q0, c1 = x1 >= 0.f ? 1.0f - q1 : q1;
-    const u64 cdf = pk(c0, c1);
-    upk(mul2(x, cdf), g0, g1);
-    upk(fma2(mul2(x, pk(0.39894228f, 0.39894228f)), e, cdf), p0, p1);
+    gelu_pair<true, true>(x0, x1, g0, g1, p0, p1);
 }
 
 template <int MODE>
@@ -44,6 +24,12 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float seed) {
         } else if (MODE == 1) {
 #pragma unroll
             for (int i = 0; i < 8; i += 2) { float g0, g1, p0, p1; gelu_both2(v[i], v[i + 1], g0, g1, p0, p1); acc += g0 * p0 + g1 * p1; v[i] = v[i] * 0.999f + 0.001f; v[i + 1] = v[i + 1] * 0.999f + 0.001f; }
+        } else if (MODE == 4) {      // value-only, scalar two-MUFU form
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc += gelu_f(v[i]); v[i] = v[i] * 0.999f + 0.001f; }
+        } else if (MODE == 5) {      // value-only, packed single-MUFU exp-polynomial form
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) { float g0, g1; gelu_val_pair(v[i], v[i + 1], g0, g1); acc += g0 + g1; v[i] = v[i] * 0.999f + 0.001f; v[i + 1] = v[i + 1] * 0.999f + 0.001f; }
         } else if (MODE == 2) {      // plain FFMA chains: 8 independent
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -84,6 +70,7 @@ void run(const char* name, int ctas_per_sm, double elems_per_iter) {
 }
 int main() {
     for (int c : {1, 2, 4}) {
+        run<4>("gelu value, 2 MUFU scalar", c, 8); run<5>("gelu value, 1 MUFU packed", c, 8);
         if (c == 1) { run<0>("gelu_both scalar", 1, 8); run<1>("gelu_both packed f32x2", 1, 8); run<2>("FFMA (fma count)", 1, 128); run<3>("FFMA2 (fma count)", 1, 128); }
         if (c == 2) { run<0>("gelu_both scalar", 2, 8); run<1>("gelu_both packed f32x2", 2, 8); run<2>("FFMA (fma count)", 2, 128); run<3>("FFMA2 (fma count)", 2, 128); }
         if (c == 4) { run<0>("gelu_both scalar", 4, 8); run<1>("gelu_both packed f32x2", 4, 8); run<2>("FFMA (fma count)", 4, 128); run<3>("FFMA2 (fma count)", 4, 128); }

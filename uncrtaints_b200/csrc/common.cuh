@@ -97,15 +97,35 @@ __device__ __forceinline__ void gelu_pair(float x0, float x1, float& g0, float& 
     if (WANT_G) unpack2(mul2(x, cdf), g0, g1);
     if (WANT_GP) unpack2(fma2(mul2(x, pack2(0.39894228040143267794f, 0.39894228040143267794f)), e, cdf), p0, p1);
 }
+// Value-only GELU with ONE MUFU per value: 0.5 * erfc(|x| / sqrt(2)) = 2^(P(|x|) - 1) with a degree-8 polynomial P (least-squares
+// fit of log2(erfc) weighted by erfc on [0, 6.22], coefficients folded for |x|; max |error| of Phi 4e-8, of gelu 6e-7 over
+// [-8, 8] in fp32 -- the fp32 rounding of x * Phi itself).  The exact-erf GELU of gelu_pair costs two MUFU (rcp + ex2) and is
+// MUFU-bound at ~6 values/clk/SM; the loaders that only need the value use this form: 8 FFMA2 + 2 ex2 per pair.
+__device__ __forceinline__ void gelu_val_pair(float x0, float x1, float& g0, float& g1) {
+    const float a0 = fminf(fabsf(x0), 6.2225397f), a1 = fminf(fabsf(x1), 6.2225397f);
+    const f32x2_t a = pack2(a0, a1);
+    f32x2_t p = fma2(a, pack2(-2.763850034e-06f, -2.763850034e-06f), pack2(3.850608118e-05f, 3.850608118e-05f));
+    p = fma2(a, p, pack2(-1.819549361e-04f, -1.819549361e-04f));
+    p = fma2(a, p, pack2(-1.473483862e-04f, -1.473483862e-04f));
+    p = fma2(a, p, pack2(7.077381015e-03f, 7.077381015e-03f));
+    p = fma2(a, p, pack2(-5.250628293e-02f, -5.250628293e-02f));
+    p = fma2(a, p, pack2(-4.592045248e-01f, -4.592045248e-01f));
+    p = fma2(a, p, pack2(-1.151105762e+00f, -1.151105762e+00f));
+    p = fma2(a, p, pack2(-1.0f + 2.239119468e-08f, -1.0f + 2.239119468e-08f));      // c0 - 1: the factor 0.5
+    float p0, p1;
+    unpack2(p, p0, p1);
+    const float h0 = fast_ex2(p0), h1 = fast_ex2(p1);                                  // Phi(-|x|)
+    unpack2(mul2(pack2(x0, x1), pack2(x0 >= 0.f ? 1.0f - h0 : h0, x1 >= 0.f ? 1.0f - h1 : h1)), g0, g1);
+}
 // float4 front ends: v = x * scale + shift first (packed as well)
 __device__ __forceinline__ void gelu_both4_packed(const float4 z, float4& g, float4& gp) {
     gelu_pair<true, true>(z.x, z.y, g.x, g.y, gp.x, gp.y);
     gelu_pair<true, true>(z.z, z.w, g.z, g.w, gp.z, gp.w);
 }
 __device__ __forceinline__ float4 gelu4_packed(const float4 z) {
-    float4 g; float d0, d1;
-    gelu_pair<true, false>(z.x, z.y, g.x, g.y, d0, d1);
-    gelu_pair<true, false>(z.z, z.w, g.z, g.w, d0, d1);
+    float4 g;
+    gelu_val_pair(z.x, z.y, g.x, g.y);
+    gelu_val_pair(z.z, z.w, g.z, g.w);
     return g;
 }
 __device__ __forceinline__ float4 gelu_grad4_packed(const float4 z) {

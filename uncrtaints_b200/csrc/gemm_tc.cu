@@ -182,9 +182,9 @@ struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
     }
     __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {          // packed f32x2 GELU: 4 pairs
-            float g0, g1, d0, d1;
-            gelu_pair<true, false>(fmaf(r.a[i], c.sc[i], c.sh[i]), fmaf(r.a[i + 1], c.sc[i + 1], c.sh[i + 1]), g0, g1, d0, d1);
+        for (int i = 0; i < 8; i += 2) {          // packed f32x2 single-MUFU GELU: 4 pairs
+            float g0, g1;
+            gelu_val_pair(fmaf(r.a[i], c.sc[i], c.sh[i]), fmaf(r.a[i + 1], c.sc[i + 1], c.sh[i + 1]), g0, g1);
             v[i] = g0 * c.g[i];
             v[i + 1] = g1 * c.g[i + 1];
         }
