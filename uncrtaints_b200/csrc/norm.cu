@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) residual_fwd_kernel(const float* __restri
     const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     const size_t base = (size_t)n * P * C + c4 * 4;
+#pragma unroll 4
     for (int p = p0 + r; p < p1; p += ROWS) {
         const float4 xv = ld4_stream(x + base + (size_t)p * C);
         const float4 yv = ld4_stream(y + base + (size_t)p * C);
@@ -209,9 +210,10 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __rest
     const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     const size_t base = (size_t)n * P * C + c4 * 4;
+#pragma unroll 4
     for (int p = p0 + r; p < p1; p += ROWS) {
-        const float4 d = ld4(dy + base + (size_t)p * C);
-        const float4 w = ld4(v + base + (size_t)p * C);
+        const float4 d = ld4_stream(dy + base + (size_t)p * C);
+        const float4 w = ld4_stream(v + base + (size_t)p * C);
         s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
         q.x += d.x * (w.x - m0.mean) * m0.rstd;
         q.y += d.y * (w.y - m1.mean) * m1.rstd;
