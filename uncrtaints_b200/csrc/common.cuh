@@ -154,8 +154,9 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // streaming (read-once / write-once) variants: keep L1 for the reused weights and coefficients
 __device__ __forceinline__ float4 ld4_stream(const float* p) {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    // not volatile: .nc data is read-only for the whole kernel, so the compiler may hoist and batch these loads
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st4_stream(float* p, float4 v) {
