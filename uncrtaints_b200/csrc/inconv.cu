@@ -262,7 +262,8 @@ __global__ void inconv_stats_from_moments_kernel(const double* __restrict__ mom,
 }
 
 // gram pass of the backward: gacc[n][o][ci] += sum_p dgn[p][o] x[p][ci], gacc[n][o][16] += sum_p dgn[p][o],
-// dgn = dX0 * [x0 > 0] (the ReLU mask is read off the saved forward output).  lane = 4 output channels, warp = pixels.
+// dgn = dX0 * [x0 > 0]: either read off the saved forward output x0, or (x0 == nullptr) already applied by the encoder block's
+// residual_bwd, which loads x0 anyway.  lane = 4 output channels, warp = pixels.
 __global__ void __launch_bounds__(256, 2) inconv_bwd_gram_kernel(const float* __restrict__ x /* [N][Cin][P] */, const float* __restrict__ x0,
                                                                const float* __restrict__ dx0, double* gacc, int Cin, int P, int chunk) {
     constexpr int C = UB_WIDTH;
@@ -295,8 +296,13 @@ __global__ void __launch_bounds__(256, 2) inconv_bwd_gram_kernel(const float* __
                 d[j] = make_float4(0, 0, 0, 0);
                 if (pb + px0 + j < p1) {
                     const size_t row = ((size_t)n * P + pb + px0 + j) * C + lane * 4;
-                    const float4 g = ld4_stream(dx0 + row), o = ld4_stream(x0 + row);
-                    d[j] = make_float4(o.x > 0.f ? g.x : 0.f, o.y > 0.f ? g.y : 0.f, o.z > 0.f ? g.z : 0.f, o.w > 0.f ? g.w : 0.f);
+                    const float4 g = ld4_stream(dx0 + row);
+                    if (x0 != nullptr) {          // dx0 not yet masked by the ReLU of in_conv
+                        const float4 o = ld4_stream(x0 + row);
+                        d[j] = make_float4(o.x > 0.f ? g.x : 0.f, o.y > 0.f ? g.y : 0.f, o.z > 0.f ? g.z : 0.f, o.w > 0.f ? g.w : 0.f);
+                    } else {
+                        d[j] = g;
+                    }
                 }
                 s.x += d[j].x; s.y += d[j].y; s.z += d[j].z; s.w += d[j].w;
             }

@@ -23,7 +23,7 @@ int launch_se_pool(const float* h2, const Coef* coef2, const MeanRstd* mr2, doub
                    int P, cudaStream_t st);
 int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
 int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
-                        cudaStream_t st);
+                        int relu_mask, cudaStream_t st);
 
 // gemm_simt.cu
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);

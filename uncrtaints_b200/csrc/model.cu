@@ -197,6 +197,7 @@ struct BlockCtx {
     void* ws;
     int N, H, W, groups, training, backend;
     int max_parts = MAX_PARTS;      // [128][256] slots available in the weight-gradient partial buffer
+    int relu_mask_dx = 0;           // backward: multiply dX by [x > 0] (the block input is in_conv's ReLU output)
     float eps, momentum;
     cudaStream_t st;
 };
@@ -304,7 +305,7 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
         UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
-    UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.st));
+    UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.relu_mask_dx, c.st));
     return UB_OK;
 }
 
@@ -556,10 +557,11 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
                            d->norm_eps, st));
     UB_PROF(KID_TEMPORAL_BWD, st, launch_maxpool_bwd(at<float>(ws, L.dpooled), at<int>(ws, L.pool_idx), gB, L.Ne, P, st));
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
+    enc.relu_mask_dx = g_inconv_moments;      // the gram pass then consumes dgn = dX0 * [x0 > 0] directly
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
     // in_conv backward (no input gradient)
     if (g_inconv_moments)
-        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, at<float>(ws, L.x0), gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
+        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, nullptr /* ReLU mask already applied by residual_bwd */, gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
                                    at<MeanRstd>(ws, L.mr_in), at<double>(ws, L.gram_in), at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
     else
         UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),

@@ -226,9 +226,11 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------
 // B1: dX = dOut + (a0*dn0 + b0*x + c0)   (residual + PreNorm backward).  C = 128.
 // ------------------------------------------------------------------------------------------
+// relu_mask != 0 (encoder block only: its input x is the ReLU output of in_conv): dx is also multiplied by [x > 0], i.e. the
+// ReLU backward of in_conv is applied here, where x is loaded anyway, and the in_conv gram pass need not read x0 again.
 __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dn0,
                                                             const float* __restrict__ x, const BCoef* __restrict__ bc0,
-                                                            float* __restrict__ dx, int P, int chunk) {
+                                                            float* __restrict__ dx, int P, int chunk, int relu_mask) {
     constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
     const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
     const BCoef k0 = bc0[(size_t)n * C + c4 * 4 + 0], k1 = bc0[(size_t)n * C + c4 * 4 + 1],
@@ -244,6 +246,10 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
         o.y = g.y + fmaf(k1.a, d.y, fmaf(k1.b, xv.y, k1.c));
         o.z = g.z + fmaf(k2.a, d.z, fmaf(k2.b, xv.z, k2.c));
         o.w = g.w + fmaf(k3.a, d.w, fmaf(k3.b, xv.w, k3.c));
+        if (relu_mask) {
+            o.x = xv.x > 0.f ? o.x : 0.f; o.y = xv.y > 0.f ? o.y : 0.f;
+            o.z = xv.z > 0.f ? o.z : 0.f; o.w = xv.w > 0.f ? o.w : 0.f;
+        }
         st4(dx + base + (size_t)p * C, o);
     }
 }
@@ -290,9 +296,9 @@ int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, d
     return UB_OK;
 }
 int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
-                        cudaStream_t st) {
+                        int relu_mask, cudaStream_t st) {
     const int chunk = chunk_for(P);
-    residual_bwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk);
+    residual_bwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk, relu_mask);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
