@@ -55,9 +55,11 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, const flo
         var = q / cnt - mean * mean;
     } else if (training) {
         double s = 0.0, q = 0.0;
-        for (int j = 0; j < N; ++j) {
-            s += stats[((size_t)j * C + c) * 2 + 0];
-            q += stats[((size_t)j * C + c) * 2 + 1];
+#pragma unroll 8
+        for (int j = 0; j < N; ++j) {             // independent loads: batch them, the sum is latency-bound otherwise
+            const double2 v = *reinterpret_cast<const double2*>(&stats[((size_t)j * C + c) * 2]);
+            s += v.x;
+            q += v.y;
         }
         const double cnt = count * N;
         mean = s / cnt;
@@ -107,9 +109,11 @@ __global__ void norm_finalize_bwd_kernel(const double* __restrict__ bstats, cons
     }
     double sdy = 0.0, sdyx = 0.0;
     if (groups == 0 || n == 0) {
+#pragma unroll 8
         for (int j = 0; j < N; ++j) {
-            sdy += bstats[((size_t)j * C + c) * 2 + 0];
-            sdyx += bstats[((size_t)j * C + c) * 2 + 1];
+            const double2 v = *reinterpret_cast<const double2*>(&bstats[((size_t)j * C + c) * 2]);
+            sdy += v.x;
+            sdyx += v.y;
         }
     }
     if (groups == 0 && training) {
