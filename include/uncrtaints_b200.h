@@ -181,6 +181,14 @@ int ub200_mgnll_forward(const float* pred, long long pred_sb, const float* targe
                         long long var_sb, int var_ch, int B, int P, float eps, float* loss, float* dpred, float* dvar,
                         int* neg_flag, void* scratch, void* stream);
 
+/* GaussianNLLLoss.forward -> gaussian_nll_loss (model/src/losses.py:46-128,222-284; `--loss GNLL`, covmode 'uni'), reduction='mean':
+ *   loss = mean over all B*13*P elements of 1/2 (log v + (pred - target)^2 / v) (+ 1/2 log(2 pi) if full), v = max(var, eps) with
+ *   identity gradient.  pred/target/var as in ub200_mgnll_forward with 13 variance planes; dpred/dvar [B][13][P] (NULL to skip);
+ *   var_out [B][13][P] = the clamped variance, the reference's second return value (NULL to skip); scratch: 16 bytes. */
+int ub200_gnll_forward(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
+                       long long var_sb, int B, int P, float eps, int full, float* loss, float* dpred, float* dvar, float* var_out,
+                       int* neg_flag, void* scratch, void* stream);
+
 /* out[i] = in[i] * grad_loss[0]  (chain rule with the upstream gradient of the scalar loss). */
 int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, size_t n, void* stream);
 

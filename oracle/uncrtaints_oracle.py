@@ -369,6 +369,28 @@ def mgnll(pred: torch.Tensor, target: torch.Tensor, var: torch.Tensor, mode: str
     return loss
 
 
+def gnll(pred: torch.Tensor, target: torch.Tensor, var: torch.Tensor, full: bool = True, eps: float = 1e-8,
+         reduction: str = "mean"):
+    """gaussian_nll_loss (losses.py:46-128), heteroscedastic case: 1/2 (log v + e^2 / v) [+ 1/2 log(2 pi)], v = var clamped to
+    eps without a gradient of the clamp (:108-111); returns (loss, clamped var) like the reference (:122-128)."""
+    import math
+    if var.size() != pred.size():
+        raise ValueError("var is of incorrect size")
+    if reduction not in ("none", "mean", "sum"):
+        raise ValueError(reduction + " is not valid")
+    if torch.any(var < 0):
+        raise ValueError("var has negative entry/entries")
+    v = var + (torch.clamp(var, min=eps) - var).detach()
+    loss = 0.5 * (torch.log(v) + (pred - target) ** 2 / v)
+    if full:
+        loss = loss + 0.5 * math.log(2 * math.pi)
+    if reduction == "mean":
+        return loss.mean(), v
+    if reduction == "sum":
+        return loss.sum(), v
+    return loss, v
+
+
 def covariance(var: torch.Tensor, mode: str = "diag", eps: float = 1e-8) -> torch.Tensor:
     """Second return value of the loss (losses.py:145,211): diag_embed of the clamped
     variance, [B,1,13,13,H,W]."""
@@ -499,13 +521,16 @@ def init_params(cfg: OracleConfig, seed: int = 1) -> Dict[str, torch.Tensor]:
     return p
 
 
-def step(p: Dict[str, torch.Tensor], x, y, dates, cfg: OracleConfig, training=True, keep_mask=None):
-    """One fwd + MGNLL + bwd of the oracle.  Returns (out, loss, grads dict, new BN buffers)."""
+def step(p: Dict[str, torch.Tensor], x, y, dates, cfg: OracleConfig, training=True, keep_mask=None, loss_name: str = "MGNLL"):
+    """One fwd + loss (MGNLL, or GNLL for `--loss GNLL`) + bwd of the oracle.  Returns (out, loss, grads dict, new BN buffers)."""
     leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
             for k, v in p.items()}
     new_buffers: dict = {}
     out = forward(leaf, x, dates, cfg, training, keep_mask, new_buffers)
-    loss = mgnll(out[:, :, :S2_BANDS], y, out[:, :, S2_BANDS:S2_BANDS + cfg.covar_dim], cfg.covmode)
+    if loss_name == "GNLL":
+        loss, _ = gnll(out[:, :, :S2_BANDS], y, out[:, :, S2_BANDS:S2_BANDS + cfg.covar_dim], full=True)
+    else:
+        loss = mgnll(out[:, :, :S2_BANDS], y, out[:, :, S2_BANDS:S2_BANDS + cfg.covar_dim], cfg.covmode)
     names = [k for k, v in leaf.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)
     gd = {k: (g if g is not None else torch.zeros_like(leaf[k])) for k, g in zip(names, grads)}

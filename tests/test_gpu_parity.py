@@ -560,3 +560,43 @@ def test_mbconv_block_dual_role_gemm(golden_weights, mask):
         _mbconv_block_vs_oracle(golden_weights, 0, 1, 3, True, (3, 32, 64), f",dual={mask}")
     finally:
         L.ub200_tc_set_dual(0)
+
+
+def test_golden_gnll():
+    """GaussianNLLLoss (`--loss GNLL`, covmode 'uni') on the CUDA path against the fixture generated from the reference."""
+    import uncrtaints_b200 as ub
+    c = load_npz("case_gnll.npz")
+    pred = torch.from_numpy(c["pred"]).cuda().requires_grad_(True)
+    var = torch.from_numpy(c["var"]).cuda().requires_grad_(True)
+    targ = torch.from_numpy(c["target"]).cuda()
+    loss, vout = ub.GaussianNLLLoss(reduction="mean", eps=1e-8, full=True)(pred, targ, var)
+    (2.0 * loss).backward()
+    assert abs(loss.item() - float(c["loss"])) / abs(float(c["loss"])) <= 1e-4
+    assert rel_l2(pred.grad / 2, torch.from_numpy(c["dpred"])) <= TOL
+    assert rel_l2(var.grad / 2, torch.from_numpy(c["dvar"])) <= TOL
+    assert rel_l2(vout, torch.from_numpy(c["var_out"])) <= 1e-6
+    with pytest.raises(ValueError, match="var has negative entry/entries"):
+        ub.GaussianNLLLoss()(pred.detach(), targ, -var.detach())
+    with pytest.raises(ValueError, match="var is of incorrect size"):
+        ub.GaussianNLLLoss()(pred.detach(), targ, var.detach()[:, :, :5])
+
+
+def test_uni_covmode_model_with_gnll(golden_weights):
+    """covmode='uni' end to end (13 variance planes, `--loss GNLL`): outputs, loss and gradients against the oracle."""
+    import uncrtaints_b200 as ub
+    B, T, H, W = 1, 2, 64, 64
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=31)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=32)
+    cfg = O.OracleConfig(covmode="uni")
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in golden_weights.items()}
+    o_out, o_loss, o_grads, _ = O.step(p64, x.double(), y.double(), d.double(), cfg, True, keep, loss_name="GNLL")
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", covmode="uni", scale_by=10.0)
+    net.load_state_dict({k: v.clone() for k, v in golden_weights.items()}, strict=True)
+    net = net.cuda().train()
+    net._injected_keep_mask = keep.to(torch.uint8)
+    out = net(x.cuda(), batch_positions=d.cuda())
+    loss, vout = ub.GaussianNLLLoss(reduction="mean", eps=1e-8, full=True)(out[:, :, :13], y.cuda(), out[:, :, 13:26])
+    loss.backward()
+    assert vout.shape == (B, 1, 13, H, W)
+    assert rel_l2(out, o_out) <= TOL and abs(loss.item() - o_loss.item()) / abs(o_loss.item()) <= TOL
+    check_grads(net.named_parameters(), o_grads, "uni+gnll")

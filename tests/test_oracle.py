@@ -168,3 +168,35 @@ def test_oracle_calibration_sweep_matches_golden(mode):
     # the restated metric also agrees with the reference's on its own golden inputs
     uce2, auce2 = O.compute_uce_auce(c[f"{mode}.mean_var"], c[f"{mode}.error"], S)
     assert abs(uce2 - float(c[f"{mode}.uce"])) < 1e-7 and abs(auce2 - float(c[f"{mode}.auce"])) < 1e-7
+
+
+def test_oracle_gnll_matches_golden():
+    """GNLL (`--loss GNLL`, covmode 'uni'): oracle restatement of gaussian_nll_loss against the fixture generated from the
+    unmodified reference (tests/golden/make_gnll.py)."""
+    c = load_npz("case_gnll.npz")
+    pred = torch.from_numpy(c["pred"]).double().requires_grad_(True)
+    var = torch.from_numpy(c["var"]).double().requires_grad_(True)
+    loss, vout = O.gnll(pred, torch.from_numpy(c["target"]).double(), var, full=True, eps=1e-8)
+    loss.backward()
+    assert abs(loss.item() - float(c["loss"])) / abs(float(c["loss"])) < 1e-9
+    assert rel_l2(pred.grad, torch.from_numpy(c["dpred"])) < 1e-6 and rel_l2(var.grad, torch.from_numpy(c["dvar"])) < 1e-6
+    assert rel_l2(vout, torch.from_numpy(c["var_out"])) < 1e-6
+    with pytest.raises(ValueError, match="var has negative entry/entries"):
+        O.gnll(pred.detach(), torch.from_numpy(c["target"]).double(), -var.detach())
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_oracle_gnll_matches_live_reference_fp64():
+    _, Lm, _ = ref_import.load()
+    g = torch.Generator("cpu").manual_seed(3)
+    pred = torch.rand(2, 1, 13, 8, 8, generator=g, dtype=torch.float64).requires_grad_(True)
+    targ = torch.rand(2, 1, 13, 8, 8, generator=g, dtype=torch.float64)
+    var = (torch.rand(2, 1, 13, 8, 8, generator=g, dtype=torch.float64) * 2).requires_grad_(True)
+    with torch.no_grad():
+        var[0, 0, 0, 0, :3] = 1e-12
+    l_ref, v_ref = Lm.GaussianNLLLoss(reduction="mean", eps=1e-8, full=True)(pred, targ, var)
+    g_ref = torch.autograd.grad(l_ref, [pred, var])
+    l_own, v_own = O.gnll(pred, targ, var, full=True, eps=1e-8)
+    g_own = torch.autograd.grad(l_own, [pred, var])
+    assert abs(l_ref.item() - l_own.item()) < 1e-12 * abs(l_ref.item())
+    assert torch.allclose(v_ref, v_own) and all(torch.allclose(a, b, rtol=1e-12, atol=1e-15) for a, b in zip(g_ref, g_own))

@@ -8,9 +8,10 @@ Public surface (mirrors the reference's):
 The compute lives in libuncrtaints_b200.so (C ABI: include/uncrtaints_b200.h); there is no CPU fallback.
 """
 from .backbone import UNCRTAINTS, set_default_gemm_backend  # noqa: F401
-from .losses import MultiGaussianNLLLoss, get_loss, calc_loss, multi_gaussian_nll_loss, covariance_diag  # noqa: F401
+from .losses import (MultiGaussianNLLLoss, GaussianNLLLoss, get_loss, calc_loss, multi_gaussian_nll_loss,  # noqa: F401
+                     gaussian_nll_loss, covariance_diag)
 from .install import install  # noqa: F401
 from .parallel import FlatGradAllReduce, HostToDevicePrefetcher, HostScalarReader, shard_batch  # noqa: F401
 
-__all__ = ["UNCRTAINTS", "MultiGaussianNLLLoss", "get_loss", "calc_loss", "multi_gaussian_nll_loss", "covariance_diag",
+__all__ = ["UNCRTAINTS", "MultiGaussianNLLLoss", "GaussianNLLLoss", "gaussian_nll_loss", "get_loss", "calc_loss", "multi_gaussian_nll_loss", "covariance_diag",
            "install", "FlatGradAllReduce", "HostToDevicePrefetcher", "HostScalarReader", "shard_batch", "set_default_gemm_backend"]

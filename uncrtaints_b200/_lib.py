@@ -24,7 +24,7 @@ ERRORS = {-1: "UB200_ERR_ARG (unsupported shape / configuration)", -2: "UB200_ER
 SYMBOLS = [
     "ub200_version", "ub200_launch_count", "ub200_prof_enable", "ub200_prof_num_kernels", "ub200_prof_kernel_name",
     "ub200_prof_read", "ub200_tc_debug_set", "ub200_tc_debug_set_wgrad", "ub200_tc_set_warp_specialized", "ub200_tc_set_split_epilogue", "ub200_tc_set_dual", "ub200_dwconv_set_bwd_split", "ub200_dwconv_set_mode", "ub200_inconv_set_moments", "ub200_gemm1_forward", "ub200_wgrad1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
-    "ub200_backward", "ub200_mgnll_forward", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
+    "ub200_backward", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
     "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward",
 ]
 
@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.ub200_forward.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, sz, vp]
     L.ub200_backward.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, C.POINTER(vp), vp, sz, vp]
     L.ub200_mgnll_forward.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, f, vp, vp, vp, vp, vp, vp]
+    L.ub200_gnll_forward.argtypes = [vp, ll, vp, ll, vp, ll, i, i, f, i, vp, vp, vp, vp, vp, vp, vp]
     L.ub200_scale_by_scalar.argtypes = [vp, vp, vp, sz, vp]
     L.ub200_covariance.argtypes = [vp, ll, i, i, i, f, vp, vp]
     L.ub200_mbconv_workspace_bytes.argtypes = [i, i, i]

@@ -267,6 +267,57 @@ __global__ void __launch_bounds__(256) mgnll_fwd_kernel(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// GNLL (gaussian_nll_loss, model/src/losses.py:46-128; `--loss GNLL`, used with covmode 'uni'): element-wise
+//   loss = mean over all elements of 1/2 (log v + e^2 / v) [+ 1/2 log(2 pi) if full],  v = max(var, eps) with identity gradient.
+// One thread per (sample, pixel) over the 13 channel planes, like the MGNLL kernel; also writes the clamped variance (the
+// loss's second return value, losses.py:122-128).  acc[0] += sum of 1/2 (log v + e^2 / v).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gnll_fwd_kernel(const float* __restrict__ pred, long long pred_sb, const float* __restrict__ target,
+                                                        long long targ_sb, const float* __restrict__ var, long long var_sb,
+                                                        float* __restrict__ dpred /* [B][13][P] or null */, float* __restrict__ dvar,
+                                                        float* __restrict__ var_out /* [B][13][P] or null */, double* acc, int* neg_flag,
+                                                        int B, int P, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    float part = 0.f;
+    bool neg = false;
+    if (p < P) {
+        const float inv_n = 1.0f / ((float)B * (float)UB_S2 * (float)P);
+        float e[UB_S2], vr[UB_S2];
+#pragma unroll
+        for (int c = 0; c < UB_S2; ++c) {
+            vr[c] = var[b * var_sb + (size_t)c * P + p];
+            e[c] = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
+        }
+#pragma unroll
+        for (int c = 0; c < UB_S2; ++c) {
+            neg |= (vr[c] < 0.f);
+            const float v = fmaxf(vr[c], eps), iv = 1.0f / v;
+            part += 0.5f * (logf(v) + e[c] * e[c] * iv);
+            if (var_out) var_out[((size_t)b * UB_S2 + c) * P + p] = v;
+            if (dpred) {
+                dpred[((size_t)b * UB_S2 + c) * P + p] = e[c] * iv * inv_n;
+                dvar[((size_t)b * UB_S2 + c) * P + p] = 0.5f * (iv - e[c] * e[c] * iv * iv) * inv_n;
+            }
+        }
+    }
+    double l = warp_sum_d((double)part);
+    __shared__ double sl[8];
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    if (lane == 0) sl[warp] = l;
+    if (neg) *neg_flag = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int i = 0; i < 8; ++i) a += sl[i];
+        atomicAdd(&acc[0], a);
+    }
+}
+__global__ void gnll_finalize_kernel(const double* acc, float* loss, double count, int full) {
+    const double cst = full ? 0.5 * 1.8378770664093453 : 0.0;       // 1/2 log(2 pi) (math.log, losses.py:118)
+    *loss = (float)(acc[0] / count + cst);
+}
+
 __global__ void mgnll_finalize_kernel(const double* acc, float* loss, int B, int P) {
     // 13/2 * log(2*float32(pi)) evaluated in float32 (losses.py:143)
     const float cst = 6.5f * logf(2.0f * 3.14159274101257324f);
@@ -336,6 +387,18 @@ int launch_mgnll(const float* pred, long long pred_sb, const float* target, long
                                                       neg_flag, B, P, eps);
     UB_CHECK_LAUNCH();
     mgnll_finalize_kernel<<<1, 1, 0, st>>>(acc, loss, B, P);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_gnll(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                float* dpred, float* dvar, float* var_out, double* acc, int* neg_flag, float* loss, int B, int P, float eps, int full,
+                cudaStream_t st) {
+    if (cudaMemsetAsync(acc, 0, 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
+    if (cudaMemsetAsync(neg_flag, 0, sizeof(int), st) != cudaSuccess) return UB_ERR_CUDA;
+    gnll_fwd_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, dpred, dvar, var_out, acc,
+                                                              neg_flag, B, P, eps);
+    UB_CHECK_LAUNCH();
+    gnll_finalize_kernel<<<1, 1, 0, st>>>(acc, loss, (double)B * UB_S2 * (double)P, full);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }

@@ -132,6 +132,9 @@ int launch_head_bwd(const float* dout, const float* out, const float* dec, const
 int launch_mgnll(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
                  long long var_sb, int var_ch, float* dpred, float* dvar, double* acc, int* neg_flag, float* loss, int B,
                  int P, float eps, cudaStream_t st);
+int launch_gnll(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                float* dpred, float* dvar, float* var_out, double* acc, int* neg_flag, float* loss, int B, int P, float eps, int full,
+                cudaStream_t st);
 int launch_scale_by_scalar(const float* in, const float* g, float* out, size_t n, cudaStream_t st);
 int launch_covariance(const float* var, long long var_sb, int var_ch, float* cov, int B, int P, float eps, cudaStream_t st);
 

@@ -590,6 +590,15 @@ int ub200_mgnll_forward(const float* pred, long long pred_sb, const float* targe
                         neg_flag, loss, B, P, eps, static_cast<cudaStream_t>(stream));
 }
 
+int ub200_gnll_forward(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var,
+                       long long var_sb, int B, int P, float eps, int full, float* loss, float* dpred, float* dvar, float* var_out,
+                       int* neg_flag, void* scratch, void* stream) {
+    if (!pred || !target || !var || !loss || !neg_flag || !scratch || B < 1 || P < 1) return UB_ERR_ARG;
+    if ((dpred == nullptr) != (dvar == nullptr)) return UB_ERR_ARG;
+    return launch_gnll(pred, pred_sb, target, targ_sb, var, var_sb, dpred, dvar, var_out, static_cast<double*>(scratch), neg_flag, loss,
+                       B, P, eps, full, static_cast<cudaStream_t>(stream));
+}
+
 int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, size_t n, void* stream) {
     if (!in || !grad_loss || !out) return UB_ERR_ARG;
     return launch_scale_by_scalar(in, grad_loss, out, n, static_cast<cudaStream_t>(stream));

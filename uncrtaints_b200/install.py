@@ -16,5 +16,6 @@ def install(verbose: bool = True) -> None:
     ref_losses = importlib.import_module("src.losses")
     ref_uncrtaints.UNCRTAINTS = backbone.UNCRTAINTS            # model_utils.get_generator looks it up at call time (:86)
     ref_losses.MultiGaussianNLLLoss = losses.MultiGaussianNLLLoss   # get_loss looks it up at call time (losses.py:19)
+    ref_losses.GaussianNLLLoss = losses.GaussianNLLLoss             # --loss GNLL (losses.py:16)
     if verbose:
-        print("[uncrtaints_b200] installed UNCRTAINTS and MultiGaussianNLLLoss into the reference's src package")
+        print("[uncrtaints_b200] installed UNCRTAINTS, MultiGaussianNLLLoss and GaussianNLLLoss into the reference's src package")

@@ -1,7 +1,8 @@
 """MGNLL loss on the B200 path, with the reference's call surface.
 
 Mirrors model/src/losses.py: ``get_loss(config)`` (:14-32), ``calc_loss(criterion, config, out, y, var)`` (:35-43),
-``MultiGaussianNLLLoss(*, full, eps, reduction, mode, chunk)(input, target, var) -> (loss, variance)`` (:288-354).
+``MultiGaussianNLLLoss(*, full, eps, reduction, mode, chunk)(input, target, var) -> (loss, variance)`` (:288-354) and
+``GaussianNLLLoss(*, full, eps, reduction)(input, target, var) -> (loss, clamped var)`` (:46-128,222-284; ``--loss GNLL``).
 
 * ``loss`` is a 0-d CUDA tensor with autograd (one fused kernel computes the loss and both gradients).
 * ``variance`` is diag_embed(max(var, eps)) of shape [B,1,13,13,H,W] (losses.py:145,211).  The reference
@@ -78,6 +79,91 @@ class _MGNLLFunction(torch.autograd.Function):
         return gp, None, gv, None, None
 
 
+class _GNLLFunction(torch.autograd.Function):
+    last_flag = None
+
+    @staticmethod
+    def forward(ctx, pred, target, var, eps, full, check_negative):
+        L = _lib.lib()
+        B, _, C, H, W = pred.shape
+        P = H * W
+        pred_v, pred_sb = _plane_view(pred)
+        targ_v, targ_sb = _plane_view(target)
+        var_v, var_sb = _plane_view(var)
+        dev = pred.device
+        need_grad = pred.requires_grad or var.requires_grad
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        scratch = torch.empty(4, dtype=torch.float64, device=dev)
+        flag = scratch[2:].view(torch.int32)[:1]
+        dpred = torch.empty((B, 1, S2_BANDS, H, W), dtype=torch.float32, device=dev) if need_grad else None
+        dvar = torch.empty((B, 1, S2_BANDS, H, W), dtype=torch.float32, device=dev) if need_grad else None
+        var_out = torch.empty((B, 1, S2_BANDS, H, W), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.ub200_gnll_forward(pred_v.data_ptr(), pred_sb, targ_v.data_ptr(), targ_sb, var_v.data_ptr(), var_sb, B, P,
+                                        float(eps), int(bool(full)), loss.data_ptr(), dpred.data_ptr() if need_grad else None,
+                                        dvar.data_ptr() if need_grad else None, var_out.data_ptr(), flag.data_ptr(),
+                                        scratch.data_ptr(), stream), "ub200_gnll_forward")
+        _GNLLFunction.last_flag = flag
+        if check_negative != "deferred" and check_negative and int(flag.item()) != 0:
+            raise ValueError("var has negative entry/entries")
+        if need_grad:
+            ctx.save_for_backward(dpred, dvar)
+        ctx.mark_non_differentiable(var_out)
+        return loss, var_out
+
+    @staticmethod
+    def backward(ctx, g, _g_var):
+        L = _lib.lib()
+        dpred, dvar = ctx.saved_tensors
+        g = g.contiguous().float()
+        stream = torch.cuda.current_stream(dpred.device).cuda_stream
+        gp, gv = torch.empty_like(dpred), torch.empty_like(dvar)
+        _lib.check(L.ub200_scale_by_scalar(dpred.data_ptr(), g.data_ptr(), gp.data_ptr(), dpred.numel(), stream), "scale")
+        _lib.check(L.ub200_scale_by_scalar(dvar.data_ptr(), g.data_ptr(), gv.data_ptr(), dvar.numel(), stream), "scale")
+        return gp, None, gv, None, None, None
+
+
+def gaussian_nll_loss(input, target, var, full=False, eps=1e-8, reduction="mean", check_negative=True):
+    """gaussian_nll_loss (losses.py:46-128) -> (loss, clamped variance).  Heteroscedastic [B,1,13,H,W] variances (what the
+    'uni' covariance head produces); reduction 'mean' (what get_loss builds, losses.py:16)."""
+    if reduction != "none" and reduction != "mean" and reduction != "sum":
+        raise ValueError(reduction + " is not valid")
+    if reduction != "mean":
+        raise NotImplementedError("B200 path: only reduction='mean' (what get_loss builds, losses.py:16) is implemented")
+    if not input.is_cuda:
+        raise RuntimeError("uncrtaints_b200 GNLL runs on CUDA tensors only (no CPU fallback)")
+    if var.size() != input.size():
+        if input.size()[:-1] == var.size() or (input.size()[:-1] == var.size()[:-1] and var.size(-1) == 1):
+            raise NotImplementedError("B200 path: homoscedastic variances are not built (the network predicts one per element)")
+        raise ValueError("var is of incorrect size")
+    if input.dim() != 5 or input.shape[2] != S2_BANDS:
+        raise NotImplementedError("B200 path: expects [B,1,13,H,W] predictions and variances")
+    return _GNLLFunction.apply(input.float(), target.float(), var.float(), eps, full, check_negative)
+
+
+class GaussianNLLLoss(nn.Module):
+    """Same constructor / call as the reference class (losses.py:222-284): (input, target, var) -> (loss, clamped var)."""
+
+    def __init__(self, *, full: bool = False, eps: float = 1e-8, reduction: str = "mean", check_negative=True) -> None:
+        super().__init__()
+        self.full, self.eps, self.reduction, self.check_negative = full, eps, reduction, check_negative
+        self._pending_flag = None
+
+    def check(self):
+        flag, self._pending_flag = self._pending_flag, None
+        if flag is not None and int(flag.item()) != 0:
+            raise ValueError("var has negative entry/entries")
+
+    def forward(self, input, target, var):
+        if self.check_negative == "deferred":
+            self.check()
+        out = gaussian_nll_loss(input, target, var, full=self.full, eps=self.eps, reduction=self.reduction,
+                                check_negative=self.check_negative)
+        if self.check_negative == "deferred":
+            self._pending_flag = _GNLLFunction.last_flag
+        return out
+
+
 def covariance_diag(var: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
     """diag_embed(max(var, eps)) -> [B,1,13,13,H,W] on var's device (losses.py:145,211)."""
     L = _lib.lib()
@@ -139,8 +225,11 @@ class MultiGaussianNLLLoss(nn.Module):
 
 def get_loss(config):
     """losses.get_loss (losses.py:14-32) for the MGNLL branch; other losses are outside the hot path."""
+    if config.loss == "GNLL":                      # losses.py:15-17
+        criterion0 = GaussianNLLLoss(reduction="mean", eps=1e-8, full=True)
+        return lambda pred, targ, var: criterion0(pred, targ, var)
     if config.loss != "MGNLL":
-        raise NotImplementedError("B200 path builds the MGNLL loss only; use the reference's losses for " + str(config.loss))
+        raise NotImplementedError("B200 path builds the GNLL / MGNLL losses only; use the reference's losses for " + str(config.loss))
     criterion1 = MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=config.covmode,
                                       chunk=getattr(config, "chunk_size", None))
     return lambda pred, targ, var: criterion1(pred, targ, var)
