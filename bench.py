@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the UnCRtainTS hot path (forward + MGNLL + backward) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (oracle port), host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]           # the UNMODIFIED reference on the host cores
+    python bench.py --impl reference --device cuda [--tf32 0|1]         # the unmodified reference, torch eager on the GPU
 
 Metric (BASELINE.json): samples/s for netG.forward + MGNLL + backward (+ one gradient all-reduce when N > 1) on
 synthetic (B, T=3, 15, 256, 256) input, train mode, fp32 -- BASELINE config #2 (1xB200, batch 16) at N=1 and the
@@ -11,10 +12,13 @@ One step = one pass of the hot path over one batch.  The optimizer step is outsi
 
 Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same through
 the public API with pinned-host inputs copied H2D and the loss read back D2H every step; `roofline` = the dominant
-kernel class, timed with CUDA events on the launch stream inside the timed region, against MEASURED_PEAKS.json;
-`cpu_baseline` = the oracle (port of the reference, fused torch CPU ops) on a bounded sample on the host cores.
+kernel class (CUDA events on the launch stream inside the timed region, against MEASURED_PEAKS.json) plus the step-level
+fraction and the per-kernel fraction table; `cpu_baseline` = the unmodified reference (baseline/_ref) on a bounded sample
+on the host cores; `gpu_eager_baseline` = the unmodified reference in torch eager on the same GPU (TF32 off / on);
+`parity` = this path against the reference on a bounded sub-batch of the same inputs (rel-L2, PSNR).
 """
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -30,7 +34,6 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-P_FULL = 256 * 256
 METRIC = "samples/sec fwd+bwd (T=3, 15x256x256)"
 
 
@@ -40,13 +43,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="--impl reference only: host cores (default) or torch eager on the GPU")
+    ap.add_argument("--tf32", type=int, default=0, help="--impl reference --device cuda: allow TF32 in cuDNN / cuBLAS")
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE config #2: 16)")
     ap.add_argument("--t", type=int, default=3)
     ap.add_argument("--hw", type=int, default=256)
     ap.add_argument("--covmode", default="diag")
     ap.add_argument("--backend", type=int, default=None, help="bit 0: tcgen05 fwd/dX GEMMs, bit 1: tcgen05 wgrad GEMMs (default 3), bit 2: single-pass bf16 MMAs (7: reduced precision); 0 = fp32 CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=2, help="samples per step of the CPU reference (BASELINE config #1: 2)")
     return ap.parse_args()
 
 
@@ -124,34 +131,49 @@ class ClockSampler:
         return out
 
 
+# algorithmic HBM bytes per frame of one launch, in units of (A, Hh): A = 128 ch, Hh = 256 ch per pixel (fp32)
+KERNEL_BYTES = {
+    "gemm1_fwd": (1, 1), "dwconv_fwd": (0, 2), "se_pool": (0, 1), "gemm2_fwd": (1, 1), "residual_fwd": (3, 0),
+    "norm_bwd_stats": (2, 0), "gemm2_bwd": (2, 2), "wgrad2": (2, 1), "dwconv_bwd": (0, 4),
+    "gemm1_bwd": (2, 2), "wgrad1": (1, 2), "residual_bwd": (4, 0),
+    # fused input-gradient + weight-gradient GEMMs (one read of the shared operands)
+    "gemm2_bwd_fused": (2, 2), "gemm1_bwd_fused": (2, 2),
+}
+
+
 def algorithmic_bytes(kernel, frames, P):
-    """algorithmic HBM bytes of one launch over `frames` frames (fp32; A = 128 ch, Hh = 256 ch per pixel)."""
+    a, h = KERNEL_BYTES.get(kernel, (0, 0))
+    return (a * 128 * P * 4 + h * 256 * P * 4) * frames
+
+
+def survey_bytes_per_sample(T, covdim, P, n_dec=5):
+    """SURVEY.md §8(d) byte model ("one HBM materialisation per normalisation barrier"): 12.06 GB / sample at T=3, diag, fp32."""
     A, Hh = 128 * P * 4, 256 * P * 4
-    per_frame = {
-        "gemm1_fwd": A + Hh, "dwconv_fwd": 2 * Hh, "se_pool": Hh, "gemm2_fwd": Hh + A, "residual_fwd": 3 * A,
-        "norm_bwd_stats": 2 * A, "gemm2_bwd": 2 * A + 2 * Hh, "wgrad2": 2 * A + Hh, "dwconv_bwd": 4 * Hh,
-        "gemm1_bwd": 2 * Hh + 2 * A, "wgrad1": A + 2 * Hh, "residual_bwd": 4 * A,
-    }
-    return per_frame.get(kernel, 0) * frames
+    mbconv = 15 * A + 13 * Hh
+    return (T + n_dec) * mbconv + T * (5 * A + 5 * 15 * P * 4) + (3 * T + 2) * A + 3 * A + (52 + 2 * covdim) * P * 4
 
 
-# kernel class (ub200_prof_* name) -> substring of the ncu kernel name in profiles/r01_traffic.json
+# kernel class (ub200_prof_* name) -> substring of the ncu kernel name in profiles/r0N_traffic.json
 NCU_NAME = {"dwconv_bwd": "dwrows_bwd2_kernel", "dwconv_fwd": "dwrows_fwd_kernel<1, 1>", "gemm1_fwd": "gemm_tc_kernel<128, 256, TLoadNormed",
             "gemm2_fwd": "gemm_tc_kernel<256, 128, TLoadGeluGate", "wgrad2": "wgrad_tc_kernel<TLoadNormBwd, TLoadGeluGate>",
-            "wgrad1": "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>", "se_pool": "se_pool_kernel"}
+            "wgrad1": "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>", "se_pool": "se_pool_kernel",
+            "gemm2_bwd_fused": "bwd_tc_kernel<2", "gemm1_bwd_fused": "bwd_tc_kernel<1"}
 
 
 def ncu_traffic_per_frame(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per frame of `kernel` from the committed ncu --set full capture
-    (profiles/r01_traffic.json, written by scripts/ncu_summary.py), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    (profiles/r0N_traffic.json, written by scripts/ncu_summary.py; the newest round that has the kernel wins), or None."""
     key = NCU_NAME.get(kernel)
-    if not key or not os.path.exists(p):
-        return None
-    for name, v in json.load(open(p)).get("per_frame_bytes", {}).items():
-        if key in name:
-            return float(v)
-    return None
+    if not key:
+        return None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        for kname, v in json.load(open(p)).get("per_frame_bytes", {}).items():
+            if key in kname:
+                return float(v), "profiles/" + name
+    return None, None
 
 
 def measured_peaks():
@@ -162,28 +184,94 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def workload_config(args, world):
+    tag = "BASELINE config #2" if (args.batch, args.t, args.covmode) == (16, 3, "diag") else \
+        ("BASELINE config #4 per-GPU batch" if (args.batch, args.t, args.covmode) == (32, 3, "diag") else
+         ("BASELINE config #3 shape" if (args.batch, args.t) == (32, 5) else "variant of BASELINE config #2"))
+    return {"workload": f"{tag}: uncrtaints --input_t {args.t} --n_head 16 --block_type mbconv --covmode "
+                        f"{args.covmode}, per-GPU batch {args.batch}, synthetic 15x{args.hw}x{args.hw}, fwd+MGNLL+bwd, train mode",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "T": args.t,
+            "parallelism": f"dp{world} (batch sharded by sample, one NCCL all-reduce of the flat 2.28 MB gradient)",
+            "l2_note": "per-step working set (>= 10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_arm(args, steps, warmup, batch):
-    """The reference's CPU path: oracle port (FUSED torch CPU ops = the ATen/oneDNN kernels the reference's modules
-    dispatch to), all host threads, each step a bounded sample of `batch` samples of the same workload."""
-    from oracle import uncrtaints_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    O.set_fused(True)
-    cfg = O.OracleConfig(covmode=args.covmode)
-    p = O.init_params(cfg, seed=1)
-    x, y, d = O.synthetic_batch(batch, args.t, args.hw, args.hw, seed=1234)
-    keep = O.dropout_keep_mask(16, batch, args.t, args.hw, args.hw)
-    for _ in range(warmup):
-        O.step(p, x, y, d, cfg, True, keep)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.step(p, x, y, d, cfg, True, keep)
-    dt = time.perf_counter() - t0
-    O.set_fused(False)
-    return {"value": batch * steps / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of B={batch}, T={args.t}, 15x{args.hw}x{args.hw}, fp32, train mode, "
-                      f"fwd+MGNLL+bwd, {cores} host threads (torch CPU / oneDNN)", "ms_per_step": 1e3 * dt / steps}
+def reference_arm(args):
+    """`--impl reference`: the unmodified reference (baseline/_ref) through its own API, same workload family as the product arm
+    (T, frame size, covmode, train mode), each step a bounded sample of it: B=2 per step on the host cores (BASELINE config #1)."""
+    from baseline import ref_runner as R
+    config = workload_config(args, 1)
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing (run python baseline/install_ref.py in the build container)"}))
+        return
+    if args.device == "cuda":
+        r = R.time_cuda(args.batch, args.t, args.hw, args.covmode, max(1, args.steps), max(1, args.warmup), bool(args.tf32))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "reference eager does not fit on this GPU even at B=1"}))
+            return
+        config["reference_sample"] = f"torch eager on the GPU, B={r['batch']} per step (largest power-of-two fraction of {args.batch} that fits), tf32={bool(args.tf32)}"
+        line = {"impl": "reference", "device": "cuda", "metric": METRIC, "value": round(r["value"], 3), "unit": "samples/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.tf32 else "f32", "data": "synthetic", "config": config,
+                "gpu_eager": r,
+                "e2e": {"value": round(r["value"], 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    cb = R.time_cpu(args.ref_batch, args.t, args.hw, args.covmode, max(1, args.steps), max(1, args.warmup))
+    config["reference_sample"] = (f"each step = B={cb['batch']} samples of the workload (BASELINE config #1 is B=2: the reference's own "
+                                  "CPU-runnable case); the product arm's step is the full per-GPU batch")
+    line = {"impl": "reference", "metric": METRIC, "value": round(cb["value"], 4), "unit": "samples/s", "n_gpus": 0,
+            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": round(cb["ms_per_step"], 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": round(cb["value"], 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def parity_vs_reference(args, dev, backend):
+    """This path against the UNMODIFIED reference (baseline/_ref, CPU fp32) on a bounded sub-batch (B=2) of the bench inputs,
+    same weights (the reference's seeded weight_init, loaded strict=True), train mode (BatchNorm batch statistics) with the
+    attention dropout switched off on both sides (the two RNG streams differ by design).  rel-L2 per tensor; PSNR =
+    20 log10(1 / RMSE) of the mean predictions after / scale_by (model/src/learning/metrics.py:21-22)."""
+    import uncrtaints_b200 as ub
+    from baseline import ref_runner as R
+    B = 2
+    ref, rcrit = R.build(args.covmode, 1, "cpu")
+    ref.temporal_aggregator.attn_dropout.p = 0.0
+    x, y, d = synthetic(B, args.t, args.hw, seed=1234)
+    torch.set_num_threads(os.cpu_count() or 1)
+    r_out = ref(x, batch_positions=d)                       # BaseModel.forward / get_loss_G / backward_G (base_model.py:60-84)
+    r_loss, _ = rcrit(r_out[:, :, :ref.mean_idx], y, r_out[:, :, ref.mean_idx:ref.vars_idx])
+    r_loss.backward()
+    r_out = r_out.detach()
+    r_grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    # the first step updated the BatchNorm running statistics; the forward of a train-mode step does not read them
+    cov = {"diag": 13, "iso": 1}[args.covmode]
+    net = ub.UNCRTAINTS(input_dim=15, out_conv=[13 + cov], out_nonlin_mean=True, out_nonlin_var="softplus",
+                        covmode=args.covmode, scale_by=10.0, gemm_backend=backend)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).train()
+    net.temporal_aggregator.attn_dropout.p = 0.0
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=args.covmode, chunk=None, covariance="none")
+    out = net(x.to(dev), batch_positions=d.to(dev))
+    loss, _ = crit(out[:, :, :net.mean_idx], y.to(dev), out[:, :, net.mean_idx:net.vars_idx])
+    loss.backward()
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).norm() / (b.norm() + 1e-300))
+    zero = ("temporal_encoder.in_norm.bias", "temporal_encoder.inconv.bias", "temporal_encoder.attention_heads.fc1_k.bias")
+    gerr = {k: rel(p.grad, r_grads[k]) for k, p in net.named_parameters()
+            if k not in zero and not (k.startswith("out_block.") and k.endswith("conv.norm.bias"))}
+    worst = max(gerr, key=gerr.get)
+    mse = float(((out[:, :, :13].detach().cpu().double() - r_out[:, :, :13].double()) / 10.0).square().mean())
+    return {"vs": "unmodified reference (baseline/_ref), CPU fp32, same weights and inputs", "sub_batch": B, "T": args.t,
+            "out_rel_l2": rel(out, r_out), "loss": float(loss), "ref_loss": float(r_loss),
+            "loss_rel": abs(float(loss) - float(r_loss)) / abs(float(r_loss)),
+            "grad_rel_l2_worst": gerr[worst], "grad_worst_name": worst, "grad_rel_l2_median": sorted(gerr.values())[len(gerr) // 2],
+            "psnr_db_vs_reference": (20 * math.log10(1.0 / math.sqrt(mse)) if mse > 0 else float("inf")),
+            "tolerance": "1e-3 rel-L2 (north_star); dropout off on both sides for this check"}
 
 
 def main():
@@ -191,25 +279,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    tag = "BASELINE config #2" if (args.batch, args.t, args.covmode) == (16, 3, "diag") else \
-        ("BASELINE config #3 shape (fp32 storage)" if (args.batch, args.t) == (32, 5) else "variant of BASELINE config #2")
-    config = {"workload": f"{tag}: uncrtaints --input_t {args.t} --n_head 16 --block_type mbconv --covmode "
-                          f"{args.covmode}, per-GPU batch {args.batch}, synthetic 15x{args.hw}x{args.hw}, fwd+MGNLL+bwd, train mode",
-              "per_gpu_batch": args.batch, "global_batch": args.batch * world, "T": args.t,
-              "parallelism": f"dp{world} (batch sharded by sample, one NCCL all-reduce of the flat 2.28 MB gradient)",
-              "l2_note": "per-step working set (>= 10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        cb = cpu_reference_arm(args, max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample_batch)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": 0,
-                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        if rank == 0:
+            reference_arm(args)
         return
+    config = workload_config(args, world)
 
     import torch.distributed as dist
     import uncrtaints_b200 as ub
@@ -252,12 +327,13 @@ def main():
     # ---- warm-up; the last warm-up step records every kernel class to find the dominant one -----------------
     nk = L.ub200_prof_num_kernels()
     names = [L.ub200_prof_kernel_name(k).decode() for k in range(nk)]
-    for w in range(max(args.warmup, 3)):
-        if w == max(args.warmup, 3) - 1:
+    nwarm = max(args.warmup, 3)
+    for w in range(nwarm):
+        if w == nwarm - 1:
+            torch.cuda.synchronize(dev)
             L.ub200_prof_enable((1 << nk) - 1)
         step(x, y, d)
     torch.cuda.synchronize(dev)
-    import ctypes
     breakdown = {}
     for k in range(nk):
         ms, n = ctypes.c_double(), ctypes.c_int()
@@ -325,24 +401,37 @@ def main():
 
     samples = args.batch * world * args.steps
     value = samples / (ms_total / 1e3)
+    ms_step = ms_total / args.steps
     peak, peak_src = measured_peaks()
-    # frames per launch of the dominant class: 1 encoder launch over B*T frames + n_dec launches over B frames per step
+    # frames per launch of a block kernel class: 1 encoder launch over B*T frames + n_dec launches over B frames per step
     n_dec = len(net.out_block)
-    total_frames = (args.batch * args.t + n_dec * args.batch) * args.steps
+    frames_step = args.batch * args.t + n_dec * args.batch
     P = args.hw * args.hw
-    bytes_total = algorithmic_bytes(top, total_frames, P)
+    bytes_total = algorithmic_bytes(top, frames_step * args.steps, P)
     achieved = bytes_total / (tms.value / 1e3) / 1e9 if tms.value > 0 else 0.0
-    tpf = ncu_traffic_per_frame(top)
-    traffic = int(tpf * total_frames / max(tn.value, 1)) if tpf else None      # per launch, like algorithmic_bytes_per_launch
+    tpf, tsrc = ncu_traffic_per_frame(top)
+    traffic = int(tpf * frames_step * args.steps / max(tn.value, 1)) if tpf else None      # per launch, like algorithmic_bytes_per_launch
+    # per-kernel fraction of the HBM roof from the profiled warm-up step, and what the classed kernels leave unattributed
+    kernel_fracs = {k: round(algorithmic_bytes(k, frames_step, P) / (v["ms"] / 1e3) / 1e9 / peak, 3)
+                    for k, v in breakdown.items() if algorithmic_bytes(k, 1, 1) > 0 and v["ms"] > 0}
+    classed_ms = sum(v["ms"] for v in breakdown.values())
+    step_bytes = survey_bytes_per_sample(args.t, cov, P, n_dec) * args.batch
+    step_gbs = step_bytes / (ms_step / 1e3) / 1e9
     roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "traffic_source": "profiles/r01_traffic.json (ncu --set full dram bytes per frame x frames per launch)" if tpf else None,
+                "traffic_source": (tsrc + " (ncu --set full dram bytes per frame x frames per launch)") if tpf else None,
                 "launches": tn.value, "avg_launch_ms": round(tms.value / max(tn.value, 1), 4),
                 "algorithmic_bytes_per_launch": bytes_total // max(tn.value, 1),
                 "share_of_step": round(tms.value / ms_total, 4),
-                "note": "achieved = algorithmic bytes (DESIGN.md §4) / CUDA-event time of the kernel class inside the timed region"}
+                "step_frac": round(step_gbs / peak, 4), "step_achieved": round(step_gbs, 1),
+                "step_bytes_model": f"SURVEY.md §8(d): {step_bytes / args.batch / 1e9:.2f} GB / sample (one HBM materialisation per normalisation barrier)",
+                "kernel_fracs": kernel_fracs,
+                "unattributed_ms_per_step": round(ms_step - classed_ms, 3),
+                "note": "achieved = algorithmic bytes (DESIGN.md §4) / CUDA-event time of the kernel class inside the timed region; "
+                        "kernel_fracs = the same ratio for every block-kernel class from the profiled warm-up step; step_frac = "
+                        "byte model of the whole step / ms_per_step / peak"}
     line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "warmup": nwarm, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MMA / f32 storage" if ((args.backend or 0) & 4) else "f32",
             "data": "synthetic", "config": config,
             "gemm_backend": int(args.backend if args.backend is not None else ub.backbone._default_backend()),
@@ -351,12 +440,37 @@ def main():
                     "h2d_bytes_per_step": int((xh.numel() + yh.numel() + dh.numel()) * 4), "d2h_bytes_per_step": 4,
                     "last_loss": last_loss},
             "roofline": roofline, "kernels_ms_per_step": breakdown}
-    if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_arm(args, 1, 0, args.cpu_sample_batch)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if world == 1:
+        # free the product arm's memory before the comparators run in the same process
+        del net, bucket, crit, pf, rd, x, y, d
+        torch.cuda.empty_cache()
+        from baseline import ref_runner as R
+        have_ref = R.available()
+        if not args.no_parity and have_ref:
+            try:
+                line["parity"] = parity_vs_reference(args, dev, args.backend)
+            except Exception as e:                      # the comparators must never take the bench line down
+                line["parity"] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+        if not args.no_eager_baseline and have_ref:
+            eager = {}
+            for tf32 in (False, True):
+                try:
+                    eager["tf32_on" if tf32 else "tf32_off"] = R.time_cuda(args.batch, args.t, args.hw, args.covmode, 3, 1, tf32, dev)
+                except Exception as e:
+                    eager["tf32_on" if tf32 else "tf32_off"] = {"error": repr(e)[:300]}
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = False
+            line["gpu_eager_baseline"] = eager
+        if not args.no_cpu_baseline:
+            if have_ref:
+                cb = R.time_cpu(args.ref_batch, args.t, args.hw, args.covmode, 2, 1)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            else:
+                line["cpu_baseline"] = {"unavailable": "baseline/_ref missing"}
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

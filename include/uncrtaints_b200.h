@@ -8,8 +8,10 @@
  *
  * Conventions
  *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
- *  - the caller owns every buffer (inputs, outputs, gradients, workspace); the library allocates nothing,
- *    retains nothing between calls and never synchronises the device;
+ *  - the caller owns every buffer (inputs, outputs, gradients, workspace); the library allocates nothing, keeps no
+ *    configuration between calls (every option is an argument or a field of ub200_desc) and never synchronises the
+ *    device.  The only process-level state are two diagnostics: the launch counter and the optional profiling
+ *    events of ub200_prof_* (bench.py); they are not thread-safe and do not influence any result;
  *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately;
  *  - return value: 0 on success, negative UB200_ERR_* otherwise;
  *  - API tensors are float32, contiguous, in the reference's layouts (NCHW); internal activations in the
@@ -106,32 +108,6 @@ int ub200_prof_num_kernels(void);
 const char* ub200_prof_kernel_name(int kid);
 int ub200_prof_read(int kid, double* total_ms, int* launches);
 
-/* Debug hook for the tcgen05 path: override the shared-memory matrix-descriptor upper word, its LBO field and the
- * instruction descriptor (defaults follow CUTLASS cute/arch/mma_sm100_desc.hpp). */
-int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
-int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
-/* 0 (default): single-role tcgen05 GEMM kernel; 1: warp-specialised variant (producer warps / epilogue warps, TMA bulk
- * weight load) -- kept for experiments, measured slightly slower. */
-int ub200_tc_set_warp_specialized(int on);
-/* 1 (default): the epilogue (TMEM -> global, statistics) of tile t-1 is spread over the K-block steps of tile t in the forward
- * GEMMs (two parts; measured -9 % / -5 %); 0: one burst after the last K-block everywhere. */
-int ub200_tc_set_split_epilogue(int on);
-/* The input-gradient GEMM and the weight-gradient GEMM of a 1x1 convolution as the two roles of ONE launch (paired CTAs
- * sweep the same tiles at the same time, so the shared activation tensors come from HBM once and from the L2 once):
- * bit 0 = expand convolution (gemm1_bwd + wgrad1, measured -5 %), bit 1 = project convolution (gemm2_bwd + wgrad2, measured
- * +6 %).  Default 0 (two launches). */
-int ub200_tc_set_dual(int mask);
-/* 1 (default): pointwise dh2 kernel + stencil kernel (6 tensor passes, measured faster); 0: fused depthwise-conv backward
- * kernel (4 tensor passes, kept for tuning). */
-int ub200_dwconv_set_bwd_split(int on);
-/* Depthwise 3x3 kernel family: bit 0 = row-streaming forward, bit 1 = row-streaming FUSED backward (both fed by 1-D TMA
- * bulk copies of whole 1 KB-per-pixel image rows), bit 2 = packed FFMA2 stencil arithmetic, bit 3 = packed f32x2 GELU in them, bit 5 = 512-thread channel-pair form of the
- * backward kernel; 0 = cp.async tile kernels.  Default 47. */
-int ub200_dwconv_set_mode(int mode);
-/* 1 (default): in_conv GroupNorm statistics and weight gradients from per-frame input moments + one gram pass over dX0;
- * 0: the recompute passes (statistics pass + weight-gradient pass, each re-evaluating the 15->128 convolution). */
-int ub200_inconv_set_moments(int on);
-
 /* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
  * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,
  * bc1: [N][256] (a,b,c,pad) quads).  scratch: 148 * 128 KB. */
@@ -189,11 +165,30 @@ int ub200_gnll_forward(const float* pred, long long pred_sb, const float* target
                        long long var_sb, int B, int P, float eps, int full, float* loss, float* dpred, float* dvar, float* var_out,
                        int* neg_flag, void* scratch, void* stream);
 
+/* reduction='none' of the two losses (losses.py:213-218, :122-128).  grad_loss == NULL: forward, writes `loss` (MGNLL: [P][B],
+ * the nested vmap's output order [H][W][B]; GNLL: [B][13][P]) and neg_flag (and GNLL's clamped variance var_out, optional).
+ * grad_loss != NULL (same shape as loss): backward, writes dpred [B][13][P] and dvar [B][var_ch | 13][P].
+ * reduction='sum' needs no entry point: it is B*P (GNLL: B*13*P) times the 'mean' value. */
+int ub200_mgnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                     int var_ch, int B, int P, float eps, const float* grad_loss, float* loss, float* dpred, float* dvar, int* neg_flag,
+                     void* stream);
+int ub200_gnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                    int B, int P, float eps, int full, const float* grad_loss, float* loss, float* var_out, float* dpred, float* dvar,
+                    int* neg_flag, void* stream);
+
 /* out[i] = in[i] * grad_loss[0]  (chain rule with the upstream gradient of the scalar loss). */
 int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, size_t n, void* stream);
 
 /* Second return value of the loss: diag_embed(max(var, eps)) -> [B][1][13][13][H][W] (losses.py:145,211). */
 int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int P, float eps, float* cov, void* stream);
+
+/* One Adam step over flat fp32 buffers of n elements (torch.optim.Adam defaults: no amsgrad, L2 weight decay folded into the
+ * gradient; replaces optimizer_G.step() + optimizer_G.zero_grad() of base_model.py:120-122 with ONE kernel):
+ *   g' = grads*grad_scale (+ weight_decay*p);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps);   grads = 0 if zero_grad.
+ * step >= 1 is the number of this update; ExponentialLR (base_model.py:51) is the caller changing lr. */
+int ub200_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, int step, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
 
 /* out_conv + head alone (uncrtaints.py:381,432-446; tests and the calibration sweep of BASELINE config #5):
  *   dec [B][P][128] pixel-major decoder output, w [out_dim][128], bias [out_dim] -> out [B][out_dim][P] with

@@ -307,10 +307,23 @@ def head(o: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
     return torch.cat([mean, var], dim=2)
 
 
+def gather_pool(x: torch.Tensor, idx: torch.Tensor, out_hw: int = ATT_DOWN) -> torch.Tensor:
+    """Max-pool *values* taken at given flat (h*W + w) positions: the pooling of `adaptive_max_pool` with the index selection
+    imposed from outside.  Diagnostic only (``forward(..., pool_idx=...)``): an fp32 implementation whose encoder output differs
+    from the fp64 oracle's in the 6th digit picks the other element of a near-tie in a handful of the 8x8 windows; the discrete
+    re-routing of that window's (large, attention-path) gradient is an O(1) change of a few elements of dEnc, which shows up as
+    5-8e-4 relative L2 on every encoder gradient although all arithmetic is accurate to ~5e-5.  Imposing the implementation's
+    own argmax (itself checked bit-exact against ATen on identical input) separates the two effects."""
+    n, c, h, w = x.shape
+    return torch.gather(x.reshape(n, c, h * w), 2, idx.reshape(n, c, -1)).reshape(n, c, out_hw, out_hw)
+
+
 def forward(p: Dict[str, torch.Tensor], x: torch.Tensor, batch_positions: Optional[torch.Tensor],
             cfg: OracleConfig, training: bool = True, keep_mask: Optional[torch.Tensor] = None,
-            new_buffers: Optional[dict] = None, taps: Optional[dict] = None) -> torch.Tensor:
-    """UNCRTAINTS.forward (uncrtaints.py:391-446).  x: [B,T,C_in,H,W] -> [B,1,13+covdim,H,W]."""
+            new_buffers: Optional[dict] = None, taps: Optional[dict] = None,
+            pool_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """UNCRTAINTS.forward (uncrtaints.py:391-446).  x: [B,T,C_in,H,W] -> [B,1,13+covdim,H,W].
+    ``pool_idx`` (int64 [B*T,128,32,32], diagnostic): impose the max-pool index selection, see `gather_pool`."""
     b, t, cin, H, W = x.shape
     pad_mask = (x == cfg.pad_value).all(dim=-1).all(dim=-1).all(dim=-1)          # :392-394
     f = x.reshape(b * t, cin, H, W)                                              # smart_forward, utae.py:422-450
@@ -323,6 +336,8 @@ def forward(p: Dict[str, torch.Tensor], x: torch.Tensor, batch_positions: Option
         f = mbconv(f, p, f"in_block.{i}.", cfg.encoder_norm, training, cfg, new_buffers, taps)
     c = f.shape[1]
     down, idx = adaptive_max_pool(f, ATT_DOWN)                                   # :403-404
+    if pool_idx is not None:
+        down, idx = gather_pool(f, pool_idx, ATT_DOWN), pool_idx
     attn = ltae_tiny(down.reshape(b, t, c, ATT_DOWN, ATT_DOWN), batch_positions, pad_mask, p, cfg)
     agg = aggregate(f.reshape(b, t, c, H, W), attn, pad_mask, training, cfg, keep_mask)
     if taps is not None:
@@ -521,12 +536,13 @@ def init_params(cfg: OracleConfig, seed: int = 1) -> Dict[str, torch.Tensor]:
     return p
 
 
-def step(p: Dict[str, torch.Tensor], x, y, dates, cfg: OracleConfig, training=True, keep_mask=None, loss_name: str = "MGNLL"):
+def step(p: Dict[str, torch.Tensor], x, y, dates, cfg: OracleConfig, training=True, keep_mask=None, loss_name: str = "MGNLL",
+         pool_idx=None):
     """One fwd + loss (MGNLL, or GNLL for `--loss GNLL`) + bwd of the oracle.  Returns (out, loss, grads dict, new BN buffers)."""
     leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
             for k, v in p.items()}
     new_buffers: dict = {}
-    out = forward(leaf, x, dates, cfg, training, keep_mask, new_buffers)
+    out = forward(leaf, x, dates, cfg, training, keep_mask, new_buffers, None, pool_idx)
     if loss_name == "GNLL":
         loss, _ = gnll(out[:, :, :S2_BANDS], y, out[:, :, S2_BANDS:S2_BANDS + cfg.covar_dim], full=True)
     else:

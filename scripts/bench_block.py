@@ -75,8 +75,7 @@ def main():
         return float((p.double() - r.double()).norm() / (r.double().norm() + 1e-300))
 
     base = None
-    for mode in [int(m) for m in a.modes.split(",")]:
-        L.ub200_dwconv_set_mode(mode)
+    for mode in [0]:
         run(); run()
         torch.cuda.synchronize()
         L.ub200_prof_enable((1 << nk) - 1)
@@ -97,7 +96,6 @@ def main():
         else:
             diff = " | diff vs first: " + " ".join(f"{k}={rel(v, base[k]):.1e}" for k, v in snap.items())
         print(f"[block N={N} {H}x{W} groups={a.groups}] mode={mode} ms: " + " ".join(line) + diff, flush=True)
-    L.ub200_dwconv_set_mode(47)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,165 @@
+"""GPU tests of the pieces around the hot path: loss reductions, NaN / dtype handling, the fused Adam step, the flat gradient
+bucket after a foreign zero_grad, error behaviour of a second backward."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz, rel_l2, is_zero_grad_param
+from oracle import uncrtaints_oracle as O
+from test_gpu_parity import make_net
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["diag", "iso"])
+@pytest.mark.parametrize("reduction", ["sum", "none"])
+def test_mgnll_reductions(mode, reduction):
+    """reduction='sum' / 'none' of MultiGaussianNLLLoss (losses.py:213-218) against the oracle's closed form, with a random
+    upstream gradient for 'none' ([H,W,B], the nested vmap's output order)."""
+    import uncrtaints_b200 as ub
+    c = load_npz("case_mgnll.npz")
+    pred = torch.from_numpy(c[f"{mode}.pred"]).cuda().requires_grad_(True)
+    var = torch.from_numpy(c[f"{mode}.var"]).cuda().requires_grad_(True)
+    targ = torch.from_numpy(c[f"{mode}.target"]).cuda()
+    p64 = torch.from_numpy(c[f"{mode}.pred"]).double().requires_grad_(True)
+    v64 = torch.from_numpy(c[f"{mode}.var"]).double().requires_grad_(True)
+    ref = O.mgnll(p64, torch.from_numpy(c[f"{mode}.target"]).double(), v64, mode, reduction=reduction)
+    loss, cov = ub.MultiGaussianNLLLoss(reduction=reduction, eps=1e-8, full=True, mode=mode, chunk=None)(pred, targ, var)
+    assert loss.shape == ref.shape
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5), dtype=torch.float64) if reduction == "none" else torch.tensor(0.7, dtype=torch.float64)
+    ref.backward(g)
+    loss.backward(g.float().cuda())
+    assert rel_l2(loss, ref) <= 1e-5
+    assert rel_l2(pred.grad, p64.grad) <= 1e-4 and rel_l2(var.grad, v64.grad) <= 1e-4
+    assert cov.shape[2:4] == (13, 13)
+
+
+@pytest.mark.parametrize("reduction", ["sum", "none"])
+def test_gnll_reductions(reduction):
+    import uncrtaints_b200 as ub
+    c = load_npz("case_gnll.npz")
+    pred = torch.from_numpy(c["pred"]).cuda().requires_grad_(True)
+    var = torch.from_numpy(c["var"]).cuda().requires_grad_(True)
+    targ = torch.from_numpy(c["target"]).cuda()
+    p64 = torch.from_numpy(c["pred"]).double().requires_grad_(True)
+    v64 = torch.from_numpy(c["var"]).double().requires_grad_(True)
+    ref, _ = O.gnll(p64, torch.from_numpy(c["target"]).double(), v64, full=True, reduction=reduction)
+    loss, vout = ub.GaussianNLLLoss(reduction=reduction, eps=1e-8, full=True)(pred, targ, var)
+    assert loss.shape == ref.shape
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6), dtype=torch.float64) if reduction == "none" else torch.tensor(1.3, dtype=torch.float64)
+    ref.backward(g)
+    loss.backward(g.float().cuda())
+    assert rel_l2(loss, ref) <= 1e-5
+    assert rel_l2(pred.grad, p64.grad) <= 1e-4 and rel_l2(var.grad, v64.grad) <= 1e-4
+    assert rel_l2(vout, torch.from_numpy(c["var_out"])) <= 1e-6
+
+
+def test_nan_variance_propagates_and_dtypes():
+    """A NaN variance must give a NaN loss (the reference's clamp_ keeps NaN, losses.py:203-205), not log(eps); the
+    covariance output accepts non-float32 variances (cast, not reinterpreted)."""
+    import uncrtaints_b200 as ub
+    c = load_npz("case_mgnll.npz")
+    pred, var, targ = (torch.from_numpy(c[f"diag.{k}"]).cuda() for k in ("pred", "var", "target"))
+    bad = var.clone()
+    bad[0, 0, 3, 1, 2] = float("nan")
+    loss, cov = ub.MultiGaussianNLLLoss(mode="diag", chunk=None)(pred, targ, bad)
+    assert torch.isnan(loss) and torch.isnan(cov[0, 0, 3, 3, 1, 2])
+    l2, v2 = ub.GaussianNLLLoss()(pred, targ, bad)
+    assert torch.isnan(l2) and torch.isnan(v2[0, 0, 3, 1, 2])
+    cov32 = ub.covariance_diag(var)
+    assert torch.equal(ub.covariance_diag(var.double()), cov32)
+    assert rel_l2(ub.covariance_diag(var.half()), cov32) < 1e-3
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ub.covariance_diag(var.cpu())
+    with pytest.raises(ValueError):
+        ub.covariance_diag(var[:, :, :5])
+
+
+def test_fused_adam_matches_torch_adam(golden_weights):
+    """uncrtaints_b200.FusedAdam (one kernel over the flat parameter / gradient / moment buffers, ExponentialLR on top) against
+    torch.optim.Adam + ExponentialLR on the same model, gradients from the real backward, for several steps."""
+    import uncrtaints_b200 as ub
+    x, y, d = O.synthetic_batch(1, 2, 64, 64, seed=41)
+    keep = O.dropout_keep_mask(16, 1, 2, 64, 64, seed=42).to(torch.uint8)
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None, covariance="none")
+    nets = [make_net(golden_weights, "diag").train() for _ in range(2)]
+    for n in nets:
+        n._injected_keep_mask = keep
+    opt_ref = torch.optim.Adam([{"params": nets[0].parameters()}], lr=1e-3)          # base_model.py:48-49
+    sch_ref = torch.optim.lr_scheduler.ExponentialLR(opt_ref, gamma=0.8)             # base_model.py:51
+    opt = ub.FusedAdam(nets[1].parameters(), lr=1e-3)
+    sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.8)
+    ptr0 = [p.data_ptr() for p in nets[1].parameters()]
+    for it in range(4):
+        losses = []
+        for n, o in zip(nets, (opt_ref, opt)):
+            o.zero_grad()
+            out = n(x.cuda(), batch_positions=d.cuda())
+            loss, _ = crit(out[:, :, :13], y.cuda(), out[:, :, 13:26])
+            loss.backward()
+            o.step()
+            losses.append(loss.item())
+        if it % 2 == 1:
+            sch_ref.step(); sch.step()
+        assert abs(losses[0] - losses[1]) <= 2e-3 * abs(losses[0]), (it, losses)
+    assert [p.data_ptr() for p in nets[1].parameters()] == ptr0, "parameters must stay views of the flat buffer"
+    assert opt.param_groups[0]["lr"] == pytest.approx(opt_ref.param_groups[0]["lr"])
+    worst = max(rel_l2(b, a) for (ka, a), (kb, b) in zip(nets[0].named_parameters(), nets[1].named_parameters())
+                if not is_zero_grad_param(ka))
+    assert worst <= 2e-3, worst          # Adam's sign-like first steps amplify 1e-5 gradient differences near g ~ 0
+    # state_dict round trip
+    sd = opt.state_dict()
+    opt2 = ub.FusedAdam(make_net(golden_weights, "diag").parameters(), lr=1e-3)
+    opt2.load_state_dict(sd)
+    assert opt2._step == 4 and torch.equal(opt2.exp_avg, opt.exp_avg)
+
+
+def test_adam_kernel_exact_on_random_buffers():
+    """ub200_adam_step on random flat buffers against torch.optim.Adam's update rule, element for element."""
+    from uncrtaints_b200 import _lib
+    g = torch.Generator("cpu").manual_seed(9)
+    n = 100003
+    p = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * 10 ** float(torch.randn((), generator=g)) for _ in range(3)]
+    ref = torch.nn.Parameter(p.clone().cuda())
+    opt = torch.optim.Adam([ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    pd, m, v = p.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for it, gr in enumerate(grads):
+        ref.grad = gr.clone().cuda()
+        opt.step()
+        gd = (gr * 4.0).cuda()                      # grad_scale = 0.25 undoes the factor: the data-parallel 1/world fold
+        _lib.check(_lib.lib().ub200_adam_step(pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, it + 1, 3e-3, 0.9, 0.999,
+                                              1e-8, 0.01, 0.25, 1, torch.cuda.current_stream().cuda_stream), "adam")
+        assert float(gd.abs().max()) == 0.0         # zero_grad fused
+    assert rel_l2(pd, ref.data) <= 1e-6
+
+
+def test_bucket_survives_foreign_zero_grad_and_second_backward_raises(golden_weights):
+    import uncrtaints_b200 as ub
+    x, y, d = O.synthetic_batch(1, 2, 64, 64, seed=5)
+    keep = O.dropout_keep_mask(16, 1, 2, 64, 64, seed=6).to(torch.uint8)
+    crit = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None, covariance="none")
+    net = make_net(golden_weights, "diag").train()
+    net._injected_keep_mask = keep
+    bucket = ub.FlatGradAllReduce(net.parameters())
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+
+    def run():
+        out = net(x.cuda(), batch_positions=d.cuda())
+        loss, _ = crit(out[:, :, :13], y.cuda(), out[:, :, 13:26])
+        loss.backward()
+        return loss
+    bucket.zero_()
+    loss = run()
+    want = bucket.flat.clone()
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+    # the reference's own loop: optimizer.zero_grad() sets every grad to None (base_model.py:120) -> fresh autograd tensors
+    net.load_state_dict(sd0, strict=True)
+    torch.optim.SGD(net.parameters(), lr=0.1).zero_grad()
+    assert all(p.grad is None for p in net.parameters())
+    run()
+    bucket.all_reduce_mean()                        # world 1: only re-attaches
+    assert bucket.reattached == len(bucket.params)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    assert rel_l2(bucket.flat, want) <= 1e-4

@@ -29,6 +29,7 @@ def make_net(weights, covmode="diag", backend=None):
     sd["out_conv.conv.conv.0.weight"] = sd["out_conv.conv.conv.0.weight"][:13 + cov]
     sd["out_conv.conv.conv.0.bias"] = sd["out_conv.conv.conv.0.bias"][:13 + cov]
     net.load_state_dict(sd, strict=True)
+    net.keep_workspace = True          # tests read intermediates out of the workspace (ub200_workspace_tap)
     return net.cuda()
 
 
@@ -63,20 +64,9 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3, 103])
+@pytest.mark.parametrize("backend", [0, 1, 3])
 def test_golden_diag_train_pad(golden_weights, backend):
-    import uncrtaints_b200 as ub
-    from uncrtaints_b200 import _lib
-    if backend >= 100:                      # 103: backend 3 with the warp-specialised tcgen05 GEMM kernel
-        backend -= 100
-        _lib.lib().ub200_tc_set_warp_specialized(1)
-    try:
-        _golden_diag_train_pad(golden_weights, backend)
-    finally:
-        _lib.lib().ub200_tc_set_warp_specialized(0)
-
-
-def _golden_diag_train_pad(golden_weights, backend):
+    """backend 3 = the product path (tcgen05 GEMMs everywhere); 0 / 1 = the fp32 CUDA-core GEMMs kept as test comparators."""
     import uncrtaints_b200 as ub
     c = load_npz("case_diag_train_pad.npz")
     x, y, d = (torch.from_numpy(c[k]).cuda() for k in ("x", "y", "dates"))
@@ -213,37 +203,14 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3, 203])
-@pytest.mark.parametrize("groups,training", [(4, 1), (0, 1), (0, 0)])
-def test_mbconv_block_vs_oracle(golden_weights, groups, training, backend):
-    """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64)."""
-    from uncrtaints_b200 import _lib
-    L = _lib.lib()
-    fused = backend >= 200                  # 203: backend 3 with the fused (single-kernel) depthwise backward
-    if fused:
-        backend -= 200
-    split = not fused
-    L.ub200_dwconv_set_bwd_split(int(split))
-    L.ub200_dwconv_set_mode(0)              # the cp.async tile kernels (the row-streaming default has its own test below)
-    try:
-        _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split)
-    finally:
-        L.ub200_dwconv_set_bwd_split(1)
-        L.ub200_dwconv_set_mode(47)
-
-
-@pytest.mark.parametrize("mode", [3, 7, 15, 47])
-@pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16))])
-def test_mbconv_block_row_streaming_dwconv(golden_weights, groups, training, shape, mode):
-    """Same block check with the row-streaming (TMA bulk copy) depthwise kernels: edge strips only (W=32), interior strips
-    and several row chunks (64x64), a 3-strip non-square frame, and a single-strip frame (W=16: both reflect columns)."""
-    from uncrtaints_b200 import _lib
-    L = _lib.lib()
-    L.ub200_dwconv_set_mode(mode)
-    try:
-        _mbconv_block_vs_oracle(golden_weights, groups, training, 3, True, shape, f",dwmode={mode}")
-    finally:
-        L.ub200_dwconv_set_mode(47)
+@pytest.mark.parametrize("backend", [0, 1, 3])
+@pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16)),
+                                                   (0, 1, (3, 16, 32)), (0, 0, (3, 16, 32))])
+def test_mbconv_block_vs_oracle(golden_weights, groups, training, shape, backend):
+    """One MBConv block (uncrtaints.py:100-146) through ub200_mbconv_forward/backward vs oracle autograd (fp64): GroupNorm and
+    BatchNorm (train / eval) blocks; edge strips only (W=32), interior strips and several row chunks (64x64), a 3-strip
+    non-square frame, and a single-strip frame (W=16: both reflect columns) for the row-streaming depthwise kernels."""
+    _mbconv_block_vs_oracle(golden_weights, groups, training, backend, True, shape)
 
 
 @pytest.mark.parametrize("groups,training", [(4, 1), (0, 1)])
@@ -322,6 +289,7 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
     (1, 2, 256, 256, "diag", True, False, 1),     # same through the tcgen05 GEMMs
     (2, 5, 64, 96, "diag", True, True, 3),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
     (1, 3, 128, 64, "iso", False, False, 0),      # eval mode, isotropic covariance
+    (16, 3, 64, 64, "diag", True, False, 3),      # BASELINE config #2's batch and sequence length (BatchNorm over 16 samples)
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub
@@ -414,8 +382,8 @@ def test_philox_dropout_statistics(golden_weights):
     assert abs(float(a1.double().mean() / base.double().mean()) - 1.0) < 5e-3
 
 
-@pytest.mark.parametrize("backend,ws", [(0, 1), (1, 0), (1, 1)])
-def test_gemm1_op_vs_fp64(backend, ws):
+@pytest.mark.parametrize("backend", [0, 1])
+def test_gemm1_op_vs_fp64(backend):
     """The 1x1 expand GEMM alone (ub200_gemm1_forward): fp32 CUDA-core path and tcgen05 bf16x3 path vs an fp64 matmul."""
     from uncrtaints_b200 import _lib
     L = _lib.lib()
@@ -430,17 +398,13 @@ def test_gemm1_op_vs_fp64(backend, ws):
     h1 = torch.zeros(N, P, 256, device="cuda")
     stats = torch.zeros(N, 256, 2, dtype=torch.float64, device="cuda")
     scratch = torch.empty(256 * 1024, dtype=torch.uint8, device="cuda")
-    L.ub200_tc_set_warp_specialized(ws)       # 1 = producer/epilogue warp-specialised kernel, 0 = single-role kernel (default)
-    try:
-        _lib.check(L.ub200_gemm1_forward(backend, xd.data_ptr(), cd.data_ptr(), wd.data_ptr(), h1.data_ptr(), stats.data_ptr(), N, P,
-                                         scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "gemm1_forward")
-        torch.cuda.synchronize()
-    finally:
-        L.ub200_tc_set_warp_specialized(0)
+    _lib.check(L.ub200_gemm1_forward(backend, xd.data_ptr(), cd.data_ptr(), wd.data_ptr(), h1.data_ptr(), stats.data_ptr(), N, P,
+                                     scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "gemm1_forward")
+    torch.cuda.synchronize()
     e = rel_l2(h1, ref)
     es = rel_l2(stats[..., 0], ref.sum(1))
     eq = rel_l2(stats[..., 1], (ref ** 2).sum(1))
-    report("parity_report.txt", [f"gemm1 op backend={backend} ws={ws}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
+    report("parity_report.txt", [f"gemm1 op backend={backend}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
     assert e < 5e-5 and es < 1e-4 and eq < 1e-4
 
 
@@ -548,20 +512,6 @@ def test_model_single_pass_bf16_backend(golden_weights):
     assert sorted(gerr.values())[len(gerr) // 2] <= 5e-2
 
 
-@pytest.mark.parametrize("mask", [1, 3])
-def test_mbconv_block_dual_role_gemm(golden_weights, mask):
-    """ub200_tc_set_dual: input-gradient and weight-gradient GEMMs of a 1x1 convolution as the two roles of one launch (paired
-    CTAs share their activation reads through the L2); same block check as the two-launch default."""
-    from uncrtaints_b200 import _lib
-    L = _lib.lib()
-    L.ub200_tc_set_dual(mask)
-    try:
-        _mbconv_block_vs_oracle(golden_weights, 4, 1, 3, True, (2, 64, 64), f",dual={mask}")
-        _mbconv_block_vs_oracle(golden_weights, 0, 1, 3, True, (3, 32, 64), f",dual={mask}")
-    finally:
-        L.ub200_tc_set_dual(0)
-
-
 def test_golden_gnll():
     """GaussianNLLLoss (`--loss GNLL`, covmode 'uni') on the CUDA path against the fixture generated from the reference."""
     import uncrtaints_b200 as ub
@@ -600,3 +550,86 @@ def test_uni_covmode_model_with_gnll(golden_weights):
     assert vout.shape == (B, 1, 13, H, W)
     assert rel_l2(out, o_out) <= TOL and abs(loss.item() - o_loss.item()) / abs(o_loss.item()) <= TOL
     check_grads(net.named_parameters(), o_grads, "uni+gnll")
+
+
+def _oracle_step64(golden_weights, x, y, d, cfg, train, keep, pool_idx=None, fused=True):
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in golden_weights.items()}
+    cov = cfg.covar_dim
+    sd64["out_conv.conv.conv.0.weight"] = sd64["out_conv.conv.conv.0.weight"][:13 + cov]
+    sd64["out_conv.conv.conv.0.bias"] = sd64["out_conv.conv.conv.0.bias"][:13 + cov]
+    O.set_fused(fused)
+    try:
+        return O.step(sd64, x.double(), y.double(), d.double(), cfg, train, keep, pool_idx=pool_idx)
+    finally:
+        O.set_fused(False)
+
+
+@pytest.mark.parametrize("B,T,covmode", [(2, 3, "diag"), (1, 3, "iso")])
+def test_headline_resolution_default_backend(golden_weights, B, T, covmode):
+    """BASELINE config #2's frame size (15x256x256, T=3) through the DEFAULT backend (tcgen05 bf16x3 forward, input-gradient and
+    weight-gradient GEMMs; 148 persistent weight-gradient CTAs with fp32 TMEM accumulation over ~2.6k pixels each at B=2)
+    against the fp64 oracle: outputs, loss and every gradient within 1e-3 -- and, with the max-pool index selection of the CUDA
+    run imposed on the oracle (O.gather_pool: the argmax itself is checked bit-exact on identical input in
+    test_golden_diag_train_pad), every gradient within 2e-4: what remains of the 5-8e-4 encoder-gradient error of the free
+    comparison is the discrete re-routing of a few near-tie windows, not arithmetic error."""
+    import uncrtaints_b200 as ub
+    H = W = 256
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=300 + B)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=9)
+    cfg = O.OracleConfig(covmode=covmode)
+    cov = cfg.covar_dim
+    net = make_net(golden_weights, covmode, None).train()          # backend None = the library default (3)
+    net._injected_keep_mask = keep.to(torch.uint8)
+    out = net(x.cuda(), batch_positions=d.cuda())
+    loss, _ = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=covmode, chunk=None, covariance="none")(
+        out[:, :, :13], y.cuda(), out[:, :, 13:13 + cov])
+    loss.backward()
+    torch.cuda.synchronize()
+    idx = tap(net, "pool_idx", (B * T, 32, 32, 128), torch.int32).permute(0, 3, 1, 2).cpu().long().contiguous()
+    tag = f"headline256[B{B}T{T} {covmode} backend=default]"
+    o_out, o_loss, o_grads, _ = _oracle_step64(golden_weights, x, y, d, cfg, True, keep)
+    e_out, e_loss = rel_l2(out, o_out), abs(loss.item() - o_loss.item()) / abs(o_loss.item())
+    gerr = {k: rel_l2(p.grad, o_grads[k]) for k, p in net.named_parameters() if not is_zero_grad_param(k)}
+    worst = max(gerr, key=gerr.get)
+    p_out, p_loss, p_grads, _ = _oracle_step64(golden_weights, x, y, d, cfg, True, keep, pool_idx=idx)
+    perr = {k: rel_l2(p.grad, p_grads[k]) for k, p in net.named_parameters() if not is_zero_grad_param(k)}
+    pworst = max(perr, key=perr.get)
+    report("parity_report.txt", [
+        f"{tag} out rel_l2={e_out:.3e} loss rel={e_loss:.3e} worst grad {worst} rel_l2={gerr[worst]:.3e}",
+        f"{tag} with the CUDA run's argmax imposed on the oracle: out rel_l2={rel_l2(out, p_out):.3e} worst grad {pworst} "
+        f"rel_l2={perr[pworst]:.3e} median {sorted(perr.values())[len(perr) // 2]:.3e}"])
+    assert e_out <= TOL and e_loss <= TOL
+    check_grads(net.named_parameters(), o_grads, tag)
+    assert rel_l2(out, p_out) <= 2e-4
+    assert perr[pworst] <= 2e-4, (pworst, perr[pworst])
+
+
+def test_config2_forward_vs_oracle(golden_weights):
+    """BASELINE config #2 itself (B=16, T=3, 15x256x256, diag, train mode, default backend): network output and MGNLL loss against
+    the oracle run in fp32 under no_grad on the host (fused ATen ops = what the reference's modules execute; ~15 s).  The
+    backward at this batch is covered by (16,3,64,64) in test_model_vs_oracle, by the 256x256 gradient test above and by the
+    full-size gradient properties in test_gpu_properties.py."""
+    import uncrtaints_b200 as ub
+    B, T, H, W = 16, 3, 256, 256
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=1234)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=11)
+    cfg = O.OracleConfig(covmode="diag")
+    O.set_fused(True)
+    try:
+        with torch.no_grad():
+            o_out = O.forward(dict(golden_weights), x, d, cfg, True, keep)
+            o_loss = O.mgnll(o_out[:, :, :13], y, o_out[:, :, 13:26], "diag")
+    finally:
+        O.set_fused(False)
+    net = make_net(golden_weights, "diag", None).train()
+    net._injected_keep_mask = keep.to(torch.uint8)
+    with torch.no_grad():
+        out = net(x.cuda(), batch_positions=d.cuda())
+        loss, _ = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None, covariance="none")(
+            out[:, :, :13], y.cuda(), out[:, :, 13:26])
+    e_out, e_loss = rel_l2(out, o_out), abs(loss.item() - o_loss.item()) / abs(o_loss.item())
+    mse = float(((out[:, :, :13].cpu().double() - o_out[:, :, :13].double()) / 10.0).square().mean())
+    psnr = 20 * np.log10(1.0 / np.sqrt(mse)) if mse > 0 else float("inf")
+    report("parity_report.txt", [f"config#2 forward (B16 T3 256x256 diag train, default backend): out rel_l2={e_out:.3e} "
+                                 f"loss rel={e_loss:.3e} PSNR(mean pred vs oracle)={psnr:.1f} dB"])
+    assert e_out <= TOL and e_loss <= TOL

@@ -200,3 +200,20 @@ def test_oracle_gnll_matches_live_reference_fp64():
     g_own = torch.autograd.grad(l_own, [pred, var])
     assert abs(l_ref.item() - l_own.item()) < 1e-12 * abs(l_ref.item())
     assert torch.allclose(v_ref, v_own) and all(torch.allclose(a, b, rtol=1e-12, atol=1e-15) for a, b in zip(g_ref, g_own))
+
+
+def test_imposed_pool_index_is_a_noop_for_the_oracles_own_argmax(golden_weights):
+    """`forward(..., pool_idx=...)` (diagnostic used by the 256x256 GPU gradient test): imposing the oracle's own argmax leaves
+    output and gradients unchanged; imposing a different element of one window changes the encoder gradients only."""
+    x, y, d = O.synthetic_batch(1, 2, 32, 32, seed=77)
+    keep = O.dropout_keep_mask(16, 1, 2, 32, 32, seed=78)
+    cfg = O.OracleConfig()
+    sd = _sd64(golden_weights)
+    taps = {}
+    O.forward(sd, x.double(), d.double(), cfg, True, keep, None, taps)
+    idx = taps["pool_idx"]
+    out0, loss0, g0, _ = O.step(sd, x.double(), y.double(), d.double(), cfg, True, keep)
+    out1, loss1, g1, _ = O.step(sd, x.double(), y.double(), d.double(), cfg, True, keep, pool_idx=idx)
+    assert torch.equal(out0, out1) and float(loss0) == float(loss1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k

@@ -21,7 +21,16 @@ def _worker(rank, world, port, q):
     lin(data[sl]).pow(2).mean().backward()
     local = bucket.flat.clone()
     bucket.all_reduce_mean()
-    q.put((rank, sl.start, sl.stop, local, bucket.flat.clone(), [p.grad.data_ptr() for p in lin.parameters()],
+    first = bucket.flat.clone()
+    # the reference's own step calls optimizer.zero_grad() (base_model.py:120), which sets the grads to None in torch >= 2:
+    # the next backward then creates fresh gradient tensors.  The bucket must fold them back in, not reduce stale data.
+    torch.optim.SGD(lin.parameters(), lr=0.1).zero_grad()
+    assert all(p.grad is None for p in lin.parameters())
+    (3.0 * lin(data[sl]).pow(2).mean()).backward()
+    bucket.all_reduce_mean()
+    assert bucket.reattached == 4 and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    assert torch.allclose(bucket.flat, 3.0 * first, rtol=1e-5, atol=1e-7), "gradients created after zero_grad(set_to_none) were lost"
+    q.put((rank, sl.start, sl.stop, local.tolist(), first.tolist(), [p.grad.data_ptr() for p in lin.parameters()],
            bucket.flat.data_ptr()))
     dist.barrier()
     dist.destroy_process_group()
@@ -39,6 +48,7 @@ def test_flat_grad_allreduce_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     (r0, a0, b0, l0, f0, ptrs0, base0), (r1, a1, b1, l1, f1, _, _) = res
+    l0, f0, l1, f1 = (torch.tensor(t) for t in (l0, f0, l1, f1))
     assert (a0, b0, a1, b1) == (0, 2, 2, 4)
     assert torch.allclose(f0, f1) and torch.allclose(f0, (l0 + l1) / 2, atol=1e-7)
     assert ptrs0[0] == base0                      # param.grad aliases the flat buffer: one collective per step

@@ -12,6 +12,7 @@ from .losses import (MultiGaussianNLLLoss, GaussianNLLLoss, get_loss, calc_loss,
                      gaussian_nll_loss, covariance_diag)
 from .install import install  # noqa: F401
 from .parallel import FlatGradAllReduce, HostToDevicePrefetcher, HostScalarReader, shard_batch  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
 __all__ = ["UNCRTAINTS", "MultiGaussianNLLLoss", "GaussianNLLLoss", "gaussian_nll_loss", "get_loss", "calc_loss", "multi_gaussian_nll_loss", "covariance_diag",
-           "install", "FlatGradAllReduce", "HostToDevicePrefetcher", "HostScalarReader", "shard_batch", "set_default_gemm_backend"]
+           "install", "FusedAdam", "FlatGradAllReduce", "HostToDevicePrefetcher", "HostScalarReader", "shard_batch", "set_default_gemm_backend"]

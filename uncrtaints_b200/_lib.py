@@ -23,9 +23,9 @@ ERRORS = {-1: "UB200_ERR_ARG (unsupported shape / configuration)", -2: "UB200_ER
 # every symbol include/uncrtaints_b200.h declares
 SYMBOLS = [
     "ub200_version", "ub200_launch_count", "ub200_prof_enable", "ub200_prof_num_kernels", "ub200_prof_kernel_name",
-    "ub200_prof_read", "ub200_tc_debug_set", "ub200_tc_debug_set_wgrad", "ub200_tc_set_warp_specialized", "ub200_tc_set_split_epilogue", "ub200_tc_set_dual", "ub200_dwconv_set_bwd_split", "ub200_dwconv_set_mode", "ub200_inconv_set_moments", "ub200_gemm1_forward", "ub200_wgrad1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
-    "ub200_backward", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
-    "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward",
+    "ub200_prof_read", "ub200_gemm1_forward", "ub200_wgrad1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
+    "ub200_backward", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_mgnll_none", "ub200_gnll_none", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
+    "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward", "ub200_adam_step",
 ]
 
 
@@ -64,15 +64,7 @@ def lib() -> C.CDLL:
     L.ub200_prof_kernel_name.argtypes = [i]
     L.ub200_prof_kernel_name.restype = C.c_char_p
     L.ub200_prof_read.argtypes = [i, C.POINTER(C.c_double), C.POINTER(i)]
-    L.ub200_tc_debug_set.argtypes = [C.c_uint, C.c_uint, C.c_uint]
     L.ub200_gemm1_forward.argtypes = [i, vp, vp, vp, vp, vp, i, i, vp, vp]
-    L.ub200_tc_debug_set_wgrad.argtypes = [C.c_uint, C.c_uint, C.c_uint]
-    L.ub200_tc_set_warp_specialized.argtypes = [i]
-    L.ub200_tc_set_split_epilogue.argtypes = [i]
-    L.ub200_tc_set_dual.argtypes = [i]
-    L.ub200_dwconv_set_bwd_split.argtypes = [i]
-    L.ub200_dwconv_set_mode.argtypes = [i]
-    L.ub200_inconv_set_moments.argtypes = [i]
     L.ub200_wgrad1_forward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
     L.ub200_num_param_slots.argtypes = [dp]
     L.ub200_workspace_bytes.argtypes = [dp]
@@ -82,22 +74,17 @@ def lib() -> C.CDLL:
     L.ub200_backward.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, C.POINTER(vp), vp, sz, vp]
     L.ub200_mgnll_forward.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, f, vp, vp, vp, vp, vp, vp]
     L.ub200_gnll_forward.argtypes = [vp, ll, vp, ll, vp, ll, i, i, f, i, vp, vp, vp, vp, vp, vp, vp]
+    L.ub200_mgnll_none.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, f, vp, vp, vp, vp, vp, vp]
+    L.ub200_gnll_none.argtypes = [vp, ll, vp, ll, vp, ll, i, i, f, i, vp, vp, vp, vp, vp, vp, vp]
     L.ub200_scale_by_scalar.argtypes = [vp, vp, vp, sz, vp]
     L.ub200_covariance.argtypes = [vp, ll, i, i, i, f, vp, vp]
     L.ub200_mbconv_workspace_bytes.argtypes = [i, i, i]
     L.ub200_mbconv_workspace_bytes.restype = sz
     L.ub200_mbconv_forward.argtypes = [vp, C.POINTER(vp), i, i, i, i, i, f, f, i, vp, vp, sz, vp]
     L.ub200_mbconv_backward.argtypes = [vp, C.POINTER(vp), vp, C.POINTER(vp), i, i, i, i, i, i, vp, vp, sz, vp]
+    L.ub200_adam_step.argtypes = [vp, vp, vp, vp, sz, i, f, f, f, f, f, f, i, vp]
     L.ub200_head_forward.argtypes = [vp, vp, vp, vp, i, i, i, f, i, f, vp]
     L.ub200_head_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, i, f, vp]
-    if os.environ.get("UB200_TC_DUAL"):
-        L.ub200_tc_set_dual(int(os.environ["UB200_TC_DUAL"]))
-    if os.environ.get("UB200_TC_SPLIT_EPI"):
-        L.ub200_tc_set_split_epilogue(int(os.environ["UB200_TC_SPLIT_EPI"], 0))
-    if os.environ.get("UB200_INCONV_MOMENTS"):
-        L.ub200_inconv_set_moments(int(os.environ["UB200_INCONV_MOMENTS"]))
-    if os.environ.get("UB200_DWCONV_MODE"):          # development override of the depthwise kernel family
-        L.ub200_dwconv_set_mode(int(os.environ["UB200_DWCONV_MODE"]))
     _lib = L
     return L
 

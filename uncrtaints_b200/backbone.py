@@ -180,16 +180,18 @@ class _UncrtaintsFunction(torch.autograd.Function):
             raise NotImplementedError(
                 f"unsupported configuration for the B200 path: B={desc.B} T={desc.T} C_in={desc.C_in} H={desc.H} W={desc.W} "
                 "(need H, W multiples of 32, T <= 8, C_in <= 16)")
-        # one workspace alive per model in the usual loop: drop the debugging reference to the previous call's workspace so that
-        # the caching allocator hands the same block back (at B=32, T=5 it is 102 GB: two would not fit in 180 GB)
+        # The workspace lives from this forward to its backward only (at B=32, T=5 it is 102 GB: two would not fit in 180 GB).
+        # ``net.keep_workspace = True`` (tests / debugging: ub200_workspace_tap) additionally keeps the last one on the module.
         net._last_workspace = None
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        out = torch.empty((desc.B, 1, desc.out_dim, desc.H, desc.W), dtype=torch.float32, device=x.device)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        params = _lib.ptr_table(table)
-        _lib.check(L.ub200_forward(desc, x.data_ptr(), params, keep_mask.data_ptr() if keep_mask is not None else None,
-                                   out.data_ptr(), ws.data_ptr(), ws_bytes, stream), "ub200_forward")
-        net._last_workspace = (desc, ws)
+        with torch.cuda.device(x.device):            # the C ABI launches on the CURRENT device: make it the tensors' device
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            out = torch.empty((desc.B, 1, desc.out_dim, desc.H, desc.W), dtype=torch.float32, device=x.device)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            params = _lib.ptr_table(table)
+            _lib.check(L.ub200_forward(desc, x.data_ptr(), params, keep_mask.data_ptr() if keep_mask is not None else None,
+                                       out.data_ptr(), ws.data_ptr(), ws_bytes, stream), "ub200_forward")
+        if net.keep_workspace:
+            net._last_workspace = (desc, ws)
         if need_grad:
             ctx.net, ctx.desc, ctx.ws, ctx.table, ctx.slots = net, desc, ws, table, slots
             ctx.keep_mask = keep_mask
@@ -199,6 +201,9 @@ class _UncrtaintsFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         L = _lib.lib()
+        if ctx.ws is None:
+            raise RuntimeError("uncrtaints_b200: backward through UNCRTAINTS.forward a second time -- the activation workspace is "
+                               "released after the first backward (retain_graph is not supported); run the forward again")
         x, out, *tensors = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         # The C ABI ACCUMULATES into every gradient slot.  Parameters whose .grad is owned by a FlatGradAllReduce (flagged
@@ -224,11 +229,12 @@ class _UncrtaintsFunction(torch.autograd.Function):
             gtable[slot] = v.data_ptr()
             views.append(v.view_as(t))
             off += n
-        stream = torch.cuda.current_stream(x.device).cuda_stream
         km = ctx.keep_mask
-        _lib.check(L.ub200_backward(ctx.desc, x.data_ptr(), _lib.ptr_table(ctx.table), km.data_ptr() if km is not None else None,
-                                    out.data_ptr(), grad_out.data_ptr(), _lib.ptr_table(gtable), ctx.ws.data_ptr(),
-                                    ctx.ws.numel(), stream), "ub200_backward")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.ub200_backward(ctx.desc, x.data_ptr(), _lib.ptr_table(ctx.table), km.data_ptr() if km is not None else None,
+                                        out.data_ptr(), grad_out.data_ptr(), _lib.ptr_table(gtable), ctx.ws.data_ptr(),
+                                        ctx.ws.numel(), stream), "ub200_backward")
         ctx.ws = None
         return (None, None, None, None, *views)
 
@@ -285,6 +291,7 @@ class UNCRTAINTS(nn.Module):
         self.variance = None
         self.gemm_backend = gemm_backend
         self._injected_keep_mask = None      # tests: explicit dropout keep mask uint8 [16,B,T,H,W]
+        self.keep_workspace = False          # debugging: keep (desc, workspace) of the last forward in _last_workspace
         self._last_workspace = None
         self._build_slots()
 

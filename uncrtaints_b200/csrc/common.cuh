@@ -32,7 +32,33 @@ namespace ub { extern unsigned long long g_launch_count; }   // kernels launched
         ++::ub::g_launch_count;                            \
     } while (0)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE, so the "already done" cache is a
+// per-call-site bit mask indexed by the current device (a process may drive several GPUs).
+#define UB_SET_SMEM(kern, bytes)                                                                                       \
+    do {                                                                                                               \
+        static unsigned long long done__ = 0ull;                                                                       \
+        int dev__ = 0;                                                                                                 \
+        if (cudaGetDevice(&dev__) != cudaSuccess) return UB_ERR_CUDA;                                                  \
+        if (dev__ >= 64 || !((done__ >> dev__) & 1ull)) {                                                              \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) != cudaSuccess)  \
+                return UB_ERR_CUDA;                                                                                    \
+            if (dev__ < 64) done__ |= 1ull << dev__;                                                                   \
+        }                                                                                                              \
+    } while (0)
+
 namespace ub {
+
+// SM count of the CURRENT device (cached per device)
+inline int device_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    return n;
+}
 
 // ---- per-(frame, channel) coefficient records --------------------------------------------
 // forward:  v_norm = v * scale + shift          (GroupNorm and BatchNorm alike)
@@ -136,6 +162,9 @@ __device__ __forceinline__ float4 gelu_grad4_packed(const float4 z) {
 }
 __device__ __forceinline__ float gelu_f(float x) { float g, gp; gelu_both(x, g, gp); return g; }
 __device__ __forceinline__ float gelu_grad_f(float x) { float g, gp; gelu_both(x, g, gp); return gp; }
+// torch.clamp_(min=eps) (losses.py:203-205) keeps NaN; CUDA's fmaxf(NaN, eps) would return eps and hide a diverged
+// variance head behind a finite loss
+__device__ __forceinline__ float clamp_min_keep_nan(float v, float lo) { return v != v ? v : fmaxf(v, lo); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -13,7 +13,7 @@
 //   * one __syncthreads later the stencil for row y reads rows y-1, y, y+1 of the ring.  A thread owns one channel quad
 //     and 4 adjacent columns: a 6-column window per ring row (6 LDS.128) feeds 4 pixels x 3 taps, the 9 x 4 depthwise
 //     taps, the Norm coefficients and the weight-gradient accumulators live in registers.
-// The backward kernel is the input-stationary form of dwconv.cu (D[tap] gathered per INPUT pixel, so gelu(z1), gelu'(z1)
+// The backward kernel is input-stationary (D[tap] gathered per INPUT pixel, so gelu(z1), gelu'(z1)
 // are evaluated once per pixel and dW needs no second tile); the adjoint of reflect padding is a rare warp-uniform
 // correction.  HBM traffic: forward 2 Hh, backward 4 Hh (du, h2, h1 in, dz1 out) -- the split dh2 + stencil pair moved 6.
 #include "common.cuh"
@@ -193,233 +193,18 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
     reduce_sq(ssum, qsum, stats2 + (size_t)n * RC * 2, sD, q, s);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// B3 fused:  dz2 = (du*gate + dpool/P) * gelu'(z2);  dh2 = a2*dz2 + b2*h2 + c2;  dg1 = DW3x3^T(dh2) (+ reflect adjoint);
-//            dz1 = dg1 * gelu'(z1);  dWdw[c][tap] += sum_p g1[p] * D[tap][p];  bstats1 += (sum dz1, sum dz1 * h1_hat)
-// grid (W/16, H/R, N), 256 threads, 1 CTA / SM (200 KB of rings)
-// ------------------------------------------------------------------------------------------------------------------
-template <bool F2, bool PG>
-__global__ void __launch_bounds__(256, 1)
-dwrows_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
-                  const float* __restrict__ gate, const float* __restrict__ dmp, const Coef* __restrict__ coef2,
-                  const BCoef* __restrict__ bc2, const Coef* __restrict__ coef1, const MeanRstd* __restrict__ mr1,
-                  const float* __restrict__ wdw, float* __restrict__ dz1, double* bstats1, float* dwdw, int H, int W, int R) {
-    extern __shared__ __align__(128) float smem[];
-    float* sD = smem;                                   // du -> dh2 ring, 5 halo rows
-    float* sH2 = sD + ND * ROWF;                        // h2 staging, 3 halo rows
-    float* sH1 = sH2 + NH2 * ROWF;                      // h1 staging, 3 centre rows
-    float4* sK2 = reinterpret_cast<float4*>(sH1 + NH1 * ROWC);   // [256] scale2, shift2, gate, dpool/P
-    float4* sB2 = sK2 + RC;                                        // [256] a2, b2, c2, -
-    const uint32_t barD = s32(sB2 + RC), barH2 = barD + ND * 8, barH1 = barH2 + NH2 * 8;
-    const int tid = threadIdx.x, q = tid & (RQ - 1), s = tid >> 6;
-    const int n = blockIdx.z, x0 = blockIdx.x * RW, ybase = blockIdx.y * R;
-    const size_t fbase = (size_t)n * H * W * RC;
-    {
-        const size_t ci = (size_t)n * RC + tid;
-        const Coef a = coef2[ci];
-        const BCoef bb = bc2[ci];
-        // channel ch = 4*quad + comp is stored at [comp * 64 + quad]: a warp's 32 quads read 512 contiguous bytes
-        const int slot = (tid & 3) * RQ + (tid >> 2);
-        sK2[slot] = make_float4(a.scale, a.shift, gate[ci], dmp[ci]);
-        sB2[slot] = make_float4(bb.a, bb.b, bb.c, 0.f);
-    }
-    float4 wr[9], sc1, sh1, mu1, rs1;
-    {
-        float w_[9][4], a_[4], b_[4], m_[4], r_[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const size_t ci = (size_t)n * RC + q * 4 + c;
-            const Coef k = coef1[ci];
-            const MeanRstd m = mr1[ci];
-            a_[c] = k.scale; b_[c] = k.shift; m_[c] = m.mean; r_[c] = m.rstd;
-#pragma unroll
-            for (int j = 0; j < 9; ++j) w_[j][c] = wdw[(size_t)(q * 4 + c) * 9 + j];
-        }
-        sc1 = make_float4(a_[0], a_[1], a_[2], a_[3]);
-        sh1 = make_float4(b_[0], b_[1], b_[2], b_[3]);
-        mu1 = make_float4(m_[0], m_[1], m_[2], m_[3]);
-        rs1 = make_float4(r_[0], r_[1], r_[2], r_[3]);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) wr[j] = make_float4(w_[j][0], w_[j][1], w_[j][2], w_[j][3]);
-    }
-    if (tid == 0) {
-        for (int i = 0; i < ND + NH2 + NH1; ++i) mbar_init(barD + i * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int xs = max(x0 - 1, 0), xe = min(x0 + RW + 1, W);
-    const uint32_t rowbytes = (uint32_t)(xe - xs) * RC * 4;
-    const int dstoff = (xs - (x0 - 1)) * RC;
-    const int NIT = R + 2;
-    auto issue_dh = [&](int i) {    // thread 0: du / h2 halo row i (image row ybase-1+i) -> sD[i % ND], sH2[i % NH2]
-        const int y = ybase - 1 + i;
-        const uint32_t bd = barD + (i % ND) * 8, bh = barH2 + (i % NH2) * 8;
-        if (y >= 0 && y < H) {
-            const size_t g = fbase + ((size_t)y * W + xs) * RC;
-            mbar_expect_tx(bd, rowbytes);
-            bulk_g2s(s32(sD + (i % ND) * ROWF + dstoff), du + g, rowbytes, bd);
-            mbar_expect_tx(bh, rowbytes);
-            bulk_g2s(s32(sH2 + (i % NH2) * ROWF + dstoff), h2 + g, rowbytes, bh);
-        } else {                    // row outside the image: nothing to load, keep the barrier phases in step
-            mbar_arrive(bd);
-            mbar_arrive(bh);
-        }
-    };
-    auto issue_h1 = [&](int c) {    // thread 0: h1 centre row c -> sH1[c % NH1]
-        const uint32_t b = barH1 + (c % NH1) * 8;
-        mbar_expect_tx(b, ROWC * 4);
-        bulk_g2s(s32(sH1 + (c % NH1) * ROWC), h1 + fbase + ((size_t)(ybase + c) * W + x0) * RC, ROWC * 4, b);
-    };
-    if (tid == 0) { issue_dh(0); issue_dh(1); }
-    float4 gw[9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) gw[j] = make_float4(0, 0, 0, 0);
-    float4 ssum = make_float4(0, 0, 0, 0), qsum = make_float4(0, 0, 0, 0);
-    const int xbase = x0 + 4 * s;
-    const bool colb = (xbase <= 1 && 1 < xbase + 4) || (xbase <= W - 2 && W - 2 < xbase + 4);
-
-    for (int i = 0; i < NIT; ++i) {
-        // ---- du row -> dh2 row in place (pixel px = s + 4k, channel quad q); 0 outside the image ----
-        {
-            const int y = ybase - 1 + i;
-            const bool row_in = (y >= 0 && y < H);
-            float* d = sD + (i % ND) * ROWF;
-            const float* hh = sH2 + (i % NH2) * ROWF;
-            mbar_wait(barD + (i % ND) * 8, (uint32_t)(i / ND) & 1u);
-            mbar_wait(barH2 + (i % NH2) * 8, (uint32_t)(i / NH2) & 1u);
-            const float4 k0 = sK2[q], k1 = sK2[RQ + q], k2 = sK2[2 * RQ + q], k3 = sK2[3 * RQ + q];
-            const float4 b0 = sB2[q], b1 = sB2[RQ + q], b2 = sB2[2 * RQ + q], b3 = sB2[3 * RQ + q];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int px = s + 4 * k;
-                if (px < RWH) {
-                    const int x = x0 - 1 + px;
-                    float4 o = make_float4(0, 0, 0, 0);
-                    if (row_in && x >= 0 && x < W) {
-                        const float4 dv = ld4(d + px * RC + q * 4);
-                        const float4 hv = ld4(hh + px * RC + q * 4);
-                        const float4 z = make_float4(fmaf(hv.x, k0.x, k0.y), fmaf(hv.y, k1.x, k1.y), fmaf(hv.z, k2.x, k2.y), fmaf(hv.w, k3.x, k3.y));
-                        float4 gp;
-                        if constexpr (PG) gp = gelu_grad4_packed(z);
-                        else gp = make_float4(gelu_grad_f(z.x), gelu_grad_f(z.y), gelu_grad_f(z.z), gelu_grad_f(z.w));
-                        o.x = fmaf(b0.x, fmaf(dv.x, k0.z, k0.w) * gp.x, fmaf(b0.y, hv.x, b0.z));
-                        o.y = fmaf(b1.x, fmaf(dv.y, k1.z, k1.w) * gp.y, fmaf(b1.y, hv.y, b1.z));
-                        o.z = fmaf(b2.x, fmaf(dv.z, k2.z, k2.w) * gp.z, fmaf(b2.y, hv.z, b2.z));
-                        o.w = fmaf(b3.x, fmaf(dv.w, k3.z, k3.w) * gp.w, fmaf(b3.y, hv.w, b3.z));
-                    }
-                    st4(d + px * RC + q * 4, o);
-                }
-            }
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            if (i + 2 < NIT) issue_dh(i + 2);
-            if (i < R) issue_h1(i);
-        }
-        if (i < 2) continue;
-        // ---- input-stationary stencil for image row yc: 4 pixels x 1 channel quad per thread ----
-        const int c = i - 2, yc = ybase + c;
-        const int woff = (4 * s) * RC + q * 4;
-        const float* rp0 = sD + ((i - 2) % ND) * ROWF + woff;     // dh2 row yc-1, window column 0 = image column xbase-1
-        const float* rp1 = sD + ((i - 1) % ND) * ROWF + woff;     // dh2 row yc
-        const float* rp2 = sD + (i % ND) * ROWF + woff;           // dh2 row yc+1
-        mbar_wait(barH1 + (c % NH1) * 8, (uint32_t)(c / NH1) & 1u);
-        const float* hp = sH1 + (c % NH1) * ROWC + woff;
-        float4 g[4], gp[4], o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 hv = ld4(hp + j * RC);
-            const float4 z = make_float4(fmaf(hv.x, sc1.x, sh1.x), fmaf(hv.y, sc1.y, sh1.y), fmaf(hv.z, sc1.z, sh1.z), fmaf(hv.w, sc1.w, sh1.w));
-            if constexpr (PG) gelu_both4_packed(z, g[j], gp[j]);
-            else {
-                gelu_both(z.x, g[j].x, gp[j].x); gelu_both(z.y, g[j].y, gp[j].y);
-                gelu_both(z.z, g[j].z, gp[j].z); gelu_both(z.w, g[j].w, gp[j].w);
-            }
-            o[j] = make_float4(0, 0, 0, 0);
-        }
-        // regular readers: tap (it, jj) of input pixel (yc, x) is read by output (yc - (it-1), x - (jj-1))
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float* rp = r == 0 ? rp0 : (r == 1 ? rp1 : rp2);
-            const int it = 2 - r;
-            float4 win[6];
-#pragma unroll
-            for (int wc = 0; wc < 6; ++wc) win[wc] = ld4(rp + wc * RC);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int jj = 0; jj < 3; ++jj) {
-                    fma4<F2>(o[j], wr[it * 3 + jj], win[j + 2 - jj]);
-                    fma4<F2>(gw[it * 3 + jj], g[j], win[j + 2 - jj]);
-                }
-        }
-        // adjoint of reflect padding (rows 1 / H-2, columns 1 / W-2 only): the mirrored readers
-        const bool y_lo = (yc == 1), y_hi = (yc == H - 2);
-        if (y_lo | y_hi | colb) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool x_lo = (xbase + j == 1), x_hi = (xbase + j == W - 2);
-                if (y_lo | y_hi | x_lo | x_hi) {
-#pragma unroll
-                    for (int it = 0; it < 3; ++it)
-#pragma unroll
-                        for (int jj = 0; jj < 3; ++jj) {
-                            const bool ya = (it == 0 && y_lo) || (it == 2 && y_hi);
-                            const bool xa = (jj == 0 && x_lo) || (jj == 2 && x_hi);
-                            if (ya | xa) {
-                                const float* ra = it == 0 ? rp0 : (it == 1 ? rp1 : rp2);        // row yc + (it-1)
-                                const float* rb = it == 0 ? rp2 : (it == 1 ? rp1 : rp0);        // row yc - (it-1)
-                                float4 e = make_float4(0, 0, 0, 0);
-                                if (ya) { const float4 t = ld4(ra + (j + 2 - jj) * RC); e.x += t.x; e.y += t.y; e.z += t.z; e.w += t.w; }
-                                if (xa) { const float4 t = ld4(rb + (j + jj) * RC); e.x += t.x; e.y += t.y; e.z += t.z; e.w += t.w; }
-                                if (ya && xa) { const float4 t = ld4(ra + (j + jj) * RC); e.x += t.x; e.y += t.y; e.z += t.z; e.w += t.w; }
-                                fma4<F2>(o[j], wr[it * 3 + jj], e);
-                                fma4<F2>(gw[it * 3 + jj], g[j], e);
-                            }
-                        }
-                }
-            }
-        }
-        float* op = dz1 + fbase + ((size_t)yc * W + xbase) * RC + q * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 dz = make_float4(o[j].x * gp[j].x, o[j].y * gp[j].y, o[j].z * gp[j].z, o[j].w * gp[j].w);
-            st4(op + j * RC, dz);
-            const float4 hv = ld4(hp + j * RC);
-            ssum.x += dz.x; ssum.y += dz.y; ssum.z += dz.z; ssum.w += dz.w;
-            qsum.x = fmaf(dz.x, (hv.x - mu1.x) * rs1.x, qsum.x);
-            qsum.y = fmaf(dz.y, (hv.y - mu1.y) * rs1.y, qsum.y);
-            qsum.z = fmaf(dz.z, (hv.z - mu1.z) * rs1.z, qsum.z);
-            qsum.w = fmaf(dz.w, (hv.w - mu1.w) * rs1.w, qsum.w);
-        }
-    }
-    __syncthreads();
-    reduce_sq(ssum, qsum, bstats1 + (size_t)n * RC * 2, sD, q, s);
-    // depthwise weight gradient: sum over the 4 column groups, one atomic per (channel, tap) per CTA
-    float4* red = reinterpret_cast<float4*>(sD);
-#pragma unroll
-    for (int j = 0; j < 9; ++j) red[(j * 4 + s) * RQ + q] = gw[j];
-    __syncthreads();
-    for (int e = tid; e < 9 * RC; e += 256) {
-        const int j = e / RC, ch = e % RC;
-        float t = 0.f;
-#pragma unroll
-        for (int ss = 0; ss < 4; ++ss) t += sD[(j * 4 + ss) * RC + ch];
-        atomicAdd(&dwdw[(size_t)ch * 9 + j], t);
-    }
-}
-
 // (A warp-specialised form -- 8 stencil warps at 200 registers + 8 transform warps at 56 via setmaxnreg, mbarrier hand-off
 // per row instead of the CTA barrier -- was built and measured at 2.0 ms against 0.96 ms for this kernel at N=16: with the
 // 5-slot ring only one row can be in flight behind the three the stencil holds, and the lean transform warps lose their
 // ILP.  It was removed)
 
 // ------------------------------------------------------------------------------------------------------------------
-// B3 fused, 512-thread form: same tiles, rings, barriers and arithmetic as dwrows_bwd_kernel, but a thread owns a channel
-// PAIR (one f32x2 lane pair) instead of a quad.  Per-thread state halves (9 taps + 9 dW accumulators + coefficients:
-// 48 registers instead of 96), the kernel fits 128 registers, and 16 warps (4 per scheduler) are resident instead of 8:
-// the row loop is latency-bound (ncu r01: 45 % issue utilisation with 2 warps per scheduler), not throughput-bound.
+// B3 fused:  dz2 = (du*gate + dpool/P) * gelu'(z2);  dh2 = a2*dz2 + b2*h2 + c2;  dg1 = DW3x3^T(dh2) (+ reflect adjoint);
+//            dz1 = dg1 * gelu'(z1);  dWdw[c][tap] += sum_p g1[p] * D[tap][p];  bstats1 += (sum dz1, sum dz1 * h1_hat)
+// grid (W/16, H/R, N), 512 threads, 1 CTA / SM (200 KB of rings).  A thread owns a channel PAIR (one f32x2 lane pair) and 4
+// adjacent columns: 9 taps + 9 dW accumulators + coefficients are 48 registers, the kernel fits 128 registers and 16 warps
+// (4 per scheduler) are resident: the row loop is latency-bound (ncu r01: 45 % issue utilisation with 2 warps per scheduler
+// in the earlier 256-thread channel-quad form), not throughput-bound.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RP = RC / 2;     // channel pairs
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -646,54 +431,25 @@ int rows_per_cta(int H, int W, int N) {
 
 }  // namespace
 
-int launch_dwrows_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
-                      int f2, cudaStream_t st) {
+int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
+                      cudaStream_t st) {
     const int R = rows_per_cta(H, W, N);
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(dwrows_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(dwrows_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(dwrows_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess)
-            return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM((dwrows_fwd_kernel<true, true>), FWD_SMEM);
     const dim3 grid(W / RW, H / R, N);
-    if (f2 & 2) dwrows_fwd_kernel<true, true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
-    else if (f2) dwrows_fwd_kernel<true, false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
-    else dwrows_fwd_kernel<false, false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
+    dwrows_fwd_kernel<true, true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
 
-int launch_dwrows_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
+int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
                       const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
-                      float* dwdw, int N, int H, int W, int f2, cudaStream_t st) {
+                      float* dwdw, int N, int H, int W, cudaStream_t st) {
     const int R = rows_per_cta(H, W, N);
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(dwrows_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(dwrows_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(dwrows_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess)
-            return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM(dwrows_bwd2_kernel<true>, BWD_SMEM);
     const dim3 grid(W / RW, H / R, N);
-    if (f2 & 8) {      // 512-thread channel-pair variant
-        static bool p_attr = false;
-        if (!p_attr) {
-            if (cudaFuncSetAttribute(dwrows_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess)
-                return UB_ERR_CUDA;
-            p_attr = true;
-        }
-        dwrows_bwd2_kernel<true><<<grid, 512, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
-        UB_CHECK_LAUNCH();
-        return UB_OK;
-    }
-    if (f2 & 2) dwrows_bwd_kernel<true, true><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
-    else if (f2) dwrows_bwd_kernel<true, false><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
-    else dwrows_bwd_kernel<false, false><<<grid, 256, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
+    dwrows_bwd2_kernel<true><<<grid, 512, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }

@@ -213,11 +213,7 @@ static int launch_gemm(ALoad al, const float* Wt, Epi ep, int N, int P, cudaStre
     if (P % 64 != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)(K * NOUT + 64 * (K + 4)) * sizeof(float);
     auto kern = gemm_px_kernel<K, NOUT, ALoad, Epi>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM(kern, smem);
     const int tiles = P / 64;
     const int tpb = tiles >= 16 ? 16 : tiles;
     kern<<<dim3((tiles + tpb - 1) / tpb, N), 256, smem, st>>>(al, Wt, ep, P, tpb);
@@ -302,11 +298,7 @@ static int launch_wgrad(LA la, LB lb, float* partial, int max_parts, float* grad
     if (P % 64 != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)64 * (128 + 256) * sizeof(float);
     auto kern = wgrad_kernel<LA, LB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM(kern, smem);
     const long long total = (long long)N * (P / 64);
     int blocks = (int)(total < max_parts ? total : max_parts);
     kern<<<blocks, 256, smem, st>>>(la, lb, partial, P, total, sa, sb);

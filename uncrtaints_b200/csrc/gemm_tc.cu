@@ -31,13 +31,13 @@ constexpr int KBLK = 64;              // channels per K-block (one 128-byte swiz
 constexpr int NSTAGE = 2;
 constexpr int STAGE_BYTES = 2 * TILE_PX * KBLK * 2;   // hi + lo tiles, 32 KB
 
-// runtime-tunable descriptor constants (ub200_tc_debug_set; defaults follow cute/arch/mma_sm100_desc.hpp)
-__device__ __constant__ uint32_t c_desc_hi = (64u) | (1u << 14) | (2u << 29);   // SBO=1024B>>4, version=1, SWIZZLE_128B
-__device__ __constant__ uint32_t c_desc_lbo = 1u;                                // LBO field (ignored for SW128 K-major)
+// shared-memory matrix descriptor constants (layout of cute/arch/mma_sm100_desc.hpp)
+constexpr uint32_t c_desc_hi = (64u) | (1u << 14) | (2u << 29);   // SBO=1024B>>4, version=1, SWIZZLE_128B
+constexpr uint32_t c_desc_lbo = 1u;                                // LBO field (ignored for SW128 K-major)
 // `single` kernel argument = 1: single-pass bf16 (gemm_backend bit 2; BASELINE config #3's "bf16 tensor-core path"): operands are
 // rounded to bf16 once, one MMA per k-step instead of three, the lo tiles are neither written nor read.  ~3e-3 relative
 // accuracy instead of ~1e-5.
-__device__ __constant__ uint32_t c_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (16u << 17) | (8u << 24);  // F32 acc, BF16 x BF16, N=128, M=128
+constexpr uint32_t c_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (16u << 17) | (8u << 24);  // F32 acc, BF16 x BF16, N=128, M=128
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -450,15 +450,6 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
     gemm_tc_body<K, NOUT, ALoad, Epi, PARTS>(al, wimg, ep, P, single, (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y);
 }
 
-// ------------------------------------------------------------------------------------------
-// Warp-specialised variant (optional, ub200_tc_set_warp_specialized(1); measured 3-10% SLOWER than the single-role kernel on
-// B200 at B=16 -- halving the producer warps costs more load parallelism than the overlap buys): warps 0-7 produce operand tiles (and thread 0 issues the MMAs), warps 8-15 run
-// the epilogue, so the TMEM -> HBM stores of tile t-1 overlap the HBM loads / conversion of tile t instead of
-// alternating with them.  Synchronisation: named barrier 1 (256 producer threads) before each MMA batch; mbarriers
-// free[slot] (tcgen05.commit -> producers), accfull[stage] (tcgen05.commit -> epilogue), accempty[stage] (8 epilogue
-// warps -> MMA thread); the weight image arrives by cp.async.bulk (TMA bulk copy) on wbar while the first tile is built.
-// Producers work in half K-blocks (64 pixel rows) so that the register prefetch depth stays at 2 items per thread.
-// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
@@ -470,169 +461,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int K, int NOUT, class ALoad, class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_ws_kernel(ALoad al, const uint4* __restrict__ wimg, Epi ep, int P, int single) {
-    constexpr int KB = K / KBLK, MH = NOUT / 128;
-    constexpr int W_BYTES = K * NOUT * 4, W_HALF = K * NOUT * 2;
-    constexpr int ACC_COLS = MH * TILE_PX;
-    constexpr int NPROD = 256;
-    extern __shared__ __align__(1024) char smem_raw[];
-    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    char* sW = smem;
-    char* sA = smem + W_BYTES;
-    float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * K);    // free[2], accfull[2], accempty[2], wbar
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 7);
-    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, n = blockIdx.y;
-    const uint32_t bFree = smem_u32(&sBar[0]), bFull = smem_u32(&sBar[2]), bEmpty = smem_u32(&sBar[4]), bW = smem_u32(&sBar[6]);
-
-    const int tiles_per_frame = P / TILE_PX;
-    const int t0 = (int)(((long long)blockIdx.x * tiles_per_frame) / gridDim.x);
-    const int t1 = (int)(((long long)(blockIdx.x + 1) * tiles_per_frame) / gridDim.x);
-    const int ntiles = t1 - t0;
-
-    al.fill(n, K, sCf);
-    if (tid == 0) {
-        mbar_init(bFree, 1); mbar_init(bFree + 8, 1);
-        mbar_init(bFull, 1); mbar_init(bFull + 8, 1);
-        mbar_init(bEmpty, 8); mbar_init(bEmpty + 8, 8);
-        mbar_init(bW, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *sTmem;
-
-    if (warp < 8) {
-        // ================= producers (+ MMA issue by thread 0) =================
-        if (tid == 0 && ntiles > 0) {        // weight image: 8 x 16 KB TMA bulk copies, completion on wbar
-            mbar_expect_tx(bW, W_BYTES);
-            for (int i = 0; i < W_BYTES / 16384; ++i)
-                bulk_g2s(smem_u32(sW) + i * 16384, reinterpret_cast<const char*>(wimg) + (size_t)i * 16384, 16384, bW);
-        }
-        const int pc8 = tid % 8, pr = tid / 8;             // chunk pc8 of rows pr, pr+32 within a 64-row half
-        const long long HS = (long long)ntiles * KB * 2;    // half-steps
-        typename ALoad::Raw raw[2];
-        if (HS > 0) {
-            const size_t row0 = (size_t)n * P + (size_t)t0 * TILE_PX;
-            al.issue(row0 + pr, K, pc8 * 8, raw[0]);
-            al.issue(row0 + pr + 32, K, pc8 * 8, raw[1]);
-        }
-        for (long long h = 0; h < HS; ++h) {
-            const int q = (int)(h >> 1), half = (int)(h & 1);
-            const int it = q / KB, kb = q % KB;
-            typename ALoad::Raw cur[2] = {raw[0], raw[1]};
-            if (h + 1 < HS) {
-                const int nq = (int)((h + 1) >> 1), nhalf = (int)((h + 1) & 1);
-                const size_t nrow0 = (size_t)n * P + (size_t)(t0 + nq / KB) * TILE_PX + nhalf * 64;
-                al.issue(nrow0 + pr, K, (nq % KB) * KBLK + pc8 * 8, raw[0]);
-                al.issue(nrow0 + pr + 32, K, (nq % KB) * KBLK + pc8 * 8, raw[1]);
-            }
-            const uint32_t slot = (uint32_t)q % NSTAGE, u = (uint32_t)q / NSTAGE;
-            if (half == 0) mbar_wait(bFree + slot * 8, (u & 1) ^ 1);
-            char* hi = sA + slot * STAGE_BYTES;
-            char* lo = hi + STAGE_BYTES / 2;
-            {
-                typename ALoad::Cf cfr;
-                al.coefs(K, kb * KBLK + pc8 * 8, sCf, cfr);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = half * 64 + pr + 32 * j;
-                    float v[8];
-                    al.finish(cur[j], cfr, v);
-                    const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
-                    split_store8(v, hi + off, lo + off, single);
-                }
-            }
-            if (half == 1) {
-                fence_proxy_async();
-                asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-                if (tid == 0) {
-                    if (q == 0) mbar_wait(bW, 0);                                  // weight image landed
-                    if (kb == 0) {                                                 // accumulator stage drained by the epilogue?
-                        const uint32_t v = (uint32_t)(it >> 1);
-                        mbar_wait(bEmpty + (it & 1) * 8, (v & 1) ^ 1);
-                    }
-                    tc_fence_after();
-                    const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
-                    const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
-                    const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
-                    const uint32_t idesc = c_idesc;
-#pragma unroll
-                    for (int j = 0; j < MH; ++j) {
-                        const uint32_t d = tmem_base + acc + j * TILE_PX;
-#pragma unroll
-                        for (int k16 = 0; k16 < KBLK / 16; ++k16) {
-                            const uint64_t wa = make_desc(a_hi + j * (128 * 128) + k16 * 32);
-                            const uint64_t wl = make_desc(a_lo + j * (128 * 128) + k16 * 32);
-                            const uint64_t xa = make_desc(b_hi + k16 * 32);
-                            const uint64_t xl = make_desc(b_lo + k16 * 32);
-                            tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
-                            if (!single) {
-                                tc_mma(d, wa, xl, idesc, 1);
-                                tc_mma(d, wl, xa, idesc, 1);
-                            }
-                        }
-                    }
-                    tc_commit(bFree + slot * 8);
-                    if (kb == KB - 1) tc_commit(bFull + (it & 1) * 8);
-                }
-            }
-        }
-    } else {
-        // ================= epilogue warps =================
-        const int ew = warp - 8, lq = ew % 4, ph = ew / 4;     // TMEM lane quarter, pixel half (64 pixels)
-        typename Epi::State est[MH];
-        float stat[MH][Epi::NS];
-#pragma unroll
-        for (int j = 0; j < MH; ++j) {
-            ep.init(n, NOUT, j * 128 + lq * 32 + lane, est[j]);
-#pragma unroll
-            for (int s = 0; s < Epi::NS; ++s) stat[j][s] = 0.f;
-        }
-        for (int it = 0; it < ntiles; ++it) {
-            mbar_wait(bFull + (it & 1) * 8, (uint32_t)(it >> 1) & 1);
-            tc_fence_after();
-            const size_t prow0 = (size_t)n * P + (size_t)(t0 + it) * TILE_PX + ph * 64;
-#pragma unroll
-            for (int j = 0; j < MH; ++j)
-#pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(it & 1) * ACC_COLS + j * TILE_PX + ph * 64 + sl * 32, v);
-                    ep.template apply<32>(est[j], prow0 + sl * 32, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
-                }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bEmpty + (it & 1) * 8);
-        }
-        double* dst = ep.dst(n, NOUT);
-#pragma unroll
-        for (int j = 0; j < MH; ++j)
-#pragma unroll
-            for (int s = 0; s < Epi::NS; ++s)
-                atomicAdd(&dst[(size_t)(j * 128 + lq * 32 + lane) * Epi::NS + s], (double)stat[j][s]);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-}
-
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
-    }
-    return n;
-}
+static int sm_count() { return device_sm_count(); }
 // CTAs per frame: G*N a multiple of the SM count (equal waves), about 8-16 tiles per CTA
 static int blocks_per_frame(int N, int tiles) {
     const int sms = sm_count();
@@ -643,30 +473,15 @@ static int blocks_per_frame(int N, int tiles) {
     return g < 1 ? 1 : g;
 }
 
-// tc_set_split_epilogue(): 1 (default) = every kernel uses its epilogue's PARTS, 0 = one burst everywhere
-static int g_split_epilogue = 1;
-static int g_single_pass = 0;           // tc_set_single_pass(): host-side, handed to every launch as a kernel argument
-static int g_warp_specialized = 0;      // tc_set_warp_specialized(): 0 = gemm_tc_kernel (default; measured faster), 1 = gemm_tc_ws_kernel
-
 template <int K, int NOUT, class ALoad, class Epi>
-static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, cudaStream_t st) {
+static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, int single, cudaStream_t st) {
     if (P % TILE_PX != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + 8 * 8 + 16 + 1024;
-    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi, 1>;
-    auto kern_split = gemm_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS>;
-    auto kern_ws = gemm_tc_ws_kernel<K, NOUT, ALoad, Epi>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        if (cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        if (cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS>;
+    UB_SET_SMEM(kern, smem);
     const int tiles = P / TILE_PX;
     const dim3 grid(blocks_per_frame(N, tiles), N);
-    if (g_warp_specialized) kern_ws<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P, g_single_pass);
-    else if (g_split_epilogue) kern_split<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P, g_single_pass);
-    else kern<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P, g_single_pass);
+    kern<<<grid, THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, P, single);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
@@ -688,9 +503,9 @@ constexpr int WG_B_BYTES = 2 * WG_PX * 256 * 2;      // hi+lo, 256 channels: 64 
 constexpr int WG_STAGE = WG_A_BYTES + WG_B_BYTES;    // 96 KB
 constexpr int WG_BLK = WG_PX * 128;                  // one [64 px][64 ch] bf16 block: 8 KB
 
-__device__ __constant__ uint32_t c_wg_desc_hi = (64u) | (1u << 14) | (2u << 29);                  // SBO = 1024 B
-__device__ __constant__ uint32_t c_wg_desc_lbo = (uint32_t)(WG_BLK >> 4);                           // LBO = 8 KB between 64-channel blocks
-__device__ __constant__ uint32_t c_wg_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (32u << 17) | (8u << 24);
+constexpr uint32_t c_wg_desc_hi = (64u) | (1u << 14) | (2u << 29);                  // SBO = 1024 B
+constexpr uint32_t c_wg_desc_lbo = (uint32_t)(WG_BLK >> 4);                           // LBO = 8 KB between 64-channel blocks
+constexpr uint32_t c_wg_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (32u << 17) | (8u << 24);
 
 __device__ __forceinline__ uint64_t make_wg_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(c_wg_desc_lbo & 0x3FFFu) << 16) | ((uint64_t)c_wg_desc_hi << 32);
@@ -830,72 +645,18 @@ wgrad_tc_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long tota
     wgrad_tc_body<LA, LB>(la, lb, partial + (size_t)blockIdx.x * 128 * 256, P, t0, t1, sa, sb, single);
 }
 
-// ------------------------------------------------------------------------------------------
-// Dual-role kernel: the input-gradient GEMM and the weight-gradient GEMM of one 1x1 convolution read the SAME activation
-// tensors (dOut, y, h2 for conv2; dz1, h1, x for conv1).  Launched back to back they stream those tensors from HBM twice
-// (the 126 MB L2 cannot hold 1-3 GB between the launches).  Here both run in ONE launch: grid (2G, N), CTA 2p of a frame
-// is the input-gradient role and CTA 2p+1 the weight-gradient role of the same tile range, so the hardware schedules the
-// two roles of a pair back to back on two SMs and they sweep the same ~14 tiles at the same time: whichever role touches
-// a line first pays the HBM access, the other one hits the L2 (and, being faster for it, catches up: the pair keeps itself
-// within a tile or two without any explicit synchronisation).  Partials: one [128][256] slot per weight-gradient CTA.
-// ------------------------------------------------------------------------------------------
-template <int K, int NOUT, class ALoad, class Epi, int PARTS, class LA, class LB>
-__global__ void __launch_bounds__(THREADS, 1)
-dual_tc_kernel(ALoad al, const uint4* __restrict__ wimg, Epi ep, LA la, LB lb, float* __restrict__ partial, int P, int sa, int sb, int single) {
-    const int pair = (int)blockIdx.x >> 1, G = (int)gridDim.x >> 1, n = (int)blockIdx.y;
-    if ((blockIdx.x & 1) == 0) {
-        gemm_tc_body<K, NOUT, ALoad, Epi, PARTS>(al, wimg, ep, P, single, pair, G, n);
-    } else {
-        const int tiles_per_frame = P / TILE_PX;
-        const long long g0 = ((long long)pair * tiles_per_frame) / G, g1 = ((long long)(pair + 1) * tiles_per_frame) / G;
-        const long long base = (long long)n * (P / WG_PX);
-        wgrad_tc_body<LA, LB>(la, lb, partial + ((size_t)n * G + pair) * 128 * 256, P, base + 2 * g0, base + 2 * g1, sa, sb, single);
-    }
-}
-
 template <class LA, class LB>
-static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb, int* nparts, cudaStream_t st) {
+static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb, int single, int* nparts,
+                           cudaStream_t st) {
     if (P % WG_PX != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)2 * WG_STAGE + 3 * 384 * sizeof(float) + 3 * 8 + 16 + 1024;
     auto kern = wgrad_tc_kernel<LA, LB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM(kern, smem);
     const long long total = (long long)N * (P / WG_PX);
     const int blocks = (int)(total < max_parts ? total : max_parts);
-    kern<<<blocks, THREADS, smem, st>>>(la, lb, partial, P, total, sa, sb, g_single_pass);
+    kern<<<blocks, THREADS, smem, st>>>(la, lb, partial, P, total, sa, sb, single);
     UB_CHECK_LAUNCH();
     *nparts = blocks;
-    return UB_OK;
-}
-
-// tc_set_dual(): bit 0 = the expand convolution's pair (gemm1_bwd + wgrad1) shares one launch, bit 1 = the project convolution's
-// pair (gemm2_bwd + wgrad2).  Measured at N=16 / N=48 frames: conv1 pair 1.234 -> 1.167 ms / 3.635 -> 3.452 ms (-5 %), conv2 pair
-// 1.256 -> 1.349 ms / 3.639 -> 3.854 ms (+6 %: both of its roles evaluate the GELU per element and are bound by their own SM, so
-// halving the SMs per role costs more than the shared reads save).  Default 0: the 1 % it buys per step is inside the box-to-box
-// noise, and bench.py's per-kernel roofline stays one kernel = one role.
-static int g_dual = 0;
-template <int K, int NOUT, class ALoad, class Epi, class LA, class LB>
-static int launch_dual(ALoad al, const void* wimg, Epi ep, LA la, LB lb, float* partial, int max_parts, int N, int P, int sa, int sb,
-                       int* nparts, cudaStream_t st) {
-    if (P % TILE_PX != 0) return UB_ERR_ARG;
-    constexpr size_t smem_g = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + 8 * 8 + 16 + 1024;
-    constexpr size_t smem_w = (size_t)2 * WG_STAGE + 3 * 384 * sizeof(float) + 3 * 8 + 16 + 1024;
-    constexpr size_t smem = smem_g > smem_w ? smem_g : smem_w;
-    auto kern = dual_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS, LA, LB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
-    const int tiles = P / TILE_PX;
-    const int G = blocks_per_frame(N, tiles);
-    if (G * N > max_parts) return UB_ERR_WORKSPACE;
-    kern<<<dim3(2 * G, N), THREADS, smem, st>>>(al, static_cast<const uint4*>(wimg), ep, la, lb, partial, P, sa, sb, g_single_pass);
-    UB_CHECK_LAUNCH();
-    *nparts = G * N;
     return UB_OK;
 }
 
@@ -921,90 +682,48 @@ int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose,
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, cudaStream_t st) {
+int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, int single, cudaStream_t st) {
     tc::TLoadNormed al{x, coef0};
     tc::TEpiStoreStats ep{h1, stats1};
-    return tc::launch<UB_WIDTH, UB_HID>(al, w1img, ep, N, P, st);
+    return tc::launch<UB_WIDTH, UB_HID>(al, w1img, ep, N, P, single, st);
 }
-int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N, int P, cudaStream_t st) {
+int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N, int P,
+                 int single, cudaStream_t st) {
     tc::TLoadGeluGate al{h2, coef2, gate};
     tc::TEpiStoreStats ep{y, stats3};
-    return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, st);
+    return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, single, st);
 }
 int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, cudaStream_t st) {
+                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, cudaStream_t st) {
     tc::TLoadNormBwd al{dout, y, bc3};
     tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
-    return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, ep, N, P, st);
+    return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, ep, N, P, single, st);
 }
 int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                 const MeanRstd* mr0, double* bstats0, int N, int P, cudaStream_t st) {
+                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, cudaStream_t st) {
     tc::TLoadNormBwd al{dz1, h1, bc1};
     tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
-    return tc::launch<UB_HID, UB_WIDTH>(al, w1timg, ep, N, P, st);
+    return tc::launch<UB_HID, UB_WIDTH>(al, w1timg, ep, N, P, single, st);
 }
 // dW2[o][k] += sum_p dy[p][o] * u[p][k]
 int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
-              float* partial, int max_parts, float* dw2, int N, int P, cudaStream_t st) {
+              float* partial, int max_parts, float* dw2, int N, int P, int single, cudaStream_t st) {
     tc::TLoadNormBwd la{dout, y, bc3};
     tc::TLoadGeluGate lb{h2, coef2, gate};
     int nparts = 0;
-    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, UB_HID, 1, &nparts, st);
+    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, UB_HID, 1, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
 }
 // dW1[o][k] += sum_p dh1[p][o] * n0[p][k]   (M side = n0 (128 channels, index k), N side = dh1 (256 channels, index o))
 int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
-              int max_parts, float* dw1, int N, int P, cudaStream_t st) {
+              int max_parts, float* dw1, int N, int P, int single, cudaStream_t st) {
     tc::TLoadNormed la{x, coef0};
     tc::TLoadNormBwd lb{dz1, h1, bc1};
     int nparts = 0;
-    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, 1, UB_WIDTH, &nparts, st);
+    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
-}
-// Dual-role launches (see dual_tc_kernel): input gradient + weight gradient of one 1x1 convolution in one kernel.
-int tc_gemm2_bwd_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
-                        float* dw2, int N, int P, cudaStream_t st) {
-    tc::TLoadNormBwd al{dout, y, bc3};
-    tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
-    tc::TLoadNormBwd la{dout, y, bc3};
-    tc::TLoadGeluGate lb{h2, coef2, gate};
-    int nparts = 0;
-    int rc = tc::launch_dual<UB_WIDTH, UB_HID>(al, w2timg, ep, la, lb, partial, max_parts, N, P, UB_HID, 1, &nparts, st);
-    if (rc != UB_OK) return rc;
-    return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
-}
-int tc_gemm1_bwd_wgrad1(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
-                        int P, cudaStream_t st) {
-    tc::TLoadNormBwd al{dz1, h1, bc1};
-    tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
-    tc::TLoadNormed la{x, coef0};
-    tc::TLoadNormBwd lb{dz1, h1, bc1};
-    int nparts = 0;
-    int rc = tc::launch_dual<UB_HID, UB_WIDTH>(al, w1timg, ep, la, lb, partial, max_parts, N, P, 1, UB_WIDTH, &nparts, st);
-    if (rc != UB_OK) return rc;
-    return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
-}
-int tc_dual_parts(int N, int P) { return tc::blocks_per_frame(N, P / tc::TILE_PX) * N; }
-int tc_set_dual(int mask) { tc::g_dual = mask & 3; return UB_OK; }
-int tc_dual_enabled() { return tc::g_dual; }
-int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
-    if (cudaMemcpyToSymbol(tc::c_wg_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
-    if (cudaMemcpyToSymbol(tc::c_wg_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;
-    if (cudaMemcpyToSymbol(tc::c_wg_idesc, &idesc, 4) != cudaSuccess) return UB_ERR_CUDA;
-    return UB_OK;
-}
-int tc_set_warp_specialized(int on) { tc::g_warp_specialized = on ? 1 : 0; return UB_OK; }
-int tc_set_split_epilogue(int on) { tc::g_split_epilogue = on ? 1 : 0; return UB_OK; }
-int tc_set_single_pass(int on) { tc::g_single_pass = on ? 1 : 0; return UB_OK; }
-int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) {
-    if (cudaMemcpyToSymbol(tc::c_desc_hi, &desc_hi, 4) != cudaSuccess) return UB_ERR_CUDA;
-    if (cudaMemcpyToSymbol(tc::c_desc_lbo, &desc_lbo, 4) != cudaSuccess) return UB_ERR_CUDA;
-    if (cudaMemcpyToSymbol(tc::c_idesc, &idesc, 4) != cudaSuccess) return UB_ERR_CUDA;
-    return UB_OK;
 }
 
 }  // namespace ub

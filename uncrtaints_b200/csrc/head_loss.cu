@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) mgnll_fwd_kernel(const float* __restrict_
         for (int c = 0; c < UB_S2; ++c) {
             const float vraw = var_ch == 1 ? vr[0] : vr[c];
             neg |= (vraw < 0.f);
-            const float v = fmaxf(vraw, eps);
+            const float v = clamp_min_keep_nan(vraw, eps);
             iv[c] = 1.0f / v;
             logdet += logf(v);
             maha = fmaf(e[c] * e[c], iv[c], maha);
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) gnll_fwd_kernel(const float* __restrict__
 #pragma unroll
         for (int c = 0; c < UB_S2; ++c) {
             neg |= (vr[c] < 0.f);
-            const float v = fmaxf(vr[c], eps), iv = 1.0f / v;
+            const float v = clamp_min_keep_nan(vr[c], eps), iv = 1.0f / v;
             part += 0.5f * (logf(v) + e[c] * e[c] * iv);
             if (var_out) var_out[((size_t)b * UB_S2 + c) * P + p] = v;
             if (dpred) {
@@ -325,6 +325,93 @@ __global__ void mgnll_finalize_kernel(const double* acc, float* loss, int B, int
     *loss = (float)v;
 }
 
+// ------------------------------------------------------------------------------------------
+// reduction='none' forms (losses.py:213-218 / :122-128): per-element losses and their backward for an arbitrary upstream
+// gradient.  MGNLL: loss[p][b] (the nested vmap's output order [H][W][B]) = const + 1/2 sum_{b',c} log v[b'][c][p] + 1/2 maha[b][p];
+// thread per pixel, loops over the batch (the log-determinant couples the samples of a pixel, losses.py:138).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mgnll_none_fwd_kernel(const float* __restrict__ pred, long long pred_sb, const float* __restrict__ target,
+                                                              long long targ_sb, const float* __restrict__ var, long long var_sb, int var_ch,
+                                                              float* __restrict__ loss /* [P][B] */, int* neg_flag, int B, int P, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float cst = 6.5f * logf(2.0f * 3.14159274101257324f);
+    float logdet = 0.f;
+    bool neg = false;
+    for (int b = 0; b < B; ++b) {
+        float maha = 0.f;
+        for (int c = 0; c < UB_S2; ++c) {
+            const float vraw = var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p];
+            neg |= (vraw < 0.f);
+            const float v = clamp_min_keep_nan(vraw, eps);
+            const float e = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
+            logdet += logf(v);
+            maha = fmaf(e * e, 1.0f / v, maha);
+        }
+        float m = maha != maha ? 0.f : maha;
+        m = fminf(m, 3.4028234663852886e38f);
+        loss[(size_t)p * B + b] = fmaxf(m, 1e-9f);
+    }
+    for (int b = 0; b < B; ++b) loss[(size_t)p * B + b] = cst + 0.5f * logdet + 0.5f * loss[(size_t)p * B + b];
+    if (neg) *neg_flag = 1;
+}
+__global__ void __launch_bounds__(256) mgnll_none_bwd_kernel(const float* __restrict__ pred, long long pred_sb, const float* __restrict__ target,
+                                                              long long targ_sb, const float* __restrict__ var, long long var_sb, int var_ch,
+                                                              const float* __restrict__ g /* [P][B] */, float* __restrict__ dpred,
+                                                              float* __restrict__ dvar, int B, int P, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float gsum = 0.f;
+    for (int b = 0; b < B; ++b) gsum += g[(size_t)p * B + b];
+    for (int b = 0; b < B; ++b) {
+        const float gb = g[(size_t)p * B + b];
+        float e[UB_S2], iv[UB_S2], maha = 0.f;
+#pragma unroll
+        for (int c = 0; c < UB_S2; ++c) {
+            const float v = clamp_min_keep_nan(var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p], eps);
+            e[c] = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
+            iv[c] = 1.0f / v;
+            maha = fmaf(e[c] * e[c], iv[c], maha);
+        }
+        const bool live = maha == maha && maha >= 1e-9f && maha <= 3.4028234663852886e38f;
+        float dv_iso = 0.f;
+#pragma unroll
+        for (int c = 0; c < UB_S2; ++c) {
+            dpred[((size_t)b * UB_S2 + c) * P + p] = live ? gb * e[c] * iv[c] : 0.f;
+            const float gv = 0.5f * iv[c] * gsum - (live ? 0.5f * gb * e[c] * e[c] * iv[c] * iv[c] : 0.f);
+            if (var_ch == 1) dv_iso += gv;
+            else dvar[((size_t)b * UB_S2 + c) * P + p] = gv;
+        }
+        if (var_ch == 1) dvar[(size_t)b * P + p] = dv_iso;
+    }
+}
+// GNLL, reduction='none': loss[b][c][p] = 1/2 (log v + e^2 / v) [+ 1/2 log(2 pi)]; backward for an element-wise upstream gradient
+__global__ void __launch_bounds__(256) gnll_none_kernel(const float* __restrict__ pred, long long pred_sb, const float* __restrict__ target,
+                                                         long long targ_sb, const float* __restrict__ var, long long var_sb,
+                                                         const float* __restrict__ g /* null: forward */, float* __restrict__ loss,
+                                                         float* __restrict__ var_out, float* __restrict__ dpred, float* __restrict__ dvar,
+                                                         int* neg_flag, int P, float eps, int full) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (p >= P) return;
+    const float cst = full ? 0.5f * 1.8378770664093453f : 0.f;
+    bool neg = false;
+    for (int c = 0; c < UB_S2; ++c) {
+        const size_t o = ((size_t)b * UB_S2 + c) * P + p;
+        const float vraw = var[b * var_sb + (size_t)c * P + p];
+        neg |= (vraw < 0.f);
+        const float v = clamp_min_keep_nan(vraw, eps), iv = 1.0f / v;
+        const float e = pred[b * pred_sb + (size_t)c * P + p] - target[b * targ_sb + (size_t)c * P + p];
+        if (g) {
+            dpred[o] = g[o] * e * iv;
+            dvar[o] = g[o] * 0.5f * (iv - e * e * iv * iv);
+        } else {
+            loss[o] = 0.5f * (logf(v) + e * e * iv) + cst;
+            if (var_out) var_out[o] = v;
+        }
+    }
+    if (neg && neg_flag) *neg_flag = 1;
+}
+
 // out[i] = in[i] * g[0]   (chain rule with the upstream scalar gradient)
 __global__ void scale_by_scalar_kernel(const float* __restrict__ in, const float* __restrict__ g, float* __restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,7 +425,7 @@ __global__ void __launch_bounds__(256) covariance_kernel(const float* __restrict
     if (p >= P) return;
     float v[UB_S2];
 #pragma unroll
-    for (int c = 0; c < UB_S2; ++c) v[c] = fmaxf(var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p], eps);
+    for (int c = 0; c < UB_S2; ++c) v[c] = clamp_min_keep_nan(var[b * var_sb + (size_t)(var_ch == 1 ? 0 : c) * P + p], eps);
     float* dst = cov + (size_t)b * UB_S2 * UB_S2 * P + p;
 #pragma unroll
     for (int i = 0; i < UB_S2; ++i)
@@ -352,13 +439,9 @@ __global__ void __launch_bounds__(256) covariance_kernel(const float* __restrict
 int launch_head_fwd(const float* dec, const float* w, const float* bias, float* out, int B, int O, int P, float scale_by,
                     int mean_sigmoid, float var_eps, cudaStream_t st) {
     if (O > HD_MAXO || O < UB_S2 || P % HF_PX) return UB_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM(head_fwd_kernel, HF_SMEM);
     const long long tiles = (long long)B * (P / HF_PX);
-    const int blocks = (int)(tiles < 2LL * 148 ? tiles : 2LL * 148);
+    const int blocks = (int)(tiles < 2LL * device_sm_count() ? tiles : 2LL * device_sm_count());
     head_fwd_kernel<<<blocks, 256, HF_SMEM, st>>>(dec, w, bias, out, O, P, tiles, scale_by, mean_sigmoid, var_eps);
     UB_CHECK_LAUNCH();
     return UB_OK;
@@ -367,11 +450,7 @@ int launch_head_bwd(const float* dout, const float* out, const float* dec, const
                     int B, int O, int P, float scale_by, int mean_sigmoid, float var_eps, int num_sms, cudaStream_t st) {
     if (O > HD_MAXO || O < UB_S2 || P % HD_PX) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)(HD_PX * UB_WIDTH + HD_MAXO * UB_WIDTH + HD_MAXO * HD_PX) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UB_ERR_CUDA;
-        attr_set = true;
-    }
+    UB_SET_SMEM(head_bwd_kernel, smem);
     const long long tiles = (long long)B * (P / HD_PX);
     const int blocks = (int)(tiles < 2LL * num_sms ? tiles : 2LL * num_sms);
     head_bwd_kernel<<<blocks, 256, smem, st>>>(dout, out, dec, w, ddec, dw, db, O, P, tiles, scale_by, mean_sigmoid, var_eps);
@@ -399,6 +478,27 @@ int launch_gnll(const float* pred, long long pred_sb, const float* target, long 
                                                               neg_flag, B, P, eps);
     UB_CHECK_LAUNCH();
     gnll_finalize_kernel<<<1, 1, 0, st>>>(acc, loss, (double)B * UB_S2 * (double)P, full);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_mgnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                      int var_ch, const float* g, float* loss, float* dpred, float* dvar, int* neg_flag, int B, int P, float eps,
+                      cudaStream_t st) {
+    if (!g) {
+        if (cudaMemsetAsync(neg_flag, 0, sizeof(int), st) != cudaSuccess) return UB_ERR_CUDA;
+        mgnll_none_fwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, loss, neg_flag, B, P, eps);
+    } else {
+        mgnll_none_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, g, dpred, dvar, B, P, eps);
+    }
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_gnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                     const float* g, float* loss, float* var_out, float* dpred, float* dvar, int* neg_flag, int B, int P, float eps,
+                     int full, cudaStream_t st) {
+    if (!g && cudaMemsetAsync(neg_flag, 0, sizeof(int), st) != cudaSuccess) return UB_ERR_CUDA;
+    gnll_none_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(pred, pred_sb, target, targ_sb, var, var_sb, g, loss, var_out, dpred, dvar,
+                                                               neg_flag, P, eps, full);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }

@@ -40,50 +40,27 @@ int simt_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float
 int simt_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
                 int max_parts, float* dw1, int N, int P, cudaStream_t st);
 
-// gemm_tc.cu (tcgen05 bf16x3 tensor-core versions of the four streaming GEMMs)
+// gemm_tc.cu (tcgen05 bf16x3 tensor-core versions of the four streaming GEMMs and the two weight-gradient GEMMs).
+// single = 1: single-pass bf16 MMAs (gemm_backend bit 2; reduced precision), 0: the fp32-parity bf16x3 split.
 int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, cudaStream_t st);
-int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, cudaStream_t st);
+int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, int single, cudaStream_t st);
 int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N,
-                 int P, cudaStream_t st);
+                 int P, int single, cudaStream_t st);
 int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, cudaStream_t st);
+                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, cudaStream_t st);
 int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                 const MeanRstd* mr0, double* bstats0, int N, int P, cudaStream_t st);
+                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, cudaStream_t st);
 int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
-              float* partial, int max_parts, float* dw2, int N, int P, cudaStream_t st);
+              float* partial, int max_parts, float* dw2, int N, int P, int single, cudaStream_t st);
 int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
-              int max_parts, float* dw1, int N, int P, cudaStream_t st);
-int tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
-int tc_set_warp_specialized(int on);
-int tc_set_split_epilogue(int on);
-int tc_set_single_pass(int on);
-int tc_gemm2_bwd_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
-                        float* dw2, int N, int P, cudaStream_t st);
-int tc_gemm1_bwd_wgrad1(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
-                        int P, cudaStream_t st);
-int tc_dual_parts(int N, int P);
-int tc_set_dual(int on);
-int tc_dual_enabled();
-int tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc);
+              int max_parts, float* dw1, int N, int P, int single, cudaStream_t st);
 
-// dwconv.cu
+// dwconv_rows.cu (row-streaming depthwise kernels fed by TMA bulk copies; the backward one is fused: du, h2, h1 -> dz1 in one pass)
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st);
-int launch_dwconv_bwd(float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
+int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
                       const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
                       float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
-
-int dwconv_set_bwd_split(int on);
-int dwconv_set_mode(int mode);
-
-// dwconv_rows.cu (row-streaming TMA bulk-copy versions; the backward one is fused: du, h2, h1 -> dz1 in one pass)
-int launch_dwrows_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
-                      int f2, cudaStream_t st);
-int launch_dwrows_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
-                      const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
-                      float* dwdw, int N, int H, int W, int f2, cudaStream_t st);
 
 // se.cu
 int launch_se_fwd(const double* pool_stats, const float* f1, const float* f2, float* save, float* gate, int N, int P,
@@ -92,14 +69,8 @@ int launch_se_bwd(const double* sums3, const double* gp_stats, const float* f1, 
                   float* df1, float* df2, float* dmp, double* bstats2, int N, int P, cudaStream_t st);
 
 // inconv.cu
-int launch_inconv_stats(const float* x, const float* w, const float* b, double* stats, int* notpad, float pad_value, int N,
-                        int Cin, int P, cudaStream_t st);
 int launch_inconv_apply(const float* x, const float* w, const float* b, const Coef* coef, float* x0, double* stats_x0, int N,
                         int Cin, int P, cudaStream_t st);
-int launch_inconv_bwd_stats(const float* x, const float* w, const float* b, const Coef* coef, const MeanRstd* mr,
-                            const float* dx0, double* bstats, int N, int Cin, int P, cudaStream_t st);
-int launch_inconv_bwd_wgrad(const float* x, const float* w, const float* b, const Coef* coef, const MeanRstd* mr,
-                            const BCoef* bc, const float* dx0, float* dw, float* db, int N, int Cin, int P, cudaStream_t st);
 
 size_t inconv_moments_bytes(int N);
 size_t inconv_gram_bytes(int N);
@@ -135,7 +106,17 @@ int launch_mgnll(const float* pred, long long pred_sb, const float* target, long
 int launch_gnll(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
                 float* dpred, float* dvar, float* var_out, double* acc, int* neg_flag, float* loss, int B, int P, float eps, int full,
                 cudaStream_t st);
+int launch_mgnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                      int var_ch, const float* g, float* loss, float* dpred, float* dvar, int* neg_flag, int B, int P, float eps,
+                      cudaStream_t st);
+int launch_gnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                     const float* g, float* loss, float* var_out, float* dpred, float* dvar, int* neg_flag, int B, int P, float eps,
+                     int full, cudaStream_t st);
 int launch_scale_by_scalar(const float* in, const float* g, float* out, size_t n, cudaStream_t st);
 int launch_covariance(const float* var, long long var_sb, int var_ch, float* cov, int B, int P, float eps, cudaStream_t st);
+
+// optim.cu
+int launch_adam_step(float* p, float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, float inv_bc1, float inv_sqrt_bc2, float grad_scale, int zero_grad, cudaStream_t st);
 
 }  // namespace ub

@@ -87,9 +87,7 @@ struct Layout {
     size_t total;
 };
 
-constexpr int MAX_PARTS = 148;
-// 1 (default): in_conv statistics / weight gradients through input moments and one gram pass (inconv.cu); 0: recompute passes
-static int g_inconv_moments = 1;
+constexpr int MAX_PARTS = 148;     // persistent weight-gradient CTAs: one [128][256] partial each
 
 static void block_fwd_stats(Bump& b, BlockWs& w, int N) {
     w.stats0 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
@@ -170,8 +168,6 @@ static int make_layout(const ub200_desc* d, Layout& L) {
         L.du = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
         L.dz1 = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
         L.max_parts = MAX_PARTS;
-        if (tc_dual_parts(L.Ne, L.P) > L.max_parts) L.max_parts = tc_dual_parts(L.Ne, L.P);
-        if (tc_dual_parts(L.B, L.P) > L.max_parts) L.max_parts = tc_dual_parts(L.B, L.P);
         L.partial = b.take((size_t)L.max_parts * UB_WIDTH * UB_HID * sizeof(float));
         L.dwup = b.take((size_t)UB_HEADS * L.Ne * P * sizeof(float));
         L.dattn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
@@ -218,6 +214,7 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     const int P = c.H * c.W;
     void* ws = c.ws;
     const bool tcb = (c.backend & 1) != 0;
+    const int single = (c.backend & 4) != 0;
     if (tcb) {
         // M-operand images: W1 [256][128] and W2 [128][256] as stored; W2^T / W1^T for the input-gradient GEMMs
         UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, c.st));
@@ -230,7 +227,7 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     }
     UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
     if (tcb)
-        UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
+        UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, single, c.st));
     else
         UB_PROF(KID_GEMM1_FWD, c.st, simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
@@ -243,7 +240,7 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
                          at<float>(ws, w.gate), c.N, P, c.st));
     if (tcb)
         UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img),
-                              at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
+                              at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, single, c.st));
     else
         UB_PROF(KID_GEMM2_FWD, c.st, simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
                               at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
@@ -261,22 +258,16 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
     const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
-    const bool dual_ok = tcb && tcw && tc_dual_parts(c.N, P) <= c.max_parts;
-    const bool dual2 = dual_ok && (tc_dual_enabled() & 2), dual1 = dual_ok && (tc_dual_enabled() & 1);
-    if (dual2)
-        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
-                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), at<float>(ws, w.gate), partial,
-                              c.max_parts, gf(c.g, UB200_B_W2), c.N, P, c.st));
-    else if (tcb)
+    const int single = (c.backend & 4) != 0;
+    if (tcb)
         UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
-                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
+                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, single, c.st));
     else
         UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    if (dual2) {
-    } else if (tcw)
+    if (tcw)
         UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
-                           at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
+                           at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
     else
         UB_PROF(KID_WGRAD2, c.st, simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                            at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
@@ -288,19 +279,15 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    if (dual1)
-        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_wgrad1(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
-                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, c.max_parts, gf(c.g, UB200_B_W1), c.N, P, c.st));
-    else if (tcb)
+    if (tcb)
         UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
-                              at<double>(ws, w.bstats0), c.N, P, c.st));
+                              at<double>(ws, w.bstats0), c.N, P, single, c.st));
     else
         UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
-    if (dual1) {
-    } else if (tcw)
+    if (tcw)
         UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
-                           gf(c.g, UB200_B_W1), c.N, P, c.st));
+                           gf(c.g, UB200_B_W1), c.N, P, single, c.st));
     else
         UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, c.st));
@@ -331,14 +318,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
     atomicAdd(&stats[((size_t)n * C + ch) * 2 + which], t);
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
-    }
-    return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 }  // namespace ub
 
@@ -350,25 +330,15 @@ int ub200_version(void) { return 100; }
 
 unsigned long long ub200_launch_count(void) { return g_launch_count; }
 
-int ub200_tc_debug_set(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set(desc_hi, desc_lbo, idesc); }
-int ub200_tc_set_warp_specialized(int on) { return tc_set_warp_specialized(on); }
-int ub200_tc_set_split_epilogue(int on) { return tc_set_split_epilogue(on); }
-int ub200_tc_set_dual(int mask) { return tc_set_dual(mask); }
-int ub200_dwconv_set_bwd_split(int on) { return dwconv_set_bwd_split(on); }
-int ub200_dwconv_set_mode(int mode) { return dwconv_set_mode(mode); }
-int ub200_inconv_set_moments(int on) { g_inconv_moments = on ? 1 : 0; return UB_OK; }
-int ub200_tc_debug_set_wgrad(unsigned desc_hi, unsigned desc_lbo, unsigned idesc) { return tc_debug_set_wgrad(desc_hi, desc_lbo, idesc); }
-
 // dW1[256][128] = sum_p dh1[p][o] * n0[p][k] with n0 = x*coef0 (x: [N*P][128]) and dh1 = a*dz1 + b*h1 + c ([N*P][256]):
 // the weight-gradient GEMM of the 1x1 expand convolution alone (unit tests).  dw1 is accumulated into.
 int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const float* dz1, const float* h1, const float* bc1,
                          float* dw1, int N, int P, void* scratch, void* stream) {
     if (!x || !coef0 || !dz1 || !h1 || !bc1 || !dw1 || !scratch || P % 64) return UB_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    UB_TRY(tc_set_single_pass((backend & 4) != 0));
     if (backend & 2)
         return tc_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
-                         static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
+                         static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, (backend & 4) != 0, st);
     return simt_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
                        static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
 }
@@ -380,10 +350,9 @@ int ub200_gemm1_forward(int backend, const float* x, const float* coef, const fl
     if (!x || !coef || !w1 || !h1 || !stats || !scratch || P % 128) return UB_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(stats, 0, (size_t)N * UB_HID * 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
-    UB_TRY(tc_set_single_pass((backend & 4) != 0));
     if (backend & 1) {
         UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, st));
-        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, st);
+        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, (backend & 4) != 0, st);
     }
     UB_TRY(launch_transpose(w1, static_cast<float*>(scratch), UB_HID, UB_WIDTH, st));
     return simt_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), static_cast<const float*>(scratch), h1, stats, N, P, st);
@@ -482,16 +451,11 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
     if (ws_bytes < L.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = L.P;
-    UB_TRY(tc_set_single_pass((d->gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, L.fwd_zero_begin), 0, L.fwd_zero_end - L.fwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
 
     // in_conv: conv1x1 + norm + ReLU (+ pad-mask test), NCHW -> pixel-major
-    if (g_inconv_moments)
-        UB_PROF(KID_INCONV, st, launch_inconv_stats_moments(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.mom_in),
-                                   at<double>(ws, L.stats_c0), at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
-    else
-        UB_PROF(KID_INCONV, st, launch_inconv_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.stats_c0),
-                                   at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
+    UB_PROF(KID_INCONV, st, launch_inconv_stats_moments(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<double>(ws, L.mom_in),
+                               at<double>(ws, L.stats_c0), at<int>(ws, L.notpad), d->pad_value, L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize(at<double>(ws, L.stats_c0), pf(params, UB200_P_IN_NORM_W), pf(params, UB200_P_IN_NORM_B),
                                 pfm(params, UB200_P_IN_NORM_RM), pfm(params, UB200_P_IN_NORM_RV), at<Coef>(ws, L.coef_in),
                                 at<MeanRstd>(ws, L.mr_in), L.Ne, UB_WIDTH, d->enc_groups, (double)P, d->norm_eps, d->bn_momentum,
@@ -529,7 +493,6 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
     if (ws_bytes < L.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = L.P;
-    UB_TRY(tc_set_single_pass((d->gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, L.bwd_zero_begin), 0, L.bwd_zero_end - L.bwd_zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     float* gA = at<float>(ws, L.gA);
     float* gB = at<float>(ws, L.gB);
@@ -557,26 +520,17 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
                            d->norm_eps, st));
     UB_PROF(KID_TEMPORAL_BWD, st, launch_maxpool_bwd(at<float>(ws, L.dpooled), at<int>(ws, L.pool_idx), gB, L.Ne, P, st));
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
-    enc.relu_mask_dx = g_inconv_moments;      // the gram pass then consumes dgn = dX0 * [x0 > 0] directly
+    enc.relu_mask_dx = 1;                     // the gram pass then consumes dgn = dX0 * [x0 > 0] directly
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
     // in_conv backward (no input gradient)
-    if (g_inconv_moments)
-        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, nullptr /* ReLU mask already applied by residual_bwd */, gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
-                                   at<MeanRstd>(ws, L.mr_in), at<double>(ws, L.gram_in), at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
-    else
-        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_stats(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
-                                   at<MeanRstd>(ws, L.mr_in), gA, at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
+    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, nullptr /* ReLU mask already applied by residual_bwd */, gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
+                               at<MeanRstd>(ws, L.mr_in), at<double>(ws, L.gram_in), at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize_bwd(at<double>(ws, L.bstats_in), pf(params, UB200_P_IN_NORM_W), at<MeanRstd>(ws, L.mr_in),
                                     at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_NORM_W), gf(grads, UB200_P_IN_NORM_B), L.Ne,
                                     UB_WIDTH, d->enc_groups, (double)P, d->training, st));
-    if (g_inconv_moments)
-        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_finish(at<double>(ws, L.gram_in), at<double>(ws, L.mom_in), pf(params, UB200_P_IN_W),
-                                   pf(params, UB200_P_IN_B), at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_W), gf(grads, UB200_P_IN_B),
-                                   L.Ne, d->C_in, P, st));
-    else
-        UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_wgrad(input, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B), at<Coef>(ws, L.coef_in),
-                                   at<MeanRstd>(ws, L.mr_in), at<BCoef>(ws, L.bc_in), gA, gf(grads, UB200_P_IN_W),
-                                   gf(grads, UB200_P_IN_B), L.Ne, d->C_in, P, st));
+    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_finish(at<double>(ws, L.gram_in), at<double>(ws, L.mom_in), pf(params, UB200_P_IN_W),
+                               pf(params, UB200_P_IN_B), at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_W), gf(grads, UB200_P_IN_B),
+                               L.Ne, d->C_in, P, st));
     return UB_OK;
 }
 
@@ -599,6 +553,24 @@ int ub200_gnll_forward(const float* pred, long long pred_sb, const float* target
                        B, P, eps, full, static_cast<cudaStream_t>(stream));
 }
 
+int ub200_mgnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                     int var_ch, int B, int P, float eps, const float* grad_loss, float* loss, float* dpred, float* dvar, int* neg_flag,
+                     void* stream) {
+    if (!pred || !target || !var || (var_ch != 1 && var_ch != UB_S2) || B < 1 || P < 1) return UB_ERR_ARG;
+    if (grad_loss ? (!dpred || !dvar) : (!loss || !neg_flag)) return UB_ERR_ARG;
+    return launch_mgnll_none(pred, pred_sb, target, targ_sb, var, var_sb, var_ch, grad_loss, loss, dpred, dvar, neg_flag, B, P, eps,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int ub200_gnll_none(const float* pred, long long pred_sb, const float* target, long long targ_sb, const float* var, long long var_sb,
+                    int B, int P, float eps, int full, const float* grad_loss, float* loss, float* var_out, float* dpred, float* dvar,
+                    int* neg_flag, void* stream) {
+    if (!pred || !target || !var || B < 1 || P < 1) return UB_ERR_ARG;
+    if (grad_loss ? (!dpred || !dvar) : (!loss || !neg_flag)) return UB_ERR_ARG;
+    return launch_gnll_none(pred, pred_sb, target, targ_sb, var, var_sb, grad_loss, loss, var_out, dpred, dvar, neg_flag, B, P, eps, full,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, size_t n, void* stream) {
     if (!in || !grad_loss || !out) return UB_ERR_ARG;
     return launch_scale_by_scalar(in, grad_loss, out, n, static_cast<cudaStream_t>(stream));
@@ -607,6 +579,15 @@ int ub200_scale_by_scalar(const float* in, const float* grad_loss, float* out, s
 int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int P, float eps, float* cov, void* stream) {
     if (!var || !cov || (var_ch != 1 && var_ch != UB_S2)) return UB_ERR_ARG;
     return launch_covariance(var, var_sb, var_ch, cov, B, P, eps, static_cast<cudaStream_t>(stream));
+}
+
+// ---- fused Adam over flat buffers (torch.optim.Adam semantics; base_model.py:48-51,122) ----
+int ub200_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, int step, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || step < 1) return UB_ERR_ARG;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    return launch_adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1),
+                            (float)(1.0 / sqrt(bc2)), grad_scale, zero_grad, static_cast<cudaStream_t>(stream));
 }
 
 // ---- standalone out_conv + head (tests, calibration sweep) ----
@@ -636,7 +617,7 @@ static void mb_layout(int N, int H, int W, MbLayout& M) {
     M.dn0 = b.take((size_t)N * H * W * UB_WIDTH * 4);
     M.du = b.take((size_t)N * H * W * UB_HID * 4);
     M.dz1 = b.take((size_t)N * H * W * UB_HID * 4);
-    M.max_parts = tc_dual_parts(N, H * W) > MAX_PARTS ? tc_dual_parts(N, H * W) : MAX_PARTS;
+    M.max_parts = MAX_PARTS;
     M.partial = b.take((size_t)M.max_parts * UB_WIDTH * UB_HID * 4);
     M.total = b.off;
 }
@@ -661,7 +642,6 @@ int ub200_mbconv_forward(const float* x, const void* const* block_params, int N,
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = H * W;
-    UB_TRY(tc_set_single_pass((gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, M.zero_begin), 0, M.zero_end - M.zero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     const int chunk = 256;
     colstats_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(x, at<double>(ws, M.w.stats0), P, chunk);
@@ -680,7 +660,6 @@ int ub200_mbconv_backward(const float* x, const void* const* block_params, const
     mb_layout(N, H, W, M);
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    UB_TRY(tc_set_single_pass((gemm_backend & 4) != 0));
     if (cudaMemsetAsync(at<char>(ws, M.bzero_begin), 0, M.bzero_end - M.bzero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     BlockCtx c = mb_ctx(M, block_params, block_grads, ws, N, H, W, groups, training, 1e-5f, 0.1f, gemm_backend, st);
     return mbconv_backward(c, x, dout, dx, at<float>(ws, M.dn0), at<float>(ws, M.du), at<float>(ws, M.dz1),

@@ -25,7 +25,13 @@ def shard_batch(n: int, rank: int, world: int) -> slice:
 class FlatGradAllReduce:
     """Owns a flat fp32 gradient buffer; ``p.grad`` of every parameter is a view into it.  The parameters are flagged so
     that ``uncrtaints_b200.UNCRTAINTS``'s backward accumulates straight into these views (the C ABI adds into its gradient
-    slots) instead of handing autograd one temporary per parameter; call ``zero_()`` before every backward."""
+    slots) instead of handing autograd one temporary per parameter; call ``zero_()`` before every backward.
+
+    The aliasing is ENFORCED, not assumed: ``optimizer.zero_grad()`` of torch >= 2.0 sets ``p.grad = None`` (the reference's
+    own step does that, base_model.py:120), after which autograd would create fresh gradient tensors and an all-reduce of the
+    flat buffer would silently reduce stale zeros.  ``ensure_attached()`` -- called by ``all_reduce_mean()`` and
+    ``zero_()`` -- folds any such foreign gradient into the flat buffer and re-points ``p.grad`` at its view.
+    """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -33,21 +39,50 @@ class FlatGradAllReduce:
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
+        self.reattached = 0                      # how many gradients had to be folded back (0 in a well-behaved loop)
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            v = self.flat[off:off + n].view_as(p)
+            self.views.append(v)
+            p.grad = v
             p._ub200_grad_in_place = True
             off += n
 
+    def ensure_attached(self, discard: bool = False) -> None:
+        """Every ``p.grad`` must be its view of the flat buffer.  If it is not, somebody set it to None since the last
+        ``zero_()`` (``zero_grad(set_to_none=True)`` semantics: None means zero), so the view's content is stale: a foreign
+        tensor (autograd allocated it during backward because the view was gone) REPLACES the view's content, a gradient
+        that is still None zeroes it -- unless ``discard`` (we are about to zero the whole buffer anyway)."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is not None and g.data_ptr() == v.data_ptr() and g.shape == v.shape:
+                continue
+            if not discard:
+                if g is None:
+                    v.zero_()
+                else:
+                    v.copy_(g.to(device=v.device, dtype=torch.float32))
+            p.grad = v
+            self.reattached += 1
+
     def zero_(self) -> None:
+        self.ensure_attached(discard=True)
         self.flat.zero_()
 
+    zero_grad = zero_         # bucket-aware replacement of optimizer.zero_grad(): zeroes in place, grads stay views
+
     def all_reduce_mean(self) -> None:
-        """Sum over ranks, scale by 1/world: the gradient of the mean of the per-rank losses."""
+        """Mean over ranks of the flat gradient (the gradient of the mean of the per-rank losses): ONE collective; NCCL's
+        AVG reduction applies the 1/world factor inside the all-reduce kernel (no separate scaling launch)."""
+        self.ensure_attached()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / dist.get_world_size(self.group))
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:                                 # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / dist.get_world_size(self.group))
 
 
 class HostToDevicePrefetcher:
