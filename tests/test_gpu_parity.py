@@ -64,9 +64,10 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3])
+@pytest.mark.parametrize("backend", [0, 1, 3, 11])
 def test_golden_diag_train_pad(golden_weights, backend):
-    """backend 3 = the product path (tcgen05 GEMMs everywhere); 0 / 1 = the fp32 CUDA-core GEMMs kept as test comparators."""
+    """backend 3 = tcgen05 GEMMs everywhere, 11 = additionally the fused input-/weight-gradient kernels; 0 / 1 = the fp32 CUDA-core
+    GEMMs kept as test comparators."""
     import uncrtaints_b200 as ub
     c = load_npz("case_diag_train_pad.npz")
     x, y, d = (torch.from_numpy(c[k]).cuda() for k in ("x", "y", "dates"))
@@ -203,7 +204,7 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3])
+@pytest.mark.parametrize("backend", [0, 1, 3, 11])
 @pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16)),
                                                    (0, 1, (3, 16, 32)), (0, 0, (3, 16, 32))])
 def test_mbconv_block_vs_oracle(golden_weights, groups, training, shape, backend):
@@ -290,6 +291,9 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
     (2, 5, 64, 96, "diag", True, True, 3),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
     (1, 3, 128, 64, "iso", False, False, 0),      # eval mode, isotropic covariance
     (16, 3, 64, 64, "diag", True, False, 3),      # BASELINE config #2's batch and sequence length (BatchNorm over 16 samples)
+    (16, 3, 64, 64, "diag", True, False, 11),     # ... with the fused input-/weight-gradient kernels (CTAs span several frames)
+    (2, 5, 64, 96, "diag", True, True, 11),
+    (1, 2, 256, 256, "diag", True, False, 11),
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub
@@ -564,8 +568,8 @@ def _oracle_step64(golden_weights, x, y, d, cfg, train, keep, pool_idx=None, fus
         O.set_fused(False)
 
 
-@pytest.mark.parametrize("B,T,covmode", [(2, 3, "diag"), (1, 3, "iso")])
-def test_headline_resolution_default_backend(golden_weights, B, T, covmode):
+@pytest.mark.parametrize("B,T,covmode,backend", [(2, 3, "diag", None), (1, 3, "iso", None), (2, 3, "diag", 11)])
+def test_headline_resolution_default_backend(golden_weights, B, T, covmode, backend):
     """BASELINE config #2's frame size (15x256x256, T=3) through the DEFAULT backend (tcgen05 bf16x3 forward, input-gradient and
     weight-gradient GEMMs; 148 persistent weight-gradient CTAs with fp32 TMEM accumulation over ~2.6k pixels each at B=2)
     against the fp64 oracle: outputs, loss and every gradient within 1e-3 -- and, with the max-pool index selection of the CUDA
@@ -578,7 +582,7 @@ def test_headline_resolution_default_backend(golden_weights, B, T, covmode):
     keep = O.dropout_keep_mask(16, B, T, H, W, seed=9)
     cfg = O.OracleConfig(covmode=covmode)
     cov = cfg.covar_dim
-    net = make_net(golden_weights, covmode, None).train()          # backend None = the library default (3)
+    net = make_net(golden_weights, covmode, backend).train()       # backend None = the library default
     net._injected_keep_mask = keep.to(torch.uint8)
     out = net(x.cuda(), batch_positions=d.cuda())
     loss, _ = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=covmode, chunk=None, covariance="none")(
@@ -586,7 +590,7 @@ def test_headline_resolution_default_backend(golden_weights, B, T, covmode):
     loss.backward()
     torch.cuda.synchronize()
     idx = tap(net, "pool_idx", (B * T, 32, 32, 128), torch.int32).permute(0, 3, 1, 2).cpu().long().contiguous()
-    tag = f"headline256[B{B}T{T} {covmode} backend=default]"
+    tag = f"headline256[B{B}T{T} {covmode} backend={backend if backend is not None else 'default'}]"
     o_out, o_loss, o_grads, _ = _oracle_step64(golden_weights, x, y, d, cfg, True, keep)
     e_out, e_loss = rel_l2(out, o_out), abs(loss.item() - o_loss.item()) / abs(o_loss.item())
     gerr = {k: rel_l2(p.grad, o_grads[k]) for k, p in net.named_parameters() if not is_zero_grad_param(k)}

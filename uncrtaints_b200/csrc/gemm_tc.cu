@@ -19,6 +19,7 @@
 //   double-buffered TMEM accumulator (2 x 256 columns): the MMAs of tile t run while the threads do the epilogue
 //   of tile t-1 and load tile t+1.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -109,16 +110,41 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
     }
 }
 
-// split 8 fp32 values into bf16 hi / lo (x ~= hi + lo) and store both 16-byte chunks
+// Operand split modes ("single" argument of the kernels): 0 = bf16 hi + bf16 lo (three MMAs; ~2^-17: the input-/weight-gradient
+// GEMMs, whose operands are gradients of unbounded range), 1 = one bf16 (single-pass, reduced precision), 2 = fp16 hi + fp16 lo
+// (three MMAs; ~2^-22, i.e. fp32-grade: the FORWARD GEMMs, whose operands are normalised activations and weights, well inside
+// fp16's range -- conversions saturate instead of overflowing).  Mode 2 exists because the max-pool argmax downstream of the
+// encoder is discrete: a forward error of 6e-6 flips a handful of near-tie windows, which alone costs 5-9e-4 on the encoder
+// gradients (tests/test_gpu_parity.py::test_headline_resolution_default_backend); with 2^-22 operands the forward is as accurate as
+// an fp32 FMA chain and the flips all but disappear.
+constexpr int SPLIT_BF16X3 = 0, SPLIT_BF16X1 = 1, SPLIT_F16X3 = 2;
+// split 8 fp32 values into hi / lo halves (x ~= hi + lo) and store both 16-byte chunks
 __device__ __forceinline__ void split_store8(const float (&v)[8], char* hi_chunk, char* lo_chunk, int single = 0) {
     uint32_t h[4], l[4];
+    if (single == SPLIT_F16X3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = v[2 * i], b = v[2 * i + 1];
+            uint32_t hp, lp;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(b), "f"(a));   // upper half <- b, lower half <- a
+            float ah, bh;
+            asm("{\n\t.reg .b16 lo16, hi16;\n\tmov.b32 {lo16, hi16}, %2;\n\tcvt.f32.f16 %0, lo16;\n\tcvt.f32.f16 %1, hi16;\n\t}"
+                : "=f"(ah), "=f"(bh) : "r"(hp));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(b - bh), "f"(a - ah));
+            h[i] = hp;
+            l[i] = lp;
+        }
+        *reinterpret_cast<uint4*>(hi_chunk) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo_chunk) = make_uint4(l[0], l[1], l[2], l[3]);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float a = v[2 * i], b = v[2 * i + 1];
         uint32_t hp;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(b), "f"(a));     // upper half <- b, lower half <- a
         h[i] = hp;
-        if (!single) {
+        if (single != SPLIT_BF16X1) {
             const float ah = __uint_as_float(hp << 16), bh = __uint_as_float(hp & 0xFFFF0000u);
             uint32_t lp;
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(b - bh), "f"(a - ah));
@@ -126,7 +152,7 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], char* hi_chunk
         }
     }
     *reinterpret_cast<uint4*>(hi_chunk) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (!single) *reinterpret_cast<uint4*>(lo_chunk) = make_uint4(l[0], l[1], l[2], l[3]);
+    if (single != SPLIT_BF16X1) *reinterpret_cast<uint4*>(lo_chunk) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -397,7 +423,8 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
             const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
             const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
             const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
-            const uint32_t idesc = c_idesc;
+            // fp16 operands: A/B format fields (bits 7-9, 10-12) = 0 (F16) instead of 1 (BF16)
+            const uint32_t idesc = single == SPLIT_F16X3 ? (c_idesc & ~((7u << 7) | (7u << 10))) : c_idesc;
 #pragma unroll
             for (int j = 0; j < MH; ++j) {
                 const uint32_t d = tmem_base + acc + j * TILE_PX;
@@ -408,7 +435,7 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
                     const uint64_t xa = make_desc(b_hi + k16 * 32);
                     const uint64_t xl = make_desc(b_lo + k16 * 32);
                     tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
-                    if (!single) {
+                    if (single != SPLIT_BF16X1) {
                         tc_mma(d, wa, xl, idesc, 1);
                         tc_mma(d, wl, xa, idesc, 1);
                     }
@@ -660,25 +687,323 @@ static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, i
     return UB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused input-gradient + weight-gradient GEMM of one 1x1 convolution (gemm_backend bit 3).
+//
+// The two GEMMs of a convolution's backward read the same activation tensors: launched separately (gemm*_bwd + wgrad*) those
+// tensors stream from HBM twice (3 A + 3 Hh per MBConv-frame = 26 % of the backward bytes).  Here ONE persistent
+// kernel builds every operand tile once and feeds it to both GEMMs:
+//     conv 1 (expand, W1 [256][128]):  S = dh1 = normbwd1(dz1, h1) (256 ch, streamed in four 64-channel blocks),  R = n0 = x*sc0+sh0 (128 ch)
+//         dn0[128 ch][px] += W1^T[:, blk] . S_blk   (K-major operands, per block)        dW1^T[k][o in blk] += R^T . S_blk   (MN-major)
+//     conv 2 (project, W2 [128][256]): R = dy = normbwd3(dOut, y) (128 ch),  S = u = gelu(norm2(h2)) * gate (256 ch, four blocks)
+//         du[256 ch][px] = W2^T . R                 (K-major, once per tile)             dW2[o][k in blk]  += R^T . S_blk     (MN-major)
+// The bytes of a [64 px][64 ch] SWIZZLE_128B block are at the same time a K-major tile (pixels = rows) and an MN-major tile
+// (pixels = the contraction), so the same shared-memory block serves both MMAs.
+//
+// Shared memory cannot hold the 128 KB weight image, a 128-pixel operand ring AND a second 128-pixel operand, so the tile is
+// 64 pixels (UMMA M=128, N=64, K=16): 128 KB weights + 32 KB resident operand R + 3 x 16 KB ring of S blocks + coefficients.
+// TMEM: double-buffered input-gradient accumulator (2 x 64 or 2 x 128 columns) + the whole 128 x 256 weight gradient (256 columns),
+// accumulated over all tiles of the CTA and written once as a partial (reduce_partials_kernel sums the <= 148 partials).
+// One persistent CTA per SM walks a contiguous range of tiles across frames; per-frame coefficient tables are refilled at frame
+// boundaries, the per-channel statistics are flushed by the epilogue when ITS tile (one behind) changes frame.
+// ------------------------------------------------------------------------------------------
+constexpr int FPX = 64;                       // pixels per tile
+constexpr int FBLK = FPX * 128;               // one [64 px][64 ch] bf16 block: 8 KB
+constexpr int FRING = 3;                      // ring stages (hi block + lo block = 16 KB each)
+constexpr int F_W_BYTES = UB_WIDTH * UB_HID * 4;      // hi + lo weight image: 128 KB
+constexpr uint32_t F_IDESC_K = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 17) | (8u << 24);      // F32 acc, BF16 x BF16, K-major A/B, N=64, M=128
+constexpr uint32_t F_IDESC_MN = F_IDESC_K | (1u << 15) | (1u << 16);                               // both operands MN-major
+
+__device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    const long long t0 = clock64();
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000ll) __trap();      // ~2 s: a protocol error must fault, not hang the GPU
+    } while (!ok);
+}
+
+template <int CONV, class LS, class LR, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __restrict__ partial, int P, long long total_tiles,
+              int sa, int sb, int single) {
+    constexpr int NOUT = CONV == 1 ? UB_WIDTH : UB_HID;       // channels of the input gradient (TMEM lanes x MH)
+    constexpr int MH = NOUT / 128;
+    constexpr int ACC = MH * FPX;                             // TMEM columns of one input-gradient stage
+    constexpr int DW_COL = 2 * ACC;                           // weight-gradient accumulator: 256 columns behind the two stages
+    constexpr int W_HALF = F_W_BYTES / 2;
+    constexpr int PARTS = 2, CH = 16 / PARTS;                 // the epilogue of tile t-1 runs in two slices during tile t
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    char* sW = smem;                                          // weight image [hi|lo][K/64][NOUT rows][128 B]
+    char* sR = sW + F_W_BYTES;                                // resident operand: hi {blk0, blk1}, lo {blk0, blk1}: 32 KB
+    char* sS = sR + 4 * FBLK;                                 // ring: FRING x {hi block, lo block}
+    float* sCfS = reinterpret_cast<float*>(sS + FRING * 2 * FBLK);      // 3 x 256 coefficients of S (SoA, quad-split)
+    float* sCfR = sCfS + 3 * UB_HID;                                     // 3 x 128 coefficients of R
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCfR + 3 * UB_WIDTH);   // ringfree[FRING], accfull[2], rfree, done
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + FRING + 4);
+    const uint32_t bRing = smem_u32(&sBar[0]), bAcc = smem_u32(&sBar[FRING]), bRfree = smem_u32(&sBar[FRING + 2]),
+                   bDone = smem_u32(&sBar[FRING + 3]);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+
+    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
+    const int ntiles = t1 > t0 ? (int)(t1 - t0) : 0;
+    const int tiles_per_frame = P / FPX;
+    const int Q = ntiles * 4;                                 // pipeline steps: (tile, 64-channel block of S)
+    float* dst = partial + (size_t)blockIdx.x * UB_WIDTH * UB_HID;
+    if (Q == 0) {
+        for (int i = tid; i < UB_WIDTH * UB_HID; i += THREADS) dst[i] = 0.f;
+        return;
+    }
+    // producer roles: S item = 8 channels (chunk sc) of row sr of the current block; R items = chunk rc of rows rr, rr + 32
+    const int sr = tid / 8, sc = tid % 8, rr = tid / 16, rc = tid % 16;
+    typename LS::Raw raws;
+    typename LR::Raw rawr[2];
+    {
+        const size_t row0 = (size_t)t0 * FPX;
+        ls.issue(row0 + sr, UB_HID, sc * 8, raws);
+        lr.issue(row0 + rr, UB_WIDTH, rc * 8, rawr[0]);
+        lr.issue(row0 + rr + 32, UB_WIDTH, rc * 8, rawr[1]);
+    }
+    // ---- one-time setup: weights, barriers, TMEM ----
+    for (int i = tid; i < F_W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
+    if (tid == 0) {
+        for (int i = 0; i < FRING + 4; ++i) mbar_init(smem_u32(&sBar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+
+    // ---- epilogue state (thread = one output channel per M-block; 16 pixels of a tile, in PARTS slices) ----
+    const int lq = warp % 4, pc = warp / 4;
+    typename Epi::State est[MH];
+    float stat[MH][Epi::NS];
+    int epi_n = -1;
+    auto flush_stats = [&]() {
+        if (epi_n < 0) return;
+        double* d = ep.dst(epi_n, NOUT);
+#pragma unroll
+        for (int j = 0; j < MH; ++j)
+#pragma unroll
+            for (int s = 0; s < Epi::NS; ++s) atomicAdd(&d[(size_t)(j * 128 + lq * 32 + lane) * Epi::NS + s], (double)stat[j][s]);
+    };
+    auto epilogue_part = [&](int e, int part) {              // local tile e, slice `part`: TMEM -> registers -> global (+ statistics)
+        const long long t = t0 + e;
+        const int n = (int)(t / tiles_per_frame);
+        if (n != epi_n) {                                     // the epilogue's tile entered a new frame (thread-local bookkeeping)
+            flush_stats();
+            epi_n = n;
+#pragma unroll
+            for (int j = 0; j < MH; ++j) {
+                ep.init(n, NOUT, j * 128 + lq * 32 + lane, est[j]);
+#pragma unroll
+                for (int s = 0; s < Epi::NS; ++s) stat[j][s] = 0.f;
+            }
+        }
+        if (part == 0) mbar_wait_guard(bAcc + (e & 1) * 8, (uint32_t)(e >> 1) & 1);
+        tc_fence_after();
+        const size_t prow0 = (size_t)t * FPX + pc * 16 + part * CH;
+#pragma unroll
+        for (int j = 0; j < MH; ++j) {
+            float v[CH];
+            tmem_ldn<CH>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(e & 1) * ACC + j * FPX + pc * 16 + part * CH, v);
+            ep.template apply<CH>(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+        }
+        tc_fence_before();
+    };
+
+    int cur_n = -1;
+    for (int q = 0; q < Q; ++q) {
+        const int it = q >> 2, blk = q & 3;
+        const long long t = t0 + it;
+        if (blk == 0) {
+            const int n = (int)(t / tiles_per_frame);
+            if (n != cur_n) {                                 // block-uniform: per-frame coefficient tables of the loaders
+                __syncthreads();
+                ls.fill(n, UB_HID, sCfS);
+                lr.fill(n, UB_WIDTH, sCfR);
+                cur_n = n;
+                __syncthreads();
+            }
+        }
+        const typename LS::Raw curs = raws;
+        const typename LR::Raw curr[2] = {rawr[0], rawr[1]};
+        if (q + 1 < Q) {                                      // prefetch the next step's operands (kept in flight across this step)
+            const int nit = (q + 1) >> 2, nblk = (q + 1) & 3;
+            const size_t nrow0 = (size_t)(t0 + nit) * FPX;
+            ls.issue(nrow0 + sr, UB_HID, nblk * 64 + sc * 8, raws);
+            if (nblk == 0) {
+                lr.issue(nrow0 + rr, UB_WIDTH, rc * 8, rawr[0]);
+                lr.issue(nrow0 + rr + 32, UB_WIDTH, rc * 8, rawr[1]);
+            }
+        }
+        const uint32_t slot = (uint32_t)q % FRING, use = (uint32_t)q / FRING;
+        mbar_wait_guard(bRing + slot * 8, (use & 1) ^ 1);              // MMAs that read this ring slot are done
+        char* s_hi = sS + slot * 2 * FBLK;
+        char* s_lo = s_hi + FBLK;
+        if (blk == 0) {
+            mbar_wait_guard(bRfree, ((uint32_t)it & 1) ^ 1);           // the previous tile's MMAs no longer read R
+            typename LR::Cf cfr;
+            lr.coefs(UB_WIDTH, rc * 8, sCfR, cfr);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = rr + 32 * j;
+                float v[8];
+                lr.finish(curr[j], cfr, v);
+                const int off = (rc / 8) * FBLK + r * 128 + (((rc % 8) ^ (r & 7)) << 4);
+                split_store8(v, sR + off, sR + 2 * FBLK + off, single);
+            }
+        }
+        {
+            typename LS::Cf cfs;
+            ls.coefs(UB_HID, blk * 64 + sc * 8, sCfS, cfs);
+            float v[8];
+            ls.finish(curs, cfs, v);
+            const int off = sr * 128 + ((sc ^ (sr & 7)) << 4);
+            split_store8(v, s_hi + off, s_lo + off, single);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t r_hi = smem_u32(sR), r_lo = r_hi + 2 * FBLK, b_hi = smem_u32(s_hi), b_lo = smem_u32(s_lo);
+            if constexpr (CONV == 1) {
+                // dn0[128][px] += W1^T[:, blk] . dh1_blk
+                const uint32_t a_hi = smem_u32(sW) + blk * (NOUT * 128), a_lo = a_hi + W_HALF;
+                const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC;
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                    const uint64_t wa = make_desc(a_hi + k16 * 32), wl = make_desc(a_lo + k16 * 32);
+                    const uint64_t xa = make_desc(b_hi + k16 * 32), xl = make_desc(b_lo + k16 * 32);
+                    tc_mma(d, wa, xa, F_IDESC_K, (blk | k16) != 0);
+                    if (!single) {
+                        tc_mma(d, wa, xl, F_IDESC_K, 1);
+                        tc_mma(d, wl, xa, F_IDESC_K, 1);
+                    }
+                }
+            } else {
+                if (blk == 0) {                               // du[256][px] = W2^T . dy   (both K-blocks of R, two M-blocks)
+#pragma unroll
+                    for (int j = 0; j < MH; ++j) {
+                        const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC + j * FPX;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                            for (int k16 = 0; k16 < 4; ++k16) {
+                                const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128) + j * (128 * 128) + k16 * 32;
+                                const uint64_t wa = make_desc(a_hi), wl = make_desc(a_hi + W_HALF);
+                                const uint64_t xa = make_desc(r_hi + kb * FBLK + k16 * 32), xl = make_desc(r_lo + kb * FBLK + k16 * 32);
+                                tc_mma(d, wa, xa, F_IDESC_K, (kb | k16) != 0);
+                                if (!single) {
+                                    tc_mma(d, wa, xl, F_IDESC_K, 1);
+                                    tc_mma(d, wl, xa, F_IDESC_K, 1);
+                                }
+                            }
+                    }
+                    tc_commit(bAcc + (it & 1) * 8);
+                }
+            }
+            // weight gradient: D[128 (channels of R)][blk*64 .. +64 (channels of S)] += R^T . S_blk  (contraction over the 64 pixels)
+            {
+                const uint32_t d = tmem_base + DW_COL + blk * 64;
+#pragma unroll
+                for (int p16 = 0; p16 < FPX / 16; ++p16) {
+                    const uint64_t ah = make_wg_desc(r_hi + p16 * 2048), al = make_wg_desc(r_lo + p16 * 2048);
+                    const uint64_t bh = make_wg_desc(b_hi + p16 * 2048), bl = make_wg_desc(b_lo + p16 * 2048);
+                    tc_mma(d, ah, bh, F_IDESC_MN, (it | p16) != 0);
+                    if (!single) {
+                        tc_mma(d, ah, bl, F_IDESC_MN, 1);
+                        tc_mma(d, al, bh, F_IDESC_MN, 1);
+                    }
+                }
+            }
+            tc_commit(bRing + slot * 8);                                   // frees the ring slot
+            if (blk == 3) {
+                if constexpr (CONV == 1) tc_commit(bAcc + (it & 1) * 8);   // input-gradient accumulator of this tile complete
+                tc_commit(bRfree);                                         // R may be overwritten by the next tile
+                if (q == Q - 1) tc_commit(bDone);
+            }
+        }
+        // a slice of the previous tile's epilogue while this step's MMAs run; the slice after the last block also covers the
+        // MMA latency before the next tile overwrites R
+        if (it > 0 && (blk & 1)) epilogue_part(it - 1, blk >> 1);
+    }
+#pragma unroll
+    for (int part = 0; part < PARTS; ++part) epilogue_part(ntiles - 1, part);
+    flush_stats();
+    // ---- weight-gradient partial of this CTA ----
+    mbar_wait_guard(bDone, 0);
+    tc_fence_after();
+    {
+        const int cbk = warp / 4;                             // lanes lq*32.., columns cbk*64..
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + DW_COL + cbk * 64 + hh * 32, v);
+            const int m = lq * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)m * sa + (size_t)(cbk * 64 + hh * 32 + i) * sb] = v[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+template <int CONV, class LS, class LR, class Epi>
+static int launch_bwd_fused(LS ls, LR lr, const void* wimg, Epi ep, float* partial, int max_parts, int N, int P, int sa, int sb,
+                            int single, int* nparts, cudaStream_t st) {
+    if (P % FPX != 0) return UB_ERR_ARG;
+    constexpr size_t smem = (size_t)F_W_BYTES + 4 * FBLK + FRING * 2 * FBLK + 3 * (UB_HID + UB_WIDTH) * sizeof(float) + (FRING + 4) * 8 + 16 + 1024;
+    auto kern = bwd_tc_kernel<CONV, LS, LR, Epi>;
+    UB_SET_SMEM(kern, smem);
+    const long long total = (long long)N * (P / FPX);
+    const int blocks = (int)(total < max_parts ? total : max_parts);
+    kern<<<blocks, THREADS, smem, st>>>(ls, lr, static_cast<const uint4*>(wimg), ep, partial, P, total, sa, sb, single);
+    UB_CHECK_LAUNCH();
+    *nparts = blocks;
+    return UB_OK;
+}
+
 // Weight image: src is fp32 [rows][K] (transpose == 0) or [K][rows] (transpose == 1, i.e. the M operand is src^T).
 // Output: bf16 hi image then lo image, each [K/64][rows][64] in the K-major SWIZZLE_128B layout.
-__global__ void prep_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ img, int rows, int K, int transpose) {
+__global__ void prep_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ img, int rows, int K, int transpose, int f16) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * K) return;
     const int r = i / K, k = i % K;
     const float w = transpose ? src[(size_t)k * rows + r] : src[i];
-    const __nv_bfloat16 hb = __float2bfloat16_rn(w);
-    const __nv_bfloat16 lb = __float2bfloat16_rn(w - __bfloat162float(hb));
+    uint16_t hbits, lbits;
+    if (f16) {            // fp16 hi / lo (forward images, SPLIT_F16X3); saturating like the activation split
+        const float ws = fminf(fmaxf(w, -65504.f), 65504.f);
+        const __half hh = __float2half_rn(ws);
+        const __half lh = __float2half_rn(fminf(fmaxf(w - __half2float(hh), -65504.f), 65504.f));
+        hbits = __half_as_ushort(hh);
+        lbits = __half_as_ushort(lh);
+    } else {
+        const __nv_bfloat16 hb = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lb = __float2bfloat16_rn(w - __bfloat162float(hb));
+        hbits = __bfloat16_as_ushort(hb);
+        lbits = __bfloat16_as_ushort(lb);
+    }
     const int kb = k / KBLK, kk = k % KBLK;
     const size_t off = ((size_t)kb * rows + r) * 128 + (((kk / 8) ^ (r & 7)) << 4) + (kk % 8) * 2;   // bytes
-    img[off / 2] = __bfloat16_as_ushort(hb);
-    img[(off + (size_t)rows * K * 2) / 2] = __bfloat16_as_ushort(lb);
+    img[off / 2] = hbits;
+    img[(off + (size_t)rows * K * 2) / 2] = lbits;
 }
 
 }  // namespace tc
 
-int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, cudaStream_t st) {
-    tc::prep_weights_kernel<<<(rows * K + 255) / 256, 256, 0, st>>>(src, static_cast<uint16_t*>(img), rows, K, transpose);
+int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, int f16, cudaStream_t st) {
+    tc::prep_weights_kernel<<<(rows * K + 255) / 256, 256, 0, st>>>(src, static_cast<uint16_t*>(img), rows, K, transpose, f16);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
@@ -722,6 +1047,31 @@ int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* 
     tc::TLoadNormBwd lb{dz1, h1, bc1};
     int nparts = 0;
     int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
+    if (rc != UB_OK) return rc;
+    return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
+}
+
+// Fused backward of the project convolution: du + Norm2-backward sums (as tc_gemm2_bwd) AND dW2 += dy^T u (as tc_wgrad2) in one pass
+int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
+                       const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
+                       float* dw2, int N, int P, int single, cudaStream_t st) {
+    tc::TLoadGeluGate ls{h2, coef2, gate};
+    tc::TLoadNormBwd lr{dout, y, bc3};
+    tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
+    int nparts = 0;
+    int rc = tc::launch_bwd_fused<2>(ls, lr, w2timg, ep, partial, max_parts, N, P, UB_HID, 1, single, &nparts, st);
+    if (rc != UB_OK) return rc;
+    return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
+}
+// Fused backward of the expand convolution: dn0 + PreNorm-backward sums (as tc_gemm1_bwd) AND dW1 += dh1^T n0 (as tc_wgrad1)
+int tc_gemm1_bwd_fused(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                       const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
+                       int P, int single, cudaStream_t st) {
+    tc::TLoadNormBwd ls{dz1, h1, bc1};
+    tc::TLoadNormed lr{x, coef0};
+    tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
+    int nparts = 0;
+    int rc = tc::launch_bwd_fused<1>(ls, lr, w1timg, ep, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
 }

@@ -41,8 +41,9 @@ int simt_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float
                 int max_parts, float* dw1, int N, int P, cudaStream_t st);
 
 // gemm_tc.cu (tcgen05 bf16x3 tensor-core versions of the four streaming GEMMs and the two weight-gradient GEMMs).
-// single = 1: single-pass bf16 MMAs (gemm_backend bit 2; reduced precision), 0: the fp32-parity bf16x3 split.
-int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, cudaStream_t st);
+// single: operand split mode -- 0 = bf16 hi/lo (three MMAs), 1 = one bf16 (single pass, gemm_backend bit 2, reduced precision),
+// 2 = fp16 hi/lo (three MMAs, fp32-grade; forward GEMMs only: needs a weight image prepared with f16 = 1).
+int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, int f16, cudaStream_t st);
 int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, int single, cudaStream_t st);
 int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N,
                  int P, int single, cudaStream_t st);
@@ -54,6 +55,14 @@ int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* 
               float* partial, int max_parts, float* dw2, int N, int P, int single, cudaStream_t st);
 int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
               int max_parts, float* dw1, int N, int P, int single, cudaStream_t st);
+
+// fused input-gradient + weight-gradient GEMMs (gemm_backend bit 3): one read of the shared operand tensors
+int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
+                       const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
+                       float* dw2, int N, int P, int single, cudaStream_t st);
+int tc_gemm1_bwd_fused(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                       const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
+                       int P, int single, cudaStream_t st);
 
 // dwconv_rows.cu (row-streaming depthwise kernels fed by TMA bulk copies; the backward one is fused: du, h2, h1 -> dz1 in one pass)
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,

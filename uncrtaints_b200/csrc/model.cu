@@ -214,13 +214,16 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     const int P = c.H * c.W;
     void* ws = c.ws;
     const bool tcb = (c.backend & 1) != 0;
-    const int single = (c.backend & 4) != 0;
+    // forward operands (normalised activations, weights) take the fp16 hi/lo split (2^-22), see gemm_tc.cu: SPLIT_F16X3
+    const int single = (c.backend & 4) ? 1 : 2;
     if (tcb) {
-        // M-operand images: W1 [256][128] and W2 [128][256] as stored; W2^T / W1^T for the input-gradient GEMMs
-        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, c.st));
-        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2img), UB_WIDTH, UB_HID, 0, c.st));
-        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2timg), UB_HID, UB_WIDTH, 1, c.st));
-        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1timg), UB_WIDTH, UB_HID, 1, c.st));
+        // M-operand images: W1 [256][128] and W2 [128][256] as stored (forward); W2^T / W1^T for the input-gradient GEMMs (bf16)
+        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, single == 2, c.st));
+        UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2img), UB_WIDTH, UB_HID, 0, single == 2, c.st));
+        if (need_gp) {
+            UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2timg), UB_HID, UB_WIDTH, 1, 0, c.st));
+            UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1timg), UB_WIDTH, UB_HID, 1, 0, c.st));
+        }
     } else {
         UB_TRY(launch_transpose(pf(c.p, UB200_B_W1), at<float>(ws, w.w1t), UB_HID, UB_WIDTH, c.st));
         UB_TRY(launch_transpose(pf(c.p, UB200_B_W2), at<float>(ws, w.w2t), UB_WIDTH, UB_HID, c.st));
@@ -259,13 +262,19 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
     const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
     const int single = (c.backend & 4) != 0;
-    if (tcb)
+    const bool fused = tcb && tcw && (c.backend & 8) != 0;     // input-gradient + weight-gradient GEMM of a convolution in one kernel
+    if (fused)
+        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_fused(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
+                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), at<float>(ws, w.gate), partial,
+                              MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
+    else if (tcb)
         UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, single, c.st));
     else
         UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    if (tcw)
+    if (fused) {
+    } else if (tcw)
         UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                            at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
     else
@@ -279,13 +288,17 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    if (tcb)
+    if (fused)
+        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_fused(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
+                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, MAX_PARTS, gf(c.g, UB200_B_W1), c.N, P, single, c.st));
+    else if (tcb)
         UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, single, c.st));
     else
         UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
-    if (tcw)
+    if (fused) {
+    } else if (tcw)
         UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, single, c.st));
     else
@@ -351,8 +364,9 @@ int ub200_gemm1_forward(int backend, const float* x, const float* coef, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(stats, 0, (size_t)N * UB_HID * 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
     if (backend & 1) {
-        UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, st));
-        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, (backend & 4) != 0, st);
+        const int mode = (backend & 4) ? 1 : 2;
+        UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, mode == 2, st));
+        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, mode, st);
     }
     UB_TRY(launch_transpose(w1, static_cast<float*>(scratch), UB_HID, UB_WIDTH, st));
     return simt_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), static_cast<const float*>(scratch), h1, stats, N, P, st);
