@@ -84,8 +84,8 @@ typedef struct ub200_desc {
     int need_grad;              /* keep what ub200_backward needs */
     int mean_sigmoid;           /* out_nonlin_mean (uncrtaints.py:384) */
     int gemm_backend;           /* bit 0: tcgen05 forward (fp16 hi/lo x3) / input-gradient (bf16 hi/lo x3) GEMMs; bit 1: tcgen05 weight-gradient GEMMs;
-                                   bit 2: single-pass bf16 in those (reduced precision); bit 3: input- and weight-gradient GEMM of a convolution
-                                   fused into one kernel (needs bits 0 and 1); 0 = fp32 CUDA cores (test comparator) */
+                                   bit 2: single-pass bf16 in those (reduced precision); bits 3 / 4: input- and weight-gradient GEMM of the expand /
+                                   project convolution fused into one kernel (need bits 0 and 1); default 11; 0 = fp32 CUDA cores (test comparator) */
     float scale_by;             /* uncrtaints.py:250,384 */
     float var_eps;              /* 1e-9 if scale_by == 1 else 1e-3 (uncrtaints.py:374) */
     float pad_value;            /* uncrtaints.py:245,392 */

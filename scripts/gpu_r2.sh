@@ -23,6 +23,21 @@ refarm)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_cpu.log 2>&1; tail -c 1500 gpurun_out/bench_reference_cpu.log ;;
 loss)
   timeout 300 python scripts/bench_loss.py > gpurun_out/bench_loss.log 2>&1; tail -5 gpurun_out/bench_loss.log ;;
+bench3)
+  BENCH_ARGS="--backend 3" ; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-parity --backend 3 > gpurun_out/bench_b3.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b3.log ;;
+bench11)
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --backend 11 > gpurun_out/bench_b11.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b11.log; grep -o '"parity": {[^}]*}' gpurun_out/bench_b11.log ;;
+bench27)
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-parity --backend 27 > gpurun_out/bench_b27.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b27.log ;;
+ncu)
+  for k in ${NCU_KERNELS}; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip ${NCU_SKIP:-6} -c ${NCU_COUNT:-1} -f \
+        -o gpurun_out/prof_$k python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-parity --batch ${NCU_BATCH:-4} ${BENCH_ARGS} > gpurun_out/ncu_$k.log 2>&1
+    echo "ncu $k exit $?"
+    ncu -i gpurun_out/prof_$k.ncu-rep --page raw --csv > gpurun_out/prof_$k.csv 2>/dev/null
+    ncu -i gpurun_out/prof_$k.ncu-rep --page details > gpurun_out/prof_$k.txt 2>/dev/null
+    [ "${NCU_KEEP:-0}" = "1" ] || rm -f gpurun_out/prof_$k.ncu-rep
+  done ;;
 cfg3)
   timeout 900 python bench.py --steps 5 --warmup 3 --batch 32 --t 5 --no-cpu-baseline --no-eager-baseline --no-parity ${CFG3_ARGS} > gpurun_out/bench_cfg3.log 2>&1; python scripts/show_bench.py gpurun_out/bench_cfg3.log ;;
 esac

@@ -64,7 +64,7 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3, 11])
+@pytest.mark.parametrize("backend", [0, 1, 3, 11, 27])
 def test_golden_diag_train_pad(golden_weights, backend):
     """backend 3 = tcgen05 GEMMs everywhere, 11 = additionally the fused input-/weight-gradient kernels; 0 / 1 = the fp32 CUDA-core
     GEMMs kept as test comparators."""
@@ -204,7 +204,7 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3, 11])
+@pytest.mark.parametrize("backend", [0, 1, 3, 11, 27])
 @pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16)),
                                                    (0, 1, (3, 16, 32)), (0, 0, (3, 16, 32))])
 def test_mbconv_block_vs_oracle(golden_weights, groups, training, shape, backend):
@@ -291,9 +291,9 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
     (2, 5, 64, 96, "diag", True, True, 3),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
     (1, 3, 128, 64, "iso", False, False, 0),      # eval mode, isotropic covariance
     (16, 3, 64, 64, "diag", True, False, 3),      # BASELINE config #2's batch and sequence length (BatchNorm over 16 samples)
-    (16, 3, 64, 64, "diag", True, False, 11),     # ... with the fused input-/weight-gradient kernels (CTAs span several frames)
-    (2, 5, 64, 96, "diag", True, True, 11),
-    (1, 2, 256, 256, "diag", True, False, 11),
+    (16, 3, 64, 64, "diag", True, False, 27),     # ... with both fused input-/weight-gradient kernels (CTAs span several frames)
+    (2, 5, 64, 96, "diag", True, True, 27),
+    (1, 2, 256, 256, "diag", True, False, 27),
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub
@@ -568,7 +568,7 @@ def _oracle_step64(golden_weights, x, y, d, cfg, train, keep, pool_idx=None, fus
         O.set_fused(False)
 
 
-@pytest.mark.parametrize("B,T,covmode,backend", [(2, 3, "diag", None), (1, 3, "iso", None), (2, 3, "diag", 11)])
+@pytest.mark.parametrize("B,T,covmode,backend", [(2, 3, "diag", None), (1, 3, "iso", None), (2, 3, "diag", 3)])
 def test_headline_resolution_default_backend(golden_weights, B, T, covmode, backend):
     """BASELINE config #2's frame size (15x256x256, T=3) through the DEFAULT backend (tcgen05 bf16x3 forward, input-gradient and
     weight-gradient GEMMs; 148 persistent weight-gradient CTAs with fp32 TMEM accumulation over ~2.6k pixels each at B=2)

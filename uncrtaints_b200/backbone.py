@@ -403,12 +403,13 @@ class UNCRTAINTS(nn.Module):
         return out
 
 
-_BACKEND = 3     # bit 0: tcgen05 bf16x3 forward/input-gradient GEMMs, bit 1: tcgen05 weight-gradient GEMMs, bit 2: single-pass bf16
-                 # MMAs in those (7 = the reduced-precision "bf16 tensor-core path" of BASELINE config #3); 0 = fp32 CUDA cores
+_BACKEND = 11    # bit 0: tcgen05 forward (fp16 hi/lo) / input-gradient (bf16 hi/lo) GEMMs, bit 1: tcgen05 weight-gradient GEMMs, bit 2:
+                 # single-pass bf16 MMAs in those (reduced precision), bit 3 / bit 4: fused input- + weight-gradient kernel of the
+                 # expand / project convolution; 0 = fp32 CUDA cores (test comparator)
 
 
 def set_default_gemm_backend(backend: int) -> None:
-    """bit 0: tcgen05 forward/input-gradient GEMMs, bit 1: tcgen05 weight-gradient GEMMs (default 3); 0 = fp32 CUDA cores."""
+    """See _BACKEND: default 11 (tcgen05 everywhere, fused expand-convolution backward); 0 = fp32 CUDA cores."""
     global _BACKEND
     _BACKEND = int(backend)
 

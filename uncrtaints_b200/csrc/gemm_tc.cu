@@ -757,13 +757,17 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         for (int i = tid; i < UB_WIDTH * UB_HID; i += THREADS) dst[i] = 0.f;
         return;
     }
-    // producer roles: S item = 8 channels (chunk sc) of row sr of the current block; R items = chunk rc of rows rr, rr + 32
+    // producer roles: S item = 8 channels (chunk sc) of row sr of the current block; R items = chunk rc of rows rr, rr + 32.
+    // Raw operand loads are issued TWO pipeline steps ahead (two S register sets, alternating): a 64-pixel step moves only
+    // 32 KB per SM, and one step of work does not cover the loaded HBM latency (measured: 0.51 of the HBM roof with one step
+    // ahead -- Little's law wants ~64 KB in flight per SM).
     const int sr = tid / 8, sc = tid % 8, rr = tid / 16, rc = tid % 16;
-    typename LS::Raw raws;
+    typename LS::Raw raws[2];
     typename LR::Raw rawr[2];
     {
         const size_t row0 = (size_t)t0 * FPX;
-        ls.issue(row0 + sr, UB_HID, sc * 8, raws);
+        ls.issue(row0 + sr, UB_HID, sc * 8, raws[0]);
+        ls.issue(row0 + sr, UB_HID, 64 + sc * 8, raws[1]);
         lr.issue(row0 + rr, UB_WIDTH, rc * 8, rawr[0]);
         lr.issue(row0 + rr + 32, UB_WIDTH, rc * 8, rawr[1]);
     }
@@ -822,7 +826,7 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
     };
 
     int cur_n = -1;
-    for (int q = 0; q < Q; ++q) {
+    auto step = [&](const int q, typename LS::Raw& sraw) {
         const int it = q >> 2, blk = q & 3;
         const long long t = t0 + it;
         if (blk == 0) {
@@ -835,13 +839,13 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                 __syncthreads();
             }
         }
-        const typename LS::Raw curs = raws;
+        const typename LS::Raw curs = sraw;
         const typename LR::Raw curr[2] = {rawr[0], rawr[1]};
-        if (q + 1 < Q) {                                      // prefetch the next step's operands (kept in flight across this step)
-            const int nit = (q + 1) >> 2, nblk = (q + 1) & 3;
+        if (q + 2 < Q) {                                      // prefetch the operands of step q + 2 (in flight across two steps)
+            const int nit = (q + 2) >> 2, nblk = (q + 2) & 3;
             const size_t nrow0 = (size_t)(t0 + nit) * FPX;
-            ls.issue(nrow0 + sr, UB_HID, nblk * 64 + sc * 8, raws);
-            if (nblk == 0) {
+            ls.issue(nrow0 + sr, UB_HID, nblk * 64 + sc * 8, sraw);
+            if (nblk == 0) {                                  // blk == 2: this tile's R was consumed two steps ago
                 lr.issue(nrow0 + rr, UB_WIDTH, rc * 8, rawr[0]);
                 lr.issue(nrow0 + rr + 32, UB_WIDTH, rc * 8, rawr[1]);
             }
@@ -936,6 +940,10 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         // a slice of the previous tile's epilogue while this step's MMAs run; the slice after the last block also covers the
         // MMA latency before the next tile overwrites R
         if (it > 0 && (blk & 1)) epilogue_part(it - 1, blk >> 1);
+    };
+    for (int q = 0; q < Q; q += 2) {                          // Q is a multiple of 4: the two register sets alternate statically
+        step(q, raws[0]);
+        step(q + 1, raws[1]);
     }
 #pragma unroll
     for (int part = 0; part < PARTS; ++part) epilogue_part(ntiles - 1, part);

@@ -262,8 +262,11 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
     const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
     const int single = (c.backend & 4) != 0;
-    const bool fused = tcb && tcw && (c.backend & 8) != 0;     // input-gradient + weight-gradient GEMM of a convolution in one kernel
-    if (fused)
+    // input-gradient + weight-gradient GEMM of a convolution in one kernel: bit 3 = expand convolution (default: measured
+    // 10.1 -> 7.7 ms per step), bit 4 = project convolution (measured slower: 10.0 -> 11.0 ms, its GELU-heavy loader and epilogue
+    // do not shrink with the bytes)
+    const bool fused1 = tcb && tcw && (c.backend & 8) != 0, fused2 = tcb && tcw && (c.backend & 16) != 0;
+    if (fused2)
         UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_fused(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), at<float>(ws, w.gate), partial,
                               MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
@@ -273,7 +276,7 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     else
         UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    if (fused) {
+    if (fused2) {
     } else if (tcw)
         UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                            at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
@@ -288,7 +291,7 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    if (fused)
+    if (fused1)
         UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_fused(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, MAX_PARTS, gf(c.g, UB200_B_W1), c.N, P, single, c.st));
     else if (tcb)
@@ -297,7 +300,7 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     else
         UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
-    if (fused) {
+    if (fused1) {
     } else if (tcw)
         UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, single, c.st));
