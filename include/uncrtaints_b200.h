@@ -75,7 +75,7 @@ enum {
 };
 
 typedef struct ub200_desc {
-    int B, T, C_in, H, W;       /* input [B][T][C_in][H][W]; H, W multiples of 32; T <= 8; C_in <= 16 */
+    int B, T, C_in, H, W;       /* input [B][T][C_in][H][W]; H, W multiples of 32; T <= 64 (T <= 8: register-resident temporal kernels); C_in <= 16 */
     int n_dec_blocks;           /* len(decoder_widths), default 5 (uncrtaints.py:236); one encoder block */
     int out_dim;                /* 13 + covar_dim: 26 (diag/uni), 14 (iso), 13 (none) (uncrtaints.py:357-368) */
     int enc_groups;             /* encoder_norm: 4 = GroupNorm(4) (default), 0 = BatchNorm2d */
@@ -191,6 +191,18 @@ int ub200_covariance(const float* var, long long var_sb, int var_ch, int B, int 
  * step >= 1 is the number of this update; ExponentialLR (base_model.py:51) is the caller changing lr. */
 int ub200_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, int step, float lr, float beta1,
                     float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
+
+/* Network input from the per-time-point tensors of a collated batch (prepare_data_multi, model/train_reconstruct.py:161-179:
+ * torch.stack x2 + torch.cat) in one pass: x [B][T][c_s1 + c_s2][P] from src_table, a DEVICE array of 2T device pointers --
+ * entries 0..T-1 the S1 tensors [B][c_s1][P] (ignored when c_s1 == 0), entries T..2T-1 the S2 tensors [B][c_s2][P].  P % 4 == 0. */
+int ub200_assemble_input(const void* const* src_table, float* x, int B, int T, int c_s1, int c_s2, int P, void* stream);
+
+/* img_metrics (model/src/learning/metrics.py:20-57) + SSIM (util/pytorch_ssim/__init__.py:17-37) for a batch of [B][13][H][W] images
+ * in two kernels.  acc: [B][16] doubles (zeroed by the call): 0 sum e^2, 1 sum |e|, 2 sum of per-pixel spectral angles (deg),
+ * 3..6 NaN-excluding sums of e^2, |e|, e and their count, 7..8 NaN-excluding sum of var and its count, 9 sum of the SSIM map.
+ * var (optional) [B][13][H][W]; pixelwise (optional) [B][4][H*W]: band-nanmean of error, |error|, error^2, var per pixel. */
+int ub200_img_metrics(const float* target, const float* pred, const float* var, int B, int H, int W, double* acc, float* pixelwise,
+                      void* stream);
 
 /* out_conv + head alone (uncrtaints.py:381,432-446; tests and the calibration sweep of BASELINE config #5):
  *   dec [B][P][128] pixel-major decoder output, w [out_dim][128], bias [out_dim] -> out [B][out_dim][P] with

@@ -427,6 +427,35 @@ def errvar_samplewise(target: torch.Tensor, pred: torch.Tensor, var: torch.Tenso
             "mean se": float(error.square().nanmean()), "mean var": float(var.nanmean())}
 
 
+def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    """pytorch_ssim.ssim (util/pytorch_ssim/__init__.py:7-37,72-80): per-channel 11x11 Gaussian (sigma 1.5, normalised in float32)
+    moments with zero padding; mean of the SSIM map.  img: [N,C,H,W]."""
+    g = torch.tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)], dtype=torch.float32)
+    g = (g / g.sum()).unsqueeze(1)
+    c = img1.shape[1]
+    win = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(c, 1, window_size, window_size).contiguous().to(img1.dtype)
+    pad = window_size // 2
+    mu1, mu2 = F.conv2d(img1, win, padding=pad, groups=c), F.conv2d(img2, win, padding=pad, groups=c)
+    s11 = F.conv2d(img1 * img1, win, padding=pad, groups=c) - mu1 * mu1
+    s22 = F.conv2d(img2 * img2, win, padding=pad, groups=c) - mu2 * mu2
+    s12 = F.conv2d(img1 * img2, win, padding=pad, groups=c) - mu1 * mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s11 + s22 + c2))).mean()
+
+
+def img_metrics(target: torch.Tensor, pred: torch.Tensor, var: Optional[torch.Tensor] = None) -> Dict[str, float]:
+    """img_metrics (model/src/learning/metrics.py:20-57) for one [1,13,H,W] sample, without the pixel-wise maps."""
+    rmse = torch.sqrt(torch.mean(torch.square(target - pred)))
+    mat = torch.sum(target * pred, 1)
+    mat = mat / torch.sqrt(torch.sum(target * target, 1)) / torch.sqrt(torch.sum(pred * pred, 1))
+    sam = torch.mean(torch.acos(torch.clamp(mat, -1, 1)) * 180 / math.pi)
+    out = {"RMSE": float(rmse), "MAE": float(torch.mean(torch.abs(target - pred))), "PSNR": float(20 * torch.log10(1 / rmse)),
+           "SAM": float(sam), "SSIM": float(ssim(target, pred))}
+    if var is not None:
+        out.update(errvar_samplewise(target, pred, var))
+    return out
+
+
 def variance_from_covariance(cov: torch.Tensor) -> torch.Tensor:
     """[B,1,13,13,H,W] covariance -> [B,1,13,H,W] variances (train_reconstruct.py:321-324)."""
     return cov.diagonal(dim1=2, dim2=3).moveaxis(-1, 2)

@@ -162,3 +162,25 @@ def test_install_patches_reference_factory_and_loss():
         os.chdir(cwd)
         if saved is not None:
             ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss = saved
+
+
+def test_prepare_data_multi_matches_the_reference(tmp_path):
+    """uncrtaints_b200.prepare_data_multi (pinned staging in the final layout; here on the CPU) returns what the reference's
+    prepare_data_multi (model/train_reconstruct.py:161-179) returns for the same collated batch, with and without SAR."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_loop
+    if not ref_loop.available():
+        pytest.skip("baseline/_ref not installed")
+    import uncrtaints_b200 as ub
+    tr = ref_loop.load_train_module(ref_loop.README_FLAGS + ["--device", "cpu"], str(tmp_path))
+    data = ref_loop.SyntheticSEN12MSCRTS(4, 3, 32, seed=5)
+    batch = next(iter(torch.utils.data.DataLoader(data, batch_size=2, shuffle=False)))
+    for use_sar in (True, False):
+        tr.config.use_sar = use_sar
+        want = tr.prepare_data_multi(batch, "cpu", tr.config)
+        got = ub.prepare_data_multi(batch, "cpu", tr.config)
+        for name, a, b in zip(("x", "y", "in_m", "dates"), got, want):
+            assert a.shape == b.shape, (name, a.shape, b.shape)
+            assert torch.equal(a.float(), b.float()), name

@@ -163,3 +163,83 @@ def test_bucket_survives_foreign_zero_grad_and_second_backward_raises(golden_wei
     assert bucket.reattached == len(bucket.params)
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
     assert rel_l2(bucket.flat, want) <= 1e-4
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 64, 64), (1, 256, 256), (2, 40, 72)])
+def test_gpu_img_metrics_vs_oracle(B, H, W):
+    """ub200_img_metrics (RMSE / MAE / PSNR / SAM / SSIM + NaN-aware error / variance statistics, metrics.py:20-57) for a batch in
+    two kernels, against the oracle's restatement of the reference per sample; includes a NaN variance and pixel-wise maps."""
+    import uncrtaints_b200 as ub
+    g = torch.Generator().manual_seed(11)
+    t, p = torch.rand(B, 1, 13, H, W, generator=g), torch.rand(B, 1, 13, H, W, generator=g)
+    v = torch.rand(B, 1, 13, H, W, generator=g) * 0.01
+    v[0, 0, 2, 1, 3] = float("nan")
+    got = ub.img_metrics_batch(t.cuda(), p.cuda(), v.cuda(), pixelwise=True)
+    assert len(got) == B
+    for b in range(B):
+        want = O.img_metrics(t[b], p[b], v[b])
+        for k in ("RMSE", "MAE", "PSNR", "SAM", "SSIM", "error", "mean ae", "mean se", "mean var"):
+            assert abs(got[b][k] - want[k]) <= 2e-5 * max(1.0, abs(want[k])), (b, k, got[b][k], want[k])
+        err = (t[b] - p[b])
+        assert np.allclose(got[b]["pixelwise error"], err.nanmean(0).nanmean(0).flatten().numpy(), atol=1e-6)
+        assert np.allclose(got[b]["pixelwise var"], v[b].nanmean(0).nanmean(0).flatten().numpy(), atol=1e-7)
+    one = ub.img_metrics(t[1].cuda(), p[1].cuda(), v[1].cuda(), pixelwise=False)        # the reference's per-sample signature
+    assert abs(one["SSIM"] - got[1]["SSIM"]) < 1e-12 and "pixelwise error" not in one
+
+
+def test_eval_fast_path_and_forward_only_workspace(golden_weights):
+    """Eval-mode specialisation (§8f-2): under no_grad the BatchNorm decoder blocks run the 3-kernel path (pooling fused into the
+    depthwise kernel, Norm3 + residual fused into the project GEMM) on a shared / ping-pong workspace; the output must equal the
+    general path (grad-enabled eval forward) and the oracle, and the workspace must be several times smaller."""
+    import uncrtaints_b200 as ub
+    from uncrtaints_b200 import _lib
+    B, T, H, W = 2, 3, 128, 128
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=61, pad_last=True)
+    net = make_net(golden_weights, "diag").eval()
+    out_general = net(x.cuda(), batch_positions=d.cuda()).detach()          # parameters require grad -> general path, full workspace
+    big = net._last_workspace[1].numel()
+    with torch.no_grad():
+        out_fast = net(x.cuda(), batch_positions=d.cuda())
+    small = net._last_workspace[1].numel()
+    cfg = O.OracleConfig()
+    O.set_fused(True)
+    try:
+        with torch.no_grad():
+            o_out = O.forward({k: (v.double() if v.is_floating_point() else v) for k, v in golden_weights.items()}, x.double(),
+                              d.double(), cfg, False)
+    finally:
+        O.set_fused(False)
+    assert rel_l2(out_fast, out_general) <= 1e-5
+    assert rel_l2(out_fast, o_out) <= 1e-4
+    assert small * 2.5 < big, (small, big)
+    desc = net._last_workspace[0]
+    import ctypes
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    assert _lib.lib().ub200_workspace_tap(desc, b"blk2.h1", ctypes.byref(off), ctypes.byref(nb)) != 0     # shared buffer: no tap
+    assert _lib.lib().ub200_workspace_tap(desc, b"blk5.out", ctypes.byref(off), ctypes.byref(nb)) == 0
+
+
+def test_prepare_data_multi_on_gpu():
+    """Host batch -> pinned staging -> async H2D, and device-resident batch -> ub200_assemble_input: both equal torch.stack/cat."""
+    import types
+    import uncrtaints_b200 as ub
+    g = torch.Generator().manual_seed(2)
+    B, T, H, W = 3, 4, 32, 64
+    batch = {"input": {"S1": [torch.rand(B, 2, H, W, generator=g) for _ in range(T)], "S2": [torch.rand(B, 13, H, W, generator=g) for _ in range(T)],
+                       "masks": [(torch.rand(B, H, W, generator=g) > 0.5).float() for _ in range(T)],
+                       "S1 TD": [torch.randint(1400, 1900, (B,), generator=g) for _ in range(T)],
+                       "S2 TD": [torch.randint(1400, 1900, (B,), generator=g) for _ in range(T)]},
+             "target": {"S2": [torch.rand(B, 13, H, W, generator=g)]}}
+    for use_sar in (True, False):
+        cfg = types.SimpleNamespace(use_sar=use_sar, batch_size=B)
+        want_x = torch.stack(batch["input"]["S2"], dim=1)
+        if use_sar:
+            want_x = torch.cat((torch.stack(batch["input"]["S1"], dim=1), want_x), dim=2)
+        x, y, m, dates = ub.prepare_data_multi(batch, "cuda", cfg)
+        assert x.is_cuda and torch.equal(x.cpu(), want_x) and torch.equal(y.cpu(), batch["target"]["S2"][0].unsqueeze(1))
+        assert torch.equal(m.cpu(), torch.stack(batch["input"]["masks"]).swapaxes(0, 1)) and dates.shape == (B, T)
+        dev_batch = {"input": {k: [t.cuda() for t in v] for k, v in batch["input"].items()},
+                     "target": {"S2": [batch["target"]["S2"][0].cuda()]}}
+        x2, y2, m2, d2 = ub.prepare_data_multi(dev_batch, "cuda", cfg)
+        torch.cuda.synchronize()
+        assert torch.equal(x2.cpu(), want_x) and torch.equal(d2.cpu(), dates.cpu()) and torch.equal(m2.cpu(), m.cpu())

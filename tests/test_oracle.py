@@ -217,3 +217,27 @@ def test_imposed_pool_index_is_a_noop_for_the_oracles_own_argmax(golden_weights)
     assert torch.equal(out0, out1) and float(loss0) == float(loss1)
     for k in g0:
         assert torch.equal(g0[k], g1[k]), k
+
+
+def test_oracle_img_metrics_match_live_reference():
+    """O.img_metrics / O.ssim (checker of the GPU metrics kernels) against the reference's own metrics.py + pytorch_ssim."""
+    import os, sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "model", "src")):
+        pytest.skip("/root/reference absent")
+    for p in (os.path.join(ref, "model"), ref):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ref, "model"))
+    try:
+        from src.learning.metrics import img_metrics as ref_img_metrics
+    finally:
+        os.chdir(cwd)
+    g = torch.Generator().manual_seed(3)
+    t, p = torch.rand(1, 13, 48, 40, generator=g), torch.rand(1, 13, 48, 40, generator=g)
+    v = torch.rand(1, 13, 48, 40, generator=g) * 0.01
+    want = ref_img_metrics(t, p, var=v)
+    got = O.img_metrics(t, p, v)
+    for k in ("RMSE", "MAE", "PSNR", "SAM", "SSIM", "error", "mean ae", "mean se", "mean var"):
+        assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, got[k], want[k])

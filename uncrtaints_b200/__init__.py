@@ -13,6 +13,8 @@ from .losses import (MultiGaussianNLLLoss, GaussianNLLLoss, get_loss, calc_loss,
 from .install import install  # noqa: F401
 from .parallel import FlatGradAllReduce, HostToDevicePrefetcher, HostScalarReader, shard_batch  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .metrics import img_metrics, img_metrics_batch  # noqa: F401
+from .data import prepare_data_multi  # noqa: F401
 
 __all__ = ["UNCRTAINTS", "MultiGaussianNLLLoss", "GaussianNLLLoss", "gaussian_nll_loss", "get_loss", "calc_loss", "multi_gaussian_nll_loss", "covariance_diag",
-           "install", "FusedAdam", "FlatGradAllReduce", "HostToDevicePrefetcher", "HostScalarReader", "shard_batch", "set_default_gemm_backend"]
+           "install", "prepare_data_multi", "img_metrics", "img_metrics_batch", "FusedAdam", "FlatGradAllReduce", "HostToDevicePrefetcher", "HostScalarReader", "shard_batch", "set_default_gemm_backend"]

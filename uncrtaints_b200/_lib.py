@@ -25,7 +25,7 @@ SYMBOLS = [
     "ub200_version", "ub200_launch_count", "ub200_prof_enable", "ub200_prof_num_kernels", "ub200_prof_kernel_name",
     "ub200_prof_read", "ub200_gemm1_forward", "ub200_wgrad1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
     "ub200_backward", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_mgnll_none", "ub200_gnll_none", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
-    "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward", "ub200_adam_step",
+    "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward", "ub200_adam_step", "ub200_img_metrics", "ub200_assemble_input",
 ]
 
 
@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
     L.ub200_mbconv_forward.argtypes = [vp, C.POINTER(vp), i, i, i, i, i, f, f, i, vp, vp, sz, vp]
     L.ub200_mbconv_backward.argtypes = [vp, C.POINTER(vp), vp, C.POINTER(vp), i, i, i, i, i, i, vp, vp, sz, vp]
     L.ub200_adam_step.argtypes = [vp, vp, vp, vp, sz, i, f, f, f, f, f, f, i, vp]
+    L.ub200_img_metrics.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp]
+    L.ub200_assemble_input.argtypes = [vp, vp, i, i, i, i, i, vp]
     L.ub200_head_forward.argtypes = [vp, vp, vp, vp, i, i, i, f, i, f, vp]
     L.ub200_head_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, i, f, vp]
     _lib = L

@@ -179,7 +179,7 @@ class _UncrtaintsFunction(torch.autograd.Function):
         if ws_bytes == 0:
             raise NotImplementedError(
                 f"unsupported configuration for the B200 path: B={desc.B} T={desc.T} C_in={desc.C_in} H={desc.H} W={desc.W} "
-                "(need H, W multiples of 32, T <= 8, C_in <= 16)")
+                "(need H, W multiples of 32, T <= 64, C_in <= 16)")
         # The workspace lives from this forward to its backward only (at B=32, T=5 it is 102 GB: two would not fit in 180 GB).
         # ``net.keep_workspace = True`` (tests / debugging: ub200_workspace_tap) additionally keeps the last one on the module.
         net._last_workspace = None

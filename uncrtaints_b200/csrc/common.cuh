@@ -15,8 +15,10 @@
 #define UB_SE 32          // SE bottleneck int(128*0.25) (uncrtaints.py:83-87,134)
 #define UB_HEADS 16       // n_head (uncrtaints.py:242)
 #define UB_LOW 32         // att_down (uncrtaints.py:403)
-#define UB_TMAX 8         // max sequence length handled by the L-TAE kernels
+#define UB_TMAX 8         // sequence lengths with register-resident (templated) L-TAE / aggregation kernels
+#define UB_TLONG 64       // longest sequence (run-time loop kernels; the dataset yields up to 30, data/dataLoader.py:200)
 #define UB_S2 13          // S2_BANDS (uncrtaints.py:13)
+#define UB_MET_ACC 16     // doubles per sample in the image-metrics accumulator (metrics.cu)
 
 #define UB_OK 0
 #define UB_ERR_ARG -1

@@ -97,10 +97,13 @@ __device__ __forceinline__ void reduce_sq(float4 ssum, float4 qsum, double* stat
 // K2:  h2 = DW3x3_reflect(gelu(h1 * scale1 + shift1)),  stats2 += column (sum, sumsq) of h2
 // grid (W/16, H/R, N), 256 threads, 2 CTAs / SM (92 KB ring each)
 // ------------------------------------------------------------------------------------------------------------------
-template <bool F2, bool PG>
+// POOL (eval-mode BatchNorm blocks: the Norm2 coefficients come from running statistics and are known before this kernel runs):
+// instead of the (sum, sumsq) of h2 the epilogue accumulates sum_p gelu(h2 * scale2 + shift2), i.e. the squeeze-excite pooling --
+// the separate se_pool pass over h2 disappears.  `stats2` then points at the pooling accumulator [N][256][2].
+template <bool F2, bool PG, bool POOL>
 __global__ void __launch_bounds__(256, 2)
 dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, const float* __restrict__ wdw,
-                  float* __restrict__ h2, double* stats2, int H, int W, int R) {
+                  float* __restrict__ h2, double* stats2, const Coef* __restrict__ coef2, int H, int W, int R) {
     extern __shared__ __align__(128) float smem[];
     float* sD = smem;
     const uint32_t barD = s32(sD + ND * ROWF);
@@ -121,6 +124,13 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
         sh = make_float4(b_[0], b_[1], b_[2], b_[3]);
 #pragma unroll
         for (int j = 0; j < 9; ++j) wr[j] = make_float4(w_[j][0], w_[j][1], w_[j][2], w_[j][3]);
+    }
+    float4 sc2 = make_float4(0, 0, 0, 0), sh2 = make_float4(0, 0, 0, 0);
+    if constexpr (POOL) {
+        const Coef k0 = coef2[(size_t)n * RC + q * 4 + 0], k1 = coef2[(size_t)n * RC + q * 4 + 1],
+                   k2 = coef2[(size_t)n * RC + q * 4 + 2], k3 = coef2[(size_t)n * RC + q * 4 + 3];
+        sc2 = make_float4(k0.scale, k1.scale, k2.scale, k3.scale);
+        sh2 = make_float4(k0.shift, k1.shift, k2.shift, k3.shift);
     }
     if (tid == 0) {
         for (int i = 0; i < ND; ++i) mbar_init(barD + i * 8, 1);
@@ -184,8 +194,14 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 st4(op + j * RC, o[j]);
-                ssum.x += o[j].x; ssum.y += o[j].y; ssum.z += o[j].z; ssum.w += o[j].w;
-                fma4<F2>(qsum, o[j], o[j]);
+                if constexpr (POOL) {
+                    const float4 g = gelu4_packed(make_float4(fmaf(o[j].x, sc2.x, sh2.x), fmaf(o[j].y, sc2.y, sh2.y),
+                                                              fmaf(o[j].z, sc2.z, sh2.z), fmaf(o[j].w, sc2.w, sh2.w)));
+                    ssum.x += g.x; ssum.y += g.y; ssum.z += g.z; ssum.w += g.w;
+                } else {
+                    ssum.x += o[j].x; ssum.y += o[j].y; ssum.z += o[j].z; ssum.w += o[j].w;
+                    fma4<F2>(qsum, o[j], o[j]);
+                }
             }
         }
     }
@@ -435,9 +451,20 @@ int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, floa
                       cudaStream_t st) {
     const int R = rows_per_cta(H, W, N);
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
-    UB_SET_SMEM((dwrows_fwd_kernel<true, true>), FWD_SMEM);
+    UB_SET_SMEM((dwrows_fwd_kernel<true, true, false>), FWD_SMEM);
     const dim3 grid(W / RW, H / R, N);
-    dwrows_fwd_kernel<true, true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, H, W, R);
+    dwrows_fwd_kernel<true, true, false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, nullptr, H, W, R);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+// eval-mode BatchNorm block: depthwise conv + squeeze-excite pooling in one pass (pool[n][c][0] += sum_p gelu(norm2(h2)))
+int launch_dwconv_fwd_pool(const float* h1, const Coef* coef1, const float* wdw, float* h2, const Coef* coef2, double* pool, int N,
+                           int H, int W, cudaStream_t st) {
+    const int R = rows_per_cta(H, W, N);
+    if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
+    UB_SET_SMEM((dwrows_fwd_kernel<true, true, true>), FWD_SMEM);
+    const dim3 grid(W / RW, H / R, N);
+    dwrows_fwd_kernel<true, true, true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, pool, coef2, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }

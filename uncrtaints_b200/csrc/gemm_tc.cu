@@ -253,6 +253,25 @@ struct TEpiStoreStats {        // raw output + (sum, sumsq)
     }
     __device__ double* dst(int n, int NOUT) const { return stats + (size_t)n * NOUT * NS; }
 };
+struct TEpiResidual {          // out = x + acc*scale3 + shift3 (+ column sums of out): eval-mode BatchNorm blocks, Norm3 known up front
+    static constexpr int NS = 2;
+    static constexpr int PARTS = 1;
+    float* out; const float* x; const Coef* coef3; double* stats;
+    struct State { Coef k; };
+    __device__ void init(int n, int NOUT, int ch, State& st) const { st.k = coef3[(size_t)n * NOUT + ch]; }
+    template <int NPX>
+    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float* v, float* s) const {
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const size_t o = (row0 + i) * NOUT + ch;
+            const float r = x[o] + fmaf(v[i], st.k.scale, st.k.shift);
+            out[o] = r;
+            s[0] += r;
+            s[1] = fmaf(r, r, s[1]);
+        }
+    }
+    __device__ double* dst(int n, int NOUT) const { return stats + (size_t)n * NOUT * NS; }
+};
 struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
     static constexpr int NS = 3;
     static constexpr int PARTS = 1;      // these epilogues also READ a tensor per element: splitting measured neutral to +4 %
@@ -1024,6 +1043,13 @@ int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const vo
                  int single, cudaStream_t st) {
     tc::TLoadGeluGate al{h2, coef2, gate};
     tc::TEpiStoreStats ep{y, stats3};
+    return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, single, st);
+}
+// eval-mode BatchNorm block: out = x + Norm3(W2 . u) in the GEMM epilogue (no y tensor, no residual pass); stats = column sums of out
+int tc_gemm2_fwd_residual(const float* h2, const Coef* coef2, const float* gate, const void* w2img, const float* x, const Coef* coef3,
+                          float* out, double* stats, int N, int P, int single, cudaStream_t st) {
+    tc::TLoadGeluGate al{h2, coef2, gate};
+    tc::TEpiResidual ep{out, x, coef3, stats};
     return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, single, st);
 }
 int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,

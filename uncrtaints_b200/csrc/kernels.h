@@ -56,6 +56,8 @@ int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* 
 int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
               int max_parts, float* dw1, int N, int P, int single, cudaStream_t st);
 
+int tc_gemm2_fwd_residual(const float* h2, const Coef* coef2, const float* gate, const void* w2img, const float* x, const Coef* coef3,
+                          float* out, double* stats, int N, int P, int single, cudaStream_t st);
 // fused input-gradient + weight-gradient GEMMs (gemm_backend bit 3): one read of the shared operand tensors
 int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
@@ -67,6 +69,8 @@ int tc_gemm1_bwd_fused(const float* dz1, const float* h1, const BCoef* bc1, cons
 // dwconv_rows.cu (row-streaming depthwise kernels fed by TMA bulk copies; the backward one is fused: du, h2, h1 -> dz1 in one pass)
 int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
                       cudaStream_t st);
+int launch_dwconv_fwd_pool(const float* h1, const Coef* coef1, const float* wdw, float* h2, const Coef* coef2, double* pool, int N,
+                           int H, int W, cudaStream_t st);
 int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
                       const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
                       float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
@@ -124,8 +128,14 @@ int launch_gnll_none(const float* pred, long long pred_sb, const float* target, 
 int launch_scale_by_scalar(const float* in, const float* g, float* out, size_t n, cudaStream_t st);
 int launch_covariance(const float* var, long long var_sb, int var_ch, float* cov, int B, int P, float eps, cudaStream_t st);
 
+// metrics.cu
+int launch_img_metrics(const float* target, const float* pred, const float* var, double* acc, float* pix, int B, int H, int W,
+                       cudaStream_t st);
+
 // optim.cu
 int launch_adam_step(float* p, float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                      float weight_decay, float inv_bc1, float inv_sqrt_bc2, float grad_scale, int zero_grad, cudaStream_t st);
+
+int launch_assemble_input(const float* const* src, float* x, int B, int T, int c1, int c2, int P, cudaStream_t st);
 
 }  // namespace ub

@@ -104,11 +104,14 @@ static void block_bwd_stats(Bump& b, BlockWs& w, int N) {
     w.bstats3 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
     w.sums3 = b.take((size_t)N * UB_HID * 3 * sizeof(double));
 }
-static void block_rest(Bump& b, BlockWs& w, int N, size_t P) {
-    w.h1 = b.take((size_t)N * P * UB_HID * sizeof(float));
-    w.h2 = b.take((size_t)N * P * UB_HID * sizeof(float));
-    w.y = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
-    w.out = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
+// acts == false: the caller assigns h1 / h2 / y / out itself (forward-only layout: blocks share them, see make_layout)
+static void block_rest(Bump& b, BlockWs& w, int N, size_t P, bool acts = true) {
+    if (acts) {
+        w.h1 = b.take((size_t)N * P * UB_HID * sizeof(float));
+        w.h2 = b.take((size_t)N * P * UB_HID * sizeof(float));
+        w.y = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
+        w.out = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
+    }
     w.coef0 = b.take((size_t)N * UB_WIDTH * sizeof(Coef));
     w.coef1 = b.take((size_t)N * UB_HID * sizeof(Coef));
     w.coef2 = b.take((size_t)N * UB_HID * sizeof(Coef));
@@ -133,7 +136,7 @@ static void block_rest(Bump& b, BlockWs& w, int N, size_t P) {
 }
 
 static int make_layout(const ub200_desc* d, Layout& L) {
-    if (!d || d->B < 1 || d->T < 1 || d->T > UB_TMAX || d->C_in < 1 || d->C_in > 16) return UB_ERR_ARG;
+    if (!d || d->B < 1 || d->T < 1 || d->T > UB_TLONG || d->C_in < 1 || d->C_in > 16) return UB_ERR_ARG;
     if (d->H < UB_LOW || d->W < UB_LOW || d->H % UB_LOW || d->W % UB_LOW) return UB_ERR_ARG;
     if (d->n_dec_blocks < 1 || d->n_dec_blocks > 16) return UB_ERR_ARG;
     if (d->out_dim < UB_S2 || d->out_dim > 26) return UB_ERR_ARG;
@@ -160,7 +163,22 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     L.pool_idx = b.take((size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * sizeof(int));
     L.attn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
     L.agg = b.take((size_t)L.B * P * UB_WIDTH * sizeof(float));
-    for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P);
+    if (d->need_grad) {
+        for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P);
+    } else {
+        // forward only (validation / inference): nothing is saved for a backward, so all blocks share one set of hidden
+        // buffers (kernels run in stream order) and the decoder outputs ping-pong between two buffers: 1 x (2 Hh + A) + 3 A
+        // instead of 6 x (2 Hh + 2 A) -- at B=32, T=5 about 40 GB instead of 107 GB.
+        const size_t h1 = b.take((size_t)L.Ne * P * UB_HID * sizeof(float)), h2 = b.take((size_t)L.Ne * P * UB_HID * sizeof(float));
+        const size_t y = b.take((size_t)L.Ne * P * UB_WIDTH * sizeof(float));
+        const size_t out0 = b.take((size_t)L.Ne * P * UB_WIDTH * sizeof(float));
+        const size_t pp[2] = {b.take((size_t)L.B * P * UB_WIDTH * sizeof(float)), b.take((size_t)L.B * P * UB_WIDTH * sizeof(float))};
+        for (int i = 0; i < L.nblk; ++i) {
+            L.blk[i].h1 = h1; L.blk[i].h2 = h2; L.blk[i].y = y;
+            L.blk[i].out = i == 0 ? out0 : pp[i & 1];
+            block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, false);
+        }
+    }
     if (d->need_grad) {
         L.gA = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
         L.gB = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
@@ -249,6 +267,33 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
                               at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats3, UB200_B_N3_W, w.coef3, w.mr3, UB_WIDTH));
     UB_PROF(KID_RESIDUAL_FWD, c.st, launch_residual_fwd(x, at<float>(ws, w.y), at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats, c.N, P, c.st));
+    return UB_OK;
+}
+
+// Eval-mode specialisation of a BatchNorm block without a backward (validation / test_reconstruct.py:104-109): all four
+// normalisations use running statistics, so every coefficient is known before the first kernel runs and two of the five passes
+// disappear -- the squeeze-excite pooling rides in the depthwise kernel's epilogue and the residual add in the project GEMM's:
+//   K1 gemm1 (A + Hh)   K2' dwconv + pool (2 Hh)   se_fwd   K4' gemm2 + Norm3 + residual (Hh + 2 A)      = 3 A + 4 Hh per frame
+// instead of 5 A + 5 Hh.  (GroupNorm blocks normalise with instance statistics in eval mode too and keep the general path.)
+static int mbconv_forward_eval_bn(const BlockCtx& c, const float* x, double* next_stats) {
+    const BlockWs& w = *c.w;
+    const int P = c.H * c.W;
+    void* ws = c.ws;
+    const int single = (c.backend & 4) ? 1 : 2;
+    UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, single == 2, c.st));
+    UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2img), UB_WIDTH, UB_HID, 0, single == 2, c.st));
+    UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
+    UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
+    UB_TRY(finalize(c, w.stats2, UB200_B_N2_W, w.coef2, w.mr2, UB_HID));
+    UB_TRY(finalize(c, w.stats3, UB200_B_N3_W, w.coef3, w.mr3, UB_WIDTH));
+    UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, single, c.st));
+    UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd_pool(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
+                             at<Coef>(ws, w.coef2), at<double>(ws, w.pool), c.N, c.H, c.W, c.st));
+    UB_TRY(launch_se_fwd(at<double>(ws, w.pool), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2), at<float>(ws, w.se_save),
+                         at<float>(ws, w.gate), c.N, P, c.st));
+    // the column sums of `out` go to the next block's PreNorm accumulator (unused by an eval-mode BatchNorm, harmless) or stats3
+    UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd_residual(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img), x,
+                          at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats ? next_stats : at<double>(ws, w.stats3), c.N, P, single, c.st));
     return UB_OK;
 }
 
@@ -434,6 +479,9 @@ int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, s
     if (sscanf(name, "blk%d.%15s", &bi, what) == 2 && bi >= 0 && bi < L.nblk) {
         const size_t N = bi == 0 ? L.Ne : L.B;
         const BlockWs& w = L.blk[bi];
+        // forward-only layout: hidden buffers are shared by all blocks and decoder outputs ping-pong; only the encoder output and
+        // the last two decoder outputs still hold what their name says after the call
+        if (!d->need_grad && (strcmp(what, "out") != 0 || (bi > 0 && bi < L.nblk - 2))) return UB_ERR_ARG;
         if (!strcmp(what, "h1")) { *offset = w.h1; *bytes = N * P * UB_HID * 4; return UB_OK; }
         if (!strcmp(what, "h2")) { *offset = w.h2; *bytes = N * P * UB_HID * 4; return UB_OK; }
         if (!strcmp(what, "y")) { *offset = w.y; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
@@ -494,7 +542,11 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
     const float* x = at<float>(ws, L.agg);
     for (int i = 1; i < L.nblk; ++i) {
         BlockCtx c = make_ctx(d, L, i, params, nullptr, ws, st);
-        UB_TRY(mbconv_forward(c, x, i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr, d->need_grad != 0));
+        double* next_stats = i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr;
+        if (!d->training && !d->need_grad && d->dec_groups == 0 && (d->gemm_backend & 1))
+            UB_TRY(mbconv_forward_eval_bn(c, x, next_stats));
+        else
+            UB_TRY(mbconv_forward(c, x, next_stats, d->need_grad != 0));
         x = at<float>(ws, L.blk[i].out);
     }
     UB_PROF(KID_HEAD, st, launch_head_fwd(x, pf(params, UB200_P_OUT_W), pf(params, UB200_P_OUT_B), output, d->B, d->out_dim, P, d->scale_by,
@@ -605,6 +657,19 @@ int ub200_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     return launch_adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1),
                             (float)(1.0 / sqrt(bc2)), grad_scale, zero_grad, static_cast<cudaStream_t>(stream));
+}
+
+// ---- device-side batch assembly (prepare_data_multi, train_reconstruct.py:161-179) ----
+int ub200_assemble_input(const void* const* src_table, float* x, int B, int T, int c_s1, int c_s2, int P, void* stream) {
+    if (!src_table || !x) return UB_ERR_ARG;
+    return launch_assemble_input(reinterpret_cast<const float* const*>(src_table), x, B, T, c_s1, c_s2, P, static_cast<cudaStream_t>(stream));
+}
+
+// ---- image metrics of the validation loop (metrics.py:20-57, pytorch_ssim) for a whole batch ----
+int ub200_img_metrics(const float* target, const float* pred, const float* var, int B, int H, int W, double* acc, float* pixelwise,
+                      void* stream) {
+    if (!target || !pred || !acc || B < 1 || H < 1 || W < 1) return UB_ERR_ARG;
+    return launch_img_metrics(target, pred, var, acc, pixelwise, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
 // ---- standalone out_conv + head (tests, calibration sweep) ----

@@ -39,3 +39,33 @@ int launch_adam_step(float* p, float* g, float* m, float* v, size_t n, float lr,
 }
 
 }  // namespace ub
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device-side batch assembly: prepare_data_multi (model/train_reconstruct.py:161-179) builds the network input
+// with torch.stack over the T per-time-point S1 tensors, torch.stack over the S2 tensors and torch.cat of the two stacks --
+// three read+write passes over the batch.  One kernel writes x[b][t][c] straight from the 2T source tensors (pointer table in
+// device memory): one read, one write.  src[t] -> S1[t] ([B][c1][P]) or null, src[T + t] -> S2[t] ([B][c2][P]).
+// ------------------------------------------------------------------------------------------------------------------
+namespace ub {
+
+__global__ void __launch_bounds__(256) assemble_input_kernel(const float* const* __restrict__ src, float* __restrict__ x, int T, int c1,
+                                                              int c2, int P4 /* H*W/4 */) {
+    const int C = c1 + c2;
+    const int plane = blockIdx.y;                       // (b*T + t)*C + c
+    const int c = plane % C, t = (plane / C) % T, b = plane / (C * T);
+    const float4* s = c < c1 ? reinterpret_cast<const float4*>(src[t]) + ((size_t)b * c1 + c) * P4
+                             : reinterpret_cast<const float4*>(src[T + t]) + ((size_t)b * c2 + (c - c1)) * P4;
+    float4* d = reinterpret_cast<float4*>(x) + (size_t)plane * P4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+int launch_assemble_input(const float* const* src, float* x, int B, int T, int c1, int c2, int P, cudaStream_t st) {
+    if (P % 4 != 0 || B < 1 || T < 1 || c2 < 1 || c1 < 0) return UB_ERR_ARG;
+    const int P4 = P / 4;
+    const int bx = (P4 + 255) / 256 < 8 ? (P4 + 255) / 256 : 8;
+    assemble_input_kernel<<<dim3(bx, B * T * (c1 + c2)), 256, 0, st>>>(src, x, T, c1, c2, P4);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+}  // namespace ub

@@ -395,6 +395,284 @@ __global__ void __launch_bounds__(256) aggregate_bwd_kernel(AggArgs a, const flo
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Long sequences (T > UB_TMAX, up to UB_TLONG): the dataset yields up to 30 time points (data/dataLoader.py:200).  Same
+// arithmetic with run-time loops over t instead of register arrays: the pooled features are re-read from the L1/L2 (they are
+// B*T*1024*128 floats in total), scores / score gradients pass through shared memory.  These tensors are low resolution or
+// touched once, so the simple form costs little; the T <= 8 templates above stay the fast path of the benchmark configurations.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ltae_stats_long(const float* __restrict__ pooled, int b, int q, int lane, int T, float eps,
+                                                float& mean, float& rstd) {
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) {
+        const float4 v = ld4(pooled + (((size_t)(b * T + t)) * UB_LOW * UB_LOW + q) * UB_WIDTH + lane * 4);
+        sum += v.x + v.y + v.z + v.w;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    mean = sum / (8.f * T);
+    float var = 0.f;
+    for (int t = 0; t < T; ++t) {
+        const float4 v = ld4(pooled + (((size_t)(b * T + t)) * UB_LOW * UB_LOW + q) * UB_WIDTH + lane * 4);
+        const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+        var = fmaf(a, a, var); var = fmaf(bb, bb, var); var = fmaf(c, c, var); var = fmaf(d, d, var);
+    }
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    rstd = 1.0f / sqrtf(var / (8.f * T) + eps);
+}
+__device__ __forceinline__ float4 ltae_xhat(const float* __restrict__ pooled, int b, int t, int q, int lane, int T, float mean, float rstd) {
+    const float4 v = ld4(pooled + (((size_t)(b * T + t)) * UB_LOW * UB_LOW + q) * UB_WIDTH + lane * 4);
+    return make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+}
+
+__global__ void __launch_bounds__(256) ltae_fwd_long_kernel(const float* __restrict__ pooled, const float* __restrict__ Ap,
+                                                             const float* __restrict__ e, const int* __restrict__ notpad,
+                                                             float* __restrict__ attn, int B, int T, float eps) {
+    __shared__ __align__(16) float sAp[UB_HEADS * UB_WIDTH];
+    __shared__ float ssc[8][UB_TLONG][UB_HEADS];
+    for (int i = threadIdx.x; i < UB_HEADS * UB_WIDTH; i += 256) sAp[i] = Ap[i];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int pix = blockIdx.x * 8 + warp;
+    if (pix >= B * UB_LOW * UB_LOW) return;
+    const int b = pix / (UB_LOW * UB_LOW), q = pix % (UB_LOW * UB_LOW);
+    float mean, rstd;
+    ltae_stats_long(pooled, b, q, lane, T, eps, mean, rstd);
+    for (int t = 0; t < T; ++t) {
+        const float4 xh = ltae_xhat(pooled, b, t, q, lane, T, mean, rstd);
+#pragma unroll 4
+        for (int h = 0; h < UB_HEADS; ++h) {
+            const float4 a = ld4(sAp + h * UB_WIDTH + lane * 4);
+            const float part = warp_sum(a.x * xh.x + a.y * xh.y + a.z * xh.z + a.w * xh.w);
+            if (lane == h) ssc[warp][t][h] = part;
+        }
+    }
+    __syncwarp();
+    if (lane < UB_HEADS) {
+        float mx = -INFINITY;
+        for (int t = 0; t < T; ++t) {
+            float sc = 0.5f * (ssc[warp][t][lane] + e[((size_t)b * T + t) * UB_HEADS + lane]);
+            if (!notpad[b * T + t]) sc = -1000.0f;
+            ssc[warp][t][lane] = sc;
+            mx = fmaxf(mx, sc);
+        }
+        float den = 0.f;
+        for (int t = 0; t < T; ++t) { const float ex = expf(ssc[warp][t][lane] - mx); ssc[warp][t][lane] = ex; den += ex; }
+        const float inv = 1.0f / den;
+        for (int t = 0; t < T; ++t) attn[(((size_t)lane * B + b) * T + t) * (UB_LOW * UB_LOW) + q] = ssc[warp][t][lane] * inv;
+    }
+}
+
+__global__ void __launch_bounds__(256) ltae_bwd_long_kernel(const float* __restrict__ pooled, const float* __restrict__ Ap,
+                                                             const float* __restrict__ attn, const float* __restrict__ dattn,
+                                                             float* __restrict__ dpooled, float* dAp, float* de, int B, int T, float eps,
+                                                             int pix_per_warp) {
+    __shared__ __align__(16) float sAp[UB_HEADS * UB_WIDTH];
+    __shared__ float sds[8][UB_TLONG][UB_HEADS];
+    for (int i = threadIdx.x; i < UB_HEADS * UB_WIDTH; i += 256) sAp[i] = Ap[i];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int npix = B * UB_LOW * UB_LOW;
+    float4 gA[UB_HEADS];
+#pragma unroll
+    for (int h = 0; h < UB_HEADS; ++h) gA[h] = make_float4(0, 0, 0, 0);
+    const int first = (blockIdx.x * 8 + warp) * pix_per_warp;
+    for (int pix = first; pix < first + pix_per_warp && pix < npix; ++pix) {
+        const int b = pix / (UB_LOW * UB_LOW), q = pix % (UB_LOW * UB_LOW);
+        float mean, rstd;
+        ltae_stats_long(pooled, b, q, lane, T, eps, mean, rstd);
+        __syncwarp();
+        if (lane < UB_HEADS) {          // softmax backward per head
+            float dot = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const size_t o = (((size_t)lane * B + b) * T + t) * (UB_LOW * UB_LOW) + q;
+                dot = fmaf(attn[o], dattn[o], dot);
+            }
+            for (int t = 0; t < T; ++t) {
+                const size_t o = (((size_t)lane * B + b) * T + t) * (UB_LOW * UB_LOW) + q;
+                const float ds = 0.5f * attn[o] * (dattn[o] - dot);
+                sds[warp][t][lane] = ds;
+                atomicAdd(&de[((size_t)b * T + t) * UB_HEADS + lane], ds);
+            }
+        }
+        __syncwarp();
+        // pass A: GroupNorm-backward means and the dAp accumulation; pass B: the input gradient
+        float m1 = 0.f, m2 = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float4 xh = ltae_xhat(pooled, b, t, q, lane, T, mean, rstd);
+            float4 dx = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int h = 0; h < UB_HEADS; ++h) {
+                const float4 a = ld4(sAp + h * UB_WIDTH + lane * 4);
+                const float d = sds[warp][t][h];
+                gA[h].x = fmaf(d, xh.x, gA[h].x); gA[h].y = fmaf(d, xh.y, gA[h].y);
+                gA[h].z = fmaf(d, xh.z, gA[h].z); gA[h].w = fmaf(d, xh.w, gA[h].w);
+                dx.x = fmaf(a.x, d, dx.x); dx.y = fmaf(a.y, d, dx.y); dx.z = fmaf(a.z, d, dx.z); dx.w = fmaf(a.w, d, dx.w);
+            }
+            m1 += dx.x + dx.y + dx.z + dx.w;
+            m2 += dx.x * xh.x + dx.y * xh.y + dx.z * xh.z + dx.w * xh.w;
+        }
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+        m1 /= 8.f * T; m2 /= 8.f * T;
+        for (int t = 0; t < T; ++t) {
+            const float4 xh = ltae_xhat(pooled, b, t, q, lane, T, mean, rstd);
+            float4 dx = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int h = 0; h < UB_HEADS; ++h) {
+                const float4 a = ld4(sAp + h * UB_WIDTH + lane * 4);
+                const float d = sds[warp][t][h];
+                dx.x = fmaf(a.x, d, dx.x); dx.y = fmaf(a.y, d, dx.y); dx.z = fmaf(a.z, d, dx.z); dx.w = fmaf(a.w, d, dx.w);
+            }
+            st4(dpooled + (((size_t)(b * T + t)) * UB_LOW * UB_LOW + q) * UB_WIDTH + lane * 4,
+                make_float4(rstd * (dx.x - m1 - xh.x * m2), rstd * (dx.y - m1 - xh.y * m2), rstd * (dx.z - m1 - xh.z * m2),
+                            rstd * (dx.w - m1 - xh.w * m2)));
+        }
+        __syncwarp();
+    }
+    __shared__ __align__(16) float red[8 * UB_WIDTH];
+#pragma unroll 1
+    for (int h = 0; h < UB_HEADS; ++h) {
+        float4 v = gA[0];
+#pragma unroll
+        for (int j = 1; j < UB_HEADS; ++j) if (j == h) v = gA[j];
+        __syncthreads();
+        st4(red + warp * UB_WIDTH + lane * 4, v);
+        __syncthreads();
+        if (threadIdx.x < UB_WIDTH) {
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += red[r * UB_WIDTH + threadIdx.x];
+            atomicAdd(&dAp[h * UB_WIDTH + threadIdx.x], t);
+        }
+    }
+}
+
+// keep / (1 - p) of head h for frame t at the 4 pixels of group (y, x0) (same Philox stream / explicit mask as agg_dropout)
+__device__ __forceinline__ void agg_dropout_long(const AggArgs& a, int h, int b, int t, int y, int x0, float (&k)[4]) {
+    if (!(a.drop_p > 0.f)) { k[0] = k[1] = k[2] = k[3] = 1.f; return; }
+    const float inv_keep = 1.f / (1.f - a.drop_p);
+    const size_t lin = ((((size_t)h * a.B + b) * a.T + t) * a.H + y) * a.W + x0;
+    if (a.keep_mask) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) k[i] = a.keep_mask[lin + i] ? inv_keep : 0.f;
+        return;
+    }
+    const unsigned long long blk = (lin >> 2) + a.offset;
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u), make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+    const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = (((float)(bits[i] >> 8) * (1.0f / 16777216.0f)) >= a.drop_p) ? inv_keep : 0.f;
+}
+// stage the vertically interpolated attention row: sv[h * stride + t * 32 + X], stride = T * 32 + 1 (dynamic shared memory)
+__device__ __forceinline__ void agg_stage_row_long(const AggArgs& a, int b, int y, float* sv, int stride) {
+    const int T = a.T;
+    const float inv_sy = (float)UB_LOW / (float)a.H;
+    int y0, y1; float ly;
+    bilinear_tap(y, inv_sy, UB_LOW, y0, y1, ly);
+    for (int i = threadIdx.x; i < UB_HEADS * T * UB_LOW; i += blockDim.x) {
+        const int h = i / (T * UB_LOW), r = i % (T * UB_LOW), t = r / UB_LOW, X = r % UB_LOW;
+        const float* src = a.attn + (((size_t)h * a.B + b) * T + t) * (UB_LOW * UB_LOW);
+        const float vv = src[y0 * UB_LOW + X] * (1.f - ly) + src[y1 * UB_LOW + X] * ly;
+        sv[h * stride + r] = a.notpad[b * T + t] ? vv : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) aggregate_fwd_long_kernel(AggArgs a, const float* __restrict__ x, float* __restrict__ out,
+                                                                  double* out_stats) {
+    constexpr int C = UB_WIDTH;
+    extern __shared__ float sv[];
+    __shared__ __align__(16) float smem[2 * 8 * C];
+    const int T = a.T, stride = T * UB_LOW + 1;
+    const int y = blockIdx.x, b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
+    const int P = a.H * a.W;
+    agg_stage_row_long(a, b, y, sv, stride);
+    __syncthreads();
+    const float inv_sx = (float)UB_LOW / (float)a.W;
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    for (int x0 = warp * 4; x0 < a.W; x0 += 32) {
+        const int p = y * a.W + x0;
+        int xa[4], xb[4]; float lx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bilinear_tap(x0 + i, inv_sx, UB_LOW, xa[i], xb[i], lx[i]);
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0, 0, 0, 0);
+        for (int t = 0; t < T; ++t) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ld4_stream(x + (((size_t)(b * T + t)) * P + p + i) * C + lane * 4);
+            float k[4];
+            agg_dropout_long(a, h, b, t, y, x0, k);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float w = (sv[h * stride + t * UB_LOW + xa[i]] * (1.f - lx[i]) + sv[h * stride + t * UB_LOW + xb[i]] * lx[i]) * k[i];
+                acc[i].x = fmaf(w, v[i].x, acc[i].x); acc[i].y = fmaf(w, v[i].y, acc[i].y);
+                acc[i].z = fmaf(w, v[i].z, acc[i].z); acc[i].w = fmaf(w, v[i].w, acc[i].w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            st4(out + ((size_t)b * P + p + i) * C + lane * 4, acc[i]);
+            s.x += acc[i].x; s.y += acc[i].y; s.z += acc[i].z; s.w += acc[i].w;
+            q.x += acc[i].x * acc[i].x; q.y += acc[i].y * acc[i].y; q.z += acc[i].z * acc[i].z; q.w += acc[i].w * acc[i].w;
+        }
+    }
+    float4* sa = reinterpret_cast<float4*>(smem);
+    sa[warp * 32 + lane] = s;
+    sa[256 + warp * 32 + lane] = q;
+    __syncthreads();
+    {
+        const int which = threadIdx.x / C, ch = threadIdx.x % C;
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += (double)smem[which * 8 * C + r * C + ch];
+        atomicAdd(&out_stats[((size_t)b * C + ch) * 2 + which], t);
+    }
+}
+
+__global__ void __launch_bounds__(256) aggregate_bwd_long_kernel(AggArgs a, const float* __restrict__ x, const float* __restrict__ dagg,
+                                                                  float* __restrict__ denc, float* __restrict__ dwup) {
+    constexpr int C = UB_WIDTH;
+    extern __shared__ float sv[];
+    const int T = a.T, stride = T * UB_LOW + 1;
+    const int y = blockIdx.x, b = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32, h = lane / 2;
+    const int P = a.H * a.W;
+    agg_stage_row_long(a, b, y, sv, stride);
+    __syncthreads();
+    const float inv_sx = (float)UB_LOW / (float)a.W;
+    for (int x0 = warp * 4; x0 < a.W; x0 += 32) {
+        const int p = y * a.W + x0;
+        float4 d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = ld4_stream(dagg + ((size_t)b * P + p + i) * C + lane * 4);
+        int xa[4], xb[4]; float lx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bilinear_tap(x0 + i, inv_sx, UB_LOW, xa[i], xb[i], lx[i]);
+        for (int t = 0; t < T; ++t) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ld4_stream(x + (((size_t)(b * T + t)) * P + p + i) * C + lane * 4);
+            float k[4];
+            agg_dropout_long(a, h, b, t, y, x0, k);
+            const size_t fr = ((size_t)(b * T + t)) * P + p;
+            const float np = a.notpad[b * T + t] ? 1.f : 0.f;
+            float dots[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float w = (sv[h * stride + t * UB_LOW + xa[i]] * (1.f - lx[i]) + sv[h * stride + t * UB_LOW + xb[i]] * lx[i]) * k[i];
+                st4(denc + (fr + i) * C + lane * 4, make_float4(w * d[i].x, w * d[i].y, w * d[i].z, w * d[i].w));
+                float dot = d[i].x * v[i].x + d[i].y * v[i].y + d[i].z * v[i].z + d[i].w * v[i].w;
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                dots[i] = dot * k[i] * np;
+            }
+            if ((lane & 1) == 0) {
+                const size_t lin = ((((size_t)h * a.B + b) * T + t) * a.H + y) * a.W + x0;
+                st4(dwup + lin, make_float4(dots[0], dots[1], dots[2], dots[3]));
+            }
+        }
+    }
+}
+
 // backward B: adjoint of the bilinear upsampling, gather form (deterministic, no atomics):
 // dattn[h,b,t,Y,X] = sum over the footprint of cell (Y,X) of tapweight * dwup[h,b,t,y,x]
 __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __restrict__ dwup, float* __restrict__ dattn,
@@ -457,6 +735,11 @@ int launch_maxpool_bwd(const float* dpooled, const int* idx, float* denc, int N,
 int launch_ltae_fwd(const float* pooled, const float* Ap, const float* e, const int* notpad, float* attn, int B, int T,
                     float eps, cudaStream_t st) {
     const int npix = B * UB_LOW * UB_LOW;
+    if (T > UB_TMAX && T <= UB_TLONG) {
+        ltae_fwd_long_kernel<<<(npix + 7) / 8, 256, 0, st>>>(pooled, Ap, e, notpad, attn, B, T, eps);
+        UB_CHECK_LAUNCH();
+        return UB_OK;
+    }
     UB_DISPATCH_T(T, (ltae_fwd_kernel<TT><<<(npix + 7) / 8, 256, 0, st>>>(pooled, Ap, e, notpad, attn, B, eps)));
     UB_CHECK_LAUNCH();
     return UB_OK;
@@ -466,6 +749,11 @@ int launch_ltae_bwd(const float* pooled, const float* Ap, const float* attn, con
     const int npix = B * UB_LOW * UB_LOW;
     const int ppw = 8;
     const int blocks = (npix + 8 * ppw - 1) / (8 * ppw);
+    if (T > UB_TMAX && T <= UB_TLONG) {
+        ltae_bwd_long_kernel<<<blocks, 256, 0, st>>>(pooled, Ap, attn, dattn, dpooled, dAp, de, B, T, eps, ppw);
+        UB_CHECK_LAUNCH();
+        return UB_OK;
+    }
     UB_DISPATCH_T(T, (ltae_bwd_kernel<TT><<<blocks, 256, 0, st>>>(pooled, Ap, attn, dattn, dpooled, dAp, de, B, eps, ppw)));
     UB_CHECK_LAUNCH();
     return UB_OK;
@@ -483,6 +771,13 @@ int launch_aggregate_fwd(const float* attn, const int* notpad, const unsigned ch
                          int T, int H, int W, cudaStream_t st) {
     if (W % 32) return UB_ERR_ARG;
     const AggArgs a = make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W);
+    if (T > UB_TMAX && T <= UB_TLONG) {
+        const size_t smem = (size_t)UB_HEADS * (T * UB_LOW + 1) * sizeof(float);
+        UB_SET_SMEM(aggregate_fwd_long_kernel, (size_t)UB_HEADS * (UB_TLONG * UB_LOW + 1) * sizeof(float));
+        aggregate_fwd_long_kernel<<<dim3(H, B), 256, smem, st>>>(a, x, out, out_stats);
+        UB_CHECK_LAUNCH();
+        return UB_OK;
+    }
     UB_DISPATCH_T(T, (aggregate_fwd_kernel<TT><<<dim3(H, B), 256, 0, st>>>(a, x, out, out_stats)));
     UB_CHECK_LAUNCH();
     return UB_OK;
@@ -492,8 +787,15 @@ int launch_aggregate_bwd(const float* attn, const int* notpad, const unsigned ch
                          float* dwup, float* dattn, int B, int T, int H, int W, cudaStream_t st) {
     if (W % 32) return UB_ERR_ARG;
     const AggArgs a = make_agg(attn, notpad, keep_mask, seed, offset, drop_p, B, T, H, W);
-    UB_DISPATCH_T(T, (aggregate_bwd_kernel<TT><<<dim3(H, B), 256, 0, st>>>(a, x, dagg, denc, dwup)));
-    UB_CHECK_LAUNCH();
+    if (T > UB_TMAX && T <= UB_TLONG) {
+        const size_t smem = (size_t)UB_HEADS * (T * UB_LOW + 1) * sizeof(float);
+        UB_SET_SMEM(aggregate_bwd_long_kernel, (size_t)UB_HEADS * (UB_TLONG * UB_LOW + 1) * sizeof(float));
+        aggregate_bwd_long_kernel<<<dim3(H, B), 256, smem, st>>>(a, x, dagg, denc, dwup);
+        UB_CHECK_LAUNCH();
+    } else {
+        UB_DISPATCH_T(T, (aggregate_bwd_kernel<TT><<<dim3(H, B), 256, 0, st>>>(a, x, dagg, denc, dwup)));
+        UB_CHECK_LAUNCH();
+    }
     const int cells = UB_HEADS * B * T * UB_LOW * UB_LOW;
     upsample_adjoint_kernel<<<(cells + 255) / 256, 256, 0, st>>>(dwup, dattn, H, W, cells);
     UB_CHECK_LAUNCH();
