@@ -183,8 +183,8 @@ def test_gpu_img_metrics_vs_oracle(B, H, W):
         err = (t[b] - p[b])
         assert np.allclose(got[b]["pixelwise error"], err.nanmean(0).nanmean(0).flatten().numpy(), atol=1e-6)
         assert np.allclose(got[b]["pixelwise var"], v[b].nanmean(0).nanmean(0).flatten().numpy(), atol=1e-7)
-    one = ub.img_metrics(t[1].cuda(), p[1].cuda(), v[1].cuda(), pixelwise=False)        # the reference's per-sample signature
-    assert abs(one["SSIM"] - got[1]["SSIM"]) < 1e-12 and "pixelwise error" not in one
+    one = ub.img_metrics(t[B - 1].cuda(), p[B - 1].cuda(), v[B - 1].cuda(), pixelwise=False)   # the reference's per-sample signature
+    assert abs(one["SSIM"] - got[B - 1]["SSIM"]) < 1e-12 and "pixelwise error" not in one
 
 
 def test_eval_fast_path_and_forward_only_workspace(golden_weights):

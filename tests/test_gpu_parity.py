@@ -295,7 +295,7 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
     (2, 5, 64, 96, "diag", True, True, 27),
     (1, 2, 256, 256, "diag", True, False, 27),
     (1, 12, 64, 64, "diag", True, True, 11),      # T > 8: run-time-T temporal kernels (the dataset yields up to 30 time points)
-    (2, 9, 32, 64, "iso", False, False, 11),
+    (2, 9, 64, 64, "iso", False, False, 11),
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub

@@ -899,29 +899,46 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         if (tid == 0) {
             tc_fence_after();
             const uint32_t r_hi = smem_u32(sR), r_lo = r_hi + 2 * FBLK, b_hi = smem_u32(s_hi), b_lo = smem_u32(s_lo);
+            // weight gradient: D[128 (channels of R)][blk*64 .. +64 (channels of S)] += R^T . S_blk  (contraction over the 64 pixels)
+            auto wgrad_mma = [&](int p16) {
+                const uint32_t d = tmem_base + DW_COL + blk * 64;
+                const uint64_t ah = make_wg_desc(r_hi + p16 * 2048), al = make_wg_desc(r_lo + p16 * 2048);
+                const uint64_t bh = make_wg_desc(b_hi + p16 * 2048), bl = make_wg_desc(b_lo + p16 * 2048);
+                tc_mma(d, ah, bh, F_IDESC_MN, (it | p16) != 0);
+                if (!single) {
+                    tc_mma(d, ah, bl, F_IDESC_MN, 1);
+                    tc_mma(d, al, bh, F_IDESC_MN, 1);
+                }
+            };
             if constexpr (CONV == 1) {
-                // dn0[128][px] += W1^T[:, blk] . dh1_blk
+                // dn0[128][px] += W1^T[:, blk] . dh1_blk, interleaved with the weight-gradient MMAs: the two accumulation chains are
+                // independent, and an N=64 MMA is shorter than the accumulate latency of its predecessor on the same accumulator
                 const uint32_t a_hi = smem_u32(sW) + blk * (NOUT * 128), a_lo = a_hi + W_HALF;
-                const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC;
+                const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC, dw = tmem_base + DW_COL + blk * 64;
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16) {
                     const uint64_t wa = make_desc(a_hi + k16 * 32), wl = make_desc(a_lo + k16 * 32);
                     const uint64_t xa = make_desc(b_hi + k16 * 32), xl = make_desc(b_lo + k16 * 32);
+                    const uint64_t ah = make_wg_desc(r_hi + k16 * 2048), al = make_wg_desc(r_lo + k16 * 2048);
+                    const uint64_t bh = make_wg_desc(b_hi + k16 * 2048), bl = make_wg_desc(b_lo + k16 * 2048);
                     tc_mma(d, wa, xa, F_IDESC_K, (blk | k16) != 0);
+                    tc_mma(dw, ah, bh, F_IDESC_MN, (it | k16) != 0);
                     if (!single) {
                         tc_mma(d, wa, xl, F_IDESC_K, 1);
+                        tc_mma(dw, ah, bl, F_IDESC_MN, 1);
                         tc_mma(d, wl, xa, F_IDESC_K, 1);
+                        tc_mma(dw, al, bh, F_IDESC_MN, 1);
                     }
                 }
             } else {
                 if (blk == 0) {                               // du[256][px] = W2^T . dy   (both K-blocks of R, two M-blocks)
 #pragma unroll
-                    for (int j = 0; j < MH; ++j) {
-                        const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC + j * FPX;
+                    for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                        for (int kb = 0; kb < 2; ++kb)
+                        for (int k16 = 0; k16 < 4; ++k16)
 #pragma unroll
-                            for (int k16 = 0; k16 < 4; ++k16) {
+                            for (int j = 0; j < MH; ++j) {   // the two M-blocks alternate: independent accumulators
+                                const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC + j * FPX;
                                 const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128) + j * (128 * 128) + k16 * 32;
                                 const uint64_t wa = make_desc(a_hi), wl = make_desc(a_hi + W_HALF);
                                 const uint64_t xa = make_desc(r_hi + kb * FBLK + k16 * 32), xl = make_desc(r_lo + kb * FBLK + k16 * 32);
@@ -931,23 +948,10 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                                     tc_mma(d, wl, xa, F_IDESC_K, 1);
                                 }
                             }
-                    }
                     tc_commit(bAcc + (it & 1) * 8);
                 }
-            }
-            // weight gradient: D[128 (channels of R)][blk*64 .. +64 (channels of S)] += R^T . S_blk  (contraction over the 64 pixels)
-            {
-                const uint32_t d = tmem_base + DW_COL + blk * 64;
 #pragma unroll
-                for (int p16 = 0; p16 < FPX / 16; ++p16) {
-                    const uint64_t ah = make_wg_desc(r_hi + p16 * 2048), al = make_wg_desc(r_lo + p16 * 2048);
-                    const uint64_t bh = make_wg_desc(b_hi + p16 * 2048), bl = make_wg_desc(b_lo + p16 * 2048);
-                    tc_mma(d, ah, bh, F_IDESC_MN, (it | p16) != 0);
-                    if (!single) {
-                        tc_mma(d, ah, bl, F_IDESC_MN, 1);
-                        tc_mma(d, al, bh, F_IDESC_MN, 1);
-                    }
-                }
+                for (int p16 = 0; p16 < FPX / 16; ++p16) wgrad_mma(p16);
             }
             tc_commit(bRing + slot * 8);                                   // frees the ring slot
             if (blk == 3) {
