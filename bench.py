@@ -432,7 +432,9 @@ def main():
                         "byte model of the whole step / ms_per_step / peak"}
     line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": nwarm, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MMA / f32 storage" if ((args.backend or 0) & 4) else "f32",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("bf16" if ((args.backend or 0) & 36) == 36 else "bf16 MMA / f32 storage" if ((args.backend or 0) & 4) else
+                      "f32 with bf16 hidden storage" if ((args.backend or 0) & 32) else "f32"),
             "data": "synthetic", "config": config,
             "gemm_backend": int(args.backend if args.backend is not None else ub.backbone._default_backend()),
             "clocks": clocks, "gpu_launches": int(launches),

@@ -85,7 +85,9 @@ typedef struct ub200_desc {
     int mean_sigmoid;           /* out_nonlin_mean (uncrtaints.py:384) */
     int gemm_backend;           /* bit 0: tcgen05 forward (fp16 hi/lo x3) / input-gradient (bf16 hi/lo x3) GEMMs; bit 1: tcgen05 weight-gradient GEMMs;
                                    bit 2: single-pass bf16 in those (reduced precision); bits 3 / 4: input- and weight-gradient GEMM of the expand /
-                                   project convolution fused into one kernel (need bits 0 and 1); default 11; 0 = fp32 CUDA cores (test comparator) */
+                                   project convolution fused into one kernel (need bits 0 and 1); bit 5: the 256-channel hidden tensors h1, h2, du, dz1
+                                   are stored as bf16 (needs bits 0 and 1, excludes bit 4; BASELINE config #3 = 47); default 11;
+                                   0 = fp32 CUDA cores (test comparator) */
     float scale_by;             /* uncrtaints.py:250,384 */
     float var_eps;              /* 1e-9 if scale_by == 1 else 1e-3 (uncrtaints.py:374) */
     float pad_value;            /* uncrtaints.py:245,392 */

@@ -221,6 +221,14 @@ def test_mbconv_block_single_pass_bf16(golden_weights, groups, training):
     _mbconv_block_vs_oracle(golden_weights, groups, training, 7, True, (2, 64, 64), ",bf16x1", tol=5e-2)
 
 
+@pytest.mark.parametrize("backend", [43, 47])
+@pytest.mark.parametrize("groups,training,shape", [(4, 1, (2, 64, 64)), (0, 1, (3, 32, 48)), (0, 0, (1, 96, 16))])
+def test_mbconv_block_bf16_hidden_storage(golden_weights, groups, training, shape, backend):
+    """gemm_backend bit 5 (BASELINE config #3): h1, h2, du, dz1 stored as bf16 -- 43 with the three-MMA operand split, 47 with
+    single-pass bf16 MMAs on top.  Reduced precision by design (2^-9 per stored element): tolerance 5e-2, errors are reported."""
+    _mbconv_block_vs_oracle(golden_weights, groups, training, backend, True, shape, ",bf16-hidden", tol=5e-2)
+
+
 def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, shape=(3, 16, 32), extra_tag="", tol=None):
     from uncrtaints_b200 import _lib
     L = _lib.lib()
@@ -493,8 +501,10 @@ def test_mgnll_deferred_negative_check():
         crit.check()
 
 
-def test_model_single_pass_bf16_backend(golden_weights):
-    """Whole model at the BASELINE config #3 sequence length (T=5) through the single-pass bf16 tensor-core backend (7):
+@pytest.mark.parametrize("backend", [7, 43, 47])
+def test_model_single_pass_bf16_backend(golden_weights, backend):
+    """Whole model at the BASELINE config #3 sequence length (T=5) through the reduced-precision backends: 7 = single-pass bf16
+    MMAs on fp32 storage, 43 = bf16 storage of the hidden tensors with three-MMA operands, 47 = both (the config #3 path):
     outputs / loss within 5e-2 of the fp64 oracle (reduced precision by design), errors reported."""
     import uncrtaints_b200 as ub
     B, T, H, W = 1, 5, 64, 64
@@ -503,7 +513,7 @@ def test_model_single_pass_bf16_backend(golden_weights):
     cfg = O.OracleConfig()
     p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in golden_weights.items()}
     o_out, o_loss, o_grads, _ = O.step(p64, x.double(), y.double(), d.double(), cfg, True, keep)
-    net = make_net(golden_weights, "diag", backend=7).train()
+    net = make_net(golden_weights, "diag", backend=backend).train()
     net._injected_keep_mask = keep.to(torch.uint8)
     out = net(x.cuda(), batch_positions=d.cuda())
     loss, _ = ub.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode="diag", chunk=None)(out[:, :, :13], y.cuda(), out[:, :, 13:26])
@@ -512,7 +522,7 @@ def test_model_single_pass_bf16_backend(golden_weights):
     e_loss = abs(loss.item() - o_loss.item()) / abs(o_loss.item())
     gerr = {k: rel_l2(p.grad, o_grads[k]) for k, p in net.named_parameters() if not is_zero_grad_param(k)}
     worst = max(gerr, key=gerr.get)
-    report("parity_report.txt", [f"bf16x1 backend: out rel_l2={e_out:.3e} loss rel={e_loss:.3e} worst grad {worst} rel_l2={gerr[worst]:.3e} "
+    report("parity_report.txt", [f"reduced-precision backend {backend}: out rel_l2={e_out:.3e} loss rel={e_loss:.3e} worst grad {worst} rel_l2={gerr[worst]:.3e} "
                                  f"median grad rel_l2={sorted(gerr.values())[len(gerr) // 2]:.3e}"])
     assert e_out <= 5e-2 and e_loss <= 5e-2
     assert sorted(gerr.values())[len(gerr) // 2] <= 5e-2

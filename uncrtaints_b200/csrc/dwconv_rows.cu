@@ -16,6 +16,7 @@
 // The backward kernel is input-stationary (D[tap] gathered per INPUT pixel, so gelu(z1), gelu'(z1)
 // are evaluated once per pixel and dW needs no second tile); the adjoint of reflect padding is a rare warp-uniform
 // correction.  HBM traffic: forward 2 Hh, backward 4 Hh (du, h2, h1 in, dz1 out) -- the split dh2 + stencil pair moved 6.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -71,6 +72,34 @@ __device__ __forceinline__ void fma4(float4& acc, const float4 a, const float4 b
         acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);
     }
 }
+// hidden-tensor storage type HT: float, or __nv_bfloat16 (gemm_backend bit 5).  Vector loads / stores of 4 and 2 elements.
+typedef __nv_bfloat16 bf16_t;
+__device__ __forceinline__ float4 ldh4(const float* p) { return ld4(p); }
+__device__ __forceinline__ float4 ldh4(const bf16_t* p) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ void sth4(float* p, float4 v) { st4(p, v); }
+__device__ __forceinline__ void sth4(bf16_t* p, float4 v) {
+    uint2 w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v.w), "f"(v.z));
+    *reinterpret_cast<uint2*>(p) = w;
+}
+__device__ __forceinline__ float2 ldh2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ldh2(const bf16_t* p) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ void sth2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void sth2(bf16_t* p, float2 v) {
+    uint32_t w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(v.y), "f"(v.x));
+    *reinterpret_cast<uint32_t*>(p) = w;
+}
+template <class T> struct is_f32 { static constexpr bool value = false; };
+template <> struct is_f32<float> { static constexpr bool value = true; };
+
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
 // reduce the per-thread (s, q) column sums over the 4 column groups of each channel quad -> stats[n][ch][0..1] (fp64)
@@ -100,13 +129,18 @@ __device__ __forceinline__ void reduce_sq(float4 ssum, float4 qsum, double* stat
 // POOL (eval-mode BatchNorm blocks: the Norm2 coefficients come from running statistics and are known before this kernel runs):
 // instead of the (sum, sumsq) of h2 the epilogue accumulates sum_p gelu(h2 * scale2 + shift2), i.e. the squeeze-excite pooling --
 // the separate se_pool pass over h2 disappears.  `stats2` then points at the pooling accumulator [N][256][2].
-template <bool F2, bool PG, bool POOL>
+// HT = bf16: the h1 halo rows arrive in a 2-slot bf16 staging area (the bulk copy cannot convert) and the Norm1 + GELU transform
+// writes them as fp32 into the ring instead of working in place; h2 is written as bf16 (statistics from the fp32 values).
+template <bool F2, bool PG, bool POOL, class HT>
 __global__ void __launch_bounds__(256, 2)
-dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, const float* __restrict__ wdw,
-                  float* __restrict__ h2, double* stats2, const Coef* __restrict__ coef2, int H, int W, int R) {
+dwrows_fwd_kernel(const HT* __restrict__ h1, const Coef* __restrict__ coef1, const float* __restrict__ wdw,
+                  HT* __restrict__ h2, double* stats2, const Coef* __restrict__ coef2, int H, int W, int R) {
+    constexpr bool F32 = is_f32<HT>::value;
+    constexpr int NSLOT = F32 ? ND : 2;                     // slots the bulk copies land in (ring itself / staging)
     extern __shared__ __align__(128) float smem[];
     float* sD = smem;
-    const uint32_t barD = s32(sD + ND * ROWF);
+    HT* sIn = F32 ? reinterpret_cast<HT*>(sD) : reinterpret_cast<HT*>(sD + ND * ROWF);
+    const uint32_t barD = F32 ? s32(sD + ND * ROWF) : s32(reinterpret_cast<char*>(sD + ND * ROWF) + 2 * ROWF * sizeof(HT));
     const int tid = threadIdx.x, q = tid & (RQ - 1), s = tid >> 6;
     const int n = blockIdx.z, x0 = blockIdx.x * RW, ybase = blockIdx.y * R;
     const size_t fbase = (size_t)n * H * W * RC;
@@ -133,36 +167,37 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
         sh2 = make_float4(k0.shift, k1.shift, k2.shift, k3.shift);
     }
     if (tid == 0) {
-        for (int i = 0; i < ND; ++i) mbar_init(barD + i * 8, 1);
+        for (int i = 0; i < NSLOT; ++i) mbar_init(barD + i * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int xs = max(x0 - 1, 0), xe = min(x0 + RW + 1, W);
-    const uint32_t rowbytes = (uint32_t)(xe - xs) * RC * 4;
+    const uint32_t rowbytes = (uint32_t)(xe - xs) * RC * sizeof(HT);
     const int dstoff = (xs - (x0 - 1)) * RC;
     const int NIT = R + 2;
-    auto issue = [&](int i) {       // thread 0: halo row i (image row reflect(ybase-1+i)) -> ring slot i % ND
+    auto issue = [&](int i) {       // thread 0: halo row i (image row reflect(ybase-1+i)) -> slot i % NSLOT
         const int y = reflect1(ybase - 1 + i, H);
-        const uint32_t b = barD + (i % ND) * 8;
-        float* dst = sD + (i % ND) * ROWF;
-        const float* src = h1 + fbase + (size_t)y * W * RC;
-        mbar_expect_tx(b, ROWF * 4);
+        const uint32_t b = barD + (i % NSLOT) * 8;
+        HT* dst = sIn + (i % NSLOT) * ROWF;
+        const HT* src = h1 + fbase + (size_t)y * W * RC;
+        mbar_expect_tx(b, ROWF * sizeof(HT));
         bulk_g2s(s32(dst + dstoff), src + (size_t)xs * RC, rowbytes, b);
-        if (x0 == 0) bulk_g2s(s32(dst), src + (size_t)1 * RC, RC * 4, b);                                  // x = -1 -> 1
-        if (x0 + RW == W) bulk_g2s(s32(dst + (RWH - 1) * RC), src + (size_t)(W - 2) * RC, RC * 4, b);      // x = W -> W-2
+        if (x0 == 0) bulk_g2s(s32(dst), src + (size_t)1 * RC, RC * sizeof(HT), b);                                  // x = -1 -> 1
+        if (x0 + RW == W) bulk_g2s(s32(dst + (RWH - 1) * RC), src + (size_t)(W - 2) * RC, RC * sizeof(HT), b);      // x = W -> W-2
     };
     if (tid == 0) { issue(0); issue(1); }
     float4 ssum = make_float4(0, 0, 0, 0), qsum = make_float4(0, 0, 0, 0);
     for (int i = 0; i < NIT; ++i) {
         float* d = sD + (i % ND) * ROWF;
-        mbar_wait(barD + (i % ND) * 8, (uint32_t)(i / ND) & 1u);
-        // in-place Norm1 + GELU of the halo row: pixel px = s + 4k, channel quad q
+        const HT* din = sIn + (i % NSLOT) * ROWF;
+        mbar_wait(barD + (i % NSLOT) * 8, (uint32_t)(i / NSLOT) & 1u);
+        // Norm1 + GELU of the halo row (in place for fp32 storage): pixel px = s + 4k, channel quad q
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             const int px = s + 4 * k;
             if (px < RWH) {
                 float* ptr = d + px * RC + q * 4;
-                const float4 v = ld4(ptr);
+                const float4 v = ldh4(din + px * RC + q * 4);
                 const float4 z = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
                 float4 g;
                 if constexpr (PG) g = gelu4_packed(z);
@@ -190,10 +225,10 @@ dwrows_fwd_kernel(const float* __restrict__ h1, const Coef* __restrict__ coef1, 
 #pragma unroll
                     for (int jj = 0; jj < 3; ++jj) fma4<F2>(o[j], wr[r * 3 + jj], win[j + jj]);
             }
-            float* op = h2 + fbase + ((size_t)yc * W + x0 + 4 * s) * RC + q * 4;
+            HT* op = h2 + fbase + ((size_t)yc * W + x0 + 4 * s) * RC + q * 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                st4(op + j * RC, o[j]);
+                sth4(op + j * RC, o[j]);
                 if constexpr (POOL) {
                     const float4 g = gelu4_packed(make_float4(fmaf(o[j].x, sc2.x, sh2.x), fmaf(o[j].y, sc2.y, sh2.y),
                                                               fmaf(o[j].z, sc2.z, sh2.z), fmaf(o[j].w, sc2.w, sh2.w)));
@@ -229,17 +264,23 @@ __device__ __forceinline__ void fma2v(float2& acc, const float2 a, const float2 
     unpack2(fma2(pack2(a.x, a.y), pack2(b.x, b.y), pack2(acc.x, acc.y)), acc.x, acc.y);
 }
 
-template <bool PG>
+// HT = bf16: du arrives in a 2-slot bf16 staging area and is written into the ring as fp32 dh2; the h2 / h1 staging rings hold bf16
+// (half the bytes); dz1 is written as bf16 (statistics from the fp32 values).
+template <bool PG, class HT>
 __global__ void __launch_bounds__(512, 1)
-dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, const float* __restrict__ h1,
+dwrows_bwd2_kernel(const HT* __restrict__ du, const HT* __restrict__ h2, const HT* __restrict__ h1,
                    const float* __restrict__ gate, const float* __restrict__ dmp, const Coef* __restrict__ coef2,
                    const BCoef* __restrict__ bc2, const Coef* __restrict__ coef1, const MeanRstd* __restrict__ mr1,
-                   const float* __restrict__ wdw, float* __restrict__ dz1, double* bstats1, float* dwdw, int H, int W, int R) {
+                   const float* __restrict__ wdw, HT* __restrict__ dz1, double* bstats1, float* dwdw, int H, int W, int R) {
+    constexpr bool F32 = is_f32<HT>::value;
+    constexpr int NDU = F32 ? ND : 2;                       // slots the du bulk copies land in (ring itself / staging)
     extern __shared__ __align__(128) float smem[];
-    float* sD = smem;
-    float* sH2 = sD + ND * ROWF;
-    float* sH1 = sH2 + NH2 * ROWF;
-    float4* sK2 = reinterpret_cast<float4*>(sH1 + NH1 * ROWC);   // [2][128] scale2, shift2, gate, dpool/P   (channel 2p+c at [c][p])
+    float* sD = smem;                                                    // dh2 ring (fp32), ND halo rows
+    HT* sH2 = reinterpret_cast<HT*>(sD + ND * ROWF);                     // h2 staging, NH2 halo rows
+    HT* sH1 = sH2 + NH2 * ROWF;                                          // h1 staging, NH1 centre rows
+    HT* sDu = F32 ? reinterpret_cast<HT*>(sD) : sH1 + NH1 * ROWC;        // du landing area
+    float4* sK2 = reinterpret_cast<float4*>(F32 ? reinterpret_cast<char*>(sH1 + NH1 * ROWC) : reinterpret_cast<char*>(sDu + 2 * ROWF));
+                                                                         // [2][128] scale2, shift2, gate, dpool/P   (channel 2p+c at [c][p])
     float4* sB2 = sK2 + RC;                                        // [2][128] a2, b2, c2, -
     const uint32_t barD = s32(sB2 + RC), barH2 = barD + ND * 8, barH1 = barH2 + NH2 * 8;
     const int tid = threadIdx.x, p = tid & (RP - 1), s = tid >> 7;
@@ -269,16 +310,16 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
     }
     __syncthreads();
     const int xs = max(x0 - 1, 0), xe = min(x0 + RW + 1, W);
-    const uint32_t rowbytes = (uint32_t)(xe - xs) * RC * 4;
+    const uint32_t rowbytes = (uint32_t)(xe - xs) * RC * sizeof(HT);
     const int dstoff = (xs - (x0 - 1)) * RC;
     const int NIT = R + 2;
     auto issue_dh = [&](int i) {
         const int y = ybase - 1 + i;
-        const uint32_t bd = barD + (i % ND) * 8, bh = barH2 + (i % NH2) * 8;
+        const uint32_t bd = barD + (i % NDU) * 8, bh = barH2 + (i % NH2) * 8;
         if (y >= 0 && y < H) {
             const size_t g = fbase + ((size_t)y * W + xs) * RC;
             mbar_expect_tx(bd, rowbytes);
-            bulk_g2s(s32(sD + (i % ND) * ROWF + dstoff), du + g, rowbytes, bd);
+            bulk_g2s(s32(sDu + (i % NDU) * ROWF + dstoff), du + g, rowbytes, bd);
             mbar_expect_tx(bh, rowbytes);
             bulk_g2s(s32(sH2 + (i % NH2) * ROWF + dstoff), h2 + g, rowbytes, bh);
         } else {
@@ -288,8 +329,8 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
     };
     auto issue_h1 = [&](int c) {
         const uint32_t b = barH1 + (c % NH1) * 8;
-        mbar_expect_tx(b, ROWC * 4);
-        bulk_g2s(s32(sH1 + (c % NH1) * ROWC), h1 + fbase + ((size_t)(ybase + c) * W + x0) * RC, ROWC * 4, b);
+        mbar_expect_tx(b, ROWC * sizeof(HT));
+        bulk_g2s(s32(sH1 + (c % NH1) * ROWC), h1 + fbase + ((size_t)(ybase + c) * W + x0) * RC, ROWC * sizeof(HT), b);
     };
     if (tid == 0) { issue_dh(0); issue_dh(1); }
     float2 gw[9];
@@ -305,8 +346,9 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
             const int y = ybase - 1 + i;
             const bool row_in = (y >= 0 && y < H);
             float* d = sD + (i % ND) * ROWF;
-            const float* hh = sH2 + (i % NH2) * ROWF;
-            mbar_wait(barD + (i % ND) * 8, (uint32_t)(i / ND) & 1u);
+            const HT* dsrc = sDu + (i % NDU) * ROWF;
+            const HT* hh = sH2 + (i % NH2) * ROWF;
+            mbar_wait(barD + (i % NDU) * 8, (uint32_t)(i / NDU) & 1u);
             mbar_wait(barH2 + (i % NH2) * 8, (uint32_t)(i / NH2) & 1u);
             const float4 k0 = sK2[p], k1 = sK2[RP + p];
             const float4 b0 = sB2[p], b1 = sB2[RP + p];
@@ -317,8 +359,8 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
                     const int x = x0 - 1 + px;
                     float2 o = make_float2(0, 0);
                     if (row_in && x >= 0 && x < W) {
-                        const float2 dv = ld2(d + px * RC + p * 2);
-                        const float2 hv = ld2(hh + px * RC + p * 2);
+                        const float2 dv = ldh2(dsrc + px * RC + p * 2);
+                        const float2 hv = ldh2(hh + px * RC + p * 2);
                         const float z0 = fmaf(hv.x, k0.x, k0.y), z1 = fmaf(hv.y, k1.x, k1.y);
                         float gp0, gp1;
                         if constexpr (PG) { float u0, u1; gelu_pair<false, true>(z0, z1, u0, u1, gp0, gp1); }
@@ -343,11 +385,11 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
         const float* rp1 = sD + ((i - 1) % ND) * ROWF + woff;
         const float* rp2 = sD + (i % ND) * ROWF + woff;
         mbar_wait(barH1 + (c % NH1) * 8, (uint32_t)(c / NH1) & 1u);
-        const float* hp = sH1 + (c % NH1) * ROWC + woff;
+        const HT* hp = sH1 + (c % NH1) * ROWC + woff;
         float2 g[4], gp[4], o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float2 hv = ld2(hp + j * RC);
+            const float2 hv = ldh2(hp + j * RC);
             const float z0 = fmaf(hv.x, sc1.x, sh1.x), z1 = fmaf(hv.y, sc1.y, sh1.y);
             if constexpr (PG) gelu_pair<true, true>(z0, z1, g[j].x, g[j].y, gp[j].x, gp[j].y);
             else { gelu_both(z0, g[j].x, gp[j].x); gelu_both(z1, g[j].y, gp[j].y); }
@@ -394,12 +436,12 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
                 }
             }
         }
-        float* op = dz1 + fbase + ((size_t)yc * W + xbase) * RC + p * 2;
+        HT* op = dz1 + fbase + ((size_t)yc * W + xbase) * RC + p * 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 dz = make_float2(o[j].x * gp[j].x, o[j].y * gp[j].y);
-            st2(op + j * RC, dz);
-            const float2 hv = ld2(hp + j * RC);
+            sth2(op + j * RC, dz);
+            const float2 hv = ldh2(hp + j * RC);
             ssum.x += dz.x; ssum.y += dz.y;
             qsum.x = fmaf(dz.x, (hv.x - mu1.x) * rs1.x, qsum.x);
             qsum.y = fmaf(dz.y, (hv.y - mu1.y) * rs1.y, qsum.y);
@@ -435,8 +477,13 @@ dwrows_bwd2_kernel(const float* __restrict__ du, const float* __restrict__ h2, c
     }
 }
 
-constexpr size_t FWD_SMEM = (size_t)ND * ROWF * 4 + ND * 8;
-constexpr size_t BWD_SMEM = (size_t)(ND + NH2) * ROWF * 4 + (size_t)NH1 * ROWC * 4 + 2 * RC * 16 + (ND + NH2 + NH1) * 8;
+template <class HT> constexpr size_t fwd_smem() {
+    return is_f32<HT>::value ? (size_t)ND * ROWF * 4 + ND * 8 : (size_t)ND * ROWF * 4 + 2 * ROWF * sizeof(HT) + 2 * 8;
+}
+template <class HT> constexpr size_t bwd_smem() {
+    return (size_t)ND * ROWF * 4 + (size_t)NH2 * ROWF * sizeof(HT) + (size_t)NH1 * ROWC * sizeof(HT) + (is_f32<HT>::value ? 0 : 2 * ROWF * sizeof(HT)) +
+           2 * RC * 16 + (ND + NH2 + NH1) * 8;
+}
 
 // rows per CTA: 64 when the grid still fills the GPU several times over (halo rows and the per-CTA prologue / reduction
 // epilogue are amortised over more rows), else 32 / 16 / 8
@@ -447,38 +494,50 @@ int rows_per_cta(int H, int W, int N) {
 
 }  // namespace
 
-int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
-                      cudaStream_t st) {
+template <bool POOL, class HT>
+static int launch_fwd_t(const void* h1, const Coef* coef1, const float* wdw, void* h2, double* stats, const Coef* coef2, int N, int H, int W,
+                        cudaStream_t st) {
     const int R = rows_per_cta(H, W, N);
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
-    UB_SET_SMEM((dwrows_fwd_kernel<true, true, false>), FWD_SMEM);
+    constexpr size_t smem = fwd_smem<HT>();
+    UB_SET_SMEM((dwrows_fwd_kernel<true, true, POOL, HT>), smem);
     const dim3 grid(W / RW, H / R, N);
-    dwrows_fwd_kernel<true, true, false><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, stats2, nullptr, H, W, R);
+    dwrows_fwd_kernel<true, true, POOL, HT><<<grid, 256, smem, st>>>(static_cast<const HT*>(h1), coef1, wdw, static_cast<HT*>(h2), stats, coef2, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
+}
+// hbf != 0: h1 / h2 (and du / dz1 in the backward) are bf16 tensors
+int launch_dwconv_fwd(const void* h1, const Coef* coef1, const float* wdw, void* h2, double* stats2, int N, int H, int W, int hbf,
+                      cudaStream_t st) {
+    return hbf ? launch_fwd_t<false, bf16_t>(h1, coef1, wdw, h2, stats2, nullptr, N, H, W, st)
+               : launch_fwd_t<false, float>(h1, coef1, wdw, h2, stats2, nullptr, N, H, W, st);
 }
 // eval-mode BatchNorm block: depthwise conv + squeeze-excite pooling in one pass (pool[n][c][0] += sum_p gelu(norm2(h2)))
-int launch_dwconv_fwd_pool(const float* h1, const Coef* coef1, const float* wdw, float* h2, const Coef* coef2, double* pool, int N,
-                           int H, int W, cudaStream_t st) {
+int launch_dwconv_fwd_pool(const void* h1, const Coef* coef1, const float* wdw, void* h2, const Coef* coef2, double* pool, int N,
+                           int H, int W, int hbf, cudaStream_t st) {
+    return hbf ? launch_fwd_t<true, bf16_t>(h1, coef1, wdw, h2, pool, coef2, N, H, W, st)
+               : launch_fwd_t<true, float>(h1, coef1, wdw, h2, pool, coef2, N, H, W, st);
+}
+
+template <class HT>
+static int launch_bwd_t(const void* du, const void* h2, const void* h1, const float* gate, const float* dmp, const Coef* coef2,
+                        const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, void* dz1, double* bstats1,
+                        float* dwdw, int N, int H, int W, cudaStream_t st) {
     const int R = rows_per_cta(H, W, N);
     if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
-    UB_SET_SMEM((dwrows_fwd_kernel<true, true, true>), FWD_SMEM);
+    constexpr size_t smem = bwd_smem<HT>();
+    UB_SET_SMEM((dwrows_bwd2_kernel<true, HT>), smem);
     const dim3 grid(W / RW, H / R, N);
-    dwrows_fwd_kernel<true, true, true><<<grid, 256, FWD_SMEM, st>>>(h1, coef1, wdw, h2, pool, coef2, H, W, R);
+    dwrows_bwd2_kernel<true, HT><<<grid, 512, smem, st>>>(static_cast<const HT*>(du), static_cast<const HT*>(h2), static_cast<const HT*>(h1), gate, dmp,
+                                                         coef2, bc2, coef1, mr1, wdw, static_cast<HT*>(dz1), bstats1, dwdw, H, W, R);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-
-int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp, const Coef* coef2,
-                      const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, float* dz1, double* bstats1,
-                      float* dwdw, int N, int H, int W, cudaStream_t st) {
-    const int R = rows_per_cta(H, W, N);
-    if (W % RW != 0 || R == 0 || H < 4 || W < 4) return UB_ERR_ARG;
-    UB_SET_SMEM(dwrows_bwd2_kernel<true>, BWD_SMEM);
-    const dim3 grid(W / RW, H / R, N);
-    dwrows_bwd2_kernel<true><<<grid, 512, BWD_SMEM, st>>>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, H, W, R);
-    UB_CHECK_LAUNCH();
-    return UB_OK;
+int launch_dwconv_bwd(const void* du, const void* h2, const void* h1, const float* gate, const float* dmp, const Coef* coef2,
+                      const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw, void* dz1, double* bstats1,
+                      float* dwdw, int N, int H, int W, int hbf, cudaStream_t st) {
+    return hbf ? launch_bwd_t<bf16_t>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, N, H, W, st)
+               : launch_bwd_t<float>(du, h2, h1, gate, dmp, coef2, bc2, coef1, mr1, wdw, dz1, bstats1, dwdw, N, H, W, st);
 }
 
 }  // namespace ub

@@ -177,6 +177,31 @@ __device__ __forceinline__ void lds8(const float* vec, int K, int ch0, float (&v
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// Storage type of the 256-channel hidden tensors (h1, h2 and the gradients du, dz1): float, or __nv_bfloat16 with gemm_backend bit 5
+// (BASELINE config #3: "bf16 tensor-core path" -- these four tensors are 16 of the 34 tensor passes of an MBConv frame and two
+// thirds of its bytes).  Raw8 = 8 consecutive elements as loaded (32 or 16 bytes in flight per item).
+typedef __nv_bfloat16 bf16_t;
+template <class T> struct Raw8;
+template <> struct Raw8<float> { float a[8]; };
+template <> struct Raw8<bf16_t> { uint4 p; };
+__device__ __forceinline__ void ld8_raw(const float* p, Raw8<float>& r) { ld8(p, r.a); }
+__device__ __forceinline__ void ld8_raw(const bf16_t* p, Raw8<bf16_t>& r) {
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.p.x), "=r"(r.p.y), "=r"(r.p.z), "=r"(r.p.w) : "l"(p));
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = r.a[i];
+}
+__device__ __forceinline__ void unpack8(const Raw8<bf16_t>& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.p.x, r.p.y, r.p.z, r.p.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+__device__ __forceinline__ float ldh(const float* p) { return *p; }
+__device__ __forceinline__ float ldh(const bf16_t* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void sth(float* p, float v) { *p = v; }
+__device__ __forceinline__ void sth(bf16_t* p, float v) { *p = __float2bfloat16_rn(v); }
+
 struct TLoadNormed {           // a = x*scale + shift
     const float* x; const Coef* coef;
     struct Raw { float a[8]; };
@@ -191,9 +216,10 @@ struct TLoadNormed {           // a = x*scale + shift
         for (int i = 0; i < 8; ++i) v[i] = fmaf(r.a[i], c.sc[i], c.sh[i]);
     }
 };
-struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
-    const float* h2; const Coef* coef; const float* gate;
-    struct Raw { float a[8]; };
+template <class HT>
+struct TLoadGeluGateT {        // a = gelu(h2*scale + shift) * gate
+    const HT* h2; const Coef* coef; const float* gate;
+    typedef Raw8<HT> Raw;
     __device__ void fill(int n, int K, float* cf) const {
         for (int k = threadIdx.x; k < K; k += THREADS) {
             const Coef c = coef[(size_t)n * K + k];
@@ -201,58 +227,68 @@ struct TLoadGeluGate {         // a = gelu(h2*scale + shift) * gate
             cf[q] = c.scale; cf[K + q] = c.shift; cf[2 * K + q] = gate[(size_t)n * K + k];
         }
     }
-    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(h2 + row * K + ch0, r.a); }
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8_raw(h2 + row * K + ch0, r); }
     struct Cf { float sc[8], sh[8], g[8]; };
     __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const {
         lds8(cf, K, ch0, c.sc); lds8(cf + K, K, ch0, c.sh); lds8(cf + 2 * K, K, ch0, c.g);
     }
     __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
+        float a[8];
+        unpack8(r, a);
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {          // packed f32x2 single-MUFU GELU: 4 pairs
             float g0, g1;
-            gelu_val_pair(fmaf(r.a[i], c.sc[i], c.sh[i]), fmaf(r.a[i + 1], c.sc[i + 1], c.sh[i + 1]), g0, g1);
+            gelu_val_pair(fmaf(a[i], c.sc[i], c.sh[i]), fmaf(a[i + 1], c.sc[i + 1], c.sh[i + 1]), g0, g1);
             v[i] = g0 * c.g[i];
             v[i + 1] = g1 * c.g[i + 1];
         }
     }
 };
-struct TLoadNormBwd {          // a = ca*dy + cb*v + cc
-    const float* dy; const float* vv; const BCoef* bc;
-    struct Raw { float a[8], b[8]; };
+typedef TLoadGeluGateT<float> TLoadGeluGate;
+template <class T>
+struct TLoadNormBwdT {         // a = ca*dy + cb*v + cc
+    const T* dy; const T* vv; const BCoef* bc;
+    struct Raw { Raw8<T> a, b; };
     __device__ void fill(int n, int K, float* cf) const {
         for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.a; cf[K + q] = c.b; cf[2 * K + q] = c.c; }
     }
-    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(dy + row * K + ch0, r.a); ld8(vv + row * K + ch0, r.b); }
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8_raw(dy + row * K + ch0, r.a); ld8_raw(vv + row * K + ch0, r.b); }
     struct Cf { float ca[8], cb[8], cc[8]; };
     __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const {
         lds8(cf, K, ch0, c.ca); lds8(cf + K, K, ch0, c.cb); lds8(cf + 2 * K, K, ch0, c.cc);
     }
     __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
+        float a[8], b[8];
+        unpack8(r.a, a);
+        unpack8(r.b, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaf(c.ca[i], r.a[i], fmaf(c.cb[i], r.b[i], c.cc[i]));
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(c.ca[i], a[i], fmaf(c.cb[i], b[i], c.cc[i]));
     }
 };
+typedef TLoadNormBwdT<float> TLoadNormBwd;
 
 // ------------------------------------------------------------------------------------------
 // epilogues: thread = one output channel; v[32] = 32 consecutive pixels of that channel
 // ------------------------------------------------------------------------------------------
-struct TEpiStoreStats {        // raw output + (sum, sumsq)
+template <class OT>
+struct TEpiStoreStatsT {       // raw output + (sum, sumsq)
     static constexpr int NS = 2;
     static constexpr int PARTS = 2;      // split epilogue (see gemm_tc_kernel): measured -9 % (128 -> 256) and -5 % (256 -> 128)
-    float* out; double* stats;
+    OT* out; double* stats;
     struct State {};
     __device__ void init(int n, int NOUT, int ch, State&) const {}
     template <int NPX>
     __device__ void apply(const State&, size_t row0, int NOUT, int ch, const float* v, float* s) const {
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
-            out[(row0 + i) * NOUT + ch] = v[i];
+            sth(out + (row0 + i) * NOUT + ch, v[i]);
             s[0] += v[i];
             s[1] = fmaf(v[i], v[i], s[1]);
         }
     }
     __device__ double* dst(int n, int NOUT) const { return stats + (size_t)n * NOUT * NS; }
 };
+typedef TEpiStoreStatsT<float> TEpiStoreStats;
 struct TEpiResidual {          // out = x + acc*scale3 + shift3 (+ column sums of out): eval-mode BatchNorm blocks, Norm3 known up front
     static constexpr int NS = 2;
     static constexpr int PARTS = 1;
@@ -272,10 +308,11 @@ struct TEpiResidual {          // out = x + acc*scale3 + shift3 (+ column sums o
     }
     __device__ double* dst(int n, int NOUT) const { return stats + (size_t)n * NOUT * NS; }
 };
-struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
+template <class HT>
+struct TEpiGemm2BwdT {         // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
     static constexpr int NS = 3;
     static constexpr int PARTS = 1;      // these epilogues also READ a tensor per element: splitting measured neutral to +4 %
-    float* du; const float* h2; const Coef* coef2; const MeanRstd* mr2; double* sums;
+    HT* du; const HT* h2; const Coef* coef2; const MeanRstd* mr2; double* sums;
     struct State { Coef k; MeanRstd m; };
     __device__ void init(int n, int NOUT, int ch, State& st) const { st.k = coef2[(size_t)n * NOUT + ch]; st.m = mr2[(size_t)n * NOUT + ch]; }
     template <int NPX>
@@ -283,9 +320,9 @@ struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
 #pragma unroll
         for (int i = 0; i < NPX; i += 2) {        // two pixels per step: packed f32x2 GELU + derivative
             const size_t o0 = (row0 + i) * NOUT + ch, o1 = o0 + NOUT;
-            du[o0] = v[i];
-            du[o1] = v[i + 1];
-            const float h0 = h2[o0], h1v = h2[o1];
+            sth(du + o0, v[i]);
+            sth(du + o1, v[i + 1]);
+            const float h0 = ldh(h2 + o0), h1v = ldh(h2 + o1);
             float g0, g1, p0, p1;
             gelu_pair<true, true>(fmaf(h0, st.k.scale, st.k.shift), fmaf(h1v, st.k.scale, st.k.shift), g0, g1, p0, p1);
             s[0] = fmaf(v[i], g0, s[0]);
@@ -298,6 +335,7 @@ struct TEpiGemm2Bwd {          // du = acc; sums (du*g2, du*gp2, du*gp2*h2hat)
     }
     __device__ double* dst(int n, int NOUT) const { return sums + (size_t)n * NOUT * NS; }
 };
+typedef TEpiGemm2BwdT<float> TEpiGemm2Bwd;
 struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
     static constexpr int NS = 2;
     static constexpr int PARTS = 1;
@@ -1038,58 +1076,63 @@ int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose,
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, int single, cudaStream_t st) {
+// hbf != 0: the 256-channel hidden tensors (h1, h2, du, dz1) are stored as bf16 (gemm_backend bit 5)
+int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, void* h1, double* stats1, int N, int P, int single, int hbf,
+                 cudaStream_t st) {
     tc::TLoadNormed al{x, coef0};
-    tc::TEpiStoreStats ep{h1, stats1};
-    return tc::launch<UB_WIDTH, UB_HID>(al, w1img, ep, N, P, single, st);
+    if (hbf) return tc::launch<UB_WIDTH, UB_HID>(al, w1img, tc::TEpiStoreStatsT<tc::bf16_t>{static_cast<tc::bf16_t*>(h1), stats1}, N, P, single, st);
+    return tc::launch<UB_WIDTH, UB_HID>(al, w1img, tc::TEpiStoreStats{static_cast<float*>(h1), stats1}, N, P, single, st);
 }
-int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N, int P,
-                 int single, cudaStream_t st) {
-    tc::TLoadGeluGate al{h2, coef2, gate};
+int tc_gemm2_fwd(const void* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N, int P,
+                 int single, int hbf, cudaStream_t st) {
     tc::TEpiStoreStats ep{y, stats3};
-    return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, single, st);
+    if (hbf) return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadGeluGateT<tc::bf16_t>{static_cast<const tc::bf16_t*>(h2), coef2, gate}, w2img, ep, N, P, single, st);
+    return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadGeluGate{static_cast<const float*>(h2), coef2, gate}, w2img, ep, N, P, single, st);
 }
 // eval-mode BatchNorm block: out = x + Norm3(W2 . u) in the GEMM epilogue (no y tensor, no residual pass); stats = column sums of out
-int tc_gemm2_fwd_residual(const float* h2, const Coef* coef2, const float* gate, const void* w2img, const float* x, const Coef* coef3,
-                          float* out, double* stats, int N, int P, int single, cudaStream_t st) {
-    tc::TLoadGeluGate al{h2, coef2, gate};
+int tc_gemm2_fwd_residual(const void* h2, const Coef* coef2, const float* gate, const void* w2img, const float* x, const Coef* coef3,
+                          float* out, double* stats, int N, int P, int single, int hbf, cudaStream_t st) {
     tc::TEpiResidual ep{out, x, coef3, stats};
-    return tc::launch<UB_HID, UB_WIDTH>(al, w2img, ep, N, P, single, st);
+    if (hbf) return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadGeluGateT<tc::bf16_t>{static_cast<const tc::bf16_t*>(h2), coef2, gate}, w2img, ep, N, P, single, st);
+    return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadGeluGate{static_cast<const float*>(h2), coef2, gate}, w2img, ep, N, P, single, st);
 }
-int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, cudaStream_t st) {
+int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, void* du, const void* h2,
+                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, int hbf, cudaStream_t st) {
     tc::TLoadNormBwd al{dout, y, bc3};
-    tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
-    return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, ep, N, P, single, st);
+    if (hbf)
+        return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, tc::TEpiGemm2BwdT<tc::bf16_t>{static_cast<tc::bf16_t*>(du), static_cast<const tc::bf16_t*>(h2), coef2, mr2, sums3},
+                                            N, P, single, st);
+    return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, tc::TEpiGemm2Bwd{static_cast<float*>(du), static_cast<const float*>(h2), coef2, mr2, sums3}, N, P, single, st);
 }
-int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, cudaStream_t st) {
-    tc::TLoadNormBwd al{dz1, h1, bc1};
+int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, int hbf, cudaStream_t st) {
     tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
-    return tc::launch<UB_HID, UB_WIDTH>(al, w1timg, ep, N, P, single, st);
+    if (hbf)
+        return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, w1timg, ep, N, P, single, st);
+    return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, w1timg, ep, N, P, single, st);
 }
 // dW2[o][k] += sum_p dy[p][o] * u[p][k]
-int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
-              float* partial, int max_parts, float* dw2, int N, int P, int single, cudaStream_t st) {
+int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* h2, const Coef* coef2, const float* gate,
+              float* partial, int max_parts, float* dw2, int N, int P, int single, int hbf, cudaStream_t st) {
     tc::TLoadNormBwd la{dout, y, bc3};
-    tc::TLoadGeluGate lb{h2, coef2, gate};
     int nparts = 0;
-    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, UB_HID, 1, single, &nparts, st);
+    int rc = hbf ? tc::launch_wgrad_tc(la, tc::TLoadGeluGateT<tc::bf16_t>{static_cast<const tc::bf16_t*>(h2), coef2, gate}, partial, max_parts, N, P, UB_HID, 1, single, &nparts, st)
+                 : tc::launch_wgrad_tc(la, tc::TLoadGeluGate{static_cast<const float*>(h2), coef2, gate}, partial, max_parts, N, P, UB_HID, 1, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
 }
 // dW1[o][k] += sum_p dh1[p][o] * n0[p][k]   (M side = n0 (128 channels, index k), N side = dh1 (256 channels, index o))
-int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
-              int max_parts, float* dw1, int N, int P, int single, cudaStream_t st) {
+int tc_wgrad1(const float* x, const Coef* coef0, const void* dz1, const void* h1, const BCoef* bc1, float* partial,
+              int max_parts, float* dw1, int N, int P, int single, int hbf, cudaStream_t st) {
     tc::TLoadNormed la{x, coef0};
-    tc::TLoadNormBwd lb{dz1, h1, bc1};
     int nparts = 0;
-    int rc = tc::launch_wgrad_tc(la, lb, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
+    int rc = hbf ? tc::launch_wgrad_tc(la, tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st)
+                 : tc::launch_wgrad_tc(la, tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
 }
-
 // Fused backward of the project convolution: du + Norm2-backward sums (as tc_gemm2_bwd) AND dW2 += dy^T u (as tc_wgrad2) in one pass
+// (fp32 hidden storage only; measured slower than the two-kernel form, kept as an option)
 int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
                        float* dw2, int N, int P, int single, cudaStream_t st) {
@@ -1102,14 +1145,16 @@ int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, cons
     return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
 }
 // Fused backward of the expand convolution: dn0 + PreNorm-backward sums (as tc_gemm1_bwd) AND dW1 += dh1^T n0 (as tc_wgrad1)
-int tc_gemm1_bwd_fused(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+int tc_gemm1_bwd_fused(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
-                       int P, int single, cudaStream_t st) {
-    tc::TLoadNormBwd ls{dz1, h1, bc1};
+                       int P, int single, int hbf, cudaStream_t st) {
     tc::TLoadNormed lr{x, coef0};
     tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
     int nparts = 0;
-    int rc = tc::launch_bwd_fused<1>(ls, lr, w1timg, ep, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
+    int rc = hbf ? tc::launch_bwd_fused<1>(tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, lr, w1timg, ep, partial,
+                                           max_parts, N, P, 1, UB_WIDTH, single, &nparts, st)
+                 : tc::launch_bwd_fused<1>(tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, lr, w1timg, ep, partial,
+                                           max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
 }

@@ -19,8 +19,8 @@ int launch_norm_finalize_bwd(const double* bstats, const float* gamma, const Mea
                              float* dbeta, int N, int C, int groups, double count, int training, cudaStream_t st);
 int launch_residual_fwd(const float* x, const float* y, const Coef* coef3, float* out, double* out_stats, int N, int P,
                         cudaStream_t st);
-int launch_se_pool(const float* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
-                   int P, cudaStream_t st);
+int launch_se_pool(const void* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
+                   int P, int hbf, cudaStream_t st);
 int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
 int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
                         int relu_mask, cudaStream_t st);
@@ -44,36 +44,37 @@ int simt_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float
 // single: operand split mode -- 0 = bf16 hi/lo (three MMAs), 1 = one bf16 (single pass, gemm_backend bit 2, reduced precision),
 // 2 = fp16 hi/lo (three MMAs, fp32-grade; forward GEMMs only: needs a weight image prepared with f16 = 1).
 int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, int f16, cudaStream_t st);
-int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, float* h1, double* stats1, int N, int P, int single, cudaStream_t st);
-int tc_gemm2_fwd(const float* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N,
-                 int P, int single, cudaStream_t st);
-int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, cudaStream_t st);
-int tc_gemm1_bwd(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, cudaStream_t st);
-int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const float* h2, const Coef* coef2, const float* gate,
-              float* partial, int max_parts, float* dw2, int N, int P, int single, cudaStream_t st);
-int tc_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float* h1, const BCoef* bc1, float* partial,
-              int max_parts, float* dw1, int N, int P, int single, cudaStream_t st);
-
-int tc_gemm2_fwd_residual(const float* h2, const Coef* coef2, const float* gate, const void* w2img, const float* x, const Coef* coef3,
-                          float* out, double* stats, int N, int P, int single, cudaStream_t st);
-// fused input-gradient + weight-gradient GEMMs (gemm_backend bit 3): one read of the shared operand tensors
+// hbf != 0: the 256-channel hidden tensors (h1, h2, du, dz1; passed as void*) are stored as bf16 (gemm_backend bit 5)
+int tc_gemm1_fwd(const float* x, const Coef* coef0, const void* w1img, void* h1, double* stats1, int N, int P, int single, int hbf,
+                 cudaStream_t st);
+int tc_gemm2_fwd(const void* h2, const Coef* coef2, const float* gate, const void* w2img, float* y, double* stats3, int N,
+                 int P, int single, int hbf, cudaStream_t st);
+int tc_gemm2_fwd_residual(const void* h2, const Coef* coef2, const float* gate, const void* w2img, const float* x, const Coef* coef3,
+                          float* out, double* stats, int N, int P, int single, int hbf, cudaStream_t st);
+int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, void* du, const void* h2,
+                 const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, int hbf, cudaStream_t st);
+int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, int hbf, cudaStream_t st);
+int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* h2, const Coef* coef2, const float* gate,
+              float* partial, int max_parts, float* dw2, int N, int P, int single, int hbf, cudaStream_t st);
+int tc_wgrad1(const float* x, const Coef* coef0, const void* dz1, const void* h1, const BCoef* bc1, float* partial,
+              int max_parts, float* dw1, int N, int P, int single, int hbf, cudaStream_t st);
+// fused input-gradient + weight-gradient GEMMs (gemm_backend bits 3 / 4): one read of the shared operand tensors
 int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
                        const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
                        float* dw2, int N, int P, int single, cudaStream_t st);
-int tc_gemm1_bwd_fused(const float* dz1, const float* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+int tc_gemm1_bwd_fused(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
-                       int P, int single, cudaStream_t st);
+                       int P, int single, int hbf, cudaStream_t st);
 
 // dwconv_rows.cu (row-streaming depthwise kernels fed by TMA bulk copies; the backward one is fused: du, h2, h1 -> dz1 in one pass)
-int launch_dwconv_fwd(const float* h1, const Coef* coef1, const float* wdw, float* h2, double* stats2, int N, int H, int W,
+int launch_dwconv_fwd(const void* h1, const Coef* coef1, const float* wdw, void* h2, double* stats2, int N, int H, int W, int hbf,
                       cudaStream_t st);
-int launch_dwconv_fwd_pool(const float* h1, const Coef* coef1, const float* wdw, float* h2, const Coef* coef2, double* pool, int N,
-                           int H, int W, cudaStream_t st);
-int launch_dwconv_bwd(const float* du, const float* h2, const float* h1, const float* gate, const float* dmp,
+int launch_dwconv_fwd_pool(const void* h1, const Coef* coef1, const float* wdw, void* h2, const Coef* coef2, double* pool, int N,
+                           int H, int W, int hbf, cudaStream_t st);
+int launch_dwconv_bwd(const void* du, const void* h2, const void* h1, const float* gate, const float* dmp,
                       const Coef* coef2, const BCoef* bc2, const Coef* coef1, const MeanRstd* mr1, const float* wdw,
-                      float* dz1, double* bstats1, float* dwdw, int N, int H, int W, cudaStream_t st);
+                      void* dz1, double* bstats1, float* dwdw, int N, int H, int W, int hbf, cudaStream_t st);
 
 // se.cu
 int launch_se_fwd(const double* pool_stats, const float* f1, const float* f2, float* save, float* gate, int N, int P,

@@ -79,6 +79,7 @@ struct BlockWs {
 
 struct Layout {
     int Ne, B, P, nblk, Nmax, max_parts;
+    size_t hes;                 // bytes per element of the 256-channel hidden tensors h1, h2, du, dz1 (4, or 2 with gemm_backend bit 5)
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
     size_t bstats_in, bc_in, mom_in, gram_in;
@@ -105,10 +106,10 @@ static void block_bwd_stats(Bump& b, BlockWs& w, int N) {
     w.sums3 = b.take((size_t)N * UB_HID * 3 * sizeof(double));
 }
 // acts == false: the caller assigns h1 / h2 / y / out itself (forward-only layout: blocks share them, see make_layout)
-static void block_rest(Bump& b, BlockWs& w, int N, size_t P, bool acts = true) {
+static void block_rest(Bump& b, BlockWs& w, int N, size_t P, bool acts = true, size_t hes = sizeof(float)) {
     if (acts) {
-        w.h1 = b.take((size_t)N * P * UB_HID * sizeof(float));
-        w.h2 = b.take((size_t)N * P * UB_HID * sizeof(float));
+        w.h1 = b.take((size_t)N * P * UB_HID * hes);
+        w.h2 = b.take((size_t)N * P * UB_HID * hes);
         w.y = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
         w.out = b.take((size_t)N * P * UB_WIDTH * sizeof(float));
     }
@@ -142,6 +143,9 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     if (d->out_dim < UB_S2 || d->out_dim > 26) return UB_ERR_ARG;
     L.B = d->B; L.Ne = d->B * d->T; L.P = d->H * d->W; L.nblk = 1 + d->n_dec_blocks;
     L.Nmax = L.Ne;
+    // bf16 hidden storage needs the tcgen05 GEMMs (the CUDA-core comparators read fp32) and excludes the fused project-conv backward
+    if ((d->gemm_backend & 32) && ((d->gemm_backend & 3) != 3 || (d->gemm_backend & 16))) return UB_ERR_ARG;
+    L.hes = (d->gemm_backend & 32) ? 2 : 4;
     const size_t P = (size_t)L.P;
     Bump b;
     L.fwd_zero_begin = b.off;
@@ -164,12 +168,12 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     L.attn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
     L.agg = b.take((size_t)L.B * P * UB_WIDTH * sizeof(float));
     if (d->need_grad) {
-        for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P);
+        for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, true, L.hes);
     } else {
         // forward only (validation / inference): nothing is saved for a backward, so all blocks share one set of hidden
         // buffers (kernels run in stream order) and the decoder outputs ping-pong between two buffers: 1 x (2 Hh + A) + 3 A
         // instead of 6 x (2 Hh + 2 A) -- at B=32, T=5 about 40 GB instead of 107 GB.
-        const size_t h1 = b.take((size_t)L.Ne * P * UB_HID * sizeof(float)), h2 = b.take((size_t)L.Ne * P * UB_HID * sizeof(float));
+        const size_t h1 = b.take((size_t)L.Ne * P * UB_HID * L.hes), h2 = b.take((size_t)L.Ne * P * UB_HID * L.hes);
         const size_t y = b.take((size_t)L.Ne * P * UB_WIDTH * sizeof(float));
         const size_t out0 = b.take((size_t)L.Ne * P * UB_WIDTH * sizeof(float));
         const size_t pp[2] = {b.take((size_t)L.B * P * UB_WIDTH * sizeof(float)), b.take((size_t)L.B * P * UB_WIDTH * sizeof(float))};
@@ -183,8 +187,8 @@ static int make_layout(const ub200_desc* d, Layout& L) {
         L.gA = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
         L.gB = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
         L.dn0 = b.take((size_t)L.Nmax * P * UB_WIDTH * sizeof(float));
-        L.du = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
-        L.dz1 = b.take((size_t)L.Nmax * P * UB_HID * sizeof(float));
+        L.du = b.take((size_t)L.Nmax * P * UB_HID * L.hes);
+        L.dz1 = b.take((size_t)L.Nmax * P * UB_HID * L.hes);
         L.max_parts = MAX_PARTS;
         L.partial = b.take((size_t)L.max_parts * UB_WIDTH * UB_HID * sizeof(float));
         L.dwup = b.take((size_t)UB_HEADS * L.Ne * P * sizeof(float));
@@ -234,6 +238,8 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     const bool tcb = (c.backend & 1) != 0;
     // forward operands (normalised activations, weights) take the fp16 hi/lo split (2^-22), see gemm_tc.cu: SPLIT_F16X3
     const int single = (c.backend & 4) ? 1 : 2;
+    const int hbf = (c.backend & 32) != 0;
+    if (hbf && !tcb) return UB_ERR_ARG;
     if (tcb) {
         // M-operand images: W1 [256][128] and W2 [128][256] as stored (forward); W2^T / W1^T for the input-gradient GEMMs (bf16)
         UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, single == 2, c.st));
@@ -248,20 +254,20 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     }
     UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
     if (tcb)
-        UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, single, c.st));
+        UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<char>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, single, hbf, c.st));
     else
         UB_PROF(KID_GEMM1_FWD, c.st, simt_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<float>(ws, w.w1t), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, c.st));
     UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
-    UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
-                             at<double>(ws, w.stats2), c.N, c.H, c.W, c.st));
+    UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd(at<char>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<char>(ws, w.h2),
+                             at<double>(ws, w.stats2), c.N, c.H, c.W, hbf, c.st));
     UB_TRY(finalize(c, w.stats2, UB200_B_N2_W, w.coef2, w.mr2, UB_HID));
-    UB_PROF(KID_SE_POOL, c.st, launch_se_pool(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.pool),
-                          need_gp ? at<double>(ws, w.gp) : nullptr, c.N, P, c.st));
+    UB_PROF(KID_SE_POOL, c.st, launch_se_pool(at<char>(ws, w.h2), at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.pool),
+                          need_gp ? at<double>(ws, w.gp) : nullptr, c.N, P, hbf, c.st));
     UB_TRY(launch_se_fwd(at<double>(ws, w.pool), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2), at<float>(ws, w.se_save),
                          at<float>(ws, w.gate), c.N, P, c.st));
     if (tcb)
-        UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img),
-                              at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, single, c.st));
+        UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd(at<char>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img),
+                              at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, single, hbf, c.st));
     else
         UB_PROF(KID_GEMM2_FWD, c.st, simt_gemm2_fwd(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<float>(ws, w.w2t),
                               at<float>(ws, w.y), at<double>(ws, w.stats3), c.N, P, c.st));
@@ -280,25 +286,26 @@ static int mbconv_forward_eval_bn(const BlockCtx& c, const float* x, double* nex
     const int P = c.H * c.W;
     void* ws = c.ws;
     const int single = (c.backend & 4) ? 1 : 2;
+    const int hbf = (c.backend & 32) != 0;
     UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W1), at<char>(ws, w.w1img), UB_HID, UB_WIDTH, 0, single == 2, c.st));
     UB_TRY(tc_prep_weights(pf(c.p, UB200_B_W2), at<char>(ws, w.w2img), UB_WIDTH, UB_HID, 0, single == 2, c.st));
     UB_TRY(finalize(c, w.stats0, UB200_B_N0_W, w.coef0, w.mr0, UB_WIDTH));
     UB_TRY(finalize(c, w.stats1, UB200_B_N1_W, w.coef1, w.mr1, UB_HID));
     UB_TRY(finalize(c, w.stats2, UB200_B_N2_W, w.coef2, w.mr2, UB_HID));
     UB_TRY(finalize(c, w.stats3, UB200_B_N3_W, w.coef3, w.mr3, UB_WIDTH));
-    UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<float>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, single, c.st));
-    UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd_pool(at<float>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<float>(ws, w.h2),
-                             at<Coef>(ws, w.coef2), at<double>(ws, w.pool), c.N, c.H, c.W, c.st));
+    UB_PROF(KID_GEMM1_FWD, c.st, tc_gemm1_fwd(x, at<Coef>(ws, w.coef0), at<char>(ws, w.w1img), at<char>(ws, w.h1), at<double>(ws, w.stats1), c.N, P, single, hbf, c.st));
+    UB_PROF(KID_DWCONV_FWD, c.st, launch_dwconv_fwd_pool(at<char>(ws, w.h1), at<Coef>(ws, w.coef1), pf(c.p, UB200_B_WDW), at<char>(ws, w.h2),
+                             at<Coef>(ws, w.coef2), at<double>(ws, w.pool), c.N, c.H, c.W, hbf, c.st));
     UB_TRY(launch_se_fwd(at<double>(ws, w.pool), pf(c.p, UB200_B_F1), pf(c.p, UB200_B_F2), at<float>(ws, w.se_save),
                          at<float>(ws, w.gate), c.N, P, c.st));
     // the column sums of `out` go to the next block's PreNorm accumulator (unused by an eval-mode BatchNorm, harmless) or stats3
-    UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd_residual(at<float>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img), x,
-                          at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats ? next_stats : at<double>(ws, w.stats3), c.N, P, single, c.st));
+    UB_PROF(KID_GEMM2_FWD, c.st, tc_gemm2_fwd_residual(at<char>(ws, w.h2), at<Coef>(ws, w.coef2), at<float>(ws, w.gate), at<char>(ws, w.w2img), x,
+                          at<Coef>(ws, w.coef3), at<float>(ws, w.out), next_stats ? next_stats : at<double>(ws, w.stats3), c.N, P, single, hbf, c.st));
     return UB_OK;
 }
 
 // dout: gradient w.r.t. the block output; dx: gradient w.r.t. the block input (may not alias dout)
-static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout, float* dx, float* dn0, float* du, float* dz1,
+static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout, float* dx, float* dn0, void* du, void* dz1,
                            float* partial) {
     const BlockWs& w = *c.w;
     const int P = c.H * c.W;
@@ -307,24 +314,28 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
     const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
     const int single = (c.backend & 4) != 0;
+    const int hbf = (c.backend & 32) != 0;
+    if (hbf && (!tcb || !tcw || (c.backend & 16))) return UB_ERR_ARG;
+    float* du_f = static_cast<float*>(du);                     // fp32 view for the CUDA-core comparators / the fused project kernel
+    float* dz1_f = static_cast<float*>(dz1);
     // input-gradient + weight-gradient GEMM of a convolution in one kernel: bit 3 = expand convolution (default: measured
     // 10.1 -> 7.7 ms per step), bit 4 = project convolution (measured slower: 10.0 -> 11.0 ms, its GELU-heavy loader and epilogue
     // do not shrink with the bytes)
     const bool fused1 = tcb && tcw && (c.backend & 8) != 0, fused2 = tcb && tcw && (c.backend & 16) != 0;
     if (fused2)
-        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_fused(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
+        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_fused(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du_f, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), at<float>(ws, w.gate), partial,
                               MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
     else if (tcb)
-        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<float>(ws, w.h2),
-                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, single, c.st));
+        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<char>(ws, w.h2),
+                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, single, hbf, c.st));
     else
-        UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du, at<float>(ws, w.h2),
+        UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du_f, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
     if (fused2) {
     } else if (tcw)
-        UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
-                           at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
+        UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.h2), at<Coef>(ws, w.coef2),
+                           at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, hbf, c.st));
     else
         UB_PROF(KID_WGRAD2, c.st, simt_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<float>(ws, w.h2), at<Coef>(ws, w.coef2),
                            at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, c.st));
@@ -332,25 +343,25 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                          at<float>(ws, w.se_save), gf(c.g, UB200_B_F1), gf(c.g, UB200_B_F2), at<float>(ws, w.dmp),
                          at<double>(ws, w.bstats2), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats2, UB200_B_N2_W, w.mr2, w.bc2, UB_HID));
-    UB_PROF(KID_DWCONV_BWD, c.st, launch_dwconv_bwd(du, at<float>(ws, w.h2), at<float>(ws, w.h1), at<float>(ws, w.gate), at<float>(ws, w.dmp),
+    UB_PROF(KID_DWCONV_BWD, c.st, launch_dwconv_bwd(du, at<char>(ws, w.h2), at<char>(ws, w.h1), at<float>(ws, w.gate), at<float>(ws, w.dmp),
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
-                             pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, c.st));
+                             pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, hbf, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
     if (fused1)
-        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_fused(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
-                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, MAX_PARTS, gf(c.g, UB200_B_W1), c.N, P, single, c.st));
+        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_fused(dz1, at<char>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
+                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, MAX_PARTS, gf(c.g, UB200_B_W1), c.N, P, single, hbf, c.st));
     else if (tcb)
-        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
-                              at<double>(ws, w.bstats0), c.N, P, single, c.st));
+        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<char>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
+                              at<double>(ws, w.bstats0), c.N, P, single, hbf, c.st));
     else
-        UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
+        UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1_f, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
     if (fused1) {
     } else if (tcw)
-        UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
-                           gf(c.g, UB200_B_W1), c.N, P, single, c.st));
+        UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<char>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
+                           gf(c.g, UB200_B_W1), c.N, P, single, hbf, c.st));
     else
-        UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
+        UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1_f, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
     UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.relu_mask_dx, c.st));
@@ -399,7 +410,7 @@ int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (backend & 2)
         return tc_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
-                         static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, (backend & 4) != 0, st);
+                         static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, (backend & 4) != 0, 0, st);
     return simt_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
                        static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
 }
@@ -414,7 +425,7 @@ int ub200_gemm1_forward(int backend, const float* x, const float* coef, const fl
     if (backend & 1) {
         const int mode = (backend & 4) ? 1 : 2;
         UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, mode == 2, st));
-        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, mode, st);
+        return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, mode, 0, st);
     }
     UB_TRY(launch_transpose(w1, static_cast<float*>(scratch), UB_HID, UB_WIDTH, st));
     return simt_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), static_cast<const float*>(scratch), h1, stats, N, P, st);
@@ -482,8 +493,8 @@ int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, s
         // forward-only layout: hidden buffers are shared by all blocks and decoder outputs ping-pong; only the encoder output and
         // the last two decoder outputs still hold what their name says after the call
         if (!d->need_grad && (strcmp(what, "out") != 0 || (bi > 0 && bi < L.nblk - 2))) return UB_ERR_ARG;
-        if (!strcmp(what, "h1")) { *offset = w.h1; *bytes = N * P * UB_HID * 4; return UB_OK; }
-        if (!strcmp(what, "h2")) { *offset = w.h2; *bytes = N * P * UB_HID * 4; return UB_OK; }
+        if (!strcmp(what, "h1")) { *offset = w.h1; *bytes = N * P * UB_HID * L.hes; return UB_OK; }
+        if (!strcmp(what, "h2")) { *offset = w.h2; *bytes = N * P * UB_HID * L.hes; return UB_OK; }
         if (!strcmp(what, "y")) { *offset = w.y; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
         if (!strcmp(what, "out")) { *offset = w.out; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
     }
@@ -566,8 +577,8 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
     float* gA = at<float>(ws, L.gA);
     float* gB = at<float>(ws, L.gB);
     float* dn0 = at<float>(ws, L.dn0);
-    float* du = at<float>(ws, L.du);
-    float* dz1 = at<float>(ws, L.dz1);
+    void* du = at<char>(ws, L.du);
+    void* dz1 = at<char>(ws, L.dz1);
     float* partial = at<float>(ws, L.partial);
 
     const float* dec_out = at<float>(ws, L.blk[L.nblk - 1].out);
@@ -687,7 +698,7 @@ int ub200_head_backward(const float* grad_out, const float* out, const float* de
 
 // ---- standalone MBConv block (tests) -------------------------------------------------------------------
 struct MbLayout { BlockWs w; size_t zero_begin, zero_end, bzero_begin, bzero_end, dn0, du, dz1, partial, total; int max_parts; };
-static void mb_layout(int N, int H, int W, MbLayout& M) {
+static void mb_layout(int N, int H, int W, MbLayout& M, size_t hes = 4) {
     Bump b;
     M.zero_begin = b.off;
     block_fwd_stats(b, M.w, N);
@@ -695,10 +706,10 @@ static void mb_layout(int N, int H, int W, MbLayout& M) {
     M.bzero_begin = b.off;
     block_bwd_stats(b, M.w, N);
     M.bzero_end = b.off;
-    block_rest(b, M.w, N, (size_t)H * W);
+    block_rest(b, M.w, N, (size_t)H * W, true, hes);
     M.dn0 = b.take((size_t)N * H * W * UB_WIDTH * 4);
-    M.du = b.take((size_t)N * H * W * UB_HID * 4);
-    M.dz1 = b.take((size_t)N * H * W * UB_HID * 4);
+    M.du = b.take((size_t)N * H * W * UB_HID * hes);
+    M.dz1 = b.take((size_t)N * H * W * UB_HID * hes);
     M.max_parts = MAX_PARTS;
     M.partial = b.take((size_t)M.max_parts * UB_WIDTH * UB_HID * 4);
     M.total = b.off;
@@ -720,7 +731,7 @@ int ub200_mbconv_forward(const float* x, const void* const* block_params, int N,
                          float eps, float momentum, int gemm_backend, float* out, void* ws, size_t ws_bytes, void* stream) {
     if (!x || !block_params || !out || !ws || N < 1 || H % 8 || W % 16) return UB_ERR_ARG;
     MbLayout M;
-    mb_layout(N, H, W, M);
+    mb_layout(N, H, W, M, (gemm_backend & 32) ? 2 : 4);      // the workspace size query assumes fp32 storage (an upper bound)
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = H * W;
@@ -739,12 +750,12 @@ int ub200_mbconv_backward(const float* x, const void* const* block_params, const
                           void* stream) {
     if (!x || !block_params || !dout || !block_grads || !dx || !ws) return UB_ERR_ARG;
     MbLayout M;
-    mb_layout(N, H, W, M);
+    mb_layout(N, H, W, M, (gemm_backend & 32) ? 2 : 4);
     if (ws_bytes < M.total) return UB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(at<char>(ws, M.bzero_begin), 0, M.bzero_end - M.bzero_begin, st) != cudaSuccess) return UB_ERR_CUDA;
     BlockCtx c = mb_ctx(M, block_params, block_grads, ws, N, H, W, groups, training, 1e-5f, 0.1f, gemm_backend, st);
-    return mbconv_backward(c, x, dout, dx, at<float>(ws, M.dn0), at<float>(ws, M.du), at<float>(ws, M.dz1),
+    return mbconv_backward(c, x, dout, dx, at<float>(ws, M.dn0), at<char>(ws, M.du), at<char>(ws, M.dz1),
                            at<float>(ws, M.partial));
 }
 

@@ -5,6 +5,7 @@
 // nn.GroupNorm(4 groups) in the encoder, nn.BatchNorm2d in the decoder; MBConv residual add
 // (uncrtaints.py:142-146).  Statistics are produced by the kernel that writes a tensor (column sums
 // in its epilogue, fp64 accumulation) and consumed as per-(frame, channel) scale/shift here.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -163,7 +164,13 @@ __global__ void __launch_bounds__(256) residual_fwd_kernel(const float* __restri
 // In training it also gathers gp_stats[n][c] += (sum_p gelu'(z2), sum_p gelu'(z2)*h2_hat): the two terms of
 // the Norm2 backward statistics that do not depend on the incoming gradient (see se_bwd_kernel).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) se_pool_kernel(const float* __restrict__ h2, const Coef* __restrict__ coef2,
+__device__ __forceinline__ float4 ld4h(const float* p) { return ld4(p); }
+__device__ __forceinline__ float4 ld4h(const __nv_bfloat16* p) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+}
+template <class HT>
+__global__ void __launch_bounds__(256) se_pool_kernel(const HT* __restrict__ h2, const Coef* __restrict__ coef2,
                                                        const MeanRstd* __restrict__ mr2, double* pool_stats,
                                                        double* gp_stats, int P, int chunk) {
     constexpr int C = UB_HID, Q = C / 4, ROWS = 256 / Q;
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const float* __restrict__ 
     const bool train = gp_stats != nullptr;
 #pragma unroll 4
     for (int p = p0 + r; p < p1; p += ROWS) {
-        const float4 v = ld4(h2 + base + (size_t)p * C);
+        const float4 v = ld4h(h2 + base + (size_t)p * C);
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -285,10 +292,14 @@ int launch_residual_fwd(const float* x, const float* y, const Coef* coef3, float
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int launch_se_pool(const float* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
-                   int P, cudaStream_t st) {
+int launch_se_pool(const void* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
+                   int P, int hbf, cudaStream_t st) {
     const int chunk = chunk_for(P);
-    se_pool_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(h2, coef2, mr2, pool_stats, gp_stats, P, chunk);
+    if (hbf)
+        se_pool_kernel<__nv_bfloat16><<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), coef2, mr2, pool_stats,
+                                                                                       gp_stats, P, chunk);
+    else
+        se_pool_kernel<float><<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(static_cast<const float*>(h2), coef2, mr2, pool_stats, gp_stats, P, chunk);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
