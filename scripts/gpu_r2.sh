@@ -36,6 +36,7 @@ ncu)
     echo "ncu $k exit $?"
     ncu -i gpurun_out/prof_$k.ncu-rep --page raw --csv > gpurun_out/prof_$k.csv 2>/dev/null
     ncu -i gpurun_out/prof_$k.ncu-rep --page details > gpurun_out/prof_$k.txt 2>/dev/null
+    [ "${NCU_SOURCE:-0}" = "1" ] && ncu -i gpurun_out/prof_$k.ncu-rep --page source --csv > gpurun_out/prof_${k}_source.csv 2>/dev/null
     [ "${NCU_KEEP:-0}" = "1" ] || rm -f gpurun_out/prof_$k.ncu-rep
   done ;;
 cfg3)

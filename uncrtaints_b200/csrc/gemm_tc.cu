@@ -949,8 +949,8 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                 }
             };
             if constexpr (CONV == 1) {
-                // dn0[128][px] += W1^T[:, blk] . dh1_blk, interleaved with the weight-gradient MMAs: the two accumulation chains are
-                // independent, and an N=64 MMA is shorter than the accumulate latency of its predecessor on the same accumulator
+                // dn0[128][px] += W1^T[:, blk] . dh1_blk, interleaved with the weight-gradient MMAs (two independent accumulation
+                // chains; the tensor pipe is ~11 % busy in this kernel, ncu r02 -- the kernel is bound by load / barrier latency)
                 const uint32_t a_hi = smem_u32(sW) + blk * (NOUT * 128), a_lo = a_hi + W_HALF;
                 const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC, dw = tmem_base + DW_COL + blk * 64;
 #pragma unroll
@@ -1152,9 +1152,9 @@ int tc_gemm1_bwd_fused(const void* dz1, const void* h1, const BCoef* bc1, const 
     tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
     int nparts = 0;
     int rc = hbf ? tc::launch_bwd_fused<1>(tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, lr, w1timg, ep, partial,
-                                           max_parts, N, P, 1, UB_WIDTH, single, &nparts, st)
+                                   max_parts, N, P, 1, UB_WIDTH, single, &nparts, st)
                  : tc::launch_bwd_fused<1>(tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, lr, w1timg, ep, partial,
-                                           max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
+                                   max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
 }
