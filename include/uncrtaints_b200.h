@@ -83,11 +83,10 @@ typedef struct ub200_desc {
     int training;               /* nn.Module.training: BatchNorm batch statistics + running update, dropout on */
     int need_grad;              /* keep what ub200_backward needs */
     int mean_sigmoid;           /* out_nonlin_mean (uncrtaints.py:384) */
-    int gemm_backend;           /* bit 0: tcgen05 forward (fp16 hi/lo x3) / input-gradient (bf16 hi/lo x3) GEMMs; bit 1: tcgen05 weight-gradient GEMMs;
-                                   bit 2: single-pass bf16 in those (reduced precision); bits 3 / 4: input- and weight-gradient GEMM of the expand /
-                                   project convolution fused into one kernel (need bits 0 and 1); bit 5: the 256-channel hidden tensors h1, h2, du, dz1
-                                   are stored as bf16 (needs bits 0 and 1, excludes bit 4; BASELINE config #3 = 47); default 11;
-                                   0 = fp32 CUDA cores (test comparator) */
+    int gemm_backend;           /* 3 (default) = tcgen05 tensor-core path: forward GEMMs with fp16 hi/lo operands (three MMAs, 2^-22), input- and
+                                   weight-gradient GEMMs with bf16 hi/lo operands, the expand convolution's two backward GEMMs fused into one kernel;
+                                   0 = fp32 CUDA-core GEMMs (test comparator).  Flags on top of 3: +4 single-pass bf16 MMAs (reduced precision),
+                                   +32 the 256-channel hidden tensors h1, h2, du, dz1 stored as bf16 (3 + 4 + 32 = 39: BASELINE config #3) */
     float scale_by;             /* uncrtaints.py:250,384 */
     float var_eps;              /* 1e-9 if scale_by == 1 else 1e-3 (uncrtaints.py:374) */
     float pad_value;            /* uncrtaints.py:245,392 */
@@ -111,12 +110,6 @@ int ub200_prof_enable(unsigned long long mask);
 int ub200_prof_num_kernels(void);
 const char* ub200_prof_kernel_name(int kid);
 int ub200_prof_read(int kid, double* total_ms, int* launches);
-
-/* The weight-gradient GEMM of the 1x1 expand convolution alone (autograd of uncrtaints.py:126):
- * dw1[256][128] += sum_p dh1[p][o] * n0[p][k], n0 = x*scale0 + shift0, dh1 = a*dz1 + b*h1 + c (coef0: [N][128] pairs,
- * bc1: [N][256] (a,b,c,pad) quads).  scratch: 148 * 128 KB. */
-int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const float* dz1, const float* h1, const float* bc1,
-                         float* dw1, int N, int P, void* scratch, void* stream);
 
 /* The 1x1 expand GEMM of an MBConv block alone (uncrtaints.py:126 with the PreNorm apply fused in front and the
  * Norm1 statistics behind): h1[N*P][256] = (x[N*P][128]*scale + shift) . W1^T; stats[N][256][2] = column (sum, sumsq).

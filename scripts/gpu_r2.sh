@@ -26,9 +26,9 @@ loss)
 bench3)
   BENCH_ARGS="--backend 3" ; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-parity --backend 3 > gpurun_out/bench_b3.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b3.log ;;
 bench11)
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --backend 11 > gpurun_out/bench_b11.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b11.log; grep -o '"parity": {[^}]*}' gpurun_out/bench_b11.log ;;
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --backend 3 > gpurun_out/bench_b11.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b11.log; grep -o '"parity": {[^}]*}' gpurun_out/bench_b11.log ;;
 bench27)
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-parity --backend 27 > gpurun_out/bench_b27.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b27.log ;;
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-parity --backend 3 > gpurun_out/bench_b27.log 2>&1; python scripts/show_bench.py gpurun_out/bench_b27.log ;;
 ncu)
   for k in ${NCU_KERNELS}; do
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip ${NCU_SKIP:-6} -c ${NCU_COUNT:-1} -f \

@@ -88,7 +88,8 @@ if len(lines) > 6:
     A, Hh = 128 * 65536 * 4, 256 * 65536 * 4
     ALG = {"dwrows_bwd2_kernel": 4 * Hh, "dwrows_fwd_kernel": 2 * Hh, "gemm_tc_kernel<128, 256, TLoadNormed": A + Hh,
            "gemm_tc_kernel<256, 128, TLoadGeluGate": Hh + A, "gemm_tc_kernel<128, 256, TLoadNormBwd": 2 * A + 2 * Hh,
-           "gemm_tc_kernel<256, 128, TLoadNormBwd": 2 * Hh + 2 * A, "wgrad_tc_kernel<TLoadNormBwd, TLoadGeluGate>": 2 * A + Hh,
+           "gemm_tc_kernel<256, 128, TLoadNormBwd": 2 * Hh + 2 * A, "bwd_tc_kernel<1": 2 * Hh + 2 * A, "bwd_tc_kernel<2": 2 * Hh + 2 * A,
+           "wgrad_tc_kernel<TLoadNormBwd, TLoadGeluGate>": 2 * A + Hh,
            "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>": A + 2 * Hh, "se_pool_kernel": Hh, "residual_bwd_kernel": 4 * A,
            "residual_fwd_kernel": 3 * A, "norm_bwd_stats_kernel": 2 * A}
     per_frame = {}

@@ -33,12 +33,22 @@ def test_desc_struct_and_workspace_query_without_gpu():
     assert L.ub200_num_param_slots(d) == _lib.UB200_P_BLOCK0 + 6 * _lib.UB200_BLOCK_STRIDE
     d.H = 250                                   # not a multiple of 32 -> unsupported
     assert L.ub200_workspace_bytes(d) == 0
-    d.H, d.T = 256, 9                           # T > 8 -> unsupported
+    d.H, d.T = 256, 9                           # T > 8: run-time-T temporal kernels (up to 64)
+    assert L.ub200_workspace_bytes(d) > n
+    d.T = 65
     assert L.ub200_workspace_bytes(d) == 0
+    d.T, d.need_grad = 3, 0                     # forward only: shared hidden buffers, ping-pong decoder outputs
+    assert L.ub200_workspace_bytes(d) < n / 2
+    d.need_grad, d.gemm_backend = 1, 1          # mixed backends do not exist: 0 (CUDA cores) or 3 (tcgen05) plus flags
+    assert L.ub200_workspace_bytes(d) == 0
+    d.gemm_backend = 3 | 32                     # bf16 hidden storage
+    assert L.ub200_workspace_bytes(d) < 0.8 * n
     off, nb = ctypes.c_size_t(), ctypes.c_size_t()
     d.T = 3
     assert L.ub200_workspace_tap(d, b"blk3.h2", ctypes.byref(off), ctypes.byref(nb)) == 0
-    assert nb.value == 16 * 65536 * 256 * 4
+    assert nb.value == 16 * 65536 * 256 * 2     # bf16 hidden storage: 2 bytes per element
+    d.gemm_backend = 3
+    assert L.ub200_workspace_tap(d, b"blk3.h2", ctypes.byref(off), ctypes.byref(nb)) == 0 and nb.value == 16 * 65536 * 256 * 4
     assert L.ub200_workspace_tap(d, b"nonsense", ctypes.byref(off), ctypes.byref(nb)) == -1
 
 

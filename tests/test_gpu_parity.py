@@ -64,10 +64,10 @@ def check_grads(named_params, ref_grads, tag, tol=TOL, training=True):
     assert not bad, f"{tag}: gradient mismatch for {bad[:8]} ({len(bad)} tensors); see gpurun_out/parity_report.txt"
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3, 11, 27])
+@pytest.mark.parametrize("backend", [0, 3])
 def test_golden_diag_train_pad(golden_weights, backend):
-    """backend 3 = tcgen05 GEMMs everywhere, 11 = additionally the fused input-/weight-gradient kernels; 0 / 1 = the fp32 CUDA-core
-    GEMMs kept as test comparators."""
+    """backend 3 = the product path (tcgen05 GEMMs, fused expand-convolution backward); 0 = the fp32 CUDA-core GEMMs kept as the
+    test comparator."""
     import uncrtaints_b200 as ub
     c = load_npz("case_diag_train_pad.npz")
     x, y, d = (torch.from_numpy(c[k]).cuda() for k in ("x", "y", "dates"))
@@ -204,7 +204,7 @@ def _nhwc(t):   # [N,C,H,W] -> [N,H*W,C]
     return t.permute(0, 2, 3, 1).reshape(n, h * w, c).contiguous()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 3, 11, 27])
+@pytest.mark.parametrize("backend", [0, 3])
 @pytest.mark.parametrize("groups,training,shape", [(4, 1, (3, 16, 32)), (0, 1, (2, 64, 64)), (0, 0, (1, 32, 48)), (4, 1, (1, 96, 16)),
                                                    (0, 1, (3, 16, 32)), (0, 0, (3, 16, 32))])
 def test_mbconv_block_vs_oracle(golden_weights, groups, training, shape, backend):
@@ -221,10 +221,10 @@ def test_mbconv_block_single_pass_bf16(golden_weights, groups, training):
     _mbconv_block_vs_oracle(golden_weights, groups, training, 7, True, (2, 64, 64), ",bf16x1", tol=5e-2)
 
 
-@pytest.mark.parametrize("backend", [43, 47])
+@pytest.mark.parametrize("backend", [35, 39])
 @pytest.mark.parametrize("groups,training,shape", [(4, 1, (2, 64, 64)), (0, 1, (3, 32, 48)), (0, 0, (1, 96, 16))])
 def test_mbconv_block_bf16_hidden_storage(golden_weights, groups, training, shape, backend):
-    """gemm_backend bit 5 (BASELINE config #3): h1, h2, du, dz1 stored as bf16 -- 43 with the three-MMA operand split, 47 with
+    """gemm_backend bit 5 (BASELINE config #3): h1, h2, du, dz1 stored as bf16 -- 35 with the three-MMA operand split, 39 with
     single-pass bf16 MMAs on top.  Reduced precision by design (2^-9 per stored element): tolerance 5e-2, errors are reported."""
     _mbconv_block_vs_oracle(golden_weights, groups, training, backend, True, shape, ",bf16-hidden", tol=5e-2)
 
@@ -295,15 +295,12 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
 
 @pytest.mark.parametrize("B,T,H,W,covmode,train,pad,backend", [
     (1, 2, 256, 256, "diag", True, False, 0),     # full-resolution frame (x8 upsampling), dropout mask injected
-    (1, 2, 256, 256, "diag", True, False, 1),     # same through the tcgen05 GEMMs
+    (1, 2, 256, 256, "diag", True, False, 3),     # same through the tcgen05 GEMMs
     (2, 5, 64, 96, "diag", True, True, 3),        # T=5 (BASELINE config #3 sequence length), non-square, padded frame
     (1, 3, 128, 64, "iso", False, False, 0),      # eval mode, isotropic covariance
     (16, 3, 64, 64, "diag", True, False, 3),      # BASELINE config #2's batch and sequence length (BatchNorm over 16 samples)
-    (16, 3, 64, 64, "diag", True, False, 27),     # ... with both fused input-/weight-gradient kernels (CTAs span several frames)
-    (2, 5, 64, 96, "diag", True, True, 27),
-    (1, 2, 256, 256, "diag", True, False, 27),
-    (1, 12, 64, 64, "diag", True, True, 11),      # T > 8: run-time-T temporal kernels (the dataset yields up to 30 time points)
-    (2, 9, 64, 64, "iso", False, False, 11),
+    (1, 12, 64, 64, "diag", True, True, 3),       # T > 8: run-time-T temporal kernels (the dataset yields up to 30 time points)
+    (2, 9, 64, 64, "iso", False, False, 3),
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub
@@ -396,7 +393,7 @@ def test_philox_dropout_statistics(golden_weights):
     assert abs(float(a1.double().mean() / base.double().mean()) - 1.0) < 5e-3
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 3])
 def test_gemm1_op_vs_fp64(backend):
     """The 1x1 expand GEMM alone (ub200_gemm1_forward): fp32 CUDA-core path and tcgen05 bf16x3 path vs an fp64 matmul."""
     from uncrtaints_b200 import _lib
@@ -420,32 +417,6 @@ def test_gemm1_op_vs_fp64(backend):
     eq = rel_l2(stats[..., 1], (ref ** 2).sum(1))
     report("parity_report.txt", [f"gemm1 op backend={backend}: h1 rel_l2={e:.3e} sum {es:.3e} sumsq {eq:.3e}"])
     assert e < 5e-5 and es < 1e-4 and eq < 1e-4
-
-
-@pytest.mark.parametrize("backend", [0, 2])
-def test_wgrad1_op_vs_fp64(backend):
-    """Weight-gradient GEMM alone (ub200_wgrad1_forward): CUDA-core path and tcgen05 MN-major bf16x3 path vs fp64."""
-    from uncrtaints_b200 import _lib
-    L = _lib.lib()
-    N, P = 3, 1024
-    g = torch.Generator("cpu").manual_seed(33)
-    x = torch.randn(N, P, 128, generator=g)
-    dz1 = torch.randn(N, P, 256, generator=g)
-    h1 = torch.randn(N, P, 256, generator=g)
-    coef0 = torch.stack([torch.rand(N, 128, generator=g) + 0.5, torch.randn(N, 128, generator=g)], dim=-1).contiguous()
-    bc1 = torch.cat([torch.randn(N, 256, 3, generator=g), torch.zeros(N, 256, 1)], dim=-1).contiguous()
-    n0 = x.double() * coef0[:, None, :, 0].double() + coef0[:, None, :, 1].double()
-    dh1 = bc1[:, None, :, 0].double() * dz1.double() + bc1[:, None, :, 1].double() * h1.double() + bc1[:, None, :, 2].double()
-    ref = torch.einsum("npo,npk->ok", dh1, n0)
-    dw1 = torch.zeros(256, 128, device="cuda")
-    scratch = torch.empty(148 * 128 * 256 * 4, dtype=torch.uint8, device="cuda")
-    args = [t.cuda() for t in (x, coef0, dz1, h1, bc1)]
-    _lib.check(L.ub200_wgrad1_forward(backend, *[a.data_ptr() for a in args], dw1.data_ptr(), N, P, scratch.data_ptr(),
-                                      torch.cuda.current_stream().cuda_stream), "wgrad1_forward")
-    torch.cuda.synchronize()
-    e = rel_l2(dw1, ref)
-    report("parity_report.txt", [f"wgrad1 op backend={backend}: rel_l2={e:.3e}"])
-    assert e < 5e-5
 
 
 def test_flat_bucket_in_place_gradients(golden_weights):
@@ -501,10 +472,10 @@ def test_mgnll_deferred_negative_check():
         crit.check()
 
 
-@pytest.mark.parametrize("backend", [7, 43, 47])
+@pytest.mark.parametrize("backend", [7, 35, 39])
 def test_model_single_pass_bf16_backend(golden_weights, backend):
     """Whole model at the BASELINE config #3 sequence length (T=5) through the reduced-precision backends: 7 = single-pass bf16
-    MMAs on fp32 storage, 43 = bf16 storage of the hidden tensors with three-MMA operands, 47 = both (the config #3 path):
+    MMAs on fp32 storage, 35 = bf16 storage of the hidden tensors with three-MMA operands, 39 = both (the config #3 path):
     outputs / loss within 5e-2 of the fp64 oracle (reduced precision by design), errors reported."""
     import uncrtaints_b200 as ub
     B, T, H, W = 1, 5, 64, 64
@@ -580,7 +551,7 @@ def _oracle_step64(golden_weights, x, y, d, cfg, train, keep, pool_idx=None, fus
         O.set_fused(False)
 
 
-@pytest.mark.parametrize("B,T,covmode,backend", [(2, 3, "diag", None), (1, 3, "iso", None), (2, 3, "diag", 3)])
+@pytest.mark.parametrize("B,T,covmode,backend", [(2, 3, "diag", None), (1, 3, "iso", None)])
 def test_headline_resolution_default_backend(golden_weights, B, T, covmode, backend):
     """BASELINE config #2's frame size (15x256x256, T=3) through the DEFAULT backend (tcgen05 bf16x3 forward, input-gradient and
     weight-gradient GEMMs; 148 persistent weight-gradient CTAs with fp32 TMEM accumulation over ~2.6k pixels each at B=2)

@@ -23,7 +23,7 @@ ERRORS = {-1: "UB200_ERR_ARG (unsupported shape / configuration)", -2: "UB200_ER
 # every symbol include/uncrtaints_b200.h declares
 SYMBOLS = [
     "ub200_version", "ub200_launch_count", "ub200_prof_enable", "ub200_prof_num_kernels", "ub200_prof_kernel_name",
-    "ub200_prof_read", "ub200_gemm1_forward", "ub200_wgrad1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
+    "ub200_prof_read", "ub200_gemm1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
     "ub200_backward", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_mgnll_none", "ub200_gnll_none", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
     "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward", "ub200_adam_step", "ub200_img_metrics", "ub200_assemble_input",
 ]
@@ -65,7 +65,6 @@ def lib() -> C.CDLL:
     L.ub200_prof_kernel_name.restype = C.c_char_p
     L.ub200_prof_read.argtypes = [i, C.POINTER(C.c_double), C.POINTER(i)]
     L.ub200_gemm1_forward.argtypes = [i, vp, vp, vp, vp, vp, i, i, vp, vp]
-    L.ub200_wgrad1_forward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
     L.ub200_num_param_slots.argtypes = [dp]
     L.ub200_workspace_bytes.argtypes = [dp]
     L.ub200_workspace_bytes.restype = sz

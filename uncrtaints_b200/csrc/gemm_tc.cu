@@ -745,24 +745,28 @@ static int launch_wgrad_tc(LA la, LB lb, float* partial, int max_parts, int N, i
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused input-gradient + weight-gradient GEMM of one 1x1 convolution (gemm_backend bit 3).
+// Fused input-gradient + weight-gradient GEMM of the 1x1 EXPAND convolution (the backward of uncrtaints.py:126).
 //
-// The two GEMMs of a convolution's backward read the same activation tensors: launched separately (gemm*_bwd + wgrad*) those
-// tensors stream from HBM twice (3 A + 3 Hh per MBConv-frame = 26 % of the backward bytes).  Here ONE persistent
-// kernel builds every operand tile once and feeds it to both GEMMs:
-//     conv 1 (expand, W1 [256][128]):  S = dh1 = normbwd1(dz1, h1) (256 ch, streamed in four 64-channel blocks),  R = n0 = x*sc0+sh0 (128 ch)
-//         dn0[128 ch][px] += W1^T[:, blk] . S_blk   (K-major operands, per block)        dW1^T[k][o in blk] += R^T . S_blk   (MN-major)
-//     conv 2 (project, W2 [128][256]): R = dy = normbwd3(dOut, y) (128 ch),  S = u = gelu(norm2(h2)) * gate (256 ch, four blocks)
-//         du[256 ch][px] = W2^T . R                 (K-major, once per tile)             dW2[o][k in blk]  += R^T . S_blk     (MN-major)
+// The two GEMMs of a convolution's backward read the same activation tensors: launched separately they stream those tensors from
+// HBM twice (for the expand convolution dz1, h1: 2 Hh, and x: A per frame).  Here ONE persistent kernel builds every operand tile
+// once and feeds it to both GEMMs:
+//     S = dh1 = normbwd1(dz1, h1) (256 channels, streamed in four 64-channel blocks),   R = n0 = x*scale0 + shift0 (128 channels)
+//     dn0[128 ch][px] += W1^T[:, blk] . S_blk   (K-major operands, per block)           dW1^T[k][o in blk] += R^T . S_blk   (MN-major)
 // The bytes of a [64 px][64 ch] SWIZZLE_128B block are at the same time a K-major tile (pixels = rows) and an MN-major tile
 // (pixels = the contraction), so the same shared-memory block serves both MMAs.
 //
 // Shared memory cannot hold the 128 KB weight image, a 128-pixel operand ring AND a second 128-pixel operand, so the tile is
 // 64 pixels (UMMA M=128, N=64, K=16): 128 KB weights + 32 KB resident operand R + 3 x 16 KB ring of S blocks + coefficients.
-// TMEM: double-buffered input-gradient accumulator (2 x 64 or 2 x 128 columns) + the whole 128 x 256 weight gradient (256 columns),
+// TMEM: double-buffered input-gradient accumulator (2 x 64 columns) + the whole 128 x 256 weight gradient (256 columns),
 // accumulated over all tiles of the CTA and written once as a partial (reduce_partials_kernel sums the <= 148 partials).
 // One persistent CTA per SM walks a contiguous range of tiles across frames; per-frame coefficient tables are refilled at frame
 // boundaries, the per-channel statistics are flushed by the epilogue when ITS tile (one behind) changes frame.
+// Measured (B=16, ms per step): gemm1_bwd 5.4 + wgrad1 4.7 = 10.1 separate -> 7.6 fused; ncu r02: 204.6 MB of DRAM traffic per frame
+// against 201.3 MB algorithmic, tensor pipe 11 % busy, stalls long_scoreboard 29 % / short_scoreboard 15 % / wait 12 % / barrier 11 %.
+// Tried and rejected (measured): the same fusion for the PROJECT convolution (11.0 ms against 5.0 + 5.0: its GELU-heavy loader and
+// epilogue do not shrink with the bytes, and 64-pixel tiles double its per-step overhead); N=128 weight-gradient batches with the
+// coefficient tables read from global memory (2x slower: the tables thrash the ~26 KB of L1 left beside 218 KB of shared memory);
+// prefetching the epilogue's x values one step ahead (+9 %: the extra loads compete with the operand prefetch).
 // ------------------------------------------------------------------------------------------
 constexpr int FPX = 64;                       // pixels per tile
 constexpr int FBLK = FPX * 128;               // one [64 px][64 ch] bf16 block: 8 KB
@@ -781,11 +785,11 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-template <int CONV, class LS, class LR, class Epi>
+template <class LS, class LR, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __restrict__ partial, int P, long long total_tiles,
               int sa, int sb, int single) {
-    constexpr int NOUT = CONV == 1 ? UB_WIDTH : UB_HID;       // channels of the input gradient (TMEM lanes x MH)
+    constexpr int NOUT = UB_WIDTH;                            // channels of the input gradient (TMEM lanes x MH)
     constexpr int MH = NOUT / 128;
     constexpr int ACC = MH * FPX;                             // TMEM columns of one input-gradient stage
     constexpr int DW_COL = 2 * ACC;                           // weight-gradient accumulator: 256 columns behind the two stages
@@ -937,20 +941,9 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         if (tid == 0) {
             tc_fence_after();
             const uint32_t r_hi = smem_u32(sR), r_lo = r_hi + 2 * FBLK, b_hi = smem_u32(s_hi), b_lo = smem_u32(s_lo);
-            // weight gradient: D[128 (channels of R)][blk*64 .. +64 (channels of S)] += R^T . S_blk  (contraction over the 64 pixels)
-            auto wgrad_mma = [&](int p16) {
-                const uint32_t d = tmem_base + DW_COL + blk * 64;
-                const uint64_t ah = make_wg_desc(r_hi + p16 * 2048), al = make_wg_desc(r_lo + p16 * 2048);
-                const uint64_t bh = make_wg_desc(b_hi + p16 * 2048), bl = make_wg_desc(b_lo + p16 * 2048);
-                tc_mma(d, ah, bh, F_IDESC_MN, (it | p16) != 0);
-                if (!single) {
-                    tc_mma(d, ah, bl, F_IDESC_MN, 1);
-                    tc_mma(d, al, bh, F_IDESC_MN, 1);
-                }
-            };
-            if constexpr (CONV == 1) {
-                // dn0[128][px] += W1^T[:, blk] . dh1_blk, interleaved with the weight-gradient MMAs (two independent accumulation
-                // chains; the tensor pipe is ~11 % busy in this kernel, ncu r02 -- the kernel is bound by load / barrier latency)
+            {
+                // dn0[128][px] += W1^T[:, blk] . dh1_blk   and   dW1^T[128 (channels of R)][blk*64 .. +64] += R^T . S_blk (contraction over
+                // the 64 pixels), interleaved: two independent accumulation chains
                 const uint32_t a_hi = smem_u32(sW) + blk * (NOUT * 128), a_lo = a_hi + W_HALF;
                 const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC, dw = tmem_base + DW_COL + blk * 64;
 #pragma unroll
@@ -968,32 +961,10 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                         tc_mma(dw, al, bh, F_IDESC_MN, 1);
                     }
                 }
-            } else {
-                if (blk == 0) {                               // du[256][px] = W2^T . dy   (both K-blocks of R, two M-blocks)
-#pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16)
-#pragma unroll
-                            for (int j = 0; j < MH; ++j) {   // the two M-blocks alternate: independent accumulators
-                                const uint32_t d = tmem_base + (uint32_t)(it & 1) * ACC + j * FPX;
-                                const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128) + j * (128 * 128) + k16 * 32;
-                                const uint64_t wa = make_desc(a_hi), wl = make_desc(a_hi + W_HALF);
-                                const uint64_t xa = make_desc(r_hi + kb * FBLK + k16 * 32), xl = make_desc(r_lo + kb * FBLK + k16 * 32);
-                                tc_mma(d, wa, xa, F_IDESC_K, (kb | k16) != 0);
-                                if (!single) {
-                                    tc_mma(d, wa, xl, F_IDESC_K, 1);
-                                    tc_mma(d, wl, xa, F_IDESC_K, 1);
-                                }
-                            }
-                    tc_commit(bAcc + (it & 1) * 8);
-                }
-#pragma unroll
-                for (int p16 = 0; p16 < FPX / 16; ++p16) wgrad_mma(p16);
             }
             tc_commit(bRing + slot * 8);                                   // frees the ring slot
             if (blk == 3) {
-                if constexpr (CONV == 1) tc_commit(bAcc + (it & 1) * 8);   // input-gradient accumulator of this tile complete
+                tc_commit(bAcc + (it & 1) * 8);                            // input-gradient accumulator of this tile complete
                 tc_commit(bRfree);                                         // R may be overwritten by the next tile
                 if (q == Q - 1) tc_commit(bDone);
             }
@@ -1028,12 +999,12 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-template <int CONV, class LS, class LR, class Epi>
+template <class LS, class LR, class Epi>
 static int launch_bwd_fused(LS ls, LR lr, const void* wimg, Epi ep, float* partial, int max_parts, int N, int P, int sa, int sb,
                             int single, int* nparts, cudaStream_t st) {
     if (P % FPX != 0) return UB_ERR_ARG;
     constexpr size_t smem = (size_t)F_W_BYTES + 4 * FBLK + FRING * 2 * FBLK + 3 * (UB_HID + UB_WIDTH) * sizeof(float) + (FRING + 4) * 8 + 16 + 1024;
-    auto kern = bwd_tc_kernel<CONV, LS, LR, Epi>;
+    auto kern = bwd_tc_kernel<LS, LR, Epi>;
     UB_SET_SMEM(kern, smem);
     const long long total = (long long)N * (P / FPX);
     const int blocks = (int)(total < max_parts ? total : max_parts);
@@ -1104,13 +1075,6 @@ int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void
                                             N, P, single, st);
     return tc::launch<UB_WIDTH, UB_HID>(al, w2timg, tc::TEpiGemm2Bwd{static_cast<float*>(du), static_cast<const float*>(h2), coef2, mr2, sums3}, N, P, single, st);
 }
-int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, int hbf, cudaStream_t st) {
-    tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
-    if (hbf)
-        return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, w1timg, ep, N, P, single, st);
-    return tc::launch<UB_HID, UB_WIDTH>(tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, w1timg, ep, N, P, single, st);
-}
 // dW2[o][k] += sum_p dy[p][o] * u[p][k]
 int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* h2, const Coef* coef2, const float* gate,
               float* partial, int max_parts, float* dw2, int N, int P, int single, int hbf, cudaStream_t st) {
@@ -1121,39 +1085,16 @@ int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* h
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
 }
-// dW1[o][k] += sum_p dh1[p][o] * n0[p][k]   (M side = n0 (128 channels, index k), N side = dh1 (256 channels, index o))
-int tc_wgrad1(const float* x, const Coef* coef0, const void* dz1, const void* h1, const BCoef* bc1, float* partial,
-              int max_parts, float* dw1, int N, int P, int single, int hbf, cudaStream_t st) {
-    tc::TLoadNormed la{x, coef0};
-    int nparts = 0;
-    int rc = hbf ? tc::launch_wgrad_tc(la, tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st)
-                 : tc::launch_wgrad_tc(la, tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, partial, max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
-    if (rc != UB_OK) return rc;
-    return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);
-}
-// Fused backward of the project convolution: du + Norm2-backward sums (as tc_gemm2_bwd) AND dW2 += dy^T u (as tc_wgrad2) in one pass
-// (fp32 hidden storage only; measured slower than the two-kernel form, kept as an option)
-int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                       const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
-                       float* dw2, int N, int P, int single, cudaStream_t st) {
-    tc::TLoadGeluGate ls{h2, coef2, gate};
-    tc::TLoadNormBwd lr{dout, y, bc3};
-    tc::TEpiGemm2Bwd ep{du, h2, coef2, mr2, sums3};
-    int nparts = 0;
-    int rc = tc::launch_bwd_fused<2>(ls, lr, w2timg, ep, partial, max_parts, N, P, UB_HID, 1, single, &nparts, st);
-    if (rc != UB_OK) return rc;
-    return launch_reduce_partials(partial, dw2, UB_WIDTH * UB_HID, nparts, st);
-}
 // Fused backward of the expand convolution: dn0 + PreNorm-backward sums (as tc_gemm1_bwd) AND dW1 += dh1^T n0 (as tc_wgrad1)
-int tc_gemm1_bwd_fused(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
                        const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
                        int P, int single, int hbf, cudaStream_t st) {
     tc::TLoadNormed lr{x, coef0};
     tc::TEpiGemm1Bwd ep{dn0, x, mr0, bstats0};
     int nparts = 0;
-    int rc = hbf ? tc::launch_bwd_fused<1>(tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, lr, w1timg, ep, partial,
+    int rc = hbf ? tc::launch_bwd_fused(tc::TLoadNormBwdT<tc::bf16_t>{static_cast<const tc::bf16_t*>(dz1), static_cast<const tc::bf16_t*>(h1), bc1}, lr, w1timg, ep, partial,
                                    max_parts, N, P, 1, UB_WIDTH, single, &nparts, st)
-                 : tc::launch_bwd_fused<1>(tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, lr, w1timg, ep, partial,
+                 : tc::launch_bwd_fused(tc::TLoadNormBwd{static_cast<const float*>(dz1), static_cast<const float*>(h1), bc1}, lr, w1timg, ep, partial,
                                    max_parts, N, P, 1, UB_WIDTH, single, &nparts, st);
     if (rc != UB_OK) return rc;
     return launch_reduce_partials(partial, dw1, UB_WIDTH * UB_HID, nparts, st);

@@ -53,19 +53,12 @@ int tc_gemm2_fwd_residual(const void* h2, const Coef* coef2, const float* gate, 
                           float* out, double* stats, int N, int P, int single, int hbf, cudaStream_t st);
 int tc_gemm2_bwd(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, void* du, const void* h2,
                  const Coef* coef2, const MeanRstd* mr2, double* sums3, int N, int P, int single, int hbf, cudaStream_t st);
-int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                 const MeanRstd* mr0, double* bstats0, int N, int P, int single, int hbf, cudaStream_t st);
 int tc_wgrad2(const float* dout, const float* y, const BCoef* bc3, const void* h2, const Coef* coef2, const float* gate,
               float* partial, int max_parts, float* dw2, int N, int P, int single, int hbf, cudaStream_t st);
-int tc_wgrad1(const float* x, const Coef* coef0, const void* dz1, const void* h1, const BCoef* bc1, float* partial,
-              int max_parts, float* dw1, int N, int P, int single, int hbf, cudaStream_t st);
-// fused input-gradient + weight-gradient GEMMs (gemm_backend bits 3 / 4): one read of the shared operand tensors
-int tc_gemm2_bwd_fused(const float* dout, const float* y, const BCoef* bc3, const void* w2timg, float* du, const float* h2,
-                       const Coef* coef2, const MeanRstd* mr2, double* sums3, const float* gate, float* partial, int max_parts,
-                       float* dw2, int N, int P, int single, cudaStream_t st);
-int tc_gemm1_bwd_fused(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
-                       const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
-                       int P, int single, int hbf, cudaStream_t st);
+// expand convolution backward: dn0 + PreNorm-backward sums AND dW1 += dh1^T n0 in ONE kernel (one read of dz1, h1, x)
+int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* w1timg, float* dn0, const float* x,
+                 const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
+                 int P, int single, int hbf, cudaStream_t st);
 
 // dwconv_rows.cu (row-streaming depthwise kernels fed by TMA bulk copies; the backward one is fused: du, h2, h1 -> dz1 in one pass)
 int launch_dwconv_fwd(const void* h1, const Coef* coef1, const float* wdw, void* h2, double* stats2, int N, int H, int W, int hbf,

@@ -144,7 +144,8 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     L.B = d->B; L.Ne = d->B * d->T; L.P = d->H * d->W; L.nblk = 1 + d->n_dec_blocks;
     L.Nmax = L.Ne;
     // bf16 hidden storage needs the tcgen05 GEMMs (the CUDA-core comparators read fp32) and excludes the fused project-conv backward
-    if ((d->gemm_backend & 32) && ((d->gemm_backend & 3) != 3 || (d->gemm_backend & 16))) return UB_ERR_ARG;
+    if ((d->gemm_backend & 3) != 0 && (d->gemm_backend & 3) != 3) return UB_ERR_ARG;
+    if ((d->gemm_backend & 32) && (d->gemm_backend & 3) != 3) return UB_ERR_ARG;
     L.hes = (d->gemm_backend & 32) ? 2 : 4;
     const size_t P = (size_t)L.P;
     Bump b;
@@ -235,7 +236,8 @@ static int mbconv_forward(const BlockCtx& c, const float* x, double* next_stats,
     const BlockWs& w = *c.w;
     const int P = c.H * c.W;
     void* ws = c.ws;
-    const bool tcb = (c.backend & 1) != 0;
+    const bool tcb = (c.backend & 3) == 3;
+    if ((c.backend & 3) != 0 && !tcb) return UB_ERR_ARG;
     // forward operands (normalised activations, weights) take the fp16 hi/lo split (2^-22), see gemm_tc.cu: SPLIT_F16X3
     const int single = (c.backend & 4) ? 1 : 2;
     const int hbf = (c.backend & 32) != 0;
@@ -312,28 +314,20 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
     void* ws = c.ws;
     UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
-    const bool tcb = (c.backend & 1) != 0, tcw = (c.backend & 2) != 0;
+    const bool tcb = (c.backend & 3) == 3;                      // 3 = tcgen05 product path, 0 = fp32 CUDA-core comparator
+    if ((c.backend & 3) != 0 && !tcb) return UB_ERR_ARG;
     const int single = (c.backend & 4) != 0;
     const int hbf = (c.backend & 32) != 0;
-    if (hbf && (!tcb || !tcw || (c.backend & 16))) return UB_ERR_ARG;
+    if (hbf && !tcb) return UB_ERR_ARG;
     float* du_f = static_cast<float*>(du);                     // fp32 view for the CUDA-core comparators / the fused project kernel
     float* dz1_f = static_cast<float*>(dz1);
-    // input-gradient + weight-gradient GEMM of a convolution in one kernel: bit 3 = expand convolution (default: measured
-    // 10.1 -> 7.7 ms per step), bit 4 = project convolution (measured slower: 10.0 -> 11.0 ms, its GELU-heavy loader and epilogue
-    // do not shrink with the bytes)
-    const bool fused1 = tcb && tcw && (c.backend & 8) != 0, fused2 = tcb && tcw && (c.backend & 16) != 0;
-    if (fused2)
-        UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd_fused(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du_f, at<float>(ws, w.h2),
-                              at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), at<float>(ws, w.gate), partial,
-                              MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, c.st));
-    else if (tcb)
+    if (tcb)
         UB_PROF(KID_GEMM2_BWD, c.st, tc_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.w2timg), du, at<char>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, single, hbf, c.st));
     else
         UB_PROF(KID_GEMM2_BWD, c.st, simt_gemm2_bwd(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), pf(c.p, UB200_B_W2), du_f, at<float>(ws, w.h2),
                               at<Coef>(ws, w.coef2), at<MeanRstd>(ws, w.mr2), at<double>(ws, w.sums3), c.N, P, c.st));
-    if (fused2) {
-    } else if (tcw)
+    if (tcb)
         UB_PROF(KID_WGRAD2, c.st, tc_wgrad2(dout, at<float>(ws, w.y), at<BCoef>(ws, w.bc3), at<char>(ws, w.h2), at<Coef>(ws, w.coef2),
                            at<float>(ws, w.gate), partial, MAX_PARTS, gf(c.g, UB200_B_W2), c.N, P, single, hbf, c.st));
     else
@@ -347,22 +341,15 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                              at<Coef>(ws, w.coef2), at<BCoef>(ws, w.bc2), at<Coef>(ws, w.coef1), at<MeanRstd>(ws, w.mr1),
                              pf(c.p, UB200_B_WDW), dz1, at<double>(ws, w.bstats1), gf(c.g, UB200_B_WDW), c.N, c.H, c.W, hbf, c.st));
     UB_TRY(finalize_bwd(c, w.bstats1, UB200_B_N1_W, w.mr1, w.bc1, UB_HID));
-    if (fused1)
-        UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd_fused(dz1, at<char>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
-                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, MAX_PARTS, gf(c.g, UB200_B_W1), c.N, P, single, hbf, c.st));
-    else if (tcb)
+    if (tcb) {     // input gradient AND weight gradient of the expand convolution in one kernel (one read of dz1, h1, x)
         UB_PROF(KID_GEMM1_BWD, c.st, tc_gemm1_bwd(dz1, at<char>(ws, w.h1), at<BCoef>(ws, w.bc1), at<char>(ws, w.w1timg), dn0, x, at<MeanRstd>(ws, w.mr0),
-                              at<double>(ws, w.bstats0), c.N, P, single, hbf, c.st));
-    else
+                              at<double>(ws, w.bstats0), at<Coef>(ws, w.coef0), partial, MAX_PARTS, gf(c.g, UB200_B_W1), c.N, P, single, hbf, c.st));
+    } else {
         UB_PROF(KID_GEMM1_BWD, c.st, simt_gemm1_bwd(dz1_f, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), pf(c.p, UB200_B_W1), dn0, x, at<MeanRstd>(ws, w.mr0),
                               at<double>(ws, w.bstats0), c.N, P, c.st));
-    if (fused1) {
-    } else if (tcw)
-        UB_PROF(KID_WGRAD1, c.st, tc_wgrad1(x, at<Coef>(ws, w.coef0), dz1, at<char>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
-                           gf(c.g, UB200_B_W1), c.N, P, single, hbf, c.st));
-    else
         UB_PROF(KID_WGRAD1, c.st, simt_wgrad1(x, at<Coef>(ws, w.coef0), dz1_f, at<float>(ws, w.h1), at<BCoef>(ws, w.bc1), partial, MAX_PARTS,
                            gf(c.g, UB200_B_W1), c.N, P, c.st));
+    }
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
     UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.relu_mask_dx, c.st));
     return UB_OK;
@@ -402,19 +389,6 @@ int ub200_version(void) { return 100; }
 
 unsigned long long ub200_launch_count(void) { return g_launch_count; }
 
-// dW1[256][128] = sum_p dh1[p][o] * n0[p][k] with n0 = x*coef0 (x: [N*P][128]) and dh1 = a*dz1 + b*h1 + c ([N*P][256]):
-// the weight-gradient GEMM of the 1x1 expand convolution alone (unit tests).  dw1 is accumulated into.
-int ub200_wgrad1_forward(int backend, const float* x, const float* coef0, const float* dz1, const float* h1, const float* bc1,
-                         float* dw1, int N, int P, void* scratch, void* stream) {
-    if (!x || !coef0 || !dz1 || !h1 || !bc1 || !dw1 || !scratch || P % 64) return UB_ERR_ARG;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (backend & 2)
-        return tc_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
-                         static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, (backend & 4) != 0, 0, st);
-    return simt_wgrad1(x, reinterpret_cast<const Coef*>(coef0), dz1, h1, reinterpret_cast<const BCoef*>(bc1),
-                       static_cast<float*>(scratch), MAX_PARTS, dw1, N, P, st);
-}
-
 // h1[N*P][256] = (x[N*P][128] * scale + shift) . W1^T, stats[N][256][2] += column (sum, sumsq): the 1x1 expand GEMM alone
 // (unit tests and the roofline micro-benchmark).  coef: [N][128] (scale, shift) pairs; scratch: 256 KB.
 int ub200_gemm1_forward(int backend, const float* x, const float* coef, const float* w1, float* h1, double* stats, int N, int P,
@@ -422,7 +396,7 @@ int ub200_gemm1_forward(int backend, const float* x, const float* coef, const fl
     if (!x || !coef || !w1 || !h1 || !stats || !scratch || P % 128) return UB_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(stats, 0, (size_t)N * UB_HID * 2 * sizeof(double), st) != cudaSuccess) return UB_ERR_CUDA;
-    if (backend & 1) {
+    if ((backend & 3) == 3) {
         const int mode = (backend & 4) ? 1 : 2;
         UB_TRY(tc_prep_weights(w1, scratch, UB_HID, UB_WIDTH, 0, mode == 2, st));
         return tc_gemm1_fwd(x, reinterpret_cast<const Coef*>(coef), scratch, h1, stats, N, P, mode, 0, st);
@@ -554,7 +528,7 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
     for (int i = 1; i < L.nblk; ++i) {
         BlockCtx c = make_ctx(d, L, i, params, nullptr, ws, st);
         double* next_stats = i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr;
-        if (!d->training && !d->need_grad && d->dec_groups == 0 && (d->gemm_backend & 1))
+        if (!d->training && !d->need_grad && d->dec_groups == 0 && (d->gemm_backend & 3) == 3)
             UB_TRY(mbconv_forward_eval_bn(c, x, next_stats));
         else
             UB_TRY(mbconv_forward(c, x, next_stats, d->need_grad != 0));
