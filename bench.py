@@ -141,14 +141,15 @@ KERNEL_BYTES = {
 }
 
 
-def algorithmic_bytes(kernel, frames, P):
+def algorithmic_bytes(kernel, frames, P, hid_bytes=4):
+    """hid_bytes: bytes per element of the 256-channel hidden tensors (2 with gemm_backend flag 32)."""
     a, h = KERNEL_BYTES.get(kernel, (0, 0))
-    return (a * 128 * P * 4 + h * 256 * P * 4) * frames
+    return (a * 128 * P * 4 + h * 256 * P * hid_bytes) * frames
 
 
-def survey_bytes_per_sample(T, covdim, P, n_dec=5):
+def survey_bytes_per_sample(T, covdim, P, n_dec=5, hid_bytes=4):
     """SURVEY.md §8(d) byte model ("one HBM materialisation per normalisation barrier"): 12.06 GB / sample at T=3, diag, fp32."""
-    A, Hh = 128 * P * 4, 256 * P * 4
+    A, Hh = 128 * P * 4, 256 * P * hid_bytes
     mbconv = 15 * A + 13 * Hh
     return (T + n_dec) * mbconv + T * (5 * A + 5 * 15 * P * 4) + (3 * T + 2) * A + 3 * A + (52 + 2 * covdim) * P * 4
 
@@ -408,15 +409,16 @@ def main():
     n_dec = len(net.out_block)
     frames_step = args.batch * args.t + n_dec * args.batch
     P = args.hw * args.hw
-    bytes_total = algorithmic_bytes(top, frames_step * args.steps, P)
+    hb = 2 if ((args.backend or 0) & 32) else 4
+    bytes_total = algorithmic_bytes(top, frames_step * args.steps, P, hb)
     achieved = bytes_total / (tms.value / 1e3) / 1e9 if tms.value > 0 else 0.0
     tpf, tsrc = ncu_traffic_per_frame(top)
     traffic = int(tpf * frames_step * args.steps / max(tn.value, 1)) if tpf else None      # per launch, like algorithmic_bytes_per_launch
     # per-kernel fraction of the HBM roof from the profiled warm-up step, and what the classed kernels leave unattributed
-    kernel_fracs = {k: round(algorithmic_bytes(k, frames_step, P) / (v["ms"] / 1e3) / 1e9 / peak, 3)
+    kernel_fracs = {k: round(algorithmic_bytes(k, frames_step, P, hb) / (v["ms"] / 1e3) / 1e9 / peak, 3)
                     for k, v in breakdown.items() if algorithmic_bytes(k, 1, 1) > 0 and v["ms"] > 0}
     classed_ms = sum(v["ms"] for v in breakdown.values())
-    step_bytes = survey_bytes_per_sample(args.t, cov, P, n_dec) * args.batch
+    step_bytes = survey_bytes_per_sample(args.t, cov, P, n_dec, hb) * args.batch
     step_gbs = step_bytes / (ms_step / 1e3) / 1e9
     roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
