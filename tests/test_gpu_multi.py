@@ -50,3 +50,27 @@ def test_nccl_data_parallel_parity(tmp_path, golden_weights):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "nccl_parity.txt"), "w") as f:
         f.write("\n".join(lines + [f"reduced == mean of per-rank gradients on {world} ranks (rel_l2 <= 1e-6), identical across ranks"]) + "\n")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_model_on_a_non_current_device(golden_weights):
+    """the C ABI launches on the current device; the shim must switch to the tensors' device, and the per-device
+    'dynamic shared memory attribute set' caches must not leak from device 0 to device 1 (one process driving two GPUs)."""
+    import uncrtaints_b200 as ub
+    x, y, d = O.synthetic_batch(1, 2, 64, 64, seed=71)
+    keep = O.dropout_keep_mask(16, 1, 2, 64, 64, seed=72).to(torch.uint8)
+    outs, grads = [], []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)                      # the current device stays 0 throughout
+        net = ub.UNCRTAINTS(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", covmode="diag", scale_by=10.0)
+        net.load_state_dict({k: v.clone() for k, v in golden_weights.items()}, strict=True)
+        net = net.to(dev).train()
+        net._injected_keep_mask = keep
+        out = net(x.to(dev), batch_positions=d.to(dev))
+        loss, cov = ub.MultiGaussianNLLLoss(mode="diag", chunk=None)(out[:, :, :13], y.to(dev), out[:, :, 13:26])
+        loss.backward()
+        torch.cuda.synchronize(dev)
+        assert out.device == torch.device(dev) and cov.device == torch.device(dev)
+        outs.append(out.detach().cpu())
+        grads.append(net.in_block[0].conv.fn[0].weight.grad.cpu())
+    assert rel_l2(outs[1], outs[0]) < 1e-5 and rel_l2(grads[1], grads[0]) < 1e-4
