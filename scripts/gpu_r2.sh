@@ -39,6 +39,8 @@ ncu)
     [ "${NCU_SOURCE:-0}" = "1" ] && ncu -i gpurun_out/prof_$k.ncu-rep --page source --csv > gpurun_out/prof_${k}_source.csv 2>/dev/null
     [ "${NCU_KEEP:-0}" = "1" ] || rm -f gpurun_out/prof_$k.ncu-rep
   done ;;
+aux)
+  timeout 600 python scripts/bench_aux.py > gpurun_out/bench_aux.log 2>&1; tail -c 1500 gpurun_out/bench_aux.log ;;
 cfg3)
   timeout 900 python bench.py --steps 5 --warmup 3 --batch 32 --t 5 --no-cpu-baseline --no-eager-baseline --no-parity ${CFG3_ARGS} > gpurun_out/bench_cfg3.log 2>&1; python scripts/show_bench.py gpurun_out/bench_cfg3.log ;;
 esac
