@@ -243,3 +243,57 @@ def test_prepare_data_multi_on_gpu():
         x2, y2, m2, d2 = ub.prepare_data_multi(dev_batch, "cuda", cfg)
         torch.cuda.synchronize()
         assert torch.equal(x2.cpu(), want_x) and torch.equal(d2.cpu(), dates.cpu()) and torch.equal(m2.cpu(), m.cpu())
+
+
+@pytest.mark.parametrize("variant", [
+    dict(encoder_norm="batch", decoder_norm="group"),                 # the other norm assignment (get_norm_layer, uncrtaints.py:16-22)
+    dict(covmode=None, out_nonlin_mean=False, scale_by=1.0),           # no covariance head, identity mean, var_eps 1e-9 branch (:374)
+    dict(input_dim=13, positional_encoding=False, n_dec_blocks=2),     # no SAR channels (--use_sar off), no positional encoding, 2 decoder blocks
+    dict(covmode="iso", input_dim=15, n_dec_blocks=1),
+])
+def test_constructor_variants_vs_oracle(variant):
+    """Constructor combinations of UNCRTAINTS.__init__ (uncrtaints.py:231-254) beyond the CLI default, each against the fp64 oracle
+    with weights drawn by oracle.init_params (the distributions of weight_init): outputs, loss and every gradient within 1e-3."""
+    import uncrtaints_b200 as ub
+    cfg = O.OracleConfig(**variant)
+    p = O.init_params(cfg, seed=5)
+    B, T, H, W = 2, 3, 64, 64
+    x, y, d = O.synthetic_batch(B, T, H, W, cin=cfg.input_dim, scale_by=cfg.scale_by, seed=81)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=82)
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in p64.items()}
+    o_out = O.forward(leaf, x.double(), d.double() if cfg.positional_encoding else None, cfg, True, keep)
+    cov = cfg.covar_dim
+    if cov:
+        o_loss = O.mgnll(o_out[:, :, :13], y.double(), o_out[:, :, 13:13 + cov], cfg.covmode)
+    else:
+        o_loss = ((o_out - y.double()) ** 2).mean()
+    names = [k for k, v in leaf.items() if v.requires_grad]
+    o_grads = dict(zip(names, torch.autograd.grad(o_loss, [leaf[k] for k in names], allow_unused=True)))
+    net = ub.UNCRTAINTS(input_dim=cfg.input_dim, decoder_widths=[128] * cfg.n_dec_blocks, out_conv=[13 + cov],
+                        out_nonlin_mean=cfg.out_nonlin_mean, out_nonlin_var="softplus", encoder_norm=cfg.encoder_norm,
+                        decoder_norm=cfg.decoder_norm, positional_encoding=cfg.positional_encoding, covmode=cfg.covmode,
+                        scale_by=cfg.scale_by)
+    net.load_state_dict(p, strict=True)
+    net = net.cuda().train()
+    net._injected_keep_mask = keep.to(torch.uint8)
+    out = net(x.cuda(), batch_positions=d.cuda() if cfg.positional_encoding else None)
+    assert out.shape == o_out.shape
+    if cov:
+        loss, _ = ub.MultiGaussianNLLLoss(mode=cfg.covmode, chunk=None, covariance="none")(out[:, :, :13], y.cuda(), out[:, :, 13:13 + cov])
+    else:
+        loss = ((out - y.cuda()) ** 2).mean()
+    loss.backward()
+    assert rel_l2(out, o_out) <= 1e-3 and abs(loss.item() - o_loss.item()) <= 1e-3 * abs(o_loss.item())
+    scale = max(float(g.norm()) for g in o_grads.values() if g is not None)
+    worst = 0.0
+    for k, prm in net.named_parameters():
+        ref = o_grads[k] if o_grads[k] is not None else torch.zeros_like(leaf[k])
+        if float(ref.norm()) <= 1e-7 * scale:          # analytically zero (or numerically nothing): absolute check
+            assert float(prm.grad.double().norm().cpu()) <= 1e-5 * scale, k
+            continue
+        e = rel_l2(prm.grad, ref)
+        worst = max(worst, e)
+        assert e <= 1e-3, (k, e)
+    from conftest import report
+    report("parity_report.txt", [f"constructor variant {variant}: out rel_l2={rel_l2(out, o_out):.3e} worst grad rel_l2={worst:.3e}"])
