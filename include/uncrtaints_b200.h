@@ -45,6 +45,22 @@ enum {
     UB200_P_LTAE_E,        /* folded additive score term e [B][T][16]                               */
     UB200_P_OUT_W,         /* out_conv.conv.conv.0.weight [out_dim][128]             (uncrtaints.py:381) */
     UB200_P_OUT_B,         /* out_conv.conv.conv.0.bias   [out_dim]                                 */
+    /* use_v only (full LTAE2d value path + include_v; ltae.py:10-141, uncrtaints.py:324-338,414-417) */
+    UB200_P_LTAE_GN_W,     /* temporal_encoder.in_norm.weight [128]   (value path; the score path has it folded into Ap) */
+    UB200_P_LTAE_GN_B,     /* temporal_encoder.in_norm.bias   [128]                                 */
+    UB200_P_LTAE_WIN,      /* temporal_encoder.inconv.weight [256][128]                  (ltae.py:48) */
+    UB200_P_LTAE_BIN,      /* temporal_encoder.inconv.bias   [256]                                  */
+    UB200_P_LTAE_PE,       /* positional table [B][T][256] (positional_encoding.py:16-31; no gradient; NULL = none) */
+    UB200_P_LTAE_MLP_W,    /* temporal_encoder.mlp.0.weight [128][256]                   (ltae.py:78) */
+    UB200_P_LTAE_MLP_B,    /* temporal_encoder.mlp.0.bias   [128]                                   */
+    UB200_P_LTAE_BN_W,     /* temporal_encoder.mlp.1.* BatchNorm1d(128)                  (ltae.py:79) */
+    UB200_P_LTAE_BN_B,
+    UB200_P_LTAE_BN_RM,
+    UB200_P_LTAE_BN_RV,
+    UB200_P_LTAE_ON_W,     /* temporal_encoder.out_norm.* GroupNorm(16, 128)             (ltae.py:68-71) */
+    UB200_P_LTAE_ON_B,
+    UB200_P_INCV_W,        /* include_v.weight [128][256]: columns 0..127 act on the aggregated features, 128..255 on up(v) (uncrtaints.py:338,417) */
+    UB200_P_INCV_B,        /* include_v.bias   [128]                                                */
     UB200_P_BLOCK0         /* first MBConv block (in_block.0); block i starts at UB200_P_BLOCK0 + i*UB200_BLOCK_STRIDE;
                               blocks 1..n_dec_blocks are out_block.0 .. out_block.(n-1)              */
 };
@@ -95,6 +111,10 @@ typedef struct ub200_desc {
     float dropout_p;            /* 0.1 in training (uncrtaints.py:154), forced to 0 when !training */
     unsigned long long seed;    /* Philox seed / offset for the attention dropout (ignored when keep_mask != NULL) */
     unsigned long long offset;
+    int use_v;                  /* use_v (uncrtaints.py:252,300-314,414-417): full LTAE2d with a value output, include_v 1x1 convolution */
+    float v_dropout_p;          /* nn.Dropout on the MLP-processed values (ltae.py:17,85,129: 0.2), training only */
+    int is_mono;                /* is_mono (uncrtaints.py:253,296,418; `--pretrain`): T == 1, no temporal encoder / aggregator -- the encoder
+                                   output feeds the decoder; UB200_P_LTAE_* are unused */
 } ub200_desc;
 
 int ub200_version(void);
@@ -125,7 +145,8 @@ int ub200_num_param_slots(const ub200_desc* d);
 size_t ub200_workspace_bytes(const ub200_desc* d);
 
 /* Locate a named intermediate inside the workspace (tests / debugging): "x0", "pooled", "pool_idx", "attn",
- * "agg", "notpad", "blk<i>.h1|h2|y|out".  Returns 0 and fills offset/bytes, or UB200_ERR_ARG. */
+ * "agg", "notpad", "blk<i>.h1|h2|y|out", and with use_v "v.m" (MLP output [B*1024][128]), "v.mr" ((mean, rstd) of its BatchNorm1d, [B][128][2])
+ * and "v.v" (value output [B*1024][128]).  Returns 0 and fills offset/bytes, or UB200_ERR_ARG. */
 int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, size_t* bytes);
 
 /* UNCRTAINTS.forward (model/src/backbones/uncrtaints.py:391-446).
@@ -135,6 +156,9 @@ int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, s
  * BatchNorm running_mean / running_var in `params` are updated in place when d->training. */
 int ub200_forward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
                   float* output, void* workspace, size_t workspace_bytes, void* stream);
+/* Same with an explicit keep mask for the value dropout of the use_v path as well (uint8 [B*1024][128], ltae.py:129; tests). */
+int ub200_forward_v(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                    const unsigned char* v_keep_mask, float* output, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of UNCRTAINTS.forward (autograd of the reference, triggered at base_model.py:77).
  *   grad_output [B][1][out_dim][H][W]; output = the tensor ub200_forward produced;
@@ -143,6 +167,9 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
 int ub200_backward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
                    const float* output, const float* grad_output, void* const* grads, void* workspace,
                    size_t workspace_bytes, void* stream);
+int ub200_backward_v(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                     const unsigned char* v_keep_mask, const float* output, const float* grad_output, void* const* grads, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* MultiGaussianNLLLoss.forward -> multi_gaussian_nll_loss (model/src/losses.py:353,149-218), reduction='mean'.
  *   pred/target/var: base pointers of [B][1][13 | var_ch][H][W] tensors whose batch stride (in elements) is

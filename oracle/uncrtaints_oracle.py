@@ -51,6 +51,10 @@ class OracleConfig:
     dropout_p: float = 0.1          # Compact_Temporal_Aggregator.attn_dropout, uncrtaints.py:154
     bn_momentum: float = 0.1
     norm_eps: float = 1e-5
+    use_v: bool = False             # full LTAE2d with a value output + include_v (uncrtaints.py:300-314,414-417)
+    v_dropout_p: float = 0.2        # LTAE2d.dropout on the MLP-processed values (ltae.py:17,85,129)
+    is_mono: bool = False           # single date, no temporal encoder (uncrtaints.py:296,418)
+    separate_out: bool = False      # separate mean / variance output convolutions (uncrtaints.py:376-379,424-430)
 
     @property
     def covar_dim(self) -> int:      # uncrtaints.py:357-365
@@ -274,6 +278,60 @@ def ltae_tiny(down, batch_positions, pad_mask, p, cfg: OracleConfig) -> torch.Te
     return attn.reshape(b, h, w, nh, t).permute(3, 0, 4, 1, 2)                  # [nh,B,T,h,w] (ltae.py:233-235)
 
 
+def ltae_full(down, batch_positions, pad_mask, p, cfg: OracleConfig, training: bool, new_buffers=None, v_keep_mask=None,
+              v_relu_mask=None):
+    """LTAE2d.forward + MultiHeadAttention + ScaledDotProductAttention (ltae.py:96-141, 265-307, 400-416) as built by UNCRTAINTS for
+    ``use_v`` (use_dropout=False: no dropout on the attention; mlp=[256,128]; dropout 0.2 on the MLP output; return_att=True).
+    down: [B,T,C,h,w] -> (v [B,128,h,w], attn [n_head,B,T,h,w]).  ``v_keep_mask`` [B*h*w,128]: keep mask of the value dropout.
+    ``v_relu_mask`` [B*h*w,128] (diagnostic, like ``pool_idx`` of `forward`): impose the active set of the MLP's ReLU.  The ReLU
+    sits between a BatchNorm and a GroupNorm over groups of 8 channels; about 2 of the 262k pre-activations of a B=2 batch lie
+    within fp32 rounding (1e-5) of zero, an fp32 implementation decides those differently from fp64, and where the rest of the
+    group is zero the GroupNorm multiplies that element's gradient by up to 1/sqrt(eps) = 316: ONE such flip moves every
+    temporal-encoder and encoder gradient by 1e-3..7e-3 (measured by shifting the threshold by +-1e-5 in fp64), although the
+    forward output changes by < 1e-7.  Imposing the implementation's own mask separates this discrete effect from arithmetic error."""
+    pre = "temporal_encoder."
+    b, t, c, h, w = down.shape
+    nh, dk = cfg.n_head, cfg.d_k
+    n = b * h * w
+    seq = down.permute(0, 3, 4, 2, 1).reshape(n, c, t)                                      # [N, C, T]  (ltae.py:102-103)
+    seq = group_norm(seq, nh, p[pre + "in_norm.weight"], p[pre + "in_norm.bias"], cfg.norm_eps)
+    z = torch.einsum("nct,dc->ndt", seq, p[pre + "inconv.weight"][:, :, 0]) + p[pre + "inconv.bias"].reshape(1, -1, 1)
+    if cfg.positional_encoding:
+        pe = positional_table(batch_positions, cfg.d_model // nh, 1000.0, nh)
+        pe = pe.reshape(b, 1, t, cfg.d_model).expand(b, h * w, t, cfg.d_model).reshape(n, t, cfg.d_model)
+        z = z + pe.permute(0, 2, 1)
+    zt = z.permute(0, 2, 1)                                                                  # [N, T, d_model]
+    key = zt @ p[pre + "attention_heads.fc1_k.weight"].t() + p[pre + "attention_heads.fc1_k.bias"]      # ltae.py:276
+    key = key.reshape(n, t, nh, dk)
+    score = torch.einsum("nthd,hd->nht", key, p[pre + "attention_heads.Q"]) / math.sqrt(dk)               # ltae.py:404-405
+    if pad_mask is not None:
+        pm = pad_mask.reshape(b, 1, 1, t).expand(b, h * w, 1, t).reshape(n, 1, t)
+        score = score.masked_fill(pm, -1e3)                                                  # ltae.py:407
+    attn = torch.softmax(score, dim=-1)                                                      # [N, nh, T]
+    val = zt.reshape(n, t, nh, cfg.d_model // nh)                                            # heads = consecutive channel slices (ltae.py:286)
+    out = torch.einsum("nht,nthe->nhe", attn, val).reshape(n, cfg.d_model)                   # concatenated heads (ltae.py:124-126)
+    m = out @ p[pre + "mlp.0.weight"].t() + p[pre + "mlp.0.bias"]
+    # nn.BatchNorm1d over the N rows (ltae.py:79)
+    k = pre + "mlp.1."
+    if training:
+        mu = m.mean(dim=0)
+        var = ((m - mu) ** 2).mean(dim=0)
+        if new_buffers is not None:
+            unbiased = var.detach() * (n / max(n - 1, 1))
+            new_buffers[k + "running_mean"] = (1 - cfg.bn_momentum) * p[k + "running_mean"] + cfg.bn_momentum * mu.detach()
+            new_buffers[k + "running_var"] = (1 - cfg.bn_momentum) * p[k + "running_var"] + cfg.bn_momentum * unbiased
+    else:
+        mu, var = p[k + "running_mean"], p[k + "running_var"]
+    m = (m - mu) / torch.sqrt(var + cfg.norm_eps) * p[k + "weight"] + p[k + "bias"]
+    m = torch.relu(m) if v_relu_mask is None else m * v_relu_mask.to(m.dtype)
+    if training and cfg.v_dropout_p > 0:
+        assert v_keep_mask is not None, "train-mode use_v oracle needs an explicit value-dropout keep mask"
+        m = m * v_keep_mask.to(m.dtype) / (1.0 - cfg.v_dropout_p)
+    v = group_norm(m, nh, p[pre + "out_norm.weight"], p[pre + "out_norm.bias"], cfg.norm_eps)            # ltae.py:131
+    v = v.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+    return v, attn.reshape(b, h, w, nh, t).permute(3, 0, 4, 1, 2)
+
+
 def aggregate(x, attn, pad_mask, training, cfg: OracleConfig, keep_mask=None) -> torch.Tensor:
     """Compact_Temporal_Aggregator, mode 'att_group' (uncrtaints.py:156-210).
     x: [B,T,C,H,W], attn: [nh,B,T,h,w].  ``keep_mask`` [nh,B,T,H,W] (bool / 0-1) is the
@@ -321,7 +379,8 @@ def gather_pool(x: torch.Tensor, idx: torch.Tensor, out_hw: int = ATT_DOWN) -> t
 def forward(p: Dict[str, torch.Tensor], x: torch.Tensor, batch_positions: Optional[torch.Tensor],
             cfg: OracleConfig, training: bool = True, keep_mask: Optional[torch.Tensor] = None,
             new_buffers: Optional[dict] = None, taps: Optional[dict] = None,
-            pool_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+            pool_idx: Optional[torch.Tensor] = None, v_keep_mask: Optional[torch.Tensor] = None,
+            v_relu_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """UNCRTAINTS.forward (uncrtaints.py:391-446).  x: [B,T,C_in,H,W] -> [B,1,13+covdim,H,W].
     ``pool_idx`` (int64 [B*T,128,32,32], diagnostic): impose the max-pool index selection, see `gather_pool`."""
     b, t, cin, H, W = x.shape
@@ -335,17 +394,34 @@ def forward(p: Dict[str, torch.Tensor], x: torch.Tensor, batch_positions: Option
     for i in range(cfg.n_enc_blocks):
         f = mbconv(f, p, f"in_block.{i}.", cfg.encoder_norm, training, cfg, new_buffers, taps)
     c = f.shape[1]
-    down, idx = adaptive_max_pool(f, ATT_DOWN)                                   # :403-404
-    if pool_idx is not None:
-        down, idx = gather_pool(f, pool_idx, ATT_DOWN), pool_idx
-    attn = ltae_tiny(down.reshape(b, t, c, ATT_DOWN, ATT_DOWN), batch_positions, pad_mask, p, cfg)
-    agg = aggregate(f.reshape(b, t, c, H, W), attn, pad_mask, training, cfg, keep_mask)
-    if taps is not None:
-        taps["pool_idx"], taps["down"], taps["attn"], taps["agg"] = idx, down, attn, agg
-    f = agg
+    if cfg.is_mono:                                                              # :418 (needs T == 1)
+        assert t == 1
+    else:
+        down, idx = adaptive_max_pool(f, ATT_DOWN)                               # :403-404
+        if pool_idx is not None:
+            down, idx = gather_pool(f, pool_idx, ATT_DOWN), pool_idx
+        if cfg.use_v:
+            v, attn = ltae_full(down.reshape(b, t, c, ATT_DOWN, ATT_DOWN), batch_positions, pad_mask, p, cfg, training, new_buffers,
+                                v_keep_mask, v_relu_mask)
+        else:
+            attn = ltae_tiny(down.reshape(b, t, c, ATT_DOWN, ATT_DOWN), batch_positions, pad_mask, p, cfg)
+        agg = aggregate(f.reshape(b, t, c, H, W), attn, pad_mask, training, cfg, keep_mask)
+        if taps is not None:
+            taps["pool_idx"], taps["down"], taps["attn"], taps["agg"] = idx, down, attn, agg
+        f = agg
+        if cfg.use_v:                                                            # :414-417
+            up_v = bilinear_upsample(v, H, W)
+            f = conv1x1(torch.cat([f, up_v], dim=1), p["include_v.weight"], p["include_v.bias"])
+            if taps is not None:
+                taps["v"], taps["mix"] = v, f
     for i in range(cfg.n_dec_blocks):
         f = mbconv(f, p, f"out_block.{i}.", cfg.decoder_norm, training, cfg, new_buffers, taps)
-    o = conv1x1(f, p["out_conv.conv.conv.0.weight"], p["out_conv.conv.conv.0.bias"])   # :381,432
+    if cfg.separate_out:                                                         # :376-379,424-430
+        o = conv1x1(f, p["out_conv_mean_1.conv.conv.0.weight"], p["out_conv_mean_1.conv.conv.0.bias"])
+        if cfg.covar_dim > 0:
+            o = torch.cat([o, conv1x1(f, p["out_conv_var_1.conv.conv.0.weight"], p["out_conv_var_1.conv.conv.0.bias"])], dim=1)
+    else:
+        o = conv1x1(f, p["out_conv.conv.conv.0.weight"], p["out_conv.conv.conv.0.bias"])   # :381,432
     if new_buffers is not None and training:
         for k in p:
             if k.endswith("num_batches_tracked"):
@@ -551,27 +627,50 @@ def init_params(cfg: OracleConfig, seed: int = 1) -> Dict[str, torch.Tensor]:
     for i in range(cfg.n_enc_blocks):
         block(f"in_block.{i}.", cfg.encoder_norm)
     t = "temporal_encoder."
-    p[t + "inconv.weight"] = torch.randn(cfg.d_model, w, 1, generator=g)
-    p[t + "inconv.bias"] = torch.randn(cfg.d_model, generator=g)
-    p[t + "attention_heads.Q"] = torch.randn(cfg.n_head, cfg.d_k, generator=g) * math.sqrt(2.0 / cfg.d_k)
-    p[t + "attention_heads.fc1_k.weight"] = xavier((cfg.n_head * cfg.d_k, cfg.d_model))
-    p[t + "attention_heads.fc1_k.bias"] = torch.randn(cfg.n_head * cfg.d_k, generator=g)
-    p[t + "in_norm.weight"] = torch.ones(w)
-    p[t + "in_norm.bias"] = torch.zeros(w)
+    if not cfg.is_mono:
+        p[t + "inconv.weight"] = torch.randn(cfg.d_model, w, 1, generator=g)
+        p[t + "inconv.bias"] = torch.randn(cfg.d_model, generator=g)
+        p[t + "attention_heads.Q"] = torch.randn(cfg.n_head, cfg.d_k, generator=g) * math.sqrt(2.0 / cfg.d_k)
+        p[t + "attention_heads.fc1_k.weight"] = xavier((cfg.n_head * cfg.d_k, cfg.d_model))
+        p[t + "attention_heads.fc1_k.bias"] = torch.randn(cfg.n_head * cfg.d_k, generator=g)
+        # GroupNorm affine parameters are left at (1, 0) by weight_init; perturbed here so that their gradients are exercised
+        p[t + "in_norm.weight"] = torch.ones(w) + (0.2 * torch.randn(w, generator=g) if cfg.use_v else 0.0)
+        p[t + "in_norm.bias"] = torch.zeros(w) + (0.2 * torch.randn(w, generator=g) if cfg.use_v else 0.0)
+    if cfg.use_v:                                       # LTAE2d extras + include_v (ltae.py:68-85, uncrtaints.py:338)
+        p[t + "out_norm.weight"] = torch.ones(w) + 0.2 * torch.randn(w, generator=g)
+        p[t + "out_norm.bias"] = 0.2 * torch.randn(w, generator=g)
+        p[t + "mlp.0.weight"] = xavier((w, cfg.d_model))
+        p[t + "mlp.0.bias"] = torch.randn(w, generator=g)
+        norm(t + "mlp.1.", w, "batch")
+        p["include_v.weight"] = xavier((w, 2 * w, 1, 1))
+        p["include_v.bias"] = torch.randn(w, generator=g)
     for i in range(cfg.n_dec_blocks):
         block(f"out_block.{i}.", cfg.decoder_norm)
-    p["out_conv.conv.conv.0.weight"] = xavier((cfg.out_dim, w, 1, 1))
-    p["out_conv.conv.conv.0.bias"] = torch.randn(cfg.out_dim, generator=g)
+    if cfg.separate_out:
+        p["out_conv_mean_1.conv.conv.0.weight"] = xavier((S2_BANDS, w, 1, 1))
+        p["out_conv_mean_1.conv.conv.0.bias"] = torch.randn(S2_BANDS, generator=g)
+        if cfg.covar_dim > 0:
+            p["out_conv_var_1.conv.conv.0.weight"] = xavier((cfg.covar_dim, w, 1, 1))
+            p["out_conv_var_1.conv.conv.0.bias"] = torch.randn(cfg.covar_dim, generator=g)
+    else:
+        p["out_conv.conv.conv.0.weight"] = xavier((cfg.out_dim, w, 1, 1))
+        p["out_conv.conv.conv.0.bias"] = torch.randn(cfg.out_dim, generator=g)
     return p
 
 
+def value_keep_mask(b: int, h: int = ATT_DOWN, w: int = ATT_DOWN, c: int = 128, p: float = 0.2, seed: int = 987):
+    """Bernoulli keep mask of LTAE2d.dropout on the [B*h*w, 128] MLP output (ltae.py:129)."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    return torch.rand(b * h * w, c, generator=g) >= p
+
+
 def step(p: Dict[str, torch.Tensor], x, y, dates, cfg: OracleConfig, training=True, keep_mask=None, loss_name: str = "MGNLL",
-         pool_idx=None):
+         pool_idx=None, v_keep_mask=None, v_relu_mask=None):
     """One fwd + loss (MGNLL, or GNLL for `--loss GNLL`) + bwd of the oracle.  Returns (out, loss, grads dict, new BN buffers)."""
     leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
             for k, v in p.items()}
     new_buffers: dict = {}
-    out = forward(leaf, x, dates, cfg, training, keep_mask, new_buffers, None, pool_idx)
+    out = forward(leaf, x, dates, cfg, training, keep_mask, new_buffers, None, pool_idx, v_keep_mask, v_relu_mask)
     if loss_name == "GNLL":
         loss, _ = gnll(out[:, :, :S2_BANDS], y, out[:, :, S2_BANDS:S2_BANDS + cfg.covar_dim], full=True)
     else:

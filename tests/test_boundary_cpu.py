@@ -71,10 +71,33 @@ def test_state_dict_surface_matches_reference():
 def test_unsupported_configurations_raise():
     import uncrtaints_b200 as ub
     kw = dict(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
-    for bad in (dict(block_type="residual"), dict(use_v=True), dict(is_mono=True), dict(n_head=4), dict(encoder_widths=[64]),
+    for bad in (dict(block_type="residual"), dict(n_head=4), dict(encoder_widths=[64]),
                 dict(agg_mode="mean"), dict(out_nonlin_var="relu"), dict(out_conv=[13])):
         with pytest.raises(NotImplementedError):
             ub.UNCRTAINTS(**{**kw, **bad})
+
+
+def test_variant_module_trees_match_the_reference_state_dict():
+    """use_v / is_mono / separate_out build the reference's module tree: same keys, same order, same shapes (checkpoints and
+    weight_init interoperate).  Needs /root/reference for the comparison; the key lists of the variants are also pinned by
+    oracle.init_params, which the fixtures of tests/golden/make_variants.py were generated with."""
+    import uncrtaints_b200 as ub
+    from oracle import ref_import, uncrtaints_oracle as O
+    kw = dict(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
+    for var in (dict(use_v=True), dict(is_mono=True), dict(separate_out=True), dict(separate_out=True, covmode=None, out_conv=[13])):
+        net = ub.UNCRTAINTS(**{**kw, **var})
+        cfg = O.OracleConfig(use_v=var.get("use_v", False), is_mono=var.get("is_mono", False), separate_out=var.get("separate_out", False),
+                             covmode=var.get("covmode", "diag"))
+        mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        assert mine == {k: tuple(v.shape) for k, v in O.init_params(cfg).items()}
+        if ref_import.available():
+            U, _, winit = ref_import.load()
+            ref = U.UNCRTAINTS(**{**kw, **var})
+            assert list(ref.state_dict().keys()) == list(net.state_dict().keys())
+            assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == mine
+            ref.apply(winit)
+            net.apply(winit)                              # isinstance dispatch of weight_init works on the holders
+            net.load_state_dict(ref.state_dict(), strict=True)
 
 
 def test_cpu_tensors_are_rejected_not_emulated():
@@ -143,7 +166,7 @@ def test_install_patches_reference_factory_and_loss():
             import uncrtaints_b200 as ub
             from src import losses as ref_losses
             from src.backbones import uncrtaints as ref_uncrtaints
-            saved = (ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss)     # restored below: other tests use the reference
+            saved = (ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss, ref_losses.GaussianNLLLoss)     # restored below: other tests use the reference
             ub.install(verbose=False)
             from src import model_utils                                # model_utils chdirs into ./model if it exists
             assert ref_uncrtaints.UNCRTAINTS is ub.UNCRTAINTS
@@ -171,7 +194,7 @@ def test_install_patches_reference_factory_and_loss():
     finally:
         os.chdir(cwd)
         if saved is not None:
-            ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss = saved
+            ref_uncrtaints.UNCRTAINTS, ref_losses.MultiGaussianNLLLoss, ref_losses.GaussianNLLLoss = saved
 
 
 def test_prepare_data_multi_matches_the_reference(tmp_path):

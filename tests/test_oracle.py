@@ -241,3 +241,67 @@ def test_oracle_img_metrics_match_live_reference():
     got = O.img_metrics(t, p, v)
     for k in ("RMSE", "MAE", "PSNR", "SAM", "SSIM", "error", "mean ae", "mean se", "mean var"):
         assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, got[k], want[k])
+
+
+# ---- constructor variants use_v / is_mono / separate_out (uncrtaints.py:296-338,376-379,414-430) ----
+from variants import VARIANTS, variant_inputs, reference_model  # noqa: E402
+
+
+def _variant_oracle_step(kw):
+    cfg, p, x, y, d, keep, vkeep = variant_inputs(kw)
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    out, loss, grads, newbuf = O.step(p64, x.double(), y.double(), d.double() if cfg.positional_encoding else None, cfg, True, keep,
+                                      v_keep_mask=vkeep)
+    return cfg, p, out, loss, grads, newbuf
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_oracle_variants_match_fixture(name):
+    """The oracle against case_variants.npz (unmodified reference in fp64, tests/golden/make_variants.py)."""
+    c = load_npz("case_variants.npz")
+    cfg, p, out, loss, grads, _ = _variant_oracle_step(VARIANTS[name])
+    assert rel_l2(out, torch.from_numpy(c[name + ".out"])) < 1e-6
+    assert abs(loss.item() - float(c[name + ".loss"])) / abs(float(c[name + ".loss"])) < 1e-9
+    scale = max(float(np.linalg.norm(c[k])) for k in c if k.startswith(name + ".grad."))
+    for k, g in grads.items():
+        ref = torch.from_numpy(c[name + ".grad." + k])
+        if float(ref.norm()) <= 1e-7 * scale:
+            assert float(g.norm()) <= 1e-6 * scale, k
+        else:
+            assert rel_l2(g, ref) < 1e-5, k
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_oracle_variants_match_live_reference_fp64(name):
+    U, Lm, _ = ref_import.load()
+    cfg, p, x, y, d, keep, vkeep = variant_inputs(VARIANTS[name])
+    m = reference_model(U, cfg, p, keep, vkeep).double().train()
+    out = m(x.double(), batch_positions=d.double())
+    loss, _ = Lm.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=cfg.covmode, chunk=None)(
+        out[:, :, :13], y.double(), out[:, :, 13:13 + cfg.covar_dim])
+    loss.backward()
+    _, _, o_out, o_loss, o_g, o_buf = _variant_oracle_step(VARIANTS[name])
+    assert rel_l2(o_out, out) < 1e-12
+    assert abs(o_loss.item() - loss.item()) / abs(loss.item()) < 1e-10
+    scale = max(float(q.grad.norm()) for q in m.parameters() if q.grad is not None)
+    for k, q in m.named_parameters():
+        ref = q.grad if q.grad is not None else torch.zeros_like(q)
+        if float(ref.norm()) <= 1e-9 * scale:
+            assert float(o_g[k].norm()) <= 1e-8 * scale, k
+        else:
+            assert rel_l2(o_g[k], ref) < 1e-9, k
+    sd = m.state_dict()
+    for k, v in o_buf.items():                        # BatchNorm running statistics incl. the BatchNorm1d of the use_v MLP
+        assert torch.allclose(v.double(), sd[k].double(), rtol=1e-10, atol=1e-12), k
+    # eval mode (running statistics, no dropout: put real nn.Dropout modules back, the injected stand-ins ignore .training)
+    if not cfg.is_mono:
+        m.temporal_aggregator.attn_dropout = torch.nn.Dropout(cfg.dropout_p)
+    if cfg.use_v:
+        m.temporal_encoder.dropout = torch.nn.Dropout(cfg.v_dropout_p)
+    m.eval()
+    with torch.no_grad():
+        e_ref = m(x.double(), batch_positions=d.double())
+    p_eval = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    e_or = O.forward(p_eval, x.double(), d.double() if cfg.positional_encoding else None, cfg, training=False)
+    assert rel_l2(e_or, e_ref) < 1e-12

@@ -11,8 +11,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libuncrtaints_b200.so")
 
-UB200_P_IN_W, UB200_P_IN_B, UB200_P_IN_NORM_W, UB200_P_IN_NORM_B, UB200_P_IN_NORM_RM, UB200_P_IN_NORM_RV, \
-    UB200_P_LTAE_AP, UB200_P_LTAE_E, UB200_P_OUT_W, UB200_P_OUT_B, UB200_P_BLOCK0 = range(11)
+(UB200_P_IN_W, UB200_P_IN_B, UB200_P_IN_NORM_W, UB200_P_IN_NORM_B, UB200_P_IN_NORM_RM, UB200_P_IN_NORM_RV,
+ UB200_P_LTAE_AP, UB200_P_LTAE_E, UB200_P_OUT_W, UB200_P_OUT_B,
+ UB200_P_LTAE_GN_W, UB200_P_LTAE_GN_B, UB200_P_LTAE_WIN, UB200_P_LTAE_BIN, UB200_P_LTAE_PE, UB200_P_LTAE_MLP_W, UB200_P_LTAE_MLP_B,
+ UB200_P_LTAE_BN_W, UB200_P_LTAE_BN_B, UB200_P_LTAE_BN_RM, UB200_P_LTAE_BN_RV, UB200_P_LTAE_ON_W, UB200_P_LTAE_ON_B,
+ UB200_P_INCV_W, UB200_P_INCV_B, UB200_P_BLOCK0) = range(26)
 (UB200_B_N0_W, UB200_B_N0_B, UB200_B_N0_RM, UB200_B_N0_RV, UB200_B_W1, UB200_B_N1_W, UB200_B_N1_B, UB200_B_N1_RM,
  UB200_B_N1_RV, UB200_B_WDW, UB200_B_N2_W, UB200_B_N2_B, UB200_B_N2_RM, UB200_B_N2_RV, UB200_B_F1, UB200_B_F2, UB200_B_W2,
  UB200_B_N3_W, UB200_B_N3_B, UB200_B_N3_RM, UB200_B_N3_RV, UB200_BLOCK_STRIDE) = range(22)
@@ -24,7 +27,7 @@ ERRORS = {-1: "UB200_ERR_ARG (unsupported shape / configuration)", -2: "UB200_ER
 SYMBOLS = [
     "ub200_version", "ub200_launch_count", "ub200_prof_enable", "ub200_prof_num_kernels", "ub200_prof_kernel_name",
     "ub200_prof_read", "ub200_gemm1_forward", "ub200_num_param_slots", "ub200_workspace_bytes", "ub200_workspace_tap", "ub200_forward",
-    "ub200_backward", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_mgnll_none", "ub200_gnll_none", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
+    "ub200_backward", "ub200_forward_v", "ub200_backward_v", "ub200_mgnll_forward", "ub200_gnll_forward", "ub200_mgnll_none", "ub200_gnll_none", "ub200_scale_by_scalar", "ub200_covariance", "ub200_mbconv_workspace_bytes",
     "ub200_mbconv_forward", "ub200_mbconv_backward", "ub200_head_forward", "ub200_head_backward", "ub200_adam_step", "ub200_img_metrics", "ub200_assemble_input",
 ]
 
@@ -38,6 +41,7 @@ class Desc(C.Structure):
         ("scale_by", C.c_float), ("var_eps", C.c_float), ("pad_value", C.c_float), ("norm_eps", C.c_float),
         ("bn_momentum", C.c_float), ("dropout_p", C.c_float),
         ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("use_v", C.c_int), ("v_dropout_p", C.c_float), ("is_mono", C.c_int),
     ]
 
 
@@ -71,6 +75,8 @@ def lib() -> C.CDLL:
     L.ub200_workspace_tap.argtypes = [dp, C.c_char_p, C.POINTER(sz), C.POINTER(sz)]
     L.ub200_forward.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, sz, vp]
     L.ub200_backward.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, C.POINTER(vp), vp, sz, vp]
+    L.ub200_forward_v.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, vp, sz, vp]
+    L.ub200_backward_v.argtypes = [dp, vp, C.POINTER(vp), vp, vp, vp, vp, C.POINTER(vp), vp, sz, vp]
     L.ub200_mgnll_forward.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, f, vp, vp, vp, vp, vp, vp]
     L.ub200_gnll_forward.argtypes = [vp, ll, vp, ll, vp, ll, i, i, f, i, vp, vp, vp, vp, vp, vp, vp]
     L.ub200_mgnll_none.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, f, vp, vp, vp, vp, vp, vp]

@@ -127,6 +127,28 @@ class LTAE2dtiny(_Holder):
         self.in_norm = nn.GroupNorm(num_groups=n_head, num_channels=in_channels)
 
 
+class MultiHeadAttention(MultiHeadAttentionSmall):
+    """Same parameters as the Small form (ltae.py:244-262); the dropout on the attention is 0 in UNCRTAINTS (use_dropout=False)."""
+
+
+class LTAE2d(_Holder):
+    """Full L-TAE of the ``use_v`` variant (ltae.py:10-94): keys ``inconv``, ``attention_heads``, ``in_norm``, ``out_norm``,
+    ``mlp.0`` (Linear 256->128), ``mlp.1`` (BatchNorm1d)."""
+
+    def __init__(self, in_channels: int, n_head: int, d_k: int, d_model: int, mlp: List[int], positional_encoding: bool,
+                 dropout: float = 0.2, T: int = 1000):
+        super().__init__()
+        assert mlp[0] == d_model and len(mlp) == 2
+        self.in_channels, self.n_head, self.d_model, self.T = in_channels, n_head, d_model, T
+        self.inconv = nn.Conv1d(in_channels, d_model, 1)
+        self.use_positional_encoding = positional_encoding
+        self.attention_heads = MultiHeadAttention(n_head=n_head, d_k=d_k, d_in=d_model)
+        self.in_norm = nn.GroupNorm(num_groups=n_head, num_channels=in_channels)
+        self.out_norm = nn.GroupNorm(num_groups=n_head, num_channels=mlp[-1])
+        self.mlp = nn.Sequential(nn.Linear(mlp[0], mlp[1]), nn.BatchNorm1d(mlp[1]), nn.ReLU())
+        self.dropout = nn.Dropout(dropout)
+
+
 class Compact_Temporal_Aggregator(_Holder):
     """Holds the dropout module of the aggregator (uncrtaints.py:149-154); its ``p`` is honoured."""
 
@@ -136,12 +158,14 @@ class Compact_Temporal_Aggregator(_Holder):
         self.attn_dropout = nn.Dropout(0.1)
 
 
-def fold_ltae(te: LTAE2dtiny, batch_positions: Optional[torch.Tensor], B: int, T: int, device) -> tuple:
+def fold_ltae(te, batch_positions: Optional[torch.Tensor], B: int, T: int, device, with_pe: bool = False) -> tuple:
     """Fold the input-independent query into the key projection (differentiable, weights only).
 
     Reference chain (ltae.py:210-224,347-350,432-433): score = Q_h . (W_k (W_in gn(x) + b_in + pe) + b_k)_h / 2.
     Returns Ap [16,128] = (Ak W_in) diag(gamma) and e [B,T,16] = pe Ak^T + t-independent constants, such that
     score[h,t] = (Ap[h] . x_hat[:,t] + e[b,t,h]) / 2 with x_hat the affine-free GroupNorm of the pooled features.
+    The full LTAE2d of the ``use_v`` variant computes the same scores (ltae.py:103-120,276-286,404-407); ``with_pe`` also
+    returns the positional table [B,T,256] its value path adds to the projected features (ltae.py:107-116).
     """
     mh = te.attention_heads
     nh, dk = mh.n_head, mh.d_k
@@ -150,6 +174,7 @@ def fold_ltae(te: LTAE2dtiny, batch_positions: Optional[torch.Tensor], B: int, T
     a = ak @ te.inconv.weight[:, :, 0]                          # [16,128]
     ap = a * te.in_norm.weight[None, :]
     const = ak @ te.inconv.bias + (mh.Q * mh.fc1_k.bias.view(nh, dk)).sum(dim=1) + a @ te.in_norm.bias   # [16]
+    pe = None
     if te.use_positional_encoding and batch_positions is not None:
         d = te.d_model // nh
         # PositionalEncoder (positional_encoding.py:11-13,20-29): float32 denominators, even->sin, odd->cos, tiled x n_head
@@ -160,6 +185,8 @@ def fold_ltae(te: LTAE2dtiny, batch_positions: Optional[torch.Tensor], B: int, T
         e = pe @ ak.t() + const[None, None, :]
     else:
         e = const[None, None, :].expand(B, T, nh)
+    if with_pe:
+        return ap.contiguous(), e.contiguous(), (pe.detach().contiguous() if pe is not None else None)
     return ap.contiguous(), e.contiguous()
 
 
@@ -167,9 +194,9 @@ class _UncrtaintsFunction(torch.autograd.Function):
     """forward/backward through ub200_forward / ub200_backward."""
 
     @staticmethod
-    def forward(ctx, net, x, keep_mask, need_grad, *tensors):
+    def forward(ctx, net, x, keep_mask, need_grad, extra_buffers, v_keep_mask, *tensors):
         L = _lib.lib()
-        desc, slots, buffers = net._describe(x, need_grad)
+        desc, slots, buffers = net._describe(x, need_grad, extra_buffers)
         table = [0] * len(net._slot_names)
         for slot, t in zip(slots, tensors):
             table[slot] = t.data_ptr()
@@ -188,13 +215,14 @@ class _UncrtaintsFunction(torch.autograd.Function):
             out = torch.empty((desc.B, 1, desc.out_dim, desc.H, desc.W), dtype=torch.float32, device=x.device)
             stream = torch.cuda.current_stream(x.device).cuda_stream
             params = _lib.ptr_table(table)
-            _lib.check(L.ub200_forward(desc, x.data_ptr(), params, keep_mask.data_ptr() if keep_mask is not None else None,
-                                       out.data_ptr(), ws.data_ptr(), ws_bytes, stream), "ub200_forward")
+            _lib.check(L.ub200_forward_v(desc, x.data_ptr(), params, keep_mask.data_ptr() if keep_mask is not None else None,
+                                         v_keep_mask.data_ptr() if v_keep_mask is not None else None,
+                                         out.data_ptr(), ws.data_ptr(), ws_bytes, stream), "ub200_forward")
         if net.keep_workspace:
             net._last_workspace = (desc, ws)
         if need_grad:
             ctx.net, ctx.desc, ctx.ws, ctx.table, ctx.slots = net, desc, ws, table, slots
-            ctx.keep_mask = keep_mask
+            ctx.keep_mask, ctx.v_keep_mask, ctx.extra_buffers = keep_mask, v_keep_mask, extra_buffers
             ctx.save_for_backward(x, out, *tensors)
         return out
 
@@ -229,21 +257,24 @@ class _UncrtaintsFunction(torch.autograd.Function):
             gtable[slot] = v.data_ptr()
             views.append(v.view_as(t))
             off += n
-        km = ctx.keep_mask
+        km, vkm = ctx.keep_mask, ctx.v_keep_mask
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(L.ub200_backward(ctx.desc, x.data_ptr(), _lib.ptr_table(ctx.table), km.data_ptr() if km is not None else None,
-                                        out.data_ptr(), grad_out.data_ptr(), _lib.ptr_table(gtable), ctx.ws.data_ptr(),
-                                        ctx.ws.numel(), stream), "ub200_backward")
+            _lib.check(L.ub200_backward_v(ctx.desc, x.data_ptr(), _lib.ptr_table(ctx.table), km.data_ptr() if km is not None else None,
+                                          vkm.data_ptr() if vkm is not None else None,
+                                          out.data_ptr(), grad_out.data_ptr(), _lib.ptr_table(gtable), ctx.ws.data_ptr(),
+                                          ctx.ws.numel(), stream), "ub200_backward")
         ctx.ws = None
-        return (None, None, None, None, *views)
+        return (None, None, None, None, None, None, *views)
 
 
 class UNCRTAINTS(nn.Module):
-    """Same constructor as the reference (uncrtaints.py:231-254).  Supported: the default UnCRtainTS
-    architecture (encoder_widths=[128], decoder_widths=[128]*k, block_type='mbconv', agg_mode='att_group',
-    n_head=16, d_model=256, d_k=4, reflect padding, group/batch norms, covmode diag|iso|uni|None);
-    other combinations raise NotImplementedError, as the reference does for its own unsupported ones (:320)."""
+    """Same constructor as the reference (uncrtaints.py:231-254).  Supported: the UnCRtainTS architecture with MBConv blocks
+    (encoder_widths=[128], decoder_widths=[128]*k, block_type='mbconv', agg_mode='att_group', n_head=16, d_model=256, d_k=4,
+    reflect padding, group/batch norms, covmode diag|iso|uni|None) and its constructor variants ``use_v`` (full LTAE2d value
+    path + include_v, :300-314,414-417), ``is_mono`` (single date, no temporal encoder, :296,418) and ``separate_out`` (two output
+    convolutions, :376-379,424-430); other combinations (block_type='residual', other widths / aggregation modes) raise
+    NotImplementedError, as the reference does for its own unsupported ones (:320)."""
 
     def __init__(self, input_dim, encoder_widths=[128], decoder_widths=[128, 128, 128, 128, 128], out_conv=[S2_BANDS],
                  out_nonlin_mean=False, out_nonlin_var="relu", agg_mode="att_group", encoder_norm="group",
@@ -253,9 +284,8 @@ class UNCRTAINTS(nn.Module):
         super().__init__()
         if list(encoder_widths) != [_WIDTH] or decoder_widths is None or any(w != _WIDTH for w in decoder_widths):
             raise NotImplementedError("B200 path: encoder_widths must be [128] and decoder_widths [128]*k")
-        if block_type != "mbconv" or use_v or is_mono or separate_out or agg_mode != "att_group":
-            raise NotImplementedError("B200 path: only block_type='mbconv', use_v=False, is_mono=False, "
-                                      "separate_out=False, agg_mode='att_group' are built")
+        if block_type != "mbconv" or agg_mode != "att_group":
+            raise NotImplementedError("B200 path: only block_type='mbconv' and agg_mode='att_group' are built")
         if (n_head, d_model, d_k) != (_HEADS, _DMODEL, _DK) or padding_mode != "reflect" or len(out_conv) != 1:
             raise NotImplementedError("B200 path: n_head=16, d_model=256, d_k=4, padding_mode='reflect', single out_conv layer")
         if input_dim > 16:
@@ -271,9 +301,15 @@ class UNCRTAINTS(nn.Module):
 
         self.in_conv = ConvBlock(input_dim, _WIDTH, norm=encoder_norm)
         self.in_block = nn.ModuleList([MBConv(_WIDTH, _WIDTH, expansion=2, norm=encoder_norm)])
-        self.temporal_encoder = LTAE2dtiny(in_channels=_WIDTH, n_head=n_head, d_k=d_k, d_model=d_model,
-                                           positional_encoding=positional_encoding)
-        self.temporal_aggregator = Compact_Temporal_Aggregator(mode=agg_mode)
+        if not self.is_mono:                                                              # uncrtaints.py:296-322
+            if self.use_v:
+                self.temporal_encoder = LTAE2d(in_channels=_WIDTH, n_head=n_head, d_k=d_k, d_model=d_model, mlp=[d_model, _WIDTH],
+                                               positional_encoding=positional_encoding)
+                self.include_v = nn.Conv2d(2 * _WIDTH, _WIDTH, 1)
+            else:
+                self.temporal_encoder = LTAE2dtiny(in_channels=_WIDTH, n_head=n_head, d_k=d_k, d_model=d_model,
+                                                   positional_encoding=positional_encoding)
+            self.temporal_aggregator = Compact_Temporal_Aggregator(mode=agg_mode)
         self.out_block = nn.ModuleList([MBConv(_WIDTH, _WIDTH, expansion=2, norm=decoder_norm) for _ in decoder_widths])
 
         self.covmode = covmode
@@ -287,10 +323,16 @@ class UNCRTAINTS(nn.Module):
             raise NotImplementedError("B200 path: out_nonlin_var must be 'softplus' (what the CLI forces, train_reconstruct.py:61)")
         self.var_eps = 1e-9 if self.scale_by == 1.0 else 1e-3                             # uncrtaints.py:374
         self.out_nonlin_mean = bool(out_nonlin_mean)
-        self.out_conv = ConvBlock(_WIDTH, self.out_dims, norm="none", last_relu=False)
+        if self.separate_out:                                                             # uncrtaints.py:376-381
+            self.out_conv_mean_1 = ConvBlock(_WIDTH, S2_BANDS, norm="none", last_relu=False)
+            if self.out_dims - self.mean_idx > 0:
+                self.out_conv_var_1 = ConvBlock(_WIDTH, self.out_dims - S2_BANDS, norm="none", last_relu=False)
+        else:
+            self.out_conv = ConvBlock(_WIDTH, self.out_dims, norm="none", last_relu=False)
         self.variance = None
         self.gemm_backend = gemm_backend
         self._injected_keep_mask = None      # tests: explicit dropout keep mask uint8 [16,B,T,H,W]
+        self._injected_v_keep_mask = None    # tests (use_v): explicit keep mask of the value dropout, uint8 [B*1024,128]
         self.keep_workspace = False          # debugging: keep (desc, workspace) of the last forward in _last_workspace
         self._last_workspace = None
         self._build_slots()
@@ -306,10 +348,23 @@ class UNCRTAINTS(nn.Module):
         names[_lib.UB200_P_IN_NORM_B] = "in_conv.conv.conv.1.bias"
         names[_lib.UB200_P_IN_NORM_RM] = "in_conv.conv.conv.1.running_mean"
         names[_lib.UB200_P_IN_NORM_RV] = "in_conv.conv.conv.1.running_var"
-        names[_lib.UB200_P_LTAE_AP] = "<Ap>"
-        names[_lib.UB200_P_LTAE_E] = "<e>"
-        names[_lib.UB200_P_OUT_W] = "out_conv.conv.conv.0.weight"
-        names[_lib.UB200_P_OUT_B] = "out_conv.conv.conv.0.bias"
+        if not self.is_mono:
+            names[_lib.UB200_P_LTAE_AP] = "<Ap>"
+            names[_lib.UB200_P_LTAE_E] = "<e>"
+        if self.use_v:
+            te = "temporal_encoder."
+            for slot, key in ((_lib.UB200_P_LTAE_GN_W, te + "in_norm.weight"), (_lib.UB200_P_LTAE_GN_B, te + "in_norm.bias"),
+                              (_lib.UB200_P_LTAE_WIN, te + "inconv.weight"), (_lib.UB200_P_LTAE_BIN, te + "inconv.bias"),
+                              (_lib.UB200_P_LTAE_PE, "<pe>"),
+                              (_lib.UB200_P_LTAE_MLP_W, te + "mlp.0.weight"), (_lib.UB200_P_LTAE_MLP_B, te + "mlp.0.bias"),
+                              (_lib.UB200_P_LTAE_BN_W, te + "mlp.1.weight"), (_lib.UB200_P_LTAE_BN_B, te + "mlp.1.bias"),
+                              (_lib.UB200_P_LTAE_BN_RM, te + "mlp.1.running_mean"), (_lib.UB200_P_LTAE_BN_RV, te + "mlp.1.running_var"),
+                              (_lib.UB200_P_LTAE_ON_W, te + "out_norm.weight"), (_lib.UB200_P_LTAE_ON_B, te + "out_norm.bias"),
+                              (_lib.UB200_P_INCV_W, "include_v.weight"), (_lib.UB200_P_INCV_B, "include_v.bias")):
+                names[slot] = key
+        # separate_out: the two output convolutions act on the same input, i.e. they are ONE convolution with stacked weights
+        names[_lib.UB200_P_OUT_W] = "<out_w>" if self.separate_out else "out_conv.conv.conv.0.weight"
+        names[_lib.UB200_P_OUT_B] = "<out_b>" if self.separate_out else "out_conv.conv.conv.0.bias"
         rel = {
             _lib.UB200_B_N0_W: "conv.norm.weight", _lib.UB200_B_N0_B: "conv.norm.bias",
             _lib.UB200_B_N0_RM: "conv.norm.running_mean", _lib.UB200_B_N0_RV: "conv.norm.running_var",
@@ -330,7 +385,9 @@ class UNCRTAINTS(nn.Module):
                 names[P0 + bi * S + k] = prefix + v
         self._slot_names = names
 
-    def _describe(self, x, need_grad):
+    _PSEUDO = ("<Ap>", "<e>", "<out_w>", "<out_b>")      # differentiable tensors derived from the parameters by tiny torch ops
+
+    def _describe(self, x, need_grad, extra_buffers=None):
         """(ub200_desc, slots of the differentiable tensors in call order, [(slot, buffer tensor)])"""
         B, T, C, H, W = x.shape
         d = _lib.Desc()
@@ -346,8 +403,11 @@ class UNCRTAINTS(nn.Module):
         d.scale_by, d.var_eps, d.pad_value = float(self.scale_by), float(self.var_eps), float(self.pad_value)
         d.norm_eps, d.bn_momentum = 1e-5, 0.1
         # the reference applies the dropout only inside the upsampling branch, i.e. when H > 32 (uncrtaints.py:197-202)
-        d.dropout_p = float(self.temporal_aggregator.attn_dropout.p) if H > 32 else 0.0
-        if self.training and d.dropout_p > 0 and self._injected_keep_mask is None:
+        d.is_mono, d.use_v = int(self.is_mono), int(self.use_v)
+        d.dropout_p = float(self.temporal_aggregator.attn_dropout.p) if (H > 32 and not self.is_mono) else 0.0
+        d.v_dropout_p = float(self.temporal_encoder.dropout.p) if self.use_v else 0.0
+        if self.training and ((d.dropout_p > 0 and self._injected_keep_mask is None) or
+                              (d.v_dropout_p > 0 and self._injected_v_keep_mask is None)):
             d.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         d.offset = 0
         named = dict(self.named_parameters())
@@ -356,20 +416,20 @@ class UNCRTAINTS(nn.Module):
         for slot, name in enumerate(self._slot_names):
             if name is None:
                 continue
-            if name in ("<Ap>", "<e>") or name in named:
+            if name in self._PSEUDO or name in named:
                 slots.append(slot)
             elif name in bufs:
                 buffers.append((slot, bufs[name]))
+            elif extra_buffers and extra_buffers.get(name) is not None:
+                buffers.append((slot, extra_buffers[name]))
         return d, slots, buffers
 
-    def _tensors_in_slot_order(self, ap, e):
+    def _tensors_in_slot_order(self, pseudo):
         named = dict(self.named_parameters())
         out = []
         for name in self._slot_names:
-            if name == "<Ap>":
-                out.append(ap)
-            elif name == "<e>":
-                out.append(e)
+            if name in self._PSEUDO:
+                out.append(pseudo[name])
             elif name is not None and name in named:
                 out.append(named[name])
         return out
@@ -383,8 +443,18 @@ class UNCRTAINTS(nn.Module):
             raise NotImplementedError("B200 path expects a 5-D [B,T,C,H,W] input")
         x = input.contiguous().float()
         B, T = x.shape[:2]
-        ap, e = fold_ltae(self.temporal_encoder, batch_positions, B, T, x.device)
-        tensors = self._tensors_in_slot_order(ap, e)
+        if self.is_mono and T != 1:
+            raise NotImplementedError("B200 path: is_mono squeezes the time dimension (uncrtaints.py:418) and needs T == 1")
+        pseudo, extra = {}, {}
+        if not self.is_mono:
+            pseudo["<Ap>"], pseudo["<e>"], pe = fold_ltae(self.temporal_encoder, batch_positions, B, T, x.device, with_pe=True)
+            if self.use_v and pe is not None:
+                extra["<pe>"] = pe.float()
+        if self.separate_out:                                     # uncrtaints.py:424-430: cat of the two convolutions' outputs
+            heads = [self.out_conv_mean_1] + ([self.out_conv_var_1] if self.out_dims - self.mean_idx > 0 else [])
+            pseudo["<out_w>"] = torch.cat([h.conv.conv[0].weight for h in heads], dim=0).contiguous()
+            pseudo["<out_b>"] = torch.cat([h.conv.conv[0].bias for h in heads], dim=0).contiguous()
+        tensors = self._tensors_in_slot_order(pseudo)
         for t in tensors:
             if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
                 raise RuntimeError("B200 path: parameters must be contiguous float32 CUDA tensors")
@@ -392,10 +462,13 @@ class UNCRTAINTS(nn.Module):
         km = self._injected_keep_mask
         if km is not None:
             km = km.to(device=x.device, dtype=torch.uint8).contiguous()
-        out = _UncrtaintsFunction.apply(self, x, km, need_grad, *tensors)
+        vkm = self._injected_v_keep_mask
+        if vkm is not None:
+            vkm = vkm.to(device=x.device, dtype=torch.uint8).contiguous()
+        out = _UncrtaintsFunction.apply(self, x, km, need_grad, extra, vkm, *tensors)
         if self.training:
             counters = [m.num_batches_tracked for m in self.modules()
-                        if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None]
+                        if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
             if counters:
                 torch._foreach_add_(counters, 1)          # one launch for all BatchNorm step counters
         if not self.covmode:

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libuncrtaints_b200.so")
 
-SOURCES = ["norm.cu", "gemm_simt.cu", "gemm_tc.cu", "dwconv_rows.cu", "se.cu", "inconv.cu", "temporal.cu", "head_loss.cu", "optim.cu", "metrics.cu", "model.cu"]
+SOURCES = ["norm.cu", "gemm_simt.cu", "gemm_tc.cu", "dwconv_rows.cu", "se.cu", "inconv.cu", "temporal.cu", "ltae_v.cu", "head_loss.cu", "optim.cu", "metrics.cu", "model.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

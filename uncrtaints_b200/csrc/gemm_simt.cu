@@ -225,26 +225,26 @@ static int launch_gemm(ALoad al, const float* Wt, Epi ep, int N, int P, cudaStre
 // weight gradient: partial[blk][ia*sa + ib*sb] = sum over the block's pixels of fa(p)[ia] * fb(p)[ib]
 // fa has 128 columns, fb has 256 columns.
 // ------------------------------------------------------------------------------------------
-template <class LA, class LB>
+template <class LA, class LB, int CB = 256>
 __global__ void __launch_bounds__(256, 1)
 wgrad_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long total_tiles, int sa, int sb) {
-    constexpr int TM = 64, CA = 128, CB = 256;
+    constexpr int TM = 64, CA = 128, JB = CB / 64, QB = CB / 4, RB = 256 / QB;
     extern __shared__ __align__(16) float smem[];
     float* As = smem;             // TM*CA
     float* Bs = smem + TM * CA;   // TM*CB
     const int tid = threadIdx.x, tb = tid % 16, ta = tid / 16;
-    float4 acc[8][4];
+    float4 acc[8][JB];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = make_float4(0, 0, 0, 0);
+        for (int j = 0; j < JB; ++j) acc[i][j] = make_float4(0, 0, 0, 0);
 
     const int tiles_per_frame = P / TM;
     const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
     const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
     int cur_n = -1;
     const int qa = tid % 32, ra = tid / 32;   // A tile: 32 quads per row, 8 rows per pass
-    const int qb = tid % 64, rb = tid / 64;   // B tile: 64 quads per row, 4 rows per pass
+    const int qb = tid % QB, rb = tid / QB;   // B tile: CB/4 quads per row, 256/(CB/4) rows per pass
     for (long long t = t0; t < t1; ++t) {
         const int n = (int)(t / tiles_per_frame);
         if (n != cur_n) { la.init(n, qa); lb.init(n, qb); cur_n = n; }
@@ -253,14 +253,14 @@ wgrad_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long total_t
 #pragma unroll 4
         for (int r = ra; r < TM; r += 8) st4(As + r * CA + qa * 4, la.load(row0 + r, qa));
 #pragma unroll 4
-        for (int r = rb; r < TM; r += 4) st4(Bs + r * CB + qb * 4, lb.load(row0 + r, qb));
+        for (int r = rb; r < TM; r += RB) st4(Bs + r * CB + qb * 4, lb.load(row0 + r, qb));
         __syncthreads();
 #pragma unroll 4
         for (int p = 0; p < TM; ++p) {
             const float4 a0 = ld4(As + p * CA + ta * 8), a1 = ld4(As + p * CA + ta * 8 + 4);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < JB; ++j) {
                 const float4 b = ld4(Bs + p * CB + tb * 4 + 64 * j);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -276,7 +276,7 @@ wgrad_kernel(LA la, LB lb, float* __restrict__ partial, int P, long long total_t
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < JB; ++j) {
             const int ia = ta * 8 + i, ib = tb * 4 + 64 * j;
             const float v[4] = {acc[i][j].x, acc[i][j].y, acc[i][j].z, acc[i][j].w};
 #pragma unroll
@@ -366,6 +366,94 @@ int simt_wgrad1(const float* x, const Coef* coef0, const float* dz1, const float
     LoadNormed la{x, coef0, UB_WIDTH};
     LoadNormBwd lb{dz1, h1, bc1, UB_HID};
     return launch_wgrad(la, lb, partial, max_parts, dw1, N, P, 1, UB_WIDTH, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic fp32 linear layers of the `use_v` L-TAE value path (ltae.py:10-141, uncrtaints.py:324-338,414-417): row-major
+// [rows][K] x [K][NOUT] products on the low-resolution grid (B*1024 rows) and the include_v 1x1 convolution at full resolution.
+// They reuse the streaming GEMM / weight-gradient kernels above with plain loaders; all operands are fp32 (exact).
+// ------------------------------------------------------------------------------------------
+struct LoadPlain {
+    const float* x; int C;
+    __device__ void init(int, int) {}
+    __device__ float4 load(size_t row, int kq) const { return ld4(x + row * C + kq * 4); }
+};
+struct EpiLinear {             // out = acc + bias[col] + rowbias[n][col]; column (sum, sumsq) into stats
+    static constexpr int NS = 2;
+    float* out; const float* bias; const float* rowbias; double* stats; int NOUT;
+    __device__ void apply(int n, size_t row, int col, float4 v, float4* s) const {
+        if (bias) { const float4 b = ld4(bias + col); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (rowbias) { const float4 b = ld4(rowbias + (size_t)n * NOUT + col); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        st4(out + row * NOUT + col, v);
+        s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+        s[1].x += v.x * v.x; s[1].y += v.y * v.y; s[1].z += v.z * v.z; s[1].w += v.w * v.w;
+    }
+    __device__ double* dst(int n) const { return stats + (size_t)n * NOUT * NS; }
+};
+struct EpiUpAdd {              // out = acc + bilinear_up(low)[n][p][col] (align_corners=False, uncrtaints.py:416); low: [N][32*32][128]
+    static constexpr int NS = 2;
+    float* out; const float* low; double* stats; int H, W;
+    __device__ void apply(int n, size_t row, int col, float4 v, float4* s) const {
+        const int p = (int)(row - (size_t)n * H * W), y = p / W, x = p % W;
+        int y0, y1, x0, x1; float ly, lx;
+        bilinear_tap(y, (float)UB_LOW / (float)H, UB_LOW, y0, y1, ly);
+        bilinear_tap(x, (float)UB_LOW / (float)W, UB_LOW, x0, x1, lx);
+        const float* base = low + (size_t)n * UB_LOW * UB_LOW * UB_WIDTH + col;
+        const float4 a = ld4(base + (size_t)(y0 * UB_LOW + x0) * UB_WIDTH), b = ld4(base + (size_t)(y0 * UB_LOW + x1) * UB_WIDTH);
+        const float4 c = ld4(base + (size_t)(y1 * UB_LOW + x0) * UB_WIDTH), d = ld4(base + (size_t)(y1 * UB_LOW + x1) * UB_WIDTH);
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        v.x += w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+        v.y += w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+        v.z += w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z;
+        v.w += w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w;
+        st4(out + row * UB_WIDTH + col, v);
+        s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+        s[1].x += v.x * v.x; s[1].y += v.y * v.y; s[1].z += v.z * v.z; s[1].w += v.w * v.w;
+    }
+    __device__ double* dst(int n) const { return stats + (size_t)n * UB_WIDTH * NS; }
+};
+
+int simt_linear(const float* a, int K, const float* wt, int NOUT, const float* bias, const float* rowbias, float* out, double* stats,
+                int N, int P, cudaStream_t st) {
+    if (!a || !wt || !out || !stats) return UB_ERR_ARG;
+    LoadPlain al{a, K};
+    EpiLinear ep{out, bias, rowbias, stats, NOUT};
+    if (K == 128 && NOUT == 256) return launch_gemm<128, 256>(al, wt, ep, N, P, st);
+    if (K == 256 && NOUT == 128) return launch_gemm<256, 128>(al, wt, ep, N, P, st);
+    if (K == 128 && NOUT == 128) return launch_gemm<128, 128>(al, wt, ep, N, P, st);
+    return UB_ERR_ARG;
+}
+int simt_linear_upadd(const float* a, const float* wt, const float* low, float* out, double* stats, int N, int H, int W, cudaStream_t st) {
+    LoadPlain al{a, UB_WIDTH};
+    EpiUpAdd ep{out, low, stats, H, W};
+    return launch_gemm<128, 128>(al, wt, ep, N, H * W, st);
+}
+
+// grad[r * ld + c] += sum_b partial[b][r][c]   (compact [rows][cols] partials into a wider matrix)
+__global__ void reduce_partials_2d_kernel(const float* __restrict__ partial, float* __restrict__ grad, int rows, int cols, int ld, int nparts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    float s = 0.f;
+    for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * rows * cols + i];
+    grad[(size_t)(i / cols) * ld + i % cols] += s;
+}
+// grad[ia*sa + ib*sb] (+ld handling for cb == 128) += sum_rows a[row][ia] * b[row][ib];  a: [N*P][128], b: [N*P][cb], cb = 128 | 256
+int simt_wgrad_plain(const float* a, const float* b, int cb, float* partial, int max_parts, float* grad, int sa, int sb, int ld, int N, int P,
+                     cudaStream_t st) {
+    if (!a || !b || !partial || !grad || P % 64 != 0) return UB_ERR_ARG;
+    LoadPlain la{a, 128}, lb{b, cb};
+    if (cb == 256) return launch_wgrad(la, lb, partial, max_parts, grad, N, P, sa, sb, st);
+    if (cb != 128) return UB_ERR_ARG;
+    constexpr size_t smem = (size_t)64 * (128 + 128) * sizeof(float);
+    auto kern = wgrad_kernel<LoadPlain, LoadPlain, 128>;
+    UB_SET_SMEM(kern, smem);
+    const long long total = (long long)N * (P / 64);
+    const int blocks = (int)(total < max_parts ? total : max_parts);
+    kern<<<blocks, 256, smem, st>>>(la, lb, partial, P, total, 128, 1);
+    UB_CHECK_LAUNCH();
+    reduce_partials_2d_kernel<<<(128 * 128 + 255) / 256, 256, 0, st>>>(partial, grad, 128, 128, ld, blocks);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
 }
 
 }  // namespace ub

@@ -102,6 +102,34 @@ int launch_aggregate_bwd(const float* attn, const int* notpad, const unsigned ch
                          unsigned long long offset, float drop_p, const float* x, const float* dagg, float* denc,
                          float* dwup, float* dattn, int B, int T, int H, int W, cudaStream_t st);
 
+// gemm_simt.cu: generic fp32 linear layers (the `use_v` value path, ltae_v.cu).  a: [N*P][K], wt: [K][NOUT], out: [N*P][NOUT] =
+// a . wt + bias[NOUT] + rowbias[N][NOUT] (either may be null); stats[N][NOUT][2] += column (sum, sumsq) (always written: pass scratch)
+int simt_linear(const float* a, int K, const float* wt, int NOUT, const float* bias, const float* rowbias, float* out, double* stats,
+                int N, int P, cudaStream_t st);
+// out[N][H*W][128] = a . wt + bilinear_up(low [N][32*32][128]); stats as above
+int simt_linear_upadd(const float* a, const float* wt, const float* low, float* out, double* stats, int N, int H, int W, cudaStream_t st);
+// grad[ia*sa + ib*sb] += sum_rows a[row][ia] * b[row][ib] (cb = 256), or grad[ia*ld + ib] += ... (cb = 128); a: [N*P][128], b: [N*P][cb]
+int simt_wgrad_plain(const float* a, const float* b, int cb, float* partial, int max_parts, float* grad, int sa, int sb, int ld, int N, int P,
+                     cudaStream_t st);
+
+// ltae_v.cu (`use_v`: full LTAE2d value path + include_v)
+int launch_ltaev_norm(const float* pooled, const float* gamma, const float* beta, float* xn, int B, int T, float eps, cudaStream_t st);
+int launch_ltaev_attnv(const float* attn, const float* z, float* o, int B, int T, cudaStream_t st);
+int launch_ltaev_attnv_bwd(const float* attn, const float* z, const float* d_o, float* dz, float* dattn, int B, int T, cudaStream_t st);
+int launch_ltaev_post_fwd(const float* m, const MeanRstd* mr, const float* bn_g, const float* bn_b, const float* gamma, const float* beta,
+                          const unsigned char* keep_mask, unsigned long long seed, unsigned long long offset, float drop_p, float* v, int B,
+                          float eps, cudaStream_t st);
+int launch_ltaev_post_bwd(const float* m, const MeanRstd* mr, const float* bn_g, const float* bn_b, const float* gamma,
+                          const unsigned char* keep_mask, unsigned long long seed, unsigned long long offset, float drop_p, const float* dv,
+                          float* dyb, double* bstats, float* dgamma, float* dbeta, int B, float eps, cudaStream_t st);
+int launch_normbwd_apply(const float* dy, const float* x, const BCoef* bc, float* dx, int N, int rows_per_frame, cudaStream_t st);
+int launch_colsum(const float* x, float* out, size_t rows, int C, cudaStream_t st);
+int launch_upsample_adjoint128(const float* dfull, float* dlow, int N, int H, int W, cudaStream_t st);
+int launch_ltaev_final_bwd(const float* pooled, const float* Ap, const float* attn, const float* dattn, const float* dxn,
+                           const float* gamma, float* dpooled, float* dAp, float* de, float* dgamma, float* dbeta, int B, int T, float eps,
+                           cudaStream_t st);
+int launch_slice2d(const float* src, float* dst, int rows, int cols, int ld, int c0, int transpose, cudaStream_t st);
+
 // head_loss.cu
 int launch_head_fwd(const float* dec, const float* w, const float* bias, float* out, int B, int O, int P, float scale_by,
                     int mean_sigmoid, float var_eps, cudaStream_t st);

@@ -85,6 +85,11 @@ struct Layout {
     size_t bstats_in, bc_in, mom_in, gram_in;
     size_t gA, gB, dn0, du, dz1, partial, dwup, dattn, dpooled;
     BlockWs blk[1 + 16];
+    // use_v (ltae_v.cu): low-resolution value path + include_v
+    struct {
+        size_t xn, z, o, m, v, vv, mix, stats_m, coef_m, mr_m, scratch_stats, winT, wmT, wvT, waT, wv, wa, dump;     // forward
+        size_t bstats_m, bc_m, dvv, dv, dyb, dm, d_o, dz, dxn;                                                   // backward
+    } V;
     size_t total;
 };
 
@@ -141,6 +146,8 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     if (d->H < UB_LOW || d->W < UB_LOW || d->H % UB_LOW || d->W % UB_LOW) return UB_ERR_ARG;
     if (d->n_dec_blocks < 1 || d->n_dec_blocks > 16) return UB_ERR_ARG;
     if (d->out_dim < UB_S2 || d->out_dim > 26) return UB_ERR_ARG;
+    if (d->is_mono && d->use_v) return UB_ERR_ARG;
+    if (d->is_mono && d->T != 1) return UB_ERR_ARG;             // out.squeeze(dim=1) (uncrtaints.py:418) needs a single frame
     L.B = d->B; L.Ne = d->B * d->T; L.P = d->H * d->W; L.nblk = 1 + d->n_dec_blocks;
     L.Nmax = L.Ne;
     // bf16 hidden storage needs the tcgen05 GEMMs (the CUDA-core comparators read fp32) and excludes the fused project-conv backward
@@ -154,11 +161,13 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     L.stats_c0 = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
     L.mom_in = b.take(inconv_moments_bytes(L.Ne));
     for (int i = 0; i < L.nblk; ++i) block_fwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
+    if (d->use_v) L.V.stats_m = b.take((size_t)L.B * UB_WIDTH * 2 * sizeof(double));
     L.fwd_zero_end = b.off;
     L.bwd_zero_begin = b.off;
     L.bstats_in = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
     L.gram_in = b.take(inconv_gram_bytes(L.Ne));
     for (int i = 0; i < L.nblk; ++i) block_bwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
+    if (d->use_v) L.V.bstats_m = b.take((size_t)L.B * UB_WIDTH * 2 * sizeof(double));
     L.bwd_zero_end = b.off;
     L.coef_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(Coef));
     L.mr_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(MeanRstd));
@@ -168,6 +177,24 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     L.pool_idx = b.take((size_t)L.Ne * UB_LOW * UB_LOW * UB_WIDTH * sizeof(int));
     L.attn = b.take((size_t)UB_HEADS * L.Ne * UB_LOW * UB_LOW * sizeof(float));
     L.agg = b.take((size_t)L.B * P * UB_WIDTH * sizeof(float));
+    if (d->use_v) {
+        const size_t Q = (size_t)L.B * UB_LOW * UB_LOW, NQ = (size_t)L.Ne * UB_LOW * UB_LOW;
+        L.V.xn = b.take(NQ * UB_WIDTH * 4); L.V.z = b.take(NQ * UB_HID * 4); L.V.o = b.take(Q * UB_HID * 4);
+        L.V.m = b.take(Q * UB_WIDTH * 4); L.V.v = b.take(Q * UB_WIDTH * 4); L.V.vv = b.take(Q * UB_WIDTH * 4);
+        L.V.mix = b.take((size_t)L.B * P * UB_WIDTH * 4);
+        L.V.coef_m = b.take((size_t)L.B * UB_WIDTH * sizeof(Coef)); L.V.mr_m = b.take((size_t)L.B * UB_WIDTH * sizeof(MeanRstd));
+        L.V.scratch_stats = b.take((size_t)L.Ne * UB_HID * 2 * sizeof(double));
+        L.V.winT = b.take((size_t)UB_WIDTH * UB_HID * 4); L.V.wmT = b.take((size_t)UB_WIDTH * UB_HID * 4);
+        L.V.wvT = b.take((size_t)UB_WIDTH * UB_WIDTH * 4); L.V.waT = b.take((size_t)UB_WIDTH * UB_WIDTH * 4);
+        L.V.wv = b.take((size_t)UB_WIDTH * UB_WIDTH * 4); L.V.wa = b.take((size_t)UB_WIDTH * UB_WIDTH * 4);
+        L.V.dump = b.take(2 * UB_HID * 4);
+        if (d->need_grad) {
+            L.V.bc_m = b.take((size_t)L.B * UB_WIDTH * sizeof(BCoef));
+            L.V.dvv = b.take(Q * UB_WIDTH * 4); L.V.dv = b.take(Q * UB_WIDTH * 4); L.V.dyb = b.take(Q * UB_WIDTH * 4);
+            L.V.dm = b.take(Q * UB_WIDTH * 4); L.V.d_o = b.take(Q * UB_HID * 4); L.V.dz = b.take(NQ * UB_HID * 4);
+            L.V.dxn = b.take(NQ * UB_WIDTH * 4);
+        }
+    }
     if (d->need_grad) {
         for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, true, L.hes);
     } else {
@@ -377,6 +404,91 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
     atomicAdd(&stats[((size_t)n * C + ch) * 2 + which], t);
 }
 
+// ---- use_v: full LTAE2d value path + include_v (ltae.py:96-141, uncrtaints.py:414-417); kernels in ltae_v.cu ----
+static int value_path_forward(const ub200_desc* d, const Layout& L, const void* const* params, const unsigned char* v_keep_mask, void* ws,
+                              cudaStream_t st) {
+    const int B = d->B, T = d->T, Ne = L.Ne;
+    const float* w_in = pf(params, UB200_P_LTAE_WIN);
+    const float* w_m = pf(params, UB200_P_LTAE_MLP_W);
+    const float* w_cv = pf(params, UB200_P_INCV_W);
+    if (!w_in || !w_m || !w_cv || !pf(params, UB200_P_LTAE_GN_W) || !pf(params, UB200_P_LTAE_BN_W) || !pf(params, UB200_P_LTAE_ON_W)) return UB_ERR_ARG;
+    double* scratch = at<double>(ws, L.V.scratch_stats);
+    // [K][NOUT] forms of the forward weights; compact copies of the two halves of include_v.weight for the backward GEMMs
+    UB_TRY(launch_slice2d(w_in, at<float>(ws, L.V.winT), UB_HID, UB_WIDTH, UB_WIDTH, 0, 1, st));
+    UB_TRY(launch_slice2d(w_m, at<float>(ws, L.V.wmT), UB_WIDTH, UB_HID, UB_HID, 0, 1, st));
+    UB_TRY(launch_slice2d(w_cv, at<float>(ws, L.V.waT), UB_WIDTH, UB_WIDTH, UB_HID, 0, 1, st));
+    UB_TRY(launch_slice2d(w_cv, at<float>(ws, L.V.wvT), UB_WIDTH, UB_WIDTH, UB_HID, UB_WIDTH, 1, st));
+    UB_TRY(launch_slice2d(w_cv, at<float>(ws, L.V.wa), UB_WIDTH, UB_WIDTH, UB_HID, 0, 0, st));
+    UB_TRY(launch_slice2d(w_cv, at<float>(ws, L.V.wv), UB_WIDTH, UB_WIDTH, UB_HID, UB_WIDTH, 0, st));
+    UB_TRY(launch_ltaev_norm(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_GN_W), pf(params, UB200_P_LTAE_GN_B), at<float>(ws, L.V.xn), B, T,
+                             d->norm_eps, st));
+    UB_TRY(simt_linear(at<float>(ws, L.V.xn), UB_WIDTH, at<float>(ws, L.V.winT), UB_HID, pf(params, UB200_P_LTAE_BIN), pf(params, UB200_P_LTAE_PE),
+                       at<float>(ws, L.V.z), scratch, Ne, UB_LOW * UB_LOW, st));
+    UB_TRY(launch_ltaev_attnv(at<float>(ws, L.attn), at<float>(ws, L.V.z), at<float>(ws, L.V.o), B, T, st));
+    UB_TRY(simt_linear(at<float>(ws, L.V.o), UB_HID, at<float>(ws, L.V.wmT), UB_WIDTH, pf(params, UB200_P_LTAE_MLP_B), nullptr, at<float>(ws, L.V.m),
+                       at<double>(ws, L.V.stats_m), B, UB_LOW * UB_LOW, st));
+    // BatchNorm1d over the B*1024 rows (ltae.py:79): per-sample partial sums, finalised like a BatchNorm2d over B frames of 1024 pixels
+    UB_TRY(launch_norm_finalize(at<double>(ws, L.V.stats_m), pf(params, UB200_P_LTAE_BN_W), pf(params, UB200_P_LTAE_BN_B),
+                                pfm(params, UB200_P_LTAE_BN_RM), pfm(params, UB200_P_LTAE_BN_RV), at<Coef>(ws, L.V.coef_m), at<MeanRstd>(ws, L.V.mr_m),
+                                B, UB_WIDTH, 0, (double)(UB_LOW * UB_LOW), d->norm_eps, d->bn_momentum, d->training, st));
+    const float vp = d->training ? d->v_dropout_p : 0.f;
+    UB_TRY(launch_ltaev_post_fwd(at<float>(ws, L.V.m), at<MeanRstd>(ws, L.V.mr_m), pf(params, UB200_P_LTAE_BN_W), pf(params, UB200_P_LTAE_BN_B),
+                                 pf(params, UB200_P_LTAE_ON_W), pf(params, UB200_P_LTAE_ON_B),
+                                 v_keep_mask, d->seed, d->offset, vp, at<float>(ws, L.V.v), B, d->norm_eps, st));
+    UB_TRY(simt_linear(at<float>(ws, L.V.v), UB_WIDTH, at<float>(ws, L.V.wvT), UB_WIDTH, pf(params, UB200_P_INCV_B), nullptr, at<float>(ws, L.V.vv),
+                       scratch, B, UB_LOW * UB_LOW, st));
+    // include_v(cat(agg, up(v))) = W_a agg + up(W_v v + b): one full-resolution 128 -> 128 GEMM; its column sums feed the first decoder PreNorm
+    UB_TRY(simt_linear_upadd(at<float>(ws, L.agg), at<float>(ws, L.V.waT), at<float>(ws, L.V.vv), at<float>(ws, L.V.mix),
+                             at<double>(ws, L.blk[1].stats0), B, d->H, d->W, st));
+    return UB_OK;
+}
+// dmix -> dagg (into `dagg`), the include_v gradients and dvv (low resolution)
+static int value_path_backward_head(const ub200_desc* d, const Layout& L, const void* const* params, void* const* grads, const float* dmix,
+                                    float* dagg, float* partial, void* ws, cudaStream_t st) {
+    const int B = d->B, P = L.P;
+    double* scratch = at<double>(ws, L.V.scratch_stats);
+    float* g_cv = gf(grads, UB200_P_INCV_W);
+    UB_TRY(launch_upsample_adjoint128(dmix, at<float>(ws, L.V.dvv), B, d->H, d->W, st));
+    UB_TRY(simt_linear(dmix, UB_WIDTH, at<float>(ws, L.V.wa), UB_WIDTH, nullptr, nullptr, dagg, scratch, B, P, st));
+    if (g_cv) {
+        UB_TRY(simt_wgrad_plain(dmix, at<float>(ws, L.agg), UB_WIDTH, partial, L.max_parts, g_cv, 0, 0, UB_HID, B, P, st));
+        UB_TRY(simt_wgrad_plain(at<float>(ws, L.V.dvv), at<float>(ws, L.V.v), UB_WIDTH, partial, L.max_parts, g_cv + UB_WIDTH, 0, 0, UB_HID, B,
+                                UB_LOW * UB_LOW, st));
+    }
+    if (gf(grads, UB200_P_INCV_B)) UB_TRY(launch_colsum(at<float>(ws, L.V.dvv), gf(grads, UB200_P_INCV_B), (size_t)B * UB_LOW * UB_LOW, UB_WIDTH, st));
+    return UB_OK;
+}
+// after aggregate_bwd has written dattn: the low-resolution chain back to dpooled and every temporal-encoder gradient
+static int value_path_backward_tail(const ub200_desc* d, const Layout& L, const void* const* params, void* const* grads,
+                                    const unsigned char* v_keep_mask, float* partial, void* ws, cudaStream_t st) {
+    const int B = d->B, T = d->T, Ne = L.Ne, LQ = UB_LOW * UB_LOW;
+    double* scratch = at<double>(ws, L.V.scratch_stats);
+    const float vp = d->training ? d->v_dropout_p : 0.f;
+    float* dump = at<float>(ws, L.V.dump);     // sink for gradient slots the caller left NULL
+    auto G = [&](int slot) { float* g = gf(grads, slot); return g ? g : dump; };
+    UB_TRY(simt_linear(at<float>(ws, L.V.dvv), UB_WIDTH, at<float>(ws, L.V.wv), UB_WIDTH, nullptr, nullptr, at<float>(ws, L.V.dv), scratch, B, LQ, st));
+    UB_TRY(launch_ltaev_post_bwd(at<float>(ws, L.V.m), at<MeanRstd>(ws, L.V.mr_m), pf(params, UB200_P_LTAE_BN_W), pf(params, UB200_P_LTAE_BN_B),
+                                 pf(params, UB200_P_LTAE_ON_W), v_keep_mask,
+                                 d->seed, d->offset, vp, at<float>(ws, L.V.dv), at<float>(ws, L.V.dyb), at<double>(ws, L.V.bstats_m),
+                                 G(UB200_P_LTAE_ON_W), G(UB200_P_LTAE_ON_B), B, d->norm_eps, st));
+    UB_TRY(launch_norm_finalize_bwd(at<double>(ws, L.V.bstats_m), pf(params, UB200_P_LTAE_BN_W), at<MeanRstd>(ws, L.V.mr_m), at<BCoef>(ws, L.V.bc_m),
+                                    gf(grads, UB200_P_LTAE_BN_W), gf(grads, UB200_P_LTAE_BN_B), B, UB_WIDTH, 0, (double)LQ, d->training, st));
+    UB_TRY(launch_normbwd_apply(at<float>(ws, L.V.dyb), at<float>(ws, L.V.m), at<BCoef>(ws, L.V.bc_m), at<float>(ws, L.V.dm), B, LQ, st));
+    if (gf(grads, UB200_P_LTAE_MLP_B)) UB_TRY(launch_colsum(at<float>(ws, L.V.dm), gf(grads, UB200_P_LTAE_MLP_B), (size_t)B * LQ, UB_WIDTH, st));
+    if (gf(grads, UB200_P_LTAE_MLP_W))
+        UB_TRY(simt_wgrad_plain(at<float>(ws, L.V.dm), at<float>(ws, L.V.o), UB_HID, partial, L.max_parts, gf(grads, UB200_P_LTAE_MLP_W), UB_HID, 1, 0, B, LQ, st));
+    UB_TRY(simt_linear(at<float>(ws, L.V.dm), UB_WIDTH, pf(params, UB200_P_LTAE_MLP_W), UB_HID, nullptr, nullptr, at<float>(ws, L.V.d_o), scratch, B, LQ, st));
+    UB_TRY(launch_ltaev_attnv_bwd(at<float>(ws, L.attn), at<float>(ws, L.V.z), at<float>(ws, L.V.d_o), at<float>(ws, L.V.dz), at<float>(ws, L.dattn), B, T, st));
+    if (gf(grads, UB200_P_LTAE_BIN)) UB_TRY(launch_colsum(at<float>(ws, L.V.dz), gf(grads, UB200_P_LTAE_BIN), (size_t)Ne * LQ, UB_HID, st));
+    if (gf(grads, UB200_P_LTAE_WIN))
+        UB_TRY(simt_wgrad_plain(at<float>(ws, L.V.xn), at<float>(ws, L.V.dz), UB_HID, partial, L.max_parts, gf(grads, UB200_P_LTAE_WIN), 1, UB_WIDTH, 0, Ne, LQ, st));
+    UB_TRY(simt_linear(at<float>(ws, L.V.dz), UB_HID, pf(params, UB200_P_LTAE_WIN), UB_WIDTH, nullptr, nullptr, at<float>(ws, L.V.dxn), scratch, Ne, LQ, st));
+    UB_TRY(launch_ltaev_final_bwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), at<float>(ws, L.attn), at<float>(ws, L.dattn),
+                                  at<float>(ws, L.V.dxn), pf(params, UB200_P_LTAE_GN_W), at<float>(ws, L.dpooled), gf(grads, UB200_P_LTAE_AP),
+                                  gf(grads, UB200_P_LTAE_E), G(UB200_P_LTAE_GN_W), G(UB200_P_LTAE_GN_B), B, T, d->norm_eps, st));
+    return UB_OK;
+}
+
 static int num_sms() { return device_sm_count(); }
 
 }  // namespace ub
@@ -459,6 +571,12 @@ int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, s
     };
     for (auto& f : fixed)
         if (!strcmp(f.n, name)) { *offset = f.off; *bytes = f.sz; return UB_OK; }
+    if (d->use_v) {           // low-resolution value path: MLP output before the BatchNorm1d, its (mean, rstd), the value output
+        const size_t Q = (size_t)L.B * UB_LOW * UB_LOW;
+        if (!strcmp(name, "v.m")) { *offset = L.V.m; *bytes = Q * UB_WIDTH * 4; return UB_OK; }
+        if (!strcmp(name, "v.mr")) { *offset = L.V.mr_m; *bytes = (size_t)L.B * UB_WIDTH * sizeof(MeanRstd); return UB_OK; }
+        if (!strcmp(name, "v.v")) { *offset = L.V.v; *bytes = Q * UB_WIDTH * 4; return UB_OK; }
+    }
     int bi = -1;
     char what[16];
     if (sscanf(name, "blk%d.%15s", &bi, what) == 2 && bi >= 0 && bi < L.nblk) {
@@ -495,6 +613,10 @@ static BlockCtx make_ctx(const ub200_desc* d, const Layout& L, int i, const void
 
 int ub200_forward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
                   float* output, void* ws, size_t ws_bytes, void* stream) {
+    return ub200_forward_v(d, input, params, keep_mask, nullptr, output, ws, ws_bytes, stream);
+}
+int ub200_forward_v(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                    const unsigned char* v_keep_mask, float* output, void* ws, size_t ws_bytes, void* stream) {
     Layout L;
     UB_TRY(make_layout(d, L));
     if (!input || !params || !output || !ws) return UB_ERR_ARG;
@@ -514,17 +636,26 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
                                at<float>(ws, L.x0), at<double>(ws, L.blk[0].stats0), L.Ne, d->C_in, P, st));
     // encoder block
     BlockCtx enc = make_ctx(d, L, 0, params, nullptr, ws, st);
-    UB_TRY(mbconv_forward(enc, at<float>(ws, L.x0), nullptr, d->need_grad != 0));
+    // is_mono (uncrtaints.py:296,418: `--pretrain`, single-date input): no temporal encoder / aggregator, the encoder output IS the
+    // decoder input, so the encoder's residual pass gathers the first decoder PreNorm's statistics
+    UB_TRY(mbconv_forward(enc, at<float>(ws, L.x0), d->is_mono ? at<double>(ws, L.blk[1].stats0) : nullptr, d->need_grad != 0));
     const float* enc_out = at<float>(ws, L.blk[0].out);
+    const float* x = enc_out;
+    if (!d->is_mono) {
     // temporal path
     UB_PROF(KID_MAXPOOL, st, launch_maxpool_fwd(enc_out, at<float>(ws, L.pooled), at<int>(ws, L.pool_idx), L.Ne, d->H, d->W, st));
     UB_PROF(KID_LTAE, st, launch_ltae_fwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), pf(params, UB200_P_LTAE_E),
                            at<int>(ws, L.notpad), at<float>(ws, L.attn), d->B, d->T, d->norm_eps, st));
     const float drop_p = d->training ? d->dropout_p : 0.f;
     UB_PROF(KID_AGGREGATE, st, launch_aggregate_fwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out,
-                                at<float>(ws, L.agg), at<double>(ws, L.blk[1].stats0), d->B, d->T, d->H, d->W, st));
+                                at<float>(ws, L.agg), at<double>(ws, d->use_v ? L.V.scratch_stats : L.blk[1].stats0), d->B, d->T, d->H, d->W, st));
+    x = at<float>(ws, L.agg);
+    if (d->use_v) {
+        UB_TRY(value_path_forward(d, L, params, v_keep_mask, ws, st));
+        x = at<float>(ws, L.V.mix);
+    }
+    }
     // decoder blocks
-    const float* x = at<float>(ws, L.agg);
     for (int i = 1; i < L.nblk; ++i) {
         BlockCtx c = make_ctx(d, L, i, params, nullptr, ws, st);
         double* next_stats = i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr;
@@ -541,6 +672,11 @@ int ub200_forward(const ub200_desc* d, const float* input, const void* const* pa
 
 int ub200_backward(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
                    const float* output, const float* grad_output, void* const* grads, void* ws, size_t ws_bytes, void* stream) {
+    return ub200_backward_v(d, input, params, keep_mask, nullptr, output, grad_output, grads, ws, ws_bytes, stream);
+}
+int ub200_backward_v(const ub200_desc* d, const float* input, const void* const* params, const unsigned char* keep_mask,
+                     const unsigned char* v_keep_mask, const float* output, const float* grad_output, void* const* grads, void* ws,
+                     size_t ws_bytes, void* stream) {
     Layout L;
     UB_TRY(make_layout(d, L));
     if (!input || !params || !output || !grad_output || !grads || !ws || !d->need_grad) return UB_ERR_ARG;
@@ -560,19 +696,32 @@ int ub200_backward(const ub200_desc* d, const float* input, const void* const* p
                            gf(grads, UB200_P_OUT_B), d->B, d->out_dim, P, d->scale_by, d->mean_sigmoid, d->var_eps, num_sms(), st));
     for (int i = L.nblk - 1; i >= 1; --i) {
         BlockCtx c = make_ctx(d, L, i, params, grads, ws, st);
-        const float* x = i == 1 ? at<float>(ws, L.agg) : at<float>(ws, L.blk[i - 1].out);
+        const float* x = i == 1 ? (d->is_mono ? at<float>(ws, L.blk[0].out) : at<float>(ws, d->use_v ? L.V.mix : L.agg)) : at<float>(ws, L.blk[i - 1].out);
         UB_TRY(mbconv_backward(c, x, gA, gB, dn0, du, dz1, partial));
         float* t = gA; gA = gB; gB = t;
     }
-    // gA = dAgg.  Temporal path backward; dEnc accumulates in gB.
+    if (d->is_mono) {         // gA = dEnc directly: make it the encoder block's incoming gradient
+        float* t = gA; gA = gB; gB = t;
+    } else {
+    // gA = dAgg (use_v: the gradient of the include_v output; dAgg = gA . W_a goes to dn0, free at this point).
+    // Temporal path backward; dEnc accumulates in gB.
     const float* enc_out = at<float>(ws, L.blk[0].out);
     const float drop_p = d->training ? d->dropout_p : 0.f;
-    UB_PROF(KID_TEMPORAL_BWD, st, launch_aggregate_bwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out, gA,
+    const float* dagg = gA;
+    if (d->use_v) {
+        UB_TRY(value_path_backward_head(d, L, params, grads, gA, dn0, partial, ws, st));
+        dagg = dn0;
+    }
+    UB_PROF(KID_TEMPORAL_BWD, st, launch_aggregate_bwd(at<float>(ws, L.attn), at<int>(ws, L.notpad), keep_mask, d->seed, d->offset, drop_p, enc_out, dagg,
                                 gB, at<float>(ws, L.dwup), at<float>(ws, L.dattn), d->B, d->T, d->H, d->W, st));
+    if (d->use_v)
+        UB_TRY(value_path_backward_tail(d, L, params, grads, v_keep_mask, partial, ws, st));
+    else
     UB_PROF(KID_TEMPORAL_BWD, st, launch_ltae_bwd(at<float>(ws, L.pooled), pf(params, UB200_P_LTAE_AP), at<float>(ws, L.attn), at<float>(ws, L.dattn),
                            at<float>(ws, L.dpooled), gf(grads, UB200_P_LTAE_AP), gf(grads, UB200_P_LTAE_E), d->B, d->T,
                            d->norm_eps, st));
     UB_PROF(KID_TEMPORAL_BWD, st, launch_maxpool_bwd(at<float>(ws, L.dpooled), at<int>(ws, L.pool_idx), gB, L.Ne, P, st));
+    }
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
     enc.relu_mask_dx = 1;                     // the gram pass then consumes dgn = dX0 * [x0 > 0] directly
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
