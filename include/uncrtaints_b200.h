@@ -90,6 +90,18 @@ enum {
     UB200_BLOCK_STRIDE
 };
 
+/* Per-block parameter offsets with block_type = 'residual' (ResidualConvBlock, uncrtaints.py:24-69; X = in_block.0 / out_block.i): the
+ * same UB200_BLOCK_STRIDE slots hold three ConvLayers l = 0..2 (X.conv1, X.conv2, X.conv3) at l*UB200_R_STRIDE + ... */
+enum {
+    UB200_R_W = 0,         /* X.conv<l+1>.conv.0.weight [128][128][3][3]  3x3, reflect padding (utae.py:478-487) */
+    UB200_R_B,             /* X.conv<l+1>.conv.0.bias   [128]                                                   */
+    UB200_R_N_W,           /* X.conv<l+1>.conv.1.*      [128]  norm (BatchNorm2d / GroupNorm(4))                */
+    UB200_R_N_B,
+    UB200_R_N_RM,
+    UB200_R_N_RV,
+    UB200_R_STRIDE
+};
+
 typedef struct ub200_desc {
     int B, T, C_in, H, W;       /* input [B][T][C_in][H][W]; H, W multiples of 32; T <= 64 (T <= 8: register-resident temporal kernels); C_in <= 16 */
     int n_dec_blocks;           /* len(decoder_widths), default 5 (uncrtaints.py:236); one encoder block */
@@ -111,6 +123,7 @@ typedef struct ub200_desc {
     float dropout_p;            /* 0.1 in training (uncrtaints.py:154), forced to 0 when !training */
     unsigned long long seed;    /* Philox seed / offset for the attention dropout (ignored when keep_mask != NULL) */
     unsigned long long offset;
+    int block_type;             /* 0 = 'mbconv' (default), 1 = 'residual' (uncrtaints.py:253,291-294,324-327; tcgen05 path, fp32 storage only) */
     int use_v;                  /* use_v (uncrtaints.py:252,300-314,414-417): full LTAE2d with a value output, include_v 1x1 convolution */
     float v_dropout_p;          /* nn.Dropout on the MLP-processed values (ltae.py:17,85,129: 0.2), training only */
     int is_mono;                /* is_mono (uncrtaints.py:253,296,418; `--pretrain`): T == 1, no temporal encoder / aggregator -- the encoder
@@ -145,7 +158,7 @@ int ub200_num_param_slots(const ub200_desc* d);
 size_t ub200_workspace_bytes(const ub200_desc* d);
 
 /* Locate a named intermediate inside the workspace (tests / debugging): "x0", "pooled", "pool_idx", "attn",
- * "agg", "notpad", "blk<i>.h1|h2|y|out", and with use_v "v.m" (MLP output [B*1024][128]), "v.mr" ((mean, rstd) of its BatchNorm1d, [B][128][2])
+ * "agg", "notpad", "blk<i>.h1|h2|y|out" (residual blocks: "blk<i>.out|c1|c2|c3" and the (scale, shift) pairs "blk<i>.k1|k2|k3"), and with use_v "v.m" (MLP output [B*1024][128]), "v.mr" ((mean, rstd) of its BatchNorm1d, [B][128][2])
  * and "v.v" (value output [B*1024][128]).  Returns 0 and fills offset/bytes, or UB200_ERR_ARG. */
 int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, size_t* bytes);
 

@@ -53,6 +53,7 @@ class OracleConfig:
     norm_eps: float = 1e-5
     use_v: bool = False             # full LTAE2d with a value output + include_v (uncrtaints.py:300-314,414-417)
     v_dropout_p: float = 0.2        # LTAE2d.dropout on the MLP-processed values (ltae.py:17,85,129)
+    block_type: str = "mbconv"      # 'mbconv' | 'residual' (ResidualConvBlock: three 3x3 ConvLayers, uncrtaints.py:24-69,291-294,324-327)
     is_mono: bool = False           # single date, no temporal encoder (uncrtaints.py:296,418)
     separate_out: bool = False      # separate mean / variance output convolutions (uncrtaints.py:376-379,424-430)
 
@@ -241,6 +242,49 @@ def mbconv(x, p, pre, kind, training, cfg, new_buffers, taps: Optional[dict] = N
     return out
 
 
+def conv3x3_reflect(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d(k=3, padding=1, padding_mode='reflect', bias=True) (utae.py:478-487): dense cross-correlation over the
+    reflect-padded input.  w: [Cout, Cin, 3, 3]."""
+    if FUSED:
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, b)
+    xp = reflect_pad1(x)
+    h, wd = x.shape[-2:]
+    out = b.reshape(1, -1, 1, 1).expand(x.shape[0], -1, h, wd)
+    for i in range(3):
+        for j in range(3):
+            out = out + torch.einsum("nchw,oc->nohw", xp[..., i:i + h, j:j + wd], w[:, :, i, j])
+    return out
+
+
+RELU_MASKS: Optional[dict] = None      # diagnostic, see residual_block
+
+
+def residual_block(x, p, pre, kind, training, cfg, new_buffers, taps: Optional[dict] = None):
+    """ResidualConvBlock (uncrtaints.py:24-69): x + L3(L2(L1(x))), L = ConvLayer = Conv3x3(reflect, bias) -> norm -> ReLU
+    (utae.py:453-497 with last_relu=True; the final ReLU and norm are NOT omitted, see the comments at :55-60).
+    Diagnostic: with the module-level RELU_MASKS = {"<pre>conv<i>": bool [N,128,H,W]} the active set of a layer's ReLU is imposed
+    instead of decided (like ``pool_idx`` / ``v_relu_mask``): on the small test shapes ONE pre-activation within fp32 rounding of
+    zero that an fp32 implementation decides differently from fp64 changes a weight gradient by ~1e-3 (a decoder frame pair has
+    8192 pixels; measured by shifting the threshold by +-1e-6 in fp64), with no visible change of the forward output."""
+    f = x
+    for i in (1, 2, 3):
+        k = f"{pre}conv{i}.conv."
+        f = conv3x3_reflect(f, p[k + "0.weight"], p[k + "0.bias"])
+        f = _norm(f, p, k + "1.", kind, training, cfg, new_buffers)
+        mask = RELU_MASKS.get(f"{pre}conv{i}") if RELU_MASKS is not None else None
+        f = torch.relu(f) if mask is None else f * mask.to(f.dtype)
+    out = x + f
+    if taps is not None:
+        taps[pre + "out"] = out
+    return out
+
+
+def _block(x, p, pre, kind, training, cfg, new_buffers, taps):
+    if cfg.block_type == "residual":
+        return residual_block(x, p, pre, kind, training, cfg, new_buffers, taps)
+    return mbconv(x, p, pre, kind, training, cfg, new_buffers, taps)
+
+
 def positional_table(batch_positions: torch.Tensor, d: int, T: float, repeat: int) -> torch.Tensor:
     """PositionalEncoder (positional_encoding.py:5-31): denominators are built in float32
     (torch.pow on a float32 arange, :11-13) whatever the compute dtype; even -> sin, odd -> cos;
@@ -392,7 +436,7 @@ def forward(p: Dict[str, torch.Tensor], x: torch.Tensor, batch_positions: Option
     if taps is not None:
         taps["pad_mask"], taps["in_conv"] = pad_mask, f
     for i in range(cfg.n_enc_blocks):
-        f = mbconv(f, p, f"in_block.{i}.", cfg.encoder_norm, training, cfg, new_buffers, taps)
+        f = _block(f, p, f"in_block.{i}.", cfg.encoder_norm, training, cfg, new_buffers, taps)
     c = f.shape[1]
     if cfg.is_mono:                                                              # :418 (needs T == 1)
         assert t == 1
@@ -415,7 +459,7 @@ def forward(p: Dict[str, torch.Tensor], x: torch.Tensor, batch_positions: Option
             if taps is not None:
                 taps["v"], taps["mix"] = v, f
     for i in range(cfg.n_dec_blocks):
-        f = mbconv(f, p, f"out_block.{i}.", cfg.decoder_norm, training, cfg, new_buffers, taps)
+        f = _block(f, p, f"out_block.{i}.", cfg.decoder_norm, training, cfg, new_buffers, taps)
     if cfg.separate_out:                                                         # :376-379,424-430
         o = conv1x1(f, p["out_conv_mean_1.conv.conv.0.weight"], p["out_conv_mean_1.conv.conv.0.bias"])
         if cfg.covar_dim > 0:
@@ -614,6 +658,12 @@ def init_params(cfg: OracleConfig, seed: int = 1) -> Dict[str, torch.Tensor]:
     norm("in_conv.conv.conv.1.", w, cfg.encoder_norm)
 
     def block(pre, kind):
+        if cfg.block_type == "residual":
+            for i in (1, 2, 3):
+                p[f"{pre}conv{i}.conv.0.weight"] = xavier((w, w, 3, 3))
+                p[f"{pre}conv{i}.conv.0.bias"] = torch.randn(w, generator=g)
+                norm(f"{pre}conv{i}.conv.1.", w, kind)
+            return
         norm(pre + "conv.norm.", w, kind)
         p[pre + "conv.fn.0.weight"] = xavier((hid, w, 1, 1))
         norm(pre + "conv.fn.1.", hid, kind)

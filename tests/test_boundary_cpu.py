@@ -71,7 +71,7 @@ def test_state_dict_surface_matches_reference():
 def test_unsupported_configurations_raise():
     import uncrtaints_b200 as ub
     kw = dict(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
-    for bad in (dict(block_type="residual"), dict(n_head=4), dict(encoder_widths=[64]),
+    for bad in (dict(block_type="bogus"), dict(n_head=4), dict(encoder_widths=[64]),
                 dict(agg_mode="mean"), dict(out_nonlin_var="relu"), dict(out_conv=[13])):
         with pytest.raises(NotImplementedError):
             ub.UNCRTAINTS(**{**kw, **bad})
@@ -84,10 +84,11 @@ def test_variant_module_trees_match_the_reference_state_dict():
     import uncrtaints_b200 as ub
     from oracle import ref_import, uncrtaints_oracle as O
     kw = dict(input_dim=15, out_conv=[26], out_nonlin_mean=True, out_nonlin_var="softplus", scale_by=10.0)
-    for var in (dict(use_v=True), dict(is_mono=True), dict(separate_out=True), dict(separate_out=True, covmode=None, out_conv=[13])):
+    for var in (dict(use_v=True), dict(is_mono=True), dict(separate_out=True), dict(separate_out=True, covmode=None, out_conv=[13]),
+                dict(block_type="residual"), dict(block_type="residual", use_v=True)):
         net = ub.UNCRTAINTS(**{**kw, **var})
         cfg = O.OracleConfig(use_v=var.get("use_v", False), is_mono=var.get("is_mono", False), separate_out=var.get("separate_out", False),
-                             covmode=var.get("covmode", "diag"))
+                             covmode=var.get("covmode", "diag"), block_type=var.get("block_type", "mbconv"))
         mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
         assert mine == {k: tuple(v.shape) for k, v in O.init_params(cfg).items()}
         if ref_import.available():

@@ -1,4 +1,5 @@
-"""Shared definition of the constructor-variant cases (use_v / is_mono / separate_out; uncrtaints.py:296-338,376-379,414-430):
+"""Shared definition of the constructor-variant cases (use_v / is_mono / separate_out / block_type='residual';
+uncrtaints.py:24-69,291-338,376-379,414-430):
 used by tests/golden/make_variants.py (fixture from the unmodified reference), tests/test_oracle.py (oracle vs fixture / live
 reference) and tests/test_gpu_extras.py (CUDA path vs oracle and fixture)."""
 import torch
@@ -10,7 +11,13 @@ VARIANTS = {
     "use_v_pad_nope": dict(use_v=True, n_dec_blocks=1, positional_encoding=False, pad_last=True, covmode="iso"),
     "is_mono": dict(is_mono=True, n_dec_blocks=1),
     "separate_out": dict(separate_out=True, n_dec_blocks=1),
+    "residual": dict(block_type="residual", n_dec_blocks=1, pad_last=True),
+    "residual_gn_dec": dict(block_type="residual", n_dec_blocks=1, encoder_norm="batch", decoder_norm="group", covmode="iso"),
 }
+
+
+# fixtures of these cases hold outputs and loss only (their gradients are checked against the oracle, which the other cases pin)
+NO_FIXTURE_GRADS = {"residual_gn_dec"}
 
 
 def variant_inputs(kw):
@@ -31,7 +38,8 @@ def reference_model(U, cfg, p, keep, vkeep):
     m = U.UNCRTAINTS(input_dim=cfg.input_dim, decoder_widths=[128] * cfg.n_dec_blocks, out_conv=[13 + cfg.covar_dim],
                      out_nonlin_mean=cfg.out_nonlin_mean, out_nonlin_var="softplus", encoder_norm=cfg.encoder_norm,
                      decoder_norm=cfg.decoder_norm, positional_encoding=cfg.positional_encoding, covmode=cfg.covmode,
-                     scale_by=cfg.scale_by, use_v=cfg.use_v, is_mono=cfg.is_mono, separate_out=cfg.separate_out)
+                     scale_by=cfg.scale_by, use_v=cfg.use_v, is_mono=cfg.is_mono, separate_out=cfg.separate_out,
+                     block_type=cfg.block_type)
     m.load_state_dict(p, strict=True)
     if not cfg.is_mono:
         m.temporal_aggregator.attn_dropout = ref_import.InjectedDropout(keep, p=cfg.dropout_p)

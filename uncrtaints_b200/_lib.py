@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(_HERE, "libuncrtaints_b200.so")
  UB200_B_N1_RV, UB200_B_WDW, UB200_B_N2_W, UB200_B_N2_B, UB200_B_N2_RM, UB200_B_N2_RV, UB200_B_F1, UB200_B_F2, UB200_B_W2,
  UB200_B_N3_W, UB200_B_N3_B, UB200_B_N3_RM, UB200_B_N3_RV, UB200_BLOCK_STRIDE) = range(22)
 
+UB200_R_W, UB200_R_B, UB200_R_N_W, UB200_R_N_B, UB200_R_N_RM, UB200_R_N_RV, UB200_R_STRIDE = range(7)
+
 ERRORS = {-1: "UB200_ERR_ARG (unsupported shape / configuration)", -2: "UB200_ERR_CUDA (kernel launch failed)",
           -3: "UB200_ERR_WORKSPACE (workspace too small)"}
 
@@ -41,7 +43,7 @@ class Desc(C.Structure):
         ("scale_by", C.c_float), ("var_eps", C.c_float), ("pad_value", C.c_float), ("norm_eps", C.c_float),
         ("bn_momentum", C.c_float), ("dropout_p", C.c_float),
         ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
-        ("use_v", C.c_int), ("v_dropout_p", C.c_float), ("is_mono", C.c_int),
+        ("block_type", C.c_int), ("use_v", C.c_int), ("v_dropout_p", C.c_float), ("is_mono", C.c_int),
     ]
 
 

@@ -45,9 +45,9 @@ def _norm_layer(kind: str, channels: int) -> nn.Module:
 class ConvLayer(_Holder):
     """in_conv / out_conv holder: keys ``conv.0`` (Conv2d k=1), ``conv.1`` (norm) (utae.py:453-497)."""
 
-    def __init__(self, cin: int, cout: int, norm: str, last_relu: bool):
+    def __init__(self, cin: int, cout: int, norm: str, last_relu: bool, k: int = 1, p: int = 0):
         super().__init__()
-        layers: List[nn.Module] = [nn.Conv2d(cin, cout, kernel_size=1, padding=0, stride=1, padding_mode="reflect")]
+        layers: List[nn.Module] = [nn.Conv2d(cin, cout, kernel_size=k, padding=p, stride=1, padding_mode="reflect")]
         if norm in ("batch", "group"):
             layers.append(_norm_layer(norm, cout))
         if last_relu:
@@ -61,6 +61,17 @@ class ConvBlock(_Holder):
     def __init__(self, cin: int, cout: int, norm: str, last_relu: bool = True):
         super().__init__()
         self.conv = ConvLayer(cin, cout, norm, last_relu)
+
+
+class ResidualConvBlock(_Holder):
+    """ResidualConvBlock(nkernels=[128, 128], k=3, p=1) holder (uncrtaints.py:24-69): keys ``conv{1,2,3}.conv.0`` (Conv2d 3x3, reflect
+    padding, bias) and ``conv{1,2,3}.conv.1`` (norm); every layer ends in a ReLU."""
+
+    def __init__(self, width: int, norm: str = "batch"):
+        super().__init__()
+        self.conv1 = ConvLayer(width, width, norm, last_relu=True, k=3, p=1)
+        self.conv2 = ConvLayer(width, width, norm, last_relu=True, k=3, p=1)
+        self.conv3 = ConvLayer(width, width, norm, last_relu=True, k=3, p=1)
 
 
 class SE(_Holder):
@@ -271,10 +282,11 @@ class _UncrtaintsFunction(torch.autograd.Function):
 class UNCRTAINTS(nn.Module):
     """Same constructor as the reference (uncrtaints.py:231-254).  Supported: the UnCRtainTS architecture with MBConv blocks
     (encoder_widths=[128], decoder_widths=[128]*k, block_type='mbconv', agg_mode='att_group', n_head=16, d_model=256, d_k=4,
-    reflect padding, group/batch norms, covmode diag|iso|uni|None) and its constructor variants ``use_v`` (full LTAE2d value
-    path + include_v, :300-314,414-417), ``is_mono`` (single date, no temporal encoder, :296,418) and ``separate_out`` (two output
-    convolutions, :376-379,424-430); other combinations (block_type='residual', other widths / aggregation modes) raise
-    NotImplementedError, as the reference does for its own unsupported ones (:320)."""
+    reflect padding, group/batch norms, covmode diag|iso|uni|None) and its constructor variants ``block_type='residual'``
+    (ResidualConvBlock: 3x3 convolutions as implicit GEMMs, :24-69,291-294,324-327), ``use_v`` (full LTAE2d value path + include_v,
+    :300-314,414-417), ``is_mono`` (single date, no temporal encoder, :296,418) and ``separate_out`` (two output convolutions,
+    :376-379,424-430); other combinations (other widths / aggregation modes) raise NotImplementedError, as the reference does
+    for its own unsupported ones (:320)."""
 
     def __init__(self, input_dim, encoder_widths=[128], decoder_widths=[128, 128, 128, 128, 128], out_conv=[S2_BANDS],
                  out_nonlin_mean=False, out_nonlin_var="relu", agg_mode="att_group", encoder_norm="group",
@@ -284,8 +296,12 @@ class UNCRTAINTS(nn.Module):
         super().__init__()
         if list(encoder_widths) != [_WIDTH] or decoder_widths is None or any(w != _WIDTH for w in decoder_widths):
             raise NotImplementedError("B200 path: encoder_widths must be [128] and decoder_widths [128]*k")
-        if block_type != "mbconv" or agg_mode != "att_group":
-            raise NotImplementedError("B200 path: only block_type='mbconv' and agg_mode='att_group' are built")
+        if block_type not in ("mbconv", "residual"):
+            raise NotImplementedError                             # as the reference (uncrtaints.py:294,327)
+        if agg_mode != "att_group":
+            raise NotImplementedError("B200 path: only agg_mode='att_group' is built")
+        if block_type == "residual" and "none" in (encoder_norm, decoder_norm):
+            raise NotImplementedError("B200 path: residual blocks need a group or batch norm")
         if (n_head, d_model, d_k) != (_HEADS, _DMODEL, _DK) or padding_mode != "reflect" or len(out_conv) != 1:
             raise NotImplementedError("B200 path: n_head=16, d_model=256, d_k=4, padding_mode='reflect', single out_conv layer")
         if input_dim > 16:
@@ -300,7 +316,9 @@ class UNCRTAINTS(nn.Module):
         self.input_dim = input_dim
 
         self.in_conv = ConvBlock(input_dim, _WIDTH, norm=encoder_norm)
-        self.in_block = nn.ModuleList([MBConv(_WIDTH, _WIDTH, expansion=2, norm=encoder_norm)])
+        def make_block(norm):                                                            # uncrtaints.py:291-294,324-327
+            return MBConv(_WIDTH, _WIDTH, expansion=2, norm=norm) if block_type == "mbconv" else ResidualConvBlock(_WIDTH, norm=norm)
+        self.in_block = nn.ModuleList([make_block(encoder_norm)])
         if not self.is_mono:                                                              # uncrtaints.py:296-322
             if self.use_v:
                 self.temporal_encoder = LTAE2d(in_channels=_WIDTH, n_head=n_head, d_k=d_k, d_model=d_model, mlp=[d_model, _WIDTH],
@@ -310,7 +328,7 @@ class UNCRTAINTS(nn.Module):
                 self.temporal_encoder = LTAE2dtiny(in_channels=_WIDTH, n_head=n_head, d_k=d_k, d_model=d_model,
                                                    positional_encoding=positional_encoding)
             self.temporal_aggregator = Compact_Temporal_Aggregator(mode=agg_mode)
-        self.out_block = nn.ModuleList([MBConv(_WIDTH, _WIDTH, expansion=2, norm=decoder_norm) for _ in decoder_widths])
+        self.out_block = nn.ModuleList([make_block(decoder_norm) for _ in decoder_widths])
 
         self.covmode = covmode
         covar_dim = {"uni": S2_BANDS, "iso": 1, "diag": S2_BANDS}.get(covmode, 0)      # uncrtaints.py:357-365
@@ -379,6 +397,13 @@ class UNCRTAINTS(nn.Module):
             _lib.UB200_B_N3_W: "conv.fn.8.weight", _lib.UB200_B_N3_B: "conv.fn.8.bias",
             _lib.UB200_B_N3_RM: "conv.fn.8.running_mean", _lib.UB200_B_N3_RV: "conv.fn.8.running_var",
         }
+        if self.block_type == "residual":             # three ConvLayers per block share the block's slot range (UB200_R_*)
+            rel = {}
+            for l in range(3):
+                base, pre = l * _lib.UB200_R_STRIDE, f"conv{l + 1}.conv."
+                rel.update({base + _lib.UB200_R_W: pre + "0.weight", base + _lib.UB200_R_B: pre + "0.bias",
+                            base + _lib.UB200_R_N_W: pre + "1.weight", base + _lib.UB200_R_N_B: pre + "1.bias",
+                            base + _lib.UB200_R_N_RM: pre + "1.running_mean", base + _lib.UB200_R_N_RV: pre + "1.running_var"})
         for bi in range(n_blocks):
             prefix = "in_block.0." if bi == 0 else f"out_block.{bi - 1}."
             for k, v in rel.items():
@@ -404,6 +429,7 @@ class UNCRTAINTS(nn.Module):
         d.norm_eps, d.bn_momentum = 1e-5, 0.1
         # the reference applies the dropout only inside the upsampling branch, i.e. when H > 32 (uncrtaints.py:197-202)
         d.is_mono, d.use_v = int(self.is_mono), int(self.use_v)
+        d.block_type = 1 if self.block_type == "residual" else 0
         d.dropout_p = float(self.temporal_aggregator.attn_dropout.p) if (H > 32 and not self.is_mono) else 0.0
         d.v_dropout_p = float(self.temporal_encoder.dropout.p) if self.use_v else 0.0
         if self.training and ((d.dropout_p > 0 and self._injected_keep_mask is None) or

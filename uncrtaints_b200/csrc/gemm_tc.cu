@@ -23,6 +23,14 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef UB_TRY
+#define UB_TRY(expr)                    \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != UB_OK) return rc__; \
+    } while (0)
+#endif
+
 namespace ub {
 namespace tc {
 
@@ -267,9 +275,110 @@ struct TLoadNormBwdT {         // a = ca*dy + cb*v + cc
 };
 typedef TLoadNormBwdT<float> TLoadNormBwd;
 
+// 3x3 convolution operand (ResidualConvBlock, uncrtaints.py:24-69; nn.Conv2d(k=3, padding=1, padding_mode='reflect'), utae.py:478-487):
+// the GEMM's K index is (tap, channel), k = tap*128 + c, and the operand row of output pixel p for tap (dy, dx) is the input pixel
+// p + (dy, dx) -- reflected at the border (forward, weight gradient) or ZERO outside the image (input gradient: the transposed
+// convolution of the zero-extended output gradient; the adjoint of the reflection is added by conv_fold_kernel).
+// a = relu?(x*scale + shift): the previous ConvLayer's normalisation + ReLU is applied here, in the consumer's prologue.
+// paired: the operand has 256 "channels" = taps (tap0, tap1) side by side (the N operand of the weight-gradient GEMM); tap1 < 0 -> zeros.
+struct TLoadConv {
+    static constexpr int CFK = 128;
+    const float* x; const Coef* coef /* null: identity */; int H, W, relu, zero_pad, paired, tap0, tap1;
+    struct Raw { float a[8]; };
+    __device__ int ncf() const { return paired ? 256 : 128; }
+    __device__ void fill(int n, int /*K*/, float* cf) const {
+        const int Kc = ncf();
+        for (int k = threadIdx.x; k < Kc; k += THREADS) {
+            const Coef c = coef ? coef[(size_t)n * 128 + (k & 127)] : Coef{1.f, 0.f};
+            const int q = cf_pos(k, Kc);
+            cf[q] = c.scale; cf[Kc + q] = c.shift;
+        }
+    }
+    __device__ void issue(size_t row, int /*K*/, int ch0, Raw& r) const {
+        const uint32_t P = (uint32_t)(H * W), row32 = (uint32_t)row;
+        const uint32_t n = row32 / P, p = row32 - n * P;
+        const int y = (int)(p / (uint32_t)W), xx = (int)(p - (uint32_t)y * (uint32_t)W);
+        const int tap = paired ? (ch0 < 128 ? tap0 : tap1) : (ch0 >> 7);
+        int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+        bool ok = tap >= 0;
+        if (zero_pad) {
+            ok = ok && yy >= 0 && yy < H && xs >= 0 && xs < W;
+        } else {
+            yy = yy < 0 ? 1 : (yy >= H ? H - 2 : yy);
+            xs = xs < 0 ? 1 : (xs >= W ? W - 2 : xs);
+        }
+        if (ok) {
+            ld8(x + ((size_t)n * P + (size_t)(yy * W + xs)) * 128 + (ch0 & 127), r.a);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r.a[i] = __int_as_float(0x7fc00000);      // marks "outside": finish() writes zeros
+        }
+    }
+    struct Cf { float sc[8], sh[8]; };
+    __device__ void coefs(int /*K*/, int ch0, const float* cf, Cf& c) const {
+        const int Kc = ncf(), k0 = paired ? ch0 : (ch0 & 127);
+        lds8(cf, Kc, k0, c.sc); lds8(cf + Kc, Kc, k0, c.sh);
+    }
+    __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
+        const bool outside = __float_as_int(r.a[0]) == 0x7fc00000 && __float_as_int(r.a[7]) == 0x7fc00000;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float a = fmaf(r.a[i], c.sc[i], c.sh[i]);
+            if (relu) a = fmaxf(a, 0.f);
+            v[i] = outside ? 0.f : a;
+        }
+    }
+};
+struct TLoadPlain128 {         // a = x (A operand of the convolution weight gradient: the materialised output gradient dc)
+    const float* x;
+    struct Raw { float a[8]; };
+    __device__ void fill(int, int, float*) const {}
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(x + row * K + ch0, r.a); }
+    struct Cf {};
+    __device__ void coefs(int, int, const float*, Cf&) const {}
+    __device__ void finish(const Raw& r, const Cf&, float (&v)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r.a[i];
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // epilogues: thread = one output channel; v[32] = 32 consecutive pixels of that channel
 // ------------------------------------------------------------------------------------------
+struct TEpiBiasStoreStats {    // out = acc + bias[ch]; (sum, sumsq) of out: the 3x3 convolutions of the residual blocks
+    static constexpr int NS = 2;
+    static constexpr int PARTS = 2;
+    float* out; const float* bias; double* stats;
+    struct State { float b; };
+    __device__ void init(int n, int NOUT, int ch, State& st) const { st.b = bias ? bias[ch] : 0.f; }
+    template <int NPX>
+    __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float* v, float* s) const {
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const float o = v[i] + st.b;
+            out[(row0 + i) * NOUT + ch] = o;
+            s[0] += o;
+            s[1] = fmaf(o, o, s[1]);
+        }
+    }
+    __device__ double* dst(int n, int NOUT) const { return stats + (size_t)n * NOUT * NS; }
+};
+struct TEpiStoreAdd {          // out = acc (+ add): input gradient of a 3x3 convolution (+ the residual branch's gradient)
+    static constexpr int NS = 1;
+    static constexpr int PARTS = 2;
+    float* out; const float* add; double* scratch;
+    struct State {};
+    __device__ void init(int, int, int, State&) const {}
+    template <int NPX>
+    __device__ void apply(const State&, size_t row0, int NOUT, int ch, const float* v, float* s) const {
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const size_t o = (row0 + i) * NOUT + ch;
+            out[o] = add ? v[i] + add[o] : v[i];
+        }
+    }
+    __device__ double* dst(int n, int NOUT) const { return scratch + (size_t)n * NOUT * NS; }
+};
 template <class OT>
 struct TEpiStoreStatsT {       // raw output + (sum, sumsq)
     static constexpr int NS = 2;
@@ -360,19 +469,26 @@ struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
 // The (tile, K-block) sequence is software pipelined: the raw loads of step q+1 are issued before step q is
 // converted, so HBM requests stay in flight across the convert / fence / barrier / MMA issue / epilogue of step q.
 // ------------------------------------------------------------------------------------------
-template <int K, int NOUT, class ALoad, class Epi, int PARTS>
+// WSTREAM (the 3x3 convolutions of the residual blocks, K = 9 taps x 128 channels): the weight image (576 KB) does not fit in
+// shared memory, so the [NOUT][64] slab of each K-block is streamed from the (L2-resident) global image into a ring slot next to
+// the activation tile of the same pipeline step -- 4 x 16 bytes per thread and step, prefetched one step ahead like the operands.
+template <int K, int NOUT, class ALoad, class Epi, int PARTS, bool WSTREAM>
 __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __restrict__ wimg, const Epi& ep, int P, int single,
                                              const int bx /* CTA index within the frame */, const int gx /* CTAs per frame */, const int n) {
     constexpr int KB = K / KBLK, MH = NOUT / 128;
-    constexpr int W_BYTES = K * NOUT * 4;                 // hi image + lo image
-    constexpr int W_HALF = K * NOUT * 2;
+    constexpr int W_HALF = K * NOUT * 2;                  // bytes of the hi image (the lo image follows it)
+    constexpr int SLAB = NOUT * 128;                      // one K-block of one image: [NOUT rows][128 B]
+    constexpr int W_BYTES = WSTREAM ? NSTAGE * 2 * SLAB : K * NOUT * 4;   // resident: hi image + lo image; streamed: ring of slabs
+    constexpr int CFK = WSTREAM ? 128 : K;                // coefficient entries per vector
     constexpr int ACC_COLS = MH * TILE_PX;                // TMEM columns per accumulator stage
+    static_assert(!WSTREAM || (2 * SLAB / 16) % THREADS == 0, "slab copy: whole uint4 per thread");
+    constexpr int WPT = WSTREAM ? (2 * SLAB / 16) / THREADS : 1;          // uint4 of a slab pair per thread
     extern __shared__ __align__(1024) char smem_raw[];
     char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
-    char* sW = smem;                                      // [hi|lo][KB][NOUT rows][128 B]
+    char* sW = smem;                                      // [hi|lo][KB][NOUT rows][128 B], or NSTAGE x {hi slab, lo slab}
     char* sA = smem + W_BYTES;                            // NSTAGE x {hi tile 16 KB, lo tile 16 KB}
-    float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);     // 3 x K coefficients (SoA)
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * K);            // free[NSTAGE], accfull[2]
+    float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);     // 3 x CFK coefficients (SoA)
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * CFK);          // free[NSTAGE], accfull[2]
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + NSTAGE + 2);
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
@@ -390,7 +506,20 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
     }
 
     // ---- one-time setup: weights, coefficients, barriers, TMEM ----
-    for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
+    uint4 wraw[WPT];
+    auto w_issue = [&](int kb) {                          // slab pair of K-block kb: uint4 index i < SLAB/16 -> hi image, else lo image
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) {
+            const int i = tid + j * THREADS;
+            const uint4* src = wimg + (i < SLAB / 16 ? (size_t)kb * (SLAB / 16) + i : (size_t)(W_HALF / 16) + (size_t)kb * (SLAB / 16) + (i - SLAB / 16));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wraw[j].x), "=r"(wraw[j].y), "=r"(wraw[j].z), "=r"(wraw[j].w) : "l"(src));
+        }
+    };
+    if constexpr (WSTREAM) {
+        if (Q > 0) w_issue(0);
+    } else {
+        for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
+    }
     al.fill(n, K, sCf);
     if (tid == 0) {
         for (int i = 0; i < NSTAGE + 2; ++i) mbar_init(smem_u32(&sBar[i]), 1);
@@ -457,10 +586,20 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
             al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
             al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
         }
+        uint4 wcur[WPT];
+        if constexpr (WSTREAM) {
+#pragma unroll
+            for (int j = 0; j < WPT; ++j) wcur[j] = wraw[j];
+            if (q + 1 < Q) w_issue((q + 1) % KB);
+        }
         const uint32_t slot = (uint32_t)q % NSTAGE, u = (uint32_t)q / NSTAGE;
         mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);    // MMAs that read this ring slot are done
         char* hi = sA + slot * STAGE_BYTES;
         char* lo = hi + STAGE_BYTES / 2;
+        if constexpr (WSTREAM) {
+#pragma unroll
+            for (int j = 0; j < WPT; ++j) reinterpret_cast<uint4*>(sW + slot * 2 * SLAB)[tid + j * THREADS] = wcur[j];
+        }
         {
             typename ALoad::Cf cfr;                        // this thread's 8 channels of the K-block: one coefficient read for both rows
             al.coefs(K, kb * KBLK + pc8 * 8, sCf, cfr);
@@ -478,7 +617,8 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
         if (tid == 0) {
             tc_fence_after();
             const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
-            const uint32_t a_hi = smem_u32(sW) + kb * (NOUT * 128), a_lo = a_hi + W_HALF;
+            const uint32_t a_hi = WSTREAM ? smem_u32(sW) + slot * 2 * SLAB : smem_u32(sW) + kb * SLAB;
+            const uint32_t a_lo = a_hi + (WSTREAM ? SLAB : W_HALF);
             const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
             // fp16 operands: A/B format fields (bits 7-9, 10-12) = 0 (F16) instead of 1 (BF16)
             const uint32_t idesc = single == SPLIT_F16X3 ? (c_idesc & ~((7u << 7) | (7u << 10))) : c_idesc;
@@ -528,10 +668,10 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-template <int K, int NOUT, class ALoad, class Epi, int PARTS>
+template <int K, int NOUT, class ALoad, class Epi, int PARTS, bool WSTREAM>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo image, K*NOUT*4 bytes */, Epi ep, int P, int single) {
-    gemm_tc_body<K, NOUT, ALoad, Epi, PARTS>(al, wimg, ep, P, single, (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y);
+    gemm_tc_body<K, NOUT, ALoad, Epi, PARTS, WSTREAM>(al, wimg, ep, P, single, (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -557,11 +697,12 @@ static int blocks_per_frame(int N, int tiles) {
     return g < 1 ? 1 : g;
 }
 
-template <int K, int NOUT, class ALoad, class Epi>
+template <int K, int NOUT, class ALoad, class Epi, bool WSTREAM = false>
 static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, int single, cudaStream_t st) {
     if (P % TILE_PX != 0) return UB_ERR_ARG;
-    constexpr size_t smem = (size_t)K * NOUT * 4 + NSTAGE * STAGE_BYTES + 3 * K * sizeof(float) + 8 * 8 + 16 + 1024;
-    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS>;
+    constexpr size_t wbytes = WSTREAM ? (size_t)NSTAGE * 2 * NOUT * 128 : (size_t)K * NOUT * 4;
+    constexpr size_t smem = wbytes + NSTAGE * STAGE_BYTES + 3 * (WSTREAM ? 128 : K) * sizeof(float) + 8 * 8 + 16 + 1024;
+    auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS, WSTREAM>;
     UB_SET_SMEM(kern, smem);
     const int tiles = P / TILE_PX;
     const dim3 grid(blocks_per_frame(N, tiles), N);
@@ -1040,7 +1181,79 @@ __global__ void prep_weights_kernel(const float* __restrict__ src, uint16_t* __r
     img[(off + (size_t)rows * K * 2) / 2] = lbits;
 }
 
+// Weight image of a 3x3 convolution, src = nn.Conv2d weight [co][ci][3][3] (128 x 128 x 9).  The GEMM's K index is k = tap*128 + c.
+//   dgrad == 0 (forward):        M[r = co][k = tap*128 + ci] = W[co][ci][tap]                       out[p] = sum_tap W_tap . in[p + tap]
+//   dgrad == 1 (input gradient): M[r = ci][k = tap*128 + co] = W[co][ci][8 - tap]                   din[q] = sum_tap W_(-tap)^T . dout[q + tap]
+// Same hi/lo split and K-major SWIZZLE_128B layout as prep_weights_kernel, rows = 128, K = 1152.
+__global__ void prep_conv_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ img, int dgrad, int f16) {
+    constexpr int rows = 128, K = 9 * 128;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * K) return;
+    const int r = i / K, k = i % K, tap = k / 128, c = k % 128;
+    const float w = dgrad ? src[((size_t)c * 128 + r) * 9 + (8 - tap)] : src[((size_t)r * 128 + c) * 9 + tap];
+    uint16_t hbits, lbits;
+    if (f16) {
+        const float ws = fminf(fmaxf(w, -65504.f), 65504.f);
+        const __half hh = __float2half_rn(ws);
+        const __half lh = __float2half_rn(fminf(fmaxf(w - __half2float(hh), -65504.f), 65504.f));
+        hbits = __half_as_ushort(hh);
+        lbits = __half_as_ushort(lh);
+    } else {
+        const __nv_bfloat16 hb = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lb = __float2bfloat16_rn(w - __bfloat162float(hb));
+        hbits = __bfloat16_as_ushort(hb);
+        lbits = __bfloat16_as_ushort(lb);
+    }
+    const int kb = k / KBLK, kk = k % KBLK;
+    const size_t off = ((size_t)kb * rows + r) * 128 + (((kk / 8) ^ (r & 7)) << 4) + (kk % 8) * 2;   // bytes
+    img[off / 2] = hbits;
+    img[(off + (size_t)rows * K * 2) / 2] = lbits;
+}
+
+// dW[co][ci][tapA | tapB] += sum over the CTA partials [co][j*128 + ci] (j = 0: tapA, 1: tapB; tapB < 0: absent)
+__global__ void reduce_conv_partials_kernel(const float* __restrict__ partial, float* __restrict__ grad, int tapA, int tapB, int nparts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * 256) return;
+    const int co = i / 256, n = i % 256, tap = n < 128 ? tapA : tapB;
+    if (tap < 0) return;
+    float s = 0.f;
+    for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * 128 * 256 + i];
+    grad[((size_t)co * 128 + (n & 127)) * 9 + tap] += s;
+}
+
 }  // namespace tc
+
+// ---- 3x3 convolutions of the residual blocks (uncrtaints.py:24-69) on the tcgen05 path ----
+int tc_prep_conv_weights(const float* w, void* img, int dgrad, int f16, cudaStream_t st) {
+    tc::prep_conv_weights_kernel<<<(128 * 1152 + 255) / 256, 256, 0, st>>>(w, static_cast<uint16_t*>(img), dgrad, f16);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+// c[N][P][128] = conv3x3_reflect(relu?(x*scale + shift)) + bias; stats[N][128][2] += column (sum, sumsq).  coef may be null (plain x).
+int tc_conv3x3_fwd(const float* x, const Coef* coef, int relu, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W,
+                   int single, cudaStream_t st) {
+    tc::TLoadConv al{x, coef, H, W, relu, 0, 0, 0, 0};
+    return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConv, tc::TEpiBiasStoreStats, true>(al, wimg, tc::TEpiBiasStoreStats{c, bias, stats}, N, H * W, single, st);
+}
+// din[N][P][128] = transposed 3x3 convolution of the zero-extended dc (+ add); the reflection's adjoint is added by launch_conv_fold
+int tc_conv3x3_dgrad(const float* dc, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,
+                     cudaStream_t st) {
+    tc::TLoadConv al{dc, nullptr, H, W, 0, 1, 0, 0, 0};
+    return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConv, tc::TEpiStoreAdd, true>(al, wimg_t, tc::TEpiStoreAdd{din, add, scratch}, N, H * W, single, st);
+}
+// dW[co][ci][tap] += sum_p dc[p][co] * relu?(x*scale + shift)[reflect(p + tap)][ci] for all 9 taps (five launches of tap pairs)
+int tc_conv3x3_wgrad(const float* dc, const float* x, const Coef* coef, int relu, float* partial, int max_parts, float* dw, int N, int H, int W,
+                     int single, cudaStream_t st) {
+    for (int t = 0; t < 9; t += 2) {
+        const int tapB = t + 1 < 9 ? t + 1 : -1;
+        tc::TLoadConv lb{x, coef, H, W, relu, 0, 1, t, tapB};
+        int nparts = 0;
+        UB_TRY(tc::launch_wgrad_tc(tc::TLoadPlain128{dc}, lb, partial, max_parts, N, H * W, UB_HID, 1, single, &nparts, st));
+        tc::reduce_conv_partials_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(partial, dw, t, tapB, nparts);
+        UB_CHECK_LAUNCH();
+    }
+    return UB_OK;
+}
 
 int tc_prep_weights(const float* src, void* img, int rows, int K, int transpose, int f16, cudaStream_t st) {
     tc::prep_weights_kernel<<<(rows * K + 255) / 256, 256, 0, st>>>(src, static_cast<uint16_t*>(img), rows, K, transpose, f16);

@@ -77,8 +77,19 @@ struct BlockWs {
     size_t bstats0, bstats1, bstats2, bstats3, sums3, bc0, bc1, bc2, bc3, dmp;
 };
 
+// Workspace slices of one residual block (block_type = 'residual'): three ConvLayers conv3x3 -> norm -> ReLU (uncrtaints.py:24-69)
+struct ResWs {
+    size_t c[3], out;                       // saved activations: the three convolution outputs (pre-norm) and the block output
+    size_t stats[3], coef[3], mr[3];        // forward statistics (zero arena), coefficients
+    size_t bstats[3], bc[3];                // backward statistics (zero arena), coefficients
+    size_t wimg[3], wimgT[3];               // tcgen05 weight images (forward: [co][tap, ci]; input gradient: [ci][tap, co], taps mirrored), 576 KB each
+};
+
 struct Layout {
     int Ne, B, P, nblk, Nmax, max_parts;
+    int residual;               // block_type: 0 = MBConv, 1 = ResidualConvBlock
+    ResWs rblk[1 + 16];
+    size_t res_scratch;         // [Nmax][128] doubles: statistics sink of the input-gradient GEMM epilogue
     size_t hes;                 // bytes per element of the 256-channel hidden tensors h1, h2, du, dz1 (4, or 2 with gemm_backend bit 5)
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
@@ -154,19 +165,38 @@ static int make_layout(const ub200_desc* d, Layout& L) {
     if ((d->gemm_backend & 3) != 0 && (d->gemm_backend & 3) != 3) return UB_ERR_ARG;
     if ((d->gemm_backend & 32) && (d->gemm_backend & 3) != 3) return UB_ERR_ARG;
     L.hes = (d->gemm_backend & 32) ? 2 : 4;
+    L.residual = d->block_type == 1;
+    if (d->block_type != 0 && d->block_type != 1) return UB_ERR_ARG;
+    // the residual blocks exist on the tcgen05 path only, with fp32 storage
+    if (L.residual && ((d->gemm_backend & 3) != 3 || (d->gemm_backend & 32))) return UB_ERR_ARG;
     const size_t P = (size_t)L.P;
     Bump b;
     L.fwd_zero_begin = b.off;
     L.notpad = b.take((size_t)L.Ne * sizeof(int));
     L.stats_c0 = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
     L.mom_in = b.take(inconv_moments_bytes(L.Ne));
-    for (int i = 0; i < L.nblk; ++i) block_fwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
+    for (int i = 0; i < L.nblk; ++i) {
+        const int N = i == 0 ? L.Ne : L.B;
+        if (L.residual) {
+            L.blk[i].stats0 = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));       // sink of the producers' "next PreNorm" sums
+            for (int l = 0; l < 3; ++l) L.rblk[i].stats[l] = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
+        } else {
+            block_fwd_stats(b, L.blk[i], N);
+        }
+    }
     if (d->use_v) L.V.stats_m = b.take((size_t)L.B * UB_WIDTH * 2 * sizeof(double));
     L.fwd_zero_end = b.off;
     L.bwd_zero_begin = b.off;
     L.bstats_in = b.take((size_t)L.Ne * UB_WIDTH * 2 * sizeof(double));
     L.gram_in = b.take(inconv_gram_bytes(L.Ne));
-    for (int i = 0; i < L.nblk; ++i) block_bwd_stats(b, L.blk[i], i == 0 ? L.Ne : L.B);
+    for (int i = 0; i < L.nblk; ++i) {
+        const int N = i == 0 ? L.Ne : L.B;
+        if (L.residual) {
+            for (int l = 0; l < 3; ++l) L.rblk[i].bstats[l] = b.take((size_t)N * UB_WIDTH * 2 * sizeof(double));
+        } else {
+            block_bwd_stats(b, L.blk[i], N);
+        }
+    }
     if (d->use_v) L.V.bstats_m = b.take((size_t)L.B * UB_WIDTH * 2 * sizeof(double));
     L.bwd_zero_end = b.off;
     L.coef_in = b.take((size_t)L.Ne * UB_WIDTH * sizeof(Coef));
@@ -195,7 +225,23 @@ static int make_layout(const ub200_desc* d, Layout& L) {
             L.V.dxn = b.take(NQ * UB_WIDTH * 4);
         }
     }
-    if (d->need_grad) {
+    if (L.residual) {
+        for (int i = 0; i < L.nblk; ++i) {
+            const size_t N = i == 0 ? L.Ne : L.B;
+            ResWs& r = L.rblk[i];
+            for (int l = 0; l < 3; ++l) {
+                r.c[l] = b.take(N * P * UB_WIDTH * sizeof(float));
+                r.coef[l] = b.take(N * UB_WIDTH * sizeof(Coef));
+                r.mr[l] = b.take(N * UB_WIDTH * sizeof(MeanRstd));
+                r.bc[l] = b.take(N * UB_WIDTH * sizeof(BCoef));
+                r.wimg[l] = b.take((size_t)9 * UB_WIDTH * UB_WIDTH * 4);
+                r.wimgT[l] = b.take((size_t)9 * UB_WIDTH * UB_WIDTH * 4);
+            }
+            r.out = b.take(N * P * UB_WIDTH * sizeof(float));
+            L.blk[i].out = r.out;
+        }
+        L.res_scratch = b.take((size_t)L.Nmax * UB_WIDTH * sizeof(double));
+    } else if (d->need_grad) {
         for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, true, L.hes);
     } else {
         // forward only (validation / inference): nothing is saved for a backward, so all blocks share one set of hidden
@@ -404,6 +450,65 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
     atomicAdd(&stats[((size_t)n * C + ch) * 2 + which], t);
 }
 
+// ---- block_type = 'residual' (ResidualConvBlock, uncrtaints.py:24-69): x + L3(L2(L1(x))), L = conv3x3(reflect, bias) -> norm -> ReLU ----
+// Per ConvLayer ONE tensor is materialised (the convolution output c, with its statistics from the GEMM epilogue); the norm + ReLU
+// is applied in the next convolution's operand loader, the last one in the residual pass.  The convolutions are implicit GEMMs
+// over (tap, channel) on the tcgen05 path (gemm_tc.cu: TLoadConv, streamed weight slabs).
+static int residual_forward(const ub200_desc* d, const Layout& L, int i, const void* const* params, const float* x, double* next_stats,
+                            void* ws, cudaStream_t st) {
+    const ResWs& w = L.rblk[i];
+    const int N = i == 0 ? L.Ne : L.B, groups = i == 0 ? d->enc_groups : d->dec_groups, P = L.P;
+    const void* const* p = params + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE;
+    const int single = (d->gemm_backend & 4) ? 1 : 2;
+    const float* in = x;
+    const Coef* incoef = nullptr;
+    for (int l = 0; l < 3; ++l) {
+        const void* const* q = p + l * UB200_R_STRIDE;
+        if (!pf(q, UB200_R_W) || !pf(q, UB200_R_B) || !pf(q, UB200_R_N_W)) return UB_ERR_ARG;
+        UB_TRY(tc_prep_conv_weights(pf(q, UB200_R_W), at<char>(ws, w.wimg[l]), 0, single == 2, st));
+        if (d->need_grad) UB_TRY(tc_prep_conv_weights(pf(q, UB200_R_W), at<char>(ws, w.wimgT[l]), 1, 0, st));
+        UB_PROF(KID_GEMM1_FWD, st, tc_conv3x3_fwd(in, incoef, l > 0, at<char>(ws, w.wimg[l]), pf(q, UB200_R_B), at<float>(ws, w.c[l]),
+                                                  at<double>(ws, w.stats[l]), N, d->H, d->W, single, st));
+        UB_TRY(launch_norm_finalize(at<double>(ws, w.stats[l]), pf(q, UB200_R_N_W), pf(q, UB200_R_N_B), pfm(q, UB200_R_N_RM), pfm(q, UB200_R_N_RV),
+                                    at<Coef>(ws, w.coef[l]), at<MeanRstd>(ws, w.mr[l]), N, UB_WIDTH, groups, (double)P, d->norm_eps,
+                                    d->bn_momentum, d->training, st));
+        in = at<float>(ws, w.c[l]);
+        incoef = at<Coef>(ws, w.coef[l]);
+    }
+    UB_PROF(KID_RESIDUAL_FWD, st, launch_residual_relu_fwd(x, at<float>(ws, w.c[2]), at<Coef>(ws, w.coef[2]), at<float>(ws, w.out), next_stats, N, P, st));
+    return UB_OK;
+}
+// dout -> dx (may not alias); dc: [N][P][128] scratch for the materialised convolution output gradient; t0, t1: two more such buffers
+static int residual_backward(const ub200_desc* d, const Layout& L, int i, const void* const* params, void* const* grads, const float* x,
+                             const float* dout, float* dx, float* dc, float* t0, float* t1, float* partial, void* ws, cudaStream_t st) {
+    const ResWs& w = L.rblk[i];
+    const int N = i == 0 ? L.Ne : L.B, groups = i == 0 ? d->enc_groups : d->dec_groups, P = L.P;
+    const void* const* p = params + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE;
+    void* const* g = grads + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE;
+    const int single = (d->gemm_backend & 4) != 0;
+    const float* dy = dout;
+    for (int l = 2; l >= 0; --l) {
+        const void* const* q = p + l * UB200_R_STRIDE;
+        void* const* gq = g + l * UB200_R_STRIDE;
+        UB_PROF(KID_NORM_BWD_STATS, st, launch_relu_norm_bwd_stats(dy, at<float>(ws, w.c[l]), at<Coef>(ws, w.coef[l]), at<MeanRstd>(ws, w.mr[l]),
+                                                                   at<double>(ws, w.bstats[l]), N, P, st));
+        UB_TRY(launch_norm_finalize_bwd(at<double>(ws, w.bstats[l]), pf(q, UB200_R_N_W), at<MeanRstd>(ws, w.mr[l]), at<BCoef>(ws, w.bc[l]),
+                                        gf(gq, UB200_R_N_W), gf(gq, UB200_R_N_B), N, UB_WIDTH, groups, (double)P, d->training, st));
+        UB_PROF(KID_RESIDUAL_BWD, st, launch_relu_norm_bwd_apply(dy, at<float>(ws, w.c[l]), at<Coef>(ws, w.coef[l]), at<BCoef>(ws, w.bc[l]), dc,
+                                                                 gf(gq, UB200_R_B), N, P, st));
+        const float* in = l == 0 ? x : at<float>(ws, w.c[l - 1]);
+        const Coef* incoef = l == 0 ? nullptr : at<Coef>(ws, w.coef[l - 1]);
+        if (gf(gq, UB200_R_W))
+            UB_PROF(KID_WGRAD1, st, tc_conv3x3_wgrad(dc, in, incoef, l > 0, partial, L.max_parts, gf(gq, UB200_R_W), N, d->H, d->W, single, st));
+        float* din = l == 0 ? dx : (l == 2 ? t0 : t1);
+        UB_PROF(KID_GEMM1_BWD, st, tc_conv3x3_dgrad(dc, at<char>(ws, w.wimgT[l]), l == 0 ? dout : nullptr, din, at<double>(ws, L.res_scratch), N,
+                                                    d->H, d->W, single, st));
+        UB_TRY(launch_conv_fold(dc, pf(q, UB200_R_W), din, N, d->H, d->W, st));
+        dy = din;
+    }
+    return UB_OK;
+}
+
 // ---- use_v: full LTAE2d value path + include_v (ltae.py:96-141, uncrtaints.py:414-417); kernels in ltae_v.cu ----
 static int value_path_forward(const ub200_desc* d, const Layout& L, const void* const* params, const unsigned char* v_keep_mask, void* ws,
                               cudaStream_t st) {
@@ -581,6 +686,12 @@ int ub200_workspace_tap(const ub200_desc* d, const char* name, size_t* offset, s
     char what[16];
     if (sscanf(name, "blk%d.%15s", &bi, what) == 2 && bi >= 0 && bi < L.nblk) {
         const size_t N = bi == 0 ? L.Ne : L.B;
+        if (L.residual) {           // residual blocks: the block output and the three convolution outputs c1..c3
+            if (!strcmp(what, "out")) { *offset = L.rblk[bi].out; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
+            if (what[0] == 'c' && what[1] >= '1' && what[1] <= '3' && !what[2]) { *offset = L.rblk[bi].c[what[1] - '1']; *bytes = N * P * UB_WIDTH * 4; return UB_OK; }
+            if (what[0] == 'k' && what[1] >= '1' && what[1] <= '3' && !what[2]) { *offset = L.rblk[bi].coef[what[1] - '1']; *bytes = N * UB_WIDTH * sizeof(Coef); return UB_OK; }
+            return UB_ERR_ARG;
+        }
         const BlockWs& w = L.blk[bi];
         // forward-only layout: hidden buffers are shared by all blocks and decoder outputs ping-pong; only the encoder output and
         // the last two decoder outputs still hold what their name says after the call
@@ -638,6 +749,9 @@ int ub200_forward_v(const ub200_desc* d, const float* input, const void* const* 
     BlockCtx enc = make_ctx(d, L, 0, params, nullptr, ws, st);
     // is_mono (uncrtaints.py:296,418: `--pretrain`, single-date input): no temporal encoder / aggregator, the encoder output IS the
     // decoder input, so the encoder's residual pass gathers the first decoder PreNorm's statistics
+    if (L.residual)
+        UB_TRY(residual_forward(d, L, 0, params, at<float>(ws, L.x0), nullptr, ws, st));
+    else
     UB_TRY(mbconv_forward(enc, at<float>(ws, L.x0), d->is_mono ? at<double>(ws, L.blk[1].stats0) : nullptr, d->need_grad != 0));
     const float* enc_out = at<float>(ws, L.blk[0].out);
     const float* x = enc_out;
@@ -659,7 +773,9 @@ int ub200_forward_v(const ub200_desc* d, const float* input, const void* const* 
     for (int i = 1; i < L.nblk; ++i) {
         BlockCtx c = make_ctx(d, L, i, params, nullptr, ws, st);
         double* next_stats = i + 1 < L.nblk ? at<double>(ws, L.blk[i + 1].stats0) : nullptr;
-        if (!d->training && !d->need_grad && d->dec_groups == 0 && (d->gemm_backend & 3) == 3)
+        if (L.residual)
+            UB_TRY(residual_forward(d, L, i, params, x, nullptr, ws, st));
+        else if (!d->training && !d->need_grad && d->dec_groups == 0 && (d->gemm_backend & 3) == 3)
             UB_TRY(mbconv_forward_eval_bn(c, x, next_stats));
         else
             UB_TRY(mbconv_forward(c, x, next_stats, d->need_grad != 0));
@@ -697,6 +813,10 @@ int ub200_backward_v(const ub200_desc* d, const float* input, const void* const*
     for (int i = L.nblk - 1; i >= 1; --i) {
         BlockCtx c = make_ctx(d, L, i, params, grads, ws, st);
         const float* x = i == 1 ? (d->is_mono ? at<float>(ws, L.blk[0].out) : at<float>(ws, d->use_v ? L.V.mix : L.agg)) : at<float>(ws, L.blk[i - 1].out);
+        if (L.residual)
+            UB_TRY(residual_backward(d, L, i, params, grads, x, gA, gB, dn0, static_cast<float*>(du), static_cast<float*>(du) + (size_t)L.Nmax * P * UB_WIDTH,
+                                     partial, ws, st));
+        else
         UB_TRY(mbconv_backward(c, x, gA, gB, dn0, du, dz1, partial));
         float* t = gA; gA = gB; gB = t;
     }
@@ -724,9 +844,13 @@ int ub200_backward_v(const ub200_desc* d, const float* input, const void* const*
     }
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
     enc.relu_mask_dx = 1;                     // the gram pass then consumes dgn = dX0 * [x0 > 0] directly
+    if (L.residual)
+        UB_TRY(residual_backward(d, L, 0, params, grads, at<float>(ws, L.x0), gB, gA, dn0, static_cast<float*>(du),
+                                 static_cast<float*>(du) + (size_t)L.Nmax * P * UB_WIDTH, partial, ws, st));
+    else
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));
-    // in_conv backward (no input gradient)
-    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, nullptr /* ReLU mask already applied by residual_bwd */, gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
+    // in_conv backward (no input gradient); MBConv: the ReLU mask of in_conv was applied by the encoder block's residual_bwd
+    UB_PROF(KID_INCONV_BWD, st, launch_inconv_bwd_gram(input, L.residual ? at<float>(ws, L.x0) : nullptr, gA, pf(params, UB200_P_IN_W), pf(params, UB200_P_IN_B),
                                at<MeanRstd>(ws, L.mr_in), at<double>(ws, L.gram_in), at<double>(ws, L.bstats_in), L.Ne, d->C_in, P, st));
     UB_TRY(launch_norm_finalize_bwd(at<double>(ws, L.bstats_in), pf(params, UB200_P_IN_NORM_W), at<MeanRstd>(ws, L.mr_in),
                                     at<BCoef>(ws, L.bc_in), gf(grads, UB200_P_IN_NORM_W), gf(grads, UB200_P_IN_NORM_B), L.Ne,

@@ -266,6 +266,137 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Residual blocks (ResidualConvBlock, uncrtaints.py:24-69): ConvLayer = conv3x3 -> norm -> ReLU.  C = 128.
+//   R-fwd : out = x + relu(c3*scale3 + shift3)                                     (uncrtaints.py:64-68)
+//   R-bwd1: bstats[n][ch] += (sum dz, sum dz * c_hat), dz = dy * [c*scale + shift > 0]   (ReLU + norm backward statistics)
+//   R-bwd2: dc = a*dz + b*c + cc (norm backward applied), dbias[ch] += sum dc       (the convolution's output gradient, materialised once
+//           because its input-gradient GEMM reads every element nine times)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) residual_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ c3,
+                                                                 const Coef* __restrict__ coef3, float* __restrict__ out, double* out_stats,
+                                                                 int P, int chunk) {
+    constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[2 * ROWS * C];
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    const Coef k0 = coef3[(size_t)n * C + c4 * 4 + 0], k1 = coef3[(size_t)n * C + c4 * 4 + 1],
+               k2 = coef3[(size_t)n * C + c4 * 4 + 2], k3 = coef3[(size_t)n * C + c4 * 4 + 3];
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    const size_t base = (size_t)n * P * C + c4 * 4;
+#pragma unroll 4
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 xv = ld4_stream(x + base + (size_t)p * C);
+        const float4 yv = ld4_stream(c3 + base + (size_t)p * C);
+        float4 o;
+        o.x = xv.x + fmaxf(fmaf(yv.x, k0.scale, k0.shift), 0.f);
+        o.y = xv.y + fmaxf(fmaf(yv.y, k1.scale, k1.shift), 0.f);
+        o.z = xv.z + fmaxf(fmaf(yv.z, k2.scale, k2.shift), 0.f);
+        o.w = xv.w + fmaxf(fmaf(yv.w, k3.scale, k3.shift), 0.f);
+        st4(out + base + (size_t)p * C, o);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        q.x += o.x * o.x; q.y += o.y * o.y; q.z += o.z * o.z; q.w += o.w * o.w;
+    }
+    if (out_stats) block_reduce_cols2<C>(s, q, out_stats + (size_t)n * C * 2, smem);
+}
+__global__ void __launch_bounds__(256) relu_norm_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ c,
+                                                                   const Coef* __restrict__ coef, const MeanRstd* __restrict__ mr,
+                                                                   double* bstats, int P, int chunk) {
+    constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[2 * ROWS * C];
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    Coef k[4]; MeanRstd m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k[i] = coef[(size_t)n * C + c4 * 4 + i]; m[i] = mr[(size_t)n * C + c4 * 4 + i]; }
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    const size_t base = (size_t)n * P * C + c4 * 4;
+#pragma unroll 4
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 d4 = ld4_stream(dy + base + (size_t)p * C);
+        const float4 c4v = ld4_stream(c + base + (size_t)p * C);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w}, cv[4] = {c4v.x, c4v.y, c4v.z, c4v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float dz = fmaf(cv[i], k[i].scale, k[i].shift) > 0.f ? d[i] : 0.f;
+            s[i] += dz;
+            q[i] = fmaf(dz, (cv[i] - m[i].mean) * m[i].rstd, q[i]);
+        }
+    }
+    block_reduce_cols2<C>(make_float4(s[0], s[1], s[2], s[3]), make_float4(q[0], q[1], q[2], q[3]), bstats + (size_t)n * C * 2, smem);
+}
+__global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ c,
+                                                                   const Coef* __restrict__ coef, const BCoef* __restrict__ bc,
+                                                                   float* __restrict__ dc, float* dbias, int P, int chunk) {
+    constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[ROWS * C];
+    const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    Coef k[4]; BCoef b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k[i] = coef[(size_t)n * C + c4 * 4 + i]; b[i] = bc[(size_t)n * C + c4 * 4 + i]; }
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    float s[4] = {0, 0, 0, 0};
+    const size_t base = (size_t)n * P * C + c4 * 4;
+#pragma unroll 4
+    for (int p = p0 + r; p < p1; p += ROWS) {
+        const float4 d4 = ld4_stream(dy + base + (size_t)p * C);
+        const float4 c4v = ld4_stream(c + base + (size_t)p * C);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w}, cv[4] = {c4v.x, c4v.y, c4v.z, c4v.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float dz = fmaf(cv[i], k[i].scale, k[i].shift) > 0.f ? d[i] : 0.f;
+            o[i] = fmaf(b[i].a, dz, fmaf(b[i].b, cv[i], b[i].c));
+            s[i] += o[i];
+        }
+        st4(dc + base + (size_t)p * C, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    if (dbias) {
+        reinterpret_cast<float4*>(smem)[r * Q + c4] = make_float4(s[0], s[1], s[2], s[3]);
+        __syncthreads();
+        if (threadIdx.x < C) {
+            float t = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) t += smem[rr * C + threadIdx.x];
+            atomicAdd(&dbias[threadIdx.x], t);
+        }
+    }
+}
+
+// Adjoint of the reflection of padding_mode='reflect' for the input gradient of a 3x3 convolution.  The main kernel computes the
+// transposed convolution g of the zero-extended output gradient on the H x W grid; the same g on the one-pixel ring AROUND the image
+// belongs to the pixels the ring reflects onto: din[(1, x')] += g[(-1, x)], din[(H-2, x')] += g[(H, x)], din[(y, 1)] += g[(y, -1)],
+// din[(y, W-2)] += g[(y, W)], x' = reflect(x) for x in [-1, W] (corners included in the two rows).
+//   g[r][ci] = sum_tap sum_co W[co][ci][tap] * dc[r - tap][co]   over the taps whose source pixel r - tap lies inside the image.
+// grid (ring positions, N); 128 threads = ci.  Ring position index: [0, W+2) top row, [W+2, 2W+4) bottom row, then H left, H right.
+__global__ void __launch_bounds__(128) conv_fold_kernel(const float* __restrict__ dc, const float* __restrict__ w /* [co][ci][9] */,
+                                                         float* din, int H, int W) {
+    __shared__ float sdc[3][UB_WIDTH];
+    const int n = blockIdx.y, pos = blockIdx.x, ci = threadIdx.x;
+    int ry, rx, ty = 0, tx = 0;          // ring pixel and the target pixel it reflects onto
+    if (pos < W + 2) { ry = -1; rx = pos - 1; ty = 1; }
+    else if (pos < 2 * (W + 2)) { ry = H; rx = pos - (W + 2) - 1; ty = H - 2; }
+    else if (pos < 2 * (W + 2) + H) { ry = pos - 2 * (W + 2); rx = -1; ty = ry; }
+    else { ry = pos - 2 * (W + 2) - H; rx = W; ty = ry; }
+    tx = rx < 0 ? 1 : (rx >= W ? W - 2 : rx);
+    // source pixels p = r - (dy, dx): at most three lie inside the image (one row or one column of taps)
+    int taps[3], np = 0;
+    size_t src[3];
+    for (int t = 0; t < 9; ++t) {
+        const int py = ry - (t / 3 - 1), px = rx - (t % 3 - 1);
+        if (py >= 0 && py < H && px >= 0 && px < W && np < 3) { taps[np] = t; src[np] = ((size_t)n * H * W + (size_t)py * W + px) * UB_WIDTH; ++np; }
+    }
+    for (int i = 0; i < np; ++i) sdc[i][ci] = dc[src[i] + ci];
+    __syncthreads();
+    float acc = 0.f;
+    for (int i = 0; i < np; ++i) {
+        const float* wt = w + (size_t)ci * 9 + taps[i];
+#pragma unroll 8
+        for (int co = 0; co < UB_WIDTH; ++co) acc = fmaf(wt[(size_t)co * UB_WIDTH * 9], sdc[i][co], acc);
+    }
+    atomicAdd(&din[((size_t)n * H * W + (size_t)ty * W + tx) * UB_WIDTH + ci], acc);
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 static inline int chunk_for(int P) { return P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64); }
@@ -314,6 +445,31 @@ int launch_residual_bwd(const float* dout, const float* dn0, const float* x, con
                         int relu_mask, cudaStream_t st) {
     const int chunk = chunk_for(P);
     residual_bwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk, relu_mask);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+int launch_residual_relu_fwd(const float* x, const float* c3, const Coef* coef3, float* out, double* out_stats, int N, int P, cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    residual_relu_fwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(x, c3, coef3, out, out_stats, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_relu_norm_bwd_stats(const float* dy, const float* c, const Coef* coef, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    relu_norm_bwd_stats_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, c, coef, mr, bstats, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, float* dc, float* dbias, int N, int P,
+                               cudaStream_t st) {
+    const int chunk = chunk_for(P);
+    relu_norm_bwd_apply_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, c, coef, bc, dc, dbias, P, chunk);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+int launch_conv_fold(const float* dc, const float* w, float* din, int N, int H, int W, cudaStream_t st) {
+    conv_fold_kernel<<<dim3(2 * (W + 2) + 2 * H, N), 128, 0, st>>>(dc, w, din, H, W);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
