@@ -36,15 +36,18 @@ def load():
     return uncrtaints, losses, weight_init
 
 
-def build(covmode: str = "diag", seed: int = 1, device: str = "cpu"):
+def build(covmode: str = "diag", seed: int = 1, device: str = "cpu", **variant):
+    """``variant``: constructor overrides (block_type='residual', use_v=True, is_mono=True, separate_out=True) for scripts/bench_variants.py."""
     uncrtaints, losses, weight_init = load()
     cov = {"diag": 13, "iso": 1, "uni": 13}[covmode]
     torch.manual_seed(seed)
-    net = uncrtaints.UNCRTAINTS(input_dim=15, encoder_widths=[128], decoder_widths=[128, 128, 128, 128, 128], out_conv=[13 + cov],
-                                out_nonlin_mean=True, out_nonlin_var="softplus", agg_mode="att_group", encoder_norm="group",
-                                decoder_norm="batch", n_head=16, d_model=256, d_k=4, pad_value=0, padding_mode="reflect",
-                                positional_encoding=True, covmode=covmode, scale_by=10.0, separate_out=False, use_v=False,
-                                block_type="mbconv", is_mono=False)
+    kw = dict(input_dim=15, encoder_widths=[128], decoder_widths=[128, 128, 128, 128, 128], out_conv=[13 + cov],
+              out_nonlin_mean=True, out_nonlin_var="softplus", agg_mode="att_group", encoder_norm="group",
+              decoder_norm="batch", n_head=16, d_model=256, d_k=4, pad_value=0, padding_mode="reflect",
+              positional_encoding=True, covmode=covmode, scale_by=10.0, separate_out=False, use_v=False,
+              block_type="mbconv", is_mono=False)
+    kw.update(variant)
+    net = uncrtaints.UNCRTAINTS(**kw)
     net.apply(weight_init)
     net = net.to(device).train()
     crit = losses.MultiGaussianNLLLoss(reduction="mean", eps=1e-8, full=True, mode=covmode, chunk=None)
@@ -105,13 +108,13 @@ def time_cpu(batch: int, t: int, hw: int, covmode: str, steps: int, warmup: int,
                       f"fwd+MGNLL+bwd, {cores} host threads ({cpu_model_name()}), torch {torch.__version__} CPU / oneDNN"}
 
 
-def time_cuda(batch: int, t: int, hw: int, covmode: str, steps: int, warmup: int, tf32: bool, device="cuda:0"):
+def time_cuda(batch: int, t: int, hw: int, covmode: str, steps: int, warmup: int, tf32: bool, device="cuda:0", **variant):
     """Reference in PyTorch eager on the GPU (cuDNN / cuBLAS / ATen kernels): the "existing Blackwell kernel" the CUDA path has
     to beat.  Falls back to smaller batches on OOM.  Returns None if even B=1 does not fit."""
     dev = torch.device(device)
     torch.backends.cudnn.allow_tf32 = bool(tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
-    net, crit = build(covmode, 1, dev)
+    net, crit = build(covmode, 1, dev, **variant)
     b = batch
     while b >= 1:
         oom, out = False, None

@@ -460,3 +460,35 @@ def test_use_v_headline_resolution_and_philox_dropout():
     net.eval()
     with torch.no_grad():
         assert rel_l2(outs[0], net(x.cuda(), batch_positions=d.cuda())) > 1e-4
+
+
+def test_residual_headline_resolution():
+    """block_type='residual' at the headline frame size (256x256, T=2, B=1, two decoder blocks -- bounded by the fp64 oracle's
+    run time) in train mode against the fp64 oracle with the CUDA path's ReLU active sets imposed; eval mode likewise."""
+    import uncrtaints_b200 as ub
+    from conftest import report
+    cfg = O.OracleConfig(block_type="residual", n_dec_blocks=2)
+    p = O.init_params(cfg, seed=24)
+    B, T, H, W = 1, 2, 256, 256
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=51)
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=52)
+    net = _variant_net(cfg, p).train()
+    net._injected_keep_mask = keep.to(torch.uint8)
+    out = net(x.cuda(), batch_positions=d.cuda())
+    masks = _residual_relu_masks(net, cfg, B, T, H, W)
+    loss, _ = ub.MultiGaussianNLLLoss(mode="diag", chunk=None, covariance="none")(out[:, :, :13], y.cuda(), out[:, :, 13:26])
+    loss.backward()
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    O.set_fused(True)                                     # F.conv2d / F.group_norm: the 3x3 convolutions at 256x256 in fp64
+    O.RELU_MASKS = masks
+    try:
+        o_out, o_loss, o_g, _ = O.step(p64, x.double(), y.double(), d.double(), cfg, True, keep)
+    finally:
+        O.RELU_MASKS = None
+        O.set_fused(False)
+    assert rel_l2(out, o_out) <= 1e-3 and abs(loss.item() - o_loss.item()) <= 1e-3 * abs(o_loss.item())
+    scale = max(float(g.norm()) for g in o_g.values())
+    errs = _grad_errors(net, o_g, scale)
+    worst = max(errs, key=errs.get)
+    report("parity_report.txt", [f"residual 256x256 B1 T2: out rel_l2={rel_l2(out, o_out):.3e} worst grad rel_l2={errs[worst]:.3e} ({worst})"])
+    assert errs[worst] <= 1e-3, (worst, errs[worst])
