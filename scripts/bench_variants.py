@@ -13,6 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+BREAKDOWN = False
 VARIANTS = {"mbconv (default)": {}, "residual": dict(block_type="residual"), "use_v": dict(use_v=True),
             "is_mono": dict(is_mono=True), "separate_out": dict(separate_out=True), "residual+use_v": dict(block_type="residual", use_v=True)}
 
@@ -37,6 +38,21 @@ def ours(variant, B, T, hw, steps, warmup=3):
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    breakdown = {}
+    if BREAKDOWN:                       # per-kernel-class device time of one step (ub200_prof_*)
+        import ctypes
+        from uncrtaints_b200 import _lib
+        L = _lib.lib()
+        nk = L.ub200_prof_num_kernels()
+        L.ub200_prof_enable((1 << nk) - 1)
+        step()
+        torch.cuda.synchronize()
+        for k in range(nk):
+            ms_k, n_k = ctypes.c_double(), ctypes.c_int()
+            _lib.check(L.ub200_prof_read(k, ctypes.byref(ms_k), ctypes.byref(n_k)), "prof_read")
+            if n_k.value:
+                breakdown[L.ub200_prof_kernel_name(k).decode()] = [round(ms_k.value, 2), n_k.value]
+        L.ub200_prof_enable(0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -46,6 +62,8 @@ def ours(variant, B, T, hw, steps, warmup=3):
     ms = e0.elapsed_time(e1) / steps
     res = {"samples_per_s": round(B * 1e3 / ms, 2), "ms_per_step": round(ms, 2), "batch": B, "loss": float(loss),
            "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    if breakdown:
+        res["kernel_ms_launches"] = breakdown
     del net, bucket, x, y, d
     torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats()
@@ -60,7 +78,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--breakdown", action="store_true")
     a = ap.parse_args()
+    global BREAKDOWN
+    BREAKDOWN = a.breakdown
     from baseline import ref_runner as R
     for name, var in VARIANTS.items():
         if a.only and name not in a.only.split(","):
