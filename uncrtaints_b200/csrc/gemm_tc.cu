@@ -210,6 +210,24 @@ __device__ __forceinline__ float ldh(const bf16_t* p) { return __bfloat162float(
 __device__ __forceinline__ void sth(float* p, float v) { *p = v; }
 __device__ __forceinline__ void sth(bf16_t* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// Loaders with `static constexpr bool PRESPLIT = true` read operands that were split into hi / lo halves beforehand (split_act_kernel:
+// a [rows][128] image of 512-byte rows, 128 hi halves then 128 lo halves): their Raw is the two 16-byte chunks as loaded and put()
+// copies them straight into the swizzled tiles -- no conversion in the GEMM.  Used where an element is read many times (the nine taps
+// of a 3x3 convolution).
+template <class L, class = void> struct IsPresplit { static constexpr bool v = false; };
+template <class L> struct IsPresplit<L, decltype((void)L::PRESPLIT)> { static constexpr bool v = L::PRESPLIT; };
+template <class L>
+__device__ __forceinline__ void convert_store(const L& l, const typename L::Raw& raw, const typename L::Cf& cf, char* hi_chunk, char* lo_chunk,
+                                              int single) {
+    if constexpr (IsPresplit<L>::v) {
+        l.put(raw, hi_chunk, lo_chunk, single);
+    } else {
+        float v[8];
+        l.finish(raw, cf, v);
+        split_store8(v, hi_chunk, lo_chunk, single);
+    }
+}
+
 struct TLoadNormed {           // a = x*scale + shift
     const float* x; const Coef* coef;
     struct Raw { float a[8]; };
@@ -275,25 +293,19 @@ struct TLoadNormBwdT {         // a = ca*dy + cb*v + cc
 };
 typedef TLoadNormBwdT<float> TLoadNormBwd;
 
-// 3x3 convolution operand (ResidualConvBlock, uncrtaints.py:24-69; nn.Conv2d(k=3, padding=1, padding_mode='reflect'), utae.py:478-487):
-// the GEMM's K index is (tap, channel), k = tap*128 + c, and the operand row of output pixel p for tap (dy, dx) is the input pixel
+// 3x3 convolution operands (ResidualConvBlock, uncrtaints.py:24-69; nn.Conv2d(k=3, padding=1, padding_mode='reflect'), utae.py:478-487).
+// The GEMM's K index is (tap, channel), k = tap*128 + c, and the operand row of output pixel p for tap (dy, dx) is the input pixel
 // p + (dy, dx) -- reflected at the border (forward, weight gradient) or ZERO outside the image (input gradient: the transposed
 // convolution of the zero-extended output gradient; the adjoint of the reflection is added by conv_fold_kernel).
-// a = relu?(x*scale + shift): the previous ConvLayer's normalisation + ReLU is applied here, in the consumer's prologue.
+// Every input element is read nine times, so the previous layer's norm + ReLU and the hi / lo split are applied ONCE into a
+// pre-split image (split_act_kernel / relu_norm_bwd_apply_kernel) and the loaders only copy 16-byte chunks.
 // paired: the operand has 256 "channels" = taps (tap0, tap1) side by side (the N operand of the weight-gradient GEMM); tap1 < 0 -> zeros.
-struct TLoadConv {
-    static constexpr int CFK = 128;
-    const float* x; const Coef* coef /* null: identity */; int H, W, relu, zero_pad, paired, tap0, tap1;
-    struct Raw { float a[8]; };
-    __device__ int ncf() const { return paired ? 256 : 128; }
-    __device__ void fill(int n, int /*K*/, float* cf) const {
-        const int Kc = ncf();
-        for (int k = threadIdx.x; k < Kc; k += THREADS) {
-            const Coef c = coef ? coef[(size_t)n * 128 + (k & 127)] : Coef{1.f, 0.f};
-            const int q = cf_pos(k, Kc);
-            cf[q] = c.scale; cf[Kc + q] = c.shift;
-        }
-    }
+constexpr int SPLIT_ROW = 512;         // bytes per pixel of a pre-split image: 128 hi halves, then 128 lo halves
+struct TLoadConvSplit {
+    static constexpr bool PRESPLIT = true;
+    const char* img; int H, W, zero_pad, paired, tap0, tap1;
+    struct Raw { uint4 h, l; };
+    __device__ void fill(int, int, float*) const {}
     __device__ void issue(size_t row, int /*K*/, int ch0, Raw& r) const {
         const uint32_t P = (uint32_t)(H * W), row32 = (uint32_t)row;
         const uint32_t n = row32 / P, p = row32 - n * P;
@@ -308,39 +320,57 @@ struct TLoadConv {
             xs = xs < 0 ? 1 : (xs >= W ? W - 2 : xs);
         }
         if (ok) {
-            ld8(x + ((size_t)n * P + (size_t)(yy * W + xs)) * 128 + (ch0 & 127), r.a);
+            const char* src = img + ((size_t)n * P + (size_t)(yy * W + xs)) * SPLIT_ROW + (ch0 & 127) * 2;
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.h.x), "=r"(r.h.y), "=r"(r.h.z), "=r"(r.h.w) : "l"(src));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.l.x), "=r"(r.l.y), "=r"(r.l.z), "=r"(r.l.w) : "l"(src + 256));
         } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r.a[i] = __int_as_float(0x7fc00000);      // marks "outside": finish() writes zeros
+            r.h = make_uint4(0, 0, 0, 0);
+            r.l = make_uint4(0, 0, 0, 0);
         }
     }
-    struct Cf { float sc[8], sh[8]; };
-    __device__ void coefs(int /*K*/, int ch0, const float* cf, Cf& c) const {
-        const int Kc = ncf(), k0 = paired ? ch0 : (ch0 & 127);
-        lds8(cf, Kc, k0, c.sc); lds8(cf + Kc, Kc, k0, c.sh);
-    }
-    __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
-        const bool outside = __float_as_int(r.a[0]) == 0x7fc00000 && __float_as_int(r.a[7]) == 0x7fc00000;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float a = fmaf(r.a[i], c.sc[i], c.sh[i]);
-            if (relu) a = fmaxf(a, 0.f);
-            v[i] = outside ? 0.f : a;
-        }
-    }
-};
-struct TLoadPlain128 {         // a = x (A operand of the convolution weight gradient: the materialised output gradient dc)
-    const float* x;
-    struct Raw { float a[8]; };
-    __device__ void fill(int, int, float*) const {}
-    __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(x + row * K + ch0, r.a); }
     struct Cf {};
     __device__ void coefs(int, int, const float*, Cf&) const {}
-    __device__ void finish(const Raw& r, const Cf&, float (&v)[8]) const {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = r.a[i];
+    __device__ void put(const Raw& r, char* hi_chunk, char* lo_chunk, int single) const {
+        *reinterpret_cast<uint4*>(hi_chunk) = r.h;
+        if (single != SPLIT_BF16X1) *reinterpret_cast<uint4*>(lo_chunk) = r.l;
     }
 };
+struct TLoadPlainSplit {       // rows of a pre-split [rows][128] image as they are (A operand of the convolution weight gradient)
+    static constexpr bool PRESPLIT = true;
+    const char* img;
+    struct Raw { uint4 h, l; };
+    __device__ void fill(int, int, float*) const {}
+    __device__ void issue(size_t row, int /*K*/, int ch0, Raw& r) const {
+        const char* src = img + row * SPLIT_ROW + ch0 * 2;
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.h.x), "=r"(r.h.y), "=r"(r.h.z), "=r"(r.h.w) : "l"(src));
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.l.x), "=r"(r.l.y), "=r"(r.l.z), "=r"(r.l.w) : "l"(src + 256));
+    }
+    struct Cf {};
+    __device__ void coefs(int, int, const float*, Cf&) const {}
+    __device__ void put(const Raw& r, char* hi_chunk, char* lo_chunk, int single) const {
+        *reinterpret_cast<uint4*>(hi_chunk) = r.h;
+        if (single != SPLIT_BF16X1) *reinterpret_cast<uint4*>(lo_chunk) = r.l;
+    }
+};
+// out = split(relu?(x*scale + shift)): the pre-split image of a [N][P][128] fp32 tensor.  thread = 8 channels of one pixel.
+__global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict__ x, const Coef* __restrict__ coef, char* __restrict__ out,
+                                                        int P, size_t rows, int relu, int mode) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * 16) return;
+    const size_t row = i / 16;
+    const int c0 = (int)(i % 16) * 8;
+    float a[8], v[8];
+    ld8(x + row * 128 + c0, a);
+    if (coef) {
+        const Coef* k = coef + (row / P) * 128 + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], k[j].scale, k[j].shift);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = relu ? fmaxf(a[j], 0.f) : a[j];
+    char* dst = out + row * SPLIT_ROW + c0 * 2;
+    split_store8(v, dst, dst + 256, mode);
+}
 
 // ------------------------------------------------------------------------------------------
 // epilogues: thread = one output channel; v[32] = 32 consecutive pixels of that channel
@@ -606,10 +636,8 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int r = pr + 64 * j;
-                float v[8];
-                al.finish(cur[j], cfr, v);
                 const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
-                split_store8(v, hi + off, lo + off, single);
+                convert_store(al, cur[j], cfr, hi + off, lo + off, single);
             }
         }
         fence_proxy_async();
@@ -804,22 +832,18 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
         char* b_lo = b_hi + WG_B_BYTES / 2;
         {
             const int r = half * 32 + ra;
-            float v[8];
             typename LA::Cf cfa;
             la.coefs(128, ca * 8, sCfA, cfa);
-            la.finish(ca_raw, cfa, v);
             const int off = (ca / 8) * WG_BLK + r * 128 + (((ca % 8) ^ (r & 7)) << 4);
-            split_store8(v, a_hi + off, a_lo + off, single);
+            convert_store(la, ca_raw, cfa, a_hi + off, a_lo + off, single);
         }
         typename LB::Cf cfb;                              // both B rows of this thread share the channel chunk
         lb.coefs(256, cb * 8, sCfB, cfb);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int r = half * 32 + rb + 16 * j;
-            float v[8];
-            lb.finish(cb_raw[j], cfb, v);
             const int off = (cb / 8) * WG_BLK + r * 128 + (((cb % 8) ^ (r & 7)) << 4);
-            split_store8(v, b_hi + off, b_lo + off, single);
+            convert_store(lb, cb_raw[j], cfb, b_hi + off, b_lo + off, single);
         }
         if (half == 1) {
             fence_proxy_async();
@@ -1229,26 +1253,35 @@ int tc_prep_conv_weights(const float* w, void* img, int dgrad, int f16, cudaStre
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-// c[N][P][128] = conv3x3_reflect(relu?(x*scale + shift)) + bias; stats[N][128][2] += column (sum, sumsq).  coef may be null (plain x).
-int tc_conv3x3_fwd(const float* x, const Coef* coef, int relu, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W,
-                   int single, cudaStream_t st) {
-    tc::TLoadConv al{x, coef, H, W, relu, 0, 0, 0, 0};
-    return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConv, tc::TEpiBiasStoreStats, true>(al, wimg, tc::TEpiBiasStoreStats{c, bias, stats}, N, H * W, single, st);
+// split[N*P][512 B] = hi / lo halves of relu?(x*scale + shift) (coef may be null); mode: 2 = fp16 hi/lo (forward operands),
+// 0 = bf16 hi/lo (gradient GEMMs), 1 = bf16 hi only
+int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N, int P, int mode, cudaStream_t st) {
+    const size_t rows = (size_t)N * P;
+    tc::split_act_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(x, coef, static_cast<char*>(split), P, rows, relu, mode);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
 }
-// din[N][P][128] = transposed 3x3 convolution of the zero-extended dc (+ add); the reflection's adjoint is added by launch_conv_fold
-int tc_conv3x3_dgrad(const float* dc, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,
+// c[N][P][128] = conv3x3_reflect(xs) + bias; stats[N][128][2] += column (sum, sumsq).  xs: pre-split input activations
+int tc_conv3x3_fwd(const void* xs, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W, int single,
+                   cudaStream_t st) {
+    tc::TLoadConvSplit al{static_cast<const char*>(xs), H, W, 0, 0, 0, 0};
+    return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConvSplit, tc::TEpiBiasStoreStats, true>(al, wimg, tc::TEpiBiasStoreStats{c, bias, stats}, N, H * W, single, st);
+}
+// din[N][P][128] = transposed 3x3 convolution of the zero-extended dc (+ add); the reflection's adjoint is added by launch_conv_fold.
+// dcs: pre-split output gradient
+int tc_conv3x3_dgrad(const void* dcs, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,
                      cudaStream_t st) {
-    tc::TLoadConv al{dc, nullptr, H, W, 0, 1, 0, 0, 0};
-    return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConv, tc::TEpiStoreAdd, true>(al, wimg_t, tc::TEpiStoreAdd{din, add, scratch}, N, H * W, single, st);
+    tc::TLoadConvSplit al{static_cast<const char*>(dcs), H, W, 1, 0, 0, 0};
+    return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConvSplit, tc::TEpiStoreAdd, true>(al, wimg_t, tc::TEpiStoreAdd{din, add, scratch}, N, H * W, single, st);
 }
-// dW[co][ci][tap] += sum_p dc[p][co] * relu?(x*scale + shift)[reflect(p + tap)][ci] for all 9 taps (five launches of tap pairs)
-int tc_conv3x3_wgrad(const float* dc, const float* x, const Coef* coef, int relu, float* partial, int max_parts, float* dw, int N, int H, int W,
-                     int single, cudaStream_t st) {
+// dW[co][ci][tap] += sum_p dc[p][co] * act[reflect(p + tap)][ci] for all 9 taps (five launches of tap pairs); both operands pre-split
+int tc_conv3x3_wgrad(const void* dcs, const void* xs, float* partial, int max_parts, float* dw, int N, int H, int W, int single,
+                     cudaStream_t st) {
     for (int t = 0; t < 9; t += 2) {
         const int tapB = t + 1 < 9 ? t + 1 : -1;
-        tc::TLoadConv lb{x, coef, H, W, relu, 0, 1, t, tapB};
+        tc::TLoadConvSplit lb{static_cast<const char*>(xs), H, W, 0, 1, t, tapB};
         int nparts = 0;
-        UB_TRY(tc::launch_wgrad_tc(tc::TLoadPlain128{dc}, lb, partial, max_parts, N, H * W, UB_HID, 1, single, &nparts, st));
+        UB_TRY(tc::launch_wgrad_tc(tc::TLoadPlainSplit{static_cast<const char*>(dcs)}, lb, partial, max_parts, N, H * W, UB_HID, 1, single, &nparts, st));
         tc::reduce_conv_partials_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(partial, dw, t, tapB, nparts);
         UB_CHECK_LAUNCH();
     }

@@ -28,9 +28,9 @@ int launch_residual_bwd(const float* dout, const float* dn0, const float* x, con
 // norm.cu: residual blocks (conv3x3 -> norm -> ReLU layers)
 int launch_residual_relu_fwd(const float* x, const float* c3, const Coef* coef3, float* out, double* out_stats, int N, int P, cudaStream_t st);
 int launch_relu_norm_bwd_stats(const float* dy, const float* c, const Coef* coef, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
-int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, float* dc, float* dbias, int N, int P,
+int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int P,
                                cudaStream_t st);
-int launch_conv_fold(const float* dc, const float* w, float* din, int N, int H, int W, cudaStream_t st);
+int launch_conv_fold(const void* dc_split, const float* w, float* din, int N, int H, int W, cudaStream_t st);
 
 // gemm_simt.cu
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);
@@ -67,14 +67,16 @@ int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* 
                  const MeanRstd* mr0, double* bstats0, const Coef* coef0, float* partial, int max_parts, float* dw1, int N,
                  int P, int single, int hbf, cudaStream_t st);
 
-// gemm_tc.cu: dense 3x3 convolutions (reflect padding) of the residual blocks as implicit GEMMs over (tap, channel), weights streamed
+// gemm_tc.cu: dense 3x3 convolutions (reflect padding) of the residual blocks as implicit GEMMs over (tap, channel), weights streamed,
+// operands read from pre-split (hi / lo) images
 int tc_prep_conv_weights(const float* w, void* img, int dgrad, int f16, cudaStream_t st);
-int tc_conv3x3_fwd(const float* x, const Coef* coef, int relu, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W,
-                   int single, cudaStream_t st);
-int tc_conv3x3_dgrad(const float* dc, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,
+int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N, int P, int mode, cudaStream_t st);
+int tc_conv3x3_fwd(const void* xs, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W, int single,
+                   cudaStream_t st);
+int tc_conv3x3_dgrad(const void* dcs, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,
                      cudaStream_t st);
-int tc_conv3x3_wgrad(const float* dc, const float* x, const Coef* coef, int relu, float* partial, int max_parts, float* dw, int N, int H, int W,
-                     int single, cudaStream_t st);
+int tc_conv3x3_wgrad(const void* dcs, const void* xs, float* partial, int max_parts, float* dw, int N, int H, int W, int single,
+                     cudaStream_t st);
 
 // dwconv_rows.cu (row-streaming depthwise kernels fed by TMA bulk copies; the backward one is fused: du, h2, h1 -> dz1 in one pass)
 int launch_dwconv_fwd(const void* h1, const Coef* coef1, const float* wdw, void* h2, double* stats2, int N, int H, int W, int hbf,

@@ -90,6 +90,7 @@ struct Layout {
     int residual;               // block_type: 0 = MBConv, 1 = ResidualConvBlock
     ResWs rblk[1 + 16];
     size_t res_scratch;         // [Nmax][128] doubles: statistics sink of the input-gradient GEMM epilogue
+    size_t res_split;           // [Nmax][P] x 512 B: pre-split (hi / lo) image of the current convolution's input activations
     size_t hes;                 // bytes per element of the 256-channel hidden tensors h1, h2, du, dz1 (4, or 2 with gemm_backend bit 5)
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
@@ -241,6 +242,7 @@ static int make_layout(const ub200_desc* d, Layout& L) {
             L.blk[i].out = r.out;
         }
         L.res_scratch = b.take((size_t)L.Nmax * UB_WIDTH * sizeof(double));
+        L.res_split = b.take((size_t)L.Nmax * P * 512);
     } else if (d->need_grad) {
         for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, true, L.hes);
     } else {
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
 // ---- block_type = 'residual' (ResidualConvBlock, uncrtaints.py:24-69): x + L3(L2(L1(x))), L = conv3x3(reflect, bias) -> norm -> ReLU ----
 // Per ConvLayer ONE tensor is materialised (the convolution output c, with its statistics from the GEMM epilogue); the norm + ReLU
 // is applied in the next convolution's operand loader, the last one in the residual pass.  The convolutions are implicit GEMMs
-// over (tap, channel) on the tcgen05 path (gemm_tc.cu: TLoadConv, streamed weight slabs).
+// over (tap, channel) on the tcgen05 path (gemm_tc.cu: TLoadConvSplit on pre-split operand images, streamed weight slabs).
 static int residual_forward(const ub200_desc* d, const Layout& L, int i, const void* const* params, const float* x, double* next_stats,
                             void* ws, cudaStream_t st) {
     const ResWs& w = L.rblk[i];
@@ -467,8 +469,13 @@ static int residual_forward(const ub200_desc* d, const Layout& L, int i, const v
         if (!pf(q, UB200_R_W) || !pf(q, UB200_R_B) || !pf(q, UB200_R_N_W)) return UB_ERR_ARG;
         UB_TRY(tc_prep_conv_weights(pf(q, UB200_R_W), at<char>(ws, w.wimg[l]), 0, single == 2, st));
         if (d->need_grad) UB_TRY(tc_prep_conv_weights(pf(q, UB200_R_W), at<char>(ws, w.wimgT[l]), 1, 0, st));
-        UB_PROF(KID_GEMM1_FWD, st, tc_conv3x3_fwd(in, incoef, l > 0, at<char>(ws, w.wimg[l]), pf(q, UB200_R_B), at<float>(ws, w.c[l]),
-                                                  at<double>(ws, w.stats[l]), N, d->H, d->W, single, st));
+        // the convolution reads every input element nine times (once per tap): the previous layer's norm + ReLU and the hi / lo operand
+        // split are applied ONCE into a pre-split image (2 A of extra traffic), the GEMM's loader then only copies 16-byte chunks
+        // (measured at B=16 against converting in the loader: conv forward 40.5 -> 35.1, input gradient 46.6 -> 41.6, weight
+        // gradient 45.2 -> 37.8 ms per step, for 12.3 ms of split passes)
+        UB_PROF(KID_SE_POOL, st, tc_split_act(in, incoef, l > 0, at<char>(ws, L.res_split), N, P, single, st));
+        UB_PROF(KID_GEMM1_FWD, st, tc_conv3x3_fwd(at<char>(ws, L.res_split), at<char>(ws, w.wimg[l]), pf(q, UB200_R_B), at<float>(ws, w.c[l]),
+                                                        at<double>(ws, w.stats[l]), N, d->H, d->W, single, st));
         UB_TRY(launch_norm_finalize(at<double>(ws, w.stats[l]), pf(q, UB200_R_N_W), pf(q, UB200_R_N_B), pfm(q, UB200_R_N_RM), pfm(q, UB200_R_N_RV),
                                     at<Coef>(ws, w.coef[l]), at<MeanRstd>(ws, w.mr[l]), N, UB_WIDTH, groups, (double)P, d->norm_eps,
                                     d->bn_momentum, d->training, st));
@@ -498,11 +505,14 @@ static int residual_backward(const ub200_desc* d, const Layout& L, int i, const 
                                                                  gf(gq, UB200_R_B), N, P, st));
         const float* in = l == 0 ? x : at<float>(ws, w.c[l - 1]);
         const Coef* incoef = l == 0 ? nullptr : at<Coef>(ws, w.coef[l - 1]);
-        if (gf(gq, UB200_R_W))
-            UB_PROF(KID_WGRAD1, st, tc_conv3x3_wgrad(dc, in, incoef, l > 0, partial, L.max_parts, gf(gq, UB200_R_W), N, d->H, d->W, single, st));
+        if (gf(gq, UB200_R_W)) {
+            UB_PROF(KID_SE_POOL, st, tc_split_act(in, incoef, l > 0, at<char>(ws, L.res_split), N, P, single, st));      // bf16 hi/lo (gradient GEMM)
+            UB_PROF(KID_WGRAD1, st, tc_conv3x3_wgrad(dc, at<char>(ws, L.res_split), partial, L.max_parts, gf(gq, UB200_R_W), N, d->H, d->W,
+                                                           single, st));
+        }
         float* din = l == 0 ? dx : (l == 2 ? t0 : t1);
         UB_PROF(KID_GEMM1_BWD, st, tc_conv3x3_dgrad(dc, at<char>(ws, w.wimgT[l]), l == 0 ? dout : nullptr, din, at<double>(ws, L.res_scratch), N,
-                                                    d->H, d->W, single, st));
+                                                          d->H, d->W, single, st));
         UB_TRY(launch_conv_fold(dc, pf(q, UB200_R_W), din, N, d->H, d->W, st));
         dy = din;
     }

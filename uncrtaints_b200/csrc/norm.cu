@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
 //   R-fwd : out = x + relu(c3*scale3 + shift3)                                     (uncrtaints.py:64-68)
 //   R-bwd1: bstats[n][ch] += (sum dz, sum dz * c_hat), dz = dy * [c*scale + shift > 0]   (ReLU + norm backward statistics)
 //   R-bwd2: dc = a*dz + b*c + cc (norm backward applied), dbias[ch] += sum dc       (the convolution's output gradient, materialised once
-//           because its input-gradient GEMM reads every element nine times)
+//           -- as a pre-split bf16 hi/lo image -- because its input-gradient GEMM reads every element nine times)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) residual_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ c3,
                                                                  const Coef* __restrict__ coef3, float* __restrict__ out, double* out_stats,
@@ -324,9 +324,22 @@ __global__ void __launch_bounds__(256) relu_norm_bwd_stats_kernel(const float* _
     }
     block_reduce_cols2<C>(make_float4(s[0], s[1], s[2], s[3]), make_float4(q[0], q[1], q[2], q[3]), bstats + (size_t)n * C * 2, smem);
 }
+// dc is written as a PRE-SPLIT image (512-byte rows: 128 bf16 hi halves, then 128 bf16 lo halves; gemm_tc.cu: SPLIT_ROW): both GEMMs
+// that consume it (input gradient: nine taps per element; weight gradient: five launches) copy the halves straight into their tiles.
+__device__ __forceinline__ void st_split4_bf16(char* row_base, int c0, const float (&v)[4]) {
+    uint2 h, l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(v[3]), "f"(v[2]));
+    const float r0 = v[0] - __uint_as_float(h.x << 16), r1 = v[1] - __uint_as_float(h.x & 0xFFFF0000u);
+    const float r2 = v[2] - __uint_as_float(h.y << 16), r3 = v[3] - __uint_as_float(h.y & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.x) : "f"(r1), "f"(r0));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.y) : "f"(r3), "f"(r2));
+    *reinterpret_cast<uint2*>(row_base + c0 * 2) = h;
+    *reinterpret_cast<uint2*>(row_base + 256 + c0 * 2) = l;
+}
 __global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ c,
                                                                    const Coef* __restrict__ coef, const BCoef* __restrict__ bc,
-                                                                   float* __restrict__ dc, float* dbias, int P, int chunk) {
+                                                                   char* __restrict__ dc, float* dbias, int P, int chunk) {
     constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
     __shared__ __align__(16) float smem[ROWS * C];
     const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
@@ -348,7 +361,7 @@ __global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* _
             o[i] = fmaf(b[i].a, dz, fmaf(b[i].b, cv[i], b[i].c));
             s[i] += o[i];
         }
-        st4(dc + base + (size_t)p * C, make_float4(o[0], o[1], o[2], o[3]));
+        st_split4_bf16(dc + ((size_t)n * P + p) * 512, c4 * 4, o);
     }
     if (dbias) {
         reinterpret_cast<float4*>(smem)[r * Q + c4] = make_float4(s[0], s[1], s[2], s[3]);
@@ -368,8 +381,8 @@ __global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* _
 // din[(y, W-2)] += g[(y, W)], x' = reflect(x) for x in [-1, W] (corners included in the two rows).
 //   g[r][ci] = sum_tap sum_co W[co][ci][tap] * dc[r - tap][co]   over the taps whose source pixel r - tap lies inside the image.
 // grid (ring positions, N); 128 threads = ci.  Ring position index: [0, W+2) top row, [W+2, 2W+4) bottom row, then H left, H right.
-__global__ void __launch_bounds__(128) conv_fold_kernel(const float* __restrict__ dc, const float* __restrict__ w /* [co][ci][9] */,
-                                                         float* din, int H, int W) {
+__global__ void __launch_bounds__(128) conv_fold_kernel(const char* __restrict__ dc /* pre-split bf16 hi/lo image */,
+                                                         const float* __restrict__ w /* [co][ci][9] */, float* din, int H, int W) {
     __shared__ float sdc[3][UB_WIDTH];
     const int n = blockIdx.y, pos = blockIdx.x, ci = threadIdx.x;
     int ry, rx, ty = 0, tx = 0;          // ring pixel and the target pixel it reflects onto
@@ -383,9 +396,13 @@ __global__ void __launch_bounds__(128) conv_fold_kernel(const float* __restrict_
     size_t src[3];
     for (int t = 0; t < 9; ++t) {
         const int py = ry - (t / 3 - 1), px = rx - (t % 3 - 1);
-        if (py >= 0 && py < H && px >= 0 && px < W && np < 3) { taps[np] = t; src[np] = ((size_t)n * H * W + (size_t)py * W + px) * UB_WIDTH; ++np; }
+        if (py >= 0 && py < H && px >= 0 && px < W && np < 3) { taps[np] = t; src[np] = ((size_t)n * H * W + (size_t)py * W + px) * 512; ++np; }
     }
-    for (int i = 0; i < np; ++i) sdc[i][ci] = dc[src[i] + ci];
+    for (int i = 0; i < np; ++i) {
+        const unsigned short hb = *reinterpret_cast<const unsigned short*>(dc + src[i] + ci * 2);
+        const unsigned short lb = *reinterpret_cast<const unsigned short*>(dc + src[i] + 256 + ci * 2);
+        sdc[i][ci] = __uint_as_float((uint32_t)hb << 16) + __uint_as_float((uint32_t)lb << 16);
+    }
     __syncthreads();
     float acc = 0.f;
     for (int i = 0; i < np; ++i) {
@@ -461,15 +478,15 @@ int launch_relu_norm_bwd_stats(const float* dy, const float* c, const Coef* coef
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, float* dc, float* dbias, int N, int P,
+int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int P,
                                cudaStream_t st) {
     const int chunk = chunk_for(P);
-    relu_norm_bwd_apply_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, c, coef, bc, dc, dbias, P, chunk);
+    relu_norm_bwd_apply_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, c, coef, bc, static_cast<char*>(dc_split), dbias, P, chunk);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int launch_conv_fold(const float* dc, const float* w, float* din, int N, int H, int W, cudaStream_t st) {
-    conv_fold_kernel<<<dim3(2 * (W + 2) + 2 * H, N), 128, 0, st>>>(dc, w, din, H, W);
+int launch_conv_fold(const void* dc_split, const float* w, float* din, int N, int H, int W, cudaStream_t st) {
+    conv_fold_kernel<<<dim3(2 * (W + 2) + 2 * H, N), 128, 0, st>>>(static_cast<const char*>(dc_split), w, din, H, W);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
