@@ -118,6 +118,14 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
     }
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // Operand split modes ("single" argument of the kernels): 0 = bf16 hi + bf16 lo (three MMAs; ~2^-17: the input-/weight-gradient
 // GEMMs, whose operands are gradients of unbounded range), 1 = one bf16 (single-pass, reduced precision), 2 = fp16 hi + fp16 lo
 // (three MMAs; ~2^-22, i.e. fp32-grade: the FORWARD GEMMs, whose operands are normalised activations and weights, well inside
@@ -500,26 +508,27 @@ struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
 // converted, so HBM requests stay in flight across the convert / fence / barrier / MMA issue / epilogue of step q.
 // ------------------------------------------------------------------------------------------
 // WSTREAM (the 3x3 convolutions of the residual blocks, K = 9 taps x 128 channels): the weight image (576 KB) does not fit in
-// shared memory, so the [NOUT][64] slab of each K-block is streamed from the (L2-resident) global image into a ring slot next to
-// the activation tile of the same pipeline step -- 4 x 16 bytes per thread and step, prefetched one step ahead like the operands.
+// shared memory, so the [NOUT][64] hi and lo slabs of each K-block are streamed from the (L2-resident) global image into a
+// four-slot ring by the TMA engine: thread 0 issues two cp.async.bulk (16 KB each, mbarrier complete_tx) two pipeline steps ahead
+// and waits for the slab's barrier right before it issues the step's MMAs -- no registers, no shared-memory stores by the threads
+// (the first version copied the slabs through registers, 4 x LDG.128 + 4 x STS.128 per thread and step; same speed, 40 more registers).
 template <int K, int NOUT, class ALoad, class Epi, int PARTS, bool WSTREAM>
 __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __restrict__ wimg, const Epi& ep, int P, int single,
                                              const int bx /* CTA index within the frame */, const int gx /* CTAs per frame */, const int n) {
     constexpr int KB = K / KBLK, MH = NOUT / 128;
     constexpr int W_HALF = K * NOUT * 2;                  // bytes of the hi image (the lo image follows it)
     constexpr int SLAB = NOUT * 128;                      // one K-block of one image: [NOUT rows][128 B]
-    constexpr int W_BYTES = WSTREAM ? NSTAGE * 2 * SLAB : K * NOUT * 4;   // resident: hi image + lo image; streamed: ring of slabs
+    constexpr int WRING = 4, WAHEAD = 2;                  // streamed weights: ring slots, prefetch distance in pipeline steps
+    constexpr int W_BYTES = WSTREAM ? WRING * 2 * SLAB : K * NOUT * 4;    // resident: hi image + lo image; streamed: ring of slab pairs
     constexpr int CFK = WSTREAM ? 128 : K;                // coefficient entries per vector
     constexpr int ACC_COLS = MH * TILE_PX;                // TMEM columns per accumulator stage
-    static_assert(!WSTREAM || (2 * SLAB / 16) % THREADS == 0, "slab copy: whole uint4 per thread");
-    constexpr int WPT = WSTREAM ? (2 * SLAB / 16) / THREADS : 1;          // uint4 of a slab pair per thread
     extern __shared__ __align__(1024) char smem_raw[];
     char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
     char* sW = smem;                                      // [hi|lo][KB][NOUT rows][128 B], or NSTAGE x {hi slab, lo slab}
     char* sA = smem + W_BYTES;                            // NSTAGE x {hi tile 16 KB, lo tile 16 KB}
     float* sCf = reinterpret_cast<float*>(sA + NSTAGE * STAGE_BYTES);     // 3 x CFK coefficients (SoA)
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * CFK);          // free[NSTAGE], accfull[2]
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + NSTAGE + 2);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCf + 3 * CFK);          // free[NSTAGE], accfull[2], wfull[WRING]
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + NSTAGE + 2 + WRING);
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
     const int tiles_per_frame = P / TILE_PX;
@@ -536,24 +545,25 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
     }
 
     // ---- one-time setup: weights, coefficients, barriers, TMEM ----
-    uint4 wraw[WPT];
-    auto w_issue = [&](int kb) {                          // slab pair of K-block kb: uint4 index i < SLAB/16 -> hi image, else lo image
-#pragma unroll
-        for (int j = 0; j < WPT; ++j) {
-            const int i = tid + j * THREADS;
-            const uint4* src = wimg + (i < SLAB / 16 ? (size_t)kb * (SLAB / 16) + i : (size_t)(W_HALF / 16) + (size_t)kb * (SLAB / 16) + (i - SLAB / 16));
-            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wraw[j].x), "=r"(wraw[j].y), "=r"(wraw[j].z), "=r"(wraw[j].w) : "l"(src));
-        }
+    // (thread 0 only) slab pair of pipeline step qq -> weight ring slot qq % WRING.  The slot was last read by the MMAs of step
+    // qq - WRING, which are complete whenever this is called (see the call sites).
+    auto w_issue = [&](int qq) {
+        const int kb = qq % KB;
+        const uint32_t bar = smem_u32(&sBar[NSTAGE + 2 + qq % WRING]), dst = smem_u32(sW) + (uint32_t)(qq % WRING) * 2 * SLAB;
+        mbar_expect_tx(bar, 2 * SLAB);
+        bulk_g2s(dst, reinterpret_cast<const char*>(wimg) + (size_t)kb * SLAB, SLAB, bar);
+        bulk_g2s(dst + SLAB, reinterpret_cast<const char*>(wimg) + (size_t)W_HALF + (size_t)kb * SLAB, SLAB, bar);
     };
-    if constexpr (WSTREAM) {
-        if (Q > 0) w_issue(0);
-    } else {
+    if constexpr (!WSTREAM) {
         for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
     }
     al.fill(n, K, sCf);
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE + 2; ++i) mbar_init(smem_u32(&sBar[i]), 1);
+        for (int i = 0; i < NSTAGE + 2 + WRING; ++i) mbar_init(smem_u32(&sBar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if constexpr (WSTREAM) {
+            for (int a = 0; a < WAHEAD && a < Q; ++a) w_issue(a);
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
@@ -616,19 +626,15 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
             al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
             al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
         }
-        uint4 wcur[WPT];
-        if constexpr (WSTREAM) {
-#pragma unroll
-            for (int j = 0; j < WPT; ++j) wcur[j] = wraw[j];
-            if (q + 1 < Q) w_issue((q + 1) % KB);
-        }
         const uint32_t slot = (uint32_t)q % NSTAGE, u = (uint32_t)q / NSTAGE;
         mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);    // MMAs that read this ring slot are done
         char* hi = sA + slot * STAGE_BYTES;
         char* lo = hi + STAGE_BYTES / 2;
         if constexpr (WSTREAM) {
-#pragma unroll
-            for (int j = 0; j < WPT; ++j) reinterpret_cast<uint4*>(sW + slot * 2 * SLAB)[tid + j * THREADS] = wcur[j];
+            // the wait above proves the MMAs of step q - NSTAGE (and all earlier ones) complete: weight slot (q + WAHEAD) % WRING,
+            // last read by step q + WAHEAD - WRING = q - NSTAGE, is free
+            static_assert(WRING - WAHEAD == NSTAGE, "weight ring reuse is tied to the operand ring's barrier");
+            if (tid == 0 && q + WAHEAD < Q) w_issue(q + WAHEAD);
         }
         {
             typename ALoad::Cf cfr;                        // this thread's 8 channels of the K-block: one coefficient read for both rows
@@ -645,7 +651,8 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
         if (tid == 0) {
             tc_fence_after();
             const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
-            const uint32_t a_hi = WSTREAM ? smem_u32(sW) + slot * 2 * SLAB : smem_u32(sW) + kb * SLAB;
+            if constexpr (WSTREAM) mbar_wait(smem_u32(&sBar[NSTAGE + 2 + q % WRING]), (uint32_t)(q / WRING) & 1);   // slab pair landed
+            const uint32_t a_hi = WSTREAM ? smem_u32(sW) + (uint32_t)(q % WRING) * 2 * SLAB : smem_u32(sW) + kb * SLAB;
             const uint32_t a_lo = a_hi + (WSTREAM ? SLAB : W_HALF);
             const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
             // fp16 operands: A/B format fields (bits 7-9, 10-12) = 0 (F16) instead of 1 (BF16)
@@ -705,14 +712,6 @@ gemm_tc_kernel(ALoad al, const uint4* __restrict__ wimg /* prepared bf16 hi/lo i
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 static int sm_count() { return device_sm_count(); }
 // CTAs per frame: G*N a multiple of the SM count (equal waves), about 8-16 tiles per CTA
@@ -728,7 +727,7 @@ static int blocks_per_frame(int N, int tiles) {
 template <int K, int NOUT, class ALoad, class Epi, bool WSTREAM = false>
 static int launch(ALoad al, const void* wimg, Epi ep, int N, int P, int single, cudaStream_t st) {
     if (P % TILE_PX != 0) return UB_ERR_ARG;
-    constexpr size_t wbytes = WSTREAM ? (size_t)NSTAGE * 2 * NOUT * 128 : (size_t)K * NOUT * 4;
+    constexpr size_t wbytes = WSTREAM ? (size_t)4 * 2 * NOUT * 128 : (size_t)K * NOUT * 4;       // streamed: four-slot ring of slab pairs
     constexpr size_t smem = wbytes + NSTAGE * STAGE_BYTES + 3 * (WSTREAM ? 128 : K) * sizeof(float) + 8 * 8 + 16 + 1024;
     auto kern = gemm_tc_kernel<K, NOUT, ALoad, Epi, Epi::PARTS, WSTREAM>;
     UB_SET_SMEM(kern, smem);
