@@ -224,6 +224,20 @@ __device__ __forceinline__ void sth(bf16_t* p, float v) { *p = __float2bfloat16_
 // of a 3x3 convolution).
 template <class L, class = void> struct IsPresplit { static constexpr bool v = false; };
 template <class L> struct IsPresplit<L, decltype((void)L::PRESPLIT)> { static constexpr bool v = L::PRESPLIT; };
+// Per-row position state for loaders whose source address needs integer division (the convolution loaders: frame / y / x of the
+// output pixel).  It changes once per tile while issue() runs once per K-block (18 times per tile for the 3x3 convolution), and
+// the producer warps are bound by the latency of their own instruction stream (ncu r02, conv kernel: 250 instructions per thread
+// and K-block, 10.7 cycles per issued instruction at four warps per scheduler), so the divisions are hoisted out of the K loop.
+template <class L, class = void> struct PosOf { struct type { size_t row; }; };
+template <class L> struct PosOf<L, decltype((void)sizeof(typename L::Pos))> { typedef typename L::Pos type; };
+template <class L>
+__device__ __forceinline__ void locate_row(const L& l, size_t row, typename PosOf<L>::type& pos) {
+    if constexpr (IsPresplit<L>::v) l.locate(row, pos); else pos.row = row;
+}
+template <class L>
+__device__ __forceinline__ void issue_row(const L& l, const typename PosOf<L>::type& pos, int K, int ch0, typename L::Raw& raw) {
+    if constexpr (IsPresplit<L>::v) l.issue_at(pos, K, ch0, raw); else l.issue(pos.row, K, ch0, raw);
+}
 template <class L>
 __device__ __forceinline__ void convert_store(const L& l, const typename L::Raw& raw, const typename L::Cf& cf, char* hi_chunk, char* lo_chunk,
                                               int single) {
@@ -313,13 +327,24 @@ struct TLoadConvSplit {
     static constexpr bool PRESPLIT = true;
     const char* img; int H, W, zero_pad, paired, tap0, tap1;
     struct Raw { uint4 h, l; };
+    struct Pos { const char* frame; int y, x; };          // frame base of the image, pixel coordinates of the operand row
     __device__ void fill(int, int, float*) const {}
-    __device__ void issue(size_t row, int /*K*/, int ch0, Raw& r) const {
+    __device__ void locate(size_t row, Pos& pos) const {
         const uint32_t P = (uint32_t)(H * W), row32 = (uint32_t)row;
         const uint32_t n = row32 / P, p = row32 - n * P;
-        const int y = (int)(p / (uint32_t)W), xx = (int)(p - (uint32_t)y * (uint32_t)W);
+        pos.y = (int)(p / (uint32_t)W);
+        pos.x = (int)(p - (uint32_t)pos.y * (uint32_t)W);
+        pos.frame = img + (size_t)n * P * SPLIT_ROW;
+    }
+    __device__ void issue(size_t row, int K, int ch0, Raw& r) const {
+        Pos pos;
+        locate(row, pos);
+        issue_at(pos, K, ch0, r);
+    }
+    __device__ void issue_at(const Pos& pos, int /*K*/, int ch0, Raw& r) const {
         const int tap = paired ? (ch0 < 128 ? tap0 : tap1) : (ch0 >> 7);
-        int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+        const int t3 = tap >= 6 ? 2 : (tap >= 3 ? 1 : 0);              // tap / 3 without a division (tap may be -1: absent)
+        int yy = pos.y + t3 - 1, xs = pos.x + (tap - 3 * t3) - 1;
         bool ok = tap >= 0;
         if (zero_pad) {
             ok = ok && yy >= 0 && yy < H && xs >= 0 && xs < W;
@@ -328,7 +353,7 @@ struct TLoadConvSplit {
             xs = xs < 0 ? 1 : (xs >= W ? W - 2 : xs);
         }
         if (ok) {
-            const char* src = img + ((size_t)n * P + (size_t)(yy * W + xs)) * SPLIT_ROW + (ch0 & 127) * 2;
+            const char* src = pos.frame + (size_t)(yy * W + xs) * SPLIT_ROW + (ch0 & 127) * 2;
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.h.x), "=r"(r.h.y), "=r"(r.h.z), "=r"(r.h.w) : "l"(src));
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.l.x), "=r"(r.l.y), "=r"(r.l.z), "=r"(r.l.w) : "l"(src + 256));
         } else {
@@ -347,6 +372,9 @@ struct TLoadPlainSplit {       // rows of a pre-split [rows][128] image as they 
     static constexpr bool PRESPLIT = true;
     const char* img;
     struct Raw { uint4 h, l; };
+    struct Pos { size_t row; };
+    __device__ void locate(size_t row, Pos& pos) const { pos.row = row; }
+    __device__ void issue_at(const Pos& pos, int K, int ch0, Raw& r) const { issue(pos.row, K, ch0, r); }
     __device__ void fill(int, int, float*) const {}
     __device__ void issue(size_t row, int /*K*/, int ch0, Raw& r) const {
         const char* src = img + row * SPLIT_ROW + ch0 * 2;
@@ -538,10 +566,18 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
     // producer role: 16-byte chunk pc8 of rows pr and pr + 64
     const int pc8 = tid % 8, pr = tid / 8;
     typename ALoad::Raw raw[2];
+    typename PosOf<ALoad>::type pos[2];                   // the two operand rows of this thread in the tile being prefetched
     if (Q > 0) {
         const size_t row0 = (size_t)n * P + (size_t)t0 * TILE_PX;
-        al.issue(row0 + pr, K, pc8 * 8, raw[0]);
-        al.issue(row0 + pr + 64, K, pc8 * 8, raw[1]);
+        if constexpr (IsPresplit<ALoad>::v) {
+            locate_row(al, row0 + pr, pos[0]);
+            locate_row(al, row0 + pr + 64, pos[1]);
+            issue_row(al, pos[0], K, pc8 * 8, raw[0]);
+            issue_row(al, pos[1], K, pc8 * 8, raw[1]);
+        } else {
+            al.issue(row0 + pr, K, pc8 * 8, raw[0]);
+            al.issue(row0 + pr + 64, K, pc8 * 8, raw[1]);
+        }
     }
 
     // ---- one-time setup: weights, coefficients, barriers, TMEM ----
@@ -623,8 +659,17 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
         if (q + 1 < Q) {                                  // prefetch the next step's operands
             const int nit = (q + 1) / KB, nkb = (q + 1) % KB;
             const size_t nrow0 = (size_t)n * P + (size_t)(t0 + nit) * TILE_PX;
-            al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
-            al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
+            if constexpr (IsPresplit<ALoad>::v) {
+                if (nkb == 0) {                           // the prefetch enters the next tile
+                    locate_row(al, nrow0 + pr, pos[0]);
+                    locate_row(al, nrow0 + pr + 64, pos[1]);
+                }
+                issue_row(al, pos[0], K, nkb * KBLK + pc8 * 8, raw[0]);
+                issue_row(al, pos[1], K, nkb * KBLK + pc8 * 8, raw[1]);
+            } else {
+                al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
+                al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
+            }
         }
         const uint32_t slot = (uint32_t)q % NSTAGE, u = (uint32_t)q / NSTAGE;
         mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);    // MMAs that read this ring slot are done
