@@ -4,7 +4,7 @@
 #  FFMA2 / FMUL2 = packed f32x2, MUFU = special-function unit).  Usage: bash scripts/sass_evidence.sh > profiles/r02_sass.txt
 cd "$(dirname "$0")/.."
 echo "# cuobjdump -sass of uncrtaints_b200/_build/*.o (nvcc $(nvcc --version | grep -o 'release [0-9.]*'), -gencode arch=compute_100a,code=sm_100a)"
-for o in gemm_tc dwconv_rows norm temporal head_loss inconv se optim metrics gemm_simt; do
+for o in gemm_tc dwconv_rows norm temporal ltae_v head_loss inconv se optim metrics gemm_simt; do
   f=uncrtaints_b200/_build/$o.o
   [ -f $f ] || continue
   cuobjdump -sass $f | awk -v obj=$o '
