@@ -180,6 +180,12 @@ def test_install_patches_reference_factory_and_loss():
                                      chunk_size=None)
             net = model_utils.get_generator(cfg)
             assert isinstance(net, ub.UNCRTAINTS) and (net.mean_idx, net.vars_idx) == (13, 26)
+            # the factory's variant flags (model_utils.py:86-108: --use_v, --block_type residual, --pretrain -> is_mono, separate_out)
+            for flags in (dict(use_v=True), dict(block_type="residual"), dict(pretrain=True), dict(separate_out=True)):
+                vnet = model_utils.get_generator(argparse.Namespace(**{**vars(cfg), **flags}))
+                assert isinstance(vnet, ub.UNCRTAINTS)
+                assert (vnet.use_v, vnet.block_type, vnet.is_mono, vnet.separate_out) == (
+                    flags.get("use_v", False), flags.get("block_type", "mbconv"), flags.get("pretrain", False), flags.get("separate_out", False))
             crit = ref_losses.get_loss(cfg)
             p = torch.rand(1, 1, 13, 4, 4)
             with pytest.raises(RuntimeError, match="CUDA"):           # our loss, reached through the reference's wrapper

@@ -492,3 +492,52 @@ def test_residual_headline_resolution():
     worst = max(errs, key=errs.get)
     report("parity_report.txt", [f"residual 256x256 B1 T2: out rel_l2={rel_l2(out, o_out):.3e} worst grad rel_l2={errs[worst]:.3e} ({worst})"])
     assert errs[worst] <= 1e-3, (worst, errs[worst])
+
+
+@pytest.mark.parametrize("case", [
+    dict(kw=dict(block_type="residual", n_dec_blocks=1), B=1, T=1, H=64, W=96),                 # tiles straddle image rows (W % 128 != 0), T = 1
+    dict(kw=dict(block_type="residual", n_dec_blocks=1, covmode="iso"), B=2, T=2, H=32, W=32),   # no upsampling (H = 32), 8 tiles per frame
+    dict(kw=dict(use_v=True, n_dec_blocks=1), B=1, T=9, H=32, W=32),                             # run-time-T temporal kernels (T > 8), no upsampling
+    dict(kw=dict(use_v=True, block_type="residual", separate_out=True, n_dec_blocks=1), B=2, T=2, H=64, W=64),   # all variants at once
+    dict(kw=dict(is_mono=True, block_type="residual", n_dec_blocks=2), B=2, T=1, H=64, W=64),
+])
+def test_variant_edge_shapes_vs_oracle(case):
+    """Edge shapes and combinations of the constructor variants against the fp64 oracle (ReLU active sets of the CUDA run imposed):
+    outputs, loss, every gradient within 1e-3; eval-mode forward likewise."""
+    import uncrtaints_b200 as ub
+    from conftest import report
+    cfg = O.OracleConfig(**case["kw"])
+    p = O.init_params(cfg, seed=61)
+    B, T, H, W = case["B"], case["T"], case["H"], case["W"]
+    x, y, d = O.synthetic_batch(B, T, H, W, seed=62, pad_last=(T > 2))
+    keep = O.dropout_keep_mask(16, B, T, H, W, seed=63)
+    vkeep = O.value_keep_mask(B, seed=64) if cfg.use_v else None
+    net = _variant_net(cfg, p).train()
+    net._injected_keep_mask = keep.to(torch.uint8)
+    if cfg.use_v:
+        net._injected_v_keep_mask = vkeep.to(torch.uint8)
+    out = net(x.cuda(), batch_positions=d.cuda())
+    v_mask = _value_relu_mask(net, B) if cfg.use_v else None
+    r_masks = _residual_relu_masks(net, cfg, B, T, H, W) if cfg.block_type == "residual" else None
+    cov = cfg.covar_dim
+    loss, _ = ub.MultiGaussianNLLLoss(mode=cfg.covmode, chunk=None, covariance="none")(out[:, :, :13], y.cuda(), out[:, :, 13:13 + cov])
+    loss.backward()
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    O.RELU_MASKS = r_masks
+    try:
+        o_out, o_loss, o_g, _ = O.step(p64, x.double(), y.double(), d.double(), cfg, True, keep, v_keep_mask=vkeep, v_relu_mask=v_mask)
+    finally:
+        O.RELU_MASKS = None
+    assert out.shape == o_out.shape
+    assert rel_l2(out, o_out) <= 1e-3 and abs(loss.item() - o_loss.item()) <= 1e-3 * abs(o_loss.item())
+    scale = max(float(g.norm()) for g in o_g.values())
+    errs = _grad_errors(net, o_g, scale)
+    worst = max(errs, key=errs.get)
+    report("parity_report.txt", [f"variant edge case {case['kw']} B{B} T{T} {H}x{W}: out rel_l2={rel_l2(out, o_out):.3e} worst grad rel_l2={errs[worst]:.3e} ({worst})"])
+    assert errs[worst] <= 1e-3, (worst, errs[worst])
+    sd = net.state_dict()
+    net.eval()
+    with torch.no_grad():
+        e_out = net(x.cuda(), batch_positions=d.cuda())
+    p_eval = {k: (v.double().cpu() if v.is_floating_point() else v.cpu()) for k, v in sd.items()}
+    assert rel_l2(e_out, O.forward(p_eval, x.double(), d.double(), cfg, training=False)) <= 1e-3
