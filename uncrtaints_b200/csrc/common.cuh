@@ -195,6 +195,16 @@ __device__ __forceinline__ void st4_stream(float* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- pre-split operand images of the 3x3 convolutions (gemm_tc.cu, norm.cu) ----
+// hi / lo halves of a [N][H][W][128] fp32 tensor: one pixel = 512 bytes (128 hi halves, then 128 lo halves, 2 bytes each); image rows
+// are padded by ONE halo pixel on each side (x' = x + 1 in [0, W + 2)), which holds the reflected neighbour (activations: x' = 0 <- x = 1,
+// x' = W + 1 <- x = W - 2) or zeros (output gradients), so that a tile shifted by a tap's dx is a plain box of the image for the TMA.
+#define UB_SPLIT_ROW 512
+__host__ __device__ __forceinline__ size_t split_pixel_offset(size_t n, int y, int x, int H, int W) {
+    return ((n * (size_t)H + (size_t)y) * (size_t)(W + 2) + (size_t)(x + 1)) * UB_SPLIT_ROW;
+}
+inline size_t split_image_bytes(size_t N, int H, int W) { return N * (size_t)H * (size_t)(W + 2) * UB_SPLIT_ROW; }
+
 // ---- Philox4x32-10 counter RNG (dropout on the upsampled attention, uncrtaints.py:154,202) ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -322,7 +322,7 @@ typedef TLoadNormBwdT<float> TLoadNormBwd;
 // Every input element is read nine times, so the previous layer's norm + ReLU and the hi / lo split are applied ONCE into a
 // pre-split image (split_act_kernel / relu_norm_bwd_apply_kernel) and the loaders only copy 16-byte chunks.
 // paired: the operand has 256 "channels" = taps (tap0, tap1) side by side (the N operand of the weight-gradient GEMM); tap1 < 0 -> zeros.
-constexpr int SPLIT_ROW = 512;         // bytes per pixel of a pre-split image: 128 hi halves, then 128 lo halves
+constexpr int SPLIT_ROW = UB_SPLIT_ROW; // bytes per pixel of a pre-split image (layout: common.cuh, split_pixel_offset)
 struct TLoadConvSplit {
     static constexpr bool PRESPLIT = true;
     const char* img; int H, W, zero_pad, paired, tap0, tap1;
@@ -334,7 +334,7 @@ struct TLoadConvSplit {
         const uint32_t n = row32 / P, p = row32 - n * P;
         pos.y = (int)(p / (uint32_t)W);
         pos.x = (int)(p - (uint32_t)pos.y * (uint32_t)W);
-        pos.frame = img + (size_t)n * P * SPLIT_ROW;
+        pos.frame = img + split_pixel_offset(n, 0, -1, H, W);          // first (halo) pixel of the frame
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const {
         Pos pos;
@@ -353,7 +353,7 @@ struct TLoadConvSplit {
             xs = xs < 0 ? 1 : (xs >= W ? W - 2 : xs);
         }
         if (ok) {
-            const char* src = pos.frame + (size_t)(yy * W + xs) * SPLIT_ROW + (ch0 & 127) * 2;
+            const char* src = pos.frame + (size_t)(yy * (W + 2) + xs + 1) * SPLIT_ROW + (ch0 & 127) * 2;
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.h.x), "=r"(r.h.y), "=r"(r.h.z), "=r"(r.h.w) : "l"(src));
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.l.x), "=r"(r.l.y), "=r"(r.l.z), "=r"(r.l.w) : "l"(src + 256));
         } else {
@@ -368,16 +368,19 @@ struct TLoadConvSplit {
         if (single != SPLIT_BF16X1) *reinterpret_cast<uint4*>(lo_chunk) = r.l;
     }
 };
-struct TLoadPlainSplit {       // rows of a pre-split [rows][128] image as they are (A operand of the convolution weight gradient)
+struct TLoadPlainSplit {       // pixels of a pre-split image as they are (A operand of the convolution weight gradient)
     static constexpr bool PRESPLIT = true;
-    const char* img;
+    const char* img; int H, W;
     struct Raw { uint4 h, l; };
     struct Pos { size_t row; };
     __device__ void locate(size_t row, Pos& pos) const { pos.row = row; }
     __device__ void issue_at(const Pos& pos, int K, int ch0, Raw& r) const { issue(pos.row, K, ch0, r); }
     __device__ void fill(int, int, float*) const {}
     __device__ void issue(size_t row, int /*K*/, int ch0, Raw& r) const {
-        const char* src = img + row * SPLIT_ROW + ch0 * 2;
+        const uint32_t P = (uint32_t)(H * W), row32 = (uint32_t)row;
+        const uint32_t n = row32 / P, p = row32 - n * P;
+        const int y = (int)(p / (uint32_t)W), x = (int)(p - (uint32_t)y * (uint32_t)W);
+        const char* src = img + split_pixel_offset(n, y, x, H, W) + ch0 * 2;
         asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.h.x), "=r"(r.h.y), "=r"(r.h.z), "=r"(r.h.w) : "l"(src));
         asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.l.x), "=r"(r.l.y), "=r"(r.l.z), "=r"(r.l.w) : "l"(src + 256));
     }
@@ -390,22 +393,27 @@ struct TLoadPlainSplit {       // rows of a pre-split [rows][128] image as they 
 };
 // out = split(relu?(x*scale + shift)): the pre-split image of a [N][P][128] fp32 tensor.  thread = 8 channels of one pixel.
 __global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict__ x, const Coef* __restrict__ coef, char* __restrict__ out,
-                                                        int P, size_t rows, int relu, int mode) {
+                                                        int H, int W, size_t rows, int relu, int mode) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= rows * 16) return;
     const size_t row = i / 16;
     const int c0 = (int)(i % 16) * 8;
+    const uint32_t P = (uint32_t)(H * W), n = (uint32_t)row / P, p = (uint32_t)row - n * P;
+    const int y = (int)(p / (uint32_t)W), xx = (int)(p - (uint32_t)y * (uint32_t)W);
     float a[8], v[8];
     ld8(x + row * 128 + c0, a);
     if (coef) {
-        const Coef* k = coef + (row / P) * 128 + c0;
+        const Coef* k = coef + (size_t)n * 128 + c0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], k[j].scale, k[j].shift);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = relu ? fmaxf(a[j], 0.f) : a[j];
-    char* dst = out + row * SPLIT_ROW + c0 * 2;
+    char* dst = out + split_pixel_offset(n, y, xx, H, W) + c0 * 2;
     split_store8(v, dst, dst + 256, mode);
+    // halo pixels hold the reflected neighbour: x' = 0 <- x = 1, x' = W + 1 <- x = W - 2
+    if (xx == 1) { char* h = out + split_pixel_offset(n, y, -1, H, W) + c0 * 2; split_store8(v, h, h + 256, mode); }
+    if (xx == W - 2) { char* h = out + split_pixel_offset(n, y, W, H, W) + c0 * 2; split_store8(v, h, h + 256, mode); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1299,9 +1307,9 @@ int tc_prep_conv_weights(const float* w, void* img, int dgrad, int f16, cudaStre
 }
 // split[N*P][512 B] = hi / lo halves of relu?(x*scale + shift) (coef may be null); mode: 2 = fp16 hi/lo (forward operands),
 // 0 = bf16 hi/lo (gradient GEMMs), 1 = bf16 hi only
-int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N, int P, int mode, cudaStream_t st) {
-    const size_t rows = (size_t)N * P;
-    tc::split_act_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(x, coef, static_cast<char*>(split), P, rows, relu, mode);
+int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N, int H, int W, int mode, cudaStream_t st) {
+    const size_t rows = (size_t)N * H * W;
+    tc::split_act_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(x, coef, static_cast<char*>(split), H, W, rows, relu, mode);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
@@ -1325,7 +1333,7 @@ int tc_conv3x3_wgrad(const void* dcs, const void* xs, float* partial, int max_pa
         const int tapB = t + 1 < 9 ? t + 1 : -1;
         tc::TLoadConvSplit lb{static_cast<const char*>(xs), H, W, 0, 1, t, tapB};
         int nparts = 0;
-        UB_TRY(tc::launch_wgrad_tc(tc::TLoadPlainSplit{static_cast<const char*>(dcs)}, lb, partial, max_parts, N, H * W, UB_HID, 1, single, &nparts, st));
+        UB_TRY(tc::launch_wgrad_tc(tc::TLoadPlainSplit{static_cast<const char*>(dcs), H, W}, lb, partial, max_parts, N, H * W, UB_HID, 1, single, &nparts, st));
         tc::reduce_conv_partials_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(partial, dw, t, tapB, nparts);
         UB_CHECK_LAUNCH();
     }

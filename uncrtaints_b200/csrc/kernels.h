@@ -28,8 +28,8 @@ int launch_residual_bwd(const float* dout, const float* dn0, const float* x, con
 // norm.cu: residual blocks (conv3x3 -> norm -> ReLU layers)
 int launch_residual_relu_fwd(const float* x, const float* c3, const Coef* coef3, float* out, double* out_stats, int N, int P, cudaStream_t st);
 int launch_relu_norm_bwd_stats(const float* dy, const float* c, const Coef* coef, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
-int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int P,
-                               cudaStream_t st);
+int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int H,
+                               int W, cudaStream_t st);
 int launch_conv_fold(const void* dc_split, const float* w, float* din, int N, int H, int W, cudaStream_t st);
 
 // gemm_simt.cu
@@ -70,7 +70,7 @@ int tc_gemm1_bwd(const void* dz1, const void* h1, const BCoef* bc1, const void* 
 // gemm_tc.cu: dense 3x3 convolutions (reflect padding) of the residual blocks as implicit GEMMs over (tap, channel), weights streamed,
 // operands read from pre-split (hi / lo) images
 int tc_prep_conv_weights(const float* w, void* img, int dgrad, int f16, cudaStream_t st);
-int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N, int P, int mode, cudaStream_t st);
+int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N, int H, int W, int mode, cudaStream_t st);
 int tc_conv3x3_fwd(const void* xs, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W, int single,
                    cudaStream_t st);
 int tc_conv3x3_dgrad(const void* dcs, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,

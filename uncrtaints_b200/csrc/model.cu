@@ -90,7 +90,8 @@ struct Layout {
     int residual;               // block_type: 0 = MBConv, 1 = ResidualConvBlock
     ResWs rblk[1 + 16];
     size_t res_scratch;         // [Nmax][128] doubles: statistics sink of the input-gradient GEMM epilogue
-    size_t res_split;           // [Nmax][P] x 512 B: pre-split (hi / lo) image of the current convolution's input activations
+    size_t res_split;           // pre-split (hi / lo) image of the current convolution's input activations (common.cuh: split_image_bytes)
+    size_t res_dcsplit;         // pre-split image of the current convolution's output gradient (backward)
     size_t hes;                 // bytes per element of the 256-channel hidden tensors h1, h2, du, dz1 (4, or 2 with gemm_backend bit 5)
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
@@ -242,7 +243,8 @@ static int make_layout(const ub200_desc* d, Layout& L) {
             L.blk[i].out = r.out;
         }
         L.res_scratch = b.take((size_t)L.Nmax * UB_WIDTH * sizeof(double));
-        L.res_split = b.take((size_t)L.Nmax * P * 512);
+        L.res_split = b.take(split_image_bytes((size_t)L.Nmax, d->H, d->W));
+        L.res_dcsplit = d->need_grad ? b.take(split_image_bytes((size_t)L.Nmax, d->H, d->W)) : 0;
     } else if (d->need_grad) {
         for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, true, L.hes);
     } else {
@@ -473,7 +475,7 @@ static int residual_forward(const ub200_desc* d, const Layout& L, int i, const v
         // split are applied ONCE into a pre-split image (2 A of extra traffic), the GEMM's loader then only copies 16-byte chunks
         // (measured at B=16 against converting in the loader: conv forward 40.5 -> 35.1, input gradient 46.6 -> 41.6, weight
         // gradient 45.2 -> 37.8 ms per step, for 12.3 ms of split passes)
-        UB_PROF(KID_SE_POOL, st, tc_split_act(in, incoef, l > 0, at<char>(ws, L.res_split), N, P, single, st));
+        UB_PROF(KID_SE_POOL, st, tc_split_act(in, incoef, l > 0, at<char>(ws, L.res_split), N, d->H, d->W, single, st));
         UB_PROF(KID_GEMM1_FWD, st, tc_conv3x3_fwd(at<char>(ws, L.res_split), at<char>(ws, w.wimg[l]), pf(q, UB200_R_B), at<float>(ws, w.c[l]),
                                                         at<double>(ws, w.stats[l]), N, d->H, d->W, single, st));
         UB_TRY(launch_norm_finalize(at<double>(ws, w.stats[l]), pf(q, UB200_R_N_W), pf(q, UB200_R_N_B), pfm(q, UB200_R_N_RM), pfm(q, UB200_R_N_RV),
@@ -485,10 +487,11 @@ static int residual_forward(const ub200_desc* d, const Layout& L, int i, const v
     UB_PROF(KID_RESIDUAL_FWD, st, launch_residual_relu_fwd(x, at<float>(ws, w.c[2]), at<Coef>(ws, w.coef[2]), at<float>(ws, w.out), next_stats, N, P, st));
     return UB_OK;
 }
-// dout -> dx (may not alias); dc: [N][P][128] scratch for the materialised convolution output gradient; t0, t1: two more such buffers
+// dout -> dx (may not alias); t0, t1: two [N][P][128] scratch buffers for the gradients between the layers
 static int residual_backward(const ub200_desc* d, const Layout& L, int i, const void* const* params, void* const* grads, const float* x,
-                             const float* dout, float* dx, float* dc, float* t0, float* t1, float* partial, void* ws, cudaStream_t st) {
+                             const float* dout, float* dx, float* t0, float* t1, float* partial, void* ws, cudaStream_t st) {
     const ResWs& w = L.rblk[i];
+    char* dc = at<char>(ws, L.res_dcsplit);                // the convolution's output gradient as a pre-split image
     const int N = i == 0 ? L.Ne : L.B, groups = i == 0 ? d->enc_groups : d->dec_groups, P = L.P;
     const void* const* p = params + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE;
     void* const* g = grads + UB200_P_BLOCK0 + i * UB200_BLOCK_STRIDE;
@@ -502,11 +505,11 @@ static int residual_backward(const ub200_desc* d, const Layout& L, int i, const 
         UB_TRY(launch_norm_finalize_bwd(at<double>(ws, w.bstats[l]), pf(q, UB200_R_N_W), at<MeanRstd>(ws, w.mr[l]), at<BCoef>(ws, w.bc[l]),
                                         gf(gq, UB200_R_N_W), gf(gq, UB200_R_N_B), N, UB_WIDTH, groups, (double)P, d->training, st));
         UB_PROF(KID_RESIDUAL_BWD, st, launch_relu_norm_bwd_apply(dy, at<float>(ws, w.c[l]), at<Coef>(ws, w.coef[l]), at<BCoef>(ws, w.bc[l]), dc,
-                                                                 gf(gq, UB200_R_B), N, P, st));
+                                                                 gf(gq, UB200_R_B), N, d->H, d->W, st));
         const float* in = l == 0 ? x : at<float>(ws, w.c[l - 1]);
         const Coef* incoef = l == 0 ? nullptr : at<Coef>(ws, w.coef[l - 1]);
         if (gf(gq, UB200_R_W)) {
-            UB_PROF(KID_SE_POOL, st, tc_split_act(in, incoef, l > 0, at<char>(ws, L.res_split), N, P, single, st));      // bf16 hi/lo (gradient GEMM)
+            UB_PROF(KID_SE_POOL, st, tc_split_act(in, incoef, l > 0, at<char>(ws, L.res_split), N, d->H, d->W, single, st));      // bf16 hi/lo (gradient GEMM)
             UB_PROF(KID_WGRAD1, st, tc_conv3x3_wgrad(dc, at<char>(ws, L.res_split), partial, L.max_parts, gf(gq, UB200_R_W), N, d->H, d->W,
                                                            single, st));
         }
@@ -824,7 +827,7 @@ int ub200_backward_v(const ub200_desc* d, const float* input, const void* const*
         BlockCtx c = make_ctx(d, L, i, params, grads, ws, st);
         const float* x = i == 1 ? (d->is_mono ? at<float>(ws, L.blk[0].out) : at<float>(ws, d->use_v ? L.V.mix : L.agg)) : at<float>(ws, L.blk[i - 1].out);
         if (L.residual)
-            UB_TRY(residual_backward(d, L, i, params, grads, x, gA, gB, dn0, static_cast<float*>(du), static_cast<float*>(du) + (size_t)L.Nmax * P * UB_WIDTH,
+            UB_TRY(residual_backward(d, L, i, params, grads, x, gA, gB, static_cast<float*>(du), static_cast<float*>(du) + (size_t)L.Nmax * P * UB_WIDTH,
                                      partial, ws, st));
         else
         UB_TRY(mbconv_backward(c, x, gA, gB, dn0, du, dz1, partial));
@@ -855,7 +858,7 @@ int ub200_backward_v(const ub200_desc* d, const float* input, const void* const*
     BlockCtx enc = make_ctx(d, L, 0, params, grads, ws, st);
     enc.relu_mask_dx = 1;                     // the gram pass then consumes dgn = dX0 * [x0 > 0] directly
     if (L.residual)
-        UB_TRY(residual_backward(d, L, 0, params, grads, at<float>(ws, L.x0), gB, gA, dn0, static_cast<float*>(du),
+        UB_TRY(residual_backward(d, L, 0, params, grads, at<float>(ws, L.x0), gB, gA, static_cast<float*>(du),
                                  static_cast<float*>(du) + (size_t)L.Nmax * P * UB_WIDTH, partial, ws, st));
     else
     UB_TRY(mbconv_backward(enc, at<float>(ws, L.x0), gB, gA, dn0, du, dz1, partial));

@@ -339,7 +339,8 @@ __device__ __forceinline__ void st_split4_bf16(char* row_base, int c0, const flo
 }
 __global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ c,
                                                                    const Coef* __restrict__ coef, const BCoef* __restrict__ bc,
-                                                                   char* __restrict__ dc, float* dbias, int P, int chunk) {
+                                                                   char* __restrict__ dc, float* dbias, int H, int W, int chunk) {
+    const int P = H * W;
     constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
     __shared__ __align__(16) float smem[ROWS * C];
     const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
@@ -361,7 +362,12 @@ __global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* _
             o[i] = fmaf(b[i].a, dz, fmaf(b[i].b, cv[i], b[i].c));
             s[i] += o[i];
         }
-        st_split4_bf16(dc + ((size_t)n * P + p) * 512, c4 * 4, o);
+        const int y = p / W, xx = p - y * W;
+        st_split4_bf16(dc + split_pixel_offset(n, y, xx, H, W), c4 * 4, o);
+        if (xx == 0 || xx == W - 1) {             // zero halo pixel beside the image (the input gradient's operand is zero-extended)
+            const float z[4] = {0.f, 0.f, 0.f, 0.f};
+            st_split4_bf16(dc + split_pixel_offset(n, y, xx == 0 ? -1 : W, H, W), c4 * 4, z);
+        }
     }
     if (dbias) {
         reinterpret_cast<float4*>(smem)[r * Q + c4] = make_float4(s[0], s[1], s[2], s[3]);
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(128) conv_fold_kernel(const char* __restrict__
     size_t src[3];
     for (int t = 0; t < 9; ++t) {
         const int py = ry - (t / 3 - 1), px = rx - (t % 3 - 1);
-        if (py >= 0 && py < H && px >= 0 && px < W && np < 3) { taps[np] = t; src[np] = ((size_t)n * H * W + (size_t)py * W + px) * 512; ++np; }
+        if (py >= 0 && py < H && px >= 0 && px < W && np < 3) { taps[np] = t; src[np] = split_pixel_offset(n, py, px, H, W); ++np; }
     }
     for (int i = 0; i < np; ++i) {
         const unsigned short hb = *reinterpret_cast<const unsigned short*>(dc + src[i] + ci * 2);
@@ -478,10 +484,10 @@ int launch_relu_norm_bwd_stats(const float* dy, const float* c, const Coef* coef
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int P,
-                               cudaStream_t st) {
-    const int chunk = chunk_for(P);
-    relu_norm_bwd_apply_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, c, coef, bc, static_cast<char*>(dc_split), dbias, P, chunk);
+int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int H,
+                               int W, cudaStream_t st) {
+    const int P = H * W, chunk = chunk_for(P);
+    relu_norm_bwd_apply_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dy, c, coef, bc, static_cast<char*>(dc_split), dbias, H, W, chunk);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
