@@ -18,6 +18,7 @@
 // * pipeline: 2-slot shared-memory ring of 64-channel K-blocks (tcgen05.commit -> mbarrier frees a slot) and a
 //   double-buffered TMEM accumulator (2 x 256 columns): the MMAs of tile t run while the threads do the epilogue
 //   of tile t-1 and load tile t+1.
+#include <cuda.h>            // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -1231,6 +1232,166 @@ static int launch_bwd_fused(LS ls, LR lr, const void* wimg, Epi ep, float* parti
     return UB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// 3x3 convolution (forward and input gradient) fed entirely by the TMA engine -- no producer warps.
+//
+// The pre-split image (common.cuh: 512-byte pixels, image rows padded by one halo pixel per side) is a 4-D tensor
+// [n][y][x'][256 halves] for the TMA; the operand tile of output pixels (y, x0 .. x0+127) for tap (dy, dx) and channel block h
+// is the box {64 halves, 128 pixels, 1, 1} at coordinates (h*64 [+128 for the lo halves], x0 + dx + 1, y + dy, n), written with the
+// hardware's 128-byte swizzle -- byte for byte the K-major SWIZZLE_128B tile the thread loaders wrote.  The halo pixels make the
+// shifted box always lie inside the padded row (reflected neighbour for the activations, zeros for the output gradient); rows
+// above / below the image are the reflected coordinate (forward) or out of bounds = zero fill (input gradient).
+// Roles: warp 0 one lane: per K-block two cp.async.bulk for the weight slabs + two cp.async.bulk.tensor for the operand halves into
+// a 3-stage ring (64 KB per stage, mbarrier complete_tx); warp 1 one lane: tcgen05.mma + commit; warps 2..9: epilogue out of the
+// double-buffered TMEM accumulator.  Requires W % 128 == 0 (a tile inside one image row); other widths use the thread-loader kernel.
+// ncu of the thread-loader version (profiles/r02_ncu_conv3x3.md): the 16 producer warps were bound by the latency of their own
+// instruction stream (250 instructions per thread and K-block), tensor pipe 29 % active.
+// ------------------------------------------------------------------------------------------
+constexpr int CT_STAGES = 3;
+constexpr int CT_STAGE_BYTES = 4 * 16384;      // weight hi slab, weight lo slab, operand hi tile, operand lo tile
+constexpr int CT_EPI_WARPS = 8;
+constexpr int CT_THREADS = 32 * (2 + CT_EPI_WARPS);
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const char* __restrict__ wimg, Epi ep, int H, int W, int reflect, int single) {
+    constexpr int KB = 18, NOUT = UB_WIDTH, SLAB = NOUT * 128, W_HALF = 9 * UB_WIDTH * NOUT * 2;
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE_BYTES);      // full[S], empty[S], accfull[2], accempty[2]
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2 * CT_STAGES + 4);
+    const uint32_t bFull = smem_u32(&sBar[0]), bEmpty = smem_u32(&sBar[CT_STAGES]), bAccFull = smem_u32(&sBar[2 * CT_STAGES]),
+                   bAccEmpty = smem_u32(&sBar[2 * CT_STAGES + 2]);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, n = blockIdx.y;
+    const int P = H * W, tiles_per_frame = P / TILE_PX, tiles_per_row = W / TILE_PX;
+    const int t0 = (int)(((long long)blockIdx.x * tiles_per_frame) / gridDim.x);
+    const int t1 = (int)(((long long)(blockIdx.x + 1) * tiles_per_frame) / gridDim.x);
+    const int ntiles = t1 - t0, Q = ntiles * KB;
+    if (tid == 0) {
+        for (int i = 0; i < 2 * CT_STAGES + 2; ++i) mbar_init(smem_u32(&sBar[i]), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(bAccEmpty + i * 8, CT_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+
+    if (warp == 0) {
+        if (lane == 0) {                       // ---- TMA producer ----
+            for (int q = 0; q < Q; ++q) {
+                const int it = q / KB, kb = q - it * KB, s = q % CT_STAGES, use = q / CT_STAGES;
+                mbar_wait_guard(bEmpty + s * 8, ((uint32_t)use & 1) ^ 1);
+                const int t = t0 + it, y = t / tiles_per_row, x0 = (t - y * tiles_per_row) * TILE_PX;
+                const int tap = kb >> 1, half = kb & 1, t3 = tap >= 6 ? 2 : (tap >= 3 ? 1 : 0);
+                int yy = y + t3 - 1;
+                const int xc = x0 + (tap - 3 * t3) - 1 + 1;                     // + 1: halo pixel in front of every image row
+                if (reflect) yy = yy < 0 ? 1 : (yy >= H ? H - 2 : yy);            // else: rows outside the image are zero-filled by the TMA
+                const uint32_t stage = smem_u32(smem) + (uint32_t)s * CT_STAGE_BYTES, bar = bFull + s * 8;
+                mbar_expect_tx(bar, CT_STAGE_BYTES);
+                bulk_g2s(stage, wimg + (size_t)kb * SLAB, SLAB, bar);
+                bulk_g2s(stage + 16384, wimg + (size_t)W_HALF + (size_t)kb * SLAB, SLAB, bar);
+                tma_load_4d(stage + 32768, &tmap, half * 64, xc, yy, n, bar);
+                tma_load_4d(stage + 49152, &tmap, 128 + half * 64, xc, yy, n, bar);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                       // ---- MMA issuer ----
+            const uint32_t idesc = single == SPLIT_F16X3 ? (c_idesc & ~((7u << 7) | (7u << 10))) : c_idesc;
+            for (int q = 0; q < Q; ++q) {
+                const int it = q / KB, kb = q - it * KB, s = q % CT_STAGES, use = q / CT_STAGES;
+                if (kb == 0) {                 // the accumulator stage must have been drained by the epilogue of tile it - 2
+                    mbar_wait_guard(bAccEmpty + (it & 1) * 8, (((uint32_t)it >> 1) & 1) ^ 1);
+                }
+                mbar_wait_guard(bFull + s * 8, (uint32_t)use & 1);
+                tc_fence_after();
+                const uint32_t stage = smem_u32(smem) + (uint32_t)s * CT_STAGE_BYTES;
+                const uint32_t a_hi = stage, a_lo = stage + 16384, b_hi = stage + 32768, b_lo = stage + 49152;
+                const uint32_t d = tmem_base + (uint32_t)(it & 1) * TILE_PX;
+#pragma unroll
+                for (int k16 = 0; k16 < KBLK / 16; ++k16) {
+                    const uint64_t wa = make_desc(a_hi + k16 * 32), wl = make_desc(a_lo + k16 * 32);
+                    const uint64_t xa = make_desc(b_hi + k16 * 32), xl = make_desc(b_lo + k16 * 32);
+                    tc_mma(d, wa, xa, idesc, (kb | k16) != 0);
+                    if (single != SPLIT_BF16X1) {
+                        tc_mma(d, wa, xl, idesc, 1);
+                        tc_mma(d, wl, xa, idesc, 1);
+                    }
+                }
+                tc_commit(bEmpty + s * 8);
+                if (kb == KB - 1) tc_commit(bAccFull + (it & 1) * 8);
+            }
+        }
+    } else {                                   // ---- epilogue: TMEM lane quarter = warp % 4, 64-pixel half = (warp - 2) / 4 ----
+        const int lq = warp % 4, ph = (warp - 2) / 4, ch = lq * 32 + lane;
+        typename Epi::State est;
+        float stat[Epi::NS];
+        ep.init(n, NOUT, ch, est);
+#pragma unroll
+        for (int i = 0; i < Epi::NS; ++i) stat[i] = 0.f;
+        for (int it = 0; it < ntiles; ++it) {
+            mbar_wait_guard(bAccFull + (it & 1) * 8, ((uint32_t)it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(it & 1) * TILE_PX + ph * 64 + c * 32, v);
+                ep.template apply<32>(est, (size_t)n * P + (size_t)(t0 + it) * TILE_PX + ph * 64 + c * 32, NOUT, ch, v, stat);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bAccEmpty + (it & 1) * 8);
+        }
+        double* dst = ep.dst(n, NOUT);
+#pragma unroll
+        for (int i = 0; i < Epi::NS; ++i) atomicAdd(&dst[(size_t)ch * Epi::NS + i], (double)stat[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+// 4-D tensor map of a pre-split image [N][H][W + 2][256 halves] with box {64, 128, 1, 1} and the 128-byte swizzle
+static int make_split_tmap(CUtensorMap* tm, const void* img, int N, int H, int W) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return UB_ERR_CUDA;
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[4] = {256, (cuuint64_t)(W + 2), (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {UB_SPLIT_ROW, (cuuint64_t)(W + 2) * UB_SPLIT_ROW, (cuuint64_t)H * (W + 2) * UB_SPLIT_ROW};
+    const cuuint32_t box[4] = {64, TILE_PX, 1, 1}, estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? UB_OK : UB_ERR_CUDA;
+}
+
+template <class Epi>
+static int launch_conv_tma(const void* img, const void* wimg, Epi ep, int N, int H, int W, int reflect, int single, cudaStream_t st) {
+    CUtensorMap tm;
+    UB_TRY(make_split_tmap(&tm, img, N, H, W));
+    constexpr size_t smem = (size_t)CT_STAGES * CT_STAGE_BYTES + (2 * CT_STAGES + 4) * 8 + 16 + 1024;
+    auto kern = conv_tma_kernel<Epi>;
+    UB_SET_SMEM(kern, smem);
+    const dim3 grid(blocks_per_frame(N, H * W / TILE_PX), N);
+    kern<<<grid, CT_THREADS, smem, st>>>(tm, static_cast<const char*>(wimg), ep, H, W, reflect, single);
+    UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
 // Weight image: src is fp32 [rows][K] (transpose == 0) or [K][rows] (transpose == 1, i.e. the M operand is src^T).
 // Output: bf16 hi image then lo image, each [K/64][rows][64] in the K-major SWIZZLE_128B layout.
 __global__ void prep_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ img, int rows, int K, int transpose, int f16) {
@@ -1316,6 +1477,7 @@ int tc_split_act(const float* x, const Coef* coef, int relu, void* split, int N,
 // c[N][P][128] = conv3x3_reflect(xs) + bias; stats[N][128][2] += column (sum, sumsq).  xs: pre-split input activations
 int tc_conv3x3_fwd(const void* xs, const void* wimg, const float* bias, float* c, double* stats, int N, int H, int W, int single,
                    cudaStream_t st) {
+    if (W % tc::TILE_PX == 0) return tc::launch_conv_tma(xs, wimg, tc::TEpiBiasStoreStats{c, bias, stats}, N, H, W, 1, single, st);
     tc::TLoadConvSplit al{static_cast<const char*>(xs), H, W, 0, 0, 0, 0};
     return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConvSplit, tc::TEpiBiasStoreStats, true>(al, wimg, tc::TEpiBiasStoreStats{c, bias, stats}, N, H * W, single, st);
 }
@@ -1323,6 +1485,7 @@ int tc_conv3x3_fwd(const void* xs, const void* wimg, const float* bias, float* c
 // dcs: pre-split output gradient
 int tc_conv3x3_dgrad(const void* dcs, const void* wimg_t, const float* add, float* din, double* scratch, int N, int H, int W, int single,
                      cudaStream_t st) {
+    if (W % tc::TILE_PX == 0) return tc::launch_conv_tma(dcs, wimg_t, tc::TEpiStoreAdd{din, add, scratch}, N, H, W, 0, single, st);
     tc::TLoadConvSplit al{static_cast<const char*>(dcs), H, W, 1, 0, 0, 0};
     return tc::launch<9 * UB_WIDTH, UB_WIDTH, tc::TLoadConvSplit, tc::TEpiStoreAdd, true>(al, wimg_t, tc::TEpiStoreAdd{din, add, scratch}, N, H * W, single, st);
 }
