@@ -1361,7 +1361,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const char* __restrict
 }
 
 // 4-D tensor map of a pre-split image [N][H][W + 2][256 halves] with box {64, 128, 1, 1} and the 128-byte swizzle
-static int make_split_tmap(CUtensorMap* tm, const void* img, int N, int H, int W) {
+static int make_split_tmap(CUtensorMap* tm, const void* img, int N, int H, int W, int box_px = TILE_PX) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
@@ -1373,7 +1373,7 @@ static int make_split_tmap(CUtensorMap* tm, const void* img, int N, int H, int W
     }
     const cuuint64_t dims[4] = {256, (cuuint64_t)(W + 2), (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {UB_SPLIT_ROW, (cuuint64_t)(W + 2) * UB_SPLIT_ROW, (cuuint64_t)H * (W + 2) * UB_SPLIT_ROW};
-    const cuuint32_t box[4] = {64, TILE_PX, 1, 1}, estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_px, 1, 1}, estr[4] = {1, 1, 1, 1};
     const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? UB_OK : UB_ERR_CUDA;
@@ -1389,6 +1389,125 @@ static int launch_conv_tma(const void* img, const void* wimg, Epi ep, int N, int
     const dim3 grid(blocks_per_frame(N, H * W / TILE_PX), N);
     kern<<<grid, CT_THREADS, smem, st>>>(tm, static_cast<const char*>(wimg), ep, H, W, reflect, single);
     UB_CHECK_LAUNCH();
+    return UB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient of a 3x3 convolution for one tap pair, TMA-fed:  dW[co][j*128 + ci] += sum_p dc[p][co] * act[reflect(p + tap_j)][ci].
+// Same MN-major tcgen05 GEMM as wgrad_tc_body (64-pixel tiles, the whole 128 x 256 gradient in TMEM), but both operands arrive as
+// TMA boxes of the pre-split images: A = four [64 px][64 halves] boxes of the output gradient (hi / lo x two channel blocks), B = eight
+// boxes of the activations (two taps x hi / lo x two channel blocks), each tap's box shifted by (dy, dx) (halo pixel / reflected row
+// coordinate).  Warp 0 lane 0: TMA producer (2-stage ring, 96 KB per stage); warp 1 lane 0: MMA issuer; warps 2..5: final TMEM read-out.
+// Requires W % 64 == 0 (a tile inside one image row); persistent CTAs walk contiguous tile ranges across frames.
+// ------------------------------------------------------------------------------------------
+constexpr int CW_STAGE_BYTES = WG_STAGE;       // 32 KB A + 64 KB B
+constexpr int CW_THREADS = 32 * 6;
+__global__ void __launch_bounds__(CW_THREADS, 1)
+conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_dc, const __grid_constant__ CUtensorMap tmap_act, float* __restrict__ partial,
+                      int H, int W, long long total_tiles, int tapA, int tapB, int single) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + 2 * CW_STAGE_BYTES);     // full[2], empty[2], done
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 5);
+    const uint32_t bFull = smem_u32(&sBar[0]), bEmpty = smem_u32(&sBar[2]), bDone = smem_u32(&sBar[4]);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
+    const int ntiles = t1 > t0 ? (int)(t1 - t0) : 0;
+    float* dst = partial + (size_t)blockIdx.x * 128 * 256;
+    if (ntiles == 0) {
+        for (int i = tid; i < 128 * 256; i += CW_THREADS) dst[i] = 0.f;
+        return;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&sBar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+    const int tiles_per_row = W / WG_PX, tiles_per_frame = H * tiles_per_row;
+    if (warp == 0) {
+        if (lane == 0) {                       // ---- TMA producer ----
+            const int tb = tapB >= 0 ? tapB : tapA;                // absent second tap: load the first one again (its columns are ignored)
+            const int taps[2] = {tapA, tb};
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i & 1, use = i >> 1;
+                mbar_wait_guard(bEmpty + s * 8, ((uint32_t)use & 1) ^ 1);
+                const long long t = t0 + i;
+                const int n = (int)(t / tiles_per_frame), r = (int)(t - (long long)n * tiles_per_frame);
+                const int y = r / tiles_per_row, x0 = (r - y * tiles_per_row) * WG_PX;
+                const uint32_t stage = smem_u32(smem) + (uint32_t)s * CW_STAGE_BYTES, bar = bFull + s * 8;
+                mbar_expect_tx(bar, CW_STAGE_BYTES);
+                // A: output gradient, hi blocks 0..1 then lo blocks 0..1 (8 KB each)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) tma_load_4d(stage + b * WG_BLK, &tmap_dc, (b >> 1) * 128 + (b & 1) * 64, x0 + 1, y, n, bar);
+                // B: activations, hi blocks {tapA c0, tapA c64, tapB c0, tapB c64} then the same four lo blocks
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const int tap = taps[(b >> 1) & 1], t3 = tap >= 6 ? 2 : (tap >= 3 ? 1 : 0);
+                    int yy = y + t3 - 1;
+                    yy = yy < 0 ? 1 : (yy >= H ? H - 2 : yy);
+                    tma_load_4d(stage + WG_A_BYTES + b * WG_BLK, &tmap_act, (b >> 2) * 128 + (b & 1) * 64, x0 + (tap - 3 * t3) - 1 + 1, yy, n, bar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                       // ---- MMA issuer ----
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i & 1, use = i >> 1;
+                mbar_wait_guard(bFull + s * 8, (uint32_t)use & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem) + (uint32_t)s * CW_STAGE_BYTES, a_lo = a_hi + WG_A_BYTES / 2;
+                const uint32_t b_hi = a_hi + WG_A_BYTES, b_lo = b_hi + WG_B_BYTES / 2;
+#pragma unroll
+                for (int p16 = 0; p16 < WG_PX / 16; ++p16) {
+                    const uint64_t ah = make_wg_desc(a_hi + p16 * 2048), al = make_wg_desc(a_lo + p16 * 2048);
+                    const uint64_t bh = make_wg_desc(b_hi + p16 * 2048), bl = make_wg_desc(b_lo + p16 * 2048);
+                    tc_mma(tmem_base, ah, bh, c_wg_idesc, (i | p16) != 0);
+                    if (!single) {
+                        tc_mma(tmem_base, ah, bl, c_wg_idesc, 1);
+                        tc_mma(tmem_base, al, bh, c_wg_idesc, 1);
+                    }
+                }
+                tc_commit(bEmpty + s * 8);
+                if (i == ntiles - 1) tc_commit(bDone);
+            }
+        }
+    } else {                                   // ---- read-out of the 128 x 256 gradient (warp's TMEM lane quarter = warp % 4) ----
+        mbar_wait_guard(bDone, 0);
+        tc_fence_after();
+        const int lq = warp % 4, m = lq * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + c * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)m * 256 + c * 32 + i] = v[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+static int launch_conv_wgrad_tma(const void* dcs, const void* xs, float* partial, int max_parts, int N, int H, int W, int tapA, int tapB,
+                                 int single, int* nparts, cudaStream_t st) {
+    CUtensorMap tm_dc, tm_act;
+    UB_TRY(make_split_tmap(&tm_dc, dcs, N, H, W, WG_PX));
+    UB_TRY(make_split_tmap(&tm_act, xs, N, H, W, WG_PX));
+    constexpr size_t smem = (size_t)2 * CW_STAGE_BYTES + 5 * 8 + 16 + 1024;
+    UB_SET_SMEM(conv_wgrad_tma_kernel, smem);
+    const long long total = (long long)N * (H * W / WG_PX);
+    const int blocks = (int)(total < max_parts ? total : max_parts);
+    conv_wgrad_tma_kernel<<<blocks, CW_THREADS, smem, st>>>(tm_dc, tm_act, partial, H, W, total, tapA, tapB, single);
+    UB_CHECK_LAUNCH();
+    *nparts = blocks;
     return UB_OK;
 }
 
@@ -1496,6 +1615,9 @@ int tc_conv3x3_wgrad(const void* dcs, const void* xs, float* partial, int max_pa
         const int tapB = t + 1 < 9 ? t + 1 : -1;
         tc::TLoadConvSplit lb{static_cast<const char*>(xs), H, W, 0, 1, t, tapB};
         int nparts = 0;
+        if (W % tc::WG_PX == 0)
+            UB_TRY(tc::launch_conv_wgrad_tma(dcs, xs, partial, max_parts, N, H, W, t, tapB, single, &nparts, st));
+        else
         UB_TRY(tc::launch_wgrad_tc(tc::TLoadPlainSplit{static_cast<const char*>(dcs), H, W}, lb, partial, max_parts, N, H * W, UB_HID, 1, single, &nparts, st));
         tc::reduce_conv_partials_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(partial, dw, t, tapB, nparts);
         UB_CHECK_LAUNCH();
