@@ -30,7 +30,8 @@ int launch_residual_relu_fwd(const float* x, const float* c3, const Coef* coef3,
 int launch_relu_norm_bwd_stats(const float* dy, const float* c, const Coef* coef, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
 int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef, const BCoef* bc, void* dc_split, float* dbias, int N, int H,
                                int W, cudaStream_t st);
-int launch_conv_fold(const void* dc_split, const float* w, float* din, int N, int H, int W, cudaStream_t st);
+int launch_conv_fold(const void* dc_split, const float* w, float* wt_scratch /* 9*128*128 floats */, float* din, int N, int H, int W,
+                     cudaStream_t st);
 
 // gemm_simt.cu
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);

@@ -92,6 +92,7 @@ struct Layout {
     size_t res_scratch;         // [Nmax][128] doubles: statistics sink of the input-gradient GEMM epilogue
     size_t res_split;           // pre-split (hi / lo) image of the current convolution's input activations (common.cuh: split_image_bytes)
     size_t res_dcsplit;         // pre-split image of the current convolution's output gradient (backward)
+    size_t res_wfold;           // [9][128][128] fp32: tap-major weights of the current layer for the reflection-adjoint kernel
     size_t hes;                 // bytes per element of the 256-channel hidden tensors h1, h2, du, dz1 (4, or 2 with gemm_backend bit 5)
     size_t fwd_zero_begin, fwd_zero_end, bwd_zero_begin, bwd_zero_end;
     size_t notpad, stats_c0, coef_in, mr_in, x0, pooled, pool_idx, attn, agg;
@@ -245,6 +246,7 @@ static int make_layout(const ub200_desc* d, Layout& L) {
         L.res_scratch = b.take((size_t)L.Nmax * UB_WIDTH * sizeof(double));
         L.res_split = b.take(split_image_bytes((size_t)L.Nmax, d->H, d->W));
         L.res_dcsplit = d->need_grad ? b.take(split_image_bytes((size_t)L.Nmax, d->H, d->W)) : 0;
+        L.res_wfold = d->need_grad ? b.take((size_t)9 * UB_WIDTH * UB_WIDTH * sizeof(float)) : 0;
     } else if (d->need_grad) {
         for (int i = 0; i < L.nblk; ++i) block_rest(b, L.blk[i], i == 0 ? L.Ne : L.B, P, true, L.hes);
     } else {
@@ -516,7 +518,7 @@ static int residual_backward(const ub200_desc* d, const Layout& L, int i, const 
         float* din = l == 0 ? dx : (l == 2 ? t0 : t1);
         UB_PROF(KID_GEMM1_BWD, st, tc_conv3x3_dgrad(dc, at<char>(ws, w.wimgT[l]), l == 0 ? dout : nullptr, din, at<double>(ws, L.res_scratch), N,
                                                           d->H, d->W, single, st));
-        UB_TRY(launch_conv_fold(dc, pf(q, UB200_R_W), din, N, d->H, d->W, st));
+        UB_PROF(KID_WGRAD2, st, launch_conv_fold(dc, pf(q, UB200_R_W), at<float>(ws, L.res_wfold), din, N, d->H, d->W, st));
         dy = din;
     }
     return UB_OK;

@@ -385,38 +385,75 @@ __global__ void __launch_bounds__(256) relu_norm_bwd_apply_kernel(const float* _
 // transposed convolution g of the zero-extended output gradient on the H x W grid; the same g on the one-pixel ring AROUND the image
 // belongs to the pixels the ring reflects onto: din[(1, x')] += g[(-1, x)], din[(H-2, x')] += g[(H, x)], din[(y, 1)] += g[(y, -1)],
 // din[(y, W-2)] += g[(y, W)], x' = reflect(x) for x in [-1, W] (corners included in the two rows).
-//   g[r][ci] = sum_tap sum_co W[co][ci][tap] * dc[r - tap][co]   over the taps whose source pixel r - tap lies inside the image.
-// grid (ring positions, N); 128 threads = ci.  Ring position index: [0, W+2) top row, [W+2, 2W+4) bottom row, then H left, H right.
+//   g[r][ci] = sum_tap sum_co W[co][ci][tap] * dc[r - tap][co]   over the taps whose source pixel r - tap lies inside the image:
+// for a ring pixel of the top / bottom row the three taps of one kernel ROW, for the left / right column those of one kernel COLUMN.
+// A CTA owns 16 consecutive ring pixels of one side of one frame: the 18 source pixels they touch are staged in shared memory, each
+// of the three 128 x 128 tap matrices is staged once ([tap][co][ci] fp32 image, conv_fold_prep_kernel) and every thread (= ci)
+// accumulates its 16 outputs with 64 FMAs per four shared-memory loads.  (The first version, one CTA per ring pixel gathering the
+// weights with stride 9 from the [co][ci][3][3] tensor, took 25 ms per step at B=16 -- as long as the weight-gradient GEMMs.)
+constexpr int FOLD_PX = 16;
+__global__ void conv_fold_prep_kernel(const float* __restrict__ w /* [co][ci][9] */, float* __restrict__ wt /* [9][co][ci] */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * UB_WIDTH * UB_WIDTH) return;
+    const int tap = i / (UB_WIDTH * UB_WIDTH), r = i % (UB_WIDTH * UB_WIDTH);
+    wt[i] = w[(size_t)r * 9 + tap];
+}
 __global__ void __launch_bounds__(128) conv_fold_kernel(const char* __restrict__ dc /* pre-split bf16 hi/lo image */,
-                                                         const float* __restrict__ w /* [co][ci][9] */, float* din, int H, int W) {
-    __shared__ float sdc[3][UB_WIDTH];
-    const int n = blockIdx.y, pos = blockIdx.x, ci = threadIdx.x;
-    int ry, rx, ty = 0, tx = 0;          // ring pixel and the target pixel it reflects onto
-    if (pos < W + 2) { ry = -1; rx = pos - 1; ty = 1; }
-    else if (pos < 2 * (W + 2)) { ry = H; rx = pos - (W + 2) - 1; ty = H - 2; }
-    else if (pos < 2 * (W + 2) + H) { ry = pos - 2 * (W + 2); rx = -1; ty = ry; }
-    else { ry = pos - 2 * (W + 2) - H; rx = W; ty = ry; }
-    tx = rx < 0 ? 1 : (rx >= W ? W - 2 : rx);
-    // source pixels p = r - (dy, dx): at most three lie inside the image (one row or one column of taps)
-    int taps[3], np = 0;
-    size_t src[3];
-    for (int t = 0; t < 9; ++t) {
-        const int py = ry - (t / 3 - 1), px = rx - (t % 3 - 1);
-        if (py >= 0 && py < H && px >= 0 && px < W && np < 3) { taps[np] = t; src[np] = split_pixel_offset(n, py, px, H, W); ++np; }
+                                                         const float* __restrict__ wt /* [9][co][ci] */, float* din, int H, int W) {
+    extern __shared__ __align__(16) float fsm[];
+    float* sW = fsm;                                    // [co][ci] of the current tap: 64 KB
+    float* sdc = fsm + UB_WIDTH * UB_WIDTH;             // [FOLD_PX + 2][co]: source pixels start-1 .. start+FOLD_PX
+    const int n = blockIdx.y, ci = threadIdx.x;
+    const int nb_row = (W + 2 + FOLD_PX - 1) / FOLD_PX, nb_col = (H + FOLD_PX - 1) / FOLD_PX;
+    int bx = blockIdx.x, side;                          // 0 top, 1 bottom, 2 left, 3 right
+    if (bx < 2 * nb_row) { side = bx / nb_row; bx -= side * nb_row; } else { bx -= 2 * nb_row; side = 2 + bx / nb_col; bx -= (side - 2) * nb_col; }
+    const bool row_side = side < 2;
+    const int len = row_side ? W : H;                   // extent of the image along the side
+    const int first = (row_side ? -1 : 0) + bx * FOLD_PX;      // ring coordinate (x for rows: -1 .. W, y for columns: 0 .. H-1) of position 0
+    const int fixed = (side == 0 || side == 2) ? 0 : (row_side ? H - 1 : W - 1);   // the image row / column the sources lie in
+    // stage the FOLD_PX + 2 source pixels along the side: coordinate first - 1 + j
+    for (int j = 0; j < FOLD_PX + 2; ++j) {
+        const int s = first - 1 + j;
+        float v = 0.f;
+        if (s >= 0 && s < len) {
+            const size_t off = row_side ? split_pixel_offset(n, fixed, s, H, W) : split_pixel_offset(n, s, fixed, H, W);
+            const unsigned short hb = *reinterpret_cast<const unsigned short*>(dc + off + ci * 2);
+            const unsigned short lb = *reinterpret_cast<const unsigned short*>(dc + off + 256 + ci * 2);
+            v = __uint_as_float((uint32_t)hb << 16) + __uint_as_float((uint32_t)lb << 16);
+        }
+        sdc[j * UB_WIDTH + ci] = v;
     }
-    for (int i = 0; i < np; ++i) {
-        const unsigned short hb = *reinterpret_cast<const unsigned short*>(dc + src[i] + ci * 2);
-        const unsigned short lb = *reinterpret_cast<const unsigned short*>(dc + src[i] + 256 + ci * 2);
-        sdc[i][ci] = __uint_as_float((uint32_t)hb << 16) + __uint_as_float((uint32_t)lb << 16);
+    float acc[FOLD_PX];
+#pragma unroll
+    for (int i = 0; i < FOLD_PX; ++i) acc[i] = 0.f;
+    for (int k = -1; k <= 1; ++k) {                     // the tap offset ALONG the side; across it the offset is fixed by the side
+        // ring pixel r = source + tap  =>  across the side: top / left: -1 = 0 + tap -> tap = -1; bottom / right: tap = +1
+        const int across = (side == 0 || side == 2) ? -1 : 1;
+        const int tap = row_side ? (across + 1) * 3 + (k + 1) : (k + 1) * 3 + (across + 1);
+        __syncthreads();
+        for (int i = ci; i < UB_WIDTH * UB_WIDTH / 4; i += 128)
+            reinterpret_cast<float4*>(sW)[i] = *reinterpret_cast<const float4*>(wt + (size_t)tap * UB_WIDTH * UB_WIDTH + (size_t)i * 4);
+        __syncthreads();
+#pragma unroll 2
+        for (int c4 = 0; c4 < UB_WIDTH / 4; ++c4) {
+            const float w0 = sW[(c4 * 4 + 0) * UB_WIDTH + ci], w1 = sW[(c4 * 4 + 1) * UB_WIDTH + ci];
+            const float w2 = sW[(c4 * 4 + 2) * UB_WIDTH + ci], w3 = sW[(c4 * 4 + 3) * UB_WIDTH + ci];
+#pragma unroll
+            for (int i = 0; i < FOLD_PX; ++i) {         // ring position first + i, source coordinate first + i - k -> staged index i + 1 - k
+                const float4 d = *reinterpret_cast<const float4*>(sdc + (i + 1 - k) * UB_WIDTH + c4 * 4);
+                acc[i] = fmaf(w0, d.x, fmaf(w1, d.y, fmaf(w2, d.z, fmaf(w3, d.w, acc[i]))));
+            }
+        }
     }
-    __syncthreads();
-    float acc = 0.f;
-    for (int i = 0; i < np; ++i) {
-        const float* wt = w + (size_t)ci * 9 + taps[i];
-#pragma unroll 8
-        for (int co = 0; co < UB_WIDTH; ++co) acc = fmaf(wt[(size_t)co * UB_WIDTH * 9], sdc[i][co], acc);
+#pragma unroll
+    for (int i = 0; i < FOLD_PX; ++i) {
+        const int r = first + i;                        // ring coordinate along the side
+        if (row_side ? (r > W) : (r >= H)) continue;
+        int ty, tx;
+        if (row_side) { ty = side == 0 ? 1 : H - 2; tx = r < 0 ? 1 : (r >= W ? W - 2 : r); }
+        else { ty = r; tx = side == 2 ? 1 : W - 2; }
+        atomicAdd(&din[((size_t)n * H * W + (size_t)ty * W + tx) * UB_WIDTH + ci], acc[i]);
     }
-    atomicAdd(&din[((size_t)n * H * W + (size_t)ty * W + tx) * UB_WIDTH + ci], acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -491,8 +528,13 @@ int launch_relu_norm_bwd_apply(const float* dy, const float* c, const Coef* coef
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int launch_conv_fold(const void* dc_split, const float* w, float* din, int N, int H, int W, cudaStream_t st) {
-    conv_fold_kernel<<<dim3(2 * (W + 2) + 2 * H, N), 128, 0, st>>>(static_cast<const char*>(dc_split), w, din, H, W);
+int launch_conv_fold(const void* dc_split, const float* w, float* wt_scratch, float* din, int N, int H, int W, cudaStream_t st) {
+    conv_fold_prep_kernel<<<(9 * UB_WIDTH * UB_WIDTH + 255) / 256, 256, 0, st>>>(w, wt_scratch);
+    UB_CHECK_LAUNCH();
+    constexpr size_t smem = (size_t)(UB_WIDTH * UB_WIDTH + (FOLD_PX + 2) * UB_WIDTH) * sizeof(float);
+    UB_SET_SMEM(conv_fold_kernel, smem);
+    const int nb_row = (W + 2 + FOLD_PX - 1) / FOLD_PX, nb_col = (H + FOLD_PX - 1) / FOLD_PX;
+    conv_fold_kernel<<<dim3(2 * nb_row + 2 * nb_col, N), 128, smem, st>>>(static_cast<const char*>(dc_split), wt_scratch, din, H, W);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
