@@ -169,41 +169,90 @@ __device__ __forceinline__ float4 ld4h(const __nv_bfloat16* p) {
     const uint2 w = *reinterpret_cast<const uint2*>(p);
     return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
 }
+// Row streaming like the depthwise kernels (dwconv_rows.cu): a pixel row is ONE contiguous 1 KB (fp32) run over all 256 channels, so
+// thread 0 moves SE_ROWS rows per stage with one cp.async.bulk (TMA, mbarrier complete_tx) into a SE_STAGES-deep shared-memory ring
+// and the 256 threads only do LDS.128 + GELU: no registers held across the HBM latency, loads always SE_STAGES - 1 stages ahead.
+// The register-loop form this replaces (4 LDG.128 per thread and iteration, consumed right away) sat at 0.58 of the HBM roof with
+// long_scoreboard 54 % of the stalls (ncu r02) although its MUFU / issue floor is 0.9 ms per step against 1.3 ms of HBM time.
+constexpr int SE_ROWS = 16, SE_STAGES = 3;      // measured at B=16 (ms per step): 3 stages (4 CTAs / SM) 1.78, 4 stages 1.90, 6 stages 1.96; register loop 2.23
+__device__ __forceinline__ uint32_t se_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void se_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    const long long t0 = clock64();
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000ll) __trap();      // ~2 s: a lost bulk copy must fault, not hang the GPU
+    } while (!ok);
+}
 template <class HT>
 __global__ void __launch_bounds__(256) se_pool_kernel(const HT* __restrict__ h2, const Coef* __restrict__ coef2,
                                                        const MeanRstd* __restrict__ mr2, double* pool_stats,
                                                        double* gp_stats, int P, int chunk) {
     constexpr int C = UB_HID, Q = C / 4, ROWS = 256 / Q;
-    __shared__ __align__(16) float smem[2 * ROWS * C];
+    constexpr uint32_t ROW_BYTES = C * sizeof(HT), STAGE_BYTES = SE_ROWS * ROW_BYTES;
+    extern __shared__ __align__(128) unsigned char se_smem[];
+    HT* ring = reinterpret_cast<HT*>(se_smem);                                             // SE_STAGES x [SE_ROWS][C]
+    float* red = reinterpret_cast<float*>(se_smem);                                        // reused by the final reduction (8 KB)
+    const uint32_t bar0 = se_s32(se_smem + SE_STAGES * STAGE_BYTES);
     const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    const int nst = (p1 - p0 + SE_ROWS - 1) / SE_ROWS;
+    const HT* src = h2 + ((size_t)n * P + p0) * C;
+    auto issue = [&](int i) {                       // thread 0: stage i -> slot i % SE_STAGES
+        const uint32_t rows = (uint32_t)min(SE_ROWS, p1 - p0 - i * SE_ROWS), b = bar0 + (i % SE_STAGES) * 8;
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(b), "r"(rows * ROW_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(se_s32(ring + (size_t)(i % SE_STAGES) * SE_ROWS * C)), "l"(src + (size_t)i * SE_ROWS * C), "r"(rows * ROW_BYTES), "r"(b) : "memory");
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SE_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + i * 8), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < SE_STAGES - 1 && i < nst; ++i) issue(i);
+    }
     Coef k[4];
     MeanRstd m[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { k[i] = coef2[(size_t)n * C + c4 * 4 + i]; m[i] = mr2[(size_t)n * C + c4 * 4 + i]; }
-    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
     float s[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, gh[4] = {0, 0, 0, 0};
-    const size_t base = (size_t)n * P * C + c4 * 4;
     const bool train = gp_stats != nullptr;
-#pragma unroll 4
-    for (int p = p0 + r; p < p1; p += ROWS) {
-        const float4 v = ld4h(h2 + base + (size_t)p * C);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+    __syncthreads();                                // barrier initialisation visible to every waiter
+    for (int i = 0; i < nst; ++i) {
+        // slot (i - 1) % SE_STAGES was drained by every thread before the barrier that ended iteration i - 1
+        if (threadIdx.x == 0 && i + SE_STAGES - 1 < nst) issue(i + SE_STAGES - 1);
+        se_mbar_wait(bar0 + (i % SE_STAGES) * 8, (uint32_t)(i / SE_STAGES) & 1u);
+        const HT* st = ring + (size_t)(i % SE_STAGES) * SE_ROWS * C + c4 * 4;
+        const int rows = min(SE_ROWS, p1 - p0 - i * SE_ROWS);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float z = fmaf(vv[i], k[i].scale, k[i].shift);
-            float gz, gp;
-            gelu_both(z, gz, gp);
-            s[i] += gz;
-            if (train) {
-                g[i] += gp;
-                gh[i] += gp * (vv[i] - m[i].mean) * m[i].rstd;
+        for (int j = 0; j < SE_ROWS / ROWS; ++j) {
+            const int row = r + j * ROWS;
+            if (row < rows) {
+                const float4 v = ld4h(st + row * C);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e += 2) {    // packed (f32x2) GELU + derivative: 21 issue slots per channel pair
+                    const float z0 = fmaf(vv[e], k[e].scale, k[e].shift), z1 = fmaf(vv[e + 1], k[e + 1].scale, k[e + 1].shift);
+                    float gz0, gz1, gp0, gp1;
+                    if (train) {
+                        gelu_pair<true, true>(z0, z1, gz0, gz1, gp0, gp1);
+                        g[e] += gp0;
+                        g[e + 1] += gp1;
+                        gh[e] = fmaf(gp0, (vv[e] - m[e].mean) * m[e].rstd, gh[e]);
+                        gh[e + 1] = fmaf(gp1, (vv[e + 1] - m[e + 1].mean) * m[e + 1].rstd, gh[e + 1]);
+                    } else {
+                        gelu_val_pair(z0, z1, gz0, gz1);
+                    }
+                    s[e] += gz0;
+                    s[e + 1] += gz1;
+                }
             }
         }
+        __syncthreads();                            // every thread is done with this slot: thread 0 may refill it next iteration
     }
-    block_reduce_cols2<C>(make_float4(s[0], s[1], s[2], s[3]), make_float4(0, 0, 0, 0), pool_stats + (size_t)n * C * 2, smem);
+    block_reduce_cols2<C>(make_float4(s[0], s[1], s[2], s[3]), make_float4(0, 0, 0, 0), pool_stats + (size_t)n * C * 2, red);
     if (train)
         block_reduce_cols2<C>(make_float4(g[0], g[1], g[2], g[3]), make_float4(gh[0], gh[1], gh[2], gh[3]),
-                              gp_stats + (size_t)n * C * 2, smem);
+                              gp_stats + (size_t)n * C * 2, red);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -483,16 +532,43 @@ int launch_residual_fwd(const float* x, const float* y, const Coef* coef3, float
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
-int launch_se_pool(const void* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
-                   int P, int hbf, cudaStream_t st) {
-    const int chunk = chunk_for(P);
-    if (hbf)
-        se_pool_kernel<__nv_bfloat16><<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), coef2, mr2, pool_stats,
-                                                                                       gp_stats, P, chunk);
-    else
-        se_pool_kernel<float><<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(static_cast<const float*>(h2), coef2, mr2, pool_stats, gp_stats, P, chunk);
+// CTAs per frame such that the whole grid is (just under) a whole number of waves of the resident CTAs: the pass is bound by its
+// instruction stream, not by HBM alone, so a ragged last wave costs its full share (1024 CTAs on 592 slots ran 2 waves for 1.73)
+static int se_pool_ctas_per_frame(int N, int P, int slots) {
+    if (P < 4096) return (P + 255) / 256;
+    const long long rows = (long long)N * P;
+    int w = 1;
+    while (rows / ((long long)slots * w) > 2048) ++w;       // at most ~2048 rows per CTA
+    int g = (int)(((long long)slots * w) / N);
+    if (g < 1) g = 1;
+    if (g > P / SE_ROWS) g = P / SE_ROWS;
+    return g;
+}
+template <class HT>
+static int launch_se_pool_t(const void* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N, int P,
+                            cudaStream_t st) {
+    constexpr size_t smem = (size_t)SE_STAGES * SE_ROWS * UB_HID * sizeof(HT) + SE_STAGES * 8;
+    static_assert(smem >= 2 * (256 / (UB_HID / 4)) * UB_HID * sizeof(float), "the ring doubles as the reduction scratch");
+    auto kern = se_pool_kernel<HT>;
+    UB_SET_SMEM(kern, smem);
+    static int occ_cache[64] = {0};
+    int dev = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return UB_ERR_CUDA;
+    if (dev >= 0 && dev < 64 && occ_cache[dev] > 0) occ = occ_cache[dev];
+    else {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+        if (dev >= 0 && dev < 64) occ_cache[dev] = occ;
+    }
+    const int g = se_pool_ctas_per_frame(N, P, device_sm_count() * occ);
+    const int chunk = ((P + g - 1) / g + SE_ROWS - 1) / SE_ROWS * SE_ROWS;
+    kern<<<dim3((P + chunk - 1) / chunk, N), 256, smem, st>>>(static_cast<const HT*>(h2), coef2, mr2, pool_stats, gp_stats, P, chunk);
     UB_CHECK_LAUNCH();
     return UB_OK;
+}
+int launch_se_pool(const void* h2, const Coef* coef2, const MeanRstd* mr2, double* pool_stats, double* gp_stats, int N,
+                   int P, int hbf, cudaStream_t st) {
+    return hbf ? launch_se_pool_t<__nv_bfloat16>(h2, coef2, mr2, pool_stats, gp_stats, N, P, st)
+               : launch_se_pool_t<float>(h2, coef2, mr2, pool_stats, gp_stats, N, P, st);
 }
 int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, double* bstats, int N, int P,
                           cudaStream_t st) {
