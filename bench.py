@@ -112,7 +112,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in open(self.path):
             f = [t.strip() for t in ln.split(",")]
@@ -122,13 +122,27 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         os.unlink(self.path)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        if pw:      # board power under load beside its enforced limit: with sw_power_cap active the step is power-, not cycle-limited
+            out.update(power_w=statistics.median(pw), power_limit_w=self.power_limit())
         return out
+
+    def power_limit(self):
+        try:
+            r = subprocess.run(["nvidia-smi", "--query-gpu=enforced.power.limit", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                               capture_output=True, text=True, timeout=10)
+            return float(r.stdout.strip().splitlines()[0])
+        except Exception:
+            return None
 
 
 # algorithmic HBM bytes per frame of one launch, in units of (A, Hh): A = 128 ch, Hh = 256 ch per pixel (fp32)
@@ -158,7 +172,7 @@ def survey_bytes_per_sample(T, covdim, P, n_dec=5, hid_bytes=4):
 NCU_NAME = {"dwconv_bwd": "dwrows_bwd2_kernel", "dwconv_fwd": "dwrows_fwd_kernel", "gemm1_fwd": "gemm_tc_kernel<128, 256, TLoadNormed",
             "gemm2_fwd": "gemm_tc_kernel<256, 128, TLoadGeluGate", "gemm2_bwd": "gemm_tc_kernel<128, 256, TLoadNormBwd",
             "wgrad2": "wgrad_tc_kernel<TLoadNormBwd", "wgrad1": "wgrad_tc_kernel<TLoadNormed", "se_pool": "se_pool_kernel",
-            "gemm1_bwd": "bwd_tc_kernel<1", "residual_bwd": "residual_bwd_kernel", "residual_fwd": "residual_fwd_kernel",
+            "gemm1_bwd": "bwd_tc_kernel<", "residual_bwd": "residual_bwd_kernel", "residual_fwd": "residual_fwd_kernel",
             "norm_bwd_stats": "norm_bwd_stats_kernel"}
 
 
