@@ -599,15 +599,21 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
         bulk_g2s(dst, reinterpret_cast<const char*>(wimg) + (size_t)kb * SLAB, SLAB, bar);
         bulk_g2s(dst + SLAB, reinterpret_cast<const char*>(wimg) + (size_t)W_HALF + (size_t)kb * SLAB, SLAB, bar);
     };
-    if constexpr (!WSTREAM) {
-        for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
-    }
     al.fill(n, K, sCf);
     if (tid == 0) {
         for (int i = 0; i < NSTAGE + 2 + WRING; ++i) mbar_init(smem_u32(&sBar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if constexpr (WSTREAM) {
             for (int a = 0; a < WAHEAD && a < Q; ++a) w_issue(a);
+        } else if (Q > 0) {
+            // resident weight image (128 KB): ONE thread hands it to the TMA engine (eight 16 KB bulk copies onto the first weight
+            // barrier) instead of 16 LDG.128 + 16 STS.128 per thread; it lands while the CTA sets up and the first operand loads are in
+            // flight, and only the MMA issuer waits for it.  With 4 ... 12 CTAs per SM and launch the prologue is paid that often.
+            const uint32_t bar = smem_u32(&sBar[NSTAGE + 2]);
+            mbar_expect_tx(bar, W_BYTES);
+#pragma unroll
+            for (int c = 0; c < W_BYTES / 16384; ++c)
+                bulk_g2s(smem_u32(sW) + c * 16384, reinterpret_cast<const char*>(wimg) + (size_t)c * 16384, 16384, bar);
         }
     }
     if (warp == 0) {
@@ -706,6 +712,7 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
             tc_fence_after();
             const uint32_t acc = (uint32_t)(it & 1) * ACC_COLS;
             if constexpr (WSTREAM) mbar_wait(smem_u32(&sBar[NSTAGE + 2 + q % WRING]), (uint32_t)(q / WRING) & 1);   // slab pair landed
+            else if (q == 0) mbar_wait(smem_u32(&sBar[NSTAGE + 2]), 0);                                              // weight image landed
             const uint32_t a_hi = WSTREAM ? smem_u32(sW) + (uint32_t)(q % WRING) * 2 * SLAB : smem_u32(sW) + kb * SLAB;
             const uint32_t a_lo = a_hi + (WSTREAM ? SLAB : W_HALF);
             const uint32_t b_hi = smem_u32(hi), b_lo = smem_u32(lo);
