@@ -668,6 +668,9 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
         tc_fence_before();
     };
 
+    // (Alternating two raw register sets statically, as wgrad_tc_body does, was measured here too: it removes the 16 ... 32 register
+    // moves of `cur = raw` per step, but the twice-unrolled step body ran slower -- gemm2_fwd 3.41 -> 3.65, gemm1_fwd 2.36 -> 2.77,
+    // gemm2_bwd 4.90 -> 5.92 ms per step with 108 bytes of spills at its 128-register cap.)
     for (int q = 0; q < Q; ++q) {
         const int it = q / KB, kb = q % KB;               // local tile, K-block
         typename ALoad::Raw cur[2] = {raw[0], raw[1]};
@@ -841,8 +844,11 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
     const long long H = (t1 > t0 ? (t1 - t0) : 0) * 2;     // pipeline steps: half tiles of 32 pixel rows
     // producer role per half tile: one A item (row ra, chunk ca) and two B items (rows rb, rb+16; chunk cb)
     const int ra = tid / 16, ca = tid % 16, rb = tid / 32, cb = tid % 32;
-    typename LA::Raw rawa;
-    typename LB::Raw rawb[2];
+    // Two raw register sets, alternating STATICALLY (the half-step loop is unrolled by two): while one set is converted the other receives
+    // the next half tile's loads.  One set plus a per-step copy cost 33 register moves per thread and tile across the loop back-edge
+    // (7 % of the instruction stream in the ncu source view); measured 5.06 -> 4.46 ms per step.
+    typename LA::Raw rawa, rawa2;
+    typename LB::Raw rawb[2], rawb2[2];
     if (H > 0) {
         const size_t row0 = (size_t)t0 * WG_PX;
         la.issue(row0 + ra, 128, ca * 8, rawa);
@@ -864,7 +870,8 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
     const uint32_t tmem_base = *sTmem;
 
     int cur_n = -1;
-    for (long long h = 0; h < H; ++h) {
+    auto hstep = [&](const long long h, const typename LA::Raw& ca_raw, const typename LB::Raw (&cb_raw)[2], typename LA::Raw& na_raw,
+                     typename LB::Raw (&nb_raw)[2]) {
         const long long t = t0 + (h >> 1);
         const int half = (int)(h & 1);
         const uint32_t use = (uint32_t)(h >> 1);
@@ -876,13 +883,11 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
             cur_n = n;
             __syncthreads();
         }
-        const typename LA::Raw ca_raw = rawa;
-        const typename LB::Raw cb_raw[2] = {rawb[0], rawb[1]};
-        if (h + 1 < H) {                        // prefetch the next half tile
+        if (h + 1 < H) {                        // prefetch the next half tile into the other register set
             const size_t nrow0 = (size_t)(t0 + ((h + 1) >> 1)) * WG_PX + (size_t)((h + 1) & 1) * 32;
-            la.issue(nrow0 + ra, 128, ca * 8, rawa);
-            lb.issue(nrow0 + rb, 256, cb * 8, rawb[0]);
-            lb.issue(nrow0 + rb + 16, 256, cb * 8, rawb[1]);
+            la.issue(nrow0 + ra, 128, ca * 8, na_raw);
+            lb.issue(nrow0 + rb, 256, cb * 8, nb_raw[0]);
+            lb.issue(nrow0 + rb + 16, 256, cb * 8, nb_raw[1]);
         }
         const uint32_t slot = use & 1, u = use >> 1;
         if (half == 0) mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);
@@ -925,6 +930,10 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
                 if (h == H - 1) tc_commit(smem_u32(&sBar[2]));
             }
         }
+    };
+    for (long long h = 0; h < H; h += 2) {          // H = 2 x tiles: half 0 consumes set 1, half 1 set 2
+        hstep(h, rawa, rawb, rawa2, rawb2);
+        hstep(h + 1, rawa2, rawb2, rawa, rawb);
     }
     if (H > 0) {
         mbar_wait(smem_u32(&sBar[2]), 0);
