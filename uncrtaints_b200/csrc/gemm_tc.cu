@@ -841,7 +841,11 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
     const int tiles_per_frame = P / WG_PX;
-    const long long H = (t1 > t0 ? (t1 - t0) : 0) * 2;     // pipeline steps: half tiles of 32 pixel rows
+    // 32-bit step counter and an incrementally tracked frame index: `frame = tile / tiles_per_frame` on 64-bit indices was an emulated
+    // division in every half step (see bwd_tc_kernel)
+    const int H = (int)(t1 > t0 ? (t1 - t0) : 0) * 2;      // pipeline steps: half tiles of 32 pixel rows
+    const int frame0 = (int)(t0 / tiles_per_frame), first_boundary = 2 * (int)((long long)(frame0 + 1) * tiles_per_frame - t0);
+    int ld_next = frame0, ld_boundary = 0;                 // the frame changes at half-step index ld_boundary
     // producer role per half tile: one A item (row ra, chunk ca) and two B items (rows rb, rb+16; chunk cb)
     const int ra = tid / 16, ca = tid % 16, rb = tid / 32, cb = tid % 32;
     // Two raw register sets, alternating STATICALLY (the half-step loop is unrolled by two): while one set is converted the other receives
@@ -869,18 +873,17 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
 
-    int cur_n = -1;
-    auto hstep = [&](const long long h, const typename LA::Raw& ca_raw, const typename LB::Raw (&cb_raw)[2], typename LA::Raw& na_raw,
+    auto hstep = [&](const int h, const typename LA::Raw& ca_raw, const typename LB::Raw (&cb_raw)[2], typename LA::Raw& na_raw,
                      typename LB::Raw (&nb_raw)[2]) {
-        const long long t = t0 + (h >> 1);
-        const int half = (int)(h & 1);
+        const int half = h & 1;
         const uint32_t use = (uint32_t)(h >> 1);
-        const int n = (int)(t / tiles_per_frame);
-        if (n != cur_n) {                       // block-uniform: refill the per-frame coefficients
+        if (h == ld_boundary) {                 // block-uniform: refill the per-frame coefficients
+            const int n = ld_next;
+            ld_next = n + 1;
+            ld_boundary = n == frame0 ? first_boundary : ld_boundary + 2 * tiles_per_frame;
             __syncthreads();
             la.fill(n, 128, sCfA);
             lb.fill(n, 256, sCfB);
-            cur_n = n;
             __syncthreads();
         }
         if (h + 1 < H) {                        // prefetch the next half tile into the other register set
@@ -931,7 +934,7 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
             }
         }
     };
-    for (long long h = 0; h < H; h += 2) {          // H = 2 x tiles: half 0 consumes set 1, half 1 set 2
+    for (int h = 0; h < H; h += 2) {                // H = 2 x tiles: half 0 consumes set 1, half 1 set 2
         hstep(h, rawa, rawb, rawa2, rawb2);
         hstep(h + 1, rawa2, rawb2, rawa, rawb);
     }
@@ -1042,11 +1045,15 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                    bDone = smem_u32(&sBar[FRING + 3]);
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
-    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const long long t0 = (long long)blockIdx.x * per, t1 = min(t0 + per, total_tiles);
-    const int ntiles = t1 > t0 ? (int)(t1 - t0) : 0;
+    // Tile indices are 32-bit and the frame of a tile is tracked INCREMENTALLY (one counter pair for the loader, one for the epilogue, which
+    // runs a tile behind): `frame = tile / tiles_per_frame` on 64-bit indices was an emulated division (~80 instructions, I2F + loop)
+    // three times per tile -- a fifth of this kernel's instruction stream in the ncu source view.
+    const int per = (int)((total_tiles + gridDim.x - 1) / gridDim.x);
+    const int t0 = (int)blockIdx.x * per, t1 = (int)min((long long)t0 + per, total_tiles);
+    const int ntiles = t1 > t0 ? t1 - t0 : 0;
     const int tiles_per_frame = P / FPX;
     const int Q = ntiles * 4;                                 // pipeline steps: (tile, 64-channel block of S)
+    const int frame0 = t0 / tiles_per_frame, first_boundary = (frame0 + 1) * tiles_per_frame - t0;      // local index of the first tile of frame0 + 1
     float* dst = partial + (size_t)blockIdx.x * UB_WIDTH * UB_HID;
     if (Q == 0) {
         for (int i = tid; i < UB_WIDTH * UB_HID; i += THREADS) dst[i] = 0.f;
@@ -1086,7 +1093,7 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
     const int lq = warp % 4, pc = warp / 4;
     typename Epi::State est[MH];
     float stat[MH][Epi::NS];
-    int epi_n = -1;
+    int epi_n = -1, epi_next = frame0, epi_boundary = 0;      // frame of the next epilogue tile changes at local tile index epi_boundary
     auto flush_stats = [&]() {
         if (epi_n < 0) return;
         double* d = ep.dst(epi_n, NOUT);
@@ -1096,9 +1103,11 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
             for (int s = 0; s < Epi::NS; ++s) atomicAdd(&d[(size_t)(j * 128 + lq * 32 + lane) * Epi::NS + s], (double)stat[j][s]);
     };
     auto epilogue_part = [&](int e, int part) {              // local tile e, slice `part`: TMEM -> registers -> global (+ statistics)
-        const long long t = t0 + e;
-        const int n = (int)(t / tiles_per_frame);
-        if (n != epi_n) {                                     // the epilogue's tile entered a new frame (thread-local bookkeeping)
+        const int t = t0 + e;
+        if (part == 0 && e == epi_boundary) {                 // the epilogue's tile entered a new frame (thread-local bookkeeping)
+            const int n = epi_next;
+            epi_next = n + 1;
+            epi_boundary = n == frame0 ? first_boundary : epi_boundary + tiles_per_frame;
             flush_stats();
             epi_n = n;
 #pragma unroll
@@ -1120,19 +1129,17 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         tc_fence_before();
     };
 
-    int cur_n = -1;
+    int ld_next = frame0, ld_boundary = 0;                    // frame of the loader's tile changes at local tile index ld_boundary
     auto step = [&](const int q, typename LS::Raw& sraw) {
         const int it = q >> 2, blk = q & 3;
-        const long long t = t0 + it;
-        if (blk == 0) {
-            const int n = (int)(t / tiles_per_frame);
-            if (n != cur_n) {                                 // block-uniform: per-frame coefficient tables of the loaders
-                __syncthreads();
-                ls.fill(n, UB_HID, sCfS);
-                lr.fill(n, UB_WIDTH, sCfR);
-                cur_n = n;
-                __syncthreads();
-            }
+        if (blk == 0 && it == ld_boundary) {                  // block-uniform: per-frame coefficient tables of the loaders
+            const int n = ld_next;
+            ld_next = n + 1;
+            ld_boundary = n == frame0 ? first_boundary : ld_boundary + tiles_per_frame;
+            __syncthreads();
+            ls.fill(n, UB_HID, sCfS);
+            lr.fill(n, UB_WIDTH, sCfR);
+            __syncthreads();
         }
         const typename LS::Raw curs = sraw;
         const typename LR::Raw curr[2] = {rawr[0], rawr[1]};
