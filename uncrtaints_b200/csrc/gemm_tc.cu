@@ -258,6 +258,7 @@ struct TLoadNormed {           // a = x*scale + shift
         for (int k = threadIdx.x; k < K; k += THREADS) { const Coef c = coef[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.scale; cf[K + q] = c.shift; }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8(x + row * K + ch0, r.a); }
+    __device__ void issue_off(size_t off, Raw& r) const { ld8(x + off, r.a); }                  // off = row * K + ch0
     struct Cf { float sc[8], sh[8]; };
     __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const { lds8(cf, K, ch0, c.sc); lds8(cf + K, K, ch0, c.sh); }
     __device__ void finish(const Raw& r, const Cf& c, float (&v)[8]) const {
@@ -302,6 +303,7 @@ struct TLoadNormBwdT {         // a = ca*dy + cb*v + cc
         for (int k = threadIdx.x; k < K; k += THREADS) { const BCoef c = bc[(size_t)n * K + k]; const int q = cf_pos(k, K); cf[q] = c.a; cf[K + q] = c.b; cf[2 * K + q] = c.c; }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8_raw(dy + row * K + ch0, r.a); ld8_raw(vv + row * K + ch0, r.b); }
+    __device__ void issue_off(size_t off, Raw& r) const { ld8_raw(dy + off, r.a); ld8_raw(vv + off, r.b); }      // off = row * K + ch0
     struct Cf { float ca[8], cb[8], cc[8]; };
     __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const {
         lds8(cf, K, ch0, c.ca); lds8(cf + K, K, ch0, c.cb); lds8(cf + 2 * K, K, ch0, c.cc);
@@ -1066,12 +1068,16 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
     const int sr = tid / 8, sc = tid % 8, rr = tid / 16, rc = tid % 16;
     typename LS::Raw raws[2];
     typename LR::Raw rawr[2];
+    // element offsets of this thread's NEXT prefetch, advanced by constants (the addresses used to be rebuilt from the tile index in
+    // every step: ~30 integer instructions of 64-bit arithmetic per thread and step)
+    size_t soff = ((size_t)t0 * FPX + sr) * UB_HID + sc * 8, roff = ((size_t)t0 * FPX + rr) * UB_WIDTH + rc * 8;
     {
-        const size_t row0 = (size_t)t0 * FPX;
-        ls.issue(row0 + sr, UB_HID, sc * 8, raws[0]);
-        ls.issue(row0 + sr, UB_HID, 64 + sc * 8, raws[1]);
-        lr.issue(row0 + rr, UB_WIDTH, rc * 8, rawr[0]);
-        lr.issue(row0 + rr + 32, UB_WIDTH, rc * 8, rawr[1]);
+        ls.issue_off(soff, raws[0]);
+        ls.issue_off(soff + 64, raws[1]);
+        lr.issue_off(roff, rawr[0]);
+        lr.issue_off(roff + 32 * UB_WIDTH, rawr[1]);
+        soff += 128;                                          // step 2: block 2 of the first tile
+        roff += (size_t)FPX * UB_WIDTH;                       // next tile
     }
     // ---- one-time setup: weights, barriers, TMEM ----
     for (int i = tid; i < F_W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wimg[i];
@@ -1147,7 +1153,17 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         mbar_wait_guard(bRing + slot * 8, (use & 1) ^ 1);              // MMAs that read this ring slot are done
         char* s_hi = sS + slot * 2 * FBLK;
         char* s_lo = s_hi + FBLK;
+        {
+            typename LS::Cf cfs;
+            ls.coefs(UB_HID, blk * 64 + sc * 8, sCfS, cfs);
+            float v[8];
+            ls.finish(curs, cfs, v);
+            const int off = sr * 128 + ((sc ^ (sr & 7)) << 4);
+            split_store8(v, s_hi + off, s_lo + off, single);
+        }
         if (blk == 0) {
+            // R after S: the previous tile's last MMAs (issued a moment ago) still read R; converting the S block first gives them time
+            // (the wait used to be polled ~11 times per tile by every warp: ncu source view)
             mbar_wait_guard(bRfree, ((uint32_t)it & 1) ^ 1);           // the previous tile's MMAs no longer read R
             typename LR::Cf cfr;
             lr.coefs(UB_WIDTH, rc * 8, sCfR, cfr);
@@ -1159,14 +1175,6 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                 const int off = (rc / 8) * FBLK + r * 128 + (((rc % 8) ^ (r & 7)) << 4);
                 split_store8(v, sR + off, sR + 2 * FBLK + off, single);
             }
-        }
-        {
-            typename LS::Cf cfs;
-            ls.coefs(UB_HID, blk * 64 + sc * 8, sCfS, cfs);
-            float v[8];
-            ls.finish(curs, cfs, v);
-            const int off = sr * 128 + ((sc ^ (sr & 7)) << 4);
-            split_store8(v, s_hi + off, s_lo + off, single);
         }
         fence_proxy_async();
         __syncthreads();
@@ -1206,12 +1214,13 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
         // loads issued at the top of the step were complete when the step ended -- in flight for the convert only; issued here they stay
         // in flight across the epilogue slice and the next step (measured 7.6 -> 7.3 ms per step at B=16).
         if (q + 2 < Q) {
-            const int nit = (q + 2) >> 2, nblk = (q + 2) & 3;
-            const size_t nrow0 = (size_t)(t0 + nit) * FPX;
-            ls.issue(nrow0 + sr, UB_HID, nblk * 64 + sc * 8, sraw);
+            const int nblk = (q + 2) & 3;
+            ls.issue_off(soff, sraw);
+            soff += nblk == 3 ? (size_t)FPX * UB_HID - 192 : 64;      // next block, or block 0 of the next tile
             if (nblk == 0) {                                  // blk == 2: this tile's R was consumed two steps ago
-                lr.issue(nrow0 + rr, UB_WIDTH, rc * 8, rawr[0]);
-                lr.issue(nrow0 + rr + 32, UB_WIDTH, rc * 8, rawr[1]);
+                lr.issue_off(roff, rawr[0]);
+                lr.issue_off(roff + 32 * UB_WIDTH, rawr[1]);
+                roff += (size_t)FPX * UB_WIDTH;
             }
         }
         // a slice of the previous tile's epilogue while this step's MMAs run; the slice after the last block also covers the
