@@ -229,6 +229,10 @@ template <class L> struct IsPresplit<L, decltype((void)L::PRESPLIT)> { static co
 // output pixel).  It changes once per tile while issue() runs once per K-block (18 times per tile for the 3x3 convolution), and
 // the producer warps are bound by the latency of their own instruction stream (ncu r02, conv kernel: 250 instructions per thread
 // and K-block, 10.7 cycles per issued instruction at four warps per scheduler), so the divisions are hoisted out of the K loop.
+// loaders of a plain row-major [rows][K] tensor offer issue_off(row * K + ch0, raw): the persistent kernels advance that offset by
+// constants instead of rebuilding the address from the tile index in every step
+template <class L, class = void> struct HasIssueOff { static constexpr bool v = false; };
+template <class L> struct HasIssueOff<L, decltype((void)&L::issue_off)> { static constexpr bool v = true; };
 template <class L, class = void> struct PosOf { struct type { size_t row; }; };
 template <class L> struct PosOf<L, decltype((void)sizeof(typename L::Pos))> { typedef typename L::Pos type; };
 template <class L>
@@ -278,6 +282,7 @@ struct TLoadGeluGateT {        // a = gelu(h2*scale + shift) * gate
         }
     }
     __device__ void issue(size_t row, int K, int ch0, Raw& r) const { ld8_raw(h2 + row * K + ch0, r); }
+    __device__ void issue_off(size_t off, Raw& r) const { ld8_raw(h2 + off, r); }                 // off = row * K + ch0
     struct Cf { float sc[8], sh[8], g[8]; };
     __device__ void coefs(int K, int ch0, const float* cf, Cf& c) const {
         lds8(cf, K, ch0, c.sc); lds8(cf + K, K, ch0, c.sh); lds8(cf + 2 * K, K, ch0, c.g);
@@ -585,11 +590,16 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
             locate_row(al, row0 + pr + 64, pos[1]);
             issue_row(al, pos[0], K, pc8 * 8, raw[0]);
             issue_row(al, pos[1], K, pc8 * 8, raw[1]);
+        } else if constexpr (HasIssueOff<ALoad>::v) {
+            al.issue_off((row0 + pr) * K + pc8 * 8, raw[0]);
+            al.issue_off((row0 + pr + 64) * K + pc8 * 8, raw[1]);
         } else {
             al.issue(row0 + pr, K, pc8 * 8, raw[0]);
             al.issue(row0 + pr + 64, K, pc8 * 8, raw[1]);
         }
     }
+    // element offset of this thread's next prefetch (step 1), advanced by constants: + one K-block, or to block 0 of the next tile
+    size_t poff = ((size_t)n * P + (size_t)t0 * TILE_PX + pr) * K + pc8 * 8 + KBLK;
 
     // ---- one-time setup: weights, coefficients, barriers, TMEM ----
     // (thread 0 only) slab pair of pipeline step qq -> weight ring slot qq % WRING.  The slot was last read by the MMAs of step
@@ -686,6 +696,10 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
                 }
                 issue_row(al, pos[0], K, nkb * KBLK + pc8 * 8, raw[0]);
                 issue_row(al, pos[1], K, nkb * KBLK + pc8 * 8, raw[1]);
+            } else if constexpr (HasIssueOff<ALoad>::v) {
+                al.issue_off(poff, raw[0]);
+                al.issue_off(poff + (size_t)64 * K, raw[1]);
+                poff += nkb == KB - 1 ? (size_t)TILE_PX * K - (KB - 1) * KBLK : KBLK;
             } else {
                 al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
                 al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
@@ -855,11 +869,21 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
     // (7 % of the instruction stream in the ncu source view); measured 5.06 -> 4.46 ms per step.
     typename LA::Raw rawa, rawa2;
     typename LB::Raw rawb[2], rawb2[2];
+    constexpr bool LINEAR = HasIssueOff<LA>::v && HasIssueOff<LB>::v;
+    size_t aoff = ((size_t)t0 * WG_PX + ra) * 128 + ca * 8, boff = ((size_t)t0 * WG_PX + rb) * 256 + cb * 8;      // next prefetch (LINEAR)
     if (H > 0) {
         const size_t row0 = (size_t)t0 * WG_PX;
-        la.issue(row0 + ra, 128, ca * 8, rawa);
-        lb.issue(row0 + rb, 256, cb * 8, rawb[0]);
-        lb.issue(row0 + rb + 16, 256, cb * 8, rawb[1]);
+        if constexpr (LINEAR) {
+            la.issue_off(aoff, rawa);
+            lb.issue_off(boff, rawb[0]);
+            lb.issue_off(boff + 16 * 256, rawb[1]);
+            aoff += 32 * 128;                           // every half step is the next 32 pixel rows
+            boff += 32 * 256;
+        } else {
+            la.issue(row0 + ra, 128, ca * 8, rawa);
+            lb.issue(row0 + rb, 256, cb * 8, rawb[0]);
+            lb.issue(row0 + rb + 16, 256, cb * 8, rawb[1]);
+        }
     }
 
     if (tid == 0) {
@@ -889,10 +913,18 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
             __syncthreads();
         }
         if (h + 1 < H) {                        // prefetch the next half tile into the other register set
-            const size_t nrow0 = (size_t)(t0 + ((h + 1) >> 1)) * WG_PX + (size_t)((h + 1) & 1) * 32;
-            la.issue(nrow0 + ra, 128, ca * 8, na_raw);
-            lb.issue(nrow0 + rb, 256, cb * 8, nb_raw[0]);
-            lb.issue(nrow0 + rb + 16, 256, cb * 8, nb_raw[1]);
+            if constexpr (LINEAR) {
+                la.issue_off(aoff, na_raw);
+                lb.issue_off(boff, nb_raw[0]);
+                lb.issue_off(boff + 16 * 256, nb_raw[1]);
+                aoff += 32 * 128;
+                boff += 32 * 256;
+            } else {
+                const size_t nrow0 = (size_t)(t0 + ((h + 1) >> 1)) * WG_PX + (size_t)((h + 1) & 1) * 32;
+                la.issue(nrow0 + ra, 128, ca * 8, na_raw);
+                lb.issue(nrow0 + rb, 256, cb * 8, nb_raw[0]);
+                lb.issue(nrow0 + rb + 16, 256, cb * 8, nb_raw[1]);
+            }
         }
         const uint32_t slot = use & 1, u = use >> 1;
         if (half == 0) mbar_wait(smem_u32(&sBar[slot]), (u & 1) ^ 1);
