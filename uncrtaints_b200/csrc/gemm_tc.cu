@@ -535,12 +535,24 @@ struct TEpiGemm1Bwd {          // dn0 = acc; sums (dn0, dn0*x_hat)
     __device__ void init(int n, int NOUT, int ch, State& st) const { st.m = mr0[(size_t)n * NOUT + ch]; }
     template <int NPX>
     __device__ void apply(const State& st, size_t row0, int NOUT, int ch, const float* v, float* s) const {
+        float xv[NPX];
+        preload<NPX>(row0, NOUT, ch, xv);
+        apply_pre<NPX>(st, row0, NOUT, ch, v, xv, s);
+    }
+    // the slice's loads of x, issued by the fused kernel BEFORE it waits for the accumulator and reads TMEM (their latency overlaps
+    // both), and in any case before the slice's stores instead of alternating with them
+    template <int NPX>
+    __device__ void preload(size_t row0, int NOUT, int ch, float* xv) const {
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) xv[i] = __ldg(x + (row0 + i) * NOUT + ch);
+    }
+    template <int NPX>
+    __device__ void apply_pre(const State& st, size_t row0, int NOUT, int ch, const float* v, const float* xv, float* s) const {
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
-            const size_t o = (row0 + i) * NOUT + ch;
-            dn0[o] = v[i];
+            dn0[(row0 + i) * NOUT + ch] = v[i];
             s[0] += v[i];
-            s[1] = fmaf(v[i], (x[o] - st.m.mean) * st.m.rstd, s[1]);
+            s[1] = fmaf(v[i], (xv[i] - st.m.mean) * st.m.rstd, s[1]);
         }
     }
     __device__ double* dst(int n, int NOUT) const { return bstats + (size_t)n * NOUT * NS; }
@@ -697,9 +709,7 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
                 issue_row(al, pos[0], K, nkb * KBLK + pc8 * 8, raw[0]);
                 issue_row(al, pos[1], K, nkb * KBLK + pc8 * 8, raw[1]);
             } else if constexpr (HasIssueOff<ALoad>::v) {
-                al.issue_off(poff, raw[0]);
-                al.issue_off(poff + (size_t)64 * K, raw[1]);
-                poff += nkb == KB - 1 ? (size_t)TILE_PX * K - (KB - 1) * KBLK : KBLK;
+                al.issue_off(poff, raw[0]);                   // the second row's loads follow the first row's convert (see below)
             } else {
                 al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
                 al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
@@ -723,6 +733,14 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
                 const int r = pr + 64 * j;
                 const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
                 convert_store(al, cur[j], cfr, hi + off, lo + off, single);
+                if constexpr (!IsPresplit<ALoad>::v && HasIssueOff<ALoad>::v) {
+                    // the step's prefetch is spread over it: up to eight LDG.128 back to back filled the LSU queue (lg_throttle) and
+                    // held up the converts behind them (measured in wgrad_tc_kernel: 4.34 -> 4.20 ms per step)
+                    if (j == 0 && q + 1 < Q) {
+                        al.issue_off(poff + (size_t)64 * K, raw[1]);
+                        poff += (q + 1) % KB == KB - 1 ? (size_t)TILE_PX * K - (KB - 1) * KBLK : KBLK;
+                    }
+                }
             }
         }
         fence_proxy_async();
@@ -914,11 +932,10 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
         }
         if (h + 1 < H) {                        // prefetch the next half tile into the other register set
             if constexpr (LINEAR) {
+                // the eight LDG.128 of a half step are spread over it (A here, B[0] after the A convert, B[1] after the first B convert):
+                // issued back to back they filled the LSU queue (lg_throttle 20 % of the stalls) and held up the converts behind them
                 la.issue_off(aoff, na_raw);
-                lb.issue_off(boff, nb_raw[0]);
-                lb.issue_off(boff + 16 * 256, nb_raw[1]);
                 aoff += 32 * 128;
-                boff += 32 * 256;
             } else {
                 const size_t nrow0 = (size_t)(t0 + ((h + 1) >> 1)) * WG_PX + (size_t)((h + 1) & 1) * 32;
                 la.issue(nrow0 + ra, 128, ca * 8, na_raw);
@@ -939,6 +956,9 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
             const int off = (ca / 8) * WG_BLK + r * 128 + (((ca % 8) ^ (r & 7)) << 4);
             convert_store(la, ca_raw, cfa, a_hi + off, a_lo + off, single);
         }
+        if constexpr (LINEAR) {
+            if (h + 1 < H) lb.issue_off(boff, nb_raw[0]);
+        }
         typename LB::Cf cfb;                              // both B rows of this thread share the channel chunk
         lb.coefs(256, cb * 8, sCfB, cfb);
 #pragma unroll
@@ -946,6 +966,9 @@ __device__ __forceinline__ void wgrad_tc_body(const LA& la, const LB& lb, float*
             const int r = half * 32 + rb + 16 * j;
             const int off = (cb / 8) * WG_BLK + r * 128 + (((cb % 8) ^ (r & 7)) << 4);
             convert_store(lb, cb_raw[j], cfb, b_hi + off, b_lo + off, single);
+            if constexpr (LINEAR) {
+                if (j == 0 && h + 1 < H) { lb.issue_off(boff + 16 * 256, nb_raw[1]); boff += 32 * 256; }
+            }
         }
         if (half == 1) {
             fence_proxy_async();
@@ -1155,14 +1178,17 @@ bwd_tc_kernel(LS ls, LR lr, const uint4* __restrict__ wimg, Epi ep, float* __res
                 for (int s = 0; s < Epi::NS; ++s) stat[j][s] = 0.f;
             }
         }
+        const size_t prow0 = (size_t)t * FPX + pc * 16 + part * CH;
+        float xv[MH][CH];
+#pragma unroll
+        for (int j = 0; j < MH; ++j) ep.template preload<CH>(prow0, NOUT, j * 128 + lq * 32 + lane, xv[j]);
         if (part == 0) mbar_wait_guard(bAcc + (e & 1) * 8, (uint32_t)(e >> 1) & 1);
         tc_fence_after();
-        const size_t prow0 = (size_t)t * FPX + pc * 16 + part * CH;
 #pragma unroll
         for (int j = 0; j < MH; ++j) {
             float v[CH];
             tmem_ldn<CH>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(e & 1) * ACC + j * FPX + pc * 16 + part * CH, v);
-            ep.template apply<CH>(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, stat[j]);
+            ep.template apply_pre<CH>(est[j], prow0, NOUT, j * 128 + lq * 32 + lane, v, xv[j], stat[j]);
         }
         tc_fence_before();
     };
