@@ -233,6 +233,11 @@ template <class L> struct IsPresplit<L, decltype((void)L::PRESPLIT)> { static co
 // constants instead of rebuilding the address from the tile index in every step
 template <class L, class = void> struct HasIssueOff { static constexpr bool v = false; };
 template <class L> struct HasIssueOff<L, decltype((void)&L::issue_off)> { static constexpr bool v = true; };
+// gemm_tc_body spreads a step's prefetch over the step (second row's loads after the first row's convert) for loaders that set
+// SPREAD_ROWS: measured gemm2_fwd 3.47 -> 3.20 ms per step (GELU loader), gemm1_fwd neutral, gemm2_bwd 4.82 -> 4.95 (two tensors per
+// row: its loads want the whole step in flight)
+template <class L, class = void> struct SpreadRows { static constexpr bool v = false; };
+template <class L> struct SpreadRows<L, decltype((void)L::SPREAD_ROWS)> { static constexpr bool v = L::SPREAD_ROWS; };
 template <class L, class = void> struct PosOf { struct type { size_t row; }; };
 template <class L> struct PosOf<L, decltype((void)sizeof(typename L::Pos))> { typedef typename L::Pos type; };
 template <class L>
@@ -272,6 +277,7 @@ struct TLoadNormed {           // a = x*scale + shift
 };
 template <class HT>
 struct TLoadGeluGateT {        // a = gelu(h2*scale + shift) * gate
+    static constexpr bool SPREAD_ROWS = true;
     const HT* h2; const Coef* coef; const float* gate;
     typedef Raw8<HT> Raw;
     __device__ void fill(int n, int K, float* cf) const {
@@ -709,7 +715,11 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
                 issue_row(al, pos[0], K, nkb * KBLK + pc8 * 8, raw[0]);
                 issue_row(al, pos[1], K, nkb * KBLK + pc8 * 8, raw[1]);
             } else if constexpr (HasIssueOff<ALoad>::v) {
-                al.issue_off(poff, raw[0]);                   // the second row's loads follow the first row's convert (see below)
+                al.issue_off(poff, raw[0]);
+                if constexpr (!SpreadRows<ALoad>::v) {        // else: the second row's loads follow the first row's convert (below)
+                    al.issue_off(poff + (size_t)64 * K, raw[1]);
+                    poff += nkb == KB - 1 ? (size_t)TILE_PX * K - (KB - 1) * KBLK : KBLK;
+                }
             } else {
                 al.issue(nrow0 + pr, K, nkb * KBLK + pc8 * 8, raw[0]);
                 al.issue(nrow0 + pr + 64, K, nkb * KBLK + pc8 * 8, raw[1]);
@@ -733,9 +743,9 @@ __device__ __forceinline__ void gemm_tc_body(const ALoad& al, const uint4* __res
                 const int r = pr + 64 * j;
                 const int off = r * 128 + ((pc8 ^ (r & 7)) << 4);
                 convert_store(al, cur[j], cfr, hi + off, lo + off, single);
-                if constexpr (!IsPresplit<ALoad>::v && HasIssueOff<ALoad>::v) {
-                    // the step's prefetch is spread over it: up to eight LDG.128 back to back filled the LSU queue (lg_throttle) and
-                    // held up the converts behind them (measured in wgrad_tc_kernel: 4.34 -> 4.20 ms per step)
+                if constexpr (!IsPresplit<ALoad>::v && HasIssueOff<ALoad>::v && SpreadRows<ALoad>::v) {
+                    // the step's prefetch is spread over it: the LDG.128 issued back to back filled the LSU queue (lg_throttle) and
+                    // held up the converts behind them (the same move in wgrad_tc_kernel: 4.34 -> 4.20 ms per step)
                     if (j == 0 && q + 1 < Q) {
                         al.issue_off(poff + (size_t)64 * K, raw[1]);
                         poff += (q + 1) % KB == KB - 1 ? (size_t)TILE_PX * K - (KB - 1) * KBLK : KBLK;
