@@ -210,11 +210,18 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const HT* __restrict__ h2,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < SE_STAGES - 1 && i < nst; ++i) issue(i);
     }
-    Coef k[4];
-    MeanRstd m[4];
+    // per channel PAIR, packed (f32x2): z = v * scale + shift, h_hat = v * rstd - mean * rstd, and the three accumulators -- the pass is
+    // issue-bound once the loads are off the threads (ncu: issue 70 %), so the statistics around the GELU are packed as well
+    f32x2_t sc2[2], sh2[2], rs2[2], nm2[2], s2[2], g2[2], gh2[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { k[i] = coef2[(size_t)n * C + c4 * 4 + i]; m[i] = mr2[(size_t)n * C + c4 * 4 + i]; }
-    float s[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, gh[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 2; ++i) {
+        const Coef ka = coef2[(size_t)n * C + c4 * 4 + 2 * i], kb = coef2[(size_t)n * C + c4 * 4 + 2 * i + 1];
+        const MeanRstd ma = mr2[(size_t)n * C + c4 * 4 + 2 * i], mb = mr2[(size_t)n * C + c4 * 4 + 2 * i + 1];
+        sc2[i] = pack2(ka.scale, kb.scale); sh2[i] = pack2(ka.shift, kb.shift);
+        rs2[i] = pack2(ma.rstd, mb.rstd);   nm2[i] = pack2(-ma.mean * ma.rstd, -mb.mean * mb.rstd);
+        s2[i] = g2[i] = gh2[i] = pack2(0.f, 0.f);
+    }
+    const f32x2_t one2 = pack2(1.f, 1.f);
     const bool train = gp_stats != nullptr;
     __syncthreads();                                // barrier initialisation visible to every waiter
     for (int i = 0; i < nst; ++i) {
@@ -230,24 +237,30 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const HT* __restrict__ h2,
                 const float4 v = ld4h(st + row * C);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int e = 0; e < 4; e += 2) {    // packed (f32x2) GELU + derivative: 21 issue slots per channel pair
-                    const float z0 = fmaf(vv[e], k[e].scale, k[e].shift), z1 = fmaf(vv[e + 1], k[e + 1].scale, k[e + 1].shift);
-                    float gz0, gz1, gp0, gp1;
+                for (int e = 0; e < 2; ++e) {       // packed (f32x2) GELU + derivative: 21 issue slots per channel pair
+                    const f32x2_t v2 = pack2(vv[2 * e], vv[2 * e + 1]);
+                    float z0, z1, gz0, gz1, gp0, gp1;
+                    unpack2(fma2(v2, sc2[e], sh2[e]), z0, z1);
                     if (train) {
                         gelu_pair<true, true>(z0, z1, gz0, gz1, gp0, gp1);
-                        g[e] += gp0;
-                        g[e + 1] += gp1;
-                        gh[e] = fmaf(gp0, (vv[e] - m[e].mean) * m[e].rstd, gh[e]);
-                        gh[e + 1] = fmaf(gp1, (vv[e + 1] - m[e + 1].mean) * m[e + 1].rstd, gh[e + 1]);
+                        const f32x2_t gp2 = pack2(gp0, gp1);
+                        g2[e] = fma2(gp2, one2, g2[e]);
+                        gh2[e] = fma2(gp2, fma2(v2, rs2[e], nm2[e]), gh2[e]);
                     } else {
                         gelu_val_pair(z0, z1, gz0, gz1);
                     }
-                    s[e] += gz0;
-                    s[e + 1] += gz1;
+                    s2[e] = fma2(pack2(gz0, gz1), one2, s2[e]);
                 }
             }
         }
         __syncthreads();                            // every thread is done with this slot: thread 0 may refill it next iteration
+    }
+    float s[4], g[4], gh[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        unpack2(s2[i], s[2 * i], s[2 * i + 1]);
+        unpack2(g2[i], g[2 * i], g[2 * i + 1]);
+        unpack2(gh2[i], gh[2 * i], gh[2 * i + 1]);
     }
     block_reduce_cols2<C>(make_float4(s[0], s[1], s[2], s[3]), make_float4(0, 0, 0, 0), pool_stats + (size_t)n * C * 2, red);
     if (train)
