@@ -16,6 +16,7 @@ namespace ub {
 
 constexpr int HD_MAXO = 26;
 constexpr int HD_PX = 128;
+constexpr int HD_WJ = (HD_MAXO + 3) / 4;   // outputs per warp in the weight-gradient loop of head_bwd_kernel
 
 // ------------------------------------------------------------------------------------------
 // out_conv + head forward.  Persistent CTAs over 128-pixel tiles.  The decoder tile is staged by cp.async into a
@@ -107,10 +108,10 @@ __global__ void __launch_bounds__(256, 2) head_bwd_kernel(const float* __restric
     float* dos = ws + HD_MAXO * C;             // [O][128 px]
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     for (int i = tid; i < O * C; i += 256) ws[i] = w[i];
-    float4 gw[4];
+    float4 gw[HD_WJ];
     float gbk[HD_MAXO / 2];   // bias-gradient partials: in the fill loop thread `tid` always sees outputs o = 2k + tid/128
 #pragma unroll
-    for (int j = 0; j < 4; ++j) gw[j] = make_float4(0, 0, 0, 0);
+    for (int j = 0; j < HD_WJ; ++j) gw[j] = make_float4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < HD_MAXO / 2; ++k) gbk[k] = 0.f;
     const int tiles_per_img = P / HD_PX;
@@ -142,37 +143,39 @@ __global__ void __launch_bounds__(256, 2) head_bwd_kernel(const float* __restric
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // input gradient: 4 consecutive pixels per warp iteration, lane = 4 channels: per output one broadcast LDS.128 of the 4
-        // `do` values and one LDS.128 of the weights feed 16 FMAs (was 2 LDS per 4 FMAs: mio_throttle + short_scoreboard 41 %)
-        for (int px0 = warp * 4; px0 < HD_PX; px0 += 32) {
-            float4 acc[4];
+        // input gradient: 8 consecutive pixels per warp iteration, lane = 4 channels: per output two broadcast LDS.128 of the 8
+        // `do` values and one LDS.128 of the weights feed 32 FMAs (4 pixels: 2 LDS per 16 FMAs, the shared-memory pipe as busy
+        // as the FMA pipe; 1 pixel: 2 LDS per 4 FMAs, mio_throttle + short_scoreboard 41 %)
+        for (int px0 = warp * 8; px0 < HD_PX; px0 += 64) {
+            float4 acc[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = make_float4(0, 0, 0, 0);
+            for (int i = 0; i < 8; ++i) acc[i] = make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int o = 0; o < HD_MAXO; ++o) {
                 if (o < O) {
-                    const float4 d4 = ld4(dos + o * HD_PX + px0);
+                    const float4 d4 = ld4(dos + o * HD_PX + px0), e4 = ld4(dos + o * HD_PX + px0 + 4);
                     const float4 wv = ld4(ws + o * C + lane * 4);
-                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                    const float dd[8] = {d4.x, d4.y, d4.z, d4.w, e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         acc[i].x = fmaf(dd[i], wv.x, acc[i].x); acc[i].y = fmaf(dd[i], wv.y, acc[i].y);
                         acc[i].z = fmaf(dd[i], wv.z, acc[i].z); acc[i].w = fmaf(dd[i], wv.w, acc[i].w);
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) st4(ddec + (row0 + px0 + i) * C + lane * 4, acc[i]);
+            for (int i = 0; i < 8; ++i) st4(ddec + (row0 + px0 + i) * C + lane * 4, acc[i]);
         }
-        // weight gradient: warp owns outputs warp + 8j; 4 pixels per iteration
+        // weight gradient: warp owns outputs (warp % 4) + 4j, j < 7, over one HALF of the tile's pixels (warp / 4): a warp reads half of
+        // the staged decoder tile for 7 outputs (all of it for 4 outputs before: the tile reads were 80 % of this loop's LDS traffic)
 #pragma unroll 2
-        for (int px0 = 0; px0 < HD_PX; px0 += 4) {
+        for (int px0 = (warp >> 2) * (HD_PX / 2); px0 < (warp >> 2) * (HD_PX / 2) + HD_PX / 2; px0 += 4) {
             float4 a[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = ld4(dect + (px0 + i) * C + lane * 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int o = warp + 8 * j;
+            for (int j = 0; j < HD_WJ; ++j) {
+                const int o = (warp & 3) + 4 * j;
                 if (o < O) {
                     const float4 d4 = ld4(dos + o * HD_PX + px0);
                     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -193,8 +196,8 @@ __global__ void __launch_bounds__(256, 2) head_bwd_kernel(const float* __restric
         if (lane == 0 && o < O) atomicAdd(&db[o], t);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int o = warp + 8 * j;
+    for (int j = 0; j < HD_WJ; ++j) {
+        const int o = (warp & 3) + 4 * j;
         if (o < O) {
             atomicAdd(&dw[o * C + lane * 4 + 0], gw[j].x); atomicAdd(&dw[o * C + lane * 4 + 1], gw[j].y);
             atomicAdd(&dw[o * C + lane * 4 + 2], gw[j].z); atomicAdd(&dw[o * C + lane * 4 + 3], gw[j].w);

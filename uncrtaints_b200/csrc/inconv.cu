@@ -16,6 +16,9 @@ constexpr int IC_MAXC = 16;   // max input channels (13 optical + 2 SAR = 15)
 constexpr int IC_PX = 256;    // pixels staged per iteration (one per thread and input channel; next tile prefetched in registers)
 constexpr int IC_GROUPS = IC_PX / 32;   // 4-pixel groups per warp and tile
 
+// (Measured and rejected: the lane's 4 x 16 weights in registers as f32x2 pairs with the input tile staged duplicated (x, x), 2 LDS + 8
+// FFMA2 per input channel and pixel group instead of 2 LDS + 16 FFMA -- 128 registers, 2 CTAs per SM: 0.69 -> 0.77 ms at N=48; the pass
+// lives on resident warps hiding the store stream, not on its instruction count.)
 // x0 = relu(gn(W x + b)) written pixel-major, stats += column (sum, sumsq) of x0
 __global__ void __launch_bounds__(256) inconv_apply_kernel(const float* __restrict__ x /* [N][Cin][P] */, const float* __restrict__ w /* [128][Cin] */,
                                                             const float* __restrict__ bias, const Coef* __restrict__ coef,
@@ -263,17 +266,22 @@ __global__ void inconv_bwd_stats_from_gram_kernel(const double* __restrict__ gac
 }
 
 // dW[o][ci] += sum_n a G + b (W[o].S2[:,ci] + bias S1[ci]) + c S1[ci];  db[o] += sum_n a g0 + b (W[o].S1 + P bias) + c P
-// grid 128 (o), 32 threads: lane ci < Cin -> dW column, lane 31 -> db
-__global__ void inconv_bwd_finish_kernel(const double* __restrict__ gacc, const double* __restrict__ mom, const float* __restrict__ w,
-                                         const float* __restrict__ bias, const BCoef* __restrict__ bc, float* dw, float* db, int N,
-                                         int Cin, double P) {
-    const int o = blockIdx.x, lane = threadIdx.x;
+// grid 128 (o), 8 warps: lane ci < Cin -> dW column, lane 31 -> db; warp w takes frames w, w+8, ... (a frame is a chain of ~17
+// dependent fp64 operations behind three dependent loads: one warp walking all N frames took 0.18 ms at N=48), fp64 partials
+// are combined through shared memory in a fixed order.
+constexpr int IF_WARPS = 8;
+__global__ void __launch_bounds__(32 * IF_WARPS) inconv_bwd_finish_kernel(const double* __restrict__ gacc, const double* __restrict__ mom,
+                                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                                         const BCoef* __restrict__ bc, float* dw, float* db, int N,
+                                                                         int Cin, double P) {
+    __shared__ double part[IF_WARPS][32];
+    const int o = blockIdx.x, lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     double wv[IC_MAXC];
     for (int ci = 0; ci < IC_MAXC; ++ci) wv[ci] = ci < Cin ? (double)w[o * Cin + ci] : 0.0;
     const double b0 = bias[o];
     double acc = 0.0;
     if (lane < Cin) {
-        for (int n = 0; n < N; ++n) {
+        for (int n = warp; n < N; n += IF_WARPS) {
             const BCoef k = bc[(size_t)n * UB_WIDTH + o];
             const double* S1 = mom + (size_t)n * IM_STRIDE;
             const double* S2 = S1 + IC_MAXC;
@@ -281,16 +289,23 @@ __global__ void inconv_bwd_finish_kernel(const double* __restrict__ gacc, const 
             for (int cj = 0; cj < Cin; ++cj) c0x += wv[cj] * S2[cj * IC_MAXC + lane];
             acc += (double)k.a * gacc[((size_t)n * UB_WIDTH + o) * IG_STRIDE + lane] + (double)k.b * c0x + (double)k.c * S1[lane];
         }
-        atomicAdd(&dw[o * Cin + lane], (float)acc);
     } else if (lane == 31) {
-        for (int n = 0; n < N; ++n) {
+        for (int n = warp; n < N; n += IF_WARPS) {
             const BCoef k = bc[(size_t)n * UB_WIDTH + o];
             const double* S1 = mom + (size_t)n * IM_STRIDE;
             double lin = 0.0;
             for (int cj = 0; cj < Cin; ++cj) lin += wv[cj] * S1[cj];
             acc += (double)k.a * gacc[((size_t)n * UB_WIDTH + o) * IG_STRIDE + IC_MAXC] + (double)k.b * (lin + P * b0) + (double)k.c * P;
         }
-        atomicAdd(&db[o], (float)acc);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < IF_WARPS; ++r) t += part[r][lane];
+        if (lane < Cin) atomicAdd(&dw[o * Cin + lane], (float)t);
+        else if (lane == 31) atomicAdd(&db[o], (float)t);
     }
 }
 
@@ -334,7 +349,7 @@ int launch_inconv_bwd_gram(const float* x, const float* x0, const float* dx0, co
 int launch_inconv_bwd_finish(const double* gacc, const double* mom, const float* w, const float* b, const BCoef* bc, float* dw,
                              float* db, int N, int Cin, int P, cudaStream_t st) {
     if (Cin > IC_MAXC) return UB_ERR_ARG;
-    inconv_bwd_finish_kernel<<<UB_WIDTH, 32, 0, st>>>(gacc, mom, w, b, bc, dw, db, N, Cin, (double)P);
+    inconv_bwd_finish_kernel<<<UB_WIDTH, 32 * IF_WARPS, 0, st>>>(gacc, mom, w, b, bc, dw, db, N, Cin, (double)P);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }

@@ -704,9 +704,72 @@ __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __re
     dattn[cell] = acc;
 }
 
+// The same adjoint with coalesced reads (W = 32 * SX): a warp owns one low-resolution row Y of one (head, sample, frame) image,
+// lane = cell X.  Per image row of the footprint every lane reads its own SX pixels (the warp reads the row contiguously) and
+// forms three dot products: into its own cell and into the cells left / right of it (the footprint of a cell reaches SX/2+1
+// pixels into each neighbour); the neighbour parts are exchanged by two shuffles at the very end.  The weight of every pixel
+// comes from the same bilinear_tap as the forward pass, so the clamped borders need no special case.
+// (The cell-per-thread form above reads with a 32-byte lane stride: 8 L1 wavefronts per load, 0.24 ms at B=16, T=3, 256x256.)
+template <int SX>
+__global__ void __launch_bounds__(256) upsample_adjoint_rows_kernel(const float* __restrict__ dwup, float* __restrict__ dattn,
+                                                                     int H, int total_rows) {
+    constexpr int W = UB_LOW * SX;
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32), X = threadIdx.x % 32;
+    if (row >= total_rows) return;
+    const int Y = row % UB_LOW;
+    const size_t img = (size_t)(row / UB_LOW);
+    const int sy = H / UB_LOW;
+    const float inv_sy = (float)UB_LOW / (float)H, inv_sx = 1.f / (float)SX;
+    float wo[SX], wl[SX], wr[SX];                 // weight of own pixel i in cell X, X-1, X+1
+#pragma unroll
+    for (int i = 0; i < SX; ++i) {
+        int x0, x1; float lx;
+        bilinear_tap(X * SX + i, inv_sx, UB_LOW, x0, x1, lx);
+        wo[i] = (x0 == X ? 1.f - lx : 0.f) + (x1 == X ? lx : 0.f);
+        wl[i] = (x0 == X - 1 ? 1.f - lx : 0.f) + (x1 == X - 1 ? lx : 0.f);
+        wr[i] = (x0 == X + 1 ? 1.f - lx : 0.f) + (x1 == X + 1 ? lx : 0.f);
+    }
+    const int ya = max(0, (Y - 1) * sy + sy / 2 - 1), yb = min(H - 1, (Y + 1) * sy + sy / 2);
+    const float* src = dwup + img * H * W + X * SX;
+    float ao = 0.f, al = 0.f, ar = 0.f;
+    for (int y = ya; y <= yb; ++y) {
+        int y0, y1; float ly;
+        bilinear_tap(y, inv_sy, UB_LOW, y0, y1, ly);
+        const float wy = (y0 == Y ? 1.f - ly : 0.f) + (y1 == Y ? ly : 0.f);
+        if (wy == 0.f) continue;
+        float v[SX];
+        if constexpr (SX % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < SX; i += 4) {
+                const float4 t = ld4(src + (size_t)y * W + i);
+                v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SX; ++i) v[i] = src[(size_t)y * W + i];
+        }
+        float ro = 0.f, rl = 0.f, rr = 0.f;
+#pragma unroll
+        for (int i = 0; i < SX; ++i) { ro = fmaf(wo[i], v[i], ro); rl = fmaf(wl[i], v[i], rl); rr = fmaf(wr[i], v[i], rr); }
+        ao = fmaf(wy, ro, ao); al = fmaf(wy, rl, al); ar = fmaf(wy, rr, ar);
+    }
+    const float from_right = __shfl_down_sync(0xffffffffu, al, 1);      // lane X+1's part for its left neighbour = this cell
+    const float from_left = __shfl_up_sync(0xffffffffu, ar, 1);         // lane X-1's part for its right neighbour = this cell
+    dattn[(size_t)row * UB_LOW + X] = ao + (X < UB_LOW - 1 ? from_right : 0.f) + (X > 0 ? from_left : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+static void launch_upsample_adjoint(const float* dwup, float* dattn, int H, int W, int images, cudaStream_t st) {
+    const int rows = images * UB_LOW;
+    if (W == UB_LOW * 8) upsample_adjoint_rows_kernel<8><<<(rows + 7) / 8, 256, 0, st>>>(dwup, dattn, H, rows);
+    else if (W == UB_LOW * 4) upsample_adjoint_rows_kernel<4><<<(rows + 7) / 8, 256, 0, st>>>(dwup, dattn, H, rows);
+    else {
+        const int cells = rows * UB_LOW;
+        upsample_adjoint_kernel<<<(cells + 255) / 256, 256, 0, st>>>(dwup, dattn, H, W, cells);
+    }
+}
 int launch_maxpool_fwd(const float* x, float* pooled, int* idx, int N, int H, int W, cudaStream_t st) {
     if (H % UB_LOW || W % UB_LOW) return UB_ERR_ARG;
     maxpool_fwd_kernel<<<dim3(UB_LOW * UB_LOW, N), 128, 0, st>>>(x, pooled, idx, H, W);
@@ -796,8 +859,7 @@ int launch_aggregate_bwd(const float* attn, const int* notpad, const unsigned ch
         UB_DISPATCH_T(T, (aggregate_bwd_kernel<TT><<<dim3(H, B), 256, 0, st>>>(a, x, dagg, denc, dwup)));
         UB_CHECK_LAUNCH();
     }
-    const int cells = UB_HEADS * B * T * UB_LOW * UB_LOW;
-    upsample_adjoint_kernel<<<(cells + 255) / 256, 256, 0, st>>>(dwup, dattn, H, W, cells);
+    launch_upsample_adjoint(dwup, dattn, H, W, UB_HEADS * B * T, st);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
