@@ -23,7 +23,7 @@ int launch_se_pool(const void* h2, const Coef* coef2, const MeanRstd* mr2, doubl
                    int P, int hbf, cudaStream_t st);
 int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, double* bstats, int N, int P, cudaStream_t st);
 int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
-                        int relu_mask, cudaStream_t st);
+                        int relu_mask, const float* y_below, const MeanRstd* mr_below, double* bstats_below, cudaStream_t st);
 
 // norm.cu: residual blocks (conv3x3 -> norm -> ReLU layers)
 int launch_residual_relu_fwd(const float* x, const float* c3, const Coef* coef3, float* out, double* out_stats, int N, int P, cudaStream_t st);

@@ -386,12 +386,15 @@ static int mbconv_forward_eval_bn(const BlockCtx& c, const float* x, double* nex
 }
 
 // dout: gradient w.r.t. the block output; dx: gradient w.r.t. the block input (may not alias dout)
+// stats_ready: the Norm3-backward statistics of (dout, y) were gathered by the residual pass of the block above (which produced dout);
+// below: the block that produced x -- dx is its output gradient, and this block's residual pass gathers ITS Norm3-backward statistics.
 static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout, float* dx, float* dn0, void* du, void* dz1,
-                           float* partial) {
+                           float* partial, bool stats_ready = false, const BlockWs* below = nullptr) {
     const BlockWs& w = *c.w;
     const int P = c.H * c.W;
     void* ws = c.ws;
-    UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
+    if (!stats_ready)
+        UB_PROF(KID_NORM_BWD_STATS, c.st, launch_norm_bwd_stats(dout, at<float>(ws, w.y), at<MeanRstd>(ws, w.mr3), at<double>(ws, w.bstats3), c.N, P, c.st));
     UB_TRY(finalize_bwd(c, w.bstats3, UB200_B_N3_W, w.mr3, w.bc3, UB_WIDTH));
     const bool tcb = (c.backend & 3) == 3;                      // 3 = tcgen05 product path, 0 = fp32 CUDA-core comparator
     if ((c.backend & 3) != 0 && !tcb) return UB_ERR_ARG;
@@ -430,7 +433,9 @@ static int mbconv_backward(const BlockCtx& c, const float* x, const float* dout,
                            gf(c.g, UB200_B_W1), c.N, P, c.st));
     }
     UB_TRY(finalize_bwd(c, w.bstats0, UB200_B_N0_W, w.mr0, w.bc0, UB_WIDTH));
-    UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.relu_mask_dx, c.st));
+    UB_PROF(KID_RESIDUAL_BWD, c.st, launch_residual_bwd(dout, dn0, x, at<BCoef>(ws, w.bc0), dx, c.N, P, c.relu_mask_dx,
+                               below ? at<float>(ws, below->y) : nullptr, below ? at<MeanRstd>(ws, below->mr3) : nullptr,
+                               below ? at<double>(ws, below->bstats3) : nullptr, c.st));
     return UB_OK;
 }
 
@@ -832,7 +837,9 @@ int ub200_backward_v(const ub200_desc* d, const float* input, const void* const*
             UB_TRY(residual_backward(d, L, i, params, grads, x, gA, gB, static_cast<float*>(du), static_cast<float*>(du) + (size_t)L.Nmax * P * UB_WIDTH,
                                      partial, ws, st));
         else
-        UB_TRY(mbconv_backward(c, x, gA, gB, dn0, du, dz1, partial));
+        // decoder blocks i >= 2: dx is the output gradient of block i-1 (same frame count), whose statistics pass rides in this block's
+        // residual pass
+        UB_TRY(mbconv_backward(c, x, gA, gB, dn0, du, dz1, partial, /*stats_ready=*/i < L.nblk - 1, i >= 2 ? &L.blk[i - 1] : nullptr));
         float* t = gA; gA = gB; gB = t;
     }
     if (d->is_mono) {         // gA = dEnc directly: make it the encoder block's incoming gradient

@@ -301,16 +301,28 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------
 // relu_mask != 0 (encoder block only: its input x is the ReLU output of in_conv): dx is also multiplied by [x > 0], i.e. the
 // ReLU backward of in_conv is applied here, where x is loaded anyway, and the in_conv gram pass need not read x0 again.
-__global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dn0,
+// BELOW: dx is the output gradient of the block below (the producer of x), whose backward starts with the statistics pass B5a over
+// (dx, y_below).  Gathering them here costs one more read stream (y_below, A) instead of a separate pass over 2 A.
+template <bool BELOW>
+__global__ void __launch_bounds__(256, BELOW ? 4 : 0) residual_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dn0,
                                                             const float* __restrict__ x, const BCoef* __restrict__ bc0,
-                                                            float* __restrict__ dx, int P, int chunk, int relu_mask) {
+                                                            float* __restrict__ dx, int P, int chunk, int relu_mask,
+                                                            const float* __restrict__ y_below, const MeanRstd* __restrict__ mr_below,
+                                                            double* bstats_below) {
     constexpr int C = UB_WIDTH, Q = C / 4, ROWS = 256 / Q;
+    __shared__ __align__(16) float smem[BELOW ? 2 * ROWS * C : 4];
     const int n = blockIdx.y, c4 = threadIdx.x % Q, r = threadIdx.x / Q;
     const BCoef k0 = bc0[(size_t)n * C + c4 * 4 + 0], k1 = bc0[(size_t)n * C + c4 * 4 + 1],
                 k2 = bc0[(size_t)n * C + c4 * 4 + 2], k3 = bc0[(size_t)n * C + c4 * 4 + 3];
+    MeanRstd m0 = {}, m1 = {}, m2 = {}, m3 = {};
+    if constexpr (BELOW) {
+        m0 = mr_below[(size_t)n * C + c4 * 4 + 0]; m1 = mr_below[(size_t)n * C + c4 * 4 + 1];
+        m2 = mr_below[(size_t)n * C + c4 * 4 + 2]; m3 = mr_below[(size_t)n * C + c4 * 4 + 3];
+    }
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, P);
     const size_t base = (size_t)n * P * C + c4 * 4;
-    for (int p = p0 + r; p < p1; p += ROWS) {
+    auto row = [&](int p) {
         const float4 g = ld4_stream(dout + base + (size_t)p * C);
         const float4 d = ld4_stream(dn0 + base + (size_t)p * C);
         const float4 xv = ld4_stream(x + base + (size_t)p * C);
@@ -324,7 +336,22 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
             o.z = xv.z > 0.f ? o.z : 0.f; o.w = xv.w > 0.f ? o.w : 0.f;
         }
         st4(dx + base + (size_t)p * C, o);
+        if constexpr (BELOW) {
+            const float4 w = ld4_stream(y_below + base + (size_t)p * C);
+            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+            q.x += o.x * (w.x - m0.mean) * m0.rstd;
+            q.y += o.y * (w.y - m1.mean) * m1.rstd;
+            q.z += o.z * (w.z - m2.mean) * m2.rstd;
+            q.w += o.w * (w.w - m3.mean) * m3.rstd;
+        }
+    };
+    if constexpr (BELOW) {
+#pragma unroll 1                                    // 64 registers (4 CTAs per SM) without spills; the compiler's 4x unrolling needs 70+
+        for (int p = p0 + r; p < p1; p += ROWS) row(p);
+    } else {
+        for (int p = p0 + r; p < p1; p += ROWS) row(p);
     }
+    if constexpr (BELOW) block_reduce_cols2<C>(s, q, bstats_below + (size_t)n * C * 2, smem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -521,6 +548,9 @@ __global__ void __launch_bounds__(128) conv_fold_kernel(const char* __restrict__
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+#ifndef UB_RB_MAXROWS
+#define UB_RB_MAXROWS 1024      // pixels per CTA of the statistics-gathering residual backward pass (whole waves, see launch_residual_bwd)
+#endif
 static inline int chunk_for(int P) { return P >= 4096 ? 1024 : (P >= 1024 ? 256 : 64); }
 
 int launch_norm_finalize(const double* stats, const float* gamma, const float* beta, float* rm, float* rv, Coef* coef,
@@ -591,9 +621,30 @@ int launch_norm_bwd_stats(const float* dy, const float* v, const MeanRstd* mr, d
     return UB_OK;
 }
 int launch_residual_bwd(const float* dout, const float* dn0, const float* x, const BCoef* bc0, float* dx, int N, int P,
-                        int relu_mask, cudaStream_t st) {
-    const int chunk = chunk_for(P);
-    residual_bwd_kernel<<<dim3((P + chunk - 1) / chunk, N), 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk, relu_mask);
+                        int relu_mask, const float* y_below, const MeanRstd* mr_below, double* bstats_below, cudaStream_t st) {
+    int chunk = chunk_for(P);
+    if (y_below && P >= 4096) {
+        // the statistics variant holds fewer CTAs per SM (registers, reduction scratch): 1024 CTAs on 3 x 148 slots ran three waves
+        // for 2.3 waves of work (0.8 of the HBM roof) -- size the grid to whole waves of what is resident, <= UB_RB_MAXROWS pixels per CTA (1024: 3.165 ms per step, 2048: 3.18)
+        static int occ_cache[64] = {0};
+        int dev = 0, occ = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return UB_ERR_CUDA;
+        if (dev >= 0 && dev < 64 && occ_cache[dev] > 0) occ = occ_cache[dev];
+        else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, residual_bwd_kernel<true>, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+            if (dev >= 0 && dev < 64) occ_cache[dev] = occ;
+        }
+        const long long slots = (long long)device_sm_count() * occ, rows = (long long)N * P;
+        int w = 1;
+        while (rows / (slots * w) > UB_RB_MAXROWS) ++w;
+        long long g = slots * w / N;
+        if (g < 1) g = 1;
+        if (g > P / 8) g = P / 8;
+        chunk = (int)(((P + g - 1) / g + 7) / 8 * 8);
+    }
+    const dim3 grid((P + chunk - 1) / chunk, N);
+    if (y_below) residual_bwd_kernel<true><<<grid, 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk, relu_mask, y_below, mr_below, bstats_below);
+    else residual_bwd_kernel<false><<<grid, 256, 0, st>>>(dout, dn0, x, bc0, dx, P, chunk, relu_mask, nullptr, nullptr, nullptr);
     UB_CHECK_LAUNCH();
     return UB_OK;
 }
