@@ -161,6 +161,17 @@ def algorithmic_bytes(kernel, frames, P, hid_bytes=4):
     return (a * 128 * P * 4 + h * 256 * P * hid_bytes) * frames
 
 
+def class_bytes(kernel, B, T, n_dec, P, hid_bytes=4):
+    """Algorithmic bytes of one STEP of a block-kernel class: one encoder launch over B*T frames + n_dec decoder launches over B
+    frames.  The Norm3-backward statistics pass runs on its own only for the encoder block and the last decoder block; for the other
+    decoder blocks it rides in the residual pass of the block above, which reads one more tensor (A) there."""
+    frames = B * T + n_dec * B
+    if kernel == "norm_bwd_stats":
+        return algorithmic_bytes(kernel, B * T + (B if n_dec else 0), P, hid_bytes)
+    extra = 128 * P * 4 * max(n_dec - 1, 0) * B if kernel == "residual_bwd" else 0
+    return algorithmic_bytes(kernel, frames, P, hid_bytes) + extra
+
+
 def survey_bytes_per_sample(T, covdim, P, n_dec=5, hid_bytes=4):
     """SURVEY.md §8(d) byte model ("one HBM materialisation per normalisation barrier"): 12.06 GB / sample at T=3, diag, fp32."""
     A, Hh = 128 * P * 4, 256 * P * hid_bytes
@@ -424,12 +435,12 @@ def main():
     frames_step = args.batch * args.t + n_dec * args.batch
     P = args.hw * args.hw
     hb = 2 if ((args.backend or 0) & 32) else 4
-    bytes_total = algorithmic_bytes(top, frames_step * args.steps, P, hb)
+    bytes_total = class_bytes(top, args.batch, args.t, n_dec, P, hb) * args.steps
     achieved = bytes_total / (tms.value / 1e3) / 1e9 if tms.value > 0 else 0.0
     tpf, tsrc = ncu_traffic_per_frame(top)
     traffic = int(tpf * frames_step * args.steps / max(tn.value, 1)) if tpf else None      # per launch, like algorithmic_bytes_per_launch
     # per-kernel fraction of the HBM roof from the profiled warm-up step, and what the classed kernels leave unattributed
-    kernel_fracs = {k: round(algorithmic_bytes(k, frames_step, P, hb) / (v["ms"] / 1e3) / 1e9 / peak, 3)
+    kernel_fracs = {k: round(class_bytes(k, args.batch, args.t, n_dec, P, hb) / (v["ms"] / 1e3) / 1e9 / peak, 3)
                     for k, v in breakdown.items() if algorithmic_bytes(k, 1, 1) > 0 and v["ms"] > 0}
     classed_ms = sum(v["ms"] for v in breakdown.values())
     step_bytes = survey_bytes_per_sample(args.t, cov, P, n_dec, hb) * args.batch

@@ -90,7 +90,7 @@ if len(lines) > 6:
            "gemm_tc_kernel<256, 128, TLoadGeluGate": Hh + A, "gemm_tc_kernel<128, 256, TLoadNormBwd": 2 * A + 2 * Hh,
            "gemm_tc_kernel<256, 128, TLoadNormBwd": 2 * Hh + 2 * A, "bwd_tc_kernel<1": 2 * Hh + 2 * A, "bwd_tc_kernel<2": 2 * Hh + 2 * A,
            "wgrad_tc_kernel<TLoadNormBwd, TLoadGeluGate>": 2 * A + Hh,
-           "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>": A + 2 * Hh, "se_pool_kernel": Hh, "residual_bwd_kernel": 4 * A,
+           "wgrad_tc_kernel<TLoadNormed, TLoadNormBwd>": A + 2 * Hh, "se_pool_kernel": Hh, "residual_bwd_kernel<1>": 5 * A, "residual_bwd_kernel": 4 * A,
            "residual_fwd_kernel": 3 * A, "norm_bwd_stats_kernel": 2 * A}
     per_frame = {}
     for name, ls in traffic.items():
