@@ -301,6 +301,7 @@ def _mbconv_block_vs_oracle(golden_weights, groups, training, backend, split, sh
     (16, 3, 64, 64, "diag", True, False, 3),      # BASELINE config #2's batch and sequence length (BatchNorm over 16 samples)
     (1, 12, 64, 64, "diag", True, True, 3),       # T > 8: run-time-T temporal kernels (the dataset yields up to 30 time points)
     (2, 9, 64, 64, "iso", False, False, 3),
+    (1, 2, 64, 128, "diag", True, True, 3),       # W = 128: the x4 instantiation of the row-form upsampling adjoint
 ])
 def test_model_vs_oracle(golden_weights, B, T, H, W, covmode, train, pad, backend):
     import uncrtaints_b200 as ub
