@@ -224,3 +224,22 @@ def test_prepare_data_multi_matches_the_reference(tmp_path):
         for name, a, b in zip(("x", "y", "in_m", "dates"), got, want):
             assert a.shape == b.shape, (name, a.shape, b.shape)
             assert torch.equal(a.float(), b.float()), name
+
+
+def test_bench_byte_model_of_the_block_kernel_classes():
+    """bench.py's roofline numerators: per-class bytes of one step add up to the pass structure the library runs --
+    the Norm3-backward statistics pass on its own for the encoder block and the last decoder block only, one more read stream (A)
+    in the residual pass of the four decoder blocks above a fused one."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    B, T, n_dec, P = 16, 3, 5, 256 * 256
+    A, Hh = 128 * P * 4, 256 * P * 4
+    frames = B * T + n_dec * B
+    assert bench.class_bytes("dwconv_bwd", B, T, n_dec, P) == 4 * Hh * frames
+    assert bench.class_bytes("norm_bwd_stats", B, T, n_dec, P) == 2 * A * (B * T + B)
+    assert bench.class_bytes("residual_bwd", B, T, n_dec, P) == 4 * A * frames + A * (n_dec - 1) * B
+    assert bench.class_bytes("dwconv_bwd", B, T, n_dec, P, hid_bytes=2) == 2 * Hh * frames
+    # the whole-step model of SURVEY.md §8(d): 12.06 GB per sample at T=3, diag, fp32
+    assert abs(bench.survey_bytes_per_sample(3, 13, P) / 1e9 - 12.06) < 0.01
